@@ -1,0 +1,310 @@
+#!/usr/bin/env python3
+"""bench.py -- reads/s through the Poisson-binomial filter (BASELINE.json metric).
+
+Own arm:  python bench.py [--gpus N] [--steps K] [--warmup W]
+  One rank per GPU (torchrun for N > 1).  Workload = BASELINE config C2: 10 M synthetic 253-bp V4
+  contigs per GPU (MiSeq profile, weak scaling), --error_calc poisson_binomial, alpha 0.005,
+  uncert 0.01, treat_as_errors.  A step = one pass of the filter over the GPU's 10 M reads.
+    value   reads/s, whole job, inputs resident in HBM (moira_filter_device, decision mode)
+    e2e     the same through moira_filter_batch with pinned HOST buffers: H2D of the slab, kernels,
+            D2H of ee/Ns/flags/counters inside the timed region
+    roofline       dominant kernel pb_tpr<K=4> against the FP64 (non-fused DMUL/DADD) issue peak
+                   measured live with moira_fp64_peak, plus the HBM view
+    cpu_baseline   the unmodified reference C core (oracle/_ref) on this box's host cores, N = 1 only
+Reference arm:  python bench.py --impl reference ...   times oracle/_ref on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+READ_LEN = 253
+STRIDE = 256
+ALPHA = 0.005
+UNCERT = 0.01
+METRIC = "reads/s Poisson-binomial filter (253-bp)"
+WORKLOAD = "C2: 10M synthetic 253-bp V4 contigs per GPU, MiSeq profile, poisson_binomial, alpha 0.005, uncert 0.01"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def _cpu_sample(n_reads, seed):
+    from moira_b200 import synth
+    return synth.generate("v4", n_reads, seed)
+
+
+def _time_reference(slab, off, ln, threads):
+    """reads/s of the reference's own C core (bernoullimodule.c test()) over a packed sample."""
+    from oracle import py_oracle as po
+    t0 = time.perf_counter()
+    if po.have_ref():
+        po.ref_batch(slab, off, ln, ALPHA, n_threads=threads)
+        kind = "reference"
+    else:
+        po.pb_batch(slab, off, ln, ALPHA, faithful=True)
+        kind, threads = "port", 1
+    dt = time.perf_counter() - t0
+    return len(ln) / dt, dt, kind, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    probe = _cpu_sample(20000, 20160105 + 1)
+    rate, _, kind, threads = _time_reference(*probe, threads=cores)
+    per_step = int(min(2_000_000, max(20000, rate * 4.0)))          # ~4 s of CPU work per step
+    slab, off, ln = _cpu_sample(per_step, 20160105 + 1)
+    for _ in range(args.warmup):
+        _time_reference(slab[: 20000 * STRIDE], off[:20000], ln[:20000], threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _time_reference(slab, off, ln, threads)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = "%d reads per step x %d steps of the C2 workload (same generator, seed 20160106)" % (per_step, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reads_per_step": per_step, "read_len": READ_LEN, "error_calc": "poisson_binomial"},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, torch_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.ok = [], 0, False, False
+        self.max_mhz = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as exc:  # pragma: no cover
+            self.err = repr(exc)
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.reasons |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def summary(self):
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        reasons = [v for k, v in names.items() if self.reasons & k and v != "gpu_idle"]
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import moira_b200
+    from moira_b200 import FilterParams, synth
+    from moira_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.reads
+    ctx = moira_b200.Context(local_rank)
+
+    # ---- synthetic input, resident in HBM (2.56 GB per GPU >> 126 MB L2: no flush needed) ----
+    slab = synth.generate_v4_device(n, 20160105 + 1 + 1000 * rank, dev)
+    ee = torch.empty(n, dtype=torch.float64, device=dev)
+    ns = torch.empty(n, dtype=torch.int32, device=dev)
+    fl = torch.empty(n, dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    p_dec = FilterParams(alpha=ALPHA, uncert=UNCERT, exact_ee=False)
+    p_exact = FilterParams(alpha=ALPHA, uncert=UNCERT, exact_ee=True)
+
+    def step(params):
+        cnt.zero_()
+        ctx.filter_device(slab.data_ptr(), None, None, STRIDE, READ_LEN, n, params, ee.data_ptr(), ns.data_ptr(),
+                          fl.data_ptr(), cnt.data_ptr(), stream)
+        if world > 1:   # the path's only collective: good/bad counts + error histogram
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(params, steps, timing=False):
+        barrier()
+        if timing:
+            ctx.set_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        e0.record()
+        for _ in range(steps):
+            step(params)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        kms, kname = (ctx.last_kernel_ms() if timing else (0.0, ""))
+        if timing:
+            ctx.set_timing(False)
+        return ms, launches, kms, kname
+
+    for _ in range(max(3, args.warmup)):
+        step(p_dec)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms, launches, kms, kname = timed(p_dec, args.steps, timing=True)
+    sampler.stop_flag = True
+    sampler.join()
+    value = world * n * args.steps / (ms * 1e-3)
+    counters = cnt.cpu().numpy().astype(np.int64)
+    accepted_frac = float(counters[L.CNT_ACCEPTED]) / max(1, int(counters[L.CNT_READS]))
+
+    # exact-ee mode (what --collapse needs), same inputs
+    for _ in range(2):
+        step(p_exact)
+    ms_x, _, _, _ = timed(p_exact, max(3, args.steps // 4))
+    value_exact = world * n * max(3, args.steps // 4) / (ms_x * 1e-3)
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------
+    k_dec = synth.decision_k(READ_LEN, UNCERT)
+    kernel_ms = kms / max(1, min(args.steps, 64))
+    w_fp64, w_hbm = synth.w_fp64(READ_LEN, k_dec), synth.w_hbm(READ_LEN)
+    peak_ops, _ = ctx.fp64_peak(40000)
+    achieved = n * w_fp64 / (kernel_ms * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = FALLBACK_HBM_GBS, "fallback"
+    if os.path.exists(peaks_path):
+        try:
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    hbm_achieved = n * w_hbm / (kernel_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "fp64", "kernel": kname, "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "TFLOP/s",
+        "frac": achieved / peak_ops, "traffic": None,
+        "peak_source": "moira_fp64_peak: register-resident non-fused DMUL/DADD probe, measured live in this run",
+        "flop_per_read": w_fp64, "kernel_ms": kernel_ms,
+        "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                "bytes_per_read": w_hbm, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)" if hbm_src == "measured" else "fallback 6650 GB/s"},
+    }
+
+    # ---- end to end through the host-buffer C-ABI call ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_slab = moira_b200.PinnedBuffer(n * STRIDE)
+        torch.cuda.synchronize()
+        h_t = torch.from_numpy(h_slab.u8)
+        h_t.copy_(slab.view(-1))
+        h_out = moira_b200.PinnedBuffer(n * 13 + 4096)
+        out = moira_b200.FilterResult(h_out.view(np.float64, n), h_out.view(np.int32, n, n * 8),
+                                      h_out.view(np.uint8, n, n * 12), np.zeros(L.N_COUNTERS, np.uint64))
+        h_meta = moira_b200.PinnedBuffer(n * 12)
+        off = h_meta.view(np.uint64, n)
+        off[:] = np.arange(n, dtype=np.uint64) * STRIDE
+        lens = h_meta.view(np.uint32, n, n * 8)
+        lens[:] = READ_LEN
+        e_steps = max(2, min(5, args.steps))
+        ctx.filter_batch(h_slab.u8, off, lens, p_dec, out)         # warm-up (allocates device buffers)
+        ctx.filter_batch(h_slab.u8, off, lens, p_dec, out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            ctx.filter_batch(h_slab.u8, off, lens, p_dec, out)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert int(out.counters[L.CNT_READS]) == n, "e2e pass did not process every read"
+        e2e = {"value": world * n * e_steps / dt, "unit": "reads/s", "h2d_bytes_per_step": n * STRIDE + n * 12,
+               "d2h_bytes_per_step": n * 13 + L.N_COUNTERS * 8, "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
+               "api": "moira_filter_batch (pinned host slab -> chunked H2D/kernels/D2H on two streams)"}
+
+    # ---- CPU baseline: the reference's own C core on this box's host cores (rank 0, N = 1) ------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        probe_n = 20000
+        rows = slab[:2_000_000].cpu().numpy().reshape(-1)
+        offs = np.arange(2_000_000, dtype=np.uint64) * STRIDE
+        lns = np.full(2_000_000, READ_LEN, dtype=np.uint32)
+        rate, _, kind, threads = _time_reference(rows, offs[:probe_n], lns[:probe_n], cores)
+        s_n = int(min(2_000_000, max(probe_n, rate * 12.0)))      # ~12 s of CPU work
+        rate, dt, kind, threads = _time_reference(rows, offs[:s_n], lns[:s_n], cores)
+        cpu = {"value": rate, "unit": "reads/s", "cores": threads, "kind": kind,
+               "sample": "first %d reads of this run's GPU workload, %.1f s, all host threads, C loop over the reference test()" % (s_n, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reads_per_gpu": n, "read_len": READ_LEN, "row_stride": STRIDE,
+                       "error_calc": "poisson_binomial", "mode": "decision (exact ee for accepted reads, lower bound for certain rejects)",
+                       "l2": "inputs (2.56 GB/GPU) larger than L2; no flush", "accepted_fraction": accepted_frac,
+                       "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU, NCCL all-reduce of 80 counters per step"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "exact_ee": {"value": value_exact, "unit": "reads/s", "note": "exact statistic for every read (escalation ladder), device-resident"},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

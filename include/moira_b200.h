@@ -1,0 +1,214 @@
+/*
+ * moira_b200.h -- C ABI of libmoira_b200.so: the B200 (sm_100a) replacement for moira's
+ * per-read quality-filter hot path.
+ *
+ * What it replaces in the reference (fpusan/moira v1.3.2, paths relative to the reference root):
+ *   moira/bernoullimodule.c:66-114   bernoulli.calculate_errors_PB binding (one read per call)
+ *   moira/bernoullimodule.c:131-263  prob_j_errors / sum_of_binomials / interpolate / test
+ *   moira/moira.py:1637-1679         calculate_errors_poisson            (mode POISSON)
+ *   moira/moira.py:1654-1663         Lambda = sum p_i                    (mode EXPECTED_ERROR)
+ *   moira/moira.py:806-833           filter half of process_data (truncate, +Ns, floor)
+ *   moira/moira.py:872-970           accept/reject decision of write_results
+ *
+ * Conventions: every entry point returns an int status (0 = MOIRA_OK, < 0 = error enum below);
+ * moira_last_error() gives a thread-local message for the last failing call on this thread.
+ * Nothing throws or aborts across this boundary.  Signatures use plain pointers and sizes only.
+ * There is no CPU fallback: without a usable CUDA device every compute entry point fails with
+ * MOIRA_ERR_CUDA.
+ *
+ * Slab encoding (one byte per base, "in band"):
+ *   0x00..0xFC  Phred quality of a called base (0 is accepted and means 1, as the reference
+ *               binding maps it, bernoullimodule.c:104-107, moira.py:814)
+ *   0xFD        padding: ignored entirely (never needed inside [0, length); the library masks
+ *               bytes at and beyond `length` itself, so row padding may hold anything)
+ *   0xFE        base 'n': skipped and counted in Ns (bernoullimodule.c:196)
+ *   0xFF        base 'N': skipped, counted in Ns, and makes the read "ambiguous" for
+ *               --ambigs disallow (moira.py:911)
+ * Row r occupies bytes [offsets[r], offsets[r] + lengths[r]); offsets must be multiples of 16
+ * and the slab must be readable up to offsets[r] + ceil16(lengths[r]).
+ */
+#ifndef MOIRA_B200_H
+#define MOIRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOIRA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MOIRA_API __attribute__((visibility("default")))
+#else
+#define MOIRA_API
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define MOIRA_OK                  0
+#define MOIRA_ERR_BAD_ALPHA      -1  /* alpha <= 0, alpha >= 1, or 1-alpha rounds to 1.0 (bernoullimodule.c:79-83) */
+#define MOIRA_ERR_LENGTH_MISMATCH -2 /* len(contig) != len(quals)            (bernoullimodule.c:85-90) */
+#define MOIRA_ERR_BAD_QUALITY    -3  /* quality outside 0..252 (not representable in the slab) */
+#define MOIRA_ERR_CUDA           -4  /* CUDA runtime/driver error, or no device */
+#define MOIRA_ERR_BAD_ARG        -5
+#define MOIRA_ERR_NOMEM          -6
+#define MOIRA_ERR_UNRESOLVED     -7  /* cumulative probability never exceeded 1-alpha (reference would run off its arrays) */
+#define MOIRA_ERR_PARSE          -8  /* malformed FASTQ / FASTA+QUAL input (host parsers) */
+
+/* ---- enums ---------------------------------------------------------------------------------- */
+#define MOIRA_MODE_PB             0  /* --error_calc poisson_binomial   (bernoullimodule.c) */
+#define MOIRA_MODE_POISSON        1  /* --error_calc poisson            (moira.py:1637-1679) */
+#define MOIRA_MODE_EXPECTED_ERROR 2  /* ee = sum p_i                    (moira.py:1654-1663) */
+
+#define MOIRA_THR_UNCERT          0  /* accept iff ee <= len * thr      (moira.py:950) */
+#define MOIRA_THR_MAXERRORS       1  /* accept iff ee <= thr            (moira.py:926) */
+
+#define MOIRA_AMBIGS_TREAT_AS_ERRORS 0 /* ee += Ns                       (moira.py:827-828) */
+#define MOIRA_AMBIGS_IGNORE          1
+#define MOIRA_AMBIGS_DISALLOW        2 /* reads containing 'N' rejected  (moira.py:911-922) */
+
+#define MOIRA_EE_RAW              0  /* ee_out = what calculate_errors_* returns */
+#define MOIRA_EE_FINAL            1  /* ee_out = what process_data returns (after +Ns and floor) */
+
+/* ---- per-read flag byte --------------------------------------------------------------------- */
+#define MOIRA_FLAG_ACCEPT       0x01
+#define MOIRA_FLAG_REASON_MASK  0x0E  /* (flags >> 1) & 7 : see MOIRA_REASON_* */
+#define MOIRA_FLAG_LOWER_BOUND  0x10  /* decision mode only: read is a certain reject and ee_out is a LOWER BOUND, not exact */
+#define MOIRA_FLAG_HAS_N        0x20  /* read contains an uppercase 'N' (0xFF byte) */
+#define MOIRA_FLAG_NUMERIC      0x40  /* statistic not computable (see MOIRA_ERR_UNRESOLVED); read rejected */
+#define MOIRA_FLAG_NEAR_CUTOFF  0x80  /* |ee - cutoff| <= 1e-12 * cutoff: decision is within FP64 tolerance of flipping */
+
+#define MOIRA_REASON_NONE    0
+#define MOIRA_REASON_ERRORS  1  /* "uncert > x" / "errors > x"  (moira.py:942, 963) */
+#define MOIRA_REASON_LENGTH  2  /* "length below"               (moira.py:872-883) */
+#define MOIRA_REASON_AMBIGS  3  /* "contains ambiguities"       (moira.py:911-922) */
+
+/* ---- counters (uint64[MOIRA_N_COUNTERS]); device side counterpart of moira.py:406-408, 483-485, 509-519 */
+#define MOIRA_CNT_READS        0
+#define MOIRA_CNT_ACCEPTED     1
+#define MOIRA_CNT_BAD_ERRORS   2
+#define MOIRA_CNT_BAD_LENGTH   3
+#define MOIRA_CNT_BAD_AMBIGS   4
+#define MOIRA_CNT_NEAR_CUTOFF  5
+#define MOIRA_CNT_LOWER_BOUND  6
+#define MOIRA_CNT_NUMERIC      7
+#define MOIRA_CNT_HIST         16  /* 64 bins of floor(final ee); last bin = >= 63 */
+#define MOIRA_N_HIST           64
+#define MOIRA_N_COUNTERS       80
+
+typedef struct moira_ctx moira_ctx;
+
+typedef struct moira_params {
+    int32_t  mode;        /* MOIRA_MODE_* */
+    int32_t  thr_kind;    /* MOIRA_THR_* */
+    int32_t  ambigs;      /* MOIRA_AMBIGS_* */
+    int32_t  round_flag;  /* --round: floor(ee) before comparing (moira.py:830-831) */
+    uint32_t truncate;    /* --truncate: 0 = off (moira.py:806-807, 872) */
+    int32_t  exact_ee;    /* 1: exact statistic for every read (what collapse needs, moira.py:466);
+                             0: decision mode, certain rejects may carry a lower bound (MOIRA_FLAG_LOWER_BOUND) */
+    int32_t  ee_output;   /* MOIRA_EE_* */
+    int32_t  reserved;
+    double   alpha;       /* --alpha */
+    double   thr;         /* --uncert or --maxerrors value */
+} moira_params;
+
+/* ---- library / context ---------------------------------------------------------------------- */
+MOIRA_API int moira_abi_version(void);
+MOIRA_API const char *moira_last_error(void);
+MOIRA_API void moira_params_default(moira_params *p);  /* reference defaults: PB, alpha .005, uncert .01, treat_as_errors */
+
+MOIRA_API int moira_ctx_create(int device, moira_ctx **out);
+MOIRA_API int moira_ctx_destroy(moira_ctx *ctx);
+MOIRA_API int moira_ctx_sm_count(const moira_ctx *ctx, int *out);
+
+/* Host-libm lookup tables the kernels use (filled at ctx creation with the reference formulas
+ * bernoullimodule.c:202, :140, :144).  Index = slab byte; entries 0xFD..0xFF are (p=0, 1-p=1, e=0). */
+/* The same tables without a context (pure host code; used by the CPU-side tests).  *e_equals_p is set
+ * to 1 when e[Q] == p[Q] and one_minus_p[Q] == 1 - p[Q] bitwise for every entry (selects the 8-byte
+ * table variant of the kernels). */
+MOIRA_API int moira_build_lut(double p[256], double one_minus_p[256], double e[256], int *e_equals_p);
+MOIRA_API int moira_ctx_get_lut(const moira_ctx *ctx, double p[256], double one_minus_p[256], double e[256]);
+
+/* Pinned host memory for the end-to-end path (copies from/to it overlap with kernels). */
+MOIRA_API int moira_host_alloc(void **ptr, size_t bytes);
+MOIRA_API int moira_host_free(void *ptr);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+/* Device-resident variant: every pointer is a DEVICE pointer, work is enqueued on `stream`
+ * (a cudaStream_t; NULL = default stream) and the call returns without synchronising.
+ * offsets may be NULL (row r starts at r * stride); lengths may be NULL (every read has
+ * fixed_length bases).  d_counters (uint64[MOIRA_N_COUNTERS]) is ACCUMULATED into; may be NULL.
+ * d_ns / d_flags may be NULL. */
+MOIRA_API int moira_filter_device(moira_ctx *ctx, const uint8_t *d_slab, const uint64_t *d_offsets,
+                        const uint32_t *d_lengths, uint64_t stride, uint32_t fixed_length,
+                        uint64_t n_reads, const moira_params *params, double *d_ee, int32_t *d_ns,
+                        uint8_t *d_flags, uint64_t *d_counters, void *stream);
+
+/* Host-buffer variant (the call a host program makes): copies the slab in chunks host->device,
+ * runs the filter and copies ee / Ns / flags back, overlapping copies of one chunk with the
+ * kernels of another on two streams.  Blocks until the results are in the output arrays.
+ * counters_out (uint64[MOIRA_N_COUNTERS]) is overwritten; ns_out, flags_out, counters_out may be NULL.
+ * slab_bytes = readable size of `slab`. */
+MOIRA_API int moira_filter_batch(moira_ctx *ctx, const uint8_t *slab, uint64_t slab_bytes,
+                       const uint64_t *offsets, const uint32_t *lengths, uint64_t n_reads,
+                       const moira_params *params, double *ee_out, int32_t *ns_out,
+                       uint8_t *flags_out, uint64_t *counters_out);
+
+/* Asynchronous pair around the same work, so a host parser can fill the next slab while this one
+ * is in flight.  At most MOIRA_MAX_INFLIGHT submissions may be outstanding per context; buffers
+ * must stay valid (and should be pinned, moira_host_alloc) until the matching moira_wait. */
+#define MOIRA_MAX_INFLIGHT 4
+MOIRA_API int moira_submit(moira_ctx *ctx, const uint8_t *slab, uint64_t slab_bytes, const uint64_t *offsets,
+                 const uint32_t *lengths, uint64_t n_reads, const moira_params *params,
+                 double *ee_out, int32_t *ns_out, uint8_t *flags_out, uint64_t *counters_out,
+                 int *ticket_out);
+MOIRA_API int moira_wait(moira_ctx *ctx, int ticket);
+
+/* Drop-in for ONE call of bernoulli.calculate_errors_PB(contig, quals, alpha)
+ * (bernoullimodule.c:66-114): same validation (alpha in (0,1); Q == 0 -> 1), same result
+ * (expected_errors, Ns), computed by the CUDA path as a batch of one. */
+MOIRA_API int moira_calculate_errors_PB(moira_ctx *ctx, const char *contig, const int32_t *quals,
+                              uint64_t length, double alpha, double *ee_out, int32_t *ns_out);
+
+/* ---- host-side packing (plain C++, no GPU) ---------------------------------------------------- */
+
+/* Merge bases + integer qualities of n reads into the in-band slab.  seq/qual rows are given by
+ * in_offsets[r] .. + lengths[r]; out_offsets[r] (multiples of 16) are written by the call, which
+ * returns the required slab size in *slab_bytes_out when slab == NULL (sizing pass).
+ * lower_n_ambiguous: 1 = 'n' is skipped like 'N' (C core, bernoullimodule.c:196); 0 = only 'N'
+ * (Python calculators, moira.py:1605, 1660). */
+MOIRA_API int moira_pack_reads(const char *seq, const int32_t *quals, const uint64_t *in_offsets,
+                     const uint32_t *lengths, uint64_t n_reads, int lower_n_ambiguous,
+                     uint8_t *slab, uint64_t slab_capacity, uint64_t *out_offsets,
+                     uint64_t *slab_bytes_out);
+
+/* Parse a FASTQ text buffer (4-line records, moira.py:1152-1204) straight into a slab.
+ * Sizing pass when slab == NULL: returns n_reads and the needed slab bytes.
+ * hdr_off/hdr_len and seq_off give, per read, the byte ranges of the header token and the
+ * sequence line inside `text` (so the host can slice names and bases without re-parsing). */
+MOIRA_API int moira_parse_fastq(const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous,
+                      uint8_t *slab, uint64_t slab_capacity, uint64_t *out_offsets,
+                      uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off,
+                      uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out);
+
+/* ---- measurement helpers ---------------------------------------------------------------------- */
+
+/* Register-resident FP64 issue-rate micro-benchmark (non-fused DMUL/DADD in the kernel's own
+ * 7:4 ratio), the denominator of the FP64 roofline.  Returns operations per second. */
+MOIRA_API int moira_fp64_peak(moira_ctx *ctx, int iters, double *ops_per_s_out, double *ms_out);
+
+/* Number of kernel launches this context has issued so far (for bench.py's gpu_launches). */
+MOIRA_API int moira_ctx_launch_count(const moira_ctx *ctx, uint64_t *out);
+
+/* Milliseconds spent in the dominant kernel (the first-pass kernel), summed over every launch since
+ * timing was last switched on with moira_ctx_set_timing(ctx, 1) (at most 64 launches are kept),
+ * measured with CUDA events on the stream the kernel was launched on. */
+MOIRA_API int moira_ctx_set_timing(moira_ctx *ctx, int enabled);
+MOIRA_API int moira_ctx_last_kernel_ms(moira_ctx *ctx, float *ms_out, const char **name_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOIRA_B200_H */

@@ -1,0 +1,105 @@
+"""ctypes binding of libmoira_b200.so (include/moira_b200.h).
+
+There is deliberately no fallback: if the shared library is missing this module raises at import
+time, and if no CUDA device is usable every compute entry point raises MoiraError(MOIRA_ERR_CUDA).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmoira_b200.so")
+
+# ---- constants mirrored from include/moira_b200.h -------------------------------------------
+ABI_VERSION = 1
+OK = 0
+ERR_BAD_ALPHA, ERR_LENGTH_MISMATCH, ERR_BAD_QUALITY, ERR_CUDA = -1, -2, -3, -4
+ERR_BAD_ARG, ERR_NOMEM, ERR_UNRESOLVED, ERR_PARSE = -5, -6, -7, -8
+MODE_PB, MODE_POISSON, MODE_EXPECTED_ERROR = 0, 1, 2
+THR_UNCERT, THR_MAXERRORS = 0, 1
+AMBIGS_TREAT_AS_ERRORS, AMBIGS_IGNORE, AMBIGS_DISALLOW = 0, 1, 2
+EE_RAW, EE_FINAL = 0, 1
+FLAG_ACCEPT, FLAG_REASON_MASK, FLAG_LOWER_BOUND = 0x01, 0x0E, 0x10
+FLAG_HAS_N, FLAG_NUMERIC, FLAG_NEAR_CUTOFF = 0x20, 0x40, 0x80
+REASON_NONE, REASON_ERRORS, REASON_LENGTH, REASON_AMBIGS = 0, 1, 2, 3
+CNT_READS, CNT_ACCEPTED, CNT_BAD_ERRORS, CNT_BAD_LENGTH, CNT_BAD_AMBIGS = 0, 1, 2, 3, 4
+CNT_NEAR_CUTOFF, CNT_LOWER_BOUND, CNT_NUMERIC, CNT_HIST, N_HIST, N_COUNTERS = 5, 6, 7, 16, 64, 80
+MAX_INFLIGHT = 4
+
+EXPORTS = [
+    "moira_abi_version", "moira_last_error", "moira_params_default", "moira_ctx_create",
+    "moira_ctx_destroy", "moira_ctx_sm_count", "moira_build_lut", "moira_ctx_get_lut",
+    "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_filter_batch",
+    "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads",
+    "moira_parse_fastq", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
+    "moira_ctx_last_kernel_ms",
+]
+
+
+class Params(ctypes.Structure):
+    """struct moira_params."""
+    _fields_ = [
+        ("mode", ctypes.c_int32), ("thr_kind", ctypes.c_int32), ("ambigs", ctypes.c_int32),
+        ("round_flag", ctypes.c_int32), ("truncate", ctypes.c_uint32), ("exact_ee", ctypes.c_int32),
+        ("ee_output", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("alpha", ctypes.c_double), ("thr", ctypes.c_double),
+    ]
+
+
+class MoiraError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("moira_b200 error %d: %s" % (code, message))
+        self.code = code
+        self.message = message
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+        "`make -C moira_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_vp, _i, _u64, _u32, _dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_double
+_pp = ctypes.POINTER(Params)
+
+lib.moira_abi_version.restype = _i
+lib.moira_last_error.restype = ctypes.c_char_p
+lib.moira_params_default.restype = None
+lib.moira_params_default.argtypes = [_pp]
+lib.moira_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
+lib.moira_ctx_destroy.argtypes = [_vp]
+lib.moira_ctx_sm_count.argtypes = [_vp, ctypes.POINTER(_i)]
+lib.moira_build_lut.argtypes = [_vp, _vp, _vp, ctypes.POINTER(_i)]
+lib.moira_ctx_get_lut.argtypes = [_vp, _vp, _vp, _vp]
+lib.moira_host_alloc.argtypes = [ctypes.POINTER(_vp), ctypes.c_size_t]
+lib.moira_host_free.argtypes = [_vp]
+lib.moira_filter_device.argtypes = [_vp, _vp, _vp, _vp, _u64, _u32, _u64, _pp, _vp, _vp, _vp, _vp, _vp]
+lib.moira_filter_batch.argtypes = [_vp, _vp, _u64, _vp, _vp, _u64, _pp, _vp, _vp, _vp, _vp]
+lib.moira_submit.argtypes = [_vp, _vp, _u64, _vp, _vp, _u64, _pp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i)]
+lib.moira_wait.argtypes = [_vp, _i]
+lib.moira_calculate_errors_PB.argtypes = [_vp, ctypes.c_char_p, _vp, _u64, _dbl, ctypes.POINTER(_dbl),
+                                          ctypes.POINTER(ctypes.c_int32)]
+lib.moira_pack_reads.argtypes = [_vp, _vp, _vp, _vp, _u64, _i, _vp, _u64, _vp, ctypes.POINTER(_u64)]
+lib.moira_parse_fastq.argtypes = [_vp, _u64, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64,
+                                  ctypes.POINTER(_u64), ctypes.POINTER(_u64)]
+lib.moira_fp64_peak.argtypes = [_vp, _i, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
+lib.moira_ctx_launch_count.argtypes = [_vp, ctypes.POINTER(_u64)]
+lib.moira_ctx_set_timing.argtypes = [_vp, _i]
+lib.moira_ctx_last_kernel_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p)]
+for _name in EXPORTS:
+    if _name not in ("moira_last_error", "moira_params_default"):
+        getattr(lib, _name).restype = _i
+
+if lib.moira_abi_version() != ABI_VERSION:
+    raise ImportError("libmoira_b200.so ABI %d != binding ABI %d" % (lib.moira_abi_version(), ABI_VERSION))
+
+
+def last_error() -> str:
+    return (lib.moira_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise MoiraError(rc, last_error())

@@ -1,0 +1,582 @@
+// moira_api.cu -- C ABI (include/moira_b200.h) over the kernels in moira_kernels.cu:
+// context, lookup tables, pass orchestration (first pass + escalation ladder, all enqueued
+// without host synchronisation), and the chunked host<->device pipeline.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "moira_internal.h"
+
+using namespace moira;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(MOIRA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr uint32_t SUB_BATCH = 1u << 24;   // reads per first-pass launch (queue indices are 32-bit)
+constexpr int MAX_TIMED = 64;
+
+struct Workspace {
+    uint32_t *queues = nullptr;
+    uint32_t *counts = nullptr;
+    uint32_t cap = 0;
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Ticket {
+    bool busy = false;
+    DevBuf slab, offsets, lengths, ee, ns, flags, counters;
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    uint64_t *counters_out = nullptr;
+    uint64_t *counters_pinned = nullptr;
+};
+
+}  // namespace
+
+namespace moira {
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace moira
+
+struct moira_ctx {
+    int device = 0;
+    int sm_count = 0;
+    double h_p[256], h_q[256], h_e[256];
+    int e_equals_p = 0;
+    double *d_p = nullptr, *d_q = nullptr, *d_e = nullptr;
+    double *d_sink = nullptr;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t meta_ready = nullptr;
+    Workspace ws[3];          // [0],[1]: pipeline streams; [2]: moira_filter_device on a caller stream
+    Ticket tickets[MOIRA_MAX_INFLIGHT];
+    uint64_t launches = 0;
+    int timing = 0;
+    int n_timed = 0;
+    cudaEvent_t t0[MAX_TIMED], t1[MAX_TIMED];
+    const char *timed_name = "";
+    // single-read scratch (pinned)
+    uint8_t *one_slab = nullptr;
+    size_t one_cap = 0;
+    double *one_out = nullptr;   // [0]=ee ; followed by ns (int32) and flags
+};
+
+namespace {
+
+// Host-libm tables, built with the reference's own expressions:
+//   p  = pow(10, Q / -10.0)                                   bernoullimodule.c:202
+//   q  = pow(1 - p, 1)                                        bernoullimodule.c:140 (n == 1)
+//   e  = ((1 - 1 + 1) / (1.0 * 1)) * (p / (1 - p)) * q        bernoullimodule.c:144 (i == 1, left to right)
+// Q == 0 uses the Q == 1 entry (bernoullimodule.c:104-107, moira.py:814).
+void build_tables(double *h_p, double *h_q, double *h_e, int *eqp)
+{
+    for (int b = 0; b < 256; b++) {
+        if (b >= 0xFD) { h_p[b] = 0.0; h_q[b] = 1.0; h_e[b] = 0.0; continue; }
+        const int Q = b == 0 ? 1 : b;
+        const int n = 1, i = 1;
+        volatile double p = pow(10, (Q / -10.0));
+        volatile double q = pow((1 - p), n);
+        volatile double ratio = p / (1 - p);
+        volatile double lead = (n - i + 1) / (1.0 * i);
+        volatile double t = lead * ratio;
+        volatile double e = t * q;
+        h_p[b] = p; h_q[b] = q; h_e[b] = e;
+    }
+    *eqp = 1;
+    for (int b = 0; b < 256; b++) {
+        volatile double omp = 1.0 - h_p[b];
+        if (h_e[b] != h_p[b] || h_q[b] != omp) *eqp = 0;
+    }
+}
+
+int ensure(DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return MOIRA_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&b.p, want) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MOIRA_ERR_NOMEM, "cudaMalloc of %zu bytes failed", want);
+    }
+    b.cap = want;
+    return MOIRA_OK;
+}
+
+int ensure_ws(Workspace &w, uint32_t cap)
+{
+    if (cap <= w.cap && w.queues) return MOIRA_OK;
+    if (w.queues) cudaFree(w.queues);
+    if (!w.counts) CU(cudaMalloc(&w.counts, NB * sizeof(uint32_t)));
+    w.queues = nullptr; w.cap = 0;
+    if (cudaMalloc(&w.queues, (size_t)NB * cap * sizeof(uint32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MOIRA_ERR_NOMEM, "cudaMalloc of escalation queues (%u reads) failed", cap);
+    }
+    w.cap = cap;
+    return MOIRA_OK;
+}
+
+int check_params(const moira_params *p)
+{
+    if (!p) return fail(MOIRA_ERR_BAD_ARG, "params is NULL");
+    if (!(p->alpha > 0.0) || !(p->alpha < 1.0)) return fail(MOIRA_ERR_BAD_ALPHA, "Alpha must be between 0 and 1");
+    volatile double oma = 1 - p->alpha;
+    if (!(oma < 1.0)) return fail(MOIRA_ERR_BAD_ALPHA, "Alpha must be between 0 and 1 (1 - alpha rounds to 1)");
+    if (p->mode < MOIRA_MODE_PB || p->mode > MOIRA_MODE_EXPECTED_ERROR) return fail(MOIRA_ERR_BAD_ARG, "unknown mode %d", p->mode);
+    if (p->thr_kind != MOIRA_THR_UNCERT && p->thr_kind != MOIRA_THR_MAXERRORS) return fail(MOIRA_ERR_BAD_ARG, "unknown thr_kind %d", p->thr_kind);
+    if (p->ambigs < 0 || p->ambigs > MOIRA_AMBIGS_DISALLOW) return fail(MOIRA_ERR_BAD_ARG, "unknown ambigs %d", p->ambigs);
+    if (!(p->thr == p->thr)) return fail(MOIRA_ERR_BAD_ARG, "threshold is NaN");
+    return MOIRA_OK;
+}
+
+int first_pass_k_template(int k_wanted)
+{
+    static const int ks[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32};
+    for (int k : ks) if (k_wanted <= k) return k;
+    return 32;
+}
+
+// Enqueue the whole filter for reads [0, n) on `stream`.  max_len = longest read if known, else 0.
+int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const uint64_t *d_offsets,
+                    const uint32_t *d_lengths, uint64_t stride, uint32_t fixed_length, uint64_t n_reads,
+                    const moira_params *p, uint32_t max_len, double *d_ee, int32_t *d_ns, uint8_t *d_flags,
+                    uint64_t *d_counters, cudaStream_t stream)
+{
+    if (n_reads == 0) return MOIRA_OK;
+    if (!d_slab || !d_ee) return fail(MOIRA_ERR_BAD_ARG, "slab / ee pointer is NULL");
+    if (((uintptr_t)d_slab & 15u) != 0) return fail(MOIRA_ERR_BAD_ARG, "slab must be 16-byte aligned");
+    if (!d_offsets && (stride & 15u)) return fail(MOIRA_ERR_BAD_ARG, "stride must be a multiple of 16");
+    if (!d_lengths) max_len = fixed_length;
+    FilterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.slab = d_slab; a.offsets = d_offsets; a.lengths = d_lengths; a.stride = stride; a.fixed_length = fixed_length;
+    a.ee = d_ee; a.ns = d_ns; a.flags = d_flags; a.counters = reinterpret_cast<unsigned long long *>(d_counters);
+    volatile double oma = 1 - p->alpha;   // evaluated like (1 - alpha) at bernoullimodule.c:244
+    a.oma = oma;
+    a.thr = p->thr;
+    a.z = sqrt(2.0 * log(1.0 / p->alpha));
+    a.mode = p->mode; a.thr_kind = p->thr_kind; a.ambigs = p->ambigs; a.round_flag = p->round_flag;
+    a.truncate = p->truncate; a.exact = p->exact_ee; a.ee_output = p->ee_output;
+    a.lut_p = c->d_p; a.lut_q = c->d_q; a.lut_e = c->d_e; a.e_equals_p = c->e_equals_p;
+    a.rung = -1;
+    LaunchCfg cfg{c->sm_count, stream};
+
+    // First-pass K: a decision needs floor(cutoff) + 2 PMF entries and the cutoff is
+    // largest for the longest read.  Unknown lengths: start at 4, the ladder settles the rest.
+    int k_first = 4;
+    bool k_decides_all = false;
+    if (p->mode == MOIRA_MODE_PB) {
+        uint32_t eff = max_len;
+        if (p->truncate && (eff == 0 || eff > p->truncate)) eff = p->truncate;
+        const bool known = p->thr_kind == MOIRA_THR_MAXERRORS || eff != 0;
+        if (known) {
+            volatile double prod = (double)eff * p->thr;
+            double cmax = p->thr_kind == MOIRA_THR_MAXERRORS ? p->thr : (double)prod;
+            double kd = cmax < 0.0 ? 2.0 : floor(cmax) + 2.0;
+            if (kd <= (double)max_first_pass_k()) { k_first = (int)kd; k_decides_all = true; }
+            else k_first = max_first_pass_k();
+        }
+        k_first = first_pass_k_template(k_first);
+        a.min_rung = 0;
+        while (a.min_rung < NB - 1 && rung_cap(a.min_rung) <= k_first) a.min_rung++;
+    }
+    const bool ladder = p->mode == MOIRA_MODE_PB && (p->exact_ee || !k_decides_all);
+    a.allow_push = ladder ? 1 : 0;
+
+    for (uint64_t start = 0; start < n_reads; start += SUB_BATCH) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(SUB_BATCH, n_reads - start);
+        a.base = start; a.n = n; a.queue = nullptr; a.queue_count = nullptr; a.rung = -1;
+        if (ladder) {
+            int rc = ensure_ws(ws, (uint32_t)std::min<uint64_t>(n_reads, SUB_BATCH));
+            if (rc) return rc;
+            a.queues = ws.queues; a.queue_counts = ws.counts; a.queue_cap = ws.cap;
+            CU(cudaMemsetAsync(ws.counts, 0, NB * sizeof(uint32_t), stream));
+        }
+        const bool timed = c->timing && c->n_timed < MAX_TIMED;
+        if (timed) CU(cudaEventRecord(c->t0[c->n_timed], stream));
+        const char *name = "";
+        int rc = p->mode == MOIRA_MODE_PB ? launch_pb_first(a, k_first, cfg, &name) : launch_lambda(a, cfg, &name);
+        if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        c->launches++;
+        if (timed) { CU(cudaEventRecord(c->t1[c->n_timed], stream)); c->n_timed++; c->timed_name = name; }
+        if (ladder) {
+            for (int b = a.min_rung; b < NB; b++) {
+                if (launch_rung(a, b, cfg)) return fail(MOIRA_ERR_CUDA, "rung %d launch failed: %s", b, cudaGetErrorString(cudaGetLastError()));
+                c->launches++;
+            }
+        }
+    }
+    return MOIRA_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int moira_abi_version(void) { return MOIRA_ABI_VERSION; }
+const char *moira_last_error(void) { return g_err; }
+
+void moira_params_default(moira_params *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->mode = MOIRA_MODE_PB;                 // --error_calc poisson_binomial (moira.py:655-657)
+    p->thr_kind = MOIRA_THR_UNCERT;
+    p->ambigs = MOIRA_AMBIGS_TREAT_AS_ERRORS;  // moira.py:658-660
+    p->alpha = 0.005;                        // moira.py:668
+    p->thr = 0.01;                           // moira.py:664
+    p->exact_ee = 1;
+    p->ee_output = MOIRA_EE_RAW;
+}
+
+int moira_ctx_create(int device, moira_ctx **out)
+{
+    if (!out) return fail(MOIRA_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MOIRA_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(MOIRA_ERR_BAD_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(MOIRA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    moira_ctx *c = new (std::nothrow) moira_ctx();
+    if (!c) return fail(MOIRA_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    build_tables(c->h_p, c->h_q, c->h_e, &c->e_equals_p);
+    if (kernels_init(c->sm_count)) {
+        int rc = fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return rc;
+    }
+    CU(cudaMalloc(&c->d_p, 256 * sizeof(double)));
+    CU(cudaMalloc(&c->d_q, 256 * sizeof(double)));
+    CU(cudaMalloc(&c->d_e, 256 * sizeof(double)));
+    CU(cudaMalloc(&c->d_sink, 64));
+    CU(cudaMemcpy(c->d_p, c->h_p, sizeof(c->h_p), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_q, c->h_q, sizeof(c->h_q), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_e, c->h_e, sizeof(c->h_e), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->meta_ready, cudaEventDisableTiming));
+    for (int i = 0; i < MAX_TIMED; i++) { CU(cudaEventCreate(&c->t0[i])); CU(cudaEventCreate(&c->t1[i])); }
+    for (auto &t : c->tickets)
+        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&t.done[i], cudaEventDisableTiming));
+    *out = c;
+    return MOIRA_OK;
+}
+
+int moira_ctx_destroy(moira_ctx *c)
+{
+    if (!c) return MOIRA_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &t : c->tickets) {
+        for (DevBuf *b : {&t.slab, &t.offsets, &t.lengths, &t.ee, &t.ns, &t.flags, &t.counters})
+            if (b->p) cudaFree(b->p);
+        for (int i = 0; i < 2; i++) if (t.done[i]) cudaEventDestroy(t.done[i]);
+        if (t.counters_pinned) cudaFreeHost(t.counters_pinned);
+    }
+    for (auto &w : c->ws) { if (w.queues) cudaFree(w.queues); if (w.counts) cudaFree(w.counts); }
+    for (int i = 0; i < MAX_TIMED; i++) { cudaEventDestroy(c->t0[i]); cudaEventDestroy(c->t1[i]); }
+    if (c->meta_ready) cudaEventDestroy(c->meta_ready);
+    for (int i = 0; i < 2; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->one_slab) cudaFreeHost(c->one_slab);
+    if (c->one_out) cudaFreeHost(c->one_out);
+    cudaFree(c->d_p); cudaFree(c->d_q); cudaFree(c->d_e); cudaFree(c->d_sink);
+    delete c;
+    return MOIRA_OK;
+}
+
+int moira_ctx_sm_count(const moira_ctx *c, int *out)
+{
+    if (!c || !out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    *out = c->sm_count;
+    return MOIRA_OK;
+}
+
+int moira_build_lut(double p[256], double q[256], double e[256], int *e_equals_p)
+{
+    double hp[256], hq[256], he[256];
+    int eqp = 0;
+    build_tables(hp, hq, he, &eqp);
+    if (p) memcpy(p, hp, sizeof(hp));
+    if (q) memcpy(q, hq, sizeof(hq));
+    if (e) memcpy(e, he, sizeof(he));
+    if (e_equals_p) *e_equals_p = eqp;
+    return MOIRA_OK;
+}
+
+int moira_ctx_get_lut(const moira_ctx *c, double p[256], double q[256], double e[256])
+{
+    if (!c) return fail(MOIRA_ERR_BAD_ARG, "ctx is NULL");
+    if (p) memcpy(p, c->h_p, sizeof(c->h_p));
+    if (q) memcpy(q, c->h_q, sizeof(c->h_q));
+    if (e) memcpy(e, c->h_e, sizeof(c->h_e));
+    return MOIRA_OK;
+}
+
+int moira_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(MOIRA_ERR_BAD_ARG, "ptr is NULL");
+    *ptr = nullptr;
+    if (cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MOIRA_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
+    }
+    return MOIRA_OK;
+}
+
+int moira_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return MOIRA_OK;
+}
+
+int moira_filter_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_offsets, const uint32_t *d_lengths,
+                        uint64_t stride, uint32_t fixed_length, uint64_t n_reads, const moira_params *params,
+                        double *d_ee, int32_t *d_ns, uint8_t *d_flags, uint64_t *d_counters, void *stream)
+{
+    if (!c) return fail(MOIRA_ERR_BAD_ARG, "ctx is NULL");
+    int rc = check_params(params);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    return run_filter_full(c, c->ws[2], d_slab, d_offsets, d_lengths, stride, fixed_length, n_reads, params, 0, d_ee,
+                           d_ns, d_flags, d_counters, (cudaStream_t)stream);
+}
+
+int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const uint64_t *offsets,
+                 const uint32_t *lengths, uint64_t n, const moira_params *params, double *ee_out, int32_t *ns_out,
+                 uint8_t *flags_out, uint64_t *counters_out, int *ticket_out)
+{
+    if (!c || !ticket_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    *ticket_out = -1;
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (n && (!slab || !offsets || !lengths || !ee_out)) return fail(MOIRA_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(c->device));
+    int ti = -1;
+    for (int i = 0; i < MOIRA_MAX_INFLIGHT; i++) if (!c->tickets[i].busy) { ti = i; break; }
+    if (ti < 0) return fail(MOIRA_ERR_BAD_ARG, "more than %d submissions in flight", MOIRA_MAX_INFLIGHT);
+    Ticket &t = c->tickets[ti];
+    t.counters_out = counters_out;
+    if (!t.counters_pinned) CU(cudaHostAlloc((void **)&t.counters_pinned, MOIRA_N_COUNTERS * sizeof(uint64_t), cudaHostAllocDefault));
+    memset(t.counters_pinned, 0, MOIRA_N_COUNTERS * sizeof(uint64_t));
+    if (n == 0) {
+        t.busy = true;
+        for (int i = 0; i < 2; i++) CU(cudaEventRecord(t.done[i], c->streams[i]));
+        *ticket_out = ti;
+        return MOIRA_OK;
+    }
+    if ((rc = ensure(t.slab, slab_bytes + 16)) || (rc = ensure(t.offsets, n * 8)) || (rc = ensure(t.lengths, n * 4)) ||
+        (rc = ensure(t.ee, n * 8)) || (rc = ensure(t.ns, n * 4)) || (rc = ensure(t.flags, n)) ||
+        (rc = ensure(t.counters, MOIRA_N_COUNTERS * 8)))
+        return rc;
+    uint8_t *d_slab = (uint8_t *)t.slab.p;
+    uint64_t *d_off = (uint64_t *)t.offsets.p;
+    uint32_t *d_len = (uint32_t *)t.lengths.p;
+    double *d_ee = (double *)t.ee.p;
+    int32_t *d_ns = (int32_t *)t.ns.p;
+    uint8_t *d_fl = (uint8_t *)t.flags.p;
+    uint64_t *d_cnt = (uint64_t *)t.counters.p;
+
+    cudaStream_t s0 = c->streams[0], s1 = c->streams[1];
+    CU(cudaMemcpyAsync(d_off, offsets, n * 8, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(d_len, lengths, n * 4, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemsetAsync(d_cnt, 0, MOIRA_N_COUNTERS * 8, s0));
+    CU(cudaEventRecord(c->meta_ready, s0));
+    CU(cudaStreamWaitEvent(s1, c->meta_ready, 0));
+
+    // Chunks of ~32 MB of slab alternate between the two streams: the H2D copy of one chunk overlaps
+    // the kernels of the previous one and the D2H copy of the one before.  Rows must be in slab order.
+    const uint64_t CHUNK_BYTES = 32ull << 20;
+    uint64_t start = 0;
+    int ci = 0;
+    while (start < n) {
+        uint64_t end = start;
+        const uint64_t b0 = offsets[start];
+        uint32_t max_len = 0;
+        uint64_t b1 = b0;
+        while (end < n) {
+            const uint64_t row_end = offsets[end] + (((uint64_t)lengths[end] + 15u) & ~15ull);
+            if (offsets[end] < b0) return fail(MOIRA_ERR_BAD_ARG, "offsets must be non-decreasing (read %llu)", (unsigned long long)end);
+            if (row_end > slab_bytes + 15) return fail(MOIRA_ERR_BAD_ARG, "read %llu extends past the slab", (unsigned long long)end);
+            if (offsets[end] & 15u) return fail(MOIRA_ERR_BAD_ARG, "offset of read %llu is not a multiple of 16", (unsigned long long)end);
+            if (end > start && row_end - b0 > CHUNK_BYTES) break;
+            b1 = std::max(b1, row_end);
+            max_len = std::max(max_len, lengths[end]);
+            end++;
+        }
+        cudaStream_t s = c->streams[ci & 1];
+        const uint64_t copy_end = std::min<uint64_t>(b1, slab_bytes);
+        if (copy_end > b0) CU(cudaMemcpyAsync(d_slab + b0, slab + b0, copy_end - b0, cudaMemcpyHostToDevice, s));
+        const uint64_t cn = end - start;
+        rc = run_filter_full(c, c->ws[ci & 1], d_slab, d_off + start, d_len + start, 0, 0, cn, params, max_len,
+                             d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ee_out + start, d_ee + start, cn * 8, cudaMemcpyDeviceToHost, s));
+        if (ns_out) CU(cudaMemcpyAsync(ns_out + start, d_ns + start, cn * 4, cudaMemcpyDeviceToHost, s));
+        if (flags_out) CU(cudaMemcpyAsync(flags_out + start, d_fl + start, cn, cudaMemcpyDeviceToHost, s));
+        start = end;
+        ci++;
+    }
+    CU(cudaEventRecord(t.done[1], s1));
+    CU(cudaStreamWaitEvent(s0, t.done[1], 0));
+    CU(cudaMemcpyAsync(t.counters_pinned, d_cnt, MOIRA_N_COUNTERS * 8, cudaMemcpyDeviceToHost, s0));
+    CU(cudaEventRecord(t.done[0], s0));
+    t.busy = true;
+    *ticket_out = ti;
+    return MOIRA_OK;
+}
+
+int moira_wait(moira_ctx *c, int ticket)
+{
+    if (!c || ticket < 0 || ticket >= MOIRA_MAX_INFLIGHT || !c->tickets[ticket].busy)
+        return fail(MOIRA_ERR_BAD_ARG, "invalid ticket %d", ticket);
+    Ticket &t = c->tickets[ticket];
+    t.busy = false;
+    CU(cudaEventSynchronize(t.done[1]));
+    CU(cudaEventSynchronize(t.done[0]));
+    if (t.counters_out) memcpy(t.counters_out, t.counters_pinned, MOIRA_N_COUNTERS * sizeof(uint64_t));
+    CU(cudaGetLastError());
+    return MOIRA_OK;
+}
+
+int moira_filter_batch(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const uint64_t *offsets,
+                       const uint32_t *lengths, uint64_t n, const moira_params *params, double *ee_out,
+                       int32_t *ns_out, uint8_t *flags_out, uint64_t *counters_out)
+{
+    int ticket = -1;
+    int rc = moira_submit(c, slab, slab_bytes, offsets, lengths, n, params, ee_out, ns_out, flags_out, counters_out, &ticket);
+    if (rc) {
+        if (c) { cudaSetDevice(c->device); cudaDeviceSynchronize(); }
+        return rc;
+    }
+    return moira_wait(c, ticket);
+}
+
+int moira_calculate_errors_PB(moira_ctx *c, const char *contig, const int32_t *quals, uint64_t length, double alpha,
+                              double *ee_out, int32_t *ns_out)
+{
+    if (!c || !contig || (!quals && length) || !ee_out || !ns_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    if (alpha <= 0 || alpha >= 1) return fail(MOIRA_ERR_BAD_ALPHA, "Alpha must be between 0 and 1");          // bernoullimodule.c:79-83
+    if (strlen(contig) != length) return fail(MOIRA_ERR_LENGTH_MISMATCH, "contig and contig_quals must have the same length");  // :85-90
+    if (length > 0xFFFFFFF0ull) return fail(MOIRA_ERR_BAD_ARG, "read too long");
+    CU(cudaSetDevice(c->device));
+    const size_t padded = ((size_t)length + 15) & ~(size_t)15;
+    if (padded + 16 > c->one_cap) {
+        if (c->one_slab) cudaFreeHost(c->one_slab);
+        c->one_slab = nullptr; c->one_cap = 0;
+        CU(cudaHostAlloc((void **)&c->one_slab, padded + 4096, cudaHostAllocDefault));
+        c->one_cap = padded + 4096;
+    }
+    if (!c->one_out) CU(cudaHostAlloc((void **)&c->one_out, 64, cudaHostAllocDefault));
+    for (uint64_t i = 0; i < length; i++) {
+        const char ch = contig[i];
+        if (ch == 78) c->one_slab[i] = 0xFF;                       // 'N'  bernoullimodule.c:196
+        else if (ch == 110) c->one_slab[i] = 0xFE;                 // 'n'
+        else {
+            const int32_t q = quals[i];
+            if (q < 0 || q > 0xFC) return fail(MOIRA_ERR_BAD_QUALITY, "quality %d at position %llu is outside 0..252", q, (unsigned long long)i);
+            c->one_slab[i] = (uint8_t)q;                           // 0 is read as 1 by the table (:104-107)
+        }
+    }
+    for (size_t i = length; i < padded; i++) c->one_slab[i] = 0xFD;
+    moira_params p;
+    moira_params_default(&p);
+    p.alpha = alpha;
+    p.exact_ee = 1;
+    p.ee_output = MOIRA_EE_RAW;
+    uint64_t off = 0;
+    uint32_t len = (uint32_t)length;
+    double *ee = c->one_out;
+    int32_t *ns = reinterpret_cast<int32_t *>(c->one_out + 1);
+    uint8_t *fl = reinterpret_cast<uint8_t *>(c->one_out + 2);
+    int rc = moira_filter_batch(c, c->one_slab, padded ? padded : 16, &off, &len, 1, &p, ee, ns, fl, nullptr);
+    if (rc) return rc;
+    if (*fl & MOIRA_FLAG_NUMERIC) return fail(MOIRA_ERR_UNRESOLVED, "cumulative probability never exceeded 1 - alpha");
+    *ee_out = *ee;
+    *ns_out = *ns;
+    return MOIRA_OK;
+}
+
+int moira_fp64_peak(moira_ctx *c, int iters, double *ops_per_s_out, double *ms_out)
+{
+    if (!c || !ops_per_s_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    if (iters < 1) iters = 1;
+    double ops = 0;
+    cudaStream_t s = c->streams[0];
+    if (launch_fp64_peak(iters / 8 + 1, c->sm_count, c->d_sink, s, &ops)) return fail(MOIRA_ERR_CUDA, "fp64_peak warm-up launch failed");
+    CU(cudaEventRecord(c->t0[0], s));
+    if (launch_fp64_peak(iters, c->sm_count, c->d_sink, s, &ops)) return fail(MOIRA_ERR_CUDA, "fp64_peak launch failed");
+    CU(cudaEventRecord(c->t1[0], s));
+    CU(cudaEventSynchronize(c->t1[0]));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->t0[0], c->t1[0]));
+    c->launches += 2;
+    *ops_per_s_out = ops / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return MOIRA_OK;
+}
+
+int moira_ctx_launch_count(const moira_ctx *c, uint64_t *out)
+{
+    if (!c || !out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    *out = c->launches;
+    return MOIRA_OK;
+}
+
+int moira_ctx_set_timing(moira_ctx *c, int enabled)
+{
+    if (!c) return fail(MOIRA_ERR_BAD_ARG, "ctx is NULL");
+    c->timing = enabled ? 1 : 0;
+    c->n_timed = 0;
+    return MOIRA_OK;
+}
+
+int moira_ctx_last_kernel_ms(moira_ctx *c, float *ms_out, const char **name_out)
+{
+    if (!c || !ms_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    float total = 0;
+    for (int i = 0; i < c->n_timed; i++) {
+        CU(cudaEventSynchronize(c->t1[i]));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->t0[i], c->t1[i]));
+        total += ms;
+    }
+    *ms_out = total;
+    if (name_out) *name_out = c->timed_name;
+    return MOIRA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// moira_internal.h -- shared between the kernel TU and the C-ABI/host TU.  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/moira_b200.h"
+
+namespace moira {
+
+// ---- escalation ladder --------------------------------------------------------------------
+// Reads whose decision / exact statistic is not settled by the first pass are pushed into one
+// of these queues, by the number K of PMF entries they are estimated to need.
+constexpr int NB = 9;
+// capacity in PMF entries of each rung: thread-per-read 8/16/32, warp-per-read 64..1024, block.
+__host__ __device__ constexpr int rung_cap(int b)
+{
+    return b == 0 ? 8 : b == 1 ? 16 : b == 2 ? 32 : b == 3 ? 64 : b == 4 ? 128 : b == 5 ? 256
+         : b == 6 ? 512 : b == 7 ? 1024 : 0x7fffffff;
+}
+
+struct FilterArgs {
+    // input
+    const uint8_t *slab;
+    const uint64_t *offsets;     // may be null: row = read * stride
+    const uint32_t *lengths;     // may be null: fixed_length
+    uint64_t stride;
+    uint32_t fixed_length;
+    uint64_t base;               // first read of this sub-batch
+    uint32_t n;                  // reads in this sub-batch (first pass)
+    const uint32_t *queue;       // ladder passes: indices relative to base; null on the first pass
+    const uint32_t *queue_count; // ladder passes: device count
+    // output
+    double *ee;
+    int32_t *ns;
+    uint8_t *flags;
+    unsigned long long *counters;
+    // parameters
+    double oma;                  // 1 - alpha, computed on the host exactly as the reference does
+    double thr;
+    double z;                    // sqrt(2 ln(1/alpha)): upper-quantile factor for the K estimate
+    int32_t mode;
+    int32_t thr_kind;
+    int32_t ambigs;
+    int32_t round_flag;
+    uint32_t truncate;
+    int32_t exact;
+    int32_t ee_output;
+    // escalation
+    uint32_t *queues;            // [NB][queue_cap]
+    uint32_t *queue_counts;      // [NB]
+    uint32_t queue_cap;
+    int32_t rung;                // -1 on the first pass, else this kernel's rung
+    int32_t min_rung;            // lowest rung the first pass may push to
+    int32_t allow_push;          // 0: no ladder follows (first-pass K provably decides everything)
+    // tables (device, 256 doubles each)
+    const double *lut_p;
+    const double *lut_q;
+    const double *lut_e;
+    int32_t e_equals_p;          // 1: e[Q] == p[Q] and q[Q] == 1 - p[Q] bitwise for all Q (checked on host)
+};
+
+struct LaunchCfg {
+    int sm_count;
+    cudaStream_t stream;
+};
+
+// first pass, thread-per-read; k_wanted is rounded up to an instantiated K (returned)
+int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, const char **name);
+// Poisson / expected-error, thread-per-read
+int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name);
+// ladder rung b over queue b
+int launch_rung(const FilterArgs &a, int b, const LaunchCfg &cfg);
+int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, double *ops_out);
+int kernels_init(int sm_count);  // sets function attributes (dynamic smem opt-in)
+int max_first_pass_k();
+
+// sets the thread-local message returned by moira_last_error() and returns `code`
+int fail(int code, const char *fmt, ...);
+
+}  // namespace moira

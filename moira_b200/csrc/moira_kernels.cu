@@ -1,0 +1,779 @@
+// moira_kernels.cu -- sm_100a kernels of the moira read filter.
+//
+// What is computed (reference: /root/reference/moira/bernoullimodule.c:182-263):
+// per read, the Poisson-binomial PMF of the number of sequencing errors, swept base by base
+// while keeping only the first K entries P[0..K-1]:
+//      P[j] <- fl( fl(q * P[j]) + fl(e * P[j-1]) )   (j = K-1 .. 1),      P[0] <- fl(q * P[0])
+// with q = 1-p and e = ((1/1.0) * (p/(1-p))) * (1-p) taken from a host-libm table.  Every cell is
+// bitwise the cell the reference computes (bernoullimodule.c:160 with n == 1; the i >= 2 terms
+// are +0.0), so no FMA contraction is allowed: all PMF arithmetic uses __dmul_rn / __dadd_rn.
+// Then acc[j] = acc[j-1] + P[j] until acc[j] > 1-alpha (:233-244) and the linear interpolation
+// of bernoullimodule.c:170-178.
+//
+// Kernels:
+//   pb_tpr<K>     thread-per-read, P[0..K-1] in registers.  Rows are staged global->shared with
+//                 per-lane cp.async.bulk (TMA bulk copy) into a double-buffered, bank-conflict-free
+//                 padded layout; the Q->p table lives in shared memory replicated 16x so that a
+//                 warp's 32 random lookups never conflict.  Persistent grid.
+//   lambda_tpr    same staging, accumulates Lambda = sum p_i sequentially (Poisson and
+//                 expected-error modes, moira.py:1637-1679).
+//   pb_wpr<M>     warp-per-read for reads that need many PMF entries (K = 32*M): lane l owns
+//                 P[l*M .. l*M+M-1], the neighbour entry travels by warp shuffle.
+//   pb_blk        block-per-read, P in shared memory, any K up to 24576: last rung.
+//   fp64_peak     register-resident DMUL/DADD issue-rate probe (roofline denominator).
+#include <math.h>
+
+#include "fact_table.h"
+#include "moira_internal.h"
+
+namespace moira {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- thread-per-read geometry ---------------------------------------------------------------
+constexpr int TPR_WARPS = 16;
+constexpr int TPR_THREADS = TPR_WARPS * 32;
+constexpr int CHUNK = 128;                       // bytes of one row staged per pipeline stage
+constexpr int ROW_STRIDE = CHUNK + 16;           // 144 B = 36 words: lane*36 mod 32 = lane*4 -> LDS.128 conflict-free
+constexpr int STAGE_BYTES = 32 * ROW_STRIDE;     // one warp, one stage
+constexpr int LUT_BYTES = 256 * 128;             // 256 entries x 128 B (16 x double or 8 x double2)
+constexpr int TPR_OFF_STAGE = LUT_BYTES;
+constexpr int TPR_OFF_BAR = TPR_OFF_STAGE + TPR_WARPS * 2 * STAGE_BYTES;
+constexpr int TPR_OFF_CNT = TPR_OFF_BAR + TPR_WARPS * 2 * 8;
+constexpr int TPR_SMEM = TPR_OFF_CNT + (16 + MOIRA_N_HIST) * 4;
+
+constexpr int WPR_THREADS = 256;
+constexpr int BLK_THREADS = 256;
+constexpr int BLK_CAP = 24576;                   // PMF entries held in shared memory by pb_blk
+constexpr int BLK_SMEM = BLK_CAP * 8 + 256 * 16;
+
+__constant__ double c_fact[MOIRA_FACT_N] = MOIRA_FACT_TABLE;
+
+// ---- PTX helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// ---- byte handling -------------------------------------------------------------------------------
+// Replace bytes at positions >= nvalid (0..4) of a little-endian word by the padding code 0xFD.
+__device__ __forceinline__ uint32_t mask_word(uint32_t w, int nvalid)
+{
+    if (nvalid >= 4) return w;
+    if (nvalid <= 0) return 0xFDFDFDFDu;
+    uint32_t keep = (1u << (8 * nvalid)) - 1u;
+    return (w & keep) | (0xFDFDFDFDu & ~keep);
+}
+__device__ __forceinline__ void count_marks(uint32_t w, int &ns, bool &has_upper_n)
+{
+    uint32_t ge = __vcmpgeu4(w, 0xFEFEFEFEu);   // 0xFF per byte that is 'n' (0xFE) or 'N' (0xFF)
+    if (ge) {
+        ns += __popc(ge) >> 3;
+        has_upper_n |= (__vcmpeq4(w, 0xFFFFFFFFu) != 0u);
+    }
+}
+
+// ---- read geometry -------------------------------------------------------------------------------
+struct ReadGeom {
+    uint64_t off;
+    uint32_t len;      // original length
+    uint32_t eff;      // after --truncate (moira.py:806-807)
+};
+__device__ __forceinline__ ReadGeom read_geom(const FilterArgs &a, uint32_t r_local)
+{
+    ReadGeom g;
+    uint64_t r = a.base + r_local;
+    g.off = a.offsets ? a.offsets[r] : r * a.stride;
+    g.len = a.lengths ? a.lengths[r] : a.fixed_length;
+    g.eff = (a.truncate && g.len > a.truncate) ? a.truncate : g.len;
+    return g;
+}
+
+// ---- per-read epilogue: process_data's +Ns / floor (moira.py:827-831), write_results' decision
+//      (moira.py:872-970), counters, and escalation of reads this pass could not settle -----------
+struct ReadResult {
+    double ee_raw;     // exact statistic, or a lower bound when !resolved
+    double p0;         // P[0] = prod(1-p_i) at the end of the sweep (PB only; K estimate)
+    uint32_t processed;  // bases swept before a (warp-wide) early exit
+    int ns;
+    bool has_n;
+    bool resolved;
+    bool numeric;
+};
+
+__device__ __forceinline__ int pick_rung(const FilterArgs &a, int kneed)
+{
+    int b = a.rung + 1 > a.min_rung ? a.rung + 1 : a.min_rung;
+    while (b < NB - 1 && rung_cap(b) < kneed) b++;
+    return b;
+}
+
+// Called by all 32 lanes of a warp (convergent).  `valid` lanes carry a read.
+__device__ __forceinline__ void finish_read(const FilterArgs &a, bool valid, uint32_t r_local, const ReadGeom &g,
+                                            const ReadResult &res, uint32_t *s_cnt, uint32_t *s_hist, int lane)
+{
+    const double nsd = (double)res.ns;
+    double ee_fin = res.ee_raw;
+    if (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) ee_fin = __dadd_rn(ee_fin, nsd);   // moira.py:828
+    if (a.round_flag) ee_fin = floor(ee_fin);                                        // moira.py:831
+    const double cutoff = (a.thr_kind == MOIRA_THR_MAXERRORS) ? a.thr : __dmul_rn((double)g.eff, a.thr);  // :926 / :950
+    bool ok = ee_fin <= cutoff;
+    int reason = MOIRA_REASON_NONE;
+    if (a.truncate && g.len < a.truncate) reason = MOIRA_REASON_LENGTH;               // :872
+    else if (res.has_n && a.ambigs == MOIRA_AMBIGS_DISALLOW) reason = MOIRA_REASON_AMBIGS;  // :911
+
+    bool undecided = false;
+    if (!res.resolved && !res.numeric) {
+        // ee_raw is a lower bound.  The read is settled only if a decision is all that is asked
+        // for and the bound already exceeds the cutoff (or another rule rejects it anyway).
+        undecided = a.exact || (reason == MOIRA_REASON_NONE && ok);
+        ok = false;
+    }
+    if (reason != MOIRA_REASON_NONE) ok = false;
+    else if (!ok) reason = MOIRA_REASON_ERRORS;
+
+    bool numeric = res.numeric;
+    bool push = valid && undecided && a.allow_push && a.rung < NB - 1;
+    if (valid && undecided && !push) numeric = true;   // nowhere left to go (see MOIRA_ERR_UNRESOLVED)
+    if (numeric) { ok = false; if (reason == MOIRA_REASON_NONE) reason = MOIRA_REASON_ERRORS; }
+
+    // ---- escalate ---------------------------------------------------------------------------
+    int rung = 0;
+    if (push) {
+        double mu = res.p0 > 0.0 ? -log(res.p0) : 1.0e9;
+        if (res.processed < g.eff) mu *= (double)g.eff / (double)(res.processed ? res.processed : 1u);
+        double kn = mu + a.z * sqrt(mu) + 3.0;
+        if (!a.exact) {   // a decision needs at most floor(cutoff on the raw statistic) + 2 entries
+            double c = (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) ? cutoff - nsd : cutoff;
+            double kd = floor(c) + 2.0;
+            if (kd < kn) kn = kd;
+        }
+        int kneed = kn > 1.0e6 ? 1000000 : (int)kn;
+        rung = pick_rung(a, kneed);
+    }
+    unsigned pm = __ballot_sync(FULL, push);
+    if (push) {
+        unsigned peers = __match_any_sync(pm, rung);
+        int leader = __ffs(peers) - 1;
+        uint32_t basepos = 0;
+        if (lane == leader) basepos = atomicAdd(&a.queue_counts[rung], (uint32_t)__popc(peers));
+        basepos = __shfl_sync(peers, basepos, leader);
+        uint32_t pos = basepos + __popc(peers & ((1u << lane) - 1u));
+        if (pos < a.queue_cap) a.queues[(size_t)rung * a.queue_cap + pos] = r_local;
+    }
+    if (!valid || push) return;
+
+    // ---- write + count ----------------------------------------------------------------------
+    const bool lower = !res.resolved && !numeric;
+    const bool near_cut = res.resolved && !numeric && fabs(ee_fin - cutoff) <= 1e-12 * cutoff;
+    uint8_t fl = (ok ? MOIRA_FLAG_ACCEPT : 0) | (uint8_t)(reason << 1) | (lower ? MOIRA_FLAG_LOWER_BOUND : 0) |
+                 (res.has_n ? MOIRA_FLAG_HAS_N : 0) | (numeric ? MOIRA_FLAG_NUMERIC : 0) |
+                 (near_cut ? MOIRA_FLAG_NEAR_CUTOFF : 0);
+    const uint64_t r = a.base + r_local;
+    a.ee[r] = (a.ee_output == MOIRA_EE_FINAL) ? ee_fin : res.ee_raw;
+    if (a.ns) a.ns[r] = res.ns;
+    if (a.flags) a.flags[r] = fl;
+    atomicAdd(&s_cnt[MOIRA_CNT_READS], 1u);
+    atomicAdd(&s_cnt[ok ? MOIRA_CNT_ACCEPTED : (MOIRA_CNT_BAD_ERRORS + reason - 1)], 1u);
+    if (near_cut) atomicAdd(&s_cnt[MOIRA_CNT_NEAR_CUTOFF], 1u);
+    if (lower) atomicAdd(&s_cnt[MOIRA_CNT_LOWER_BOUND], 1u);
+    if (numeric) atomicAdd(&s_cnt[MOIRA_CNT_NUMERIC], 1u);
+    int bin = ee_fin >= 63.0 ? 63 : (ee_fin > 0.0 ? (int)ee_fin : 0);
+    atomicAdd(&s_hist[bin], 1u);
+}
+
+__device__ __forceinline__ void flush_counters(const FilterArgs &a, const uint32_t *s_cnt, const uint32_t *s_hist)
+{
+    if (!a.counters) return;
+    for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += blockDim.x) {
+        uint32_t v = i < 16 ? s_cnt[i] : s_hist[i - 16];
+        if (v) atomicAdd(&a.counters[i], (unsigned long long)v);
+    }
+}
+
+// bernoullimodule.c:233-254: cumulative sum in index order, strict '>' against 1-alpha, then
+// interpolate().  j* == 0 gives 0 (the interpolation is negative there and clamps, :173-176).
+template <int K>
+__device__ __forceinline__ bool cdf_quantile(const double (&P)[K], double oma, double &ee)
+{
+    double acc = P[0];
+    if (acc > oma) { ee = 0.0; return true; }
+#pragma unroll
+    for (int j = 1; j < K; j++) {
+        double prev = acc;
+        acc = __dadd_rn(prev, P[j]);
+        if (acc > oma) {
+            ee = __dadd_rn((double)(j - 1), __ddiv_rn(__dsub_rn(oma, prev), __dsub_rn(acc, prev)));
+            return true;
+        }
+    }
+    ee = (double)(K - 1);   // j* >= K  =>  ee >= K-1
+    return false;
+}
+
+// ==================================================================================================
+// thread-per-read kernels
+// ==================================================================================================
+// MODE 0: Poisson-binomial with K entries.  MODE 1: Lambda accumulation (K ignored).
+template <int K, int MODE, bool EQP>
+__global__ void __launch_bounds__(TPR_THREADS, 1) tpr_kernel(const FilterArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + TPR_OFF_CNT);
+    uint32_t *s_hist = s_cnt + 16;
+
+    // ---- one-time setup: replicated lookup table, barriers, counters ----
+    constexpr bool PL = EQP || MODE == 1;   // table holds p only (8 B entries, 16 replicas)
+    if (PL) {
+        double *lut = reinterpret_cast<double *>(smem);
+        for (int i = threadIdx.x; i < 256 * 16; i += TPR_THREADS) lut[i] = a.lut_p[i >> 4];
+    } else {
+        double2 *lut = reinterpret_cast<double2 *>(smem);
+        for (int i = threadIdx.x; i < 256 * 8; i += TPR_THREADS) lut[i] = make_double2(a.lut_q[i >> 3], a.lut_e[i >> 3]);
+    }
+    for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += TPR_THREADS) s_cnt[i] = 0;
+    const uint32_t bar0 = smem_u32(smem + TPR_OFF_BAR) + warp * 16;
+    if (lane == 0) {
+        mbar_init(bar0, 32);
+        mbar_init(bar0 + 8, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t lut_lane = smem_u32(smem) + (PL ? (lane & 15) * 8 : (lane & 7) * 16);
+    const uint32_t stage0 = smem_u32(smem + TPR_OFF_STAGE) + warp * 2 * STAGE_BYTES + lane * ROW_STRIDE;
+
+    const uint32_t count = a.queue ? *a.queue_count : a.n;
+    const uint32_t n_tiles = (count + 31) >> 5;
+    const uint32_t total_warps = gridDim.x * TPR_WARPS;
+    uint32_t tile = blockIdx.x * TPR_WARPS + warp;
+    uint32_t it = 0;   // stage jobs issued == consumed so far by this warp
+
+    auto tile_read = [&](uint32_t t, bool &valid, uint32_t &r_local, ReadGeom &g) {
+        uint32_t i = t * 32 + lane;
+        valid = t < n_tiles && i < count;
+        r_local = 0;
+        g.off = 0; g.len = 0; g.eff = 0;
+        if (valid) {
+            r_local = a.queue ? a.queue[i] : i;
+            g = read_geom(a, r_local);
+        }
+    };
+    // stage job (read geometry g, chunk c) into stage `s`
+    auto issue = [&](const ReadGeom &g, uint32_t c, uint32_t s) {
+        const uint32_t bar = bar0 + (s & 1) * 8;
+        const uint32_t padded = (g.eff + 15u) & ~15u;
+        const uint32_t begin = c * CHUNK;
+        uint32_t bytes = padded > begin ? padded - begin : 0u;
+        if (bytes > CHUNK) bytes = CHUNK;
+        if (bytes) {
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_g2s(stage0 + (s & 1) * STAGE_BYTES, a.slab + g.off + begin, bytes, bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    };
+
+    bool valid, nvalid;
+    uint32_t r_local, nr_local;
+    ReadGeom g, ng;
+    tile_read(tile, valid, r_local, g);
+    if (tile < n_tiles) issue(g, 0, it);
+
+    while (tile < n_tiles) {
+        const uint32_t next_tile = tile + total_warps;
+        tile_read(next_tile, nvalid, nr_local, ng);
+        const uint32_t maxeff = __reduce_max_sync(FULL, g.eff);
+        const uint32_t nch = (maxeff + CHUNK - 1) / CHUNK;
+
+        double P[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) P[j] = 0.0;
+        if (MODE == 0) P[0] = 1.0;
+        int ns = 0;
+        bool has_n = false;
+        uint32_t processed = 0;
+
+        if (nch == 0) {   // tile of empty reads: its (empty) stage job still has to be consumed
+            if (next_tile < n_tiles) issue(ng, 0, it + 1);
+            mbar_wait(bar0 + (it & 1) * 8, (it >> 1) & 1);
+            it++;
+        }
+        for (uint32_t c = 0; c < nch; c++) {
+            if (c + 1 < nch) issue(g, c + 1, it + 1);
+            else if (next_tile < n_tiles) issue(ng, 0, it + 1);
+            mbar_wait(bar0 + (it & 1) * 8, (it >> 1) & 1);
+            const uint32_t row = stage0 + (it & 1) * STAGE_BYTES;
+            it++;
+
+            const uint32_t cbeg = c * CHUNK;
+            const uint32_t cend = maxeff - cbeg < CHUNK ? maxeff - cbeg : CHUNK;   // warp-uniform
+            for (uint32_t v = 0; v < cend; v += 16) {
+                uint4 q4 = lds128(row + v);
+                const int rem = (int)g.eff - (int)(cbeg + v);
+                uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+                if (rem < 16) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) w[i] = mask_word(w[i], rem - 4 * i);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    count_marks(w[i], ns, has_n);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        // LUT byte offset = Q * 128
+                        uint32_t sh = (b == 0) ? (w[i] << 7) : (w[i] >> (8 * b - 7));
+                        uint32_t addr = lut_lane + (sh & 0x7F80u);
+                        if (MODE == 0) {
+                            double q, e;
+                            if (EQP) {
+                                e = lds_f64(addr);
+                                q = __dsub_rn(1.0, e);                 // (1 - p), bernoullimodule.c:140
+                            } else {
+                                double2 qe = lds_f64x2(addr);
+                                q = qe.x; e = qe.y;
+                            }
+#pragma unroll
+                            for (int j = K - 1; j >= 1; j--)
+                                P[j] = __dadd_rn(__dmul_rn(q, P[j]), __dmul_rn(e, P[j - 1]));
+                            P[0] = __dmul_rn(q, P[0]);
+                        } else {
+                            double p = lds_f64(addr);
+                            P[0] = __dadd_rn(P[0], p);                     // moira.py:1663, in index order
+                        }
+                    }
+                }
+            }
+            processed = cbeg + cend;
+            if (MODE == 0 && c + 1 < nch) {
+                // Early exit: sum_{j<K} P_k[j] never increases with k, so once it is safely below
+                // 1-alpha these K entries cannot reach the quantile.  Only taken warp-wide.
+                double tracked = P[0];
+#pragma unroll
+                for (int j = 1; j < K; j++) tracked += P[j];
+                bool dead = !valid || tracked < a.oma - 1e-9 || processed >= g.eff;
+                bool certain = !valid || tracked < a.oma - 1e-9;
+                if (__all_sync(FULL, dead) && __any_sync(FULL, valid && certain)) {
+                    // only leave if no lane could still resolve: lanes that are merely finished
+                    // (processed >= eff) are unaffected by the skipped (all padding) chunks.
+                    mbar_wait(bar0 + (it & 1) * 8, (it >> 1) & 1);   // drain the prefetched chunk
+                    it++;
+                    if (next_tile < n_tiles) issue(ng, 0, it);
+                    break;
+                }
+            }
+        }
+
+        // ---- per-read epilogue ----
+        ReadResult res;
+        res.ns = ns;
+        res.has_n = has_n;
+        res.numeric = false;
+        res.processed = processed < g.eff ? processed : g.eff;
+        if (MODE == 0) {
+            res.p0 = P[0];
+            res.resolved = cdf_quantile<K>(P, a.oma, res.ee_raw);
+            if (res.processed < g.eff) { res.resolved = false; res.ee_raw = (double)(K - 1); }
+        } else {
+            res.p0 = 1.0;
+            const double lam = P[0];
+            if (a.mode == MOIRA_MODE_EXPECTED_ERROR) {
+                res.ee_raw = lam;
+                res.resolved = true;
+            } else {
+                // moira.py:1668-1677.  Decision mode needs terms j = 0 .. floor(c)+1 only.
+                int jlim = MOIRA_FACT_N - 1;
+                if (!a.exact) {
+                    double cutoff = (a.thr_kind == MOIRA_THR_MAXERRORS) ? a.thr : __dmul_rn((double)g.eff, a.thr);
+                    if (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) cutoff -= (double)ns;
+                    double jl = floor(cutoff) + 1.0;
+                    if (jl < (double)jlim) jlim = jl < 0.0 ? -1 : (int)jl;
+                }
+                const double el = exp(-lam);
+                double acc = 0.0, prev = 0.0;
+                res.resolved = false;
+                res.ee_raw = jlim > 0 ? (double)jlim : 0.0;
+                for (int j = 0; valid && j <= jlim; j++) {
+                    double pw = pow(lam, (double)j);
+                    if (isinf(pw)) { res.numeric = true; break; }     // reference raises OverflowError here
+                    double pmf = __ddiv_rn(__dmul_rn(el, pw), c_fact[j]);
+                    prev = acc;
+                    acc = __dadd_rn(prev, pmf);
+                    if (acc > a.oma) {
+                        double e = __dadd_rn((double)(j - 1), __ddiv_rn(__dsub_rn(a.oma, prev), __dsub_rn(acc, prev)));
+                        res.ee_raw = e < 0.0 ? 0.0 : e;
+                        res.resolved = true;
+                        break;
+                    }
+                }
+                if (!res.resolved && !res.numeric && (a.exact || jlim == MOIRA_FACT_N - 1)) res.numeric = true;
+            }
+        }
+        finish_read(a, valid, r_local, g, res, s_cnt, s_hist, lane);
+
+        tile = next_tile;
+        valid = nvalid; r_local = nr_local; g = ng;
+    }
+    __syncthreads();
+    flush_counters(a, s_cnt, s_hist);
+}
+
+// ==================================================================================================
+// warp-per-read: K = 32*M entries, lane l owns P[l*M + m]
+// ==================================================================================================
+template <int M>
+__global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
+{
+    __shared__ double2 s_lut[256];
+    __shared__ uint32_t s_cnt[16 + MOIRA_N_HIST];
+    for (int i = threadIdx.x; i < 256; i += WPR_THREADS) s_lut[i] = make_double2(a.lut_q[i], a.lut_e[i]);
+    for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += WPR_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    uint32_t *s_hist = s_cnt + 16;
+    const int lane = threadIdx.x & 31;
+    const uint32_t count = *a.queue_count < a.queue_cap ? *a.queue_count : a.queue_cap;
+    const uint32_t total_warps = gridDim.x * (WPR_THREADS / 32);
+    constexpr int K = 32 * M;
+
+    for (uint32_t i = blockIdx.x * (WPR_THREADS / 32) + (threadIdx.x >> 5); i < count; i += total_warps) {
+        const uint32_t r_local = a.queue[i];
+        const ReadGeom g = read_geom(a, r_local);
+        const uint8_t *row = a.slab + g.off;
+        double P[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) P[m] = 0.0;
+        if (lane == 0) P[0] = 1.0;
+        int ns = 0;
+        bool has_n = false;
+        bool dead = false;
+        uint32_t pos = 0;
+        uint4 cur = make_uint4(0xFDFDFDFDu, 0xFDFDFDFDu, 0xFDFDFDFDu, 0xFDFDFDFDu);
+        if (g.eff) cur = __ldg(reinterpret_cast<const uint4 *>(row));
+        for (; pos < g.eff && !dead; pos += 16) {
+            uint4 nxt = cur;
+            if (pos + 16 < g.eff) nxt = __ldg(reinterpret_cast<const uint4 *>(row + pos + 16));
+            const int rem = (int)g.eff - (int)pos;
+            uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+            if (rem < 16) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] = mask_word(w[k], rem - 4 * k);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                count_marks(w[k], ns, has_n);
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t q8 = (w[k] >> (8 * b)) & 0xFFu;
+                    if (q8 >= 0xFDu) continue;               // warp-uniform: padding / N / n leave P untouched
+                    const double2 qe = s_lut[q8];
+                    double up = __shfl_up_sync(FULL, P[M - 1], 1);
+                    if (lane == 0) up = 0.0;
+#pragma unroll
+                    for (int m = M - 1; m >= 1; m--)
+                        P[m] = __dadd_rn(__dmul_rn(qe.x, P[m]), __dmul_rn(qe.y, P[m - 1]));
+                    P[0] = __dadd_rn(__dmul_rn(qe.x, P[0]), __dmul_rn(qe.y, up));
+                }
+            }
+            cur = nxt;
+            if (((pos >> 4) & 3) == 3) {   // every 64 bases: can these K entries still reach 1-alpha?
+                double t = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; m++) t += P[m];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+                dead = t < a.oma - 1e-9;
+            }
+        }
+        const uint32_t processed = pos < g.eff ? pos : g.eff;
+
+        // cumulative sum in index order across lanes (bernoullimodule.c:233-244)
+        double acc = 0.0, prev = 0.0, ee = (double)(K - 1);
+        bool found = false;
+        if (!dead) {
+            for (int l = 0; l < 32 && !found; l++) {
+                double my_prev = 0.0, my_acc = acc;
+                int my_j = -1;
+                if (lane == l) {
+#pragma unroll
+                    for (int m = 0; m < M; m++) {
+                        if (my_j < 0) {
+                            double p2 = my_acc;
+                            my_acc = __dadd_rn(p2, P[m]);    // acc[0] = 0 + P[0] == P[0] bitwise
+                            if (my_acc > a.oma) { my_j = l * M + m; my_prev = p2; }
+                        }
+                    }
+                }
+                acc = __shfl_sync(FULL, my_acc, l);
+                int j = __shfl_sync(FULL, my_j, l);
+                if (j >= 0) {
+                    prev = __shfl_sync(FULL, my_prev, l);
+                    found = true;
+                    ee = (j == 0) ? 0.0
+                                  : __dadd_rn((double)(j - 1), __ddiv_rn(__dsub_rn(a.oma, prev), __dsub_rn(acc, prev)));
+                }
+            }
+        }
+        ReadResult res;
+        res.ee_raw = ee;
+        res.p0 = __shfl_sync(FULL, P[0], 0);
+        res.processed = processed;
+        res.ns = ns;
+        res.has_n = has_n;
+        res.resolved = found;
+        res.numeric = false;
+        finish_read(a, lane == 0, r_local, g, res, s_cnt, s_hist, lane);
+    }
+    __syncthreads();
+    flush_counters(a, s_cnt, s_hist);
+}
+
+// ==================================================================================================
+// block-per-read, P in shared memory: any K up to BLK_CAP (last rung)
+// ==================================================================================================
+__global__ void __launch_bounds__(BLK_THREADS) blk_kernel(const FilterArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    double *P = reinterpret_cast<double *>(smem);
+    double2 *s_lut = reinterpret_cast<double2 *>(smem + (size_t)BLK_CAP * 8);
+    __shared__ uint32_t s_cnt[16 + MOIRA_N_HIST];
+    __shared__ double s_res[4];
+    __shared__ int s_j;
+    for (int i = threadIdx.x; i < 256; i += BLK_THREADS) s_lut[i] = make_double2(a.lut_q[i], a.lut_e[i]);
+    for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += BLK_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    uint32_t *s_hist = s_cnt + 16;
+    const int lane = threadIdx.x & 31;
+    const uint32_t count = *a.queue_count < a.queue_cap ? *a.queue_count : a.queue_cap;
+
+    for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+        const uint32_t r_local = a.queue[i];
+        const ReadGeom g = read_geom(a, r_local);
+        const uint8_t *row = a.slab + g.off;
+        const int K = (int)(g.eff + 1 < (uint32_t)BLK_CAP ? g.eff + 1 : (uint32_t)BLK_CAP);
+        for (int j = threadIdx.x; j < K; j += BLK_THREADS) P[j] = j == 0 ? 1.0 : 0.0;
+        __syncthreads();
+        int ns = 0, nn = 0;   // nn = non-N bases swept so far: entries above nn are still zero
+        bool has_n = false;
+        for (uint32_t pos = 0; pos < g.eff; pos++) {
+            const uint32_t q8 = row[pos];
+            if (q8 >= 0xFEu) { ns++; has_n |= (q8 == 0xFFu); continue; }
+            if (q8 == 0xFDu) continue;
+            const double2 qe = s_lut[q8];
+            const int hi = nn + 1 < K - 1 ? nn + 1 : K - 1;
+            for (int top = hi; top >= 0; top -= BLK_THREADS) {
+                const int j = top - (int)threadIdx.x;
+                double nv = 0.0;
+                if (j >= 0) {
+                    double pj = P[j];
+                    double pm = j > 0 ? P[j - 1] : 0.0;
+                    nv = j > 0 ? __dadd_rn(__dmul_rn(qe.x, pj), __dmul_rn(qe.y, pm)) : __dmul_rn(qe.x, pj);
+                }
+                __syncthreads();
+                if (j >= 0) P[j] = nv;
+                __syncthreads();
+            }
+            nn++;
+        }
+        if (threadIdx.x == 0) {
+            double acc = 0.0, prev = 0.0;
+            int js = -1;
+            for (int j = 0; j < K; j++) {
+                prev = acc;
+                acc = __dadd_rn(prev, P[j]);
+                if (acc > a.oma) { js = j; break; }
+            }
+            s_j = js;
+            s_res[0] = prev;
+            s_res[1] = acc;
+            s_res[2] = P[0];
+        }
+        __syncthreads();
+        ReadResult res;
+        const int js = s_j;
+        res.resolved = js >= 0;
+        res.ee_raw = js < 0 ? (double)(K - 1)
+                   : js == 0 ? 0.0
+                             : __dadd_rn((double)(js - 1), __ddiv_rn(__dsub_rn(a.oma, s_res[0]), __dsub_rn(s_res[1], s_res[0])));
+        res.p0 = s_res[2];
+        res.processed = g.eff;
+        res.ns = ns;
+        res.has_n = has_n;
+        res.numeric = false;
+        if (threadIdx.x < 32) finish_read(a, threadIdx.x == 0, r_local, g, res, s_cnt, s_hist, lane);
+        __syncthreads();
+    }
+    __syncthreads();
+    flush_counters(a, s_cnt, s_hist);
+}
+
+// ==================================================================================================
+// FP64 issue-rate probe: per thread 4 independent copies of the K=4 update (7 DMUL + 4 DADD).
+// ==================================================================================================
+__global__ void __launch_bounds__(512) fp64_peak_kernel(int iters, double *sink, double p)
+{
+    double P[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) P[c][j] = 1.0 / (1.0 + threadIdx.x + c + j);
+    double e = p;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            double q = __dsub_rn(1.0, e);
+#pragma unroll
+            for (int j = 3; j >= 1; j--) P[c][j] = __dadd_rn(__dmul_rn(q, P[c][j]), __dmul_rn(e, P[c][j - 1]));
+            P[c][0] = __dmul_rn(q, P[c][0]);
+        }
+        e = __dmul_rn(e, 1.0000001);   // keeps the compiler from hoisting q; 1 extra DMUL per iteration (counted)
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s += P[c][j];
+    if (s == 123.456) sink[0] = s;
+}
+
+template <int K>
+int launch_tpr_pb(const FilterArgs &a, const LaunchCfg &cfg)
+{
+    if (a.e_equals_p) tpr_kernel<K, 0, true><<<cfg.sm_count, TPR_THREADS, TPR_SMEM, cfg.stream>>>(a);
+    else tpr_kernel<K, 0, false><<<cfg.sm_count, TPR_THREADS, TPR_SMEM, cfg.stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <int K>
+int init_tpr()
+{
+    if (cudaFuncSetAttribute(tpr_kernel<K, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(tpr_kernel<K, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    return 0;
+}
+
+}  // namespace
+
+#define MOIRA_FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(16) X(20) X(24) X(32)
+
+int max_first_pass_k() { return 32; }
+
+int kernels_init(int)
+{
+#define X(k) if (init_tpr<k>()) return -1;
+    MOIRA_FOR_EACH_K(X)
+#undef X
+    if (cudaFuncSetAttribute(tpr_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(tpr_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM) != cudaSuccess) return -1;
+    return 0;
+}
+
+int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, const char **name)
+{
+    static const char *names[] = {"pb_tpr<K=2>", "pb_tpr<K=3>", "pb_tpr<K=4>", "pb_tpr<K=5>", "pb_tpr<K=6>",
+                                  "pb_tpr<K=7>", "pb_tpr<K=8>", "pb_tpr<K=10>", "pb_tpr<K=12>", "pb_tpr<K=16>",
+                                  "pb_tpr<K=20>", "pb_tpr<K=24>", "pb_tpr<K=32>"};
+    int idx = 0;
+#define X(k)                                                   \
+    if (k_wanted <= k) {                                       \
+        if (name) *name = names[idx];                          \
+        return launch_tpr_pb<k>(a, cfg) ? -1 : k;              \
+    }                                                          \
+    idx++;
+    MOIRA_FOR_EACH_K(X)
+#undef X
+    if (name) *name = names[12];
+    return launch_tpr_pb<32>(a, cfg) ? -1 : 32;
+}
+
+int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name)
+{
+    if (name) *name = "lambda_tpr";
+    if (a.e_equals_p) tpr_kernel<1, 1, true><<<cfg.sm_count, TPR_THREADS, TPR_SMEM, cfg.stream>>>(a);
+    else tpr_kernel<1, 1, false><<<cfg.sm_count, TPR_THREADS, TPR_SMEM, cfg.stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg)
+{
+    FilterArgs a = a0;
+    a.rung = b;
+    a.queue = a0.queues + (size_t)b * a0.queue_cap;
+    a.queue_count = a0.queue_counts + b;
+    const int wpr_grid = cfg.sm_count * 4;
+    switch (b) {
+    case 0: return launch_tpr_pb<8>(a, cfg);
+    case 1: return launch_tpr_pb<16>(a, cfg);
+    case 2: return launch_tpr_pb<32>(a, cfg);
+    case 3: wpr_kernel<2><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 4: wpr_kernel<4><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 5: wpr_kernel<8><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 6: wpr_kernel<16><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 7: wpr_kernel<32><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    default: blk_kernel<<<cfg.sm_count, BLK_THREADS, BLK_SMEM, cfg.stream>>>(a); break;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, double *ops_out)
+{
+    const int blocks = sm_count * 2, threads = 512;
+    fp64_peak_kernel<<<blocks, threads, 0, s>>>(iters, d_sink, 1e-3);
+    // per iteration and thread: 4 x (1 DSUB + 7 DMUL + 3 DADD) + 1 DMUL
+    *ops_out = (double)blocks * threads * (double)iters * 45.0;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace moira

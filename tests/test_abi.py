@@ -1,0 +1,125 @@
+"""CPU: the C-ABI library loads, exports what include/moira_b200.h declares, its host-side pieces
+(tables, packers, parsers, validation) agree with the oracle, and it fails loudly without a GPU."""
+import ctypes
+import gzip
+import os
+import re
+
+import numpy as np
+import pytest
+
+import moira_b200
+from moira_b200 import _lib as L
+from oracle import py_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_all_exported():
+    hdr = open(os.path.join(ROOT, "include", "moira_b200.h")).read()
+    declared = re.findall(r"^MOIRA_API [^;(]*?\b(moira_\w+)\(", hdr, re.M)
+    assert len(declared) >= 20
+    assert sorted(declared) == sorted(L.EXPORTS)
+    for name in declared:
+        assert hasattr(L.lib, name), name
+    assert L.lib.moira_abi_version() == int(re.search(r"#define MOIRA_ABI_VERSION (\d+)", hdr).group(1))
+
+
+def test_header_constants_match_binding():
+    hdr = open(os.path.join(ROOT, "include", "moira_b200.h")).read()
+    consts = dict(re.findall(r"^#define MOIRA_(\w+)\s+(-?(?:0x)?[0-9A-Fa-f]+)\b", hdr, re.M))
+    for k, v in consts.items():
+        if hasattr(L, k):
+            assert getattr(L, k) == int(v, 0), k
+    assert ctypes.sizeof(L.Params) == 48
+
+
+def test_lut_matches_oracle_tables():
+    p, q, e, eqp = moira_b200.build_lut()
+    op, oq, oe = np.zeros(256), np.zeros(256), np.zeros(256)
+    po.oracle_lib().oracle_tables(op.ctypes.data, oq.ctypes.data, oe.ctypes.data)
+    assert np.array_equal(p[1:0xFD], op[1:0xFD])
+    assert np.array_equal(q[1:0xFD], oq[1:0xFD])
+    assert np.array_equal(e[1:0xFD], oe[1:0xFD])
+    assert (p[0], q[0], e[0]) == (op[1], oq[1], oe[1])             # Q == 0 -> 1
+    assert np.all(p[0xFD:] == 0) and np.all(q[0xFD:] == 1) and np.all(e[0xFD:] == 0)
+    assert eqp is True                                             # glibc: e == p bitwise
+
+
+def test_pack_reads_matches_oracle_packer(forward_records):
+    seqs = [s for _, s, _ in forward_records[:200]] + ["ACGTNnacgt", "N", "a"]
+    quals = [q for _, _, q in forward_records[:200]] + [[0, 1, 2, 3, 4, 5, 93, 252, 40, -3], [7], [9]]
+    for lower in (True, False):
+        slab, off, ln = moira_b200.pack_reads(seqs, quals, lower_n_ambiguous=lower)
+        qs = [[max(v, 0) for v in q] for q in quals]
+        oslab, ooff, oln = po.pack_records(seqs, qs, lower_n_ambiguous=lower)
+        assert np.array_equal(off, ooff) and np.array_equal(ln, oln)
+        assert np.array_equal(slab, oslab[:slab.size])
+
+
+def test_pack_rejects_unrepresentable_quality():
+    with pytest.raises(moira_b200.MoiraError) as ei:
+        moira_b200.pack_reads(["AC"], [[10, 253]])
+    assert ei.value.code == L.ERR_BAD_QUALITY
+
+
+def test_parse_fastq_matches_oracle_parser(forward_records):
+    text = gzip.open(os.path.join(ROOT, "tests", "golden", "test1.fastq.gz"), "rb").read()
+    slab, off, ln, hoff, hlen, soff = moira_b200.parse_fastq(text, 33, True)
+    assert len(ln) == len(forward_records) == 1000
+    seqs = [s for _, s, _ in forward_records]
+    quals = [q for _, _, q in forward_records]
+    oslab, ooff, oln = po.pack_records(seqs, [[max(v, 0) for v in q] for q in quals])
+    assert np.array_equal(off, ooff) and np.array_equal(ln, oln) and np.array_equal(slab, oslab[:slab.size])
+    for i in (0, 1, 17, 999):
+        h = text[int(hoff[i]):int(hoff[i]) + int(hlen[i])].decode().replace(":", "_")
+        assert h == forward_records[i][0]
+        assert text[int(soff[i]):int(soff[i]) + int(ln[i])].decode() == seqs[i]
+
+
+def test_parse_fastq_errors():
+    for bad, word in ((b"@r1\nACGT\n+\nIII\n", "LengthMismatchError"), (b"@r1\n\n+\nIII\n", "EmptySeqError"),
+                      (b"@r1\nACG\n+\n\n", "EmptyQualError")):
+        with pytest.raises(moira_b200.MoiraError) as ei:
+            moira_b200.parse_fastq(bad)
+        assert ei.value.code == L.ERR_PARSE and word in ei.value.message
+    slab, off, ln, *_ = moira_b200.parse_fastq(b"@r1 x\tb\n ACGN \n+\nII#I\n@partial\nAC\n")
+    assert list(ln) == [4] and list(slab[:4]) == [40, 40, 2, 0xFF]
+
+
+def test_shim_validation_is_the_reference_binding_s():
+    # bernoullimodule.c:74-90: TypeError for wrong types, ValueError for alpha / length -- raised
+    # before any GPU work, so checkable on CPU
+    from moira_b200 import bernoulli
+    with pytest.raises(ValueError, match="Alpha must be between 0 and 1"):
+        bernoulli.calculate_errors_PB("ACGT", [30] * 4, 0.0)
+    with pytest.raises(ValueError, match="Alpha must be between 0 and 1"):
+        bernoulli.calculate_errors_PB("ACGT", [30] * 4, 1.0)
+    with pytest.raises(ValueError, match="same length"):
+        bernoulli.calculate_errors_PB("ACGT", [30] * 3, 0.005)
+    with pytest.raises(TypeError):
+        bernoulli.calculate_errors_PB("ACGT", (30, 30, 30, 30), 0.005)
+    with pytest.raises(TypeError):
+        bernoulli.calculate_errors_PB(b"ACGT", [30] * 4, 0.005)
+    with pytest.raises(TypeError):
+        bernoulli.calculate_errors_PB("ACGT", [30, 30, 3.5, 30], 0.005)
+    import bernoulli as top
+    assert top.calculate_errors_PB is bernoulli.calculate_errors_PB
+
+
+def test_no_silent_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(moira_b200.MoiraError) as ei:
+        moira_b200.Context(0)
+    assert ei.value.code == L.ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "moira_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                for needle in ("import oracle", "from oracle", "liboracle", "oracle/", "py_oracle", "_ref"):
+                    assert needle not in src, (f, needle)

@@ -1,0 +1,289 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the committed
+golden vectors.  Bit-exact for Poisson-binomial ee / Ns / decisions; the Poisson mode within the
+stated FP64 tolerance (device exp/pow vs glibc), decisions identical outside the 1e-12 band."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import moira_b200
+from moira_b200 import FilterParams, synth
+from moira_b200 import _lib as L
+from oracle import py_oracle as po
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _q1(kat):
+    return [ord(c) - kat["fastq_offset"] for c in kat["testQual1_ascii"]]
+
+
+def _has_n(slab, off, ln):
+    return np.array([(slab[int(o):int(o) + int(l)] == 0xFF).any() for o, l in zip(off, ln)], dtype=bool)
+
+
+def _check_decisions(res, ee_raw, ns, ln, has_n, params, exact=True):
+    ok, reason, eef = po.decide_batch(
+        ee_raw, ns, ln, has_n, thr_kind="maxerrors" if params.maxerrors else "uncert",
+        thr=params.maxerrors if params.maxerrors else params.uncert, ambigs=params.ambigs,
+        round_flag=params.round, truncate=params.truncate)
+    near = res.near_cutoff
+    assert np.array_equal(res.accept[~near], ok[~near])
+    assert np.array_equal(res.reason[~near], reason[~near])
+    return ok, reason, eef
+
+
+# ---- the reference's own known answers, through the drop-in `bernoulli` module -------------------
+def test_kat_through_bernoulli_shim(kat):
+    import bernoulli
+    assert bernoulli.calculate_errors_PB(kat["testSeq1"], _q1(kat), 0.005) == tuple(kat["pb_expected"])   # test_moira.py:43
+    fp = kat["forward_process"]
+    ee, ns = bernoulli.calculate_errors_PB(fp["seq"], fp["quals"], 0.005)
+    assert ee + ns == fp["ee"]                                                                         # test_moira.py:127
+    pp = kat["paired_process"]
+    ee, ns = bernoulli.calculate_errors_PB(pp["seq"], pp["quals"], 0.005)
+    assert ee + ns == pp["ee"]                                                                         # test_moira.py:128
+    assert bernoulli.calculate_errors_PB("", [], 0.005) == (0.0, 0)
+    assert bernoulli.calculate_errors_PB("NNnN", [2, 2, 2, 2], 0.005) == (0.0, 4)
+    assert bernoulli.calculate_errors_PB("A", [40], 0.005) == (0.0, 0)
+    assert bernoulli.calculate_errors_PB("AC", [0, 0], 0.3) == po.pb_c("AC", [1, 1], 0.3)
+    with pytest.raises(ValueError):
+        bernoulli.calculate_errors_PB("AC", [10, 300], 0.005)
+
+
+def test_reference_binary_outputs_synthetic(ctx, ref_outputs):
+    """4000 seeded reads (N/n, Q=0, L=1..600, six alphas): ee and Ns bit-equal to the unmodified
+    reference binary's outputs stored in tests/golden/ref_outputs.npz."""
+    slab, off, ln = ref_outputs["syn_slab"], ref_outputs["syn_offsets"], ref_outputs["syn_lengths"]
+    alphas = ref_outputs["syn_alpha"]
+    for a in np.unique(alphas):
+        sel = np.nonzero(alphas == a)[0]
+        p = FilterParams(alpha=float(a), exact_ee=True)
+        res = ctx.filter_batch(slab, off[sel], ln[sel], p)
+        assert not res.numeric.any() and not res.lower_bound.any()
+        assert np.array_equal(res.ee, ref_outputs["syn_ee"][sel])
+        assert np.array_equal(res.ns, ref_outputs["syn_ns"][sel])
+        _check_decisions(res, res.ee, res.ns, ln[sel], _has_n(slab, off[sel], ln[sel]), p)
+        assert int(res.counters[L.CNT_READS]) == len(sel)
+        assert int(res.counters[L.CNT_ACCEPTED]) == int(res.accept.sum())
+
+
+def test_forward_fixture_full_pipeline_partition(ctx, forward_records, forward_names, ref_outputs):
+    """The reference's forward full-pipeline test (test_moira.py:74-87): fastq -> slab (C parser) ->
+    CUDA filter -> collapse -> 122 good / 365 bad uniques with identical member lists."""
+    text = gzip.open(os.path.join(ROOT, "tests", "golden", "test1.fastq.gz"), "rb").read()
+    slab, off, ln, hoff, hlen, soff = moira_b200.parse_fastq(text, 33, True)
+    p = FilterParams(exact_ee=True, ee_output="final")
+    res = ctx.filter_batch(slab, off, ln, p)
+    assert np.array_equal(res.ee - res.ns, ref_outputs["forward_ee"])          # raw ee bit-equal to the reference binary
+    uniques = {}
+    for i, (header, seq, _) in enumerate(forward_records):
+        u = uniques.get(seq)
+        if u is None:
+            uniques[seq] = {"rep": header, "ee": res.ee[i], "names": [header]}
+        elif res.ee[i] < u["ee"]:                                               # moira.py:466
+            u.update(rep=header, ee=res.ee[i])
+            u["names"].insert(0, header)
+        else:
+            u["names"].append(header)
+    good = {u["rep"]: u["names"] for s, u in uniques.items() if u["ee"] <= len(s) * 0.01}
+    bad = {u["rep"]: u["names"] for s, u in uniques.items() if not u["ee"] <= len(s) * 0.01}
+    assert good == forward_names["good"] and bad == forward_names["bad"]
+    # per-read device decision == decision on the representative's own ee
+    for i, (_, seq, _) in enumerate(forward_records):
+        assert bool(res.accept[i]) == bool(res.ee[i] <= len(seq) * 0.01)
+
+
+def test_golden_contigs(ctx, contigs, ref_outputs):
+    slab, off, ln = moira_b200.pack_reads([c["seq"] for c in contigs], [c["quals"] for c in contigs])
+    for exact in (True, False):
+        res = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact))
+        assert [bool(a) for a in res.accept] == [c["label"] == "good" for c in contigs]
+        sel = ~res.lower_bound
+        assert np.array_equal(res.ee[sel], ref_outputs["contigs_ee"][sel])
+        if exact:
+            assert sel.all()
+
+
+@pytest.mark.parametrize("profile,n,seed", [("v4", 20000, 1), ("v3v4", 6000, 2), ("mixed", 6000, 3), ("ccs", 300, 4)])
+def test_profiles_exact_and_decision_modes(ctx, profile, n, seed):
+    slab, off, ln = synth.generate(profile, n, seed)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    has_n = _has_n(slab, off, ln)
+    p = FilterParams(exact_ee=True)
+    res = ctx.filter_batch(slab, off, ln, p)
+    assert not res.numeric.any()
+    assert np.array_equal(res.ee, ee_o) and np.array_equal(res.ns, ns_o)
+    ok, reason, _ = _check_decisions(res, ee_o, ns_o, ln, has_n, p)
+    assert np.array_equal((res.flags & L.FLAG_HAS_N) != 0, has_n)
+    # decision mode: same partition; exact ee wherever it is not flagged as a lower bound
+    pd = FilterParams(exact_ee=False)
+    rd = ctx.filter_batch(slab, off, ln, pd)
+    assert np.array_equal(rd.accept, res.accept) and np.array_equal(rd.reason, res.reason)
+    lb = rd.lower_bound
+    assert np.array_equal(rd.ee[~lb], ee_o[~lb])
+    assert not rd.accept[lb].any() and np.all(rd.ee[lb] <= ee_o[lb])
+    assert int(rd.counters[L.CNT_ACCEPTED]) == int(ok.sum())
+    assert int(rd.counters[L.CNT_READS]) == n
+    hist = np.bincount(np.minimum(np.floor(res.ee + res.ns), 63).astype(int), minlength=64)
+    assert np.array_equal(res.counters[L.CNT_HIST:L.CNT_HIST + 64].astype(np.int64), hist)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(maxerrors=1.0), dict(maxerrors=3.5, round=True), dict(uncert=0.02, ambigs="ignore"),
+    dict(ambigs="disallow"), dict(truncate=200), dict(truncate=300, ambigs="disallow", round=True),
+    dict(uncert=0.2), dict(maxerrors=60.0), dict(alpha=0.2), dict(alpha=1e-9, uncert=0.05),
+])
+def test_decision_rules(ctx, kw):
+    """A10/A11: truncate, +Ns, floor, maxerrors/uncert, ambigs -- both modes, every rule."""
+    slab, off, ln = synth.generate("mixed", 3000, 11)
+    for exact in (True, False):
+        p = FilterParams(exact_ee=exact, **kw)
+        res = ctx.filter_batch(slab, off, ln, p)
+        eff = np.minimum(ln, p.truncate) if p.truncate else ln
+        ee_o, ns_o = po.pb_batch(slab, off, eff.astype(np.uint32), p.alpha)
+        has_n = _has_n(slab, off, eff)
+        _check_decisions(res, ee_o, ns_o, ln, has_n, p)
+        lb = res.lower_bound
+        assert np.array_equal(res.ee[~lb], ee_o[~lb]) and np.array_equal(res.ns, ns_o)
+        assert exact is False or not lb.any()
+        pf = FilterParams(exact_ee=exact, ee_output="final", **kw)
+        rf = ctx.filter_batch(slab, off, ln, pf)
+        _, _, eef = po.decide_batch(ee_o, ns_o, ln, has_n, thr_kind="maxerrors" if p.maxerrors else "uncert",
+                                    thr=p.maxerrors or p.uncert, ambigs=p.ambigs, round_flag=p.round, truncate=p.truncate)
+        assert np.array_equal(rf.ee[~lb], eef[~lb])
+
+
+def test_escalation_ladder_every_rung(ctx):
+    """Reads needing 1 .. >1024 PMF entries: thread-, warp- and block-per-read rungs all bit-exact."""
+    rng = np.random.default_rng(5)
+    seqs, quals = [], []
+    for L_, qlo, qhi in ((300, 30, 41), (300, 10, 20), (400, 3, 9), (600, 1, 4), (1500, 0, 3), (1500, 2, 6),
+                         (2600, 0, 2), (3000, 1, 3), (40, 0, 2), (5000, 25, 40)):
+        for _ in range(6):
+            seqs.append("".join(rng.choice(list("ACGTN"), size=L_, p=[.245, .245, .25, .25, .01])))
+            quals.append([int(v) for v in rng.integers(qlo, qhi, size=L_)])
+    slab, off, ln = moira_b200.pack_reads(seqs, quals)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    assert ee_o.max() > 1100 and ee_o.min() < 1
+    res = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=True))
+    assert not res.numeric.any() and not res.lower_bound.any()
+    assert np.array_equal(res.ee, ee_o) and np.array_equal(res.ns, ns_o)
+    # decision mode with a cutoff far above the first-pass K (maxerrors 700 -> needs the ladder too)
+    p = FilterParams(exact_ee=False, maxerrors=700.0)
+    rd = ctx.filter_batch(slab, off, ln, p)
+    ok, _, _ = po.decide_batch(ee_o, ns_o, ln, _has_n(slab, off, ln), thr_kind="maxerrors", thr=700.0,
+                               ambigs="treat_as_errors", round_flag=False, truncate=None)
+    assert np.array_equal(rd.accept, ok)
+
+
+def test_poisson_and_expected_error_modes(ctx, kat):
+    slab, off, ln = synth.generate("mixed", 1500, 21)
+    ee_o, ns_o, lam_o = po.poisson_batch(slab, off, ln, 0.005)
+    has_n = _has_n(slab, off, ln)
+    pe = FilterParams(error_calc="expected_error", exact_ee=True)
+    re_ = ctx.filter_batch(slab, off, ln, pe)
+    assert np.array_equal(re_.ee, lam_o) and np.array_equal(re_.ns, ns_o)      # sequential sum: bit-exact
+    _check_decisions(re_, lam_o, ns_o, ln, has_n, pe)
+    pp = FilterParams(error_calc="poisson", exact_ee=True)
+    rp = ctx.filter_batch(slab, off, ln, pp)
+    assert not rp.numeric.any()
+    assert np.allclose(rp.ee, ee_o, rtol=1e-12, atol=1e-13)                    # device exp/pow vs glibc: stated tolerance
+    ok, _, _ = _check_decisions(rp, ee_o, ns_o, ln, has_n, pp)
+    rd = ctx.filter_batch(slab, off, ln, FilterParams(error_calc="poisson", exact_ee=False))
+    near = rd.near_cutoff | rp.near_cutoff
+    assert np.array_equal(rd.accept[~near], ok[~near])
+    # the reference's own Poisson KAT (test_moira.py:44-45), to the stated tolerance
+    s, o, l = moira_b200.pack_reads([kat["testSeq1"]], [_q1(kat)], lower_n_ambiguous=False)
+    r1 = ctx.filter_batch(s, o, l, pp)
+    assert abs(r1.ee[0] - kat["poisson_expected"][0]) <= 1e-12 * kat["poisson_expected"][0]
+
+
+def test_edge_batches(ctx):
+    p = FilterParams()
+    r0 = ctx.filter_batch(np.zeros(16, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32), p)
+    assert r0.ee.size == 0 and int(r0.counters[L.CNT_READS]) == 0
+    # ragged: empty read, 1 base, 15/16/17 bases, all-N, garbage in the row padding
+    seqs = ["", "A", "A" * 15, "C" * 16, "G" * 17, "N" * 33, "ACGT" * 70]
+    quals = [[], [2], [30] * 15, [3] * 16, [40] * 17, [2] * 33, [38] * 280]
+    slab, off, ln = moira_b200.pack_reads(seqs, quals)
+    slab = slab.copy()
+    for o, l in zip(off, ln):
+        pad = (int(l) + 15) // 16 * 16 - int(l)
+        slab[int(o) + int(l):int(o) + int(l) + pad] = np.random.default_rng(1).integers(0, 256, pad)
+    ee_o = np.array([po.pb_c(s, q, 0.005)[0] for s, q in zip(seqs, quals)])
+    res = ctx.filter_batch(slab, off, ln, p)
+    assert np.array_equal(res.ee, ee_o)
+    assert list(res.ns) == [0, 0, 0, 0, 0, 33, 0]
+    with pytest.raises(moira_b200.MoiraError) as ei:
+        ctx.filter_batch(slab, off, ln, FilterParams(alpha=1.5))
+    assert ei.value.code == L.ERR_BAD_ALPHA
+    with pytest.raises(moira_b200.MoiraError):
+        ctx.filter_batch(slab, off + 3, ln, p)
+
+
+def test_device_resident_api_and_properties_at_scale(ctx):
+    """BASELINE config C2's shape at 2M reads, device-resident: decision mode == exact mode,
+    permutation invariance, counters == sums over flags, and a sampled oracle check."""
+    import torch
+    n = 2_000_000
+    dev = torch.device("cuda", 0)
+    slab = synth.generate_v4_device(n, 1234, dev)
+    ee = torch.empty(n, dtype=torch.float64, device=dev)
+    ns = torch.empty(n, dtype=torch.int32, device=dev)
+    fl = torch.empty(n, dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    outs = {}
+    for exact in (False, True):
+        cnt.zero_()
+        ctx.filter_device(slab.data_ptr(), None, None, synth.V4_STRIDE, synth.V4_LEN, n,
+                          FilterParams(exact_ee=exact), ee.data_ptr(), ns.data_ptr(), fl.data_ptr(),
+                          cnt.data_ptr(), stream)
+        torch.cuda.synchronize()
+        outs[exact] = (ee.cpu().numpy().copy(), ns.cpu().numpy().copy(), fl.cpu().numpy().copy(), cnt.cpu().numpy().copy())
+    (ee_d, ns_d, fl_d, c_d), (ee_x, ns_x, fl_x, c_x) = outs[False], outs[True]
+    assert np.array_equal(fl_d & 1, fl_x & 1) and np.array_equal(ns_d, ns_x)
+    lb = (fl_d & L.FLAG_LOWER_BOUND) != 0
+    assert np.array_equal(ee_d[~lb], ee_x[~lb]) and not ((fl_x & L.FLAG_LOWER_BOUND) != 0).any()
+    assert c_x[L.CNT_READS] == n and c_x[L.CNT_ACCEPTED] == int((fl_x & 1).sum()) == c_d[L.CNT_ACCEPTED]
+    assert 0.7 < c_x[L.CNT_ACCEPTED] / n < 0.9                      # ~80 % accepted
+    # sampled bit-exact check against the oracle
+    idx = np.random.default_rng(9).choice(n, 4000, replace=False)
+    rows = slab[torch.as_tensor(idx, device=dev)].cpu().numpy()
+    off = np.arange(len(idx), dtype=np.uint64) * synth.V4_STRIDE
+    ee_o, ns_o = po.pb_batch(rows.reshape(-1), off, np.full(len(idx), synth.V4_LEN, np.uint32), 0.005)
+    assert np.array_equal(ee_x[idx], ee_o) and np.array_equal(ns_x[idx], ns_o)
+    # permutation invariance (reads are independent, moira.py:455-487)
+    perm = torch.randperm(n, device=dev)
+    slab_p = slab[perm].contiguous()
+    cnt.zero_()
+    ctx.filter_device(slab_p.data_ptr(), None, None, synth.V4_STRIDE, synth.V4_LEN, n, FilterParams(exact_ee=True),
+                      ee.data_ptr(), ns.data_ptr(), fl.data_ptr(), cnt.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(ee.cpu().numpy(), ee_x[perm.cpu().numpy()])
+    assert np.array_equal(cnt.cpu().numpy(), c_x)
+
+
+def test_async_submit_wait_pinned(ctx):
+    slab, off, ln = synth.generate("v4", 50000, 77)
+    bufs, outs, tickets = [], [], []
+    p = FilterParams(exact_ee=False)
+    for k in range(3):
+        pb = moira_b200.PinnedBuffer(slab.nbytes)
+        pb.u8[:] = slab
+        out = moira_b200.FilterResult(np.empty(len(ln)), np.empty(len(ln), np.int32), np.empty(len(ln), np.uint8),
+                                      np.zeros(L.N_COUNTERS, np.uint64))
+        tickets.append(ctx.submit(pb.u8, off, ln, p, out))
+        bufs.append(pb)
+        outs.append(out)
+    for t in tickets:
+        ctx.wait(t)
+    ref = ctx.filter_batch(slab, off, ln, p)
+    for out in outs:
+        assert np.array_equal(out.ee, ref.ee) and np.array_equal(out.flags, ref.flags)
+        assert np.array_equal(out.counters, ref.counters)
+    for pb in bufs:
+        pb.free()
