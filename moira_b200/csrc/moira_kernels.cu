@@ -113,12 +113,22 @@ __device__ __forceinline__ uint32_t mask_word(uint32_t w, int nvalid)
     uint32_t keep = (1u << (8 * nvalid)) - 1u;
     return (w & keep) | (0xFDFDFDFDu & ~keep);
 }
-__device__ __forceinline__ void count_marks(uint32_t w, int &ns, bool &has_upper_n)
+// Bit 7 of every byte that is >= 0xFE ('n' / 'N' marker): 3 integer ops per word, no branch.
+__device__ __forceinline__ uint32_t mark_bits(uint32_t w)
 {
-    uint32_t ge = __vcmpgeu4(w, 0xFEFEFEFEu);   // 0xFF per byte that is 'n' (0xFE) or 'N' (0xFF)
-    if (ge) {
-        ns += __popc(ge) >> 3;
-        has_upper_n |= (__vcmpeq4(w, 0xFFFFFFFFu) != 0u);
+    return ((w & 0x7F7F7F7Fu) + 0x02020202u) & w & 0x80808080u;
+}
+// Bit 7 of every byte that is == 0xFF ('N').
+__device__ __forceinline__ uint32_t upper_n_bits(uint32_t w)
+{
+    return ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u;
+}
+__device__ __forceinline__ void count_marks4(const uint32_t (&w)[4], int &ns, bool &has_upper_n)
+{
+    const uint32_t m0 = mark_bits(w[0]), m1 = mark_bits(w[1]), m2 = mark_bits(w[2]), m3 = mark_bits(w[3]);
+    if (m0 | m1 | m2 | m3) {   // rare: only reads with ambiguous bases
+        ns += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        has_upper_n |= (upper_n_bits(w[0]) | upper_n_bits(w[1]) | upper_n_bits(w[2]) | upper_n_bits(w[3])) != 0u;
     }
 }
 
@@ -260,6 +270,50 @@ __device__ __forceinline__ bool cdf_quantile(const double (&P)[K], double oma, d
     return false;
 }
 
+// One staged chunk of one row (thread-per-read): `cend` bytes starting at shared address `row`,
+// of which the first `rem0` belong to the read (the rest is masked to padding).
+// MATH = false keeps only the N/n accounting (after a warp-wide early exit).
+template <int K, int MODE, bool PL, bool MATH>
+__device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t cend, int rem0, uint32_t lut_lane, double (&P)[K],
+                                            int &ns, bool &has_n)
+{
+    for (uint32_t v = 0; v < cend; v += 16) {
+        const uint4 q4 = lds128(row + v);
+        const int rem = rem0 - (int)v;
+        uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+        if (rem < 16) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[i] = mask_word(w[i], rem - 4 * i);
+        }
+        count_marks4(w, ns, has_n);
+        if (!MATH) continue;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t q8 = __byte_perm(w[i], 0u, 0x4440u + b);   // zero-extended byte b
+                const uint32_t addr = lut_lane + (q8 << 7);               // table row = Q * 128 bytes
+                if (MODE == 0) {
+                    double q, e;
+                    if (PL) {
+                        e = lds_f64(addr);
+                        q = __dsub_rn(1.0, e);                 // (1 - p), bernoullimodule.c:140
+                    } else {
+                        const double2 qe = lds_f64x2(addr);
+                        q = qe.x; e = qe.y;
+                    }
+#pragma unroll
+                    for (int j = K - 1; j >= 1; j--)
+                        P[j] = __dadd_rn(__dmul_rn(q, P[j]), __dmul_rn(e, P[j - 1]));
+                    P[0] = __dmul_rn(q, P[0]);
+                } else {
+                    P[0] = __dadd_rn(P[0], lds_f64(addr));     // moira.py:1663, in index order
+                }
+            }
+        }
+    }
+}
+
 // ==================================================================================================
 // thread-per-read kernels
 // ==================================================================================================
@@ -345,6 +399,7 @@ __global__ void __launch_bounds__(TPR_THREADS, 1) tpr_kernel(const FilterArgs a)
         int ns = 0;
         bool has_n = false;
         uint32_t processed = 0;
+        bool skip_math = false;   // warp-uniform
 
         if (nch == 0) {   // tile of empty reads: its (empty) stage job still has to be consumed
             if (next_tile < n_tiles) issue(ng, 0, it + 1);
@@ -360,59 +415,20 @@ __global__ void __launch_bounds__(TPR_THREADS, 1) tpr_kernel(const FilterArgs a)
 
             const uint32_t cbeg = c * CHUNK;
             const uint32_t cend = maxeff - cbeg < CHUNK ? maxeff - cbeg : CHUNK;   // warp-uniform
-            for (uint32_t v = 0; v < cend; v += 16) {
-                uint4 q4 = lds128(row + v);
-                const int rem = (int)g.eff - (int)(cbeg + v);
-                uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
-                if (rem < 16) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) w[i] = mask_word(w[i], rem - 4 * i);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    count_marks(w[i], ns, has_n);
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        // LUT byte offset = Q * 128
-                        uint32_t sh = (b == 0) ? (w[i] << 7) : (w[i] >> (8 * b - 7));
-                        uint32_t addr = lut_lane + (sh & 0x7F80u);
-                        if (MODE == 0) {
-                            double q, e;
-                            if (EQP) {
-                                e = lds_f64(addr);
-                                q = __dsub_rn(1.0, e);                 // (1 - p), bernoullimodule.c:140
-                            } else {
-                                double2 qe = lds_f64x2(addr);
-                                q = qe.x; e = qe.y;
-                            }
-#pragma unroll
-                            for (int j = K - 1; j >= 1; j--)
-                                P[j] = __dadd_rn(__dmul_rn(q, P[j]), __dmul_rn(e, P[j - 1]));
-                            P[0] = __dmul_rn(q, P[0]);
-                        } else {
-                            double p = lds_f64(addr);
-                            P[0] = __dadd_rn(P[0], p);                     // moira.py:1663, in index order
-                        }
-                    }
-                }
-            }
-            processed = cbeg + cend;
-            if (MODE == 0 && c + 1 < nch) {
+            if (!skip_math) sweep_chunk<K, MODE, PL, true>(row, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+            else sweep_chunk<K, MODE, PL, false>(row, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+            if (!skip_math) processed = cbeg + cend;
+            if (MODE == 0 && c + 1 < nch && !skip_math) {
                 // Early exit: sum_{j<K} P_k[j] never increases with k, so once it is safely below
-                // 1-alpha these K entries cannot reach the quantile.  Only taken warp-wide.
+                // 1-alpha these K entries cannot reach the quantile.  Taken warp-wide only: the
+                // remaining chunks are still staged and scanned for N/n (Ns stays exact) but the
+                // FP64 sweep -- the binding resource -- is skipped.
                 double tracked = P[0];
 #pragma unroll
                 for (int j = 1; j < K; j++) tracked += P[j];
-                bool dead = !valid || tracked < a.oma - 1e-9 || processed >= g.eff;
-                bool certain = !valid || tracked < a.oma - 1e-9;
-                if (__all_sync(FULL, dead) && __any_sync(FULL, valid && certain)) {
-                    // only leave if no lane could still resolve: lanes that are merely finished
-                    // (processed >= eff) are unaffected by the skipped (all padding) chunks.
-                    mbar_wait(bar0 + (it & 1) * 8, (it >> 1) & 1);   // drain the prefetched chunk
-                    it++;
-                    if (next_tile < n_tiles) issue(ng, 0, it);
-                    break;
-                }
+                const bool certain = valid && tracked < a.oma - 1e-9;
+                const bool finished = !valid || processed >= g.eff;
+                if (__all_sync(FULL, certain || finished) && __any_sync(FULL, certain)) skip_math = true;
             }
         }
 
@@ -501,7 +517,8 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
         uint32_t pos = 0;
         uint4 cur = make_uint4(0xFDFDFDFDu, 0xFDFDFDFDu, 0xFDFDFDFDu, 0xFDFDFDFDu);
         if (g.eff) cur = __ldg(reinterpret_cast<const uint4 *>(row));
-        for (; pos < g.eff && !dead; pos += 16) {
+        uint32_t swept = 0;   // bases covered by the FP64 sweep
+        for (; pos < g.eff; pos += 16) {
             uint4 nxt = cur;
             if (pos + 16 < g.eff) nxt = __ldg(reinterpret_cast<const uint4 *>(row + pos + 16));
             const int rem = (int)g.eff - (int)pos;
@@ -510,9 +527,10 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
 #pragma unroll
                 for (int k = 0; k < 4; k++) w[k] = mask_word(w[k], rem - 4 * k);
             }
+            count_marks4(w, ns, has_n);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                count_marks(w[k], ns, has_n);
+                if (dead) continue;                          // keep counting N/n, skip the FP64 sweep
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     const uint32_t q8 = (w[k] >> (8 * b)) & 0xFFu;
@@ -527,7 +545,8 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
                 }
             }
             cur = nxt;
-            if (((pos >> 4) & 3) == 3) {   // every 64 bases: can these K entries still reach 1-alpha?
+            if (!dead) swept = pos + 16;
+            if (!dead && ((pos >> 4) & 3) == 3) {   // every 64 bases: can these K entries still reach 1-alpha?
                 double t = 0.0;
 #pragma unroll
                 for (int m = 0; m < M; m++) t += P[m];
@@ -536,7 +555,7 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
                 dead = t < a.oma - 1e-9;
             }
         }
-        const uint32_t processed = pos < g.eff ? pos : g.eff;
+        const uint32_t processed = swept < g.eff ? swept : g.eff;
 
         // cumulative sum in index order across lanes (bernoullimodule.c:233-244)
         double acc = 0.0, prev = 0.0, ee = (double)(K - 1);
@@ -663,21 +682,22 @@ __global__ void __launch_bounds__(BLK_THREADS) blk_kernel(const FilterArgs a)
 // ==================================================================================================
 __global__ void __launch_bounds__(512) fp64_peak_kernel(int iters, double *sink, double p)
 {
-    double P[4][4];
+    double P[4][4], e[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++)
+    for (int c = 0; c < 4; c++) {
+        e[c] = p * (1.0 + 0.125 * c);
 #pragma unroll
         for (int j = 0; j < 4; j++) P[c][j] = 1.0 / (1.0 + threadIdx.x + c + j);
-    double e = p;
+    }
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            double q = __dsub_rn(1.0, e);
+            e[c] = __dmul_rn(e[c], 1.0000001);           // 1 DMUL (keeps q loop-variant and per-copy)
+            const double q = __dsub_rn(1.0, e[c]);       // 1 DADD
 #pragma unroll
-            for (int j = 3; j >= 1; j--) P[c][j] = __dadd_rn(__dmul_rn(q, P[c][j]), __dmul_rn(e, P[c][j - 1]));
-            P[c][0] = __dmul_rn(q, P[c][0]);
+            for (int j = 3; j >= 1; j--) P[c][j] = __dadd_rn(__dmul_rn(q, P[c][j]), __dmul_rn(e[c], P[c][j - 1]));
+            P[c][0] = __dmul_rn(q, P[c][0]);             // 7 DMUL + 3 DADD
         }
-        e = __dmul_rn(e, 1.0000001);   // keeps the compiler from hoisting q; 1 extra DMUL per iteration (counted)
     }
     double s = 0.0;
 #pragma unroll
@@ -771,8 +791,8 @@ int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, do
 {
     const int blocks = sm_count * 2, threads = 512;
     fp64_peak_kernel<<<blocks, threads, 0, s>>>(iters, d_sink, 1e-3);
-    // per iteration and thread: 4 x (1 DSUB + 7 DMUL + 3 DADD) + 1 DMUL
-    *ops_out = (double)blocks * threads * (double)iters * 45.0;
+    // per iteration and thread: 4 x (8 DMUL + 4 DADD) = 48 FP64 instructions (checked in the SASS)
+    *ops_out = (double)blocks * threads * (double)iters * 48.0;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
