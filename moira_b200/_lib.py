@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmoira_b200.so")
+LIB_PATH = os.environ.get("MOIRA_B200_LIB") or os.path.join(_HERE, "libmoira_b200.so")   # env override: tuning experiments only
 
 # ---- constants mirrored from include/moira_b200.h -------------------------------------------
 ABI_VERSION = 1

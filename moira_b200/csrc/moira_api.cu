@@ -26,8 +26,8 @@ thread_local char g_err[512] = "";
             return fail(MOIRA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr uint32_t SUB_BATCH = 1u << 24;   // reads per first-pass launch (queue indices are 32-bit)
-constexpr int MAX_TIMED = 64;
+constexpr uint32_t SUB_BATCH = 1u << 22;   // reads per first-pass launch when a ladder follows (bounds the queue memory)
+constexpr int MAX_TIMED = 256;
 
 struct Workspace {
     uint32_t *queues = nullptr;
@@ -152,6 +152,19 @@ int check_params(const moira_params *p)
     return MOIRA_OK;
 }
 
+// Phi^-1(p) by bisection on erfc (host only; accuracy far beyond what a K estimate needs).
+double normal_quantile(double p)
+{
+    double lo = -40.0, hi = 40.0;
+    for (int i = 0; i < 200; i++) {
+        const double mid = 0.5 * (lo + hi);
+        const double cdf = 0.5 * erfc(-mid / sqrt(2.0));
+        if (cdf < p) lo = mid; else hi = mid;
+    }
+    const double z = 0.5 * (lo + hi);
+    return z < 0.0 ? 0.0 : z;
+}
+
 int first_pass_k_template(int k_wanted)
 {
     static const int ks[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32};
@@ -177,7 +190,8 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
     volatile double oma = 1 - p->alpha;   // evaluated like (1 - alpha) at bernoullimodule.c:244
     a.oma = oma;
     a.thr = p->thr;
-    a.z = sqrt(2.0 * log(1.0 / p->alpha));
+    a.z = normal_quantile(1.0 - p->alpha);
+    a.zc = (a.z * a.z - 1.0) / 6.0 + 2.5;   // skew bound + continuity (0.5) + K = j*+1 (1) + margin (1)
     a.mode = p->mode; a.thr_kind = p->thr_kind; a.ambigs = p->ambigs; a.round_flag = p->round_flag;
     a.truncate = p->truncate; a.exact = p->exact_ee; a.ee_output = p->ee_output;
     a.lut_p = c->d_p; a.lut_q = c->d_q; a.lut_e = c->d_e; a.e_equals_p = c->e_equals_p;
@@ -200,14 +214,15 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             else k_first = max_first_pass_k();
         }
         k_first = first_pass_k_template(k_first);
-        a.min_rung = 0;
+        a.min_rung = 1;
         while (a.min_rung < NB - 1 && rung_cap(a.min_rung) <= k_first) a.min_rung++;
     }
     const bool ladder = p->mode == MOIRA_MODE_PB && (p->exact_ee || !k_decides_all);
     a.allow_push = ladder ? 1 : 0;
 
-    for (uint64_t start = 0; start < n_reads; start += SUB_BATCH) {
-        const uint32_t n = (uint32_t)std::min<uint64_t>(SUB_BATCH, n_reads - start);
+    const uint64_t sub = ladder ? SUB_BATCH : (1ull << 31);
+    for (uint64_t start = 0; start < n_reads; start += sub) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(sub, n_reads - start);
         a.base = start; a.n = n; a.queue = nullptr; a.queue_count = nullptr; a.rung = -1;
         if (ladder) {
             int rc = ensure_ws(ws, (uint32_t)std::min<uint64_t>(n_reads, SUB_BATCH));
@@ -223,7 +238,8 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
         c->launches++;
         if (timed) { CU(cudaEventRecord(c->t1[c->n_timed], stream)); c->n_timed++; c->timed_name = name; }
         if (ladder) {
-            for (int b = a.min_rung; b < NB; b++) {
+            for (int b = 0; b < NB; b++) {
+                if (b > 0 && b < a.min_rung) continue;
                 if (launch_rung(a, b, cfg)) return fail(MOIRA_ERR_CUDA, "rung %d launch failed: %s", b, cudaGetErrorString(cudaGetLastError()));
                 c->launches++;
             }

@@ -8,14 +8,17 @@
 namespace moira {
 
 // ---- escalation ladder --------------------------------------------------------------------
-// Reads whose decision / exact statistic is not settled by the first pass are pushed into one
-// of these queues, by the number K of PMF entries they are estimated to need.
-constexpr int NB = 9;
-// capacity in PMF entries of each rung: thread-per-read 8/16/32, warp-per-read 64..1024, block.
+// Reads whose decision / exact statistic is not settled by the first pass are pushed to rung 0, a
+// classifier that estimates how many PMF entries K each of them needs (mean + upper quantile of
+// the error count, fp32) and forwards it to the cheapest rung that holds that many.  A rung that
+// still cannot settle a read hands it to the next one; the last rung (block-per-read) takes any K.
+constexpr int NB = 15;
+constexpr int N_TPR_RUNGS = 9;   // rungs 1..9 thread-per-read, 10..13 warp-per-read, 14 block-per-read
 __host__ __device__ constexpr int rung_cap(int b)
 {
-    return b == 0 ? 8 : b == 1 ? 16 : b == 2 ? 32 : b == 3 ? 64 : b == 4 ? 128 : b == 5 ? 256
-         : b == 6 ? 512 : b == 7 ? 1024 : 0x7fffffff;
+    return b == 0 ? 0 : b == 1 ? 8 : b == 2 ? 12 : b == 3 ? 16 : b == 4 ? 20 : b == 5 ? 24 : b == 6 ? 32
+         : b == 7 ? 40 : b == 8 ? 48 : b == 9 ? 64 : b == 10 ? 128 : b == 11 ? 256 : b == 12 ? 512
+         : b == 13 ? 1024 : 0x7fffffff;
 }
 
 struct FilterArgs {
@@ -37,7 +40,8 @@ struct FilterArgs {
     // parameters
     double oma;                  // 1 - alpha, computed on the host exactly as the reference does
     double thr;
-    double z;                    // sqrt(2 ln(1/alpha)): upper-quantile factor for the K estimate
+    double z;                    // standard-normal quantile of 1-alpha (K estimate of the classifier)
+    double zc;                   // Cornish-Fisher skew bound (z^2-1)/6 + rounding/safety margin
     int32_t mode;
     int32_t thr_kind;
     int32_t ambigs;
@@ -50,7 +54,7 @@ struct FilterArgs {
     uint32_t *queue_counts;      // [NB]
     uint32_t queue_cap;
     int32_t rung;                // -1 on the first pass, else this kernel's rung
-    int32_t min_rung;            // lowest rung the first pass may push to
+    int32_t min_rung;            // lowest rung the classifier may forward to (its cap exceeds the first-pass K)
     int32_t allow_push;          // 0: no ladder follows (first-pass K provably decides everything)
     // tables (device, 256 doubles each)
     const double *lut_p;

@@ -32,16 +32,27 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- thread-per-read geometry ---------------------------------------------------------------
-constexpr int TPR_WARPS = 16;
-constexpr int TPR_THREADS = TPR_WARPS * 32;
-constexpr int CHUNK = 128;                       // bytes of one row staged per pipeline stage
-constexpr int ROW_STRIDE = CHUNK + 16;           // 144 B = 36 words: lane*36 mod 32 = lane*4 -> LDS.128 conflict-free
+#ifndef MOIRA_CHUNK
+#define MOIRA_CHUNK 128
+#endif
+#ifndef MOIRA_WARPS_SMALLK
+#define MOIRA_WARPS_SMALLK 16
+#endif
+#ifndef MOIRA_PAIR_LUT
+#define MOIRA_PAIR_LUT 1   // 1: first-pass kernels look up (q, e) pairs (no DSUB, LDS.128); 0: p only (LDS.64 + DSUB)
+#endif
+constexpr int CHUNK = MOIRA_CHUNK;               // bytes of one row staged per pipeline stage (64 or 128)
+// row stride = CHUNK + 16 B (144 B = 36 words / 80 B = 20 words): the 8 lanes of an LDS.128 phase
+// start at word offsets lane*36 (or lane*20) mod 32 = distinct multiples of 4 -> conflict-free
+constexpr int ROW_STRIDE = CHUNK + 16;
 constexpr int STAGE_BYTES = 32 * ROW_STRIDE;     // one warp, one stage
-constexpr int LUT_BYTES = 256 * 128;             // 256 entries x 128 B (16 x double or 8 x double2)
-constexpr int TPR_OFF_STAGE = LUT_BYTES;
-constexpr int TPR_OFF_BAR = TPR_OFF_STAGE + TPR_WARPS * 2 * STAGE_BYTES;
-constexpr int TPR_OFF_CNT = TPR_OFF_BAR + TPR_WARPS * 2 * 8;
-constexpr int TPR_SMEM = TPR_OFF_CNT + (16 + MOIRA_N_HIST) * 4;
+// Q -> probability table: 256 rows of 256 bytes at a 64 KB-aligned shared address, so that one PRMT
+// builds the lane's lookup address  table | Q << 8 | replica  (byte 1 <- quality byte) and the
+// replicas make a warp's 32 random lookups conflict-free: 32 x double (p) or 16 x double2 (q, e).
+constexpr int LUT_BYTES = 256 * 256;
+constexpr int TPR_SMEM = 227 * 1024;             // whole opt-in shared memory; laid out at run time
+// P[0..K-1] lives in registers: 16 warps per CTA up to K = 24 (<= 128 registers), 8 above (<= 255).
+__host__ __device__ constexpr int tpr_warps(int k) { return k <= 4 ? MOIRA_WARPS_SMALLK : k <= 24 ? 16 : 8; }
 
 constexpr int WPR_THREADS = 256;
 constexpr int BLK_THREADS = 256;
@@ -85,6 +96,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// Ampere-style asynchronous 16-byte copy global -> shared (SASS: LDGSTS); src_size 0 zero-fills.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_size)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ uint4 lds128(uint32_t addr)
 {
     uint4 v;
@@ -118,17 +138,18 @@ __device__ __forceinline__ uint32_t mark_bits(uint32_t w)
 {
     return ((w & 0x7F7F7F7Fu) + 0x02020202u) & w & 0x80808080u;
 }
-// Bit 7 of every byte that is == 0xFF ('N').
-__device__ __forceinline__ uint32_t upper_n_bits(uint32_t w)
+// N/n accounting for one 16-byte vector.  Real qualities never have bit 7 set, so one OR/AND over
+// the four words filters out every vector without markers (and without tail padding); the exact
+// count runs only for the others.  ns128 accumulates 128 per marker byte.
+__device__ __forceinline__ void count_marks4(const uint32_t (&w)[4], uint32_t &ns, uint32_t &upper_n)
 {
-    return ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u;
-}
-__device__ __forceinline__ void count_marks4(const uint32_t (&w)[4], int &ns, bool &has_upper_n)
-{
-    const uint32_t m0 = mark_bits(w[0]), m1 = mark_bits(w[1]), m2 = mark_bits(w[2]), m3 = mark_bits(w[3]);
-    if (m0 | m1 | m2 | m3) {   // rare: only reads with ambiguous bases
-        ns += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-        has_upper_n |= (upper_n_bits(w[0]) | upper_n_bits(w[1]) | upper_n_bits(w[2]) | upper_n_bits(w[3])) != 0u;
+    if ((w[0] | w[1] | w[2] | w[3]) & 0x80808080u) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t m = mark_bits(w[i]);
+            ns += __popc(m);
+            upper_n |= m & (w[i] << 7);     // marker byte with bit 0 set == 0xFF ('N')
+        }
     }
 }
 
@@ -152,7 +173,6 @@ __device__ __forceinline__ ReadGeom read_geom(const FilterArgs &a, uint32_t r_lo
 //      (moira.py:872-970), counters, and escalation of reads this pass could not settle -----------
 struct ReadResult {
     double ee_raw;     // exact statistic, or a lower bound when !resolved
-    double p0;         // P[0] = prod(1-p_i) at the end of the sweep (PB only; K estimate)
     uint32_t processed;  // bases swept before a (warp-wide) early exit
     int ns;
     bool has_n;
@@ -162,9 +182,25 @@ struct ReadResult {
 
 __device__ __forceinline__ int pick_rung(const FilterArgs &a, int kneed)
 {
-    int b = a.rung + 1 > a.min_rung ? a.rung + 1 : a.min_rung;
+    int b = a.min_rung > 1 ? a.min_rung : 1;
     while (b < NB - 1 && rung_cap(b) < kneed) b++;
     return b;
+}
+
+// Append read r_local to the queue of `rung` (warp-aggregated).  Called convergently; lanes with
+// push == false only take part in the ballot.
+__device__ __forceinline__ void push_read(const FilterArgs &a, bool push, int rung, uint32_t r_local, int lane)
+{
+    const unsigned pm = __ballot_sync(FULL, push);
+    if (push) {
+        const unsigned peers = __match_any_sync(pm, rung);
+        const int leader = __ffs(peers) - 1;
+        uint32_t basepos = 0;
+        if (lane == leader) basepos = atomicAdd(&a.queue_counts[rung], (uint32_t)__popc(peers));
+        basepos = __shfl_sync(peers, basepos, leader);
+        const uint32_t pos = basepos + __popc(peers & ((1u << lane) - 1u));
+        if (pos < a.queue_cap) a.queues[(size_t)rung * a.queue_cap + pos] = r_local;
+    }
 }
 
 // Called by all 32 lanes of a warp (convergent).  `valid` lanes carry a read.
@@ -192,34 +228,12 @@ __device__ __forceinline__ void finish_read(const FilterArgs &a, bool valid, uin
     else if (!ok) reason = MOIRA_REASON_ERRORS;
 
     bool numeric = res.numeric;
-    bool push = valid && undecided && a.allow_push && a.rung < NB - 1;
+    const bool push = valid && undecided && a.allow_push && a.rung < NB - 1;
     if (valid && undecided && !push) numeric = true;   // nowhere left to go (see MOIRA_ERR_UNRESOLVED)
     if (numeric) { ok = false; if (reason == MOIRA_REASON_NONE) reason = MOIRA_REASON_ERRORS; }
 
-    // ---- escalate ---------------------------------------------------------------------------
-    int rung = 0;
-    if (push) {
-        double mu = res.p0 > 0.0 ? -log(res.p0) : 1.0e9;
-        if (res.processed < g.eff) mu *= (double)g.eff / (double)(res.processed ? res.processed : 1u);
-        double kn = mu + a.z * sqrt(mu) + 3.0;
-        if (!a.exact) {   // a decision needs at most floor(cutoff on the raw statistic) + 2 entries
-            double c = (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) ? cutoff - nsd : cutoff;
-            double kd = floor(c) + 2.0;
-            if (kd < kn) kn = kd;
-        }
-        int kneed = kn > 1.0e6 ? 1000000 : (int)kn;
-        rung = pick_rung(a, kneed);
-    }
-    unsigned pm = __ballot_sync(FULL, push);
-    if (push) {
-        unsigned peers = __match_any_sync(pm, rung);
-        int leader = __ffs(peers) - 1;
-        uint32_t basepos = 0;
-        if (lane == leader) basepos = atomicAdd(&a.queue_counts[rung], (uint32_t)__popc(peers));
-        basepos = __shfl_sync(peers, basepos, leader);
-        uint32_t pos = basepos + __popc(peers & ((1u << lane) - 1u));
-        if (pos < a.queue_cap) a.queues[(size_t)rung * a.queue_cap + pos] = r_local;
-    }
+    // ---- escalate: first pass -> classifier (rung 0); a rung -> the next one -------------------
+    push_read(a, push, a.rung + 1, r_local, lane);
     if (!valid || push) return;
 
     // ---- write + count ----------------------------------------------------------------------
@@ -270,90 +284,137 @@ __device__ __forceinline__ bool cdf_quantile(const double (&P)[K], double oma, d
     return false;
 }
 
-// One staged chunk of one row (thread-per-read): `cend` bytes starting at shared address `row`,
-// of which the first `rem0` belong to the read (the rest is masked to padding).
-// MATH = false keeps only the N/n accounting (after a warp-wide early exit).
-template <int K, int MODE, bool PL, bool MATH>
-__device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t cend, int rem0, uint32_t lut_lane, double (&P)[K],
-                                            int &ns, bool &has_n)
+// Load one 16-byte vector of a staged row, mask what lies beyond the read to padding, account N/n.
+__device__ __forceinline__ void load_vec(uint32_t addr, int rem, uint32_t (&w)[4], uint32_t &ns, uint32_t &has_n)
 {
-    for (uint32_t v = 0; v < cend; v += 16) {
-        const uint4 q4 = lds128(row + v);
-        const int rem = rem0 - (int)v;
-        uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
-        if (rem < 16) {
+    const uint4 q4 = lds128(addr);
+    w[0] = q4.x; w[1] = q4.y; w[2] = q4.z; w[3] = q4.w;
+    if (rem < 16) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) w[i] = mask_word(w[i], rem - 4 * i);
-        }
-        count_marks4(w, ns, has_n);
-        if (!MATH) continue;
+        for (int i = 0; i < 4; i++) w[i] = mask_word(w[i], rem - 4 * i);
+    }
+    count_marks4(w, ns, has_n);
+}
+
+// Lookup address of byte b of w: table base (64 KB aligned) | Q << 8 | lane replica offset, in one PRMT.
+template <int B>
+__device__ __forceinline__ uint32_t lut_addr_of(uint32_t w, uint32_t lut_lane)
+{
+    return __byte_perm(w, lut_lane, 0x7604u | (B << 4));
+}
+// The per-base work on one 16-byte vector already in registers.
+template <int K, int MODE, bool PL>
+__device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_lane, double (&P)[K])
+{
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 4; i++) {
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const uint32_t q8 = __byte_perm(w[i], 0u, 0x4440u + b);   // zero-extended byte b
-                const uint32_t addr = lut_lane + (q8 << 7);               // table row = Q * 128 bytes
-                if (MODE == 0) {
-                    double q, e;
-                    if (PL) {
-                        e = lds_f64(addr);
-                        q = __dsub_rn(1.0, e);                 // (1 - p), bernoullimodule.c:140
-                    } else {
-                        const double2 qe = lds_f64x2(addr);
-                        q = qe.x; e = qe.y;
-                    }
-#pragma unroll
-                    for (int j = K - 1; j >= 1; j--)
-                        P[j] = __dadd_rn(__dmul_rn(q, P[j]), __dmul_rn(e, P[j - 1]));
-                    P[0] = __dmul_rn(q, P[0]);
+        for (int b = 0; b < 4; b++) {
+            const uint32_t addr = __byte_perm(w[i], lut_lane, 0x7604u | (b << 4));   // table | Q << 8 | replica
+            if (MODE == 0) {
+                double q, e;
+                if (PL) {
+                    e = lds_f64(addr);
+                    q = __dsub_rn(1.0, e);                 // (1 - p), bernoullimodule.c:140
                 } else {
-                    P[0] = __dadd_rn(P[0], lds_f64(addr));     // moira.py:1663, in index order
+                    const double2 qe = lds_f64x2(addr);
+                    q = qe.x; e = qe.y;
                 }
+#pragma unroll
+                for (int j = K - 1; j >= 1; j--)
+                    P[j] = __dadd_rn(__dmul_rn(q, P[j]), __dmul_rn(e, P[j - 1]));
+                P[0] = __dmul_rn(q, P[0]);
+            } else if (MODE == 1) {
+                P[0] = __dadd_rn(P[0], lds_f64(addr));     // moira.py:1663, in index order
+            } else {
+                const double2 t = lds_f64x2(addr);         // classifier: mean and variance of the error count
+                P[0] += t.x;
+                P[1] += t.y;
             }
         }
+    }
+}
+
+// One staged chunk of one row (thread-per-read): `cend` bytes starting at shared address `row`, of
+// which the first `rem0` belong to this lane's read (the rest is masked to padding).  The first
+// `cfull` bytes (warp-uniform, multiple of 16) are inside the read for EVERY lane: no masking there.
+// MATH = false keeps only the N/n accounting (after a warp-wide early exit).
+template <int K, int MODE, bool PL, bool MATH>
+__device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t cfull, uint32_t cend, int rem0, uint32_t lut_lane,
+                                            double (&P)[K], uint32_t &ns, uint32_t &has_n)
+{
+    uint32_t v = 0;
+    for (; v < cfull; v += 16) {
+        const uint4 q4 = lds128(row + v);
+        const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+        count_marks4(w, ns, has_n);
+        if (MATH) sweep_vec<K, MODE, PL>(w, lut_lane, P);
+    }
+    for (; v < cend; v += 16) {
+        uint32_t w[4];
+        load_vec(row + v, rem0 - (int)v, w, ns, has_n);
+        if (MATH) sweep_vec<K, MODE, PL>(w, lut_lane, P);
     }
 }
 
 // ==================================================================================================
 // thread-per-read kernels
 // ==================================================================================================
-// MODE 0: Poisson-binomial with K entries.  MODE 1: Lambda accumulation (K ignored).
+// MODE 0: Poisson-binomial with K entries.  MODE 1: Lambda accumulation (K == 1).
+// MODE 2: ladder classifier (K == 2): mean/variance of the error count -> rung.
 template <int K, int MODE, bool EQP>
-__global__ void __launch_bounds__(TPR_THREADS, 1) tpr_kernel(const FilterArgs a)
+__global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterArgs a)
 {
+    constexpr int TPR_WARPS = tpr_warps(K);
+    constexpr int TPR_THREADS = TPR_WARPS * 32;
     extern __shared__ __align__(128) uint8_t smem[];
+    if (a.queue && *a.queue_count == 0) return;   // empty rung: nothing to set up
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + TPR_OFF_CNT);
-    uint32_t *s_hist = s_cnt + 16;
 
-    // ---- one-time setup: replicated lookup table, barriers, counters ----
-    constexpr bool PL = EQP || MODE == 1;   // table holds p only (8 B entries, 16 replicas)
+    // ---- run-time layout of the dynamic shared memory (TPR_SMEM bytes) ----------------------
+    //   [base, lut)            stage buffers of the first nA warps (whatever fits below the table)
+    //   [lut, lut + 64 KB)     lookup table, 64 KB aligned (see LUT_BYTES)
+    //   [lut + 64 KB, ...)     stage buffers of the remaining warps, then counters + histogram
+    const uint32_t base = smem_u32(smem);
+    const uint32_t lut = (base + 0xFFFFu) & ~0xFFFFu;
+    const uint32_t n_below = min((lut - base) / (2u * STAGE_BYTES), (uint32_t)TPR_WARPS);
+    const uint32_t above = lut + LUT_BYTES;
+    const uint32_t cnt_addr = above + (TPR_WARPS - n_below) * 2u * STAGE_BYTES;
+    if (cnt_addr + (16 + MOIRA_N_HIST) * 4 - base > (uint32_t)TPR_SMEM) __trap();   // cannot happen for base <= 1 KB
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + (cnt_addr - base));
+    uint32_t *s_hist = s_cnt + 16;
+    uint8_t *lut_ptr = smem + (lut - base);
+
+    // ---- one-time setup: replicated lookup table, counters ----
+    constexpr bool PL = (EQP && MODE == 0 && !(MOIRA_PAIR_LUT && K <= 8)) || MODE == 1;   // p only: 32 x 8 B per row
     if (PL) {
-        double *lut = reinterpret_cast<double *>(smem);
-        for (int i = threadIdx.x; i < 256 * 16; i += TPR_THREADS) lut[i] = a.lut_p[i >> 4];
+        double *t = reinterpret_cast<double *>(lut_ptr);
+        for (int i = threadIdx.x; i < 256 * 32; i += TPR_THREADS) t[i] = a.lut_p[i >> 5];
+    } else if (MODE == 0) {
+        double2 *t = reinterpret_cast<double2 *>(lut_ptr);
+        for (int i = threadIdx.x; i < 256 * 16; i += TPR_THREADS) t[i] = make_double2(a.lut_q[i >> 4], a.lut_e[i >> 4]);
     } else {
-        double2 *lut = reinterpret_cast<double2 *>(smem);
-        for (int i = threadIdx.x; i < 256 * 8; i += TPR_THREADS) lut[i] = make_double2(a.lut_q[i >> 3], a.lut_e[i >> 3]);
+        double2 *t = reinterpret_cast<double2 *>(lut_ptr);
+        for (int i = threadIdx.x; i < 256 * 16; i += TPR_THREADS) {
+            const double pv = a.lut_p[i >> 4];
+            t[i] = make_double2(pv, pv * (1.0 - pv));
+        }
     }
     for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += TPR_THREADS) s_cnt[i] = 0;
-    const uint32_t bar0 = smem_u32(smem + TPR_OFF_BAR) + warp * 16;
-    if (lane == 0) {
-        mbar_init(bar0, 32);
-        mbar_init(bar0 + 8, 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    const uint32_t lut_lane = smem_u32(smem) + (PL ? (lane & 15) * 8 : (lane & 7) * 16);
-    const uint32_t stage0 = smem_u32(smem + TPR_OFF_STAGE) + warp * 2 * STAGE_BYTES + lane * ROW_STRIDE;
+    const uint32_t lut_lane = lut + (PL ? lane * 8 : (lane & 15) * 16);
+    const uint32_t stage_warp = (uint32_t)warp < n_below ? base + warp * 2 * STAGE_BYTES
+                                                         : above + (warp - n_below) * 2 * STAGE_BYTES;
+    const uint32_t stage0 = stage_warp + lane * ROW_STRIDE;
 
     const uint32_t count = a.queue ? *a.queue_count : a.n;
     const uint32_t n_tiles = (count + 31) >> 5;
     const uint32_t total_warps = gridDim.x * TPR_WARPS;
     uint32_t tile = blockIdx.x * TPR_WARPS + warp;
     uint32_t it = 0;   // stage jobs issued == consumed so far by this warp
+    const bool coop = a.queue == nullptr;   // rows of a first-pass tile are neighbours in the slab
 
     auto tile_read = [&](uint32_t t, bool &valid, uint32_t &r_local, ReadGeom &g) {
         uint32_t i = t * 32 + lane;
@@ -365,19 +426,53 @@ __global__ void __launch_bounds__(TPR_THREADS, 1) tpr_kernel(const FilterArgs a)
             g = read_geom(a, r_local);
         }
     };
-    // stage job (read geometry g, chunk c) into stage `s`
+    // Stage chunk c of the tile's 32 rows into stage `s` with LDGSTS (cp.async), 16 bytes per lane
+    // and instruction.  First pass: the warp copies cooperatively -- 8 consecutive lanes fetch one
+    // whole 128-byte line of one row, so every global request is a full line.  Ladder passes (rows
+    // scattered through the slab): every lane copies its own row.  One commit group per job.
     auto issue = [&](const ReadGeom &g, uint32_t c, uint32_t s) {
-        const uint32_t bar = bar0 + (s & 1) * 8;
         const uint32_t padded = (g.eff + 15u) & ~15u;
         const uint32_t begin = c * CHUNK;
-        uint32_t bytes = padded > begin ? padded - begin : 0u;
-        if (bytes > CHUNK) bytes = CHUNK;
-        if (bytes) {
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_g2s(stage0 + (s & 1) * STAGE_BYTES, a.slab + g.off + begin, bytes, bar);
+        const uint32_t dst_stage = (s & 1) * STAGE_BYTES;
+        if (coop && !a.offsets && !a.lengths) {
+            // uniform stride and length: addresses follow from the tile's first row (lane 0)
+            const uint32_t col = (lane & (CHUNK / 16 - 1)) * 16;
+            constexpr int ROWS_PER_INST = 32 / (CHUNK / 16);
+            const uint64_t off0 = __shfl_sync(FULL, g.off, 0);
+            const uint32_t nrows = __popc(__ballot_sync(FULL, g.eff != 0u || g.len != 0u));
+            const bool col_in = begin + col < __shfl_sync(FULL, padded, 0);   // every row has lane 0's length here
+            const uint8_t *src = a.slab + off0 + begin + col + (uint64_t)(lane / (CHUNK / 16)) * a.stride;
+            const uint32_t dst = stage_warp + dst_stage + (lane / (CHUNK / 16)) * ROW_STRIDE + col;
+#pragma unroll
+            for (int i = 0; i < 32 / ROWS_PER_INST; i++) {
+                const bool in = col_in && (uint32_t)(lane / (CHUNK / 16) + ROWS_PER_INST * i) < nrows;
+                cp_async16(dst + i * ROWS_PER_INST * ROW_STRIDE, in ? src + (uint64_t)i * ROWS_PER_INST * a.stride : a.slab,
+                           in ? 16u : 0u);
+            }
+        } else if (coop) {
+            const uint32_t col = (lane & (CHUNK / 16 - 1)) * 16;
+            constexpr int ROWS_PER_INST = 32 / (CHUNK / 16);
+#pragma unroll
+            for (int i = 0; i < 32 / ROWS_PER_INST; i++) {
+                const int rr = lane / (CHUNK / 16) + ROWS_PER_INST * i;
+                const uint64_t o = __shfl_sync(FULL, g.off, rr);
+                const uint32_t pd = __shfl_sync(FULL, padded, rr);
+                const bool in = begin + col < pd;
+                cp_async16(stage_warp + dst_stage + rr * ROW_STRIDE + col, a.slab + (in ? o + begin + col : 0), in ? 16u : 0u);
+            }
         } else {
-            mbar_arrive(bar);
+#pragma unroll
+            for (int i = 0; i < CHUNK / 16; i++) {
+                const bool in = begin + i * 16 < padded;
+                cp_async16(stage0 + dst_stage + i * 16, a.slab + (in ? g.off + begin + i * 16 : 0), in ? 16u : 0u);
+            }
         }
+        cp_async_commit();
+    };
+    // wait for the oldest outstanding job of this lane, then make every lane's copies visible
+    auto consume = [&](bool next_issued) {
+        if (next_issued) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
     };
 
     bool valid, nvalid;
@@ -390,33 +485,38 @@ __global__ void __launch_bounds__(TPR_THREADS, 1) tpr_kernel(const FilterArgs a)
         const uint32_t next_tile = tile + total_warps;
         tile_read(next_tile, nvalid, nr_local, ng);
         const uint32_t maxeff = __reduce_max_sync(FULL, g.eff);
+        const uint32_t mineff = __reduce_min_sync(FULL, g.eff);
         const uint32_t nch = (maxeff + CHUNK - 1) / CHUNK;
 
         double P[K];
 #pragma unroll
         for (int j = 0; j < K; j++) P[j] = 0.0;
         if (MODE == 0) P[0] = 1.0;
-        int ns = 0;
-        bool has_n = false;
+        uint32_t ns = 0, has_n = 0;
         uint32_t processed = 0;
         bool skip_math = false;   // warp-uniform
 
         if (nch == 0) {   // tile of empty reads: its (empty) stage job still has to be consumed
-            if (next_tile < n_tiles) issue(ng, 0, it + 1);
-            mbar_wait(bar0 + (it & 1) * 8, (it >> 1) & 1);
+            const bool nx = next_tile < n_tiles;
+            __syncwarp();
+            if (nx) issue(ng, 0, it + 1);
+            consume(nx);
             it++;
         }
         for (uint32_t c = 0; c < nch; c++) {
+            const bool nx = c + 1 < nch || next_tile < n_tiles;
+            __syncwarp();   // every lane is done reading the stage the next job overwrites
             if (c + 1 < nch) issue(g, c + 1, it + 1);
             else if (next_tile < n_tiles) issue(ng, 0, it + 1);
-            mbar_wait(bar0 + (it & 1) * 8, (it >> 1) & 1);
+            consume(nx);
             const uint32_t row = stage0 + (it & 1) * STAGE_BYTES;
             it++;
 
             const uint32_t cbeg = c * CHUNK;
             const uint32_t cend = maxeff - cbeg < CHUNK ? maxeff - cbeg : CHUNK;   // warp-uniform
-            if (!skip_math) sweep_chunk<K, MODE, PL, true>(row, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
-            else sweep_chunk<K, MODE, PL, false>(row, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+            const uint32_t cfull = mineff > cbeg ? min((mineff - cbeg) & ~15u, cend) : 0u;   // warp-uniform
+            if (!skip_math) sweep_chunk<K, MODE, PL, true>(row, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+            else sweep_chunk<K, MODE, PL, false>(row, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
             if (!skip_math) processed = cbeg + cend;
             if (MODE == 0 && c + 1 < nch && !skip_math) {
                 // Early exit: sum_{j<K} P_k[j] never increases with k, so once it is safely below
@@ -434,16 +534,31 @@ __global__ void __launch_bounds__(TPR_THREADS, 1) tpr_kernel(const FilterArgs a)
 
         // ---- per-read epilogue ----
         ReadResult res;
-        res.ns = ns;
-        res.has_n = has_n;
+        res.ns = (int)ns;
+        res.has_n = has_n != 0u;
         res.numeric = false;
         res.processed = processed < g.eff ? processed : g.eff;
+        if (MODE == 2) {
+            // Upper quantile of the error count by Cornish-Fisher with the Poisson skew bound:
+            // j* <~ mu + z*sigma + (z^2-1)/6; K = j* + 1 plus margin (zc holds the constants).
+            // An under-estimate only costs one more rung; the result is never affected.
+            double kn = P[0] + a.z * sqrt(P[1]) + a.zc;
+            if (!a.exact) {   // a decision needs at most floor(cutoff on the raw statistic) + 2 entries
+                double c = (a.thr_kind == MOIRA_THR_MAXERRORS) ? a.thr : __dmul_rn((double)g.eff, a.thr);
+                if (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) c -= (double)ns;
+                const double kd = floor(c) + 2.0;
+                if (kd < kn) kn = kd;
+            }
+            const int kneed = kn > 1.0e6 ? 1000000 : (kn < 2.0 ? 2 : (int)kn);
+            push_read(a, valid, pick_rung(a, kneed), r_local, lane);
+            tile = next_tile;
+            valid = nvalid; r_local = nr_local; g = ng;
+            continue;
+        }
         if (MODE == 0) {
-            res.p0 = P[0];
             res.resolved = cdf_quantile<K>(P, a.oma, res.ee_raw);
             if (res.processed < g.eff) { res.resolved = false; res.ee_raw = (double)(K - 1); }
         } else {
-            res.p0 = 1.0;
             const double lam = P[0];
             if (a.mode == MOIRA_MODE_EXPECTED_ERROR) {
                 res.ee_raw = lam;
@@ -494,6 +609,7 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
 {
     __shared__ double2 s_lut[256];
     __shared__ uint32_t s_cnt[16 + MOIRA_N_HIST];
+    if (*a.queue_count == 0) return;
     for (int i = threadIdx.x; i < 256; i += WPR_THREADS) s_lut[i] = make_double2(a.lut_q[i], a.lut_e[i]);
     for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += WPR_THREADS) s_cnt[i] = 0;
     __syncthreads();
@@ -511,8 +627,7 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
 #pragma unroll
         for (int m = 0; m < M; m++) P[m] = 0.0;
         if (lane == 0) P[0] = 1.0;
-        int ns = 0;
-        bool has_n = false;
+        uint32_t ns = 0, has_n = 0;
         bool dead = false;
         uint32_t pos = 0;
         uint4 cur = make_uint4(0xFDFDFDFDu, 0xFDFDFDFDu, 0xFDFDFDFDu, 0xFDFDFDFDu);
@@ -586,10 +701,9 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
         }
         ReadResult res;
         res.ee_raw = ee;
-        res.p0 = __shfl_sync(FULL, P[0], 0);
         res.processed = processed;
-        res.ns = ns;
-        res.has_n = has_n;
+        res.ns = (int)ns;
+        res.has_n = has_n != 0u;
         res.resolved = found;
         res.numeric = false;
         finish_read(a, lane == 0, r_local, g, res, s_cnt, s_hist, lane);
@@ -609,6 +723,7 @@ __global__ void __launch_bounds__(BLK_THREADS) blk_kernel(const FilterArgs a)
     __shared__ uint32_t s_cnt[16 + MOIRA_N_HIST];
     __shared__ double s_res[4];
     __shared__ int s_j;
+    if (*a.queue_count == 0) return;
     for (int i = threadIdx.x; i < 256; i += BLK_THREADS) s_lut[i] = make_double2(a.lut_q[i], a.lut_e[i]);
     for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += BLK_THREADS) s_cnt[i] = 0;
     __syncthreads();
@@ -656,7 +771,6 @@ __global__ void __launch_bounds__(BLK_THREADS) blk_kernel(const FilterArgs a)
             s_j = js;
             s_res[0] = prev;
             s_res[1] = acc;
-            s_res[2] = P[0];
         }
         __syncthreads();
         ReadResult res;
@@ -665,7 +779,6 @@ __global__ void __launch_bounds__(BLK_THREADS) blk_kernel(const FilterArgs a)
         res.ee_raw = js < 0 ? (double)(K - 1)
                    : js == 0 ? 0.0
                              : __dadd_rn((double)(js - 1), __ddiv_rn(__dsub_rn(a.oma, s_res[0]), __dsub_rn(s_res[1], s_res[0])));
-        res.p0 = s_res[2];
         res.processed = g.eff;
         res.ns = ns;
         res.has_n = has_n;
@@ -707,19 +820,21 @@ __global__ void __launch_bounds__(512) fp64_peak_kernel(int iters, double *sink,
     if (s == 123.456) sink[0] = s;
 }
 
-template <int K>
-int launch_tpr_pb(const FilterArgs &a, const LaunchCfg &cfg)
+template <int K, int MODE>
+int launch_tpr(const FilterArgs &a, const LaunchCfg &cfg)
 {
-    if (a.e_equals_p) tpr_kernel<K, 0, true><<<cfg.sm_count, TPR_THREADS, TPR_SMEM, cfg.stream>>>(a);
-    else tpr_kernel<K, 0, false><<<cfg.sm_count, TPR_THREADS, TPR_SMEM, cfg.stream>>>(a);
+    constexpr int W = tpr_warps(K);
+    if (a.e_equals_p) tpr_kernel<K, MODE, true><<<cfg.sm_count, W * 32, TPR_SMEM, cfg.stream>>>(a);
+    else tpr_kernel<K, MODE, false><<<cfg.sm_count, W * 32, TPR_SMEM, cfg.stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-template <int K>
+template <int K, int MODE>
 int init_tpr()
 {
-    if (cudaFuncSetAttribute(tpr_kernel<K, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(tpr_kernel<K, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    constexpr int W = tpr_warps(K);
+    if (cudaFuncSetAttribute(tpr_kernel<K, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(tpr_kernel<K, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -731,11 +846,11 @@ int max_first_pass_k() { return 32; }
 
 int kernels_init(int)
 {
-#define X(k) if (init_tpr<k>()) return -1;
+#define X(k) if (init_tpr<k, 0>()) return -1;
     MOIRA_FOR_EACH_K(X)
+    X(40) X(48) X(64)
 #undef X
-    if (cudaFuncSetAttribute(tpr_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(tpr_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (init_tpr<1, 1>() || init_tpr<2, 2>()) return -1;
     if (cudaFuncSetAttribute(blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM) != cudaSuccess) return -1;
     return 0;
 }
@@ -749,21 +864,19 @@ int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, con
 #define X(k)                                                   \
     if (k_wanted <= k) {                                       \
         if (name) *name = names[idx];                          \
-        return launch_tpr_pb<k>(a, cfg) ? -1 : k;              \
+        return launch_tpr<k, 0>(a, cfg) ? -1 : k;              \
     }                                                          \
     idx++;
     MOIRA_FOR_EACH_K(X)
 #undef X
     if (name) *name = names[12];
-    return launch_tpr_pb<32>(a, cfg) ? -1 : 32;
+    return launch_tpr<32, 0>(a, cfg) ? -1 : 32;
 }
 
 int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name)
 {
     if (name) *name = "lambda_tpr";
-    if (a.e_equals_p) tpr_kernel<1, 1, true><<<cfg.sm_count, TPR_THREADS, TPR_SMEM, cfg.stream>>>(a);
-    else tpr_kernel<1, 1, false><<<cfg.sm_count, TPR_THREADS, TPR_SMEM, cfg.stream>>>(a);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return launch_tpr<1, 1>(a, cfg);
 }
 
 int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg)
@@ -774,14 +887,20 @@ int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg)
     a.queue_count = a0.queue_counts + b;
     const int wpr_grid = cfg.sm_count * 4;
     switch (b) {
-    case 0: return launch_tpr_pb<8>(a, cfg);
-    case 1: return launch_tpr_pb<16>(a, cfg);
-    case 2: return launch_tpr_pb<32>(a, cfg);
-    case 3: wpr_kernel<2><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 4: wpr_kernel<4><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 5: wpr_kernel<8><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 6: wpr_kernel<16><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 7: wpr_kernel<32><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 0: return launch_tpr<2, 2>(a, cfg);     // classifier
+    case 1: return launch_tpr<8, 0>(a, cfg);
+    case 2: return launch_tpr<12, 0>(a, cfg);
+    case 3: return launch_tpr<16, 0>(a, cfg);
+    case 4: return launch_tpr<20, 0>(a, cfg);
+    case 5: return launch_tpr<24, 0>(a, cfg);
+    case 6: return launch_tpr<32, 0>(a, cfg);
+    case 7: return launch_tpr<40, 0>(a, cfg);
+    case 8: return launch_tpr<48, 0>(a, cfg);
+    case 9: return launch_tpr<64, 0>(a, cfg);
+    case 10: wpr_kernel<4><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 11: wpr_kernel<8><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 12: wpr_kernel<16><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 13: wpr_kernel<32><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
     default: blk_kernel<<<cfg.sm_count, BLK_THREADS, BLK_SMEM, cfg.stream>>>(a); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
