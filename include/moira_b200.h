@@ -186,12 +186,13 @@ MOIRA_API int moira_pack_reads(const char *seq, const int32_t *quals, const uint
 
 /* Parse a FASTQ text buffer (4-line records, moira.py:1152-1204) straight into a slab.
  * Sizing pass when slab == NULL: returns n_reads and the needed slab bytes.
- * hdr_off/hdr_len and seq_off give, per read, the byte ranges of the header token and the
- * sequence line inside `text` (so the host can slice names and bases without re-parsing). */
+ * hdr_off/hdr_len, seq_off and qual_off give, per read, the byte ranges of the header token, the
+ * sequence line and the quality line inside `text` (so the host can slice names, bases and quality
+ * characters without re-parsing; sequence and quality lines are lengths[r] bytes long). */
 MOIRA_API int moira_parse_fastq(const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous,
                       uint8_t *slab, uint64_t slab_capacity, uint64_t *out_offsets,
                       uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off,
-                      uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out);
+                      uint64_t *qual_off, uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out);
 
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 

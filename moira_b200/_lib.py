@@ -82,7 +82,7 @@ lib.moira_wait.argtypes = [_vp, _i]
 lib.moira_calculate_errors_PB.argtypes = [_vp, ctypes.c_char_p, _vp, _u64, _dbl, ctypes.POINTER(_dbl),
                                           ctypes.POINTER(ctypes.c_int32)]
 lib.moira_pack_reads.argtypes = [_vp, _vp, _vp, _vp, _u64, _i, _vp, _u64, _vp, ctypes.POINTER(_u64)]
-lib.moira_parse_fastq.argtypes = [_vp, _u64, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64,
+lib.moira_parse_fastq.argtypes = [_vp, _u64, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                   ctypes.POINTER(_u64), ctypes.POINTER(_u64)]
 lib.moira_fp64_peak.argtypes = [_vp, _i, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
 lib.moira_ctx_launch_count.argtypes = [_vp, ctypes.POINTER(_u64)]

@@ -273,14 +273,14 @@ def pack_arrays(seq_all, q_all, in_off, lengths, lower_n_ambiguous: bool = True,
 
 
 def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = True):
-    """FASTQ bytes -> (slab, offsets, lengths, hdr_off, hdr_len, seq_off) via moira_parse_fastq.
+    """FASTQ bytes -> (slab, offsets, lengths, hdr_off, hdr_len, seq_off, qual_off) via moira_parse_fastq.
     Raises MoiraError(ERR_PARSE) with the reference's error class name in the message
     (EmptySeqError / EmptyQualError / LengthMismatchError, moira.py:1178-1183)."""
     buf = np.frombuffer(text, dtype=np.uint8)
     n = ctypes.c_uint64()
     nb = ctypes.c_uint64()
     L.check(lib.moira_parse_fastq(_ptr(buf), buf.nbytes, int(fastq_offset), int(lower_n_ambiguous), None, 0,
-                                  None, None, None, None, None, 0, ctypes.byref(n), ctypes.byref(nb)))
+                                  None, None, None, None, None, None, 0, ctypes.byref(n), ctypes.byref(nb)))
     nr = n.value
     slab = np.empty(max(16, nb.value), dtype=np.uint8)
     offsets = np.empty(nr, np.uint64)
@@ -288,10 +288,11 @@ def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = T
     hdr_off = np.empty(nr, np.uint64)
     hdr_len = np.empty(nr, np.uint32)
     seq_off = np.empty(nr, np.uint64)
+    qual_off = np.empty(nr, np.uint64)
     L.check(lib.moira_parse_fastq(_ptr(buf), buf.nbytes, int(fastq_offset), int(lower_n_ambiguous), _ptr(slab),
                                   slab.nbytes, _ptr(offsets), _ptr(lengths), _ptr(hdr_off), _ptr(hdr_len),
-                                  _ptr(seq_off), nr, ctypes.byref(n), ctypes.byref(nb)))
-    return slab, offsets, lengths, hdr_off, hdr_len, seq_off
+                                  _ptr(seq_off), _ptr(qual_off), nr, ctypes.byref(n), ctypes.byref(nb)))
+    return slab, offsets, lengths, hdr_off, hdr_len, seq_off, qual_off
 
 
 __all__ = ["Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",

@@ -1,0 +1,404 @@
+"""moira_b200 command line: the Python-3 host of the B200 path.
+
+Keeps the reference CLI's flags, defaults, input sniffing, collapse logic, output files and
+formatting (fpusan/moira v1.3.2, moira/moira.py: parse_arguments :581-675, check_arguments :678-781,
+main :264-578, write_results :842-970, parsers :1058-1204), but instead of calling
+`bernoulli.calculate_errors_PB` once per read (moira.py:817) it parses reads in batches straight into
+quality slabs and runs them through libmoira_b200.so (one moira_filter_batch per batch).
+
+Scope: single-end filtering (`--forward_fastq` or `--forward_fasta` + `--forward_qual`).  Paired-end
+contig construction (`--paired`, `--only_contig`) is upstream of the hot path and not part of this
+build; those flags are accepted and rejected with a message.
+`--error_calc` adds `expected_error` (north_star) and drops `bootstrap` (deprecated, moira.py:772-776);
+`poisson_binomial_py` is an alias of `poisson_binomial` with the Python twin's 'N'-only rule.
+"""
+from __future__ import annotations
+
+import argparse
+import bz2
+import gzip
+import io
+import sys
+import time
+
+import numpy as np
+
+from . import _lib as L
+from .api import Context, FilterParams, MoiraError, pack_reads, parse_fastq
+
+__version__ = "0.1.0 (moira 1.3.2 compatible)"
+
+BATCH_BYTES = 64 << 20   # FASTQ text per batch
+
+
+# ---- exceptions of the reference (moira.py:973-1055) ---------------------------------------------
+class ReturnedNaNError(Exception):
+    pass
+
+
+class UnpairedFilesError(Exception):
+    pass
+
+
+class NameMismatchError(Exception):
+    def __init__(self, *headers):
+        super().__init__("Sequence headers do not match: %s" % ", ".join(str(h) for h in headers))
+
+
+class LengthMismatchError(Exception):
+    def __init__(self, header, *files):
+        super().__init__("Sequence and quality lengths differ for %s (%s)" % (header, ", ".join(map(str, files))))
+
+
+class EmptySeqError(Exception):
+    def __init__(self, header, fname):
+        super().__init__("Empty sequence for %s in %s" % (header, fname))
+
+
+class EmptyQualError(Exception):
+    def __init__(self, header, fname):
+        super().__init__("Empty qualities for %s in %s" % (header, fname))
+
+
+# ---- arguments (moira.py:581-781) ------------------------------------------------------------------
+def parse_arguments(argv=None):
+    def str2bool(value):
+        return value.lower() in ("yes", "true", "t", "1")
+
+    parser = argparse.ArgumentParser(description="Perform quality filtering on a set of sequences (B200 path).")
+    general = parser.add_argument_group("General options")
+    general.add_argument("-ff", "--forward_fasta", type=str)
+    general.add_argument("-fq", "--forward_qual", type=str)
+    general.add_argument("-rf", "--reverse_fasta", type=str)
+    general.add_argument("-rq", "--reverse_qual", type=str)
+    general.add_argument("-ffq", "--forward_fastq", type=str)
+    general.add_argument("-rfq", "--reverse_fastq", type=str)
+    general.add_argument("-l", "--relabel", type=str)
+    general.add_argument("-o", "--output_format", type=str, default="fasta", choices=("fasta", "fastq"))
+    general.add_argument("-pi", "--pipeline", type=str, default="mothur", choices=("mothur", "USEARCH"))
+    general.add_argument("-op", "--output_prefix", type=str)
+    general.add_argument("-oc", "--output_compression", type=str, default="none", choices=("none", "gz", "bz2"))
+    general.add_argument("-p", "--processors", type=int, default=1,
+                         help="Accepted for compatibility; the GPU path does not use worker processes.")
+    general.add_argument("--paired", action="store_true")
+    general.add_argument("-fo", "--fastq_offset", type=int, default=33)
+    general.add_argument("--only_contig", action="store_true")
+    general.add_argument("--silent", action="store_true")
+    general.add_argument("--nowarnings", action="store_true")
+    general.add_argument("--doc", action="store_true")
+    general.add_argument("--device", type=int, default=0, help="CUDA device index (B200 path only).")
+    filtering = parser.add_argument_group("Sequence filtering options")
+    filtering.add_argument("-c", "--collapse", type=str2bool, default="True")
+    filtering.add_argument("-t", "--truncate", type=int)
+    filtering.add_argument("-mo", "--min_overlap", type=int)
+    filtering.add_argument("-e", "--error_calc", type=str, default="poisson_binomial",
+                           choices=("poisson_binomial", "poisson_binomial_py", "poisson", "expected_error"))
+    filtering.add_argument("-n", "--ambigs", type=str, default="treat_as_errors",
+                           choices=("disallow", "ignore", "treat_as_errors"))
+    filtering.add_argument("-r", "--round", action="store_true")
+    err_uncert = filtering.add_mutually_exclusive_group()
+    err_uncert.add_argument("-u", "--uncert", type=float, default=0.01)
+    err_uncert.add_argument("-me", "--maxerrors", type=float)
+    filtering.add_argument("-a", "--alpha", type=float, default=0.005)
+    args = parser.parse_args(argv)
+    if isinstance(args.collapse, str):
+        args.collapse = str2bool(args.collapse)
+    return args
+
+
+def check_arguments(args, out=sys.stdout):
+    """moira.py:678-781 for the flags this build implements."""
+    ok = True
+
+    def warn(msg):
+        if not args.nowarnings:
+            print(msg, file=out)
+
+    if args.doc:
+        print(__doc__, file=out)
+        return False
+    if args.paired or args.only_contig:
+        warn("- Paired-end contig construction (--paired / --only_contig) is not part of the B200 build; "
+             "assemble contigs first and pass them as --forward_fastq or --forward_fasta/--forward_qual.")
+        return False
+    if not args.forward_fastq and (not args.forward_fasta or not args.forward_qual):
+        warn("- You must at least provide one fastq file, or a fasta and quality files.")
+        ok = False
+    if not 0 < args.uncert <= 1:
+        warn("- The uncert parameter must be between 0 (not included) and 1.")
+        ok = False
+    if args.maxerrors is not None and args.maxerrors <= 0:
+        warn("- The maxerrors parameter must be greater than 0.")
+        ok = False
+    if not 0 < args.alpha < 1:
+        warn("- The alpha parameter must be between 0 (not included) and 1.")
+        ok = False
+    if args.truncate and args.truncate <= 0:
+        warn("- The truncate parameter must be greater than 0.")
+        ok = False
+    if not ok:
+        warn("\nFor more info type moira.py -h or moira.py --doc.\n")
+        return False
+    if (args.reverse_fasta or args.reverse_fastq) and not args.paired:
+        warn("You provided a reverse sequence file, but not the --paired flag. Note that only the forward file will be processed.\n")
+    return True
+
+
+# ---- input (moira.py:1058-1204) -------------------------------------------------------------------
+def open_input(filename):
+    """Sniff gzip / bzip2 by magic bytes (moira.py:1065-1068) and return a binary file object."""
+    fh = io.open(filename, mode="rb", buffering=1 << 20)
+    start = fh.peek(3)[:3]
+    if start.startswith(b"\x1f\x8b\x08"):
+        fh.close()
+        return gzip.GzipFile(filename=filename)
+    if start.startswith(b"\x42\x5a\x68"):
+        fh.close()
+        return bz2.BZ2File(filename)
+    return fh
+
+
+def _norm_header(raw: str, lead: str) -> str:
+    return raw.strip().replace("\t", " ").split(" ")[0].lstrip(lead).replace(":", "_")
+
+
+def read_fastq_batches(fh, fastq_offset, lower_n_ambiguous, fname):
+    """Yield (headers, seqs, quals_arrays, slab, offsets, lengths) per batch of whole 4-line records."""
+    carry = b""
+    while True:
+        block = fh.read(BATCH_BYTES)
+        data = carry + block
+        if not data:
+            break
+        if block:
+            # keep whole records: cut at the last newline that ends a multiple of 4 lines
+            n_lines = data.count(b"\n")
+            keep_lines = n_lines - (n_lines % 4)
+            if keep_lines == 0:
+                carry = data
+                continue
+            pos = -1
+            # find position after keep_lines-th newline
+            idx = np.flatnonzero(np.frombuffer(data, dtype=np.uint8) == 10)
+            pos = int(idx[keep_lines - 1]) + 1
+            text, carry = data[:pos], data[pos:]
+        else:
+            text, carry = data, b""
+        try:
+            slab, offsets, lengths, hoff, hlen, soff, qoff = parse_fastq(text, fastq_offset, lower_n_ambiguous)
+        except MoiraError as exc:
+            if exc.code == L.ERR_PARSE:
+                name = exc.message.split(":")[0]
+                cls = {"EmptySeqError": EmptySeqError, "EmptyQualError": EmptyQualError}.get(name)
+                if cls:
+                    raise cls(exc.message, fname) from None
+                raise LengthMismatchError(exc.message, fname) from None
+            raise
+        n = len(lengths)
+        headers = [text[int(hoff[i]):int(hoff[i]) + int(hlen[i])].decode("latin-1").replace(":", "_") for i in range(n)]
+        seqs = [text[int(soff[i]):int(soff[i]) + int(lengths[i])].decode("latin-1") for i in range(n)]
+        # qualities for the writers, as process_data returns them (Q <= 0 -> 1, moira.py:814)
+        buf = np.frombuffer(text, dtype=np.uint8)
+        quals = []
+        for i in range(n):
+            q = buf[int(qoff[i]):int(qoff[i]) + int(lengths[i])].astype(np.int32) - fastq_offset
+            quals.append(np.where(q > 0, q, 1))
+        yield headers, seqs, quals, slab, offsets, lengths
+        if not block:
+            break
+
+
+def read_fasta_qual_batches(ffh, qfh, lower_n_ambiguous, fasta_name, qual_name, batch_reads=200000):
+    """moira.py:1093-1149, single-end: sequences and qualities on one line each."""
+    while True:
+        headers, seqs, quals = [], [], []
+        while len(headers) < batch_reads:
+            fh_line = ffh.readline()
+            qh_line = qfh.readline()
+            if not fh_line and not qh_line:
+                break
+            fheader = _norm_header(fh_line.decode("latin-1"), ">")
+            seq = ffh.readline().decode("latin-1").strip()
+            qheader = _norm_header(qh_line.decode("latin-1"), ">")
+            qline = qfh.readline().decode("latin-1").strip().replace("\t", " ")
+            q = [int(x) for x in qline.split(" ")] if qline else []
+            if fheader != qheader:
+                raise NameMismatchError(fheader, qheader)
+            if not seq:
+                raise EmptySeqError(fheader, fasta_name)
+            if not q:
+                raise EmptyQualError(qheader, qual_name)
+            if len(seq) != len(q):
+                raise LengthMismatchError(fheader, fasta_name, qual_name)
+            headers.append(fheader)
+            seqs.append(seq)
+            quals.append(np.asarray([v if v > 0 else 1 for v in q], dtype=np.int32))
+        if not headers:
+            break
+        slab, offsets, lengths = pack_reads(seqs, quals, lower_n_ambiguous)
+        yield headers, seqs, quals, slab, offsets, lengths
+        if len(headers) < batch_reads:
+            break
+
+
+# ---- output (moira.py:842-970) ----------------------------------------------------------------------
+class Writers:
+    def __init__(self, args, output_name):
+        opener, suffix = {"none": (open, ""), "gz": (gzip.open, ".gz"), "bz2": (bz2.open, ".bz2")}[args.output_compression]
+        self.files = []
+
+        def op(name):
+            fh = opener(name + suffix, "wt")
+            self.files.append(fh)
+            self.names.append(name + suffix)
+            return fh
+
+        self.names = []
+        if args.output_format == "fastq":
+            self.good = op("%s.qc.good.fastq" % output_name)
+            self.good_qual = None
+            self.bad = op("%s.qc.bad.fastq" % output_name)
+            self.bad_qual = None
+        else:
+            self.good = op("%s.qc.good.fasta" % output_name)
+            self.good_qual = op("%s.qc.good.qual" % output_name)
+            self.bad = op("%s.qc.bad.fasta" % output_name)
+            self.bad_qual = op("%s.qc.bad.qual" % output_name)
+        if args.collapse and args.pipeline == "mothur":
+            self.good_names = op("%s.qc.good.names" % output_name)
+            self.bad_names = op("%s.qc.bad.names" % output_name)
+        else:
+            self.good_names = self.bad_names = None
+
+    def close(self):
+        for fh in self.files:
+            fh.close()
+
+
+def write_result(index, header, sequence, quals, expected_errors, names_info, accept, reason, args, w: Writers):
+    """One record, formatted as write_results does (moira.py:842-970); the accept/reason pair comes
+    from the device.  Returns (discarded_errors, discarded_minlength)."""
+    if args.relabel:
+        header = "%s%d" % (args.relabel, index)
+    if args.pipeline == "USEARCH":
+        header = header + ";ee=%.2f;size=%d;" % (expected_errors, len(names_info) if names_info else 1)
+    n_members = len(names_info) if names_info else 1
+    if accept:
+        out, out_q, out_n, note = w.good, w.good_qual, w.good_names, ""
+    else:
+        out, out_q, out_n = w.bad, w.bad_qual, w.bad_names
+        if reason == L.REASON_LENGTH:
+            note = "\tlength below %s" % args.truncate
+        elif reason == L.REASON_AMBIGS:
+            note = "\tcontains ambiguities"
+        elif args.maxerrors:
+            note = "\terrors > %.2f" % args.maxerrors
+        else:
+            note = "\tuncert > %.3f" % args.uncert
+    if args.output_format == "fastq":
+        out.write("@%s%s\n%s\n+\n%s\n" % (header, note, sequence, "".join(chr(int(q) + args.fastq_offset) for q in quals)))
+    else:
+        out.write(">%s%s\n%s\n" % (header, note, sequence))
+        out_q.write(">%s%s\n%s\n" % (header, note, " ".join(str(int(q)) for q in quals)))
+    if args.collapse and args.pipeline == "mothur" and out_n is not None:
+        out_n.write("%s\t%s\n" % (header, ",".join(names_info)))
+    if accept:
+        return 0, 0
+    return (0, n_members) if reason == L.REASON_LENGTH else (n_members, 0)
+
+
+# ---- main (moira.py:264-578) ---------------------------------------------------------------------------
+def main(args, out=sys.stdout) -> int:
+    if not args.silent:
+        print("\nmoira_b200 %s -- Poisson-binomial read filtering on NVIDIA B200\n" % __version__, file=out)
+    if not check_arguments(args, out):
+        return 1
+    if args.output_prefix:
+        output_name = args.output_prefix
+    elif args.forward_fastq:
+        output_name = ".".join(args.forward_fastq.split(".")[:-1])
+    else:
+        output_name = ".".join(args.forward_fasta.split(".")[:-1])
+
+    calc = "poisson_binomial" if args.error_calc == "poisson_binomial_py" else args.error_calc
+    params = FilterParams(error_calc=calc, alpha=args.alpha, uncert=args.uncert, maxerrors=args.maxerrors,
+                          ambigs=args.ambigs, round=args.round, truncate=args.truncate,
+                          exact_ee=bool(args.collapse) or args.pipeline == "USEARCH", ee_output="final")
+    lower_n = args.error_calc == "poisson_binomial"      # bernoullimodule.c:196 vs moira.py:1605/1660
+
+    try:
+        if args.forward_fastq:
+            batches = read_fastq_batches(open_input(args.forward_fastq), args.fastq_offset, lower_n, args.forward_fastq)
+        else:
+            batches = read_fasta_qual_batches(open_input(args.forward_fasta), open_input(args.forward_qual), lower_n,
+                                              args.forward_fasta, args.forward_qual)
+        writers = Writers(args, output_name)
+    except IOError as exc:
+        print(exc, file=out)
+        return 1
+
+    ctx = Context(args.device)
+    processed = 0
+    discarded_errors = discarded_minlength = 0
+    uniques = {}
+    t0 = time.time()
+    try:
+        for headers, seqs, quals, slab, offsets, lengths in batches:
+            res = ctx.filter_batch(slab, offsets, lengths, params)
+            if np.isnan(res.ee).any() or res.numeric.any():
+                bad = int(np.flatnonzero(np.isnan(res.ee) | res.numeric)[0])
+                raise ReturnedNaNError("Error calculation failed for sequence %s" % headers[bad])
+            accept = res.accept
+            reason = res.reason
+            for i, header in enumerate(headers):
+                contig, cq = seqs[i], quals[i]
+                if args.truncate:
+                    contig, cq = contig[:args.truncate], cq[:args.truncate]        # moira.py:806-807
+                ee = float(res.ee[i])
+                if args.collapse:
+                    u = uniques.get(contig)
+                    if u is None:
+                        uniques[contig] = [header, ee, cq, [header], bool(accept[i]), int(reason[i])]
+                    elif ee < u[1]:                                                # moira.py:466
+                        u[0], u[1], u[2], u[4], u[5] = header, ee, cq, bool(accept[i]), int(reason[i])
+                        u[3].insert(0, header)
+                    else:
+                        u[3].append(header)
+                else:
+                    de, dl = write_result(processed, header, contig, cq, ee, None, bool(accept[i]), int(reason[i]), args, writers)
+                    discarded_errors += de
+                    discarded_minlength += dl
+                processed += 1
+            if not args.silent:
+                print("%d sequences processed in %.1f seconds.\r" % (processed, time.time() - t0), end="", file=out)
+        if args.collapse:
+            order = sorted(uniques, key=lambda s: len(uniques[s][3]), reverse=True)   # moira.py:492
+            for index, sequence in enumerate(order, start=1):
+                header, ee, cq, names, acc, rsn = uniques[sequence]
+                de, dl = write_result(index, header, sequence, cq, ee, names, acc, rsn, args, writers)
+                discarded_errors += de
+                discarded_minlength += dl
+    finally:
+        writers.close()
+        ctx.close()
+
+    if not args.silent and processed:
+        remaining = processed - discarded_errors - discarded_minlength
+        print("\n- Kept %d (%.2f%%) of the original sequences." % (remaining, remaining / processed * 100), file=out)
+        if args.truncate:
+            print("- %d (%.2f%%) of the original sequences were discarded due to length < %s." %
+                  (discarded_minlength, discarded_minlength / processed * 100, args.truncate), file=out)
+        print("- %d (%.2f%%) of the original sequences were discarded due to low quality.\n" %
+              (discarded_errors, discarded_errors / processed * 100), file=out)
+        print("The following output files were generated:", file=out)
+        for name in writers.names:
+            print(name, file=out)
+    return 0
+
+
+def run(argv=None) -> int:
+    return main(parse_arguments(argv))
+
+
+if __name__ == "__main__":
+    sys.exit(run())

@@ -52,7 +52,8 @@ extern "C" int moira_pack_reads(const char *seq, const int32_t *quals, const uin
 
 extern "C" int moira_parse_fastq(const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous,
                                  uint8_t *slab, uint64_t slab_capacity, uint64_t *out_offsets, uint32_t *lengths,
-                                 uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off, uint64_t max_reads,
+                                 uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off, uint64_t *qual_off,
+                                 uint64_t max_reads,
                                  uint64_t *n_reads_out, uint64_t *slab_bytes_out)
 {
     if (!text || !n_reads_out || !slab_bytes_out) return hfail(MOIRA_ERR_BAD_ARG, "NULL argument");
@@ -101,6 +102,7 @@ extern "C" int moira_parse_fastq(const char *text, uint64_t text_bytes, int fast
             if (hdr_off) hdr_off[n] = hb;
             if (hdr_len) hdr_len[n] = (uint32_t)(he - hb);
             if (seq_off) seq_off[n] = lb[1];
+            if (qual_off) qual_off[n] = lb[3];
         }
         pos += padded;
         n++;

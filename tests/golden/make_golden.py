@@ -10,6 +10,7 @@ Outputs (all small, committed):
   test1.fastq.gz         the reference's 1000-read MiSeq forward fixture (moira/test/test1.fastq.gz)
   forward_names.json.gz  golden .names partitions of the forward full-pipeline test
                          (moira/test/test_results/forward.qc.{good,bad}.names)
+  forward_outputs.json.gz  golden fasta/qual records of the same test (header line -> [sequence, quality line])
   contigs.json.gz        the 400 golden paired contigs (fasta+qual) with good/bad labels
                          (moira/test/test_results/paired.qc.{good,bad}.{fasta,qual})
   ref_outputs.npz        outputs of the UNMODIFIED reference binary (oracle/_ref) on: the 1000
@@ -38,6 +39,13 @@ T = open(os.path.join(REF, "test", "test_moira.py")).read()
 def grab(name):
     m = re.search(r"^%s = (.*)$" % re.escape(name), T, re.M)
     return ast.literal_eval(m.group(1))
+
+
+def _dump_gz(name, obj):
+    """json -> gzip with a fixed mtime so regenerating the fixtures is byte-reproducible."""
+    with open(os.path.join(HERE, name), "wb") as raw:
+        with gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as gz:
+            gz.write(json.dumps(obj).encode())
 
 
 def main():
@@ -73,8 +81,19 @@ def main():
             rep, members = line.rstrip("\n").split("\t")
             d[rep] = members.split(",")
         names[lab] = d
-    with gzip.open(os.path.join(HERE, "forward_names.json.gz"), "wt") as fh:
-        json.dump(names, fh)
+    _dump_gz("forward_names.json.gz", names)
+
+    # ---- golden forward output records (fasta + qual, keyed by header; order is Py2-dict dependent) ---
+    fwd_out = {}
+    for lab in ("good", "bad"):
+        fa = open(os.path.join(REF, "test", "test_results", "forward.qc.%s.fasta" % lab)).read().splitlines()
+        qu = open(os.path.join(REF, "test", "test_results", "forward.qc.%s.qual" % lab)).read().splitlines()
+        d = {}
+        for i in range(0, len(fa), 2):
+            assert fa[i] == qu[i]
+            d[fa[i]] = [fa[i + 1], qu[i + 1]]
+        fwd_out[lab] = d
+    _dump_gz("forward_outputs.json.gz", fwd_out)
 
     # ---- golden contigs (paired run outputs, used as single-end fasta+qual inputs) ------------
     contigs = []
@@ -88,8 +107,7 @@ def main():
         for header, seq, quals in po.parse_fasta_qual_text(fa, qu):
             contigs.append({"header": header, "seq": seq, "quals": quals, "label": lab,
                             "reason": hdr_reason.get(header, "")})
-    with gzip.open(os.path.join(HERE, "contigs.json.gz"), "wt") as fh:
-        json.dump(contigs, fh)
+    _dump_gz("contigs.json.gz", contigs)
 
     # ---- reference-binary outputs -------------------------------------------------------------
     out = {}

@@ -65,7 +65,7 @@ def test_pack_rejects_unrepresentable_quality():
 
 def test_parse_fastq_matches_oracle_parser(forward_records):
     text = gzip.open(os.path.join(ROOT, "tests", "golden", "test1.fastq.gz"), "rb").read()
-    slab, off, ln, hoff, hlen, soff = moira_b200.parse_fastq(text, 33, True)
+    slab, off, ln, hoff, hlen, soff, qoff = moira_b200.parse_fastq(text, 33, True)
     assert len(ln) == len(forward_records) == 1000
     seqs = [s for _, s, _ in forward_records]
     quals = [q for _, _, q in forward_records]

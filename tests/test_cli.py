@@ -1,0 +1,109 @@
+"""The Python-3 host (moira_b200/cli.py) against the reference's full-pipeline goldens
+(moira/test/test_moira.py:74-113).  Record ORDER among equal-abundance uniques comes from a
+Python-2 dict in the reference (moira.py:492), so files are compared as record sets."""
+import bz2
+import gzip
+import io
+import json
+import os
+import shutil
+
+import pytest
+
+from moira_b200 import cli
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _records(path, opener=open):
+    lines = opener(path, "rt").read().splitlines()
+    return {lines[i]: lines[i + 1] for i in range(0, len(lines), 2)}
+
+
+def _names(path, opener=open):
+    out = {}
+    for line in opener(path, "rt"):
+        rep, members = line.rstrip("\n").split("\t")
+        out[rep] = members.split(",")
+    return out
+
+
+def test_argument_surface_matches_reference_defaults():
+    a = cli.parse_arguments(["-ffq", "x.fastq"])
+    assert (a.alpha, a.uncert, a.maxerrors, a.error_calc, a.ambigs, a.round, a.truncate) == \
+        (0.005, 0.01, None, "poisson_binomial", "treat_as_errors", False, None)      # moira.py:649-668
+    assert a.collapse is True and a.pipeline == "mothur" and a.output_format == "fasta" and a.fastq_offset == 33
+    assert cli.parse_arguments(["-ffq", "x", "-c", "False"]).collapse is False
+    with pytest.raises(SystemExit):
+        cli.parse_arguments(["-ffq", "x", "-u", "0.02", "-me", "2"])                  # mutually exclusive, moira.py:663-667
+    buf = io.StringIO()
+    assert cli.check_arguments(cli.parse_arguments(["-ffq", "x", "-a", "1.5"]), buf) is False
+    assert "alpha parameter must be between 0" in buf.getvalue()
+    assert cli.check_arguments(cli.parse_arguments(["-ffq", "x", "--paired"]), io.StringIO()) is False
+    assert cli.check_arguments(cli.parse_arguments([]), io.StringIO()) is False
+
+
+def test_open_input_sniffs_compression(tmp_path):
+    raw = gzip.open(os.path.join(GOLDEN, "test1.fastq.gz"), "rb").read()
+    plain, gz, bz = tmp_path / "a.fastq", tmp_path / "b.anything", tmp_path / "c.anything"
+    plain.write_bytes(raw)
+    gz.write_bytes(gzip.compress(raw))
+    bz.write_bytes(bz2.compress(raw))
+    for p in (plain, gz, bz):
+        assert cli.open_input(str(p)).read() == raw                                   # moira.py:1058-1090
+
+
+def test_fastq_batches_cut_on_record_boundaries(tmp_path, forward_records, monkeypatch):
+    raw = gzip.open(os.path.join(GOLDEN, "test1.fastq.gz"), "rb").read()
+    monkeypatch.setattr(cli, "BATCH_BYTES", 50000)
+    headers, seqs, quals = [], [], []
+    for h, s, q, slab, off, ln in cli.read_fastq_batches(io.BytesIO(raw), 33, True, "mem"):
+        headers += h
+        seqs += s
+        quals += [list(map(int, x)) for x in q]
+    assert headers == [r[0] for r in forward_records] and seqs == [r[1] for r in forward_records]
+    assert quals == [[v if v > 0 else 1 for v in r[2]] for r in forward_records]
+
+
+@pytest.mark.gpu
+def test_forward_dataset_outputs_match_goldens(tmp_path, forward_names):
+    """test_moira.py:74-87 (testProcessForwardDataset) through the new host + CUDA path."""
+    fq = tmp_path / "test1.fastq"
+    fq.write_bytes(gzip.open(os.path.join(GOLDEN, "test1.fastq.gz"), "rb").read())
+    prefix = str(tmp_path / "forward")
+    assert cli.run(["-ffq", str(fq), "-op", prefix, "--silent"]) == 0
+    golden = json.load(gzip.open(os.path.join(GOLDEN, "forward_outputs.json.gz"), "rt"))
+    for lab in ("good", "bad"):
+        fa = _records("%s.qc.%s.fasta" % (prefix, lab))
+        qu = _records("%s.qc.%s.qual" % (prefix, lab))
+        assert set(fa) == set(golden[lab]) == set(qu)
+        for hdr, (seq, qual) in golden[lab].items():
+            assert fa[hdr] == seq and qu[hdr] == qual
+        assert _names("%s.qc.%s.names" % (prefix, lab)) == forward_names[lab]
+    assert len(golden["good"]) == 122 and len(golden["bad"]) == 365
+
+
+@pytest.mark.gpu
+def test_compression_and_formats(tmp_path):
+    """test_moira.py:102-113 (testCompression) + fastq/USEARCH/no-collapse outputs stay self-consistent."""
+    src = os.path.join(GOLDEN, "test1.fastq.gz")
+    base = str(tmp_path / "plain")
+    assert cli.run(["-ffq", src, "-op", base, "--silent"]) == 0
+    plain = open(base + ".qc.good.fasta").read()
+    for comp, opener in (("gz", gzip.open), ("bz2", bz2.open)):
+        pre = str(tmp_path / comp)
+        assert cli.run(["-ffq", src, "-op", pre, "-oc", comp, "--silent"]) == 0
+        assert opener("%s.qc.good.fasta.%s" % (pre, comp), "rt").read() == plain
+    # no collapse, fastq output, USEARCH headers, maxerrors mode, truncation
+    pre = str(tmp_path / "nc")
+    assert cli.run(["-ffq", src, "-op", pre, "-c", "False", "-o", "fastq", "-pi", "USEARCH", "-me", "2", "-t", "200",
+                    "--silent"]) == 0
+    good = open(pre + ".qc.good.fastq").read().splitlines()
+    bad = open(pre + ".qc.bad.fastq").read().splitlines()
+    assert (len(good) + len(bad)) // 4 == 1000
+    assert all(len(good[i + 1]) == 200 and ";ee=" in good[i] and ";size=1;" in good[i] for i in range(0, len(good), 4))
+    assert all("errors > 2.00" in bad[i] or "length below 200" in bad[i] for i in range(0, len(bad), 4))
+    for i in range(0, len(good), 4):
+        assert float(good[i].split(";ee=")[1].split(";")[0]) <= 2.0
+    shutil.rmtree(tmp_path, ignore_errors=True)

@@ -74,7 +74,7 @@ def test_forward_fixture_full_pipeline_partition(ctx, forward_records, forward_n
     """The reference's forward full-pipeline test (test_moira.py:74-87): fastq -> slab (C parser) ->
     CUDA filter -> collapse -> 122 good / 365 bad uniques with identical member lists."""
     text = gzip.open(os.path.join(ROOT, "tests", "golden", "test1.fastq.gz"), "rb").read()
-    slab, off, ln, hoff, hlen, soff = moira_b200.parse_fastq(text, 33, True)
+    slab, off, ln, hoff, hlen, soff, qoff = moira_b200.parse_fastq(text, 33, True)
     p = FilterParams(exact_ee=True, ee_output="final")
     res = ctx.filter_batch(slab, off, ln, p)
     assert np.array_equal(res.ee - res.ns, ref_outputs["forward_ee"])          # raw ee bit-equal to the reference binary
