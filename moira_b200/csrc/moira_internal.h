@@ -12,13 +12,12 @@ namespace moira {
 // classifier that estimates how many PMF entries K each of them needs (mean + upper quantile of
 // the error count, fp32) and forwards it to the cheapest rung that holds that many.  A rung that
 // still cannot settle a read hands it to the next one; the last rung (block-per-read) takes any K.
-constexpr int NB = 15;
-constexpr int N_TPR_RUNGS = 9;   // rungs 1..9 thread-per-read, 10..13 warp-per-read, 14 block-per-read
+constexpr int NB = 20;
+// rungs 1..14 thread-per-read, 15..18 warp-per-read, 19 block-per-read
 __host__ __device__ constexpr int rung_cap(int b)
 {
-    return b == 0 ? 0 : b == 1 ? 8 : b == 2 ? 12 : b == 3 ? 16 : b == 4 ? 20 : b == 5 ? 24 : b == 6 ? 32
-         : b == 7 ? 40 : b == 8 ? 48 : b == 9 ? 64 : b == 10 ? 128 : b == 11 ? 256 : b == 12 ? 512
-         : b == 13 ? 1024 : 0x7fffffff;
+    constexpr int caps[NB] = {0, 8, 10, 12, 14, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 0x7fffffff};
+    return caps[b];
 }
 
 struct FilterArgs {

@@ -51,8 +51,8 @@ constexpr int STAGE_BYTES = 32 * ROW_STRIDE;     // one warp, one stage
 // replicas make a warp's 32 random lookups conflict-free: 32 x double (p) or 16 x double2 (q, e).
 constexpr int LUT_BYTES = 256 * 256;
 constexpr int TPR_SMEM = 227 * 1024;             // whole opt-in shared memory; laid out at run time
-// P[0..K-1] lives in registers: 16 warps per CTA up to K = 24 (<= 128 registers), 8 above (<= 255).
-__host__ __device__ constexpr int tpr_warps(int k) { return k <= 4 ? MOIRA_WARPS_SMALLK : k <= 24 ? 16 : 8; }
+// P[0..K-1] lives in registers: 16 warps per CTA up to K = 16 (<= 128 registers), 8 above (<= 255).
+__host__ __device__ constexpr int tpr_warps(int k) { return k <= 4 ? MOIRA_WARPS_SMALLK : k <= 16 ? 16 : 8; }
 
 constexpr int WPR_THREADS = 256;
 constexpr int BLK_THREADS = 256;
@@ -840,7 +840,7 @@ int init_tpr()
 
 }  // namespace
 
-#define MOIRA_FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(16) X(20) X(24) X(32)
+#define MOIRA_FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(28) X(32)
 
 int max_first_pass_k() { return 32; }
 
@@ -858,8 +858,9 @@ int kernels_init(int)
 int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, const char **name)
 {
     static const char *names[] = {"pb_tpr<K=2>", "pb_tpr<K=3>", "pb_tpr<K=4>", "pb_tpr<K=5>", "pb_tpr<K=6>",
-                                  "pb_tpr<K=7>", "pb_tpr<K=8>", "pb_tpr<K=10>", "pb_tpr<K=12>", "pb_tpr<K=16>",
-                                  "pb_tpr<K=20>", "pb_tpr<K=24>", "pb_tpr<K=32>"};
+                                  "pb_tpr<K=7>", "pb_tpr<K=8>", "pb_tpr<K=10>", "pb_tpr<K=12>", "pb_tpr<K=14>",
+                                  "pb_tpr<K=16>", "pb_tpr<K=18>", "pb_tpr<K=20>", "pb_tpr<K=22>", "pb_tpr<K=24>",
+                                  "pb_tpr<K=28>", "pb_tpr<K=32>"};
     int idx = 0;
 #define X(k)                                                   \
     if (k_wanted <= k) {                                       \
@@ -869,7 +870,7 @@ int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, con
     idx++;
     MOIRA_FOR_EACH_K(X)
 #undef X
-    if (name) *name = names[12];
+    if (name) *name = names[16];
     return launch_tpr<32, 0>(a, cfg) ? -1 : 32;
 }
 
@@ -889,18 +890,23 @@ int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg)
     switch (b) {
     case 0: return launch_tpr<2, 2>(a, cfg);     // classifier
     case 1: return launch_tpr<8, 0>(a, cfg);
-    case 2: return launch_tpr<12, 0>(a, cfg);
-    case 3: return launch_tpr<16, 0>(a, cfg);
-    case 4: return launch_tpr<20, 0>(a, cfg);
-    case 5: return launch_tpr<24, 0>(a, cfg);
-    case 6: return launch_tpr<32, 0>(a, cfg);
-    case 7: return launch_tpr<40, 0>(a, cfg);
-    case 8: return launch_tpr<48, 0>(a, cfg);
-    case 9: return launch_tpr<64, 0>(a, cfg);
-    case 10: wpr_kernel<4><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 11: wpr_kernel<8><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 12: wpr_kernel<16><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 13: wpr_kernel<32><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 2: return launch_tpr<10, 0>(a, cfg);
+    case 3: return launch_tpr<12, 0>(a, cfg);
+    case 4: return launch_tpr<14, 0>(a, cfg);
+    case 5: return launch_tpr<16, 0>(a, cfg);
+    case 6: return launch_tpr<18, 0>(a, cfg);
+    case 7: return launch_tpr<20, 0>(a, cfg);
+    case 8: return launch_tpr<22, 0>(a, cfg);
+    case 9: return launch_tpr<24, 0>(a, cfg);
+    case 10: return launch_tpr<28, 0>(a, cfg);
+    case 11: return launch_tpr<32, 0>(a, cfg);
+    case 12: return launch_tpr<40, 0>(a, cfg);
+    case 13: return launch_tpr<48, 0>(a, cfg);
+    case 14: return launch_tpr<64, 0>(a, cfg);
+    case 15: wpr_kernel<4><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 16: wpr_kernel<8><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 17: wpr_kernel<16><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case 18: wpr_kernel<32><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
     default: blk_kernel<<<cfg.sm_count, BLK_THREADS, BLK_SMEM, cfg.stream>>>(a); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
