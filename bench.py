@@ -215,9 +215,16 @@ def run_ours(args):
         except Exception:
             pass
     hbm_achieved = n * w_hbm / (kernel_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["pb_tpr<K=4>"]["dram_bytes_per_read"] * n
+    except Exception:
+        pass
     roofline = {
         "bound": "fp64", "kernel": kname, "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "TFLOP/s",
-        "frac": achieved / peak_ops, "traffic": None,
+        "frac": achieved / peak_ops, "traffic": traffic,
         "peak_source": "moira_fp64_peak: register-resident non-fused DMUL/DADD probe, measured live in this run",
         "flop_per_read": w_fp64, "kernel_ms": kernel_ms,
         "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
@@ -257,6 +264,49 @@ def run_ours(args):
                "d2h_bytes_per_step": n * 13 + L.N_COUNTERS * 8, "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
                "api": "moira_filter_batch (pinned host slab -> chunked H2D/kernels/D2H on two streams)"}
 
+    # ---- other --error_calc modes on the same resident slab (kernel-only, decision mode) --------------
+    modes = {}
+    for calc in ("poisson", "expected_error"):
+        pm = FilterParams(error_calc=calc, alpha=ALPHA, uncert=UNCERT, exact_ee=False)
+        for _ in range(2):
+            step(pm)
+        ms_m, _, _, _ = timed(pm, 5)
+        modes[calc] = {"value": world * n * 5 / (ms_m * 1e-3), "unit": "reads/s"}
+
+    # ---- end to end INCLUDING host parsing: FASTQ text -> C parser (all host threads) -> filter ------
+    e2e_parse = None
+    if not args.no_e2e:
+        m = min(n, 2_000_000)
+        rows = slab[:m].cpu().numpy()
+        rec = np.empty((m, 10 + READ_LEN + 3 + READ_LEN + 1), dtype=np.uint8)
+        ids = np.char.zfill(np.arange(m).astype("U8"), 8)
+        rec[:, 0] = ord("@"); rec[:, 1] = ord("r")
+        rec[:, 2:10] = np.frombuffer("".join(ids.tolist()).encode(), dtype=np.uint8).reshape(m, 8)
+        q = rows[:, :READ_LEN]
+        isn = q == 0xFF
+        rec[:, 10] = 10
+        rec[:, 11:11 + READ_LEN] = np.where(isn, ord("N"), ord("A"))
+        rec[:, 11 + READ_LEN:14 + READ_LEN] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+        rec[:, 14 + READ_LEN:14 + 2 * READ_LEN] = np.where(isn, 2, q) + 33
+        rec[:, -1] = 10
+        text = rec.tobytes()
+        del rec, rows, q, isn, ids
+        def parse_step():
+            sl, of, ln_, *_ = moira_b200.parse_fastq(text, 33, True)
+            return ctx.filter_batch(sl, of, ln_, p_dec)
+        r0 = parse_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            r0 = parse_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / 3
+        e2e_parse = {"value": world * m / dt, "unit": "reads/s", "reads": m, "fastq_bytes": len(text),
+                     "text_gb_per_s": len(text) / dt / 1e9, "host_threads": os.cpu_count(),
+                     "accepted": int(r0.counters[L.CNT_ACCEPTED]),
+                     "api": "moira_parse_fastq (pageable FASTQ text, all host threads) + moira_filter_batch"}
+        del text
+
     # ---- CPU baseline: the reference's own C core on this box's host cores (rank 0, N = 1) ------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -281,7 +331,7 @@ def run_ours(args):
                        "l2": "inputs (2.56 GB/GPU) larger than L2; no flush", "accepted_fraction": accepted_frac,
                        "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU, NCCL all-reduce of 80 counters per step"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
+            "clocks": sampler.summary(), "modes": modes, "e2e_parse": e2e_parse,
             "exact_ee": {"value": value_exact, "unit": "reads/s", "note": "exact statistic for every read (escalation ladder), device-resident"},
         }
         print(json.dumps(line))

@@ -194,6 +194,9 @@ MOIRA_API int moira_parse_fastq(const char *text, uint64_t text_bytes, int fastq
                       uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off,
                       uint64_t *qual_off, uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out);
 
+/* Host threads used by moira_parse_fastq (0 = one per hardware thread, at most 64). */
+MOIRA_API int moira_set_host_threads(int n);
+
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 
 /* Register-resident FP64 issue-rate micro-benchmark (non-fused DMUL/DADD in the kernel's own

@@ -123,3 +123,38 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 for needle in ("import oracle", "from oracle", "liboracle", "oracle/", "py_oracle", "_ref"):
                     assert needle not in src, (f, needle)
+
+
+def test_parse_fastq_multithreaded_equals_single_thread():
+    """>= 1 MB of FASTQ takes the parallel path (ranges cut anywhere, also inside records whose
+    quality line starts with '@'); results must equal the one-thread parse."""
+    rng = np.random.default_rng(12)
+    recs = []
+    for i in range(6000):
+        L_ = int(rng.integers(1, 400))
+        seq = "".join(rng.choice(list("ACGTNn"), size=L_, p=[.24, .24, .24, .24, .03, .01]))
+        q = rng.integers(33, 74, size=L_)
+        if i % 3 == 0:
+            q[0] = ord("@")                       # '@' as a quality character must not start a record
+        if i % 5 == 0:
+            q[-1] = ord("+")
+        recs.append("@r%d:x desc\n%s\n+r%d\n%s\n" % (i, seq, i, q.astype(np.uint8).tobytes().decode()))
+    text = "".join(recs).encode() + b"@partial\nACGT\n+\n"
+    assert len(text) > (1 << 20)
+    outs = []
+    for threads in (1, 7, 16):
+        assert L.lib.moira_set_host_threads(threads) == 0
+        outs.append(moira_b200.parse_fastq(text, 33, True))
+    L.lib.moira_set_host_threads(0)
+    assert len(outs[0][2]) == 6000
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+    # errors are reported for the first bad record, whatever the thread count
+    bad = "".join(recs[:3000]).encode() + b"@bad\nACGT\n+\nIII\n" + "".join(recs[3000:]).encode()
+    for threads in (1, 9):
+        L.lib.moira_set_host_threads(threads)
+        with pytest.raises(moira_b200.MoiraError) as ei:
+            moira_b200.parse_fastq(bad, 33, True)
+        assert ei.value.code == L.ERR_PARSE and "record 3000" in ei.value.message and "LengthMismatchError" in ei.value.message
+    L.lib.moira_set_host_threads(0)
