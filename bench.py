@@ -278,7 +278,7 @@ def run_ours(args):
     if not args.no_e2e:
         m = min(n, 2_000_000)
         rows = slab[:m].cpu().numpy()
-        rec = np.empty((m, 10 + READ_LEN + 3 + READ_LEN + 1), dtype=np.uint8)
+        rec = np.empty((m, 10 + 1 + READ_LEN + 3 + READ_LEN + 1), dtype=np.uint8)
         ids = np.char.zfill(np.arange(m).astype("U8"), 8)
         rec[:, 0] = ord("@"); rec[:, 1] = ord("r")
         rec[:, 2:10] = np.frombuffer("".join(ids.tolist()).encode(), dtype=np.uint8).reshape(m, 8)

@@ -1,6 +1,7 @@
 // moira_api.cu -- C ABI (include/moira_b200.h) over the kernels in moira_kernels.cu:
 // context, lookup tables, pass orchestration (first pass + escalation ladder, all enqueued
 // without host synchronisation), and the chunked host<->device pipeline.
+#include <cuda.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -73,6 +74,7 @@ struct moira_ctx {
     Workspace ws[3];          // [0],[1]: pipeline streams; [2]: moira_filter_device on a caller stream
     Ticket tickets[MOIRA_MAX_INFLIGHT];
     uint64_t launches = 0;
+    int use_tma = 1;
     int timing = 0;
     int n_timed = 0;
     cudaEvent_t t0[MAX_TIMED], t1[MAX_TIMED];
@@ -165,6 +167,41 @@ double normal_quantile(double p)
     return z < 0.0 ? 0.0 : z;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D uint8 tensor over `rows` slab rows of `stride` bytes; box = 128 bytes x 32 rows, 128-byte swizzle.
+bool make_slab_tmap(CUtensorMap *tm, const uint8_t *d_rows, uint64_t stride, uint64_t rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || stride < 16 || (stride & 15u) || rows == 0 || rows >= (1ull << 31)) return false;
+    cuuint64_t gdim[2] = {stride, rows};
+    cuuint64_t gstr[1] = {stride};
+    cuuint32_t box[2] = {128, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(d_rows), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int first_pass_k_template(int k_wanted)
 {
     static const int ks[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 20, 22, 24, 28, 32};
@@ -230,6 +267,11 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             a.queues = ws.queues; a.queue_counts = ws.counts; a.queue_cap = ws.cap;
             CU(cudaMemsetAsync(ws.counts, 0, NB * sizeof(uint32_t), stream));
         }
+        // uniform-stride slab: feed the first pass with TMA tensor tiles of this sub-batch's rows
+        CUtensorMap tmap;
+        cfg.tmap = nullptr;
+        if (!d_offsets && c->use_tma && make_slab_tmap(&tmap, d_slab + start * stride, stride, n))
+            cfg.tmap = &tmap;   // tile t of the launch = rows [32 t, 32 t + 32) of this map
         const bool timed = c->timing && c->n_timed < MAX_TIMED;
         if (timed) CU(cudaEventRecord(c->t0[c->n_timed], stream));
         const char *name = "";
@@ -290,6 +332,7 @@ int moira_ctx_create(int device, moira_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     build_tables(c->h_p, c->h_q, c->h_e, &c->e_equals_p);
+    if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
     if (kernels_init(c->sm_count)) {
         int rc = fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;

@@ -65,6 +65,7 @@ struct FilterArgs {
 struct LaunchCfg {
     int sm_count;
     cudaStream_t stream;
+    const void *tmap = nullptr;   // CUtensorMap of the sub-batch's slab when the first pass may use TMA tiles
 };
 
 // first pass, thread-per-read; k_wanted is rounded up to an instantiated K (returned)

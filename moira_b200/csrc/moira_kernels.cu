@@ -21,6 +21,7 @@
 //                 P[l*M .. l*M+M-1], the neighbour entry travels by warp shuffle.
 //   pb_blk        block-per-read, P in shared memory, any K up to 24576: last rung.
 //   fp64_peak     register-resident DMUL/DADD issue-rate probe (roofline denominator).
+#include <cuda.h>
 #include <math.h>
 
 #include "fact_table.h"
@@ -104,6 +105,15 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// TMA tensor-tile copy global -> shared (SASS: UTMALDG): one 2-D box {x .. x+127 bytes, y .. y+31 rows}
+// of the slab, written with the 128-byte swizzle; completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *tmap, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr)
 {
@@ -339,20 +349,21 @@ __device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_l
 // which the first `rem0` belong to this lane's read (the rest is masked to padding).  The first
 // `cfull` bytes (warp-uniform, multiple of 16) are inside the read for EVERY lane: no masking there.
 // MATH = false keeps only the N/n accounting (after a warp-wide early exit).
+// `swz` is the lane's XOR term of the TMA 128-byte swizzle ((lane & 7) << 4), 0 for the padded layout.
 template <int K, int MODE, bool PL, bool MATH>
-__device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t cfull, uint32_t cend, int rem0, uint32_t lut_lane,
-                                            double (&P)[K], uint32_t &ns, uint32_t &has_n)
+__device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t swz, uint32_t cfull, uint32_t cend, int rem0,
+                                            uint32_t lut_lane, double (&P)[K], uint32_t &ns, uint32_t &has_n)
 {
     uint32_t v = 0;
     for (; v < cfull; v += 16) {
-        const uint4 q4 = lds128(row + v);
+        const uint4 q4 = lds128(row + (v ^ swz));
         const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
         count_marks4(w, ns, has_n);
         if (MATH) sweep_vec<K, MODE, PL>(w, lut_lane, P);
     }
     for (; v < cend; v += 16) {
         uint32_t w[4];
-        load_vec(row + v, rem0 - (int)v, w, ns, has_n);
+        load_vec(row + (v ^ swz), rem0 - (int)v, w, ns, has_n);
         if (MATH) sweep_vec<K, MODE, PL>(w, lut_lane, P);
     }
 }
@@ -362,11 +373,14 @@ __device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t cfull, uint32
 // ==================================================================================================
 // MODE 0: Poisson-binomial with K entries.  MODE 1: Lambda accumulation (K == 1).
 // MODE 2: ladder classifier (K == 2): mean/variance of the error count -> rung.
-template <int K, int MODE, bool EQP>
-__global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterArgs a)
+// TMA: uniform-stride first pass; tiles arrive as swizzled 2-D tensor boxes (one UTMALDG per warp and
+// chunk) instead of cp.async pieces.
+template <int K, int MODE, bool EQP, bool TMA>
+__global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int TPR_WARPS = tpr_warps(K);
     constexpr int TPR_THREADS = TPR_WARPS * 32;
+    constexpr uint32_t STG = TMA ? 32u * CHUNK : (uint32_t)STAGE_BYTES;   // bytes of one warp-stage
     extern __shared__ __align__(128) uint8_t smem[];
     if (a.queue && *a.queue_count == 0) return;   // empty rung: nothing to set up
     const int lane = threadIdx.x & 31;
@@ -378,10 +392,12 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
     //   [lut + 64 KB, ...)     stage buffers of the remaining warps, then counters + histogram
     const uint32_t base = smem_u32(smem);
     const uint32_t lut = (base + 0xFFFFu) & ~0xFFFFu;
-    const uint32_t n_below = min((lut - base) / (2u * STAGE_BYTES), (uint32_t)TPR_WARPS);
+    const uint32_t below0 = (base + 1023u) & ~1023u;           // stage buffers are 1 KB aligned (TMA swizzle atom)
+    const uint32_t n_below = min((lut - below0) / (2u * STG), (uint32_t)TPR_WARPS);
     const uint32_t above = lut + LUT_BYTES;
-    const uint32_t cnt_addr = above + (TPR_WARPS - n_below) * 2u * STAGE_BYTES;
-    if (cnt_addr + (16 + MOIRA_N_HIST) * 4 - base > (uint32_t)TPR_SMEM) __trap();   // cannot happen for base <= 1 KB
+    const uint32_t cnt_addr = above + (TPR_WARPS - n_below) * 2u * STG;
+    const uint32_t bar_addr = cnt_addr + (16 + MOIRA_N_HIST) * 4;
+    if (bar_addr + TPR_WARPS * 16 - base > (uint32_t)TPR_SMEM) __trap();   // cannot happen for base <= 1 KB
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + (cnt_addr - base));
     uint32_t *s_hist = s_cnt + 16;
     uint8_t *lut_ptr = smem + (lut - base);
@@ -402,12 +418,21 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
         }
     }
     for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += TPR_THREADS) s_cnt[i] = 0;
+    const uint32_t bar0 = bar_addr + warp * 16;
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(bar0, 1);
+            mbar_init(bar0 + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
 
     const uint32_t lut_lane = lut + (PL ? lane * 8 : (lane & 15) * 16);
-    const uint32_t stage_warp = (uint32_t)warp < n_below ? base + warp * 2 * STAGE_BYTES
-                                                         : above + (warp - n_below) * 2 * STAGE_BYTES;
-    const uint32_t stage0 = stage_warp + lane * ROW_STRIDE;
+    const uint32_t stage_warp = (uint32_t)warp < n_below ? below0 + warp * 2 * STG : above + (warp - n_below) * 2 * STG;
+    const uint32_t stage0 = stage_warp + lane * (TMA ? CHUNK : ROW_STRIDE);
+    const uint32_t swz = TMA ? (lane & 7) << 4 : 0u;
 
     const uint32_t count = a.queue ? *a.queue_count : a.n;
     const uint32_t n_tiles = (count + 31) >> 5;
@@ -430,10 +455,18 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
     // and instruction.  First pass: the warp copies cooperatively -- 8 consecutive lanes fetch one
     // whole 128-byte line of one row, so every global request is a full line.  Ladder passes (rows
     // scattered through the slab): every lane copies its own row.  One commit group per job.
-    auto issue = [&](const ReadGeom &g, uint32_t c, uint32_t s) {
+    auto issue = [&](const ReadGeom &g, uint32_t t, uint32_t c, uint32_t s) {
+        if (TMA) {
+            if (lane == 0) {
+                const uint32_t bar = bar0 + (s & 1) * 8;
+                mbar_arrive_expect_tx(bar, 32u * CHUNK);
+                tma_tile_g2s(stage_warp + (s & 1) * STG, &tmap, (int)(c * CHUNK), (int)(t * 32u), bar);
+            }
+            return;
+        }
         const uint32_t padded = (g.eff + 15u) & ~15u;
         const uint32_t begin = c * CHUNK;
-        const uint32_t dst_stage = (s & 1) * STAGE_BYTES;
+        const uint32_t dst_stage = (s & 1) * STG;
         if (coop && !a.offsets && !a.lengths) {
             // uniform stride and length: addresses follow from the tile's first row (lane 0)
             const uint32_t col = (lane & (CHUNK / 16 - 1)) * 16;
@@ -470,7 +503,11 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
         cp_async_commit();
     };
     // wait for the oldest outstanding job of this lane, then make every lane's copies visible
-    auto consume = [&](bool next_issued) {
+    auto consume = [&](bool next_issued, uint32_t job) {
+        if (TMA) {
+            mbar_wait(bar0 + (job & 1) * 8, (job >> 1) & 1);
+            return;
+        }
         if (next_issued) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncwarp();
     };
@@ -479,7 +516,7 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
     uint32_t r_local, nr_local;
     ReadGeom g, ng;
     tile_read(tile, valid, r_local, g);
-    if (tile < n_tiles) issue(g, 0, it);
+    if (tile < n_tiles) issue(g, tile, 0, it);
 
     while (tile < n_tiles) {
         const uint32_t next_tile = tile + total_warps;
@@ -499,24 +536,24 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
         if (nch == 0) {   // tile of empty reads: its (empty) stage job still has to be consumed
             const bool nx = next_tile < n_tiles;
             __syncwarp();
-            if (nx) issue(ng, 0, it + 1);
-            consume(nx);
+            if (nx) issue(ng, next_tile, 0, it + 1);
+            consume(nx, it);
             it++;
         }
         for (uint32_t c = 0; c < nch; c++) {
             const bool nx = c + 1 < nch || next_tile < n_tiles;
             __syncwarp();   // every lane is done reading the stage the next job overwrites
-            if (c + 1 < nch) issue(g, c + 1, it + 1);
-            else if (next_tile < n_tiles) issue(ng, 0, it + 1);
-            consume(nx);
-            const uint32_t row = stage0 + (it & 1) * STAGE_BYTES;
+            if (c + 1 < nch) issue(g, tile, c + 1, it + 1);
+            else if (next_tile < n_tiles) issue(ng, next_tile, 0, it + 1);
+            consume(nx, it);
+            const uint32_t row = stage0 + (it & 1) * STG;
             it++;
 
             const uint32_t cbeg = c * CHUNK;
             const uint32_t cend = maxeff - cbeg < CHUNK ? maxeff - cbeg : CHUNK;   // warp-uniform
             const uint32_t cfull = mineff > cbeg ? min((mineff - cbeg) & ~15u, cend) : 0u;   // warp-uniform
-            if (!skip_math) sweep_chunk<K, MODE, PL, true>(row, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
-            else sweep_chunk<K, MODE, PL, false>(row, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+            if (!skip_math) sweep_chunk<K, MODE, PL, true>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+            else sweep_chunk<K, MODE, PL, false>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
             if (!skip_math) processed = cbeg + cend;
             if (MODE == 0 && c + 1 < nch && !skip_math) {
                 // Early exit: sum_{j<K} P_k[j] never increases with k, so once it is safely below
@@ -820,21 +857,33 @@ __global__ void __launch_bounds__(512) fp64_peak_kernel(int iters, double *sink,
     if (s == 123.456) sink[0] = s;
 }
 
+const CUtensorMap g_no_tmap = {};
+
 template <int K, int MODE>
 int launch_tpr(const FilterArgs &a, const LaunchCfg &cfg)
 {
     constexpr int W = tpr_warps(K);
-    if (a.e_equals_p) tpr_kernel<K, MODE, true><<<cfg.sm_count, W * 32, TPR_SMEM, cfg.stream>>>(a);
-    else tpr_kernel<K, MODE, false><<<cfg.sm_count, W * 32, TPR_SMEM, cfg.stream>>>(a);
+    if (a.e_equals_p) tpr_kernel<K, MODE, true, false><<<cfg.sm_count, W * 32, TPR_SMEM, cfg.stream>>>(a, g_no_tmap);
+    else tpr_kernel<K, MODE, false, false><<<cfg.sm_count, W * 32, TPR_SMEM, cfg.stream>>>(a, g_no_tmap);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// first-pass variant fed by TMA tensor tiles (uniform-stride slabs)
 template <int K, int MODE>
-int init_tpr()
+int launch_tpr_tma(const FilterArgs &a, const LaunchCfg &cfg)
 {
     constexpr int W = tpr_warps(K);
-    if (cudaFuncSetAttribute(tpr_kernel<K, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(tpr_kernel<K, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    const CUtensorMap &tm = *static_cast<const CUtensorMap *>(cfg.tmap);
+    if (a.e_equals_p) tpr_kernel<K, MODE, true, true><<<cfg.sm_count, W * 32, TPR_SMEM, cfg.stream>>>(a, tm);
+    else tpr_kernel<K, MODE, false, true><<<cfg.sm_count, W * 32, TPR_SMEM, cfg.stream>>>(a, tm);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <int K, int MODE, bool TMA>
+int init_tpr()
+{
+    if (cudaFuncSetAttribute(tpr_kernel<K, MODE, true, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(tpr_kernel<K, MODE, false, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -846,11 +895,11 @@ int max_first_pass_k() { return 32; }
 
 int kernels_init(int)
 {
-#define X(k) if (init_tpr<k, 0>()) return -1;
+#define X(k) if (init_tpr<k, 0, false>() || init_tpr<k, 0, true>()) return -1;
     MOIRA_FOR_EACH_K(X)
-    X(40) X(48) X(64)
 #undef X
-    if (init_tpr<1, 1>() || init_tpr<2, 2>()) return -1;
+    if (init_tpr<40, 0, false>() || init_tpr<48, 0, false>() || init_tpr<64, 0, false>()) return -1;
+    if (init_tpr<1, 1, false>() || init_tpr<1, 1, true>() || init_tpr<2, 2, false>()) return -1;
     if (cudaFuncSetAttribute(blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM) != cudaSuccess) return -1;
     return 0;
 }
@@ -865,24 +914,26 @@ int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, con
 #define X(k)                                                   \
     if (k_wanted <= k) {                                       \
         if (name) *name = names[idx];                          \
-        return launch_tpr<k, 0>(a, cfg) ? -1 : k;              \
+        return (cfg.tmap ? launch_tpr_tma<k, 0>(a, cfg) : launch_tpr<k, 0>(a, cfg)) ? -1 : k; \
     }                                                          \
     idx++;
     MOIRA_FOR_EACH_K(X)
 #undef X
     if (name) *name = names[16];
-    return launch_tpr<32, 0>(a, cfg) ? -1 : 32;
+    return (cfg.tmap ? launch_tpr_tma<32, 0>(a, cfg) : launch_tpr<32, 0>(a, cfg)) ? -1 : 32;
 }
 
 int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name)
 {
     if (name) *name = "lambda_tpr";
-    return launch_tpr<1, 1>(a, cfg);
+    return cfg.tmap ? launch_tpr_tma<1, 1>(a, cfg) : launch_tpr<1, 1>(a, cfg);
 }
 
-int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg)
+int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg0)
 {
     FilterArgs a = a0;
+    LaunchCfg cfg = cfg0;
+    cfg.tmap = nullptr;
     a.rung = b;
     a.queue = a0.queues + (size_t)b * a0.queue_cap;
     a.queue_count = a0.queue_counts + b;

@@ -1,0 +1,110 @@
+#!/usr/bin/env python3
+"""Turn the scratch ncu captures under gpurun_out/ into the committed summaries under profiles/.
+
+  python tools/summarize_profiles.py r01     # reads gpurun_out/r01_launches.csv, gpurun_out/r01_pb_tpr4.ncu-rep
+Writes profiles/<tag>_launches.csv (our kernels only, per launch), profiles/<tag>_launches_summary.md,
+profiles/<tag>_pb_tpr4_ncu.md (key counters of the dominant kernel) and profiles/traffic.json
+(dram bytes per read of the dominant kernel, used by bench.py's roofline.traffic)."""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+reads = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
+out = os.path.join(ROOT, "profiles")
+os.makedirs(out, exist_ok=True)
+
+# ---- launch list ------------------------------------------------------------------------------------
+rows = list(csv.reader(open(os.path.join(ROOT, "gpurun_out", "%s_launches.csv" % tag))))
+hdr, ours, agg, total_all = None, [], collections.OrderedDict(), 0.0
+for r in rows:
+    if "Kernel Name" in r:
+        hdr = r
+        continue
+    if hdr is None or len(r) != len(hdr):
+        continue
+    d = dict(zip(hdr, r))
+    ns = float(d["Metric Value"].replace(",", ""))
+    total_all += ns
+    if "moira" in d["Kernel Name"]:
+        ours.append((d["ID"], d["Kernel Name"], d["Grid Size"], d["Block Size"], ns))
+        a = agg.setdefault(d["Kernel Name"], [0, 0.0])
+        a[0] += 1
+        a[1] += ns
+with open(os.path.join(out, "%s_launches.csv" % tag), "w") as fh:
+    fh.write("id,kernel,grid,block,gpu__time_duration_ns\n")
+    for o in ours:
+        fh.write('%s,"%s","%s","%s",%.0f\n' % o)
+tot = sum(a[1] for a in agg.values())
+with open(os.path.join(out, "%s_launches_summary.md" % tag), "w") as fh:
+    fh.write("# %s: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu`\n\n" % tag)
+    fh.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare shares).\n")
+    fh.write("Only this repo's kernels are listed; the torch kernels of the synthetic-data generator (%.1f ms) are not.\n\n" % ((total_all - tot) / 1e6))
+    fh.write("| kernel | launches | total ms | share of our kernels | mean us |\n|---|---|---|---|---|\n")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        fh.write("| `%s` | %d | %.3f | %.1f %% | %.1f |\n" % (k.replace("moira::<unnamed>::", ""), a[0], a[1] / 1e6, 100 * a[1] / tot, a[1] / a[0] / 1e3))
+    fh.write("\nThe decision-mode step is one `tpr_kernel<4,0,1>` launch (pb_tpr<K=4>); exact-ee steps add the classifier\n"
+             "(`tpr_kernel<2,2,1>`) and the ladder rungs. `fp64_peak_kernel` is the roofline probe, outside the timed region.\n")
+
+# ---- full capture of the dominant kernel ---------------------------------------------------------------
+rep = os.path.join(ROOT, "gpurun_out", "%s_pb_tpr4.ncu-rep" % tag)
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines()))
+h, units, vals = rr[0], rr[1], rr[2]
+d = dict(zip(h, vals))
+u = dict(zip(h, units))
+want = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg.per_second", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
+]
+def num(x):
+    return float(x.replace(",", ""))
+def to_bytes(key):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u[key]]
+    return num(d[key]) * scale
+traffic = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+with open(os.path.join(out, "%s_pb_tpr4_ncu.md" % tag), "w") as fh:
+    fh.write("# %s: `ncu --set full --clock-control none` of the dominant kernel `%s`\n\n" % (tag, d.get("Kernel Name", "")))
+    fh.write("Workload: %d reads x 253 bp (bench.py C2), one launch.  Raw report kept in gpurun_out/ (scratch).\n\n" % reads)
+    fh.write("| metric | value | unit |\n|---|---|---|\n")
+    for k in want:
+        if k in d:
+            fh.write("| %s | %s | %s |\n" % (k, d[k], u[k]))
+    fh.write("\nDRAM traffic per launch: %.4g bytes = %.1f bytes/read (algorithmic: 272 B/read -> %.4g bytes).\n" % (traffic, traffic / reads, 272.0 * reads))
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    sr = list(csv.reader(src.splitlines()))
+    sh = sr[1]
+    ix = {n: i for i, n in enumerate(sh)}
+    cnt = collections.Counter()
+    for r in sr[2:]:
+        if len(r) < len(sh) or r[0] in ("Address", "Kernel Name"):
+            continue
+        t = r[ix["Source"]].split()
+        op = (t[1] if t[0].startswith("@") else t[0]).split(".")[0]
+        cnt[op] += int(r[ix["Instructions Executed"]])
+    base_warps = reads * 253 / 32
+    fh.write("\nExecuted warp instructions per base-warp (reads x 253 / 32 = %.4g base-warps):\n\n| opcode | per base |\n|---|---|\n" % base_warps)
+    for op, c in cnt.most_common(16):
+        fh.write("| %s | %.3f |\n" % (op, c / base_warps))
+    fh.write("| **total** | %.3f |\n" % (sum(cnt.values()) / base_warps))
+json.dump({"pb_tpr<K=4>": {"dram_bytes_per_read": traffic / reads, "source": "profiles/%s_pb_tpr4_ncu.md" % tag}},
+          open(os.path.join(out, "traffic.json"), "w"), indent=1)
+print(open(os.path.join(out, "%s_pb_tpr4_ncu.md" % tag)).read())
+print(open(os.path.join(out, "%s_launches_summary.md" % tag)).read())
