@@ -121,6 +121,32 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa(torch_index):
+    """Multi-rank runs: pin this rank (and the pinned buffers it allocates, first touch) to the CPUs
+    local to its GPU so that 8 ranks do not all stream host memory through one socket."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        cpus = set()
+        for part in open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -134,6 +160,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.reads
@@ -260,9 +287,9 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         assert int(out.counters[L.CNT_READS]) == n, "e2e pass did not process every read"
-        e2e = {"value": world * n * e_steps / dt, "unit": "reads/s", "h2d_bytes_per_step": n * STRIDE + n * 12,
+        e2e = {"value": world * n * e_steps / dt, "unit": "reads/s", "h2d_bytes_per_step": n * STRIDE,
                "d2h_bytes_per_step": n * 13 + L.N_COUNTERS * 8, "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
-               "api": "moira_filter_batch (pinned host slab -> chunked H2D/kernels/D2H on two streams)"}
+               "api": "moira_filter_batch (pinned host slab -> chunked H2D/kernels/D2H on two streams; uniform rows: offsets/lengths stay on the host)"}
 
     # ---- other --error_calc modes on the same resident slab (kernel-only, decision mode) --------------
     modes = {}
@@ -291,9 +318,12 @@ def run_ours(args):
         rec[:, -1] = 10
         text = rec.tobytes()
         del rec, rows, q, isn, ids
+        h_out2 = moira_b200.PinnedBuffer(m * 13 + 4096)
+        out2 = moira_b200.FilterResult(h_out2.view(np.float64, m), h_out2.view(np.int32, m, m * 8),
+                                       h_out2.view(np.uint8, m, m * 12), np.zeros(L.N_COUNTERS, np.uint64))
+
         def parse_step():
-            sl, of, ln_, *_ = moira_b200.parse_fastq(text, 33, True)
-            return ctx.filter_batch(sl, of, ln_, p_dec)
+            return ctx.filter_fastq(text, p_dec, 33, out2)[0]
         r0 = parse_step()
         barrier()
         t0 = time.perf_counter()
@@ -304,7 +334,7 @@ def run_ours(args):
         e2e_parse = {"value": world * m / dt, "unit": "reads/s", "reads": m, "fastq_bytes": len(text),
                      "text_gb_per_s": len(text) / dt / 1e9, "host_threads": os.cpu_count(),
                      "accepted": int(r0.counters[L.CNT_ACCEPTED]),
-                     "api": "moira_parse_fastq (pageable FASTQ text, all host threads) + moira_filter_batch"}
+                     "api": "moira_filter_fastq: FASTQ text in host memory -> parse ranges on all host threads -> pinned slabs -> async submits"}
         del text
 
     # ---- CPU baseline: the reference's own C core on this box's host cores (rank 0, N = 1) ------------
@@ -329,7 +359,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "reads_per_gpu": n, "read_len": READ_LEN, "row_stride": STRIDE,
                        "error_calc": "poisson_binomial", "mode": "decision (exact ee for accepted reads, lower bound for certain rejects)",
                        "l2": "inputs (2.56 GB/GPU) larger than L2; no flush", "accepted_fraction": accepted_frac,
-                       "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU, NCCL all-reduce of 80 counters per step"},
+                       "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU, NCCL all-reduce of 80 counters per step",
+                       "rank_cpu_affinity": numa_cpus},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "modes": modes, "e2e_parse": e2e_parse,
             "exact_ee": {"value": value_exact, "unit": "reads/s", "note": "exact statistic for every read (escalation ladder), device-resident"},

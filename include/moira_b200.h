@@ -194,6 +194,19 @@ MOIRA_API int moira_parse_fastq(const char *text, uint64_t text_bytes, int fastq
                       uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off,
                       uint64_t *qual_off, uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out);
 
+/* Number of complete 4-line records in a FASTQ text buffer (to size the output arrays). */
+MOIRA_API int moira_fastq_count_reads(const char *text, uint64_t text_bytes, uint64_t *n_reads_out);
+
+/* FASTQ text in, decisions out, in one call: the text is cut into ~64 MB ranges that are parsed (all
+ * host threads, moira_parse_fastq semantics) into pinned slabs and submitted asynchronously, so the
+ * parser of range k+1 overlaps the copies and kernels of range k (the batched replacement of the
+ * reference's read-parse-process loop, moira.py:416-487).  Outputs are in input order; lengths_out
+ * (may be NULL) receives the read lengths; counters_out is the sum over all ranges. */
+MOIRA_API int moira_filter_fastq(moira_ctx *ctx, const char *text, uint64_t text_bytes, int fastq_offset,
+                                 int lower_n_ambiguous, const moira_params *params, uint64_t max_reads,
+                                 double *ee_out, int32_t *ns_out, uint8_t *flags_out, uint32_t *lengths_out,
+                                 uint64_t *counters_out, uint64_t *n_reads_out);
+
 /* Host threads used by moira_parse_fastq (0 = one per hardware thread, at most 64). */
 MOIRA_API int moira_set_host_threads(int n);
 

@@ -214,6 +214,22 @@ class Context:
         L.check(lib.moira_filter_device(self._h, d_slab, d_offsets, d_lengths, int(stride), int(fixed_length),
                                         int(n_reads), ctypes.byref(cp), d_ee, d_ns, d_flags, d_counters, stream))
 
+    def filter_fastq(self, text: bytes, params: FilterParams, fastq_offset: int = 33, out: FilterResult | None = None):
+        """FASTQ text -> FilterResult in one streaming C call (moira_filter_fastq); also returns lengths."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        n = ctypes.c_uint64()
+        L.check(lib.moira_fastq_count_reads(_ptr(buf), buf.nbytes, ctypes.byref(n)))
+        nr = n.value
+        if out is None:
+            out = FilterResult(np.empty(nr, np.float64), np.empty(nr, np.int32), np.empty(nr, np.uint8),
+                               np.zeros(L.N_COUNTERS, np.uint64))
+        lengths = np.empty(nr, np.uint32)
+        cp = params.to_c()
+        L.check(lib.moira_filter_fastq(self._h, _ptr(buf), buf.nbytes, int(fastq_offset), int(params.lower_n_ambiguous),
+                                       ctypes.byref(cp), nr, _ptr(out.ee), _ptr(out.ns), _ptr(out.flags), _ptr(lengths),
+                                       _ptr(out.counters), ctypes.byref(n)))
+        return out, lengths
+
     def calculate_errors_PB(self, contig: str, contig_quals, alpha: float):
         """One read through the CUDA path (moira_calculate_errors_PB)."""
         q = np.ascontiguousarray(contig_quals, dtype=np.int32)
@@ -274,6 +290,7 @@ def pack_arrays(seq_all, q_all, in_off, lengths, lower_n_ambiguous: bool = True,
 
 def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = True):
     """FASTQ bytes -> (slab, offsets, lengths, hdr_off, hdr_len, seq_off, qual_off) via moira_parse_fastq.
+    Rows parsed by different host threads are separated by a little slack in the slab (offsets skip it).
     Raises MoiraError(ERR_PARSE) with the reference's error class name in the message
     (EmptySeqError / EmptyQualError / LengthMismatchError, moira.py:1178-1183)."""
     buf = np.frombuffer(text, dtype=np.uint8)
@@ -292,6 +309,7 @@ def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = T
     L.check(lib.moira_parse_fastq(_ptr(buf), buf.nbytes, int(fastq_offset), int(lower_n_ambiguous), _ptr(slab),
                                   slab.nbytes, _ptr(offsets), _ptr(lengths), _ptr(hdr_off), _ptr(hdr_len),
                                   _ptr(seq_off), _ptr(qual_off), nr, ctypes.byref(n), ctypes.byref(nb)))
+    slab = slab[:max(16, nb.value)]   # the sizing call returns an upper bound, the fill call the bytes in use
     return slab, offsets, lengths, hdr_off, hdr_len, seq_off, qual_off
 
 

@@ -41,6 +41,41 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// pinned parse buffers of one streaming slot (moira_filter_fastq)
+struct StreamBuf {
+    uint8_t *slab = nullptr;
+    uint64_t *offsets = nullptr;
+    uint32_t *lengths = nullptr;
+    uint64_t slab_cap = 0, read_cap = 0;
+    int ensure(uint64_t slab_bytes, uint64_t reads)
+    {
+        if (slab_bytes > slab_cap) {
+            if (slab) cudaFreeHost(slab);
+            slab = nullptr; slab_cap = 0;
+            const uint64_t want = slab_bytes + slab_bytes / 4;
+            if (cudaHostAlloc((void **)&slab, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return MOIRA_ERR_NOMEM; }
+            slab_cap = want;
+        }
+        if (reads > read_cap) {
+            if (offsets) cudaFreeHost(offsets);
+            if (lengths) cudaFreeHost(lengths);
+            offsets = nullptr; lengths = nullptr; read_cap = 0;
+            const uint64_t want = reads + reads / 4 + 1024;
+            if (cudaHostAlloc((void **)&offsets, want * 8, cudaHostAllocDefault) != cudaSuccess ||
+                cudaHostAlloc((void **)&lengths, want * 4, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return MOIRA_ERR_NOMEM; }
+            read_cap = want;
+        }
+        return MOIRA_OK;
+    }
+    void release()
+    {
+        if (slab) cudaFreeHost(slab);
+        if (offsets) cudaFreeHost(offsets);
+        if (lengths) cudaFreeHost(lengths);
+        slab = nullptr; offsets = nullptr; lengths = nullptr; slab_cap = read_cap = 0;
+    }
+};
+
 struct Ticket {
     bool busy = false;
     DevBuf slab, offsets, lengths, ee, ns, flags, counters;
@@ -73,6 +108,7 @@ struct moira_ctx {
     cudaEvent_t meta_ready = nullptr;
     Workspace ws[3];          // [0],[1]: pipeline streams; [2]: moira_filter_device on a caller stream
     Ticket tickets[MOIRA_MAX_INFLIGHT];
+    StreamBuf fq[3];
     uint64_t launches = 0;
     int use_tma = 1;
     int timing = 0;
@@ -365,6 +401,7 @@ int moira_ctx_destroy(moira_ctx *c)
         for (int i = 0; i < 2; i++) if (t.done[i]) cudaEventDestroy(t.done[i]);
         if (t.counters_pinned) cudaFreeHost(t.counters_pinned);
     }
+    for (auto &b : c->fq) b.release();
     for (auto &w : c->ws) { if (w.queues) cudaFree(w.queues); if (w.counts) cudaFree(w.counts); }
     for (int i = 0; i < MAX_TIMED; i++) { cudaEventDestroy(c->t0[i]); cudaEventDestroy(c->t1[i]); }
     if (c->meta_ready) cudaEventDestroy(c->meta_ready);
@@ -469,8 +506,6 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
     uint64_t *d_cnt = (uint64_t *)t.counters.p;
 
     cudaStream_t s0 = c->streams[0], s1 = c->streams[1];
-    CU(cudaMemcpyAsync(d_off, offsets, n * 8, cudaMemcpyHostToDevice, s0));
-    CU(cudaMemcpyAsync(d_len, lengths, n * 4, cudaMemcpyHostToDevice, s0));
     CU(cudaMemsetAsync(d_cnt, 0, MOIRA_N_COUNTERS * 8, s0));
     CU(cudaEventRecord(c->meta_ready, s0));
     CU(cudaStreamWaitEvent(s1, c->meta_ready, 0));
@@ -485,6 +520,10 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
         const uint64_t b0 = offsets[start];
         uint32_t max_len = 0;
         uint64_t b1 = b0;
+        // uniform chunk (every row `stride0` bytes after the previous one, all of one length): offsets and
+        // lengths need not travel, and the first pass can be fed by TMA tensor tiles
+        bool uniform = true;
+        const uint64_t stride0 = start + 1 < n ? offsets[start + 1] - offsets[start] : (((uint64_t)lengths[start] + 15u) & ~15ull);
         while (end < n) {
             const uint64_t row_end = offsets[end] + (((uint64_t)lengths[end] + 15u) & ~15ull);
             if (offsets[end] < b0) return fail(MOIRA_ERR_BAD_ARG, "offsets must be non-decreasing (read %llu)", (unsigned long long)end);
@@ -493,14 +532,23 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
             if (end > start && row_end - b0 > CHUNK_BYTES) break;
             b1 = std::max(b1, row_end);
             max_len = std::max(max_len, lengths[end]);
+            uniform = uniform && lengths[end] == lengths[start] && offsets[end] == b0 + (end - start) * stride0;
             end++;
         }
         cudaStream_t s = c->streams[ci & 1];
         const uint64_t copy_end = std::min<uint64_t>(b1, slab_bytes);
         if (copy_end > b0) CU(cudaMemcpyAsync(d_slab + b0, slab + b0, copy_end - b0, cudaMemcpyHostToDevice, s));
         const uint64_t cn = end - start;
-        rc = run_filter_full(c, c->ws[ci & 1], d_slab, d_off + start, d_len + start, 0, 0, cn, params, max_len,
-                             d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
+        uniform = uniform && stride0 >= 16 && (stride0 & 15u) == 0 && stride0 >= lengths[start];
+        if (uniform) {
+            rc = run_filter_full(c, c->ws[ci & 1], d_slab + b0, nullptr, nullptr, stride0, lengths[start], cn, params, max_len,
+                                 d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
+        } else {
+            CU(cudaMemcpyAsync(d_off + start, offsets + start, cn * 8, cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(d_len + start, lengths + start, cn * 4, cudaMemcpyHostToDevice, s));
+            rc = run_filter_full(c, c->ws[ci & 1], d_slab, d_off + start, d_len + start, 0, 0, cn, params, max_len,
+                                 d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
+        }
         if (rc) return rc;
         CU(cudaMemcpyAsync(ee_out + start, d_ee + start, cn * 8, cudaMemcpyDeviceToHost, s));
         if (ns_out) CU(cudaMemcpyAsync(ns_out + start, d_ns + start, cn * 4, cudaMemcpyDeviceToHost, s));
@@ -541,6 +589,68 @@ int moira_filter_batch(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, c
         return rc;
     }
     return moira_wait(c, ticket);
+}
+
+// FASTQ text -> decisions, streaming: ranges of ~64 MB of text are parsed (all host threads) into
+// pinned slabs and submitted asynchronously, so parsing range k+1 overlaps the H2D copy, the kernels
+// and the D2H copy of range k.
+int moira_filter_fastq(moira_ctx *c, const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous,
+                       const moira_params *params, uint64_t max_reads, double *ee_out, int32_t *ns_out,
+                       uint8_t *flags_out, uint32_t *lengths_out, uint64_t *counters_out, uint64_t *n_reads_out)
+{
+    if (!c || (!text && text_bytes) || !ee_out || !n_reads_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    int rc = check_params(params);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    constexpr int SLOTS = 3;
+    const uint64_t RANGE = 64ull << 20;
+    struct Slot { int ticket = -1; uint64_t counters[MOIRA_N_COUNTERS]; };
+    Slot slots[SLOTS];
+    uint64_t total[MOIRA_N_COUNTERS] = {0};
+    auto retire = [&](Slot &s) -> int {
+        if (s.ticket < 0) return MOIRA_OK;
+        int r = moira_wait(c, s.ticket);
+        s.ticket = -1;
+        for (int i = 0; i < MOIRA_N_COUNTERS; i++) total[i] += s.counters[i];
+        return r;
+    };
+    uint64_t pos = 0, n_done = 0;
+    int k = 0;
+    while (pos < text_bytes) {
+        Slot &s = slots[k % SLOTS];
+        if ((rc = retire(s))) break;                       // its pinned buffers are free again
+        StreamBuf &b = c->fq[k % SLOTS];
+        const uint64_t len = std::min<uint64_t>(RANGE, text_bytes - pos);
+        const int final_range = pos + len >= text_bytes;
+        uint64_t n = 0, cap = 0, consumed = 0;
+        // sizing (newline count only), then the single parsing pass into the slot's pinned buffers
+        rc = parse_fastq_range(text + pos, len, fastq_offset, lower_n_ambiguous, nullptr, 0, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, 0, &n, &cap, nullptr, final_range);
+        if (rc) break;
+        if (n_done + n > max_reads) { rc = fail(MOIRA_ERR_BAD_ARG, "more than max_reads = %llu records", (unsigned long long)max_reads); break; }
+        if (n == 0) {
+            if (final_range) break;
+            rc = fail(MOIRA_ERR_PARSE, "a FASTQ record is longer than the %llu-byte streaming range", (unsigned long long)RANGE);
+            break;
+        }
+        if ((rc = b.ensure(cap + 16, n))) break;
+        uint64_t used = 0;
+        rc = parse_fastq_range(text + pos, len, fastq_offset, lower_n_ambiguous, b.slab, b.slab_cap, b.offsets, b.lengths,
+                               nullptr, nullptr, nullptr, nullptr, n, &n, &used, &consumed, final_range);
+        if (rc) break;
+        if (lengths_out) memcpy(lengths_out + n_done, b.lengths, n * sizeof(uint32_t));
+        rc = moira_submit(c, b.slab, used ? used : 16, b.offsets, b.lengths, n, params, ee_out + n_done,
+                          ns_out ? ns_out + n_done : nullptr, flags_out ? flags_out + n_done : nullptr, s.counters, &s.ticket);
+        if (rc) break;
+        n_done += n;
+        pos += consumed ? consumed : len;
+        k++;
+    }
+    for (auto &s : slots) { int r = retire(s); if (!rc) rc = r; }
+    if (rc) { cudaDeviceSynchronize(); return rc; }
+    if (counters_out) memcpy(counters_out, total, sizeof(total));
+    *n_reads_out = n_done;
+    return MOIRA_OK;
 }
 
 int moira_calculate_errors_PB(moira_ctx *c, const char *contig, const int32_t *quals, uint64_t length, double alpha,

@@ -64,7 +64,9 @@ struct FqSeg {
     uint64_t newlines = 0;              // in [begin, end)
     uint64_t first_line = 0;            // index of the first line that STARTS in the range
     uint64_t first_line_pos = 0;        // its byte position (== end if none)
+    uint64_t rec_start = 0;             // byte position of the first record ('@' line, line index % 4 == 0) at or after it
     uint64_t n_reads = 0, slab_bytes = 0;
+    uint64_t consumed = 0;              // text position after the last record parsed
     uint64_t read_base = 0, slab_base = 0;
     int err = 0;
     uint64_t err_local = 0;
@@ -80,21 +82,14 @@ struct FqJob {
     uint32_t *lengths, *hdr_len;
 };
 
-// Parse the records owned by one segment.  fill == false: count reads / slab bytes and validate.
-void fq_parse_segment(const FqJob &j, FqSeg &g, bool fill, uint64_t next_begin)
+// Parse the records owned by one range and write their rows into the range's slice of the slab.
+void fq_parse_segment(const FqJob &j, FqSeg &g, uint64_t next_begin)
 {
     const char *text = j.text;
-    uint64_t cur = g.first_line_pos;
-    uint64_t line = g.first_line;
-    // advance to the first record start (line index multiple of 4) inside the segment
-    while (cur < j.text_bytes && (line & 3u) != 0) {
-        const char *nl = (const char *)memchr(text + cur, '\n', j.text_bytes - cur);
-        if (!nl) { cur = j.text_bytes; break; }
-        cur = (uint64_t)(nl - text) + 1;
-        line++;
-    }
+    uint64_t cur = g.rec_start;
     uint64_t n = 0, pos = 0;
-    while (cur < j.text_bytes && cur < next_begin) {
+    g.consumed = cur;
+    while (cur < j.text_bytes && cur < next_begin && n < g.n_reads) {
         uint64_t lb[4], le[4];
         int have = 0;
         uint64_t c = cur;
@@ -127,7 +122,7 @@ void fq_parse_segment(const FqJob &j, FqSeg &g, bool fill, uint64_t next_begin)
             break;
         }
         const uint64_t padded = (slen + 15u) & ~15ull;
-        if (fill) {
+        {
             const uint64_t r = g.read_base + n;
             uint8_t *row = j.slab + g.slab_base + pos;
             const char *s = text + lb[1];
@@ -157,8 +152,9 @@ void fq_parse_segment(const FqJob &j, FqSeg &g, bool fill, uint64_t next_begin)
         }
         pos += padded;
         n++;
+        g.consumed = cur;
     }
-    if (!fill) { g.n_reads = n; g.slab_bytes = pos; }
+    g.slab_bytes = pos;
 }
 
 int g_host_threads = 0;
@@ -176,11 +172,35 @@ extern "C" int moira_parse_fastq(const char *text, uint64_t text_bytes, int fast
                                  uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off, uint64_t *qual_off,
                                  uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out)
 {
+    return moira::parse_fastq_range(text, text_bytes, fastq_offset, lower_n_ambiguous, slab, slab_capacity, out_offsets,
+                                    lengths, hdr_off, hdr_len, seq_off, qual_off, max_reads, n_reads_out, slab_bytes_out,
+                                    nullptr, 1);
+}
+
+extern "C" int moira_fastq_count_reads(const char *text, uint64_t text_bytes, uint64_t *n_reads_out)
+{
+    uint64_t n = 0, cap = 0;
+    int rc = moira::parse_fastq_range(text, text_bytes, 33, 1, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                      nullptr, 0, &n, &cap, nullptr, 1);
+    if (n_reads_out) *n_reads_out = n;
+    return rc;
+}
+
+// consumed_out: bytes of `text` up to the end of the last complete record (what a streaming caller
+// advances by; a trailing partial record is left for the next range).  final_range = 0: the range
+// may end in the middle of a line, which then does not count.
+int moira::parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous,
+                             uint8_t *slab, uint64_t slab_capacity, uint64_t *out_offsets, uint32_t *lengths,
+                             uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off, uint64_t *qual_off,
+                             uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out, uint64_t *consumed_out,
+                             int final_range)
+{
     if (!text || !n_reads_out || !slab_bytes_out) return hfail(MOIRA_ERR_BAD_ARG, "NULL argument");
     int T = g_host_threads > 0 ? g_host_threads : (int)std::thread::hardware_concurrency();
     if (T < 1) T = 1;
     if (T > 64) T = 64;
     if (text_bytes < (1u << 20)) T = 1;
+    if (consumed_out) *consumed_out = 0;
     std::vector<FqSeg> segs(T);
     for (int t = 0; t < T; t++) {
         segs[t].begin = text_bytes * (uint64_t)t / T;
@@ -217,23 +237,55 @@ extern "C" int moira_parse_fastq(const char *text, uint64_t text_bytes, int fast
         g.first_line = before + ((g.begin == 0 || text[g.begin - 1] == '\n') ? 0 : 1);
         before += g.newlines;
     }
-    FqJob job{text, text_bytes, fastq_offset, lower_n_ambiguous, slab, out_offsets, hdr_off, seq_off, qual_off, lengths, hdr_len};
-    auto next_begin = [&](int t) { return t + 1 < T ? segs[t + 1].first_line_pos : text_bytes; };
-    // a thread owns records whose first line starts in [first_line_pos(t), first_line_pos(t+1))
-    run([&](int t) { if (segs[t].first_line_pos < next_begin(t) || t == T - 1) fq_parse_segment(job, segs[t], false, next_begin(t)); });
-    uint64_t n = 0, bytes = 0;
+    // Reads per range follow from the line numbers alone (records start at lines 0, 4, 8, ...; a record
+    // counts if all 4 of its lines exist), and so does an upper bound of the slab bytes a range produces
+    // (each row <= half of its record's text + 15 bytes of padding).  So the ranges can be parsed in ONE
+    // pass, each thread writing its rows into its own slice of the slab; offsets[] skips the slack.
+    run([&](int t) {
+        FqSeg &g = segs[t];
+        uint64_t cur = g.first_line_pos, line = g.first_line;
+        while (cur < text_bytes && (line & 3u) != 0) {
+            const char *nl = (const char *)memchr(text + cur, '\n', text_bytes - cur);
+            if (!nl) { cur = text_bytes; break; }
+            cur = (uint64_t)(nl - text) + 1;
+            line++;
+        }
+        g.rec_start = cur < text_bytes ? cur : text_bytes;
+    });
+    // an unterminated last line is a line only at the true end of the input (a streaming range may end mid-line)
+    const uint64_t total_lines = before + ((final_range && text_bytes && text[text_bytes - 1] != '\n') ? 1 : 0);
+    const uint64_t n_complete = total_lines / 4;
+    auto records_before_line = [&](uint64_t line) { return std::min<uint64_t>((line + 3) / 4, n_complete); };
+    uint64_t n = 0, cap = 0;
     for (int t = 0; t < T; t++) {
-        if (segs[t].err) return hfail(segs[t].err, "%s (record %llu)", segs[t].msg, (unsigned long long)(n + segs[t].err_local));
-        segs[t].read_base = n; segs[t].slab_base = bytes;
-        n += segs[t].n_reads; bytes += segs[t].slab_bytes;
+        FqSeg &g = segs[t];
+        const uint64_t line_end = t + 1 < T ? segs[t + 1].first_line : total_lines;
+        const uint64_t lo = records_before_line(g.first_line), hi = records_before_line(std::max(line_end, g.first_line));
+        g.n_reads = hi - lo;
+        g.read_base = lo;
+        g.slab_base = cap;
+        // the range's records are exactly the text [rec_start(t), rec_start(t+1)): each row <= half of its
+        // record's bytes, plus at most 15 bytes of padding
+        const uint64_t rec_end = t + 1 < T ? std::max(segs[t + 1].rec_start, g.rec_start) : text_bytes;
+        cap += (((rec_end - g.rec_start) / 2 + 16 * (g.n_reads + 1)) + 15u) & ~15ull;
+        n += g.n_reads;
     }
     *n_reads_out = n;
-    *slab_bytes_out = bytes;
+    *slab_bytes_out = cap;
     if (!slab) return MOIRA_OK;
     if (n > max_reads) return hfail(MOIRA_ERR_BAD_ARG, "more than max_reads = %llu records", (unsigned long long)max_reads);
-    if (bytes > slab_capacity) return hfail(MOIRA_ERR_BAD_ARG, "slab capacity too small");
-    run([&](int t) { if (segs[t].n_reads) fq_parse_segment(job, segs[t], true, next_begin(t)); });
-    for (int t = 0; t < T; t++)
+    if (cap > slab_capacity) return hfail(MOIRA_ERR_BAD_ARG, "slab capacity too small (need %llu)", (unsigned long long)cap);
+    FqJob job{text, text_bytes, fastq_offset, lower_n_ambiguous, slab, out_offsets, hdr_off, seq_off, qual_off, lengths, hdr_len};
+    auto next_begin = [&](int t) { return t + 1 < T ? segs[t + 1].rec_start : text_bytes; };
+    run([&](int t) { if (segs[t].n_reads) fq_parse_segment(job, segs[t], next_begin(t)); });
+    uint64_t used = 0;
+    for (int t = 0; t < T; t++) {
         if (segs[t].err) return hfail(segs[t].err, "%s (record %llu)", segs[t].msg, (unsigned long long)(segs[t].read_base + segs[t].err_local));
+        if (segs[t].n_reads) {
+            used = segs[t].slab_base + segs[t].slab_bytes;
+            if (consumed_out) *consumed_out = segs[t].consumed;
+        }
+    }
+    *slab_bytes_out = used;   // end of the last row: what has to travel to the GPU
     return MOIRA_OK;
 }

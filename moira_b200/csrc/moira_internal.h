@@ -78,6 +78,12 @@ int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, do
 int kernels_init(int sm_count);  // sets function attributes (dynamic smem opt-in)
 int max_first_pass_k();
 
+// moira_parse_fastq with the number of text bytes consumed (moira_host.cpp)
+int parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous, uint8_t *slab,
+                      uint64_t slab_capacity, uint64_t *out_offsets, uint32_t *lengths, uint64_t *hdr_off,
+                      uint32_t *hdr_len, uint64_t *seq_off, uint64_t *qual_off, uint64_t max_reads,
+                      uint64_t *n_reads_out, uint64_t *slab_bytes_out, uint64_t *consumed_out, int final_range);
+
 // sets the thread-local message returned by moira_last_error() and returns `code`
 int fail(int code, const char *fmt, ...);
 

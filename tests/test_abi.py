@@ -147,9 +147,13 @@ def test_parse_fastq_multithreaded_equals_single_thread():
         outs.append(moira_b200.parse_fastq(text, 33, True))
     L.lib.moira_set_host_threads(0)
     assert len(outs[0][2]) == 6000
+    rows0 = [outs[0][0][int(o):int(o) + int(l)] for o, l in zip(outs[0][1], outs[0][2])]
     for other in outs[1:]:
-        for a, b in zip(outs[0], other):
+        for a, b in zip(outs[0][2:], other[2:]):            # lengths and the byte ranges inside the text
             assert np.array_equal(a, b)
+        assert np.all(other[1] % 16 == 0) and np.all(np.diff(other[1].astype(np.int64)) > 0)
+        for r0, o, l in zip(rows0, other[1], other[2]):     # same rows, possibly with slack between threads' slices
+            assert np.array_equal(r0, other[0][int(o):int(o) + int(l)])
     # errors are reported for the first bad record, whatever the thread count
     bad = "".join(recs[:3000]).encode() + b"@bad\nACGT\n+\nIII\n" + "".join(recs[3000:]).encode()
     for threads in (1, 9):

@@ -287,3 +287,25 @@ def test_async_submit_wait_pinned(ctx):
         assert np.array_equal(out.counters, ref.counters)
     for pb in bufs:
         pb.free()
+
+
+def test_streaming_fastq_entry_point(ctx):
+    """moira_filter_fastq (parse ranges -> pinned slabs -> async submits) == parse_fastq + filter_batch,
+    across a range boundary (> 64 MB of text) and with a trailing partial record."""
+    text = gzip.open(os.path.join(ROOT, "tests", "golden", "test1.fastq.gz"), "rb").read()
+    p = FilterParams(exact_ee=True, ee_output="final")
+    slab, off, ln, *_ = moira_b200.parse_fastq(text, 33, True)
+    ref = ctx.filter_batch(slab, off, ln, p)
+    res, lengths = ctx.filter_fastq(text, p)
+    assert np.array_equal(lengths, ln) and np.array_equal(res.ee, ref.ee) and np.array_equal(res.flags, ref.flags)
+    assert np.array_equal(res.counters, ref.counters)
+    big = text * 130 + b"@partial\nACGT\n"                      # ~74 MB: two streaming ranges
+    assert len(big) > (64 << 20)
+    res2, lengths2 = ctx.filter_fastq(big, p)
+    assert len(lengths2) == 130 * len(ln)
+    assert np.array_equal(lengths2, np.tile(ln, 130)) and np.array_equal(res2.ee, np.tile(ref.ee, 130))
+    assert np.array_equal(res2.flags, np.tile(ref.flags, 130))
+    assert np.array_equal(res2.counters, ref.counters * np.uint64(130))
+    with pytest.raises(moira_b200.MoiraError) as ei:
+        ctx.filter_fastq(text[:5000] + b"@bad\nACGT\n+\nIII\n" + text[5000:], p)
+    assert ei.value.code == L.ERR_PARSE
