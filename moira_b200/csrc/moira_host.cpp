@@ -82,6 +82,27 @@ struct FqJob {
     uint32_t *lengths, *hdr_len;
 };
 
+// One row: quality = max(q - offset, 0) (moira.py:1177, :814), overridden by the in-band markers for
+// N / n.  Branch-free so the compiler vectorises it (AVX2 clone picked at load time when available).
+// Returns the largest q - offset seen.
+__attribute__((target_clones("avx2", "default")))
+int fq_convert_row(uint8_t *__restrict__ row, const char *__restrict__ s, const unsigned char *__restrict__ q,
+                   uint64_t slen, int off, uint8_t low_n)
+{
+    int worst = 0;
+    for (uint64_t i = 0; i < slen; i++) {
+        int v = (int)q[i] - off;
+        worst = v > worst ? v : worst;
+        v = v < 0 ? 0 : v;
+        uint8_t out = (uint8_t)v;
+        const uint8_t b = (uint8_t)s[i];
+        out = b == low_n ? (uint8_t)0xFE : out;       // low_n == 0 never matches a sequence byte
+        out = b == (uint8_t)'N' ? (uint8_t)0xFF : out;
+        row[i] = out;
+    }
+    return worst;
+}
+
 // Parse the records owned by one range and write their rows into the range's slice of the slab.
 void fq_parse_segment(const FqJob &j, FqSeg &g, uint64_t next_begin)
 {
@@ -127,16 +148,13 @@ void fq_parse_segment(const FqJob &j, FqSeg &g, uint64_t next_begin)
             uint8_t *row = j.slab + g.slab_base + pos;
             const char *s = text + lb[1];
             const unsigned char *q = (const unsigned char *)text + lb[3];
+            const int off = j.fastq_offset;
+            const int worst = fq_convert_row(row, s, q, slen, off, j.lower_n ? (uint8_t)'n' : (uint8_t)0);
+            // a quality above 252 only matters where the base is not N/n; rare, so re-check exactly
             bool bad_q = false;
-            for (uint64_t i = 0; i < slen; i++) {
-                if (s[i] == 'N') row[i] = 0xFF;
-                else if (s[i] == 'n' && j.lower_n) row[i] = 0xFE;
-                else {
-                    const int v = (int)q[i] - j.fastq_offset;                 // moira.py:1177
-                    if (v > 0xFC) bad_q = true;
-                    row[i] = v <= 0 ? 0 : (uint8_t)v;                        // moira.py:814
-                }
-            }
+            if (worst > 0xFC)
+                for (uint64_t i = 0; i < slen; i++)
+                    if (s[i] != 'N' && !(s[i] == 'n' && j.lower_n) && (int)q[i] - off > 0xFC) bad_q = true;
             if (bad_q) {
                 g.err = MOIRA_ERR_BAD_QUALITY; g.err_local = n;
                 snprintf(g.msg, sizeof(g.msg), "a quality of record (%.*s) is outside 0..252", (int)(he - hb < 100 ? he - hb : 100), text + hb);
