@@ -228,6 +228,20 @@ def run_ours(args):
     ms_x, _, _, _ = timed(p_exact, max(3, args.steps // 4))
     value_exact = world * n * max(3, args.steps // 4) / (ms_x * 1e-3)
 
+    # ---- parity on a bounded sample of THIS run's reads: GPU (exact mode, last step) vs the oracle ----
+    parity = None
+    if rank == 0:
+        from oracle import py_oracle as po
+        k = 20000
+        rows_s = slab[:k].cpu().numpy().reshape(-1)
+        ee_o, ns_o = po.pb_batch(rows_s, np.arange(k, dtype=np.uint64) * STRIDE, np.full(k, READ_LEN, np.uint32), ALPHA)
+        ee_g, ns_g, fl_g = ee[:k].cpu().numpy(), ns[:k].cpu().numpy(), fl[:k].cpu().numpy()
+        ok_o = (ee_o + ns_o) <= READ_LEN * UNCERT
+        near = (fl_g & L.FLAG_NEAR_CUTOFF) != 0
+        parity = {"sample_reads": k, "ee_bit_mismatches": int((ee_g != ee_o).sum()), "ns_mismatches": int((ns_g != ns_o).sum()),
+                  "decision_mismatches_outside_band": int((((fl_g & 1) != 0) != ok_o)[~near].sum()),
+                  "near_cutoff_reads_whole_run": int(counters[L.CNT_NEAR_CUTOFF]), "checker": "oracle/pb_oracle.c"}
+
     # ---- roofline of the dominant kernel --------------------------------------------------------
     k_dec = synth.decision_k(READ_LEN, UNCERT)
     kernel_ms = kms / max(1, min(args.steps, 64))
@@ -350,6 +364,21 @@ def run_ours(args):
         rate, dt, kind, threads = _time_reference(rows, offs[:s_n], lns[:s_n], cores)
         cpu = {"value": rate, "unit": "reads/s", "cores": threads, "kind": kind,
                "sample": "first %d reads of this run's GPU workload, %.1f s, all host threads, C loop over the reference test()" % (s_n, dt)}
+        # the same core as moira itself calls it (moira.py:817): one Python call per read, list of ints, 1 core
+        try:
+            from oracle import py_oracle as po
+            if po.have_ref():
+                ref = po.ref_module()
+                k = 20000
+                seqs = ["".join("N" if v == 0xFF else "A" for v in r[:READ_LEN]) for r in rows.reshape(-1, STRIDE)[:k].tolist()]
+                quals = [[2 if v >= 0xFE else (1 if v == 0 else v) for v in r[:READ_LEN]] for r in rows.reshape(-1, STRIDE)[:k].tolist()]
+                t0 = time.perf_counter()
+                for s_, q_ in zip(seqs, quals):
+                    ref.calculate_errors_PB(s_, q_, ALPHA)
+                cpu["python_api_1core"] = {"value": k / (time.perf_counter() - t0), "unit": "reads/s",
+                                           "sample": "%d reads through bernoulli.calculate_errors_PB(str, list, float), 1 core" % k}
+        except Exception as exc:  # pragma: no cover
+            cpu["python_api_1core"] = {"error": repr(exc)}
 
     if rank == 0:
         line = {
@@ -362,7 +391,7 @@ def run_ours(args):
                        "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU, NCCL all-reduce of 80 counters per step",
                        "rank_cpu_affinity": numa_cpus},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "modes": modes, "e2e_parse": e2e_parse,
+            "clocks": sampler.summary(), "parity": parity, "modes": modes, "e2e_parse": e2e_parse,
             "exact_ee": {"value": value_exact, "unit": "reads/s", "note": "exact statistic for every read (escalation ladder), device-resident"},
         }
         print(json.dumps(line))

@@ -39,6 +39,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef MOIRA_WARPS_SMALLK
 #define MOIRA_WARPS_SMALLK 16
 #endif
+#ifndef MOIRA_WARPS16_MAXK
+#define MOIRA_WARPS16_MAXK 12   // largest K that still runs 16 warps per CTA (<= 128 registers per thread)
+#endif
 #ifndef MOIRA_PAIR_LUT
 #define MOIRA_PAIR_LUT 1   // 1: first-pass kernels look up (q, e) pairs (no DSUB, LDS.128); 0: p only (LDS.64 + DSUB)
 #endif
@@ -52,8 +55,8 @@ constexpr int STAGE_BYTES = 32 * ROW_STRIDE;     // one warp, one stage
 // replicas make a warp's 32 random lookups conflict-free: 32 x double (p) or 16 x double2 (q, e).
 constexpr int LUT_BYTES = 256 * 256;
 constexpr int TPR_SMEM = 227 * 1024;             // whole opt-in shared memory; laid out at run time
-// P[0..K-1] lives in registers: 16 warps per CTA up to K = 16 (<= 128 registers), 8 above (<= 255).
-__host__ __device__ constexpr int tpr_warps(int k) { return k <= 4 ? MOIRA_WARPS_SMALLK : k <= 16 ? 16 : 8; }
+// P[0..K-1] lives in registers: 16 warps per CTA up to K = 12, 8 above (<= 255 registers; measured best for the ladder).
+__host__ __device__ constexpr int tpr_warps(int k) { return k <= 4 ? MOIRA_WARPS_SMALLK : k <= MOIRA_WARPS16_MAXK ? 16 : 8; }
 
 constexpr int WPR_THREADS = 256;
 constexpr int BLK_THREADS = 256;
