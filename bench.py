@@ -232,10 +232,11 @@ def run_ours(args):
     parity = None
     if rank == 0:
         from oracle import py_oracle as po
-        k = 20000
-        rows_s = slab[:k].cpu().numpy().reshape(-1)
+        k = 20000   # the first and the last 10 000 reads (the last ones sit in the second ladder sub-batch)
+        sel = torch.cat([torch.arange(0, k // 2, device=dev), torch.arange(n - k // 2, n, device=dev)])
+        rows_s = slab[sel].cpu().numpy().reshape(-1)
         ee_o, ns_o = po.pb_batch(rows_s, np.arange(k, dtype=np.uint64) * STRIDE, np.full(k, READ_LEN, np.uint32), ALPHA)
-        ee_g, ns_g, fl_g = ee[:k].cpu().numpy(), ns[:k].cpu().numpy(), fl[:k].cpu().numpy()
+        ee_g, ns_g, fl_g = ee[sel].cpu().numpy(), ns[sel].cpu().numpy(), fl[sel].cpu().numpy()
         ok_o = (ee_o + ns_o) <= READ_LEN * UNCERT
         near = (fl_g & L.FLAG_NEAR_CUTOFF) != 0
         parity = {"sample_reads": k, "ee_bit_mismatches": int((ee_g != ee_o).sum()), "ns_mismatches": int((ns_g != ns_o).sum()),

@@ -108,7 +108,7 @@ typedef struct moira_params {
     int32_t  exact_ee;    /* 1: exact statistic for every read (what collapse needs, moira.py:466);
                              0: decision mode, certain rejects may carry a lower bound (MOIRA_FLAG_LOWER_BOUND) */
     int32_t  ee_output;   /* MOIRA_EE_* */
-    int32_t  reserved;
+    int32_t  length_sort; /* ragged batches: 0 = bucket reads by length on the device when it pays (default), 2 = never */
     double   alpha;       /* --alpha */
     double   thr;         /* --uncert or --maxerrors value */
 } moira_params;

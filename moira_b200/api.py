@@ -28,6 +28,7 @@ class FilterParams:
     truncate: int | None = None            # --truncate
     exact_ee: bool = True                  # exact statistic for every read (needed by --collapse, moira.py:466)
     ee_output: str = "raw"                 # 'raw' = calculate_errors_* value, 'final' = process_data value
+    length_sort: int = 0                   # ragged batches: 0 = bucket by length on the device when it pays, 2 = never
 
     def to_c(self) -> L.Params:
         if self.error_calc not in _MODES:
@@ -45,6 +46,7 @@ class FilterParams:
         p.truncate = int(self.truncate) if self.truncate else 0
         p.exact_ee = 1 if self.exact_ee else 0
         p.ee_output = L.EE_FINAL if self.ee_output == "final" else L.EE_RAW
+        p.length_sort = int(self.length_sort)
         p.alpha = float(self.alpha)
         return p
 

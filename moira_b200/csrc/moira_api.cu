@@ -34,6 +34,10 @@ struct Workspace {
     uint32_t *queues = nullptr;
     uint32_t *counts = nullptr;
     uint32_t cap = 0;
+    // length bucketing of ragged batches
+    uint32_t *lqueue = nullptr;
+    uint32_t *ltables = nullptr;   // hist | bucket_start | cursor | group_start | group_count
+    uint32_t lcap = 0;
 };
 
 struct DevBuf {
@@ -111,6 +115,7 @@ struct moira_ctx {
     StreamBuf fq[3];
     uint64_t launches = 0;
     int use_tma = 1;
+    int length_sort = 1;
     int timing = 0;
     int n_timed = 0;
     cudaEvent_t t0[MAX_TIMED], t1[MAX_TIMED];
@@ -174,6 +179,28 @@ int ensure_ws(Workspace &w, uint32_t cap)
         return fail(MOIRA_ERR_NOMEM, "cudaMalloc of escalation queues (%u reads) failed", cap);
     }
     w.cap = cap;
+    return MOIRA_OK;
+}
+
+int ensure_lsort(Workspace &w, uint32_t cap, LenSortBufs &b)
+{
+    constexpr size_t TABLE_WORDS = 3 * LEN_BUCKETS + 2 * 32;
+    if (!w.ltables) CU(cudaMalloc(&w.ltables, TABLE_WORDS * sizeof(uint32_t)));
+    if (cap > w.lcap || !w.lqueue) {
+        if (w.lqueue) cudaFree(w.lqueue);
+        w.lqueue = nullptr; w.lcap = 0;
+        if (cudaMalloc(&w.lqueue, (size_t)cap * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MOIRA_ERR_NOMEM, "cudaMalloc of the length-sort queue (%u reads) failed", cap);
+        }
+        w.lcap = cap;
+    }
+    b.queue = w.lqueue;
+    b.hist = w.ltables;
+    b.bucket_start = w.ltables + LEN_BUCKETS;
+    b.cursor = w.ltables + 2 * LEN_BUCKETS;
+    b.group_start = w.ltables + 3 * LEN_BUCKETS;
+    b.group_count = b.group_start + 32;
     return MOIRA_OK;
 }
 
@@ -248,7 +275,7 @@ int first_pass_k_template(int k_wanted)
 // Enqueue the whole filter for reads [0, n) on `stream`.  max_len = longest read if known, else 0.
 int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const uint64_t *d_offsets,
                     const uint32_t *d_lengths, uint64_t stride, uint32_t fixed_length, uint64_t n_reads,
-                    const moira_params *p, uint32_t max_len, double *d_ee, int32_t *d_ns, uint8_t *d_flags,
+                    const moira_params *p, uint32_t max_len, uint32_t min_len, double *d_ee, int32_t *d_ns, uint8_t *d_flags,
                     uint64_t *d_counters, cudaStream_t stream)
 {
     if (n_reads == 0) return MOIRA_OK;
@@ -311,9 +338,38 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
         const bool timed = c->timing && c->n_timed < MAX_TIMED;
         if (timed) CU(cudaEventRecord(c->t0[c->n_timed], stream));
         const char *name = "";
-        int rc = p->mode == MOIRA_MODE_PB ? launch_pb_first(a, k_first, cfg, &name) : launch_lambda(a, cfg, &name);
-        if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        c->launches++;
+        int rc = 0;
+        // Ragged batch: bucket the reads by length on the device first, so that a warp tile holds reads of
+        // (almost) one length and every tile runs with the K its own cutoff needs.
+        // auto: only when the caller's lengths are known to spread by more than a quarter (host path); the
+        // device-pointer API sorts only on request (length_sort = 1)
+        const bool lsort = d_lengths && c->length_sort && n >= 32768 && p->length_sort != 2 &&
+                           (p->length_sort == 1 || (max_len && min_len * 4 < max_len * 3));
+        if (lsort) {
+            cfg.tmap = nullptr;   // tiles follow the sorted permutation, not the slab order
+            LenSortBufs lb;
+            if ((rc = ensure_lsort(ws, (uint32_t)std::min<uint64_t>(n_reads, sub), lb))) return rc;
+            CU(cudaMemsetAsync(lb.hist, 0, LEN_BUCKETS * sizeof(uint32_t), stream));
+            const int single = p->mode != MOIRA_MODE_PB;
+            if (launch_length_sort(a, lb, single, cfg)) return fail(MOIRA_ERR_CUDA, "length-sort launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            c->launches += 3;
+            a.queue = lb.queue;
+            a.min_rung = 1;
+            for (int g = 0; g < (single ? 1 : N_FIRST_K); g++) {
+                a.seg_start = lb.group_start + g;
+                a.seg_count = lb.group_count + g;
+                a.queue_count = lb.group_count + g;
+                rc = single ? launch_lambda(a, cfg, &name) : launch_pb_first_k(a, g, cfg, &name);
+                if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                c->launches++;
+            }
+            if (!single) name = "pb_tpr<K per length bucket>";
+            a.queue = nullptr; a.queue_count = nullptr; a.seg_start = nullptr; a.seg_count = nullptr;
+        } else {
+            rc = p->mode == MOIRA_MODE_PB ? launch_pb_first(a, k_first, cfg, &name) : launch_lambda(a, cfg, &name);
+            if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            c->launches++;
+        }
         if (timed) { CU(cudaEventRecord(c->t1[c->n_timed], stream)); c->n_timed++; c->timed_name = name; }
         if (ladder) {
             for (int b = 0; b < NB; b++) {
@@ -368,6 +424,7 @@ int moira_ctx_create(int device, moira_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     build_tables(c->h_p, c->h_q, c->h_e, &c->e_equals_p);
+    if (const char *e = getenv("MOIRA_B200_NO_LENSORT")) c->length_sort = (e[0] == '1') ? 0 : 1;   // diagnostics
     if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
     if (kernels_init(c->sm_count)) {
         int rc = fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -402,7 +459,12 @@ int moira_ctx_destroy(moira_ctx *c)
         if (t.counters_pinned) cudaFreeHost(t.counters_pinned);
     }
     for (auto &b : c->fq) b.release();
-    for (auto &w : c->ws) { if (w.queues) cudaFree(w.queues); if (w.counts) cudaFree(w.counts); }
+    for (auto &w : c->ws) {
+        if (w.queues) cudaFree(w.queues);
+        if (w.counts) cudaFree(w.counts);
+        if (w.lqueue) cudaFree(w.lqueue);
+        if (w.ltables) cudaFree(w.ltables);
+    }
     for (int i = 0; i < MAX_TIMED; i++) { cudaEventDestroy(c->t0[i]); cudaEventDestroy(c->t1[i]); }
     if (c->meta_ready) cudaEventDestroy(c->meta_ready);
     for (int i = 0; i < 2; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -466,7 +528,7 @@ int moira_filter_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_o
     int rc = check_params(params);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    return run_filter_full(c, c->ws[2], d_slab, d_offsets, d_lengths, stride, fixed_length, n_reads, params, 0, d_ee,
+    return run_filter_full(c, c->ws[2], d_slab, d_offsets, d_lengths, stride, fixed_length, n_reads, params, 0, 0, d_ee,
                            d_ns, d_flags, d_counters, (cudaStream_t)stream);
 }
 
@@ -518,7 +580,7 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
     while (start < n) {
         uint64_t end = start;
         const uint64_t b0 = offsets[start];
-        uint32_t max_len = 0;
+        uint32_t max_len = 0, min_len = 0xFFFFFFFFu;
         uint64_t b1 = b0;
         // uniform chunk (every row `stride0` bytes after the previous one, all of one length): offsets and
         // lengths need not travel, and the first pass can be fed by TMA tensor tiles
@@ -532,6 +594,7 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
             if (end > start && row_end - b0 > CHUNK_BYTES) break;
             b1 = std::max(b1, row_end);
             max_len = std::max(max_len, lengths[end]);
+            min_len = std::min(min_len, lengths[end]);
             uniform = uniform && lengths[end] == lengths[start] && offsets[end] == b0 + (end - start) * stride0;
             end++;
         }
@@ -541,12 +604,12 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
         const uint64_t cn = end - start;
         uniform = uniform && stride0 >= 16 && (stride0 & 15u) == 0 && stride0 >= lengths[start];
         if (uniform) {
-            rc = run_filter_full(c, c->ws[ci & 1], d_slab + b0, nullptr, nullptr, stride0, lengths[start], cn, params, max_len,
+            rc = run_filter_full(c, c->ws[ci & 1], d_slab + b0, nullptr, nullptr, stride0, lengths[start], cn, params, max_len, max_len,
                                  d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
         } else {
             CU(cudaMemcpyAsync(d_off + start, offsets + start, cn * 8, cudaMemcpyHostToDevice, s));
             CU(cudaMemcpyAsync(d_len + start, lengths + start, cn * 4, cudaMemcpyHostToDevice, s));
-            rc = run_filter_full(c, c->ws[ci & 1], d_slab, d_off + start, d_len + start, 0, 0, cn, params, max_len,
+            rc = run_filter_full(c, c->ws[ci & 1], d_slab, d_off + start, d_len + start, 0, 0, cn, params, max_len, min_len,
                                  d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
         }
         if (rc) return rc;

@@ -52,6 +52,9 @@ struct FilterArgs {
     uint32_t *queues;            // [NB][queue_cap]
     uint32_t *queue_counts;      // [NB]
     uint32_t queue_cap;
+    // first pass over a length-sorted permutation: this launch covers queue[*seg_start .. +*seg_count)
+    const uint32_t *seg_start;
+    const uint32_t *seg_count;
     int32_t rung;                // -1 on the first pass, else this kernel's rung
     int32_t min_rung;            // lowest rung the classifier may forward to (its cap exceeds the first-pass K)
     int32_t allow_push;          // 0: no ladder follows (first-pass K provably decides everything)
@@ -74,6 +77,25 @@ int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, con
 int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name);
 // ladder rung b over queue b
 int launch_rung(const FilterArgs &a, int b, const LaunchCfg &cfg);
+// ---- on-device length bucketing of ragged batches (counting sort by padded length) ----------------
+constexpr int LEN_BUCKETS = 4096;        // bucket b holds reads with ceil16(eff)/16 == b (last bucket: anything longer)
+constexpr int N_FIRST_K = 17;            // first-pass K templates, see first_pass_ks()
+__host__ __device__ constexpr int first_pass_k(int i)
+{
+    constexpr int ks[N_FIRST_K] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 20, 22, 24, 28, 32};
+    return ks[i];
+}
+struct LenSortBufs {
+    uint32_t *queue;         // [n] read indices sorted by bucket
+    uint32_t *hist;          // [LEN_BUCKETS]
+    uint32_t *bucket_start;  // [LEN_BUCKETS]
+    uint32_t *cursor;        // [LEN_BUCKETS]
+    uint32_t *group_start;   // [N_FIRST_K] segment of the queue handled with first_pass_k(g)
+    uint32_t *group_count;   // [N_FIRST_K]
+};
+// enqueue histogram + scan + scatter; single_group: every read goes to group 0 (modes without a per-length K)
+int launch_length_sort(const FilterArgs &a, const LenSortBufs &b, int single_group, const LaunchCfg &cfg);
+int launch_pb_first_k(const FilterArgs &a, int k_index, const LaunchCfg &cfg, const char **name);
 int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, double *ops_out);
 int kernels_init(int sm_count);  // sets function attributes (dynamic smem opt-in)
 int max_first_pass_k();

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
     constexpr int TPR_THREADS = TPR_WARPS * 32;
     constexpr uint32_t STG = TMA ? 32u * CHUNK : (uint32_t)STAGE_BYTES;   // bytes of one warp-stage
     extern __shared__ __align__(128) uint8_t smem[];
-    if (a.queue && *a.queue_count == 0) return;   // empty rung: nothing to set up
+    if (a.queue && (a.seg_count ? *a.seg_count : *a.queue_count) == 0) return;   // empty rung / segment: nothing to set up
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 
@@ -437,12 +437,15 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
     const uint32_t stage0 = stage_warp + lane * (TMA ? CHUNK : ROW_STRIDE);
     const uint32_t swz = TMA ? (lane & 7) << 4 : 0u;
 
-    const uint32_t count = a.queue ? *a.queue_count : a.n;
+    const uint32_t *queue = a.queue && a.seg_start ? a.queue + *a.seg_start : a.queue;
+    const uint32_t count = a.queue ? (a.seg_count ? *a.seg_count : *a.queue_count) : a.n;
     const uint32_t n_tiles = (count + 31) >> 5;
     const uint32_t total_warps = gridDim.x * TPR_WARPS;
     uint32_t tile = blockIdx.x * TPR_WARPS + warp;
     uint32_t it = 0;   // stage jobs issued == consumed so far by this warp
-    const bool coop = a.queue == nullptr;   // rows of a first-pass tile are neighbours in the slab
+    // Always copy cooperatively (8 consecutive lanes fetch one 128-byte line of one row): 4 L1 tags per
+    // LDGSTS instead of 32 when every lane fetches from its own row -- also for scattered ladder rows.
+    const bool coop = true;
 
     auto tile_read = [&](uint32_t t, bool &valid, uint32_t &r_local, ReadGeom &g) {
         uint32_t i = t * 32 + lane;
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
         r_local = 0;
         g.off = 0; g.len = 0; g.eff = 0;
         if (valid) {
-            r_local = a.queue ? a.queue[i] : i;
+            r_local = queue ? queue[i] : i;
             g = read_geom(a, r_local);
         }
     };
@@ -470,8 +473,8 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
         const uint32_t padded = (g.eff + 15u) & ~15u;
         const uint32_t begin = c * CHUNK;
         const uint32_t dst_stage = (s & 1) * STG;
-        if (coop && !a.offsets && !a.lengths) {
-            // uniform stride and length: addresses follow from the tile's first row (lane 0)
+        if (coop && !a.offsets && !a.lengths && !queue) {
+            // uniform stride and length, rows in slab order: addresses follow from the tile's first row (lane 0)
             const uint32_t col = (lane & (CHUNK / 16 - 1)) * 16;
             constexpr int ROWS_PER_INST = 32 / (CHUNK / 16);
             const uint64_t off0 = __shfl_sync(FULL, g.off, 0);
@@ -831,6 +834,130 @@ __global__ void __launch_bounds__(BLK_THREADS) blk_kernel(const FilterArgs a)
 }
 
 // ==================================================================================================
+// length bucketing of ragged batches: counting sort of the read indices by padded length, so that the
+// 32 reads of a warp tile have (almost) the same length and every tile runs with the K its own
+// cutoff needs.  Three tiny kernels, no host synchronisation.
+// ==================================================================================================
+__device__ __forceinline__ uint32_t len_bucket(uint32_t eff)
+{
+    const uint32_t b = (eff + 15u) >> 4;
+    return b < LEN_BUCKETS ? b : LEN_BUCKETS - 1;
+}
+
+// warp-aggregated increment of counter[key]: one atomic per distinct key and warp; returns the old
+// value + the lane's rank among the lanes with the same key (a unique slot).  Convergent call.
+__device__ __forceinline__ uint32_t warp_agg_inc(uint32_t *counter, uint32_t key, bool active, int lane)
+{
+    const unsigned am = __ballot_sync(FULL, active);
+    uint32_t slot = 0;
+    if (active) {
+        const unsigned peers = __match_any_sync(am, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&counter[key], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        slot = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    return slot;
+}
+
+constexpr int LS_CHUNK = 4096;   // reads per block iteration of the length-sort kernels
+
+__global__ void __launch_bounds__(256) len_hist_kernel(const FilterArgs a, uint32_t *hist)
+{
+    __shared__ uint32_t s_h[LEN_BUCKETS];
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < LEN_BUCKETS; i += 256) s_h[i] = 0;
+    __syncthreads();
+    const uint32_t n_round = (a.n + 255u) & ~255u;
+    for (uint32_t r = blockIdx.x * 256 + threadIdx.x; r < n_round; r += gridDim.x * 256) {
+        const bool ok = r < a.n;
+        warp_agg_inc(s_h, ok ? len_bucket(read_geom(a, r).eff) : 0u, ok, lane);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < LEN_BUCKETS; i += 256)
+        if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
+}
+
+// one block: exclusive scan of the histogram, and the queue segment of every first-pass K template
+__global__ void __launch_bounds__(1024) len_scan_kernel(const FilterArgs a, const uint32_t *hist, uint32_t *bucket_start,
+                                                        uint32_t *cursor, uint32_t *group_start, uint32_t *group_count,
+                                                        int single_group)
+{
+    __shared__ uint32_t s_part[1024];
+    __shared__ uint32_t s_gs[N_FIRST_K], s_gc[N_FIRST_K];
+    constexpr int PER = LEN_BUCKETS / 1024;
+    const int t = threadIdx.x;
+    if (t < N_FIRST_K) { s_gs[t] = 0xFFFFFFFFu; s_gc[t] = 0; }
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] = hist[t * PER + i]; sum += v[i]; }
+    s_part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {       // Hillis-Steele inclusive scan of the per-thread sums
+        uint32_t x = t >= o ? s_part[t - o] : 0u;
+        __syncthreads();
+        s_part[t] += x;
+        __syncthreads();
+    }
+    uint32_t run = s_part[t] - sum;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int b = t * PER + i;
+        bucket_start[b] = run;
+        cursor[b] = 0;
+        if (v[i]) {
+            int g = 0;
+            if (!single_group) {
+                // K a decision needs for the longest read of the bucket: floor(cutoff) + 2
+                const double cutoff = a.thr_kind == MOIRA_THR_MAXERRORS ? a.thr : __dmul_rn((double)(b * 16), a.thr);
+                const double kd = cutoff < 0.0 ? 2.0 : floor(cutoff) + 2.0;
+                while (g < N_FIRST_K - 1 && (double)first_pass_k(g) < kd) g++;
+            }
+            atomicMin(&s_gs[g], run);
+            atomicAdd(&s_gc[g], v[i]);
+        }
+        run += v[i];
+    }
+    __syncthreads();
+    if (t < N_FIRST_K) { group_start[t] = s_gc[t] ? s_gs[t] : 0u; group_count[t] = s_gc[t]; }
+}
+
+// Each block takes contiguous chunks of LS_CHUNK reads, counts them per bucket in shared memory,
+// reserves one contiguous range per bucket with a single global atomic, and writes its reads there:
+// neighbours in the queue stay neighbours in the slab (DRAM locality of the gather), and the global
+// atomics are per (block-chunk, bucket) instead of per read.
+__global__ void __launch_bounds__(256) len_scatter_kernel(const FilterArgs a, const uint32_t *bucket_start, uint32_t *cursor,
+                                                          uint32_t *queue)
+{
+    __shared__ uint32_t s_cnt[LEN_BUCKETS];
+    __shared__ uint32_t s_base[LEN_BUCKETS];
+    const int lane = threadIdx.x & 31;
+    for (uint32_t c0 = blockIdx.x * LS_CHUNK; c0 < a.n; c0 += gridDim.x * LS_CHUNK) {
+        for (int i = threadIdx.x; i < LEN_BUCKETS; i += 256) s_cnt[i] = 0;
+        __syncthreads();
+        uint32_t slot[LS_CHUNK / 256], bkt[LS_CHUNK / 256];
+#pragma unroll
+        for (int k = 0; k < LS_CHUNK / 256; k++) {
+            const uint32_t r = c0 + k * 256 + threadIdx.x;
+            const bool ok = r < a.n;
+            bkt[k] = ok ? len_bucket(read_geom(a, r).eff) : 0u;
+            slot[k] = warp_agg_inc(s_cnt, bkt[k], ok, lane);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < LEN_BUCKETS; i += 256)
+            if (s_cnt[i]) s_base[i] = bucket_start[i] + atomicAdd(&cursor[i], s_cnt[i]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LS_CHUNK / 256; k++) {
+            const uint32_t r = c0 + k * 256 + threadIdx.x;
+            if (r < a.n) queue[s_base[bkt[k]] + slot[k]] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// ==================================================================================================
 // FP64 issue-rate probe: per thread 4 independent copies of the K=4 update (7 DMUL + 4 DADD).
 // ==================================================================================================
 __global__ void __launch_bounds__(512) fp64_peak_kernel(int iters, double *sink, double p)
@@ -924,6 +1051,20 @@ int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, con
 #undef X
     if (name) *name = names[16];
     return (cfg.tmap ? launch_tpr_tma<32, 0>(a, cfg) : launch_tpr<32, 0>(a, cfg)) ? -1 : 32;
+}
+
+int launch_pb_first_k(const FilterArgs &a, int k_index, const LaunchCfg &cfg, const char **name)
+{
+    return launch_pb_first(a, first_pass_k(k_index), cfg, name) < 0 ? -1 : 0;
+}
+
+int launch_length_sort(const FilterArgs &a, const LenSortBufs &b, int single_group, const LaunchCfg &cfg)
+{
+    const int grid = cfg.sm_count * 4;
+    len_hist_kernel<<<grid, 256, 0, cfg.stream>>>(a, b.hist);
+    len_scan_kernel<<<1, 1024, 0, cfg.stream>>>(a, b.hist, b.bucket_start, b.cursor, b.group_start, b.group_count, single_group);
+    len_scatter_kernel<<<grid, 256, 0, cfg.stream>>>(a, b.bucket_start, b.cursor, b.queue);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name)

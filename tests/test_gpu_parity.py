@@ -309,3 +309,32 @@ def test_streaming_fastq_entry_point(ctx):
     with pytest.raises(moira_b200.MoiraError) as ei:
         ctx.filter_fastq(text[:5000] + b"@bad\nACGT\n+\nIII\n" + text[5000:], p)
     assert ei.value.code == L.ERR_PARSE
+
+
+def test_length_bucketing_of_ragged_batches(ctx):
+    """>= 32768 ragged reads take the on-device counting sort by length (per-bucket K); results must be
+    identical to the unsorted path and to the oracle, in input order."""
+    slab, off, ln = synth.generate("mixed", 40000, 31)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    has_n = _has_n(slab, off, ln)
+    for kw in (dict(), dict(maxerrors=3.0), dict(truncate=333), dict(uncert=0.08)):
+        for exact in (True, False):
+            p_on = FilterParams(exact_ee=exact, length_sort=1, **kw)
+            p_off = FilterParams(exact_ee=exact, length_sort=2, **kw)
+            r_on = ctx.filter_batch(slab, off, ln, p_on)
+            r_off = ctx.filter_batch(slab, off, ln, p_off)
+            assert np.array_equal(r_on.accept, r_off.accept) and np.array_equal(r_on.ns, r_off.ns)
+            assert np.array_equal(r_on.reason, r_off.reason)
+            both = ~r_on.lower_bound & ~r_off.lower_bound
+            assert np.array_equal(r_on.ee[both], r_off.ee[both])
+            assert int(r_on.counters[L.CNT_READS]) == 40000
+            assert np.array_equal(r_on.counters[:5], r_off.counters[:5])
+            if not kw:
+                assert np.array_equal(r_on.ns, ns_o)
+                lb = r_on.lower_bound
+                assert np.array_equal(r_on.ee[~lb], ee_o[~lb]) and (exact is False or not lb.any())
+                _check_decisions(r_on, ee_o, ns_o, ln, has_n, p_on)
+    for calc in ("poisson", "expected_error"):
+        r_on = ctx.filter_batch(slab, off, ln, FilterParams(error_calc=calc, length_sort=1))
+        r_off = ctx.filter_batch(slab, off, ln, FilterParams(error_calc=calc, length_sort=2))
+        assert np.array_equal(r_on.ee, r_off.ee) and np.array_equal(r_on.flags, r_off.flags)
