@@ -574,7 +574,8 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
 
     // Chunks of ~32 MB of slab alternate between the two streams: the H2D copy of one chunk overlaps
     // the kernels of the previous one and the D2H copy of the one before.  Rows must be in slab order.
-    const uint64_t CHUNK_BYTES = 32ull << 20;
+    uint64_t CHUNK_BYTES = 32ull << 20;
+    if (const char *e = getenv("MOIRA_B200_CHUNK_MB")) { const long v = atol(e); if (v > 0) CHUNK_BYTES = (uint64_t)v << 20; }   // tuning
     uint64_t start = 0;
     int ci = 0;
     while (start < n) {

@@ -11,16 +11,20 @@
 // of bernoullimodule.c:170-178.
 //
 // Kernels:
-//   pb_tpr<K>     thread-per-read, P[0..K-1] in registers.  Rows are staged global->shared with
-//                 per-lane cp.async.bulk (TMA bulk copy) into a double-buffered, bank-conflict-free
-//                 padded layout; the Q->p table lives in shared memory replicated 16x so that a
-//                 warp's 32 random lookups never conflict.  Persistent grid.
-//   lambda_tpr    same staging, accumulates Lambda = sum p_i sequentially (Poisson and
+//   tpr_kernel<K,0>  "pb_tpr": thread-per-read, P[0..K-1] in registers, persistent grid.  Rows are staged
+//                 global->shared in 128-byte chunks, double-buffered per warp: by TMA tensor tiles
+//                 (one UTMALDG per warp and chunk, 128-byte swizzle) for uniform-stride slabs, by
+//                 cooperative cp.async (LDGSTS) otherwise.  The Q->(q,e) table lives in shared memory at a
+//                 64 KB-aligned address, 16 replicas per row, so that one PRMT builds the lookup address
+//                 and a warp's 32 random lookups never conflict.
+//   tpr_kernel<1,1>  "lambda_tpr": same staging, accumulates Lambda = sum p_i sequentially (Poisson and
 //                 expected-error modes, moira.py:1637-1679).
-//   pb_wpr<M>     warp-per-read for reads that need many PMF entries (K = 32*M): lane l owns
+//   tpr_kernel<2,2>  ladder classifier: mean/variance of the error count -> rung.
+//   wpr_kernel<M>    warp-per-read for reads that need many PMF entries (K = 32*M): lane l owns
 //                 P[l*M .. l*M+M-1], the neighbour entry travels by warp shuffle.
-//   pb_blk        block-per-read, P in shared memory, any K up to 24576: last rung.
-//   fp64_peak     register-resident DMUL/DADD issue-rate probe (roofline denominator).
+//   blk_kernel       block-per-read, P in shared memory, any K up to 24576: last rung.
+//   len_*_kernel     counting sort of read indices by length (ragged batches).
+//   fp64_peak_kernel register-resident DMUL/DADD issue-rate probe (roofline denominator).
 #include <cuda.h>
 #include <math.h>
 
@@ -76,10 +80,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done;
@@ -92,13 +92,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
-}
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
 }
 // Ampere-style asynchronous 16-byte copy global -> shared (SASS: LDGSTS); src_size 0 zero-fills.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_size)
