@@ -585,7 +585,7 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
         uint64_t b1 = b0;
         // uniform chunk (every row `stride0` bytes after the previous one, all of one length): offsets and
         // lengths need not travel, and the first pass can be fed by TMA tensor tiles
-        bool uniform = true;
+        bool uniform = true, same_len = true;
         const uint64_t stride0 = start + 1 < n ? offsets[start + 1] - offsets[start] : (((uint64_t)lengths[start] + 15u) & ~15ull);
         while (end < n) {
             const uint64_t row_end = offsets[end] + (((uint64_t)lengths[end] + 15u) & ~15ull);
@@ -596,16 +596,21 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
             b1 = std::max(b1, row_end);
             max_len = std::max(max_len, lengths[end]);
             min_len = std::min(min_len, lengths[end]);
-            uniform = uniform && lengths[end] == lengths[start] && offsets[end] == b0 + (end - start) * stride0;
+            same_len = same_len && lengths[end] == lengths[start];
+            uniform = uniform && offsets[end] == b0 + (end - start) * stride0;
             end++;
         }
         cudaStream_t s = c->streams[ci & 1];
         const uint64_t copy_end = std::min<uint64_t>(b1, slab_bytes);
         if (copy_end > b0) CU(cudaMemcpyAsync(d_slab + b0, slab + b0, copy_end - b0, cudaMemcpyHostToDevice, s));
         const uint64_t cn = end - start;
-        uniform = uniform && stride0 >= 16 && (stride0 & 15u) == 0 && stride0 >= lengths[start];
-        if (uniform) {
+        uniform = uniform && stride0 >= 16 && (stride0 & 15u) == 0 && stride0 >= max_len;
+        if (uniform && same_len) {
             rc = run_filter_full(c, c->ws[ci & 1], d_slab + b0, nullptr, nullptr, stride0, lengths[start], cn, params, max_len, max_len,
+                                 d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
+        } else if (uniform) {   // rows at a fixed pitch, lengths vary: only the lengths travel; TMA tiles still apply
+            CU(cudaMemcpyAsync(d_len + start, lengths + start, cn * 4, cudaMemcpyHostToDevice, s));
+            rc = run_filter_full(c, c->ws[ci & 1], d_slab + b0, nullptr, d_len + start, stride0, 0, cn, params, max_len, min_len,
                                  d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
         } else {
             CU(cudaMemcpyAsync(d_off + start, offsets + start, cn * 8, cudaMemcpyHostToDevice, s));

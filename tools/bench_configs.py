@@ -18,7 +18,8 @@ def run(ctx, name, profile, n, seed, uncert=0.01, maxerrors=None, reps=5, length
     d_slab = torch.from_numpy(slab).to(dev)
     uniform = bool((ln == ln[0]).all())
     stride = int(off[1] - off[0]) if n > 1 else 0
-    d_off = None if uniform else torch.from_numpy(off.astype(np.int64)).to(dev)
+    fixed_pitch = bool((np.diff(off.astype(np.int64)) == stride).all())      # rows at a fixed pitch (lengths may vary)
+    d_off = None if fixed_pitch else torch.from_numpy(off.astype(np.int64)).to(dev)
     d_len = None if uniform else torch.from_numpy(ln.astype(np.int32)).to(dev)
     ee = torch.empty(n, dtype=torch.float64, device=dev)
     ns = torch.empty(n, dtype=torch.int32, device=dev)
@@ -33,7 +34,7 @@ def run(ctx, name, profile, n, seed, uncert=0.01, maxerrors=None, reps=5, length
         def step():
             cnt.zero_()
             ctx.filter_device(d_slab.data_ptr(), d_off.data_ptr() if d_off is not None else None,
-                              d_len.data_ptr() if d_len is not None else None, stride if uniform else 0,
+                              d_len.data_ptr() if d_len is not None else None, stride if fixed_pitch else 0,
                               int(ln[0]) if uniform else 0, n, p, ee.data_ptr(), ns.data_ptr(), fl.data_ptr(), cnt.data_ptr(), stream)
         for _ in range(3):
             step()
