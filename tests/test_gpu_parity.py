@@ -339,3 +339,17 @@ def test_length_bucketing_of_ragged_batches(ctx):
         r_on = ctx.filter_batch(slab, off, ln, FilterParams(error_calc=calc, length_sort=1))
         r_off = ctx.filter_batch(slab, off, ln, FilterParams(error_calc=calc, length_sort=2))
         assert np.array_equal(r_on.ee, r_off.ee) and np.array_equal(r_on.flags, r_off.flags)
+
+
+def test_near_cutoff_band_is_flagged_and_counted(ctx):
+    """Reads whose statistic lies within 1e-12 (relative) of the cutoff carry MOIRA_FLAG_NEAR_CUTOFF and
+    are counted (north_star's tolerance band); outside the band the flag is clear."""
+    slab, off, ln = synth.generate("v4", 64, 5)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    i = int(np.argmax((ee_o > 0.5) & (ns_o == 0)))
+    target = float(ee_o[i])
+    for thr, expect_near in ((target, True), (target * (1 - 3e-13), True), (target * (1 + 1e-9), False)):
+        r = ctx.filter_batch(slab, off, ln, FilterParams(maxerrors=thr, ambigs="ignore"))
+        assert bool(r.near_cutoff[i]) is expect_near
+        assert bool(r.accept[i]) == (target <= thr)
+        assert int(r.counters[L.CNT_NEAR_CUTOFF]) == int(r.near_cutoff.sum())
