@@ -207,6 +207,21 @@ MOIRA_API int moira_filter_fastq(moira_ctx *ctx, const char *text, uint64_t text
                                  double *ee_out, int32_t *ns_out, uint8_t *flags_out, uint32_t *lengths_out,
                                  uint64_t *counters_out, uint64_t *n_reads_out);
 
+/* Dereplication of identical sequences, the reference's --collapse (moira.py:459-475, 491-504), on
+ * all host threads.  Read r's (already truncated) sequence is text[seq_off[r] .. + seq_len[r]); ee[r]
+ * is its final expected-error value.  Outputs (all caller-allocated, capacity n, member_start n+1):
+ *   group_of_read[r]            group of read r; groups are numbered by first appearance
+ *   group_rep[g]                representative read: first read with the strictly smallest ee (moira.py:466)
+ *   group_size[g]               number of reads
+ *   members[member_start[g] .. member_start[g+1])   the group's reads in the order of the reference's
+ *                               names list (each new representative inserted at the front, moira.py:470)
+ *   abundance_order[0..G)       group ids, largest group first, ties by first appearance (moira.py:492)
+ * n_threads = 0: one per hardware thread. */
+MOIRA_API int moira_collapse(const char *text, const uint64_t *seq_off, const uint32_t *seq_len, const double *ee,
+                             uint64_t n, int n_threads, uint64_t *group_of_read, uint64_t *n_groups_out,
+                             uint64_t *group_rep, uint64_t *group_size, uint64_t *member_start, uint64_t *members,
+                             uint64_t *abundance_order);
+
 /* Host threads used by moira_parse_fastq (0 = one per hardware thread, at most 64). */
 MOIRA_API int moira_set_host_threads(int n);
 

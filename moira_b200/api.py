@@ -315,5 +315,36 @@ def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = T
     return slab, offsets, lengths, hdr_off, hdr_len, seq_off, qual_off
 
 
-__all__ = ["Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",
+@dataclass
+class CollapseResult:
+    group_of_read: np.ndarray   # uint64[n]
+    rep: np.ndarray             # uint64[G] representative read of every group
+    size: np.ndarray            # uint64[G]
+    member_start: np.ndarray    # uint64[G + 1]
+    members: np.ndarray         # uint64[n] reads of group g = members[member_start[g]:member_start[g+1]] in names order
+    order: np.ndarray           # uint64[G] groups by abundance (largest first, ties by first appearance)
+
+
+def collapse(text, seq_off, seq_len, ee, n_threads: int = 0) -> CollapseResult:
+    """moira_collapse: dereplicate identical sequences with the reference's --collapse semantics
+    (moira.py:459-475, 491-504).  `text` is a bytes-like buffer holding the sequences."""
+    buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+    seq_off = _as(seq_off, np.uint64)
+    seq_len = _as(seq_len, np.uint32)
+    ee = _as(ee, np.float64)
+    n = int(seq_len.shape[0])
+    g_of = np.empty(n, np.uint64)
+    rep = np.empty(n, np.uint64)
+    size = np.empty(n, np.uint64)
+    mstart = np.empty(n + 1, np.uint64)
+    members = np.empty(n, np.uint64)
+    order = np.empty(n, np.uint64)
+    ng = ctypes.c_uint64()
+    L.check(lib.moira_collapse(_ptr(buf), _ptr(seq_off), _ptr(seq_len), _ptr(ee), n, int(n_threads), _ptr(g_of),
+                               ctypes.byref(ng), _ptr(rep), _ptr(size), _ptr(mstart), _ptr(members), _ptr(order)))
+    G = ng.value
+    return CollapseResult(g_of, rep[:G], size[:G], mstart[:G + 1], members, order[:G])
+
+
+__all__ = ["collapse", "CollapseResult","Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",
            "pack_arrays", "parse_fastq", "build_lut"]

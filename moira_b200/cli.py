@@ -24,7 +24,7 @@ import time
 import numpy as np
 
 from . import _lib as L
-from .api import Context, FilterParams, MoiraError, pack_reads, parse_fastq
+from .api import Context, FilterParams, MoiraError, collapse, pack_reads, parse_fastq
 
 __version__ = "0.1.0 (moira 1.3.2 compatible)"
 
@@ -340,7 +340,7 @@ def main(args, out=sys.stdout) -> int:
     ctx = Context(args.device)
     processed = 0
     discarded_errors = discarded_minlength = 0
-    uniques = {}
+    all_headers, all_seqs, all_quals, all_ee, all_acc, all_rsn = [], [], [], [], [], []   # --collapse: kept for the epilogue
     t0 = time.time()
     try:
         for headers, seqs, quals, slab, offsets, lengths in batches:
@@ -350,32 +350,41 @@ def main(args, out=sys.stdout) -> int:
                 raise ReturnedNaNError("Error calculation failed for sequence %s" % headers[bad])
             accept = res.accept
             reason = res.reason
-            for i, header in enumerate(headers):
-                contig, cq = seqs[i], quals[i]
-                if args.truncate:
-                    contig, cq = contig[:args.truncate], cq[:args.truncate]        # moira.py:806-807
-                ee = float(res.ee[i])
-                if args.collapse:
-                    u = uniques.get(contig)
-                    if u is None:
-                        uniques[contig] = [header, ee, cq, [header], bool(accept[i]), int(reason[i])]
-                    elif ee < u[1]:                                                # moira.py:466
-                        u[0], u[1], u[2], u[4], u[5] = header, ee, cq, bool(accept[i]), int(reason[i])
-                        u[3].insert(0, header)
-                    else:
-                        u[3].append(header)
-                else:
-                    de, dl = write_result(processed, header, contig, cq, ee, None, bool(accept[i]), int(reason[i]), args, writers)
+            if args.truncate:                                                      # moira.py:806-807
+                seqs = [s_[:args.truncate] for s_ in seqs]
+                quals = [q_[:args.truncate] for q_ in quals]
+            if args.collapse:
+                all_headers += headers
+                all_seqs += seqs
+                all_quals += quals
+                all_ee.append(res.ee.copy())
+                all_acc.append(accept.copy())
+                all_rsn.append(reason.copy())
+                processed += len(headers)
+            else:
+                for i, header in enumerate(headers):
+                    de, dl = write_result(processed, header, seqs[i], quals[i], float(res.ee[i]), None, bool(accept[i]),
+                                          int(reason[i]), args, writers)
                     discarded_errors += de
                     discarded_minlength += dl
-                processed += 1
+                    processed += 1
             if not args.silent:
                 print("%d sequences processed in %.1f seconds.\r" % (processed, time.time() - t0), end="", file=out)
-        if args.collapse:
-            order = sorted(uniques, key=lambda s: len(uniques[s][3]), reverse=True)   # moira.py:492
-            for index, sequence in enumerate(order, start=1):
-                header, ee, cq, names, acc, rsn = uniques[sequence]
-                de, dl = write_result(index, header, sequence, cq, ee, names, acc, rsn, args, writers)
+        if args.collapse and processed:
+            # moira.py:459-475 + 491-504, natively: groups by first appearance, representative = first read
+            # with the strictly smallest ee, names in the reference's order, output by abundance
+            ee_all = np.concatenate(all_ee)
+            acc_all = np.concatenate(all_acc)
+            rsn_all = np.concatenate(all_rsn)
+            seq_len = np.fromiter((len(s_) for s_ in all_seqs), dtype=np.uint32, count=processed)
+            seq_off = np.zeros(processed, dtype=np.uint64)
+            seq_off[1:] = np.cumsum(seq_len[:-1], dtype=np.uint64)
+            col = collapse("".join(all_seqs).encode("latin-1"), seq_off, seq_len, ee_all)
+            for index, g in enumerate(col.order.tolist(), start=1):
+                rep = int(col.rep[g])
+                names = [all_headers[r] for r in col.members[int(col.member_start[g]):int(col.member_start[g + 1])].tolist()]
+                de, dl = write_result(index, all_headers[rep], all_seqs[rep], all_quals[rep], float(ee_all[rep]), names,
+                                      bool(acc_all[rep]), int(rsn_all[rep]), args, writers)
                 discarded_errors += de
                 discarded_minlength += dl
     finally:

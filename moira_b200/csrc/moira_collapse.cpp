@@ -1,0 +1,176 @@
+// moira_collapse.cpp -- host-side dereplication of identical sequences, the step that
+// sits right behind the filter kernels when --collapse is on.
+//
+// Reference semantics (moira/moira.py:459-475 and the epilogue :491-504), reproduced exactly:
+//   * reads with the same (already truncated) sequence string form one group, groups are numbered in
+//     order of first appearance (a Python-3 dict's insertion order);
+//   * walking a group's reads in input order, the representative starts as the first read and is
+//     replaced by a later read only if that read's expected errors are STRICTLY smaller (:466); every
+//     new representative is inserted at the FRONT of the names list (:470), every other read is appended;
+//   * groups are written by abundance, largest first (`sorted(..., reverse=True)`, :492 -- stable, so
+//     ties keep first-appearance order).
+//
+// Parallel plan: 64-bit hash of every sequence (all host threads) -> stable counting sort of the read
+// indices into 256 hash buckets -> each bucket grouped independently with an open-addressing table
+// (hash match + memcmp: exact strings, never hashes alone) -> groups ordered by first read.
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "moira_internal.h"
+
+namespace {
+
+inline uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 32;
+    x *= 0xd6e8feb86659fd93ull;
+    x ^= x >> 32;
+    x *= 0xd6e8feb86659fd93ull;
+    x ^= x >> 32;
+    return x;
+}
+
+uint64_t hash_bytes(const char *p, uint32_t len)
+{
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ len;
+    uint32_t i = 0;
+    for (; i + 8 <= len; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = mix64(h ^ w) + 0x9e3779b97f4a7c15ull;
+    }
+    uint64_t w = 0;
+    if (i < len) memcpy(&w, p + i, len - i);
+    return mix64(h ^ w);
+}
+
+struct LocalGroup {
+    uint64_t first;                 // first read of the group (also its hash-table identity)
+    std::vector<uint64_t> members;  // in input order
+};
+
+template <typename F>
+void parallel_for(int n_items, int threads, F &&fn)
+{
+    if (threads <= 1 || n_items <= 1) {
+        for (int i = 0; i < n_items; i++) fn(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < std::min(threads, n_items); t++)
+        th.emplace_back([&] {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n_items) break;
+                fn(i);
+            }
+        });
+    for (auto &x : th) x.join();
+}
+
+}  // namespace
+
+extern "C" int moira_collapse(const char *text, const uint64_t *seq_off, const uint32_t *seq_len, const double *ee,
+                              uint64_t n, int n_threads, uint64_t *group_of_read, uint64_t *n_groups_out,
+                              uint64_t *group_rep, uint64_t *group_size, uint64_t *member_start, uint64_t *members,
+                              uint64_t *abundance_order)
+{
+    if ((n && (!text || !seq_off || !seq_len || !ee || !group_of_read || !group_rep || !group_size || !member_start || !members ||
+               !abundance_order)) || !n_groups_out)
+        return moira::fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 64) T = 64;
+    constexpr int NBK = 256;
+    std::vector<uint64_t> hash(n);
+    {
+        const int parts = T * 4;
+        parallel_for(parts, T, [&](int p) {
+            for (uint64_t r = n * (uint64_t)p / parts, e = n * (uint64_t)(p + 1) / parts; r < e; r++)
+                hash[r] = hash_bytes(text + seq_off[r], seq_len[r]);
+        });
+    }
+    // stable counting sort of read indices by the top 8 hash bits
+    std::vector<uint64_t> bstart(NBK + 1, 0), sorted(n);
+    for (uint64_t r = 0; r < n; r++) bstart[(hash[r] >> 56) + 1]++;
+    for (int b = 0; b < NBK; b++) bstart[b + 1] += bstart[b];
+    {
+        std::vector<uint64_t> cur(bstart.begin(), bstart.end() - 1);
+        for (uint64_t r = 0; r < n; r++) sorted[cur[hash[r] >> 56]++] = r;
+    }
+    // group every bucket on its own
+    std::vector<std::vector<LocalGroup>> local(NBK);
+    parallel_for(NBK, T, [&](int b) {
+        const uint64_t lo = bstart[b], hi = bstart[b + 1], cnt = hi - lo;
+        if (!cnt) return;
+        uint64_t cap = 16;
+        while (cap < cnt * 2) cap <<= 1;
+        std::vector<uint32_t> table(cap, 0xFFFFFFFFu);     // slot -> local group index
+        std::vector<LocalGroup> &groups = local[b];
+        for (uint64_t k = lo; k < hi; k++) {
+            const uint64_t r = sorted[k];
+            const uint64_t h = hash[r];
+            uint64_t slot = (h >> 8) & (cap - 1);
+            for (;;) {
+                const uint32_t gi = table[slot];
+                if (gi == 0xFFFFFFFFu) {
+                    table[slot] = (uint32_t)groups.size();
+                    groups.push_back(LocalGroup{r, {r}});
+                    break;
+                }
+                const uint64_t f = groups[gi].first;
+                if (hash[f] == h && seq_len[f] == seq_len[r] && memcmp(text + seq_off[f], text + seq_off[r], seq_len[r]) == 0) {
+                    groups[gi].members.push_back(r);
+                    break;
+                }
+                slot = (slot + 1) & (cap - 1);
+            }
+        }
+    });
+    // global group ids in order of first appearance
+    struct Ref { uint64_t first; int bucket; uint32_t idx; };
+    std::vector<Ref> refs;
+    for (int b = 0; b < NBK; b++)
+        for (uint32_t i = 0; i < local[b].size(); i++) refs.push_back(Ref{local[b][i].first, b, i});
+    std::sort(refs.begin(), refs.end(), [](const Ref &x, const Ref &y) { return x.first < y.first; });
+    const uint64_t G = refs.size();
+    *n_groups_out = G;
+    uint64_t pos = 0;
+    for (uint64_t g = 0; g < G; g++) {
+        member_start[g] = pos;
+        pos += local[refs[g].bucket][refs[g].idx].members.size();
+    }
+    if (n) member_start[G] = pos;
+    // representative + names order of every group (moira.py:466-475)
+    {
+        const int parts = T * 8;
+        parallel_for(parts, T, [&](int p) {
+            std::vector<uint64_t> breakers, others;
+            for (uint64_t g = G * (uint64_t)p / parts, e = G * (uint64_t)(p + 1) / parts; g < e; g++) {
+                const std::vector<uint64_t> &m = local[refs[g].bucket][refs[g].idx].members;
+                breakers.clear();
+                others.clear();
+                uint64_t rep = m[0];
+                breakers.push_back(rep);
+                for (size_t k = 1; k < m.size(); k++) {
+                    if (ee[m[k]] < ee[rep]) { rep = m[k]; breakers.push_back(rep); }
+                    else others.push_back(m[k]);
+                }
+                uint64_t *out = members + member_start[g];
+                for (size_t k = 0; k < breakers.size(); k++) out[k] = breakers[breakers.size() - 1 - k];
+                for (size_t k = 0; k < others.size(); k++) out[breakers.size() + k] = others[k];
+                group_rep[g] = rep;
+                group_size[g] = m.size();
+                for (uint64_t r : m) group_of_read[r] = g;
+            }
+        });
+    }
+    for (uint64_t g = 0; g < G; g++) abundance_order[g] = g;
+    std::stable_sort(abundance_order, abundance_order + G, [&](uint64_t x, uint64_t y) { return group_size[x] > group_size[y]; });
+    return MOIRA_OK;
+}

@@ -162,3 +162,51 @@ def test_parse_fastq_multithreaded_equals_single_thread():
             moira_b200.parse_fastq(bad, 33, True)
         assert ei.value.code == L.ERR_PARSE and "record 3000" in ei.value.message and "LengthMismatchError" in ei.value.message
     L.lib.moira_set_host_threads(0)
+
+
+def test_collapse_matches_reference_semantics(forward_records, forward_names):
+    """moira_collapse vs the oracle's restatement of moira.py:459-475/491-504: groups, representatives,
+    names order and abundance order -- on the forward fixture (golden .names) and on synthetic duplicates."""
+    args = po.Args()
+    ee = np.array([po.process_filter(s, q, args)[2] for _, s, q in forward_records])
+    seqs = [s for _, s, _ in forward_records]
+    heads = [h for h, _, _ in forward_records]
+    ln = np.array([len(s) for s in seqs], dtype=np.uint32)
+    off = np.zeros(len(seqs), dtype=np.uint64)
+    off[1:] = np.cumsum(ln[:-1])
+    for threads in (1, 5):
+        col = moira_b200.collapse("".join(seqs).encode(), off, ln, ee, n_threads=threads)
+        got = {}
+        for g in col.order.tolist():
+            m = col.members[int(col.member_start[g]):int(col.member_start[g + 1])]
+            got[heads[int(col.rep[g])]] = [heads[int(r)] for r in m]
+            assert int(col.size[g]) == len(m) and int(m[0]) == int(col.rep[g])
+        golden = dict(forward_names["good"])
+        golden.update(forward_names["bad"])
+        assert got == golden and len(got) == 487
+        assert np.all(np.diff(col.size[col.order].astype(np.int64)) <= 0)        # abundance, largest first
+    # synthetic: heavy duplication, equal-ee ties, one-read groups; compare with the pure-python loop
+    rng = np.random.default_rng(4)
+    pool = ["".join(rng.choice(list("ACGT"), size=int(rng.integers(5, 40)))) for _ in range(300)]
+    seqs = [pool[int(i)] for i in rng.zipf(1.3, size=20000) % 300]
+    ee = np.round(rng.random(20000) * 4, 1)                                       # many exact ties
+    uniq = {}
+    for r, (s, e) in enumerate(zip(seqs, ee)):
+        u = uniq.get(s)
+        if u is None:
+            uniq[s] = [r, e, [r]]
+        elif e < u[1]:
+            u[0], u[1] = r, e
+            u[2].insert(0, r)
+        else:
+            u[2].append(r)
+    order = sorted(uniq, key=lambda s: len(uniq[s][2]), reverse=True)
+    ln = np.array([len(s) for s in seqs], dtype=np.uint32)
+    off = np.zeros(len(seqs), dtype=np.uint64)
+    off[1:] = np.cumsum(ln[:-1])
+    col = moira_b200.collapse("".join(seqs).encode(), off, ln, ee)
+    assert len(col.order) == len(order)
+    for g, s in zip(col.order.tolist(), order):
+        assert int(col.rep[g]) == uniq[s][0]
+        assert col.members[int(col.member_start[g]):int(col.member_start[g + 1])].tolist() == uniq[s][2]
+    assert np.array_equal(col.group_of_read[col.rep.astype(np.int64)], np.arange(len(col.rep), dtype=np.uint64))
