@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MOIRA_ABI_VERSION 1
+#define MOIRA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MOIRA_API __attribute__((visibility("default")))
@@ -67,6 +67,9 @@ extern "C" {
 #define MOIRA_AMBIGS_TREAT_AS_ERRORS 0 /* ee += Ns                       (moira.py:827-828) */
 #define MOIRA_AMBIGS_IGNORE          1
 #define MOIRA_AMBIGS_DISALLOW        2 /* reads containing 'N' rejected  (moira.py:911-922) */
+
+#define MOIRA_SLAB_Q8             0  /* one byte per base (the format described above) */
+#define MOIRA_SLAB_Q6             1  /* 6-bit transport image of a Q8 slab, see moira_pack_q6 (host-buffer entry points only) */
 
 #define MOIRA_EE_RAW              0  /* ee_out = what calculate_errors_* returns */
 #define MOIRA_EE_FINAL            1  /* ee_out = what process_data returns (after +Ns and floor) */
@@ -109,6 +112,8 @@ typedef struct moira_params {
                              0: decision mode, certain rejects may carry a lower bound (MOIRA_FLAG_LOWER_BOUND) */
     int32_t  ee_output;   /* MOIRA_EE_* */
     int32_t  length_sort; /* ragged batches: 0 = bucket reads by length on the device when it pays (default), 2 = never */
+    int32_t  slab_format; /* MOIRA_SLAB_*: format of the HOST slab given to moira_filter_batch / moira_submit */
+    int32_t  reserved;
     double   alpha;       /* --alpha */
     double   thr;         /* --uncert or --maxerrors value */
 } moira_params;
@@ -183,6 +188,15 @@ MOIRA_API int moira_pack_reads(const char *seq, const int32_t *quals, const uint
                      const uint32_t *lengths, uint64_t n_reads, int lower_n_ambiguous,
                      uint8_t *slab, uint64_t slab_capacity, uint64_t *out_offsets,
                      uint64_t *slab_bytes_out);
+
+/* 6-bit transport format.  A Q8 slab whose bytes are all <= 60 or markers (0xFD..0xFF) -- every Illumina
+ * run -- can cross PCIe at 3/4 of its size: every 16 slab bytes become 12 (four 6-bit codes per 3 bytes,
+ * little endian; 61/62/63 = pad/'n'/'N').  The image keeps the slab's structure (row r starts at
+ * offsets[r] * 3 / 4), so offsets[] and lengths[] are passed unchanged, in Q8 units; the library expands
+ * the image on the device before filtering.  slab8_bytes must be a multiple of 16 (pad with 0xFD).
+ * Returns MOIRA_ERR_BAD_QUALITY if a byte is not representable (use the Q8 slab then). */
+MOIRA_API int moira_pack_q6(const uint8_t *slab8, uint64_t slab8_bytes, uint8_t *slab6, uint64_t slab6_capacity,
+                            int n_threads);
 
 /* Parse a FASTQ text buffer (4-line records, moira.py:1152-1204) straight into a slab.
  * Sizing pass when slab == NULL: returns n_reads and the needed slab bytes.

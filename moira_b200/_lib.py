@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOIRA_B200_LIB") or os.path.join(_HERE, "libmoira_b200.so")   # env override: tuning experiments only
 
 # ---- constants mirrored from include/moira_b200.h -------------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK = 0
 ERR_BAD_ALPHA, ERR_LENGTH_MISMATCH, ERR_BAD_QUALITY, ERR_CUDA = -1, -2, -3, -4
 ERR_BAD_ARG, ERR_NOMEM, ERR_UNRESOLVED, ERR_PARSE = -5, -6, -7, -8
@@ -20,6 +20,7 @@ MODE_PB, MODE_POISSON, MODE_EXPECTED_ERROR = 0, 1, 2
 THR_UNCERT, THR_MAXERRORS = 0, 1
 AMBIGS_TREAT_AS_ERRORS, AMBIGS_IGNORE, AMBIGS_DISALLOW = 0, 1, 2
 EE_RAW, EE_FINAL = 0, 1
+SLAB_Q8, SLAB_Q6 = 0, 1
 FLAG_ACCEPT, FLAG_REASON_MASK, FLAG_LOWER_BOUND = 0x01, 0x0E, 0x10
 FLAG_HAS_N, FLAG_NUMERIC, FLAG_NEAR_CUTOFF = 0x20, 0x40, 0x80
 REASON_NONE, REASON_ERRORS, REASON_LENGTH, REASON_AMBIGS = 0, 1, 2, 3
@@ -31,7 +32,7 @@ EXPORTS = [
     "moira_abi_version", "moira_last_error", "moira_params_default", "moira_ctx_create",
     "moira_ctx_destroy", "moira_ctx_sm_count", "moira_build_lut", "moira_ctx_get_lut",
     "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_filter_batch",
-    "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads",
+    "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads", "moira_pack_q6",
     "moira_parse_fastq", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
     "moira_ctx_last_kernel_ms",
 ]
@@ -43,6 +44,7 @@ class Params(ctypes.Structure):
         ("mode", ctypes.c_int32), ("thr_kind", ctypes.c_int32), ("ambigs", ctypes.c_int32),
         ("round_flag", ctypes.c_int32), ("truncate", ctypes.c_uint32), ("exact_ee", ctypes.c_int32),
         ("ee_output", ctypes.c_int32), ("length_sort", ctypes.c_int32),
+        ("slab_format", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("alpha", ctypes.c_double), ("thr", ctypes.c_double),
     ]
 
@@ -82,6 +84,7 @@ lib.moira_wait.argtypes = [_vp, _i]
 lib.moira_calculate_errors_PB.argtypes = [_vp, ctypes.c_char_p, _vp, _u64, _dbl, ctypes.POINTER(_dbl),
                                           ctypes.POINTER(ctypes.c_int32)]
 lib.moira_pack_reads.argtypes = [_vp, _vp, _vp, _vp, _u64, _i, _vp, _u64, _vp, ctypes.POINTER(_u64)]
+lib.moira_pack_q6.argtypes = [_vp, _u64, _vp, _u64, _i]
 lib.moira_parse_fastq.argtypes = [_vp, _u64, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                   ctypes.POINTER(_u64), ctypes.POINTER(_u64)]
 lib.moira_fastq_count_reads.argtypes = [_vp, _u64, ctypes.POINTER(_u64)]

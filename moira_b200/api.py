@@ -28,6 +28,7 @@ class FilterParams:
     truncate: int | None = None            # --truncate
     exact_ee: bool = True                  # exact statistic for every read (needed by --collapse, moira.py:466)
     ee_output: str = "raw"                 # 'raw' = calculate_errors_* value, 'final' = process_data value
+    slab_format: str = "q8"                # host slab format: 'q8' (one byte per base) or 'q6' (pack_q6 transport image)
     length_sort: int = 0                   # ragged batches: 0 = bucket by length on the device when it pays, 2 = never
 
     def to_c(self) -> L.Params:
@@ -47,6 +48,7 @@ class FilterParams:
         p.exact_ee = 1 if self.exact_ee else 0
         p.ee_output = L.EE_FINAL if self.ee_output == "final" else L.EE_RAW
         p.length_sort = int(self.length_sort)
+        p.slab_format = L.SLAB_Q6 if self.slab_format == "q6" else L.SLAB_Q8
         p.alpha = float(self.alpha)
         return p
 
@@ -290,6 +292,19 @@ def pack_arrays(seq_all, q_all, in_off, lengths, lower_n_ambiguous: bool = True,
     return slab[:nbytes], offsets, lengths
 
 
+def pack_q6(slab8, out=None, n_threads: int = 0):
+    """6-bit transport image of a Q8 slab (moira_pack_q6): 3/4 of the bytes over PCIe.  Raises
+    MoiraError(ERR_BAD_QUALITY) if a quality above 60 is present."""
+    slab8 = _as(slab8, np.uint8)
+    if slab8.nbytes % 16:
+        slab8 = np.concatenate([slab8, np.full(16 - slab8.nbytes % 16, 0xFD, np.uint8)])
+    need = slab8.nbytes // 16 * 12
+    if out is None:
+        out = np.empty(need, dtype=np.uint8)
+    L.check(lib.moira_pack_q6(_ptr(slab8), slab8.nbytes, _ptr(out), out.nbytes, int(n_threads)))
+    return out[:need]
+
+
 def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = True):
     """FASTQ bytes -> (slab, offsets, lengths, hdr_off, hdr_len, seq_off, qual_off) via moira_parse_fastq.
     Rows parsed by different host threads are separated by a little slack in the slab (offsets skip it).
@@ -347,4 +362,4 @@ def collapse(text, seq_off, seq_len, ee, n_threads: int = 0) -> CollapseResult:
 
 
 __all__ = ["collapse", "CollapseResult","Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",
-           "pack_arrays", "parse_fastq", "build_lut"]
+           "pack_arrays", "pack_q6", "parse_fastq", "build_lut"]

@@ -82,7 +82,7 @@ struct StreamBuf {
 
 struct Ticket {
     bool busy = false;
-    DevBuf slab, offsets, lengths, ee, ns, flags, counters;
+    DevBuf slab, slab6, offsets, lengths, ee, ns, flags, counters;
     cudaEvent_t done[2] = {nullptr, nullptr};
     uint64_t *counters_out = nullptr;
     uint64_t *counters_pinned = nullptr;
@@ -212,6 +212,7 @@ int check_params(const moira_params *p)
     if (!(oma < 1.0)) return fail(MOIRA_ERR_BAD_ALPHA, "Alpha must be between 0 and 1 (1 - alpha rounds to 1)");
     if (p->mode < MOIRA_MODE_PB || p->mode > MOIRA_MODE_EXPECTED_ERROR) return fail(MOIRA_ERR_BAD_ARG, "unknown mode %d", p->mode);
     if (p->thr_kind != MOIRA_THR_UNCERT && p->thr_kind != MOIRA_THR_MAXERRORS) return fail(MOIRA_ERR_BAD_ARG, "unknown thr_kind %d", p->thr_kind);
+    if (p->slab_format != MOIRA_SLAB_Q8 && p->slab_format != MOIRA_SLAB_Q6) return fail(MOIRA_ERR_BAD_ARG, "unknown slab_format %d", p->slab_format);
     if (p->ambigs < 0 || p->ambigs > MOIRA_AMBIGS_DISALLOW) return fail(MOIRA_ERR_BAD_ARG, "unknown ambigs %d", p->ambigs);
     if (!(p->thr == p->thr)) return fail(MOIRA_ERR_BAD_ARG, "threshold is NaN");
     return MOIRA_OK;
@@ -453,7 +454,7 @@ int moira_ctx_destroy(moira_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &t : c->tickets) {
-        for (DevBuf *b : {&t.slab, &t.offsets, &t.lengths, &t.ee, &t.ns, &t.flags, &t.counters})
+        for (DevBuf *b : {&t.slab, &t.slab6, &t.offsets, &t.lengths, &t.ee, &t.ns, &t.flags, &t.counters})
             if (b->p) cudaFree(b->p);
         for (int i = 0; i < 2; i++) if (t.done[i]) cudaEventDestroy(t.done[i]);
         if (t.counters_pinned) cudaFreeHost(t.counters_pinned);
@@ -555,7 +556,10 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
         *ticket_out = ti;
         return MOIRA_OK;
     }
-    if ((rc = ensure(t.slab, slab_bytes + 16)) || (rc = ensure(t.offsets, n * 8)) || (rc = ensure(t.lengths, n * 4)) ||
+    const bool q6 = params->slab_format == MOIRA_SLAB_Q6;   // `slab` is the 3/4-size transport image; offsets/lengths are in slab units
+    const uint64_t slab8_bytes = q6 ? slab_bytes / 12 * 16 : slab_bytes;
+    if (q6 && (rc = ensure(t.slab6, slab_bytes + 256))) return rc;
+    if ((rc = ensure(t.slab, slab8_bytes + 256)) || (rc = ensure(t.offsets, n * 8)) || (rc = ensure(t.lengths, n * 4)) ||
         (rc = ensure(t.ee, n * 8)) || (rc = ensure(t.ns, n * 4)) || (rc = ensure(t.flags, n)) ||
         (rc = ensure(t.counters, MOIRA_N_COUNTERS * 8)))
         return rc;
@@ -590,7 +594,7 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
         while (end < n) {
             const uint64_t row_end = offsets[end] + (((uint64_t)lengths[end] + 15u) & ~15ull);
             if (offsets[end] < b0) return fail(MOIRA_ERR_BAD_ARG, "offsets must be non-decreasing (read %llu)", (unsigned long long)end);
-            if (row_end > slab_bytes + 15) return fail(MOIRA_ERR_BAD_ARG, "read %llu extends past the slab", (unsigned long long)end);
+            if (row_end > slab8_bytes + 15) return fail(MOIRA_ERR_BAD_ARG, "read %llu extends past the slab", (unsigned long long)end);
             if (offsets[end] & 15u) return fail(MOIRA_ERR_BAD_ARG, "offset of read %llu is not a multiple of 16", (unsigned long long)end);
             if (end > start && row_end - b0 > CHUNK_BYTES) break;
             b1 = std::max(b1, row_end);
@@ -601,8 +605,18 @@ int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const u
             end++;
         }
         cudaStream_t s = c->streams[ci & 1];
-        const uint64_t copy_end = std::min<uint64_t>(b1, slab_bytes);
-        if (copy_end > b0) CU(cudaMemcpyAsync(d_slab + b0, slab + b0, copy_end - b0, cudaMemcpyHostToDevice, s));
+        if (q6) {
+            // image bytes [b0*3/4, b1*3/4) travel (b0, b1 are multiples of 16), then expand on the device
+            const uint64_t i0 = b0 / 16 * 12, i1 = std::min<uint64_t>((b1 + 15) / 16 * 12, slab_bytes);
+            uint8_t *d_img = (uint8_t *)t.slab6.p;
+            if (i1 > i0) CU(cudaMemcpyAsync(d_img + i0, slab + i0, i1 - i0, cudaMemcpyHostToDevice, s));
+            LaunchCfg ucfg{c->sm_count, s};
+            if (launch_unpack_q6(d_img + i0, d_slab + b0, b1 - b0, ucfg)) return fail(MOIRA_ERR_CUDA, "unpack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            c->launches++;
+        } else {
+            const uint64_t copy_end = std::min<uint64_t>(b1, slab_bytes);
+            if (copy_end > b0) CU(cudaMemcpyAsync(d_slab + b0, slab + b0, copy_end - b0, cudaMemcpyHostToDevice, s));
+        }
         const uint64_t cn = end - start;
         uniform = uniform && stride0 >= 16 && (stride0 & 15u) == 0 && stride0 >= max_len;
         if (uniform && same_len) {

@@ -53,6 +53,56 @@ extern "C" int moira_pack_reads(const char *seq, const int32_t *quals, const uin
     return MOIRA_OK;
 }
 
+// ---- 6-bit transport image ------------------------------------------------------------------------
+namespace {
+// 16 slab bytes -> 12 image bytes; returns the OR of "not representable" flags
+__attribute__((target_clones("avx2", "default")))
+uint32_t q6_pack_range(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint64_t groups)
+{
+    uint32_t bad = 0;
+    for (uint64_t g = 0; g < groups; g++) {
+        const uint8_t *s = in + g * 16;
+        uint8_t *d = out + g * 12;
+        uint8_t c[16];
+        for (int i = 0; i < 16; i++) {
+            const uint8_t b = s[i];
+            const uint8_t m = (uint8_t)(b - 192);                 // 0xFD..0xFF -> 61..63
+            c[i] = b >= 0xFD ? m : b;
+            bad |= (uint32_t)(b > 60 && b < 0xFD);
+        }
+        for (int k = 0; k < 4; k++) {
+            const uint32_t v = (uint32_t)c[4 * k] | ((uint32_t)c[4 * k + 1] << 6) | ((uint32_t)c[4 * k + 2] << 12) | ((uint32_t)c[4 * k + 3] << 18);
+            d[3 * k] = (uint8_t)v;
+            d[3 * k + 1] = (uint8_t)(v >> 8);
+            d[3 * k + 2] = (uint8_t)(v >> 16);
+        }
+    }
+    return bad;
+}
+}  // namespace
+
+extern "C" int moira_pack_q6(const uint8_t *slab8, uint64_t slab8_bytes, uint8_t *slab6, uint64_t slab6_capacity, int n_threads)
+{
+    if ((slab8_bytes && (!slab8 || !slab6)) || (slab8_bytes & 15u)) return hfail(MOIRA_ERR_BAD_ARG, "slab8_bytes must be a multiple of 16");
+    if (slab6_capacity < slab8_bytes / 16 * 12) return hfail(MOIRA_ERR_BAD_ARG, "slab6 capacity too small (need %llu)", (unsigned long long)(slab8_bytes / 16 * 12));
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 64) T = 64;
+    const uint64_t groups = slab8_bytes / 16;
+    if (groups < (1u << 16)) T = 1;
+    std::vector<uint32_t> bad(T, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) {
+        const uint64_t a = groups * (uint64_t)t / T, b = groups * (uint64_t)(t + 1) / T;
+        auto fn = [&, t, a, b] { bad[t] = q6_pack_range(slab8 + a * 16, slab6 + a * 12, b - a); };
+        if (T == 1) fn(); else th.emplace_back(fn);
+    }
+    for (auto &x : th) x.join();
+    for (int t = 0; t < T; t++)
+        if (bad[t]) return hfail(MOIRA_ERR_BAD_QUALITY, "a quality above 60 cannot travel in the 6-bit format; use the Q8 slab");
+    return MOIRA_OK;
+}
+
 // ---- FASTQ ---------------------------------------------------------------------------------------
 // Parallel over host threads: the text is cut into byte ranges, every thread counts the newlines of
 // its range, a prefix sum gives each range its first line number, and a thread owns the records

@@ -28,6 +28,8 @@
 #include <cuda.h>
 #include <math.h>
 
+#include <algorithm>
+
 #include "fact_table.h"
 #include "moira_internal.h"
 
@@ -951,6 +953,32 @@ __global__ void __launch_bounds__(256) len_scatter_kernel(const FilterArgs a, co
 }
 
 // ==================================================================================================
+// 6-bit transport image -> slab: 12 image bytes (16 codes) -> 16 slab bytes per thread; flat over the
+// whole chunk (rows keep their positions: image offset = slab offset * 3/4).  Memory-bound.
+// ==================================================================================================
+__device__ __forceinline__ uint32_t q6_expand4(uint32_t v24)
+{
+    // four 6-bit codes in bits 0..23 -> four bytes; 61..63 -> 0xFD..0xFF
+    uint32_t b = (v24 & 0x3Fu) | ((v24 & 0xFC0u) << 2) | ((v24 & 0x3F000u) << 4) | ((v24 & 0xFC0000u) << 6);
+    const uint32_t hi = ((b + 0x03030303u) & 0x40404040u) >> 6;      // 1 in every byte whose code is > 60
+    return b + hi * 192u;
+}
+
+// one thread per 16 slab bytes (= 12 image bytes = 3 words): exact, never writes past the range
+__global__ void __launch_bounds__(256) unpack_q6_kernel(const uint32_t *__restrict__ in, uint4 *__restrict__ out, uint64_t n16)
+{
+    for (uint64_t u = blockIdx.x * 256ull + threadIdx.x; u < n16; u += gridDim.x * 256ull) {
+        const uint32_t w0 = __ldg(in + 3 * u), w1 = __ldg(in + 3 * u + 1), w2 = __ldg(in + 3 * u + 2);
+        uint4 o;
+        o.x = q6_expand4(w0 & 0xFFFFFFu);
+        o.y = q6_expand4((w0 >> 24) | ((w1 & 0xFFFFu) << 8));
+        o.z = q6_expand4((w1 >> 16) | ((w2 & 0xFFu) << 16));
+        o.w = q6_expand4(w2 >> 8);
+        out[u] = o;
+    }
+}
+
+// ==================================================================================================
 // FP64 issue-rate probe: per thread 4 independent copies of the K=4 update (7 DMUL + 4 DADD).
 // ==================================================================================================
 __global__ void __launch_bounds__(512) fp64_peak_kernel(int iters, double *sink, double p)
@@ -1057,6 +1085,16 @@ int launch_length_sort(const FilterArgs &a, const LenSortBufs &b, int single_gro
     len_hist_kernel<<<grid, 256, 0, cfg.stream>>>(a, b.hist);
     len_scan_kernel<<<1, 1024, 0, cfg.stream>>>(a, b.hist, b.bucket_start, b.cursor, b.group_start, b.group_count, single_group);
     len_scatter_kernel<<<grid, 256, 0, cfg.stream>>>(a, b.bucket_start, b.cursor, b.queue);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_bytes, const LaunchCfg &cfg)
+{
+    const uint64_t n48 = slab_bytes / 16;           // units of 16 slab bytes <- 12 image bytes
+    if (!n48) return 0;
+    const uint64_t want = (n48 + 255) / 256;
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)cfg.sm_count * 16);
+    unpack_q6_kernel<<<grid, 256, 0, cfg.stream>>>(reinterpret_cast<const uint32_t *>(d_image), reinterpret_cast<uint4 *>(d_slab), n48);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

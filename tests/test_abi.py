@@ -31,7 +31,7 @@ def test_header_constants_match_binding():
     for k, v in consts.items():
         if hasattr(L, k):
             assert getattr(L, k) == int(v, 0), k
-    assert ctypes.sizeof(L.Params) == 48
+    assert ctypes.sizeof(L.Params) == 56
 
 
 def test_lut_matches_oracle_tables():
@@ -210,3 +210,25 @@ def test_collapse_matches_reference_semantics(forward_records, forward_names):
         assert int(col.rep[g]) == uniq[s][0]
         assert col.members[int(col.member_start[g]):int(col.member_start[g + 1])].tolist() == uniq[s][2]
     assert np.array_equal(col.group_of_read[col.rep.astype(np.int64)], np.arange(len(col.rep), dtype=np.uint64))
+
+
+def test_q6_transport_image_roundtrip():
+    """moira_pack_q6: 16 slab bytes -> 12 image bytes; decoded with numpy it gives the slab back."""
+    rng = np.random.default_rng(1)
+    slab = rng.integers(0, 61, size=16 * 70000, dtype=np.uint8)
+    slab[rng.random(slab.size) < 0.02] = 0xFF
+    slab[rng.random(slab.size) < 0.01] = 0xFE
+    slab[rng.random(slab.size) < 0.03] = 0xFD
+    for threads in (1, 6):
+        img = moira_b200.pack_q6(slab, n_threads=threads)
+        assert img.size == slab.size * 3 // 4
+        b = img.reshape(-1, 3).astype(np.uint32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        codes = np.stack([(v >> (6 * k)) & 63 for k in range(4)], axis=1).reshape(-1)
+        back = np.where(codes > 60, codes + 192, codes).astype(np.uint8)
+        assert np.array_equal(back, slab)
+    bad = slab.copy()
+    bad[12345] = 61
+    with pytest.raises(moira_b200.MoiraError) as ei:
+        moira_b200.pack_q6(bad)
+    assert ei.value.code == L.ERR_BAD_QUALITY

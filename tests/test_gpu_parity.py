@@ -353,3 +353,15 @@ def test_near_cutoff_band_is_flagged_and_counted(ctx):
         assert bool(r.near_cutoff[i]) is expect_near
         assert bool(r.accept[i]) == (target <= thr)
         assert int(r.counters[L.CNT_NEAR_CUTOFF]) == int(r.near_cutoff.sum())
+
+
+def test_q6_transport_format_gives_identical_results(ctx):
+    """Host slabs sent as 6-bit images (3/4 of the PCIe bytes) are expanded on the device: same outputs."""
+    for profile, n in (("v4", 30000), ("mixed", 5000)):
+        slab, off, ln = synth.generate(profile, n, 17)
+        img = moira_b200.pack_q6(slab)
+        for exact in (False, True):
+            r8 = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact))
+            r6 = ctx.filter_batch(img, off, ln, FilterParams(exact_ee=exact, slab_format="q6"))
+            assert np.array_equal(r8.ee, r6.ee) and np.array_equal(r8.ns, r6.ns) and np.array_equal(r8.flags, r6.flags)
+            assert np.array_equal(r8.counters, r6.counters)
