@@ -107,3 +107,28 @@ def test_compression_and_formats(tmp_path):
     for i in range(0, len(good), 4):
         assert float(good[i].split(";ee=")[1].split(";")[0]) <= 2.0
     shutil.rmtree(tmp_path, ignore_errors=True)
+
+
+@pytest.mark.gpu
+def test_fasta_qual_input_reclassifies_golden_contigs(tmp_path, contigs):
+    """BASELINE config C1's shape: 253-bp contigs as fasta + qual (the reference's own golden contigs,
+    moira/test/test_results/paired.qc.*): 324 good / 76 bad, same labels, same records."""
+    fa, qu = tmp_path / "c.fasta", tmp_path / "c.qual"
+    with open(fa, "w") as f, open(qu, "w") as q:
+        for c in contigs:
+            f.write(">%s\textra\n%s\n" % (c["header"], c["seq"]))
+            q.write(">%s\n%s\n" % (c["header"], " ".join(map(str, c["quals"]))))
+    prefix = str(tmp_path / "out")
+    assert cli.run(["-ff", str(fa), "-fq", str(qu), "-op", prefix, "-c", "False", "--silent"]) == 0
+    good = _records(prefix + ".qc.good.fasta")
+    bad = _records(prefix + ".qc.bad.fasta")
+    assert len(good) == 324 and len(bad) == 76
+    for c in contigs:
+        if c["label"] == "good":
+            assert good[">" + c["header"]] == c["seq"]
+        else:
+            assert bad[">%s\tuncert > 0.010" % c["header"]] == c["seq"]
+    with pytest.raises(cli.NameMismatchError):
+        bad_q = tmp_path / "bad.qual"
+        bad_q.write_text(open(qu).read().replace(contigs[3]["header"], "someone_else", 1))
+        cli.run(["-ff", str(fa), "-fq", str(bad_q), "-op", prefix, "--silent"])
