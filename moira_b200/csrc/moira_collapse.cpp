@@ -16,7 +16,6 @@
 #include <string.h>
 
 #include <algorithm>
-#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -56,21 +55,7 @@ struct LocalGroup {
 template <typename F>
 void parallel_for(int n_items, int threads, F &&fn)
 {
-    if (threads <= 1 || n_items <= 1) {
-        for (int i = 0; i < n_items; i++) fn(i);
-        return;
-    }
-    std::atomic<int> next{0};
-    std::vector<std::thread> th;
-    for (int t = 0; t < std::min(threads, n_items); t++)
-        th.emplace_back([&] {
-            for (;;) {
-                const int i = next.fetch_add(1);
-                if (i >= n_items) break;
-                fn(i);
-            }
-        });
-    for (auto &x : th) x.join();
+    moira::parallel_run(n_items, threads, std::function<void(int)>(fn));
 }
 
 }  // namespace

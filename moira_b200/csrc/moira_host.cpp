@@ -6,12 +6,84 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 #include "moira_internal.h"
 
 #define hfail moira::fail
+
+// ---- persistent worker pool -------------------------------------------------------------------------
+// The parsers run several short parallel phases per call; spawning threads each time costs more than
+// the phases themselves.  Workers are created once and parked on a condition variable.
+namespace moira {
+namespace {
+struct Pool {
+    std::mutex run_mutex;                 // one parallel_run at a time
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> workers;
+    const std::function<void(int)> *fn = nullptr;
+    int n_tasks = 0, next = 0, pending = 0;
+    uint64_t generation = 0;
+    void worker()
+    {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_work.wait(lk, [&] { return generation != seen && next < n_tasks; });
+            while (next < n_tasks) {
+                const int t = next++;
+                lk.unlock();
+                (*fn)(t);
+                lk.lock();
+                if (--pending == 0) cv_done.notify_all();
+            }
+            seen = generation;
+        }
+    }
+};
+Pool &pool()
+{
+    static Pool *p = new Pool();   // never destroyed: workers outlive static destruction safely
+    return *p;
+}
+}  // namespace
+
+void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn)
+{
+    if (n_tasks <= 0) return;
+    if (n_tasks == 1 || n_threads <= 1) {
+        for (int t = 0; t < n_tasks; t++) fn(t);
+        return;
+    }
+    Pool &p = pool();
+    std::lock_guard<std::mutex> run_lock(p.run_mutex);
+    std::unique_lock<std::mutex> lk(p.m);
+    while ((int)p.workers.size() < n_threads - 1) {
+        p.workers.emplace_back([&p] { p.worker(); });
+        p.workers.back().detach();
+    }
+    p.fn = &fn;
+    p.n_tasks = n_tasks;
+    p.next = 0;
+    p.pending = n_tasks;
+    p.generation++;
+    p.cv_work.notify_all();
+    while (p.next < p.n_tasks) {          // the caller works too
+        const int t = p.next++;
+        lk.unlock();
+        fn(t);
+        lk.lock();
+        --p.pending;
+    }
+    p.cv_done.wait(lk, [&] { return p.pending == 0; });
+    p.fn = nullptr;
+}
+}  // namespace moira
 
 namespace {
 
@@ -91,13 +163,10 @@ extern "C" int moira_pack_q6(const uint8_t *slab8, uint64_t slab8_bytes, uint8_t
     const uint64_t groups = slab8_bytes / 16;
     if (groups < (1u << 16)) T = 1;
     std::vector<uint32_t> bad(T, 0);
-    std::vector<std::thread> th;
-    for (int t = 0; t < T; t++) {
+    moira::parallel_run(T, T, [&](int t) {
         const uint64_t a = groups * (uint64_t)t / T, b = groups * (uint64_t)(t + 1) / T;
-        auto fn = [&, t, a, b] { bad[t] = q6_pack_range(slab8 + a * 16, slab6 + a * 12, b - a); };
-        if (T == 1) fn(); else th.emplace_back(fn);
-    }
-    for (auto &x : th) x.join();
+        bad[t] = q6_pack_range(slab8 + a * 16, slab6 + a * 12, b - a);
+    });
     for (int t = 0; t < T; t++)
         if (bad[t]) return hfail(MOIRA_ERR_BAD_QUALITY, "a quality above 60 cannot travel in the 6-bit format; use the Q8 slab");
     return MOIRA_OK;
@@ -274,12 +343,7 @@ int moira::parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_of
         segs[t].begin = text_bytes * (uint64_t)t / T;
         segs[t].end = text_bytes * (uint64_t)(t + 1) / T;
     }
-    auto run = [&](auto &&fn) {
-        if (T == 1) { fn(0); return; }
-        std::vector<std::thread> th;
-        for (int t = 0; t < T; t++) th.emplace_back(fn, t);
-        for (auto &x : th) x.join();
-    };
+    auto run = [&](const std::function<void(int)> &fn) { moira::parallel_run(T, T, fn); };
     // phase 0: newlines per range, and the first line start inside each range
     run([&](int t) {
         FqSeg &g = segs[t];

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
+
 #include "../../include/moira_b200.h"
 
 namespace moira {
@@ -107,6 +109,9 @@ int parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_offset, i
                       uint64_t slab_capacity, uint64_t *out_offsets, uint32_t *lengths, uint64_t *hdr_off,
                       uint32_t *hdr_len, uint64_t *seq_off, uint64_t *qual_off, uint64_t max_reads,
                       uint64_t *n_reads_out, uint64_t *slab_bytes_out, uint64_t *consumed_out, int final_range);
+
+// run fn(0..n_tasks-1) on up to n_threads threads of a persistent host worker pool (moira_host.cpp)
+void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn);
 
 // sets the thread-local message returned by moira_last_error() and returns `code`
 int fail(int code, const char *fmt, ...);
