@@ -122,3 +122,25 @@ def test_decide_batch_matches_scalar():
         for i in rng.choice(200, 40, replace=False):
             seq = "N" * int(has_n[i]) + "A" * (int(ln[i]) - int(has_n[i]))
             assert (bool(ok[i]), int(reason[i])) == po.decide(seq, float(eef[i]), args)
+
+
+def test_property_restatements_agree_with_reference_binary():
+    """hypothesis: random short reads (N/n, Q = 0..93, any alpha): the O(L j*) restatement, the faithful
+    O(L j*^2) restatement and -- when built -- the unmodified reference binary agree bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    ref = po.ref_module() if po.have_ref() else None
+    read = st.lists(st.tuples(st.sampled_from("ACGTNn"), st.integers(0, 93)), min_size=0, max_size=60)
+
+    @settings(max_examples=300, deadline=None)
+    @given(read, st.sampled_from([0.5, 0.2, 0.05, 0.005, 0.001, 1e-6]))
+    def check(pairs, alpha):
+        seq = "".join(b for b, _ in pairs)
+        quals = [q for _, q in pairs]
+        fast = po.pb_c(seq, quals, alpha)
+        assert fast == po.pb_c(seq, quals, alpha, faithful=True)
+        if ref is not None:
+            assert fast == ref.calculate_errors_PB(seq, quals, alpha)
+        assert fast[1] == seq.count("N") + seq.count("n") and fast[0] >= 0.0
+
+    check()
