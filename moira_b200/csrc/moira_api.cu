@@ -374,7 +374,12 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
         if (timed) { CU(cudaEventRecord(c->t1[c->n_timed], stream)); c->n_timed++; c->timed_name = name; }
         if (ladder) {
             for (int b = 0; b < NB; b++) {
-                if (b > 0 && b < a.min_rung) continue;
+                if (b == 1) {   // every thread-per-read rung in one launch
+                    if (launch_ladder_tpr(a, cfg)) return fail(MOIRA_ERR_CUDA, "ladder launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    c->launches++;
+                    b = N_TPR_RUNGS;
+                    continue;
+                }
                 if (launch_rung(a, b, cfg)) return fail(MOIRA_ERR_CUDA, "rung %d launch failed: %s", b, cudaGetErrorString(cudaGetLastError()));
                 c->launches++;
             }

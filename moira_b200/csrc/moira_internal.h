@@ -15,6 +15,7 @@ namespace moira {
 // the error count, fp32) and forwards it to the cheapest rung that holds that many.  A rung that
 // still cannot settle a read hands it to the next one; the last rung (block-per-read) takes any K.
 constexpr int NB = 20;
+constexpr int N_TPR_RUNGS = 14;   // rungs 1..14 (one fused launch, ladder_tpr_kernel)
 // rungs 1..14 thread-per-read, 15..18 warp-per-read, 19 block-per-read
 __host__ __device__ constexpr int rung_cap(int b)
 {
@@ -77,8 +78,10 @@ struct LaunchCfg {
 int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, const char **name);
 // Poisson / expected-error, thread-per-read
 int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name);
-// ladder rung b over queue b
+// ladder rung b over queue b (b == 0: classifier; b > N_TPR_RUNGS: warp-/block-per-read rungs)
 int launch_rung(const FilterArgs &a, int b, const LaunchCfg &cfg);
+// rungs 1..N_TPR_RUNGS in one launch
+int launch_ladder_tpr(const FilterArgs &a, const LaunchCfg &cfg);
 // ---- on-device length bucketing of ragged batches (counting sort by padded length) ----------------
 constexpr int LEN_BUCKETS = 4096;        // bucket b holds reads with ceil16(eff)/16 == b (last bucket: anything longer)
 constexpr int N_FIRST_K = 17;            // first-pass K templates, see first_pass_ks()

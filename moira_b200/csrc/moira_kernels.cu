@@ -369,21 +369,24 @@ __device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t swz, uint32_t
 // ==================================================================================================
 // thread-per-read kernels
 // ==================================================================================================
-// MODE 0: Poisson-binomial with K entries.  MODE 1: Lambda accumulation (K == 1).
-// MODE 2: ladder classifier (K == 2): mean/variance of the error count -> rung.
-// TMA: uniform-stride first pass; tiles arrive as swizzled 2-D tensor boxes (one UTMALDG per warp and
-// chunk) instead of cp.async pieces.
-template <int K, int MODE, bool EQP, bool TMA>
-__global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterArgs a, const __grid_constant__ CUtensorMap tmap)
+// Shared-memory context of a thread-per-read CTA.
+struct TprCtx {
+    uint32_t lut_lane;     // shared address of this lane's replica column of the lookup table
+    uint32_t stage_warp;   // shared address of this warp's two stage buffers
+    uint32_t bar0;         // shared address of this warp's two mbarriers (TMA staging)
+    uint32_t *s_cnt, *s_hist;
+    int lane, warp;
+};
+
+// One-time CTA setup: run-time layout of the dynamic shared memory, replicated lookup table, counters,
+// mbarriers.  PL: the table holds p only (32 x 8 B per row) instead of (q, e) pairs (16 x 16 B).
+template <int TPR_WARPS, int MODE, bool PL, bool TMA>
+__device__ __forceinline__ TprCtx tpr_setup(const FilterArgs &a, uint8_t *smem)
 {
-    constexpr int TPR_WARPS = tpr_warps(K);
     constexpr int TPR_THREADS = TPR_WARPS * 32;
     constexpr uint32_t STG = TMA ? 32u * CHUNK : (uint32_t)STAGE_BYTES;   // bytes of one warp-stage
-    extern __shared__ __align__(128) uint8_t smem[];
-    if (a.queue && (a.seg_count ? *a.seg_count : *a.queue_count) == 0) return;   // empty rung / segment: nothing to set up
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-
     // ---- run-time layout of the dynamic shared memory (TPR_SMEM bytes) ----------------------
     //   [base, lut)            stage buffers of the first nA warps (whatever fits below the table)
     //   [lut, lut + 64 KB)     lookup table, 64 KB aligned (see LUT_BYTES)
@@ -401,7 +404,6 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
     uint8_t *lut_ptr = smem + (lut - base);
 
     // ---- one-time setup: replicated lookup table, counters ----
-    constexpr bool PL = (EQP && MODE == 0 && !(MOIRA_PAIR_LUT && K <= 8)) || MODE == 1;   // p only: 32 x 8 B per row
     if (PL) {
         double *t = reinterpret_cast<double *>(lut_ptr);
         for (int i = threadIdx.x; i < 256 * 32; i += TPR_THREADS) t[i] = a.lut_p[i >> 5];
@@ -427,16 +429,32 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
     }
     __syncthreads();
 
-    const uint32_t lut_lane = lut + (PL ? lane * 8 : (lane & 15) * 16);
-    const uint32_t stage_warp = (uint32_t)warp < n_below ? below0 + warp * 2 * STG : above + (warp - n_below) * 2 * STG;
+    TprCtx c;
+    c.lut_lane = lut + (PL ? lane * 8 : (lane & 15) * 16);
+    c.stage_warp = (uint32_t)warp < n_below ? below0 + warp * 2 * STG : above + (warp - n_below) * 2 * STG;
+    c.bar0 = bar0;
+    c.s_cnt = s_cnt;
+    c.s_hist = s_hist;
+    c.lane = lane;
+    c.warp = warp;
+    return c;
+}
+
+// The persistent tile loop of one warp: tiles first_tile, first_tile + tile_step, ... of `count` reads
+// (taken through `queue` when it is not null), K PMF entries per read.  All staging state is local, so
+// a CTA may call this several times with different K (ladder kernel).
+template <int K, int MODE, bool PL, bool TMA>
+__device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap *tmap_ptr, const TprCtx &ctx,
+                                          const uint32_t *queue, uint32_t count, uint32_t first_tile, uint32_t total_warps)
+{
+    constexpr uint32_t STG = TMA ? 32u * CHUNK : (uint32_t)STAGE_BYTES;
+    const int lane = ctx.lane;
+    const uint32_t lut_lane = ctx.lut_lane, stage_warp = ctx.stage_warp, bar0 = ctx.bar0;
+    uint32_t *s_cnt = ctx.s_cnt, *s_hist = ctx.s_hist;
     const uint32_t stage0 = stage_warp + lane * (TMA ? CHUNK : ROW_STRIDE);
     const uint32_t swz = TMA ? (lane & 7) << 4 : 0u;
-
-    const uint32_t *queue = a.queue && a.seg_start ? a.queue + *a.seg_start : a.queue;
-    const uint32_t count = a.queue ? (a.seg_count ? *a.seg_count : *a.queue_count) : a.n;
     const uint32_t n_tiles = (count + 31) >> 5;
-    const uint32_t total_warps = gridDim.x * TPR_WARPS;
-    uint32_t tile = blockIdx.x * TPR_WARPS + warp;
+    uint32_t tile = first_tile;
     uint32_t it = 0;   // stage jobs issued == consumed so far by this warp
     // Always copy cooperatively (8 consecutive lanes fetch one 128-byte line of one row): 4 L1 tags per
     // LDGSTS instead of 32 when every lane fetches from its own row -- also for scattered ladder rows.
@@ -461,7 +479,7 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
             if (lane == 0) {
                 const uint32_t bar = bar0 + (s & 1) * 8;
                 mbar_arrive_expect_tx(bar, 32u * CHUNK);
-                tma_tile_g2s(stage_warp + (s & 1) * STG, &tmap, (int)(c * CHUNK), (int)(t * 32u), bar);
+                tma_tile_g2s(stage_warp + (s & 1) * STG, tmap_ptr, (int)(c * CHUNK), (int)(t * 32u), bar);
             }
             return;
         }
@@ -635,8 +653,61 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
         tile = next_tile;
         valid = nvalid; r_local = nr_local; g = ng;
     }
+}
+
+// MODE 0: Poisson-binomial with K entries.  MODE 1: Lambda accumulation (K == 1).
+// MODE 2: ladder classifier (K == 2): mean/variance of the error count -> rung.
+// TMA: uniform-stride first pass; tiles arrive as swizzled 2-D tensor boxes (one UTMALDG per warp and
+// chunk) instead of cp.async pieces.
+template <int K, int MODE, bool EQP, bool TMA>
+__global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+    constexpr int TPR_WARPS = tpr_warps(K);
+    constexpr bool PL = (EQP && MODE == 0 && !(MOIRA_PAIR_LUT && K <= 8)) || MODE == 1;
+    extern __shared__ __align__(128) uint8_t smem[];
+    if (a.queue && (a.seg_count ? *a.seg_count : *a.queue_count) == 0) return;   // empty rung / segment: nothing to set up
+    const TprCtx ctx = tpr_setup<TPR_WARPS, MODE, PL, TMA>(a, smem);
+    const uint32_t *queue = a.queue && a.seg_start ? a.queue + *a.seg_start : a.queue;
+    const uint32_t count = a.queue ? (a.seg_count ? *a.seg_count : *a.queue_count) : a.n;
+    tpr_tiles<K, MODE, PL, TMA>(a, &tmap, ctx, queue, count, blockIdx.x * TPR_WARPS + ctx.warp, gridDim.x * TPR_WARPS);
     __syncthreads();
-    flush_counters(a, s_cnt, s_hist);
+    flush_counters(a, ctx.s_cnt, ctx.s_hist);
+}
+
+// All thread-per-read rungs of the escalation ladder in ONE launch: the CTA sets its table up once and
+// every warp walks its share of the tiles of rung 1, rung 2, ... with the K of each rung, so no warp
+// waits at a kernel boundary for the last wave of the previous rung.  Reads a rung cannot settle go
+// straight to the first warp-per-read rung.
+template <bool EQP>
+__global__ void __launch_bounds__(256, 1) ladder_tpr_kernel(const FilterArgs a0)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t counts[N_TPR_RUNGS + 1];
+    uint32_t any = 0;
+#pragma unroll
+    for (int r = 1; r <= N_TPR_RUNGS; r++) {
+        const uint32_t c = a0.queue_counts[r];
+        counts[r] = c < a0.queue_cap ? c : a0.queue_cap;
+        any |= counts[r];
+    }
+    if (!any) return;
+    const TprCtx ctx = tpr_setup<8, 0, EQP, false>(a0, smem);
+    FilterArgs a = a0;
+    a.rung = N_TPR_RUNGS;                      // escalations of this kernel land in rung N_TPR_RUNGS + 1
+    const uint32_t W = gridDim.x * 8, gw = blockIdx.x * 8 + ctx.warp;
+    uint32_t before = 0;                       // tiles of the rungs already walked: keeps the load balanced
+#define MOIRA_RUNG(r, k)                                                                                      \
+    if (counts[r]) {                                                                                          \
+        const uint32_t first = (gw + W - before % W) % W;                                                     \
+        tpr_tiles<k, 0, EQP, false>(a, nullptr, ctx, a0.queues + (size_t)(r) * a0.queue_cap, counts[r], first, W); \
+        before += (counts[r] + 31) >> 5;                                                                      \
+    }
+    MOIRA_RUNG(1, 8) MOIRA_RUNG(2, 10) MOIRA_RUNG(3, 12) MOIRA_RUNG(4, 14) MOIRA_RUNG(5, 16) MOIRA_RUNG(6, 18)
+    MOIRA_RUNG(7, 20) MOIRA_RUNG(8, 22) MOIRA_RUNG(9, 24) MOIRA_RUNG(10, 28) MOIRA_RUNG(11, 32) MOIRA_RUNG(12, 40)
+    MOIRA_RUNG(13, 48) MOIRA_RUNG(14, 64)
+#undef MOIRA_RUNG
+    __syncthreads();
+    flush_counters(a, ctx.s_cnt, ctx.s_hist);
 }
 
 // ==================================================================================================
@@ -1049,8 +1120,9 @@ int kernels_init(int)
 #define X(k) if (init_tpr<k, 0, false>() || init_tpr<k, 0, true>()) return -1;
     MOIRA_FOR_EACH_K(X)
 #undef X
-    if (init_tpr<40, 0, false>() || init_tpr<48, 0, false>() || init_tpr<64, 0, false>()) return -1;
     if (init_tpr<1, 1, false>() || init_tpr<1, 1, true>() || init_tpr<2, 2, false>()) return -1;
+    if (cudaFuncSetAttribute(ladder_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ladder_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM) != cudaSuccess) return -1;
     return 0;
 }
@@ -1098,6 +1170,13 @@ int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_byte
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+int launch_ladder_tpr(const FilterArgs &a, const LaunchCfg &cfg)
+{
+    if (a.e_equals_p) ladder_tpr_kernel<true><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a);
+    else ladder_tpr_kernel<false><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name)
 {
     if (name) *name = "lambda_tpr";
@@ -1115,25 +1194,12 @@ int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg0)
     const int wpr_grid = cfg.sm_count * 4;
     switch (b) {
     case 0: return launch_tpr<2, 2>(a, cfg);     // classifier
-    case 1: return launch_tpr<8, 0>(a, cfg);
-    case 2: return launch_tpr<10, 0>(a, cfg);
-    case 3: return launch_tpr<12, 0>(a, cfg);
-    case 4: return launch_tpr<14, 0>(a, cfg);
-    case 5: return launch_tpr<16, 0>(a, cfg);
-    case 6: return launch_tpr<18, 0>(a, cfg);
-    case 7: return launch_tpr<20, 0>(a, cfg);
-    case 8: return launch_tpr<22, 0>(a, cfg);
-    case 9: return launch_tpr<24, 0>(a, cfg);
-    case 10: return launch_tpr<28, 0>(a, cfg);
-    case 11: return launch_tpr<32, 0>(a, cfg);
-    case 12: return launch_tpr<40, 0>(a, cfg);
-    case 13: return launch_tpr<48, 0>(a, cfg);
-    case 14: return launch_tpr<64, 0>(a, cfg);
     case 15: wpr_kernel<4><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
     case 16: wpr_kernel<8><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
     case 17: wpr_kernel<16><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
     case 18: wpr_kernel<32><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    default: blk_kernel<<<cfg.sm_count, BLK_THREADS, BLK_SMEM, cfg.stream>>>(a); break;
+    case NB - 1: blk_kernel<<<cfg.sm_count, BLK_THREADS, BLK_SMEM, cfg.stream>>>(a); break;
+    default: return -1;   // rungs 1..N_TPR_RUNGS run fused, see launch_ladder_tpr
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
