@@ -356,15 +356,17 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             c->launches += 3;
             a.queue = lb.queue;
             a.min_rung = 1;
-            for (int g = 0; g < (single ? 1 : N_FIRST_K); g++) {
-                a.seg_start = lb.group_start + g;
-                a.seg_count = lb.group_count + g;
-                a.queue_count = lb.group_count + g;
-                rc = single ? launch_lambda(a, cfg, &name) : launch_pb_first_k(a, g, cfg, &name);
-                if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-                c->launches++;
+            if (single) {
+                a.seg_start = lb.group_start;
+                a.seg_count = lb.group_count;
+                a.queue_count = lb.group_count;
+                rc = launch_lambda(a, cfg, &name);
+            } else {
+                rc = launch_sorted_first(a, lb.group_start, lb.group_count, cfg);
+                name = "pb_tpr<K per length bucket>";
             }
-            if (!single) name = "pb_tpr<K per length bucket>";
+            if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            c->launches++;
             a.queue = nullptr; a.queue_count = nullptr; a.seg_start = nullptr; a.seg_count = nullptr;
         } else {
             rc = p->mode == MOIRA_MODE_PB ? launch_pb_first(a, k_first, cfg, &name) : launch_lambda(a, cfg, &name);

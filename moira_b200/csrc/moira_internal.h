@@ -100,6 +100,8 @@ struct LenSortBufs {
 };
 // enqueue histogram + scan + scatter; single_group: every read goes to group 0 (modes without a per-length K)
 int launch_length_sort(const FilterArgs &a, const LenSortBufs &b, int single_group, const LaunchCfg &cfg);
+// first pass over the length-sorted permutation, all K groups in one launch (PB mode)
+int launch_sorted_first(const FilterArgs &a, const uint32_t *seg_start, const uint32_t *seg_count, const LaunchCfg &cfg);
 int launch_pb_first_k(const FilterArgs &a, int k_index, const LaunchCfg &cfg, const char **name);
 // expand a 6-bit transport image into slab bytes [0, slab_bytes) (both device pointers, 16-byte aligned)
 int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_bytes, const LaunchCfg &cfg);

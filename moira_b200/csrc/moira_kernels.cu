@@ -710,6 +710,32 @@ __global__ void __launch_bounds__(256, 1) ladder_tpr_kernel(const FilterArgs a0)
     flush_counters(a, ctx.s_cnt, ctx.s_hist);
 }
 
+// First pass over a length-sorted permutation, every K template in ONE launch: segment g of the queue
+// (seg_start[g], seg_count[g]; written by len_scan_kernel) is swept with first_pass_k(g) entries.
+template <bool EQP>
+__global__ void __launch_bounds__(256, 1) sorted_first_kernel(const FilterArgs a, const uint32_t *seg_start, const uint32_t *seg_count)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const TprCtx ctx = tpr_setup<8, 0, EQP, false>(a, smem);
+    const uint32_t W = gridDim.x * 8, gw = blockIdx.x * 8 + ctx.warp;
+    uint32_t before = 0;
+#define MOIRA_GROUP(g, k)                                                                              \
+    {                                                                                                  \
+        const uint32_t cnt = seg_count[g];                                                             \
+        if (cnt) {                                                                                     \
+            const uint32_t first = (gw + W - before % W) % W;                                          \
+            tpr_tiles<k, 0, EQP, false>(a, nullptr, ctx, a.queue + seg_start[g], cnt, first, W);       \
+            before += (cnt + 31) >> 5;                                                                 \
+        }                                                                                              \
+    }
+    MOIRA_GROUP(0, 2) MOIRA_GROUP(1, 3) MOIRA_GROUP(2, 4) MOIRA_GROUP(3, 5) MOIRA_GROUP(4, 6) MOIRA_GROUP(5, 7)
+    MOIRA_GROUP(6, 8) MOIRA_GROUP(7, 10) MOIRA_GROUP(8, 12) MOIRA_GROUP(9, 14) MOIRA_GROUP(10, 16) MOIRA_GROUP(11, 18)
+    MOIRA_GROUP(12, 20) MOIRA_GROUP(13, 22) MOIRA_GROUP(14, 24) MOIRA_GROUP(15, 28) MOIRA_GROUP(16, 32)
+#undef MOIRA_GROUP
+    __syncthreads();
+    flush_counters(a, ctx.s_cnt, ctx.s_hist);
+}
+
 // ==================================================================================================
 // warp-per-read: K = 32*M entries, lane l owns P[l*M + m]
 // ==================================================================================================
@@ -1121,6 +1147,8 @@ int kernels_init(int)
     MOIRA_FOR_EACH_K(X)
 #undef X
     if (init_tpr<1, 1, false>() || init_tpr<1, 1, true>() || init_tpr<2, 2, false>()) return -1;
+    if (cudaFuncSetAttribute(sorted_first_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(sorted_first_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(ladder_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(ladder_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM) != cudaSuccess) return -1;
@@ -1167,6 +1195,13 @@ int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_byte
     const uint64_t want = (n48 + 255) / 256;
     const int grid = (int)std::min<uint64_t>(want, (uint64_t)cfg.sm_count * 16);
     unpack_q6_kernel<<<grid, 256, 0, cfg.stream>>>(reinterpret_cast<const uint32_t *>(d_image), reinterpret_cast<uint4 *>(d_slab), n48);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_sorted_first(const FilterArgs &a, const uint32_t *seg_start, const uint32_t *seg_count, const LaunchCfg &cfg)
+{
+    if (a.e_equals_p) sorted_first_kernel<true><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a, seg_start, seg_count);
+    else sorted_first_kernel<false><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a, seg_start, seg_count);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
