@@ -104,6 +104,9 @@ with open(os.path.join(out, "%s_pb_tpr4_ncu.md" % tag), "w") as fh:
     for op, c in cnt.most_common(16):
         fh.write("| %s | %.3f |\n" % (op, c / base_warps))
     fh.write("| **total** | %.3f |\n" % (sum(cnt.values()) / base_warps))
+    fh.write("\nDFMA: %.4f per base (%.1f per read and thread) -- all of it the IEEE division of the interpolation step\n"
+             "(`__ddiv_rn`, once per read, bernoullimodule.c:172); the PMF recurrence itself is DMUL/DADD only.\n"
+             % (cnt.get("DFMA", 0) / base_warps, cnt.get("DFMA", 0) / base_warps * 253))
 json.dump({"pb_tpr<K=4>": {"dram_bytes_per_read": traffic / reads, "source": "profiles/%s_pb_tpr4_ncu.md" % tag}},
           open(os.path.join(out, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out, "%s_pb_tpr4_ncu.md" % tag)).read())
