@@ -208,6 +208,17 @@ MOIRA_API int moira_parse_fastq(const char *text, uint64_t text_bytes, int fastq
                       uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off,
                       uint64_t *qual_off, uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out);
 
+/* Parse a FASTA text and its QUAL text (one header line + one data line per record in each file,
+ * moira.py:1093-1149) into a slab; same sizing convention as moira_parse_fastq (slab == NULL: returns
+ * n_reads and an upper bound of the slab bytes).  Headers are compared after normalisation
+ * (NameMismatchError); EmptySeqError / EmptyQualError / LengthMismatchError as in the reference.
+ * qual_slab (may be NULL, same capacity and offsets as slab) receives the plain qualities as
+ * process_data hands them on (Q <= 0 -> 1, moira.py:814), for writing .qual output. */
+MOIRA_API int moira_parse_fasta_qual(const char *fasta, uint64_t fasta_bytes, const char *qual, uint64_t qual_bytes,
+                                     int lower_n_ambiguous, uint8_t *slab, uint64_t slab_capacity, uint8_t *qual_slab,
+                                     uint64_t *out_offsets, uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len,
+                                     uint64_t *seq_off, uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out);
+
 /* Number of complete 4-line records in a FASTQ text buffer (to size the output arrays). */
 MOIRA_API int moira_fastq_count_reads(const char *text, uint64_t text_bytes, uint64_t *n_reads_out);
 

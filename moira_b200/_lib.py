@@ -33,7 +33,7 @@ EXPORTS = [
     "moira_ctx_destroy", "moira_ctx_sm_count", "moira_build_lut", "moira_ctx_get_lut",
     "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_filter_batch",
     "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads", "moira_pack_q6",
-    "moira_parse_fastq", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
+    "moira_parse_fastq", "moira_parse_fasta_qual", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
     "moira_ctx_last_kernel_ms",
 ]
 
@@ -87,6 +87,8 @@ lib.moira_pack_reads.argtypes = [_vp, _vp, _vp, _vp, _u64, _i, _vp, _u64, _vp, c
 lib.moira_pack_q6.argtypes = [_vp, _u64, _vp, _u64, _i]
 lib.moira_parse_fastq.argtypes = [_vp, _u64, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                   ctypes.POINTER(_u64), ctypes.POINTER(_u64)]
+lib.moira_parse_fasta_qual.argtypes = [_vp, _u64, _vp, _u64, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
+                                       ctypes.POINTER(_u64), ctypes.POINTER(_u64)]
 lib.moira_fastq_count_reads.argtypes = [_vp, _u64, ctypes.POINTER(_u64)]
 lib.moira_filter_fastq.argtypes = [_vp, _vp, _u64, _i, _i, _pp, _u64, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_u64)]
 lib.moira_collapse.argtypes = [_vp, _vp, _vp, _vp, _u64, _i, _vp, ctypes.POINTER(_u64), _vp, _vp, _vp, _vp, _vp]

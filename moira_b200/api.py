@@ -330,6 +330,31 @@ def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = T
     return slab, offsets, lengths, hdr_off, hdr_len, seq_off, qual_off
 
 
+def parse_fasta_qual(fasta: bytes, qual: bytes, lower_n_ambiguous: bool = True):
+    """FASTA + QUAL bytes -> (slab, qual_slab, offsets, lengths, hdr_off, hdr_len, seq_off) via
+    moira_parse_fasta_qual.  qual_slab holds the plain qualities (Q <= 0 -> 1) at the slab's offsets."""
+    fb = np.frombuffer(fasta, dtype=np.uint8)
+    qb = np.frombuffer(qual, dtype=np.uint8)
+    n = ctypes.c_uint64()
+    nb = ctypes.c_uint64()
+    L.check(lib.moira_parse_fasta_qual(_ptr(fb), fb.nbytes, _ptr(qb), qb.nbytes, int(lower_n_ambiguous), None, 0, None,
+                                       None, None, None, None, None, 0, ctypes.byref(n), ctypes.byref(nb)))
+    nr = n.value
+    cap = max(16, nb.value)
+    slab = np.empty(cap, np.uint8)
+    qslab = np.empty(cap, np.uint8)
+    offsets = np.empty(nr, np.uint64)
+    lengths = np.empty(nr, np.uint32)
+    hdr_off = np.empty(nr, np.uint64)
+    hdr_len = np.empty(nr, np.uint32)
+    seq_off = np.empty(nr, np.uint64)
+    L.check(lib.moira_parse_fasta_qual(_ptr(fb), fb.nbytes, _ptr(qb), qb.nbytes, int(lower_n_ambiguous), _ptr(slab), cap,
+                                       _ptr(qslab), _ptr(offsets), _ptr(lengths), _ptr(hdr_off), _ptr(hdr_len),
+                                       _ptr(seq_off), nr, ctypes.byref(n), ctypes.byref(nb)))
+    used = max(16, nb.value)
+    return slab[:used], qslab[:used], offsets, lengths, hdr_off, hdr_len, seq_off
+
+
 @dataclass
 class CollapseResult:
     group_of_read: np.ndarray   # uint64[n]
@@ -362,4 +387,4 @@ def collapse(text, seq_off, seq_len, ee, n_threads: int = 0) -> CollapseResult:
 
 
 __all__ = ["collapse", "CollapseResult","Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",
-           "pack_arrays", "pack_q6", "parse_fastq", "build_lut"]
+           "pack_arrays", "pack_q6", "parse_fastq", "parse_fasta_qual", "build_lut"]

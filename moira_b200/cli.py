@@ -24,7 +24,7 @@ import time
 import numpy as np
 
 from . import _lib as L
-from .api import Context, FilterParams, MoiraError, collapse, pack_reads, parse_fastq
+from .api import Context, FilterParams, MoiraError, collapse, pack_reads, parse_fasta_qual, parse_fastq
 
 __version__ = "0.1.0 (moira 1.3.2 compatible)"
 
@@ -208,36 +208,67 @@ def read_fastq_batches(fh, fastq_offset, lower_n_ambiguous, fname):
             break
 
 
-def read_fasta_qual_batches(ffh, qfh, lower_n_ambiguous, fasta_name, qual_name, batch_reads=200000):
-    """moira.py:1093-1149, single-end: sequences and qualities on one line each."""
+def _cut_lines(data: bytes, n_lines: int) -> int:
+    """Byte position just after the n_lines-th newline of data (len(data) if it has fewer)."""
+    idx = np.flatnonzero(np.frombuffer(data, dtype=np.uint8) == 10)
+    return int(idx[n_lines - 1]) + 1 if 0 < n_lines <= len(idx) else len(data)
+
+
+def read_fasta_qual_batches(ffh, qfh, lower_n_ambiguous, fasta_name, qual_name):
+    """moira.py:1093-1149, single-end: sequences and qualities on one line each.  Whole-record blocks of
+    both files go through the native parser (moira_parse_fasta_qual)."""
+    fcarry = qcarry = b""
     while True:
-        headers, seqs, quals = [], [], []
-        while len(headers) < batch_reads:
-            fh_line = ffh.readline()
-            qh_line = qfh.readline()
-            if not fh_line and not qh_line:
+        block = ffh.read(BATCH_BYTES)
+        fdata = fcarry + block
+        if block:
+            n_lines = fdata.count(b"\n")
+            keep = n_lines - (n_lines % 2)
+            if keep == 0:
+                fcarry = fdata
+                continue
+            pos = _cut_lines(fdata, keep)
+            ftext, fcarry = fdata[:pos], fdata[pos:]
+        else:
+            ftext, fcarry = fdata, b""
+            keep = ftext.count(b"\n") + (1 if ftext and not ftext.endswith(b"\n") else 0)
+            keep -= keep % 2
+        # the same number of lines from the qual file
+        while qcarry.count(b"\n") < keep:
+            qblock = qfh.read(BATCH_BYTES)
+            if not qblock:
                 break
-            fheader = _norm_header(fh_line.decode("latin-1"), ">")
-            seq = ffh.readline().decode("latin-1").strip()
-            qheader = _norm_header(qh_line.decode("latin-1"), ">")
-            qline = qfh.readline().decode("latin-1").strip().replace("\t", " ")
-            q = [int(x) for x in qline.split(" ")] if qline else []
-            if fheader != qheader:
-                raise NameMismatchError(fheader, qheader)
-            if not seq:
-                raise EmptySeqError(fheader, fasta_name)
-            if not q:
-                raise EmptyQualError(qheader, qual_name)
-            if len(seq) != len(q):
-                raise LengthMismatchError(fheader, fasta_name, qual_name)
-            headers.append(fheader)
-            seqs.append(seq)
-            quals.append(np.asarray([v if v > 0 else 1 for v in q], dtype=np.int32))
-        if not headers:
+            qcarry += qblock
+        if block:
+            qpos = _cut_lines(qcarry, keep)
+            qtext, qcarry = qcarry[:qpos], qcarry[qpos:]
+        else:
+            qtext, qcarry = qcarry + qfh.read(), b""
+            if len(qtext.split()) and not ftext.strip():
+                raise NameMismatchError("", _norm_header(qtext.decode("latin-1").splitlines()[0], ">"))
+        if not ftext.strip():
             break
-        slab, offsets, lengths = pack_reads(seqs, quals, lower_n_ambiguous)
+        try:
+            slab, qslab, offsets, lengths, hoff, hlen, soff = parse_fasta_qual(ftext, qtext, lower_n_ambiguous)
+        except MoiraError as exc:
+            if exc.code == L.ERR_PARSE:
+                name = exc.message.split(":")[0]
+                if name == "NameMismatchError":
+                    raise NameMismatchError(exc.message, "") from None
+                if name == "EmptySeqError":
+                    raise EmptySeqError(exc.message, fasta_name) from None
+                if name == "EmptyQualError":
+                    raise EmptyQualError(exc.message, qual_name) from None
+                if name == "LengthMismatchError":
+                    raise LengthMismatchError(exc.message, fasta_name, qual_name) from None
+                raise ValueError(exc.message) from None
+            raise
+        n = len(lengths)
+        headers = [ftext[int(hoff[i]):int(hoff[i]) + int(hlen[i])].decode("latin-1").replace(":", "_") for i in range(n)]
+        seqs = [ftext[int(soff[i]):int(soff[i]) + int(lengths[i])].decode("latin-1") for i in range(n)]
+        quals = [qslab[int(offsets[i]):int(offsets[i]) + int(lengths[i])].astype(np.int32) for i in range(n)]
         yield headers, seqs, quals, slab, offsets, lengths
-        if len(headers) < batch_reads:
+        if not block:
             break
 
 

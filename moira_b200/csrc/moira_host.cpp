@@ -421,3 +421,178 @@ int moira::parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_of
     *slab_bytes_out = used;   // end of the last row: what has to travel to the GPU
     return MOIRA_OK;
 }
+
+// ---- FASTA + QUAL ------------------------------------------------------------------------------------
+// Record semantics of parse_fasta_and_qual (moira/moira.py:1093-1149, single-end): both files hold one
+// header line and one data line per record ("Expects sequences and qualities to be stored in a single
+// line"); headers are compared after normalisation (strip, tab -> space, first token, lstrip('>'));
+// qualities are whitespace-separated integers.  Parallel over FASTA byte ranges; the matching position
+// in the QUAL text is found through per-range newline counts.
+namespace {
+
+struct TwoLineIndex {
+    std::vector<uint64_t> begin, nl_before;   // byte ranges and number of newlines before each range
+    uint64_t total_lines = 0;
+};
+
+TwoLineIndex index_lines(const char *text, uint64_t bytes, int T)
+{
+    TwoLineIndex ix;
+    ix.begin.resize(T + 1);
+    ix.nl_before.assign(T + 1, 0);
+    std::vector<uint64_t> cnt(T, 0);
+    for (int t = 0; t <= T; t++) ix.begin[t] = bytes * (uint64_t)t / T;
+    moira::parallel_run(T, T, [&](int t) {
+        uint64_t c = 0;
+        const char *p = text + ix.begin[t], *e = text + ix.begin[t + 1];
+        while (p < e) {
+            const char *nl = (const char *)memchr(p, '\n', e - p);
+            if (!nl) break;
+            c++;
+            p = nl + 1;
+        }
+        cnt[t] = c;
+    });
+    for (int t = 0; t < T; t++) ix.nl_before[t + 1] = ix.nl_before[t] + cnt[t];
+    ix.total_lines = ix.nl_before[T] + ((bytes && text[bytes - 1] != '\n') ? 1 : 0);
+    return ix;
+}
+
+// byte position where line `line` starts (bytes if there is no such line)
+uint64_t line_start(const char *text, uint64_t bytes, const TwoLineIndex &ix, uint64_t line)
+{
+    if (line == 0) return 0;
+    int u = 0;
+    const int T = (int)ix.begin.size() - 1;
+    while (u + 1 < T && ix.nl_before[u + 1] < line) u++;
+    uint64_t pos = ix.begin[u];
+    for (uint64_t k = line - ix.nl_before[u]; k > 0; k--) {
+        const char *nl = (const char *)memchr(text + pos, '\n', bytes - pos);
+        if (!nl) return bytes;
+        pos = (uint64_t)(nl - text) + 1;
+    }
+    return pos;
+}
+
+inline void next_line(const char *text, uint64_t bytes, uint64_t &cur, uint64_t &b, uint64_t &e)
+{
+    const char *nl = cur < bytes ? (const char *)memchr(text + cur, '\n', bytes - cur) : nullptr;
+    const uint64_t end = nl ? (uint64_t)(nl - text) : bytes;
+    b = cur < bytes ? cur : bytes;
+    e = end;
+    while (b < e && is_space((unsigned char)text[b])) b++;
+    while (e > b && is_space((unsigned char)text[e - 1])) e--;
+    cur = nl ? end + 1 : bytes;
+}
+
+inline void header_token(const char *text, uint64_t b, uint64_t e, uint64_t &hb, uint64_t &he)
+{
+    hb = b; he = b;
+    while (he < e && text[he] != ' ' && text[he] != '\t') he++;
+    while (hb < he && text[hb] == '>') hb++;
+}
+
+}  // namespace
+
+extern "C" int moira_parse_fasta_qual(const char *fasta, uint64_t fasta_bytes, const char *qual, uint64_t qual_bytes,
+                                      int lower_n_ambiguous, uint8_t *slab, uint64_t slab_capacity, uint8_t *qual_slab,
+                                      uint64_t *out_offsets, uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len,
+                                      uint64_t *seq_off, uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out)
+{
+    if (!fasta || !qual || !n_reads_out || !slab_bytes_out) return hfail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    int T = g_host_threads > 0 ? g_host_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 64) T = 64;
+    if (fasta_bytes < (1u << 20)) T = 1;
+    const TwoLineIndex fx = index_lines(fasta, fasta_bytes, T), qx = index_lines(qual, qual_bytes, T);
+    // trailing blank lines do not make records (the reference stops at the first empty header pair)
+    uint64_t f_lines = fx.total_lines, q_lines = qx.total_lines;
+    const uint64_t n = f_lines / 2;
+    if (q_lines / 2 < n) return hfail(MOIRA_ERR_PARSE, "NameMismatchError: the qual file has %llu records, the fasta file %llu",
+                                      (unsigned long long)(q_lines / 2), (unsigned long long)n);
+    // records [r0(t), r0(t+1)) per thread; slab slices sized from the FASTA bytes they cover
+    std::vector<uint64_t> r0(T + 1), fpos(T + 1), qpos(T + 1), sbase(T + 1, 0);
+    for (int t = 0; t <= T; t++) r0[t] = n * (uint64_t)t / T;
+    moira::parallel_run(T + 1, T, [&](int t) {
+        fpos[t] = t == T ? fasta_bytes : line_start(fasta, fasta_bytes, fx, 2 * r0[t]);
+        qpos[t] = t == T ? qual_bytes : line_start(qual, qual_bytes, qx, 2 * r0[t]);
+    });
+    for (int t = 0; t < T; t++)
+        sbase[t + 1] = sbase[t] + (((fpos[t + 1] - fpos[t]) + 16 * (r0[t + 1] - r0[t] + 1) + 15u) & ~15ull);
+    *n_reads_out = n;
+    *slab_bytes_out = sbase[T];
+    if (!slab) return MOIRA_OK;
+    if (n > max_reads) return hfail(MOIRA_ERR_BAD_ARG, "more than max_reads = %llu records", (unsigned long long)max_reads);
+    if (sbase[T] > slab_capacity) return hfail(MOIRA_ERR_BAD_ARG, "slab capacity too small (need %llu)", (unsigned long long)sbase[T]);
+    struct Err { int code = 0; uint64_t rec = 0; char msg[256] = ""; };
+    std::vector<Err> errs(T);
+    std::vector<uint64_t> used(T, 0);
+    moira::parallel_run(T, T, [&](int t) {
+        uint64_t fc = fpos[t], qc = qpos[t], pos = 0;
+        Err &er = errs[t];
+        for (uint64_t r = r0[t]; r < r0[t + 1]; r++) {
+            uint64_t hb, he, sb, se, qhb, qhe, qb, qe, a, b;
+            next_line(fasta, fasta_bytes, fc, a, b);
+            header_token(fasta, a, b, hb, he);
+            next_line(fasta, fasta_bytes, fc, sb, se);
+            next_line(qual, qual_bytes, qc, a, b);
+            header_token(qual, a, b, qhb, qhe);
+            next_line(qual, qual_bytes, qc, qb, qe);
+            const uint64_t slen = se - sb;
+            const char *what = nullptr;
+            if (he - hb != qhe - qhb || memcmp(fasta + hb, qual + qhb, he - hb) != 0) what = "NameMismatchError";
+            else if (slen == 0) what = "EmptySeqError";
+            else if (qe == qb) what = "EmptyQualError";
+            uint8_t *row = slab + sbase[t] + pos;
+            uint8_t *qrow = qual_slab ? qual_slab + sbase[t] + pos : nullptr;
+            uint64_t nq = 0;
+            bool bad_q = false;
+            if (!what) {
+                uint64_t p = qb;
+                while (p < qe) {                                   // map(int, line.split(' ')), moira.py:1124
+                    while (p < qe && is_space((unsigned char)qual[p])) p++;
+                    if (p >= qe) break;
+                    bool neg = false;
+                    if (qual[p] == '-' || qual[p] == '+') { neg = qual[p] == '-'; p++; }
+                    long v = 0;
+                    bool digits = false;
+                    while (p < qe && qual[p] >= '0' && qual[p] <= '9') { v = v < 100000 ? v * 10 + (qual[p] - '0') : v; p++; digits = true; }
+                    if (!digits || (p < qe && !is_space((unsigned char)qual[p]))) { what = "ValueError"; break; }
+                    if (neg) v = -v;
+                    if (nq < slen) {
+                        const char ch = fasta[sb + nq];
+                        const uint8_t qv = v <= 0 ? 0 : (v > 0xFC ? 0xFC : (uint8_t)v);
+                        if (qrow) qrow[nq] = v <= 0 ? 1 : (v > 255 ? 255 : (uint8_t)v);   // what process_data writes back (moira.py:814)
+                        if (ch == 'N') row[nq] = 0xFF;
+                        else if (ch == 'n' && lower_n_ambiguous) row[nq] = 0xFE;
+                        else { row[nq] = qv; bad_q |= v > 0xFC; }
+                    }
+                    nq++;
+                }
+                if (!what && nq != slen) what = "LengthMismatchError";
+            }
+            if (what || bad_q) {
+                er.code = what ? MOIRA_ERR_PARSE : MOIRA_ERR_BAD_QUALITY;
+                er.rec = r;
+                snprintf(er.msg, sizeof(er.msg), "%s: record %llu (%.*s): %llu bases, %llu qualities", what ? what : "quality outside 0..252",
+                         (unsigned long long)r, (int)(he - hb < 100 ? he - hb : 100), fasta + hb, (unsigned long long)slen, (unsigned long long)nq);
+                return;
+            }
+            const uint64_t padded = (slen + 15u) & ~15ull;
+            memset(row + slen, 0xFD, padded - slen);
+            if (qrow) memset(qrow + slen, 0, padded - slen);
+            if (out_offsets) out_offsets[r] = sbase[t] + pos;
+            if (lengths) lengths[r] = (uint32_t)slen;
+            if (hdr_off) hdr_off[r] = hb;
+            if (hdr_len) hdr_len[r] = (uint32_t)(he - hb);
+            if (seq_off) seq_off[r] = sb;
+            pos += padded;
+        }
+        used[t] = pos;
+    });
+    for (int t = 0; t < T; t++)
+        if (errs[t].code) return hfail(errs[t].code, "%s", errs[t].msg);
+    for (int t = T - 1; t >= 0; t--)
+        if (r0[t + 1] > r0[t]) { *slab_bytes_out = sbase[t] + used[t]; break; }
+    return MOIRA_OK;
+}

@@ -232,3 +232,67 @@ def test_q6_transport_image_roundtrip():
     with pytest.raises(moira_b200.MoiraError) as ei:
         moira_b200.pack_q6(bad)
     assert ei.value.code == L.ERR_BAD_QUALITY
+
+
+def _fasta_qual_text(records):
+    fa = "".join(">%s some description\n%s\n" % (h.replace("_", ":"), s) for h, s, _ in records)
+    qu = "".join(">%s\tother words\n%s\n" % (h.replace("_", ":"), " ".join(map(str, q))) for h, _, q in records)
+    return fa.encode(), qu.encode()
+
+
+def test_parse_fasta_qual_matches_oracle_parser(forward_records):
+    """moira_parse_fasta_qual against the oracle's restatement of moira.py:1093-1149 on the reference's own
+    test reads written as fasta + qual."""
+    fa, qu = _fasta_qual_text(forward_records)
+    recs = po.parse_fasta_qual_text(fa.decode(), qu.decode())
+    assert [(h, s, q) for h, s, q in recs] == [(h, s, q) for h, s, q in forward_records]
+    slab, qslab, off, ln, hoff, hlen, soff = moira_b200.parse_fasta_qual(fa, qu, True)
+    oslab, ooff, oln = po.pack_records([r[1] for r in recs], [[max(v, 0) for v in r[2]] for r in recs])
+    assert np.array_equal(off, ooff) and np.array_equal(ln, oln) and np.array_equal(slab, oslab[:slab.size])
+    for i in (0, 3, 500, 999):
+        assert fa[int(hoff[i]):int(hoff[i]) + int(hlen[i])].decode().replace(":", "_") == recs[i][0]
+        assert fa[int(soff[i]):int(soff[i]) + int(ln[i])].decode() == recs[i][1]
+        assert list(qslab[int(off[i]):int(off[i]) + int(ln[i])]) == [v if v > 0 else 1 for v in recs[i][2]]
+
+
+def test_parse_fasta_qual_errors_and_threads():
+    P = moira_b200.parse_fasta_qual
+    for fa, qu, word in ((b">a\nACGT\n", b">b\n1 2 3 4\n", "NameMismatchError"), (b">a\n\n", b">a\n1 2\n", "EmptySeqError"),
+                         (b">a\nAC\n", b">a\n\n", "EmptyQualError"), (b">a\nACG\n", b">a\n1 2\n", "LengthMismatchError"),
+                         (b">a\nACG\n", b">a\n1 x 3\n", "ValueError"), (b">a\nAC\n>b\nAC\n", b">a\n1 2\n", "NameMismatchError")):
+        with pytest.raises(moira_b200.MoiraError) as ei:
+            P(fa, qu)
+        assert ei.value.code == L.ERR_PARSE and word in ei.value.message, (fa, qu)
+    with pytest.raises(moira_b200.MoiraError) as ei:
+        P(b">a\nAC\n", b">a\n7 300\n")
+    assert ei.value.code == L.ERR_BAD_QUALITY
+    slab, qslab, off, ln, *_ = P(b">r1 d\n ANnT \n>r2\nC", b">r1\n 40\t0  -3 12\n>r2\n9\n\n")
+    assert list(ln) == [4, 1] and list(slab[:4]) == [40, 0xFF, 0xFE, 12] and slab[16] == 9 and list(qslab[:4]) == [40, 1, 1, 12]
+    assert list(P(b">r\nAn\n", b">r\n5 6\n", False)[0][:2]) == [5, 6]
+    # parallel path (>= 1 MB): identical rows for any thread count, and the first bad record is the one reported
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(5000):
+        n = int(rng.integers(1, 500))
+        recs.append(("r%d" % i, "".join(rng.choice(list("ACGTN"), size=n)), [int(v) for v in rng.integers(0, 94, size=n)]))
+    fa, qu = _fasta_qual_text(recs)
+    assert len(fa) > (1 << 20)
+    outs = []
+    for threads in (1, 5, 16):
+        L.lib.moira_set_host_threads(threads)
+        outs.append(P(fa, qu, True))
+    rows = lambda o, which: [o[which][int(a):int(a) + int(b)] for a, b in zip(o[2], o[3])]
+    for other in outs[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(outs[0][3:], other[3:]))
+        assert all(np.array_equal(x, y) for x, y in zip(rows(outs[0], 0), rows(other, 0)))
+        assert all(np.array_equal(x, y) for x, y in zip(rows(outs[0], 1), rows(other, 1)))
+    assert [list(r) for r in rows(outs[2], 1)[:50]] == [[max(v, 1) for v in q] for _, _, q in recs[:50]]
+    bad = list(recs)
+    bad[3210] = ("r3210", "ACGT", [1, 2, 3])
+    fa, qu = _fasta_qual_text(bad)
+    for threads in (1, 11):
+        L.lib.moira_set_host_threads(threads)
+        with pytest.raises(moira_b200.MoiraError) as ei:
+            P(fa, qu, True)
+        assert "record 3210" in ei.value.message and "LengthMismatchError" in ei.value.message
+    L.lib.moira_set_host_threads(0)
