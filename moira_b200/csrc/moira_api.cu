@@ -118,7 +118,7 @@ struct moira_ctx {
     int length_sort = 1;
     int timing = 0;
     int n_timed = 0;
-    cudaEvent_t t0[MAX_TIMED], t1[MAX_TIMED];
+    cudaEvent_t t0[MAX_TIMED] = {}, t1[MAX_TIMED] = {};
     const char *timed_name = "";
     // single-read scratch (pinned)
     uint8_t *one_slab = nullptr;
@@ -237,18 +237,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {   // looked up once (thread-safe static initialisation)
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            cudaGetLastError();
-    }
+            return reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -268,9 +265,8 @@ bool make_slab_tmap(CUtensorMap *tm, const uint8_t *d_rows, uint64_t stride, uin
 
 int first_pass_k_template(int k_wanted)
 {
-    static const int ks[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 20, 22, 24, 28, 32};
-    for (int k : ks) if (k_wanted <= k) return k;
-    return 32;
+    for (int i = 0; i < N_FIRST_K; i++) if (k_wanted <= first_pass_k(i)) return first_pass_k(i);
+    return first_pass_k(N_FIRST_K - 1);
 }
 
 // Enqueue the whole filter for reads [0, n) on `stream`.  max_len = longest read if known, else 0.
@@ -413,6 +409,8 @@ void moira_params_default(moira_params *p)
     p->ee_output = MOIRA_EE_RAW;
 }
 
+static int ctx_init(moira_ctx *c, int device, int sm_count);
+
 int moira_ctx_create(int device, moira_ctx **out)
 {
     if (!out) return fail(MOIRA_ERR_BAD_ARG, "out is NULL");
@@ -429,16 +427,20 @@ int moira_ctx_create(int device, moira_ctx **out)
     if (prop.major < 10) return fail(MOIRA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     moira_ctx *c = new (std::nothrow) moira_ctx();
     if (!c) return fail(MOIRA_ERR_NOMEM, "out of host memory");
+    const int rc = ctx_init(c, device, prop.multiProcessorCount);
+    if (rc) { moira_ctx_destroy(c); return rc; }   // g_err keeps the failing step's message
+    *out = c;
+    return MOIRA_OK;
+}
+
+static int ctx_init(moira_ctx *c, int device, int sm_count)
+{
     c->device = device;
-    c->sm_count = prop.multiProcessorCount;
+    c->sm_count = sm_count;
     build_tables(c->h_p, c->h_q, c->h_e, &c->e_equals_p);
     if (const char *e = getenv("MOIRA_B200_NO_LENSORT")) c->length_sort = (e[0] == '1') ? 0 : 1;   // diagnostics
     if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
-    if (kernels_init(c->sm_count)) {
-        int rc = fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
-        delete c;
-        return rc;
-    }
+    if (kernels_init(c->sm_count)) return fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaMalloc(&c->d_p, 256 * sizeof(double)));
     CU(cudaMalloc(&c->d_q, 256 * sizeof(double)));
     CU(cudaMalloc(&c->d_e, 256 * sizeof(double)));
@@ -451,7 +453,6 @@ int moira_ctx_create(int device, moira_ctx **out)
     for (int i = 0; i < MAX_TIMED; i++) { CU(cudaEventCreate(&c->t0[i])); CU(cudaEventCreate(&c->t1[i])); }
     for (auto &t : c->tickets)
         for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&t.done[i], cudaEventDisableTiming));
-    *out = c;
     return MOIRA_OK;
 }
 
@@ -473,12 +474,16 @@ int moira_ctx_destroy(moira_ctx *c)
         if (w.lqueue) cudaFree(w.lqueue);
         if (w.ltables) cudaFree(w.ltables);
     }
-    for (int i = 0; i < MAX_TIMED; i++) { cudaEventDestroy(c->t0[i]); cudaEventDestroy(c->t1[i]); }
+    for (int i = 0; i < MAX_TIMED; i++) {
+        if (c->t0[i]) cudaEventDestroy(c->t0[i]);
+        if (c->t1[i]) cudaEventDestroy(c->t1[i]);
+    }
     if (c->meta_ready) cudaEventDestroy(c->meta_ready);
     for (int i = 0; i < 2; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->one_slab) cudaFreeHost(c->one_slab);
     if (c->one_out) cudaFreeHost(c->one_out);
     cudaFree(c->d_p); cudaFree(c->d_q); cudaFree(c->d_e); cudaFree(c->d_sink);
+    cudaGetLastError();
     delete c;
     return MOIRA_OK;
 }
@@ -540,9 +545,27 @@ int moira_filter_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_o
                            d_ns, d_flags, d_counters, (cudaStream_t)stream);
 }
 
+static int submit_impl(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const uint64_t *offsets,
+                       const uint32_t *lengths, uint64_t n, const moira_params *params, double *ee_out, int32_t *ns_out,
+                       uint8_t *flags_out, uint64_t *counters_out, int *ticket_out);
+
 int moira_submit(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const uint64_t *offsets,
                  const uint32_t *lengths, uint64_t n, const moira_params *params, double *ee_out, int32_t *ns_out,
                  uint8_t *flags_out, uint64_t *counters_out, int *ticket_out)
+{
+    const int rc = submit_impl(c, slab, slab_bytes, offsets, lengths, n, params, ee_out, ns_out, flags_out, counters_out, ticket_out);
+    if (rc && c) {
+        // a failure part-way may have left copies and kernels of earlier chunks in flight: drain them, so
+        // that nothing writes into the caller's buffers after the error is returned (g_err is kept)
+        for (cudaStream_t s : c->streams) if (s) cudaStreamSynchronize(s);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int submit_impl(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const uint64_t *offsets,
+                       const uint32_t *lengths, uint64_t n, const moira_params *params, double *ee_out, int32_t *ns_out,
+                       uint8_t *flags_out, uint64_t *counters_out, int *ticket_out)
 {
     if (!c || !ticket_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
     *ticket_out = -1;

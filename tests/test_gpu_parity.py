@@ -365,3 +365,22 @@ def test_q6_transport_format_gives_identical_results(ctx):
             r6 = ctx.filter_batch(img, off, ln, FilterParams(exact_ee=exact, slab_format="q6"))
             assert np.array_equal(r8.ee, r6.ee) and np.array_equal(r8.ns, r6.ns) and np.array_equal(r8.flags, r6.flags)
             assert np.array_equal(r8.counters, r6.counters)
+
+
+@pytest.mark.gpu
+def test_submit_failing_midway_leaves_the_context_usable(ctx):
+    """A batch whose later chunk is malformed fails with BAD_ARG after earlier chunks were enqueued; the
+    streams are drained before the error returns and the next call gives the same results as ever."""
+    slab, off, ln = synth.generate("v4", 400000, 5)             # ~100 MB: several 32 MB chunks
+    p = FilterParams(exact_ee=False)
+    good = ctx.filter_batch(slab, off, ln, p)
+    bad_off = off.copy()
+    bad_off[-10] += 8                                           # not a multiple of 16, in the last chunk
+    out = moira_b200.FilterResult(np.empty(len(ln)), np.empty(len(ln), np.int32), np.empty(len(ln), np.uint8),
+                                  np.zeros(L.N_COUNTERS, np.uint64))
+    with pytest.raises(moira_b200.MoiraError) as ei:
+        ctx.submit(slab, bad_off, ln, p, out)
+    assert ei.value.code == L.ERR_BAD_ARG and "multiple of 16" in ei.value.message
+    for _ in range(L.MAX_INFLIGHT + 1):                         # no ticket leaked by the failed submission
+        again = ctx.filter_batch(slab, off, ln, p)
+        assert np.array_equal(again.flags, good.flags) and np.array_equal(again.counters, good.counters)
