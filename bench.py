@@ -53,6 +53,17 @@ def _time_reference(slab, off, ln, threads):
     return len(ln) / dt, dt, kind, threads
 
 
+def _pool_chunk(chunk):
+    """Pool worker: the reference module's per-read Python API over one chunk of (sequence, quality list) pairs."""
+    from oracle import py_oracle as po
+    ref = po.ref_module()
+    seqs, quals = chunk
+    return [ref.calculate_errors_PB(s_, q_, ALPHA) for s_, q_ in zip(seqs, quals)]
+
+
+_POOL = None   # forked in main() before CUDA is initialised (the workers only ever run _pool_chunk)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -396,8 +407,23 @@ def run_ours(args):
                     ref.calculate_errors_PB(s_, q_, ALPHA)
                 cpu["python_api_1core"] = {"value": k / (time.perf_counter() - t0), "unit": "reads/s",
                                            "sample": "%d reads through bernoulli.calculate_errors_PB(str, list, float), 1 core" % k}
+                # ... and as moira runs it on a multi-core host: multiprocessing.Pool, chunked map (moira.py:398-399, 431-438)
+                if _POOL is not None:
+                    per, rep = 2000, 8 * cores
+                    chunks = [(seqs[i:i + per], quals[i:i + per]) for i in range(0, k, per)] * (rep * per // k + 1)
+                    chunks = chunks[:rep]
+                    _POOL.map(_pool_chunk, chunks[:cores])                       # warm-up: module import in every worker
+                    t0 = time.perf_counter()
+                    got = _POOL.map(_pool_chunk, chunks, chunksize=1)
+                    dtp = time.perf_counter() - t0
+                    cpu["python_api_pool"] = {"value": sum(len(g) for g in got) / dtp, "unit": "reads/s", "cores": cores,
+                                              "sample": "%d reads in chunks of %d through multiprocessing.Pool(%d).map, reads pickled to the workers"
+                                                        % (rep * per, per, cores)}
         except Exception as exc:  # pragma: no cover
             cpu["python_api_1core"] = {"error": repr(exc)}
+        finally:
+            if _POOL is not None:
+                _POOL.terminate()
 
     if rank == 0:
         line = {
@@ -429,6 +455,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    global _POOL
+    if args.impl != "reference" and int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu:
+        try:
+            import multiprocessing as mp
+            from oracle import py_oracle as po
+            if po.have_ref():
+                _POOL = mp.get_context("fork").Pool(os.cpu_count() or 1)   # before any CUDA call: forking is safe here
+        except Exception:  # pragma: no cover
+            _POOL = None
     if args.impl == "reference":
         run_reference(args)
     else:

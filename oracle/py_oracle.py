@@ -383,3 +383,124 @@ def decide_batch(ee_raw, ns, lengths, has_N, *, thr_kind, thr, ambigs, round_fla
         reason = np.where(short, REASON_LENGTH, reason).astype(np.uint8)
         ok = ok & ~short
     return ok, reason, ee
+
+
+# --------------------------------------------------------------------------------------------
+# paired-end contig constructor: wrappers over oracle/contig_oracle.c and the
+# unmodified reference aligner oracle/_ref/nw_align.so
+# --------------------------------------------------------------------------------------------
+REF_NW_SO = os.path.join(_HERE, "_ref", "nw_align.so")
+CONSENSUS = {"best": 0, "sum": 1, "posterior": 2}
+_ref_nw = None
+_contig_ready = False
+
+
+def have_ref_nw() -> bool:
+    return os.path.exists(REF_NW_SO)
+
+
+def ref_nw_module():
+    """The unmodified reference aligner (moira/nw_align.pyx), cythonised by oracle/Makefile."""
+    global _ref_nw
+    if _ref_nw is None:
+        spec = importlib.util.spec_from_file_location("nw_align", REF_NW_SO)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _ref_nw = mod
+    return _ref_nw
+
+
+def _contig_lib():
+    global _contig_ready
+    lib = oracle_lib()
+    if not _contig_ready:
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        ip = ctypes.POINTER(ctypes.c_int)
+        lib.oracle_reverse_complement.restype = ctypes.c_int
+        lib.oracle_reverse_complement.argtypes = [ctypes.c_char_p, i32p, ctypes.c_int, ctypes.c_char_p, i32p]
+        lib.oracle_nw_align.restype = ctypes.c_int
+        lib.oracle_nw_align.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ip, ctypes.POINTER(ctypes.c_long)]
+        lib.oracle_make_contig.restype = ctypes.c_int
+        lib.oracle_make_contig.argtypes = [ctypes.c_char_p, i32p, ctypes.c_int, ctypes.c_char_p, i32p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_char_p, i32p, ip, ip, ip, ip]
+        lib.oracle_pair_to_contig.restype = ctypes.c_int
+        lib.oracle_pair_to_contig.argtypes = [ctypes.c_char_p, i32p, ctypes.c_int, ctypes.c_char_p, i32p, ctypes.c_int] + \
+            [ctypes.c_int] * 8 + [ctypes.c_char_p, i32p, ip, ip, ip, ip]
+        _contig_ready = True
+    return lib
+
+
+def _i32(values):
+    arr = (ctypes.c_int32 * max(1, len(values)))(*values)
+    return arr
+
+
+def reverse_complement(sequence, quals=None):
+    """moira.py:1207-1236: reverse complement of an IUPAC string, qualities reversed along."""
+    lib = _contig_lib()
+    n = len(sequence)
+    out = ctypes.create_string_buffer(n + 1)
+    qi = _i32(list(quals)) if quals else None
+    qo = (ctypes.c_int32 * max(1, n))()
+    if quals and len(quals) != n:
+        raise ValueError("LengthMismatchError")
+    rc = lib.oracle_reverse_complement(sequence.encode("latin-1"), qi, n, out, qo)
+    if rc:
+        raise ValueError('"%s" is not a recognizable IUPAC-coded base.' % sequence[rc - 1])
+    s = out.raw[:n].decode("latin-1")
+    return (s, list(qo[:n])) if quals else s
+
+
+def nw_align(seq_1, seq_2, match, mismatch, gap):
+    """nw_align.pyx:49-145 with refine_overlap=True -> (seq_1_aligned, seq_2_aligned, score)."""
+    lib = _contig_lib()
+    l1, l2 = len(seq_1), len(seq_2)
+    a1 = ctypes.create_string_buffer(l1 + l2 + 1)
+    a2 = ctypes.create_string_buffer(l1 + l2 + 1)
+    n = ctypes.c_int()
+    score = ctypes.c_long()
+    if lib.oracle_nw_align(seq_1.encode("latin-1"), l1, seq_2.encode("latin-1"), l2, match, mismatch, gap, a1, a2,
+                           ctypes.byref(n), ctypes.byref(score)):
+        raise MemoryError
+    return a1.raw[:n.value].decode("latin-1"), a2.raw[:n.value].decode("latin-1"), score.value
+
+
+def make_contig(forward_aligned, forward_quals, reverse_aligned, reverse_quals, insert, deltaq, consensus_qscore, qscore_cap,
+                trim_overlap):
+    """moira.py:1375-1558 -> (contig, contig_quals, overlap_length, gaps, mismatches)."""
+    lib = _contig_lib()
+    if consensus_qscore not in CONSENSUS:
+        raise ValueError('consensus_qscore must be "best", "sum" or "posterior".')
+    n = len(forward_aligned)
+    assert len(reverse_aligned) == n
+    contig = ctypes.create_string_buffer(n + 1)
+    cq = (ctypes.c_int32 * max(1, n))()
+    clen, ov, gaps, mism = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.oracle_make_contig(forward_aligned.encode("latin-1"), _i32(list(forward_quals)), len(forward_quals),
+                                reverse_aligned.encode("latin-1"), _i32(list(reverse_quals)), len(reverse_quals), n, int(insert),
+                                int(deltaq), CONSENSUS[consensus_qscore], int(qscore_cap), int(bool(trim_overlap)), contig, cq,
+                                ctypes.byref(clen), ctypes.byref(ov), ctypes.byref(gaps), ctypes.byref(mism))
+    if rc == -2:
+        raise ValueError("LengthMismatchError")
+    if rc:
+        raise ValueError("make_contig failed with code %d" % rc)
+    return contig.raw[:clen.value].decode("latin-1"), list(cq[:clen.value]), ov.value, gaps.value, mism.value
+
+
+def pair_to_contig(forward_sequence, forward_quals, reverse_sequence, reverse_quals, match=1, mismatch=-1, gap=-2, insert=20,
+                   deltaq=6, consensus_qscore="best", qscore_cap=40, trim_overlap=False):
+    """The paired branch of process_data (moira.py:791-803) for one pair of raw reads."""
+    lib = _contig_lib()
+    l1, l2 = len(forward_sequence), len(reverse_sequence)
+    contig = ctypes.create_string_buffer(l1 + l2 + 1)
+    cq = (ctypes.c_int32 * max(1, l1 + l2))()
+    clen, ov, gaps, mism = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.oracle_pair_to_contig(forward_sequence.encode("latin-1"), _i32(list(forward_quals)), l1,
+                                   reverse_sequence.encode("latin-1"), _i32(list(reverse_quals)), l2, match, mismatch, gap, insert,
+                                   deltaq, CONSENSUS[consensus_qscore], qscore_cap, int(bool(trim_overlap)), contig, cq,
+                                   ctypes.byref(clen), ctypes.byref(ov), ctypes.byref(gaps), ctypes.byref(mism))
+    if rc:
+        raise ValueError("pair_to_contig failed with code %d" % rc)
+    return contig.raw[:clen.value].decode("latin-1"), list(cq[:clen.value]), ov.value, gaps.value, mism.value

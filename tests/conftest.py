@@ -45,6 +45,34 @@ def forward_names():
 
 
 @pytest.fixture(scope="session")
+def reverse_records():
+    import bz2
+    from oracle import py_oracle as po
+    return po.parse_fastq_text(bz2.open(os.path.join(GOLDEN, "test2.fastq.bz2"), "rt").read())
+
+
+@pytest.fixture(scope="session")
+def paired_names():
+    return json.load(gzip.open(os.path.join(GOLDEN, "paired_names.json.gz"), "rt"))
+
+
+@pytest.fixture(scope="session")
+def ref_alignments():
+    return json.load(gzip.open(os.path.join(GOLDEN, "ref_alignments.json.gz"), "rt"))
+
+
+@pytest.fixture(scope="session")
+def oracle_contigs(forward_records, reverse_records):
+    """(header, contig, quals, overlap, gaps, mismatches) of the 1000 fixture pairs, by the oracle (default arguments)."""
+    from oracle import py_oracle as po
+    out = []
+    for (h, fs, fq), (h2, rs, rq) in zip(forward_records, reverse_records):
+        assert h == h2
+        out.append((h,) + po.pair_to_contig(fs, fq, rs, rq))
+    return out
+
+
+@pytest.fixture(scope="session")
 def contigs():
     return json.load(gzip.open(os.path.join(GOLDEN, "contigs.json.gz"), "rt"))
 

@@ -13,6 +13,11 @@ Outputs (all small, committed):
   forward_outputs.json.gz  golden fasta/qual records of the same test (header line -> [sequence, quality line])
   contigs.json.gz        the 400 golden paired contigs (fasta+qual) with good/bad labels
                          (moira/test/test_results/paired.qc.{good,bad}.{fasta,qual})
+  test2.fastq.bz2        the matching reverse reads (moira/test/test2.fastq.bz2), for the paired pipeline
+  paired_names.json.gz   golden .names partitions of the paired full-pipeline test
+                         (moira/test/test_results/paired.qc.{good,bad}.names)
+  ref_alignments.json.gz outputs of the UNMODIFIED reference aligner (oracle/_ref/nw_align.so, cythonised
+                         from moira/nw_align.pyx) on 240 seeded pairs, several scoring schemes
   ref_outputs.npz        outputs of the UNMODIFIED reference binary (oracle/_ref) on: the 1000
                          forward reads, the 400 contigs, and 4000 seeded synthetic reads covering
                          N/n, Q=0, L=1..600, several alphas -- as packed slabs + (ee, Ns)
@@ -68,6 +73,15 @@ def main():
         "paired_process": {"seq": par[1], "quals": list(par[2]), "ee": par[3],
                            "overlap": par[4], "gaps": par[5], "mismatches": par[6]},
     }
+    # contig constructor vectors (test_moira.py:49-59, 118-135) and the arguments they were made with
+    rc2 = grab("testRC2")
+    al = grab("test_aligned")
+    ct = grab("test_contig")
+    kat["contig_args"] = {"match": 1, "mismatch": -1, "gap": -2, "insert": 20, "deltaq": 6, "consensus_qscore": "best",
+                          "qscore_cap": 40, "trim_overlap": False}
+    kat["testRC2"] = [rc2[0], list(rc2[1])]
+    kat["test_aligned"] = [al[0], al[1], al[2]]
+    kat["test_contig"] = [ct[0], list(ct[1]), ct[2], ct[3], ct[4]]
     q1 = [ord(c) - 33 for c in q1s]
     assert ref.calculate_errors_PB(s1, q1, 0.005) == tuple(kat["pb_expected"])
     json.dump(kat, open(os.path.join(HERE, "kat.json"), "w"), indent=1)
@@ -82,6 +96,38 @@ def main():
             d[rep] = members.split(",")
         names[lab] = d
     _dump_gz("forward_names.json.gz", names)
+    shutil.copyfile(os.path.join(REF, "test", "test2.fastq.bz2"), os.path.join(HERE, "test2.fastq.bz2"))
+    names = {}
+    for lab in ("good", "bad"):
+        d = {}
+        for line in open(os.path.join(REF, "test", "test_results", "paired.qc.%s.names" % lab)):
+            rep, members = line.rstrip("\n").split("\t")
+            d[rep] = members.split(",")
+        names[lab] = d
+    _dump_gz("paired_names.json.gz", names)
+
+    # ---- the unmodified reference aligner on seeded pairs -------------------------------------
+    nw = po.ref_nw_module()
+    rng = np.random.Generator(np.random.PCG64(20160401))
+    schemes = [(1, -1, -2), (2, -3, -5), (1, -1, -1), (0, 0, 0), (5, -4, -10), (1, -2, 0)]
+    cases = []
+    for it in range(240):
+        l1, l2 = int(rng.integers(1, 140)), int(rng.integers(1, 140))
+        a = "".join(rng.choice(list("ACGT"), l1))
+        if it % 3:      # overlapping pair with a few substitutions / indels, like a read pair
+            k = int(rng.integers(0, l1))
+            b = list(a[k:] + "".join(rng.choice(list("ACGT"), l2)))
+            b = [c if rng.random() > 0.06 else "ACGTN"[int(rng.integers(5))] for c in b]
+            if rng.random() < 0.5 and len(b) > 4:
+                del b[int(rng.integers(len(b)))]
+            b = "".join(b)[:max(1, l2)]
+        else:
+            b = "".join(rng.choice(list("ACGTN"), l2))
+        m, x, g = schemes[it % len(schemes)]
+        a1, a2, score = nw.nw_align(a, b, m, x, g)
+        cases.append({"seq_1": a, "seq_2": b, "match": m, "mismatch": x, "gap": g, "aligned_1": a1, "aligned_2": a2,
+                      "score": int(score)})
+    _dump_gz("ref_alignments.json.gz", cases)
 
     # ---- golden forward output records (fasta + qual, keyed by header; order is Py2-dict dependent) ---
     fwd_out = {}

@@ -144,3 +144,80 @@ def test_property_restatements_agree_with_reference_binary():
         assert fast[1] == seq.count("N") + seq.count("n") and fast[0] >= 0.0
 
     check()
+
+
+# ---- paired-end contig constructor (oracle/contig_oracle.c) ------------------------------------------
+def _q2(kat):
+    return [ord(c) - kat["fastq_offset"] for c in kat["testQual2_ascii"]]
+
+
+def test_contig_constructor_kats(kat):
+    # moira/test/test_moira.py:49-59 -- testReverseComplement, testNwPython / testNwC, testContig
+    a = kat["contig_args"]
+    rc_seq, rc_q = po.reverse_complement(kat["testSeq2"], _q2(kat))
+    assert [rc_seq, rc_q] == kat["testRC2"]
+    al = po.nw_align(kat["testSeq1"], rc_seq, a["match"], a["mismatch"], a["gap"])
+    assert list(al) == kat["test_aligned"]
+    ct = po.make_contig(al[0], _q1(kat), al[1], rc_q, a["insert"], a["deltaq"], a["consensus_qscore"], a["qscore_cap"],
+                        a["trim_overlap"])
+    assert list(ct) == kat["test_contig"]
+    # process_data, paired (test_moira.py:67-70): contig -> truncate 200 -> PB
+    contig, quals, ov, gaps, mism = po.pair_to_contig(kat["testSeq1"], _q1(kat), kat["testSeq2"], _q2(kat))
+    pp = kat["paired_process"]
+    c200, q200, ee = po.process_filter(contig, quals, po.Args(truncate=200))
+    assert (c200, q200, ee, ov, gaps, mism) == (pp["seq"], pp["quals"], pp["ee"], pp["overlap"], pp["gaps"], pp["mismatches"])
+    with pytest.raises(ValueError):
+        po.reverse_complement("ACGX")
+
+
+def test_aligner_matches_reference_aligner_outputs(ref_alignments):
+    # committed outputs of the unmodified reference aligner (oracle/_ref/nw_align.so)
+    for c in ref_alignments:
+        got = po.nw_align(c["seq_1"], c["seq_2"], c["match"], c["mismatch"], c["gap"])
+        assert got == (c["aligned_1"], c["aligned_2"], c["score"])
+
+
+@pytest.mark.skipif(not po.have_ref_nw(), reason="oracle/_ref/nw_align.so not built (reference tree absent)")
+def test_aligner_matches_live_reference_aligner(kat):
+    nw = po.ref_nw_module()
+    rng = np.random.default_rng(99)
+    for it in range(150):
+        a = "".join(rng.choice(list("ACGTN"), int(rng.integers(1, 90))))
+        b = "".join(rng.choice(list("ACGTN"), int(rng.integers(1, 90))))
+        if it % 2:
+            b = a[int(rng.integers(0, len(a))):] + b
+        m, x, g = [(1, -1, -2), (3, -2, -4), (1, 0, -1)][it % 3]
+        assert po.nw_align(a, b, m, x, g) == tuple(nw.nw_align(a, b, m, x, g))
+    rc = po.reverse_complement(kat["testSeq2"])
+    assert list(nw.nw_align(kat["testSeq1"], rc, 1, -1, -2)) == kat["test_aligned"]
+
+
+def test_paired_pipeline_contigs_and_partition(oracle_contigs, contigs, paired_names):
+    # moira/test/test_moira.py:88-101: test1 + test2 -> 1000 contigs -> collapse -> golden fasta / qual / names
+    by_header = {h: (c, q) for h, c, q, _, _, _ in oracle_contigs}
+    for g in contigs:                                   # every golden representative is its pair's contig
+        c, q = by_header[g["header"]]
+        assert c == g["seq"] and [v if v > 0 else 1 for v in q] == g["quals"]
+    good, bad = po.collapse_and_decide([(h, c, q) for h, c, q, _, _, _ in oracle_contigs], po.Args())
+    assert {k: v[0] for k, v in good.items()} == paired_names["good"]
+    assert {k: v[0] for k, v in bad.items()} == paired_names["bad"]
+
+
+def test_make_contig_modes_and_validation():
+    fa, ra = "ACGTAC--", "--GTTCGA"
+    fq, rq = [30, 30, 30, 10, 12, 12], [20, 20, 14, 40, 25, 25]
+    best = po.make_contig(fa, fq, ra, rq, 20, 6, "best", 40, False)
+    assert best == ("ACGTNCGA", [30, 30, 30, 20, 2, 40, 25, 25], 3, 0, 1)          # |12-14| < 6 -> N, Q 2
+    assert po.make_contig(fa, fq, ra, rq, 20, 6, "sum", 0, False)[1] == [30, 30, 50, 30, 2, 52, 25, 25]
+    assert po.make_contig(fa, fq, ra, rq, 20, 6, "sum", 40, True) == ("GTNC", [40, 30, 2, 40], 3, 0, 1)
+    post = po.make_contig(fa, fq, ra, rq, 20, 6, "posterior", 0, False)
+    assert post[0] == "ACGTTCGA" and post[1][2] == 54 and post[1][4] == 4           # Edgar & Flyvbjerg posteriors
+    gap = po.make_contig("ACG-TT", [30, 30, 30, 30, 30], "ACGATT", [30, 30, 30, 21, 30, 30], 20, 6, "best", 40, False)
+    assert gap == ("ACGATT", [30, 30, 30, 21, 30, 30], 5, 1, 0)                     # inserted: 21 > insert
+    gap = po.make_contig("ACG-TT", [30, 30, 30, 30, 30], "ACGATT", [30, 30, 30, 20, 30, 30], 20, 6, "best", 40, False)
+    assert gap[0] == "ACGTT" and gap[3] == 1                                         # 20 is not > insert: dropped
+    assert po.make_contig("ACG-TT", [30] * 5, "ACGATT", [30] * 6, 20, 6, "posterior", 40, False)[0] == "ACGNTT"
+    with pytest.raises(ValueError):
+        po.make_contig("ACG", [30, 30], "ACG", [30, 30, 30], 20, 6, "best", 40, False)
+    with pytest.raises(ValueError):
+        po.make_contig("ACG", [30] * 3, "ACG", [30] * 3, 0, 6, "best", 40, False)
