@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MOIRA_ABI_VERSION 2
+#define MOIRA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MOIRA_API __attribute__((visibility("default")))
@@ -212,8 +212,8 @@ MOIRA_API int moira_parse_fastq(const char *text, uint64_t text_bytes, int fastq
  * moira.py:1093-1149) into a slab; same sizing convention as moira_parse_fastq (slab == NULL: returns
  * n_reads and an upper bound of the slab bytes).  Headers are compared after normalisation
  * (NameMismatchError); EmptySeqError / EmptyQualError / LengthMismatchError as in the reference.
- * qual_slab (may be NULL, same capacity and offsets as slab) receives the plain qualities as
- * process_data hands them on (Q <= 0 -> 1, moira.py:814), for writing .qual output. */
+ * qual_slab (may be NULL, same capacity and offsets as slab) receives the plain qualities (negative
+ * values as 0), for the contig constructor and for writing .qual output. */
 MOIRA_API int moira_parse_fasta_qual(const char *fasta, uint64_t fasta_bytes, const char *qual, uint64_t qual_bytes,
                                      int lower_n_ambiguous, uint8_t *slab, uint64_t slab_capacity, uint8_t *qual_slab,
                                      uint64_t *out_offsets, uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len,
@@ -246,6 +246,71 @@ MOIRA_API int moira_collapse(const char *text, const uint64_t *seq_off, const ui
                              uint64_t n, int n_threads, uint64_t *group_of_read, uint64_t *n_groups_out,
                              uint64_t *group_rep, uint64_t *group_size, uint64_t *member_start, uint64_t *members,
                              uint64_t *abundance_order);
+
+/* ---- paired-end contig construction ------------------------------------------
+ * The producer of the contigs the filter runs on when --paired is given (process_data, moira.py:791-803):
+ * reverse_complement (moira.py:1207-1236) -> nw_align with mothur's overlap refinement
+ * (nw_align.pyx:49-202) -> make_contig (moira.py:1375-1558), one warp per pair on the device. */
+#define MOIRA_CONSENSUS_BEST 0        /* --consensus_qscore best (default, moira.py:642) */
+#define MOIRA_CONSENSUS_SUM 1
+#define MOIRA_CONSENSUS_POSTERIOR 2
+/* per-pair status */
+#define MOIRA_PAIR_OK 0
+#define MOIRA_PAIR_EMPTY 1            /* a read of length 0 */
+#define MOIRA_PAIR_BAD_BASE 2         /* reverse read holds a character outside the IUPAC table (ValueError, moira.py:1229) */
+#define MOIRA_PAIR_BAD_QUALITY 3      /* a consensus quality outside 0..252 (only 'sum' without a cap can get there) */
+#define MOIRA_PAIR_TOO_LONG 4         /* reverse read longer than 1024 bases, or longer than the batch maximum given */
+
+typedef struct moira_contig_params {
+    int32_t match;          /* --match      1  (moira.py:630) */
+    int32_t mismatch;       /* --mismatch  -1  (moira.py:632) */
+    int32_t gap;            /* --gap       -2  (moira.py:634) */
+    int32_t insert;         /* --insert    20  (moira.py:638) */
+    int32_t deltaq;         /* --deltaq     6  (moira.py:640) */
+    int32_t consensus;      /* MOIRA_CONSENSUS_* */
+    int32_t qscore_cap;     /* --qscore_cap 40, 0 = no cap (moira.py:645) */
+    int32_t trim_overlap;   /* --trim_overlap */
+} moira_contig_params;
+MOIRA_API void moira_contig_params_default(moira_contig_params *p);
+
+/* Contigs of n_pairs read pairs, and -- when filter_params is not NULL -- the quality filter on them, all on
+ * the device: the contig kernel writes the filter's slab, the filter kernels read it in place.
+ * Inputs (host): bases (ASCII) and qualities of the forward and of the reverse reads as given in the files
+ * (the reverse read is reverse-complemented on the device); read r of either file has its bases at
+ * [off[r], off[r] + len[r]) of the base array and its qualities at [qual_off[r], ...) of the quality array
+ * (qual_off == NULL: same offsets); a quality is byte - qual_base and must land in 0..252.  With the arrays
+ * moira_parse_fastq returns, the FASTQ text itself is both arrays (off = seq_off, qual_off = qual_off,
+ * qual_base = the FASTQ offset): nothing is repacked on the host.  *_bytes are the sizes of the arrays.
+ * Outputs (host), row r at r * out_stride, out_stride >= max(fwd_len) + max(rev_len), multiple of 16:
+ *   contig_seq / contig_qual   bases and consensus qualities as make_contig returns them (0..252; 253..255 stand for
+ *                              -3..-1: the posterior formulas give -1 when one of the two bases has quality 0)
+ *   contig_len, overlap, gaps, mismatches, status[r] (MOIRA_PAIR_*; pairs that fail give an empty contig)
+ *   ee / ns / flags / counters  as moira_filter_batch, for the contigs (ignored when filter_params is NULL;
+ *                               filter_params->truncate applies to the contig as in moira.py:806-807). */
+MOIRA_API int moira_filter_pairs(moira_ctx *ctx, const char *fwd_seq, uint64_t fwd_seq_bytes, const uint8_t *fwd_qual,
+                                 uint64_t fwd_qual_bytes, const uint64_t *fwd_off, const uint64_t *fwd_qual_off,
+                                 const uint32_t *fwd_len, const char *rev_seq, uint64_t rev_seq_bytes,
+                                 const uint8_t *rev_qual, uint64_t rev_qual_bytes, const uint64_t *rev_off,
+                                 const uint64_t *rev_qual_off, const uint32_t *rev_len,
+                                 int qual_base, uint64_t n_pairs, const moira_contig_params *contig_params,
+                                 int lower_n_ambiguous, const moira_params *filter_params, uint64_t out_stride,
+                                 char *contig_seq, uint8_t *contig_qual, uint32_t *contig_len, int32_t *overlap,
+                                 int32_t *gaps, int32_t *mismatches, uint8_t *status, double *ee_out, int32_t *ns_out,
+                                 uint8_t *flags_out, uint64_t *counters_out);
+
+/* Drop-in for ONE call of nw_align.nw_align(seq_1, seq_2, match, mismatch, gap) (nw_align.pyx:49, refine_overlap
+ * = True): aligned strings (NUL-terminated, capacity len_1 + len_2 + 1 each) and the reference's score (sum of the
+ * matrix cells on the traceback path, nw_align.pyx:127). */
+MOIRA_API int moira_nw_align(moira_ctx *ctx, const char *seq_1, const char *seq_2, int match, int mismatch, int gap,
+                             char *aligned_1, char *aligned_2, uint64_t *aligned_len, int64_t *score);
+
+/* Drop-in for ONE call of make_contig (moira.py:1375): aligned strings + unaligned qualities in; contig
+ * (capacity strlen(aligned) + 1), qualities, overlap length, gaps, mismatches out.  MOIRA_ERR_LENGTH_MISMATCH /
+ * MOIRA_ERR_BAD_ARG mirror LengthMismatchError / ValueError (moira.py:1405-1416). */
+MOIRA_API int moira_make_contig(moira_ctx *ctx, const char *fwd_aligned, const int32_t *fwd_quals, uint64_t n_fwd_quals,
+                                const char *rev_aligned, const int32_t *rev_quals, uint64_t n_rev_quals,
+                                const moira_contig_params *params, char *contig, int32_t *contig_quals,
+                                uint64_t *contig_len, int32_t *overlap, int32_t *gaps, int32_t *mismatches);
 
 /* Host threads used by moira_parse_fastq (0 = one per hardware thread, at most 64). */
 MOIRA_API int moira_set_host_threads(int n);

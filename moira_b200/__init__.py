@@ -1,6 +1,7 @@
 """moira_b200 -- B200-native (sm_100a CUDA) implementation of moira's per-read quality-filter
 hot path, behind the reference's own interfaces.  See DESIGN.md and include/moira_b200.h."""
-from .api import (CollapseResult, collapse, Context, FilterParams, FilterResult, MoiraError, PinnedBuffer, build_lut,  # noqa: F401
-                  pack_arrays, pack_q6, pack_reads, parse_fasta_qual, parse_fastq)
+from .api import (CollapseResult, collapse, ContigParams, Context, FilterParams, FilterResult, MoiraError, PairResult,  # noqa: F401
+                  PinnedBuffer, build_lut,
+                  pack_arrays, pack_q6, pack_reads, pack_sequences, parse_fasta_qual, parse_fastq)
 
 __version__ = "0.1.0"

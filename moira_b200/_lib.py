@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOIRA_B200_LIB") or os.path.join(_HERE, "libmoira_b200.so")   # env override: tuning experiments only
 
 # ---- constants mirrored from include/moira_b200.h -------------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK = 0
 ERR_BAD_ALPHA, ERR_LENGTH_MISMATCH, ERR_BAD_QUALITY, ERR_CUDA = -1, -2, -3, -4
 ERR_BAD_ARG, ERR_NOMEM, ERR_UNRESOLVED, ERR_PARSE = -5, -6, -7, -8
@@ -27,6 +27,8 @@ REASON_NONE, REASON_ERRORS, REASON_LENGTH, REASON_AMBIGS = 0, 1, 2, 3
 CNT_READS, CNT_ACCEPTED, CNT_BAD_ERRORS, CNT_BAD_LENGTH, CNT_BAD_AMBIGS = 0, 1, 2, 3, 4
 CNT_NEAR_CUTOFF, CNT_LOWER_BOUND, CNT_NUMERIC, CNT_HIST, N_HIST, N_COUNTERS = 5, 6, 7, 16, 64, 80
 MAX_INFLIGHT = 4
+CONSENSUS_BEST, CONSENSUS_SUM, CONSENSUS_POSTERIOR = 0, 1, 2
+PAIR_OK, PAIR_EMPTY, PAIR_BAD_BASE, PAIR_BAD_QUALITY, PAIR_TOO_LONG = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "moira_abi_version", "moira_last_error", "moira_params_default", "moira_ctx_create",
@@ -34,7 +36,7 @@ EXPORTS = [
     "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_filter_batch",
     "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads", "moira_pack_q6",
     "moira_parse_fastq", "moira_parse_fasta_qual", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
-    "moira_ctx_last_kernel_ms",
+    "moira_ctx_last_kernel_ms", "moira_contig_params_default", "moira_filter_pairs", "moira_nw_align", "moira_make_contig",
 ]
 
 
@@ -47,6 +49,12 @@ class Params(ctypes.Structure):
         ("slab_format", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("alpha", ctypes.c_double), ("thr", ctypes.c_double),
     ]
+
+
+class ContigParams(ctypes.Structure):
+    """struct moira_contig_params."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("match", "mismatch", "gap", "insert", "deltaq", "consensus", "qscore_cap",
+                                              "trim_overlap")]
 
 
 class MoiraError(RuntimeError):
@@ -97,8 +105,18 @@ lib.moira_fp64_peak.argtypes = [_vp, _i, ctypes.POINTER(_dbl), ctypes.POINTER(_d
 lib.moira_ctx_launch_count.argtypes = [_vp, ctypes.POINTER(_u64)]
 lib.moira_ctx_set_timing.argtypes = [_vp, _i]
 lib.moira_ctx_last_kernel_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p)]
+_cpp = ctypes.POINTER(ContigParams)
+lib.moira_contig_params_default.restype = None
+lib.moira_contig_params_default.argtypes = [_cpp]
+lib.moira_filter_pairs.argtypes = [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _i, _u64, _cpp, _i, _pp, _u64,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.moira_nw_align.argtypes = [_vp, ctypes.c_char_p, ctypes.c_char_p, _i, _i, _i, ctypes.c_char_p, ctypes.c_char_p,
+                               ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_int64)]
+lib.moira_make_contig.argtypes = [_vp, ctypes.c_char_p, _vp, _u64, ctypes.c_char_p, _vp, _u64, _cpp, ctypes.c_char_p, _vp,
+                                  ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                  ctypes.POINTER(ctypes.c_int32)]
 for _name in EXPORTS:
-    if _name not in ("moira_last_error", "moira_params_default"):
+    if _name not in ("moira_last_error", "moira_params_default", "moira_contig_params_default"):
         getattr(lib, _name).restype = _i
 
 if lib.moira_abi_version() != ABI_VERSION:

@@ -59,6 +59,51 @@ class FilterParams:
         return self.error_calc == "poisson_binomial"
 
 
+_CONSENSUS = {"best": L.CONSENSUS_BEST, "sum": L.CONSENSUS_SUM, "posterior": L.CONSENSUS_POSTERIOR}
+
+
+@dataclass
+class ContigParams:
+    """Contig construction options, with the reference's names and defaults (moira.py:629-646)."""
+    match: int = 1
+    mismatch: int = -1
+    gap: int = -2
+    insert: int = 20
+    deltaq: int = 6
+    consensus_qscore: str = "best"
+    qscore_cap: int = 40
+    trim_overlap: bool = False
+
+    def to_c(self) -> L.ContigParams:
+        if self.consensus_qscore not in _CONSENSUS:
+            raise ValueError('consensus_qscore must be "best", "sum" or "posterior".')          # moira.py:1405-1406
+        p = L.ContigParams()
+        p.match, p.mismatch, p.gap = int(self.match), int(self.mismatch), int(self.gap)
+        p.insert, p.deltaq = int(self.insert), int(self.deltaq)
+        p.consensus = _CONSENSUS[self.consensus_qscore]
+        p.qscore_cap = int(self.qscore_cap)
+        p.trim_overlap = 1 if self.trim_overlap else 0
+        return p
+
+
+@dataclass
+class PairResult:
+    """Contigs of a batch of read pairs (row r of contig_seq / contig_qual holds contig_len[r] entries)."""
+    contig_seq: np.ndarray     # uint8[n, out_stride], ASCII
+    contig_qual: np.ndarray    # uint8[n, out_stride]
+    contig_len: np.ndarray     # uint32[n]
+    overlap: np.ndarray        # int32[n]
+    gaps: np.ndarray
+    mismatches: np.ndarray
+    status: np.ndarray         # uint8[n], L.PAIR_*
+    filter: "FilterResult | None" = None
+
+    def contig(self, r: int):
+        n = int(self.contig_len[r])
+        q = self.contig_qual[r, :n].astype(np.int32)
+        return self.contig_seq[r, :n].tobytes().decode("latin-1"), np.where(q > 0xFC, q - 256, q).tolist()
+
+
 @dataclass
 class FilterResult:
     ee: np.ndarray        # float64[n]
@@ -234,6 +279,69 @@ class Context:
                                        _ptr(out.counters), ctypes.byref(n)))
         return out, lengths
 
+    def filter_pairs(self, fwd_seq, fwd_qual, fwd_off, fwd_len, rev_seq, rev_qual, rev_off, rev_len,
+                     contig_params: ContigParams, filter_params: FilterParams | None = None,
+                     lower_n_ambiguous: bool = True, fwd_qual_off=None, rev_qual_off=None, qual_base: int = 0) -> PairResult:
+        """Read pairs -> contigs (and, with filter_params, the filter on them) in one C call (moira_filter_pairs).
+        *_seq: uint8 ASCII bases at [off[r], off[r] + len[r]); *_qual: uint8 qualities (+ qual_base) at
+        [qual_off[r], ...) (qual_off None: same offsets).  Passing the FASTQ text as both arrays with the parser's
+        seq_off / qual_off and qual_base = the FASTQ offset avoids any repacking."""
+        fwd_seq, fwd_qual = _as(fwd_seq, np.uint8), _as(fwd_qual, np.uint8)
+        rev_seq, rev_qual = _as(rev_seq, np.uint8), _as(rev_qual, np.uint8)
+        fwd_off, rev_off = _as(fwd_off, np.uint64), _as(rev_off, np.uint64)
+        fwd_len, rev_len = _as(fwd_len, np.uint32), _as(rev_len, np.uint32)
+        fwd_qual_off = None if fwd_qual_off is None else _as(fwd_qual_off, np.uint64)
+        rev_qual_off = None if rev_qual_off is None else _as(rev_qual_off, np.uint64)
+        n = int(fwd_len.shape[0])
+        if not (rev_len.shape[0] == fwd_off.shape[0] == rev_off.shape[0] == n):
+            raise ValueError("offset / length arrays of the two files differ in size")
+        mx = (int(fwd_len.max()) if n else 0) + (min(int(rev_len.max()), 1024) if n else 0)
+        stride = max(16, (mx + 15) // 16 * 16)
+        res = PairResult(np.zeros((n, stride), np.uint8), np.zeros((n, stride), np.uint8), np.zeros(n, np.uint32),
+                         np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8))
+        cp = contig_params.to_c()
+        fr = None
+        fp = None
+        if filter_params is not None:
+            fp = filter_params.to_c()
+            fr = FilterResult(np.zeros(n, np.float64), np.zeros(n, np.int32), np.zeros(n, np.uint8),
+                              np.zeros(L.N_COUNTERS, np.uint64))
+            res.filter = fr
+        L.check(lib.moira_filter_pairs(
+            self._h, _ptr(fwd_seq), fwd_seq.nbytes, _ptr(fwd_qual), fwd_qual.nbytes, _ptr(fwd_off), _ptr(fwd_qual_off),
+            _ptr(fwd_len), _ptr(rev_seq), rev_seq.nbytes, _ptr(rev_qual), rev_qual.nbytes, _ptr(rev_off), _ptr(rev_qual_off),
+            _ptr(rev_len), int(qual_base), n, ctypes.byref(cp), int(lower_n_ambiguous),
+            ctypes.byref(fp) if fp is not None else None, stride, _ptr(res.contig_seq), _ptr(res.contig_qual),
+            _ptr(res.contig_len), _ptr(res.overlap), _ptr(res.gaps), _ptr(res.mismatches), _ptr(res.status),
+            _ptr(fr.ee) if fr else None, _ptr(fr.ns) if fr else None, _ptr(fr.flags) if fr else None,
+            _ptr(fr.counters) if fr else None))
+        return res
+
+    def nw_align(self, seq_1: str, seq_2: str, match: int, mismatch: int, gap: int):
+        """One alignment through the CUDA path (moira_nw_align) -> (seq_1_aligned, seq_2_aligned, score)."""
+        cap = len(seq_1) + len(seq_2) + 1
+        a1, a2 = ctypes.create_string_buffer(cap), ctypes.create_string_buffer(cap)
+        n, score = ctypes.c_uint64(), ctypes.c_int64()
+        L.check(lib.moira_nw_align(self._h, seq_1.encode("latin-1"), seq_2.encode("latin-1"), int(match), int(mismatch), int(gap),
+                                   a1, a2, ctypes.byref(n), ctypes.byref(score)))
+        return a1.raw[:n.value].decode("latin-1"), a2.raw[:n.value].decode("latin-1"), score.value
+
+    def make_contig(self, forward_aligned: str, forward_quals, reverse_aligned: str, reverse_quals, params: ContigParams):
+        """One consensus through the CUDA path (moira_make_contig) -> (contig, quals, overlap_length, gaps, mismatches)."""
+        fq = np.ascontiguousarray(forward_quals, dtype=np.int32)
+        rq = np.ascontiguousarray(reverse_quals, dtype=np.int32)
+        cap = len(forward_aligned) + 1
+        contig = ctypes.create_string_buffer(cap)
+        cq = np.zeros(cap, np.int32)
+        n = ctypes.c_uint64()
+        ov, gp, mm = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        cp = params.to_c()
+        L.check(lib.moira_make_contig(self._h, forward_aligned.encode("latin-1"), _ptr(fq) if fq.size else None, int(fq.size),
+                                      reverse_aligned.encode("latin-1"), _ptr(rq) if rq.size else None, int(rq.size),
+                                      ctypes.byref(cp), contig, _ptr(cq), ctypes.byref(n), ctypes.byref(ov), ctypes.byref(gp),
+                                      ctypes.byref(mm)))
+        return contig.raw[:n.value].decode("latin-1"), cq[:n.value].tolist(), ov.value, gp.value, mm.value
+
     def calculate_errors_PB(self, contig: str, contig_quals, alpha: float):
         """One read through the CUDA path (moira_calculate_errors_PB)."""
         q = np.ascontiguousarray(contig_quals, dtype=np.int32)
@@ -243,6 +351,23 @@ class Context:
                                            int(q.shape[0]), float(alpha), ctypes.byref(ee), ctypes.byref(ns))
         L.check(rc)
         return ee.value, ns.value
+
+
+def pack_sequences(seqs, quals_list):
+    """Python reads -> (bases uint8, qualities uint8, offsets uint64, lengths uint32), back to back: the layout
+    Context.filter_pairs takes for either file of a pair."""
+    lengths = np.array([len(s) for s in seqs], dtype=np.uint32)
+    offsets = np.zeros(len(seqs), dtype=np.uint64)
+    if len(seqs):
+        offsets[1:] = np.cumsum(lengths.astype(np.uint64))[:-1]
+    bases = np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+    flat = [q for ql in quals_list for q in ql]
+    if any(q < 0 or q > 0xFC for q in flat):
+        raise MoiraError(L.ERR_BAD_QUALITY, "quality outside 0..252")
+    quals = np.asarray(flat, dtype=np.uint8)
+    if bases.size == 0:
+        bases, quals = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    return bases, quals, offsets, lengths
 
 
 # ---- host-side packing (C++ in the library, no GPU) ---------------------------------------------
@@ -332,7 +457,7 @@ def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = T
 
 def parse_fasta_qual(fasta: bytes, qual: bytes, lower_n_ambiguous: bool = True):
     """FASTA + QUAL bytes -> (slab, qual_slab, offsets, lengths, hdr_off, hdr_len, seq_off) via
-    moira_parse_fasta_qual.  qual_slab holds the plain qualities (Q <= 0 -> 1) at the slab's offsets."""
+    moira_parse_fasta_qual.  qual_slab holds the plain qualities (negative values as 0) at the slab's offsets."""
     fb = np.frombuffer(fasta, dtype=np.uint8)
     qb = np.frombuffer(qual, dtype=np.uint8)
     n = ctypes.c_uint64()
@@ -387,4 +512,4 @@ def collapse(text, seq_off, seq_len, ee, n_threads: int = 0) -> CollapseResult:
 
 
 __all__ = ["collapse", "CollapseResult","Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",
-           "pack_arrays", "pack_q6", "parse_fastq", "parse_fasta_qual", "build_lut"]
+           "pack_arrays", "pack_q6", "parse_fastq", "parse_fasta_qual", "build_lut", "ContigParams", "PairResult", "pack_sequences"]

@@ -24,7 +24,7 @@ import time
 import numpy as np
 
 from . import _lib as L
-from .api import Context, FilterParams, MoiraError, collapse, pack_reads, parse_fasta_qual, parse_fastq
+from .api import ContigParams, Context, FilterParams, MoiraError, collapse, pack_reads, parse_fasta_qual, parse_fastq
 
 __version__ = "0.1.0 (moira 1.3.2 compatible)"
 
@@ -87,6 +87,15 @@ def parse_arguments(argv=None):
     general.add_argument("--nowarnings", action="store_true")
     general.add_argument("--doc", action="store_true")
     general.add_argument("--device", type=int, default=0, help="CUDA device index (B200 path only).")
+    constructor = parser.add_argument_group("Contig construction options")     # moira.py:629-646
+    constructor.add_argument("-m", "--match", type=int, default=1)
+    constructor.add_argument("-x", "--mismatch", type=int, default=-1)
+    constructor.add_argument("-g", "--gap", type=int, default=-2)
+    constructor.add_argument("--trim_overlap", action="store_true")
+    constructor.add_argument("-i", "--insert", type=int, default=20)
+    constructor.add_argument("-d", "--deltaq", type=int, default=6)
+    constructor.add_argument("-q", "--consensus_qscore", type=str, default="best", choices=("best", "sum", "posterior"))
+    constructor.add_argument("-z", "--qscore_cap", type=int, default=40)
     filtering = parser.add_argument_group("Sequence filtering options")
     filtering.add_argument("-c", "--collapse", type=str2bool, default="True")
     filtering.add_argument("-t", "--truncate", type=int)
@@ -117,12 +126,34 @@ def check_arguments(args, out=sys.stdout):
     if args.doc:
         print(__doc__, file=out)
         return False
-    if args.paired or args.only_contig:
-        warn("- Paired-end contig construction (--paired / --only_contig) is not part of the B200 build; "
-             "assemble contigs first and pass them as --forward_fastq or --forward_fasta/--forward_qual.")
-        return False
+    if args.only_contig:                                                       # moira.py:695-696
+        args.paired = True
     if not args.forward_fastq and (not args.forward_fasta or not args.forward_qual):
         warn("- You must at least provide one fastq file, or a fasta and quality files.")
+        ok = False
+    if args.paired and not args.reverse_fastq and (not args.reverse_fasta or not args.reverse_qual):
+        warn("- You must provide one reverse fastq file, or reverse fasta and quality files.")
+        ok = False
+    if args.match < 0:
+        warn("- Needleman-Wunsch match score must be a non-negative integer.")
+        ok = False
+    if args.mismatch > 0:
+        warn("- Needleman-Wunsch mismatch penalty must be a non-positive integer.")
+        ok = False
+    if args.gap > 0:
+        warn("- Needleman-Wunsch gap penalty must be a non-positive integer.")
+        ok = False
+    if args.insert < 1:
+        warn("- The contig constructor insert parameter must be a positive integer.")
+        ok = False
+    if args.deltaq < 1:
+        warn("- The contig constructor deltaq parameter must be a positive integer.")
+        ok = False
+    if args.qscore_cap < 0:
+        warn("- The contig constructor qscore_cap parameter must be a non-negative integer.")
+        ok = False
+    if args.min_overlap is not None and args.min_overlap <= 0:
+        warn("- The min_overlap parameter must be greater than 0.")
         ok = False
     if not 0 < args.uncert <= 1:
         warn("- The uncert parameter must be between 0 (not included) and 1.")
@@ -141,6 +172,8 @@ def check_arguments(args, out=sys.stdout):
         return False
     if (args.reverse_fasta or args.reverse_fastq) and not args.paired:
         warn("You provided a reverse sequence file, but not the --paired flag. Note that only the forward file will be processed.\n")
+    if args.min_overlap and not args.paired:
+        warn("You specified a value for --min_overlap, but not the --paired flag. Note that contigs will not be assembled.")
     return True
 
 
@@ -266,9 +299,97 @@ def read_fasta_qual_batches(ffh, qfh, lower_n_ambiguous, fasta_name, qual_name):
         n = len(lengths)
         headers = [ftext[int(hoff[i]):int(hoff[i]) + int(hlen[i])].decode("latin-1").replace(":", "_") for i in range(n)]
         seqs = [ftext[int(soff[i]):int(soff[i]) + int(lengths[i])].decode("latin-1") for i in range(n)]
-        quals = [qslab[int(offsets[i]):int(offsets[i]) + int(lengths[i])].astype(np.int32) for i in range(n)]
+        quals = [np.maximum(qslab[int(offsets[i]):int(offsets[i]) + int(lengths[i])].astype(np.int32), 1) for i in range(n)]   # moira.py:814
         yield headers, seqs, quals, slab, offsets, lengths
         if not block:
+            break
+
+
+def _whole_records(fh, carry, lines_per_record, want_lines=None):
+    """Next block of whole records of a text file: (text, carry, n_lines, at_eof).  want_lines: exactly that many
+    lines (the partner file's block decides); None: whatever a BATCH_BYTES read holds."""
+    data = carry
+    eof = False
+    while True:
+        n_lines = data.count(b"\n")
+        if want_lines is not None and n_lines >= want_lines:
+            break
+        block = fh.read(BATCH_BYTES)
+        if not block:
+            eof = True
+            break
+        data += block
+        if want_lines is None:
+            break
+    n_lines = data.count(b"\n")
+    if eof:
+        if data and not data.endswith(b"\n"):
+            n_lines += 1
+        keep = n_lines - n_lines % lines_per_record if want_lines is None else min(want_lines, n_lines)
+        if want_lines is None or keep >= n_lines:
+            return data, b"", keep, True
+    else:
+        keep = n_lines - n_lines % lines_per_record if want_lines is None else want_lines
+    pos = _cut_lines(data, keep)
+    return data[:pos], data[pos:], keep, eof and pos >= len(data)
+
+
+def read_pair_batches(args, lower_n_ambiguous):
+    """Paired input (moira.py:1093-1204 with both files): blocks of whole records of the forward file and the same
+    number of records of the reverse file, parsed natively, headers compared (NameMismatchError).
+    Yields (headers, fwd, rev) with fwd / rev = (bases u8, quals u8, seq_off, qual_off, lengths, qual_base)."""
+    fastq = bool(args.forward_fastq)
+    if fastq:
+        files = [(open_input(args.forward_fastq), args.forward_fastq), (open_input(args.reverse_fastq), args.reverse_fastq)]
+        per = 4
+    else:
+        files = [(open_input(args.forward_fasta), args.forward_fasta), (open_input(args.forward_qual), args.forward_qual),
+                 (open_input(args.reverse_fasta), args.reverse_fasta), (open_input(args.reverse_qual), args.reverse_qual)]
+        per = 2
+    carries = [b""] * len(files)
+    while True:
+        text0, carries[0], n_lines, eof = _whole_records(files[0][0], carries[0], per)
+        texts = [text0]
+        for k in range(1, len(files)):
+            t, carries[k], got, _ = _whole_records(files[k][0], carries[k], per, n_lines)
+            texts.append(t)
+        if not text0.strip():
+            if any(t.strip() for t in texts[1:]) or any(c.strip() for c in carries[1:]):
+                raise NameMismatchError("", "(the forward file ended first)")
+            break
+
+        def parse(idx):
+            try:
+                if fastq:
+                    _, _, ln, hoff, hlen, soff, qoff = parse_fastq(texts[idx], args.fastq_offset, lower_n_ambiguous)
+                    buf = np.frombuffer(texts[idx], dtype=np.uint8)
+                    return texts[idx], hoff, hlen, (buf, buf, soff, qoff, ln, args.fastq_offset)
+                _, qslab, off, ln, hoff, hlen, soff = parse_fasta_qual(texts[2 * idx], texts[2 * idx + 1], lower_n_ambiguous)
+                return texts[2 * idx], hoff, hlen, (np.frombuffer(texts[2 * idx], dtype=np.uint8), qslab, soff, off, ln, 0)
+            except MoiraError as exc:
+                if exc.code == L.ERR_PARSE:
+                    name = exc.message.split(":")[0]
+                    cls = {"EmptySeqError": EmptySeqError, "EmptyQualError": EmptyQualError}.get(name)
+                    fname = files[idx if fastq else 2 * idx][1]
+                    if cls:
+                        raise cls(exc.message, fname) from None
+                    if name == "NameMismatchError":
+                        raise NameMismatchError(exc.message, "") from None
+                    raise LengthMismatchError(exc.message, fname) from None
+                raise
+
+        ftext, fh_off, fh_len, fwd = parse(0)
+        rtext, rh_off, rh_len, rev = parse(1)
+        n = len(fwd[4])
+        if len(rev[4]) != n:
+            raise NameMismatchError("(%d forward records)" % n, "(%d reverse records)" % len(rev[4]))
+        headers = [ftext[int(fh_off[i]):int(fh_off[i]) + int(fh_len[i])].decode("latin-1").replace(":", "_") for i in range(n)]
+        for i in range(n):                                                   # moira.py:1141-1142, 1199-1200
+            rh = rtext[int(rh_off[i]):int(rh_off[i]) + int(rh_len[i])].decode("latin-1").replace(":", "_")
+            if rh != headers[i]:
+                raise NameMismatchError(headers[i], None, rh, None)
+        yield headers, fwd, rev
+        if eof:
             break
 
 
@@ -300,26 +421,44 @@ class Writers:
             self.bad_names = op("%s.qc.bad.names" % output_name)
         else:
             self.good_names = self.bad_names = None
+        if args.paired:                                                           # moira.py:366-368
+            self.report = op("%s.contigs.report" % output_name)
+            self.report.write("header\tn_seqs\toverlap_length\tgaps\tmismatches\n")
+        else:
+            self.report = None
 
     def close(self):
         for fh in self.files:
             fh.close()
 
 
-def write_result(index, header, sequence, quals, expected_errors, names_info, accept, reason, args, w: Writers):
+REASON_OVERLAP = 100   # host-side: "overlap length below" (moira.py:886-897); the device knows reasons 0..3
+
+
+def write_result(index, header, sequence, quals, expected_errors, names_info, accept, reason, args, w: Writers, contig_stats=None):
     """One record, formatted as write_results does (moira.py:842-970); the accept/reason pair comes
-    from the device.  Returns (discarded_errors, discarded_minlength)."""
+    from the device.  Returns (discarded_errors, discarded_minlength, discarded_minoverlap)."""
     if args.relabel:
         header = "%s%d" % (args.relabel, index)
     if args.pipeline == "USEARCH":
         header = header + ";ee=%.2f;size=%d;" % (expected_errors, len(names_info) if names_info else 1)
     n_members = len(names_info) if names_info else 1
+    if w.report is not None and contig_stats is not None:                        # moira.py:866-870
+        w.report.write("%s\t%s\t%s\t%s\t%s\n" % ((header, n_members) + tuple(contig_stats)))
+        # the rules that sit between the length check and the error filter when contigs were built (moira.py:886-908)
+        if reason != L.REASON_LENGTH:
+            if args.min_overlap and contig_stats[0] < args.min_overlap:
+                accept, reason = False, REASON_OVERLAP
+            elif args.only_contig:
+                accept, reason = True, L.REASON_NONE
     if accept:
         out, out_q, out_n, note = w.good, w.good_qual, w.good_names, ""
     else:
         out, out_q, out_n = w.bad, w.bad_qual, w.bad_names
         if reason == L.REASON_LENGTH:
             note = "\tlength below %s" % args.truncate
+        elif reason == REASON_OVERLAP:                                            # the fastq branch prints --truncate (moira.py:888)
+            note = "\toverlap length below %s" % (args.truncate if args.output_format == "fastq" else args.min_overlap)
         elif reason == L.REASON_AMBIGS:
             note = "\tcontains ambiguities"
         elif args.maxerrors:
@@ -334,8 +473,10 @@ def write_result(index, header, sequence, quals, expected_errors, names_info, ac
     if args.collapse and args.pipeline == "mothur" and out_n is not None:
         out_n.write("%s\t%s\n" % (header, ",".join(names_info)))
     if accept:
-        return 0, 0
-    return (0, n_members) if reason == L.REASON_LENGTH else (n_members, 0)
+        return 0, 0, 0
+    if reason == L.REASON_LENGTH:
+        return 0, n_members, 0
+    return (0, 0, n_members) if reason == REASON_OVERLAP else (n_members, 0, 0)
 
 
 # ---- main (moira.py:264-578) ---------------------------------------------------------------------------
@@ -357,8 +498,12 @@ def main(args, out=sys.stdout) -> int:
                           exact_ee=bool(args.collapse) or args.pipeline == "USEARCH", ee_output="final")
     lower_n = args.error_calc == "poisson_binomial"      # bernoullimodule.c:196 vs moira.py:1605/1660
 
+    contig_params = ContigParams(match=args.match, mismatch=args.mismatch, gap=args.gap, insert=args.insert, deltaq=args.deltaq,
+                                 consensus_qscore=args.consensus_qscore, qscore_cap=args.qscore_cap, trim_overlap=args.trim_overlap)
     try:
-        if args.forward_fastq:
+        if args.paired:
+            batches = read_pair_batches(args, lower_n)
+        elif args.forward_fastq:
             batches = read_fastq_batches(open_input(args.forward_fastq), args.fastq_offset, lower_n, args.forward_fastq)
         else:
             batches = read_fasta_qual_batches(open_input(args.forward_fasta), open_input(args.forward_qual), lower_n,
@@ -369,13 +514,51 @@ def main(args, out=sys.stdout) -> int:
         return 1
 
     ctx = Context(args.device)
+
+    def results():
+        """(headers, sequences, qualities, ee, accept, reason, contig statistics or None) per batch."""
+        if not args.paired:
+            for headers, seqs, quals, slab, offsets, lengths in batches:
+                res = ctx.filter_batch(slab, offsets, lengths, params)
+                yield headers, seqs, quals, res, None
+            return
+        for headers, fwd, rev in batches:
+            # contigs and the filter on them in one call (process_data, moira.py:791-833); --only_contig skips the filter
+            pr = ctx.filter_pairs(fwd[0], fwd[1], fwd[2], fwd[4], rev[0], rev[1], rev[2], rev[4], contig_params,
+                                  None if args.only_contig else params, lower_n, fwd[3], rev[3], fwd[5])
+            bad = np.flatnonzero(pr.status)
+            if bad.size:
+                r = int(bad[0])
+                st = int(pr.status[r])
+                if st == L.PAIR_BAD_BASE:                                          # moira.py:1228-1229
+                    seq = rev[0][int(rev[2][r]):int(rev[2][r]) + int(rev[4][r])].tobytes().decode("latin-1")
+                    wrong = [c for c in seq if c not in "ACTGNWSRYMKBVDH-."]
+                    raise ValueError('"%s" is not a recognizable IUPAC-coded base.' % (wrong[0] if wrong else "?"))
+                raise ValueError("Contig construction failed for %s (%s)" % (headers[r], {
+                    L.PAIR_EMPTY: "empty read", L.PAIR_BAD_QUALITY: "a quality score outside 0..252",
+                    L.PAIR_TOO_LONG: "reverse read longer than 1024 bases"}.get(st, "status %d" % st)))
+            seqs, quals = [], []
+            for r in range(len(headers)):
+                c, q = pr.contig(r)
+                seqs.append(c)
+                quals.append(np.maximum(np.asarray(q, dtype=np.int32), 1))         # moira.py:814
+            if pr.filter is None:                                                  # expected_errors = 0 (moira.py:809-810)
+                n = len(headers)
+                from .api import FilterResult
+                res = FilterResult(np.zeros(n), np.zeros(n, np.int32), np.full(n, L.FLAG_ACCEPT, np.uint8), np.zeros(L.N_COUNTERS, np.uint64))
+                if args.truncate:
+                    short = pr.contig_len < args.truncate
+                    res.flags[short] = L.REASON_LENGTH << 1
+            else:
+                res = pr.filter
+            yield headers, seqs, quals, res, np.stack([pr.overlap, pr.gaps, pr.mismatches], axis=1)
+
     processed = 0
-    discarded_errors = discarded_minlength = 0
-    all_headers, all_seqs, all_quals, all_ee, all_acc, all_rsn = [], [], [], [], [], []   # --collapse: kept for the epilogue
+    discarded_errors = discarded_minlength = discarded_minoverlap = 0
+    all_headers, all_seqs, all_quals, all_ee, all_acc, all_rsn, all_stats = [], [], [], [], [], [], []   # --collapse: kept for the epilogue
     t0 = time.time()
     try:
-        for headers, seqs, quals, slab, offsets, lengths in batches:
-            res = ctx.filter_batch(slab, offsets, lengths, params)
+        for headers, seqs, quals, res, stats in results():
             if np.isnan(res.ee).any() or res.numeric.any():
                 bad = int(np.flatnonzero(np.isnan(res.ee) | res.numeric)[0])
                 raise ReturnedNaNError("Error calculation failed for sequence %s" % headers[bad])
@@ -391,13 +574,16 @@ def main(args, out=sys.stdout) -> int:
                 all_ee.append(res.ee.copy())
                 all_acc.append(accept.copy())
                 all_rsn.append(reason.copy())
+                if stats is not None:
+                    all_stats.append(stats)
                 processed += len(headers)
             else:
                 for i, header in enumerate(headers):
-                    de, dl = write_result(processed, header, seqs[i], quals[i], float(res.ee[i]), None, bool(accept[i]),
-                                          int(reason[i]), args, writers)
+                    de, dl, do = write_result(processed, header, seqs[i], quals[i], float(res.ee[i]), None, bool(accept[i]),
+                                              int(reason[i]), args, writers, None if stats is None else stats[i].tolist())
                     discarded_errors += de
                     discarded_minlength += dl
+                    discarded_minoverlap += do
                     processed += 1
             if not args.silent:
                 print("%d sequences processed in %.1f seconds.\r" % (processed, time.time() - t0), end="", file=out)
@@ -407,6 +593,7 @@ def main(args, out=sys.stdout) -> int:
             ee_all = np.concatenate(all_ee)
             acc_all = np.concatenate(all_acc)
             rsn_all = np.concatenate(all_rsn)
+            stats_all = np.concatenate(all_stats) if all_stats else None
             seq_len = np.fromiter((len(s_) for s_ in all_seqs), dtype=np.uint32, count=processed)
             seq_off = np.zeros(processed, dtype=np.uint64)
             seq_off[1:] = np.cumsum(seq_len[:-1], dtype=np.uint64)
@@ -414,20 +601,25 @@ def main(args, out=sys.stdout) -> int:
             for index, g in enumerate(col.order.tolist(), start=1):
                 rep = int(col.rep[g])
                 names = [all_headers[r] for r in col.members[int(col.member_start[g]):int(col.member_start[g + 1])].tolist()]
-                de, dl = write_result(index, all_headers[rep], all_seqs[rep], all_quals[rep], float(ee_all[rep]), names,
-                                      bool(acc_all[rep]), int(rsn_all[rep]), args, writers)
+                de, dl, do = write_result(index, all_headers[rep], all_seqs[rep], all_quals[rep], float(ee_all[rep]), names,
+                                          bool(acc_all[rep]), int(rsn_all[rep]), args, writers,
+                                          None if stats_all is None else stats_all[rep].tolist())
                 discarded_errors += de
                 discarded_minlength += dl
+                discarded_minoverlap += do
     finally:
         writers.close()
         ctx.close()
 
     if not args.silent and processed:
-        remaining = processed - discarded_errors - discarded_minlength
+        remaining = processed - discarded_errors - discarded_minlength - discarded_minoverlap
         print("\n- Kept %d (%.2f%%) of the original sequences." % (remaining, remaining / processed * 100), file=out)
         if args.truncate:
             print("- %d (%.2f%%) of the original sequences were discarded due to length < %s." %
                   (discarded_minlength, discarded_minlength / processed * 100, args.truncate), file=out)
+        if args.min_overlap and args.paired:
+            print("- %d (%.2f%%) of the original sequences were discarded due to overlap length < %s." %
+                  (discarded_minoverlap, discarded_minoverlap / processed * 100, args.min_overlap), file=out)
         print("- %d (%.2f%%) of the original sequences were discarded due to low quality.\n" %
               (discarded_errors, discarded_errors / processed * 100), file=out)
         print("The following output files were generated:", file=out)

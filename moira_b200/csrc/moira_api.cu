@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "moira_internal.h"
@@ -80,6 +81,14 @@ struct StreamBuf {
     }
 };
 
+// device buffers of one chunk of read pairs (moira_filter_pairs)
+struct PairBufs {
+    DevBuf fseq, fqual, foff, flen, rseq, rqual, roff, rlen;
+    DevBuf cseq, cqual, slab, clen, overlap, gaps, mism, status, ee, ns, flags;
+    DevBuf *all[19] = {&fseq, &fqual, &foff, &flen, &rseq, &rqual, &roff, &rlen, &cseq, &cqual, &slab, &clen,
+                       &overlap, &gaps, &mism, &status, &ee, &ns, &flags};
+};
+
 struct Ticket {
     bool busy = false;
     DevBuf slab, slab6, offsets, lengths, ee, ns, flags, counters;
@@ -120,6 +129,10 @@ struct moira_ctx {
     int n_timed = 0;
     cudaEvent_t t0[MAX_TIMED] = {}, t1[MAX_TIMED] = {};
     const char *timed_name = "";
+    // paired-end contig construction: per-stream device buffers, traceback scratch, posterior tables
+    PairBufs pb[2];
+    DevBuf trace, hbuf, post, pair_counters;
+    bool post_ready = false;
     // single-read scratch (pinned)
     uint8_t *one_slab = nullptr;
     size_t one_cap = 0;
@@ -468,6 +481,9 @@ int moira_ctx_destroy(moira_ctx *c)
         if (t.counters_pinned) cudaFreeHost(t.counters_pinned);
     }
     for (auto &b : c->fq) b.release();
+    for (auto &pb : c->pb)
+        for (DevBuf *b : pb.all) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : {&c->trace, &c->hbuf, &c->post, &c->pair_counters}) if (b->p) cudaFree(b->p);
     for (auto &w : c->ws) {
         if (w.queues) cudaFree(w.queues);
         if (w.counts) cudaFree(w.counts);
@@ -808,6 +824,359 @@ int moira_calculate_errors_PB(moira_ctx *c, const char *contig, const int32_t *q
     if (*fl & MOIRA_FLAG_NUMERIC) return fail(MOIRA_ERR_UNRESOLVED, "cumulative probability never exceeded 1 - alpha");
     *ee_out = *ee;
     *ns_out = *ns;
+    return MOIRA_OK;
+}
+
+
+// ---- paired-end contig construction --------------------------------------------------------------
+void moira_contig_params_default(moira_contig_params *p)
+{
+    if (!p) return;
+    p->match = 1; p->mismatch = -1; p->gap = -2;      // moira.py:630-634
+    p->insert = 20; p->deltaq = 6;                    // moira.py:638-640
+    p->consensus = MOIRA_CONSENSUS_BEST;              // moira.py:642
+    p->qscore_cap = 40;                               // moira.py:645
+    p->trim_overlap = 0;
+}
+
+static int check_contig_params(const moira_contig_params *p)
+{
+    if (!p) return fail(MOIRA_ERR_BAD_ARG, "contig params is NULL");
+    if (p->consensus < MOIRA_CONSENSUS_BEST || p->consensus > MOIRA_CONSENSUS_POSTERIOR)
+        return fail(MOIRA_ERR_BAD_ARG, "consensus_qscore must be \"best\", \"sum\" or \"posterior\".");   // moira.py:1405-1406
+    if (p->insert <= 0) return fail(MOIRA_ERR_BAD_ARG, "insert must be a positive integer");              // moira.py:1411-1412
+    if (p->deltaq <= 0) return fail(MOIRA_ERR_BAD_ARG, "deltaq must be a positive integer");              // moira.py:1413-1414
+    if (p->qscore_cap < 0) return fail(MOIRA_ERR_BAD_ARG, "qscore_cap must be a non-negative integer");   // moira.py:1415-1416
+    return MOIRA_OK;
+}
+
+// Posterior consensus qualities for every pair of input qualities, with the host libm and the reference's
+// own expressions (moira.py:1391-1395, 1522-1524, 1547-1553): [0, 65536) agreeing bases, [65536, 131072)
+// disagreeing bases indexed [better * 256 + worse].
+static int ensure_post_tables(moira_ctx *c)
+{
+    if (c->post_ready) return MOIRA_OK;
+    int rc = ensure(c->post, 2 * 65536 * sizeof(int16_t));
+    if (rc) return rc;
+    std::vector<int16_t> t(2 * 65536);
+    auto qual2prob = [](int q) { volatile double p = pow(10, (q / (-10.0))); return (double)p; };
+    auto prob2qual = [](double prob) { const double v = floor(-10 * log10(prob)); return (int16_t)(v > 32000 ? 32000 : (v < -32000 ? -32000 : v)); };
+    for (int a = 0; a < 256; a++)
+        for (int b = 0; b < 256; b++) {
+            {
+                const double p1 = qual2prob(a), p2 = qual2prob(b);
+                volatile double num = p1 * p2 / 3;
+                volatile double den = 1 - p1 - p2 + (4 * p1 * p2 / 3);
+                volatile double post = num / den;
+                t[a * 256 + b] = prob2qual(post);
+            }
+            if (a > b) {   // a: quality of the base that is kept
+                const double p1 = qual2prob(a), p2 = qual2prob(b);
+                volatile double num = p1 * (1 - p2 / 3);
+                volatile double den = p1 + p2 - (4 * p1 * p2 / 3);
+                volatile double post = num / den;
+                t[65536 + a * 256 + b] = prob2qual(post);
+            } else t[65536 + a * 256 + b] = 2;
+        }
+    CU(cudaMemcpy(c->post.p, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    c->post_ready = true;
+    return MOIRA_OK;
+}
+
+static void fill_contig_args(ContigArgs &a, const moira_ctx *c, const moira_contig_params *p, int lower_n)
+{
+    memset(&a, 0, sizeof(a));
+    a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap; a.insert = p->insert; a.deltaq = p->deltaq;
+    a.consensus = p->consensus; a.qscore_cap = p->qscore_cap; a.trim_overlap = p->trim_overlap ? 1 : 0; a.lower_n = lower_n ? 1 : 0;
+    a.post_match = (const int16_t *)c->post.p;
+    a.post_mis = a.post_match ? a.post_match + 65536 : nullptr;
+}
+
+int moira_filter_pairs(moira_ctx *c, const char *fwd_seq, uint64_t fwd_bytes, const uint8_t *fwd_qual, uint64_t fwd_qbytes,
+                       const uint64_t *fwd_off, const uint64_t *fwd_qoff, const uint32_t *fwd_len, const char *rev_seq,
+                       uint64_t rev_bytes, const uint8_t *rev_qual, uint64_t rev_qbytes, const uint64_t *rev_off,
+                       const uint64_t *rev_qoff, const uint32_t *rev_len,
+                       int qual_base, uint64_t n, const moira_contig_params *cp, int lower_n,
+                       const moira_params *fp, uint64_t out_stride, char *contig_seq, uint8_t *contig_qual, uint32_t *contig_len,
+                       int32_t *overlap, int32_t *gaps, int32_t *mismatches, uint8_t *status, double *ee_out, int32_t *ns_out,
+                       uint8_t *flags_out, uint64_t *counters_out)
+{
+    if (!c) return fail(MOIRA_ERR_BAD_ARG, "ctx is NULL");
+    int rc = check_contig_params(cp);
+    if (rc) return rc;
+    if (fp && (rc = check_params(fp))) return rc;
+    if (fp && fp->slab_format != MOIRA_SLAB_Q8) return fail(MOIRA_ERR_BAD_ARG, "slab_format does not apply to read pairs");
+    if (counters_out) memset(counters_out, 0, MOIRA_N_COUNTERS * sizeof(uint64_t));
+    if (n == 0) return MOIRA_OK;
+    if (!fwd_seq || !fwd_qual || !fwd_off || !fwd_len || !rev_seq || !rev_qual || !rev_off || !rev_len || !contig_seq ||
+        !contig_qual || !contig_len || !status || (fp && !ee_out))
+        return fail(MOIRA_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(c->device));
+    uint32_t max_l1 = 0, max_l2 = 0;
+    if (!fwd_qoff) fwd_qoff = fwd_off;
+    if (!rev_qoff) rev_qoff = rev_off;
+    for (uint64_t r = 0; r < n; r++) {
+        if (fwd_off[r] + fwd_len[r] > fwd_bytes || rev_off[r] + rev_len[r] > rev_bytes || fwd_qoff[r] + fwd_len[r] > fwd_qbytes ||
+            rev_qoff[r] + rev_len[r] > rev_qbytes)
+            return fail(MOIRA_ERR_BAD_ARG, "pair %llu extends past its arrays", (unsigned long long)r);
+        max_l1 = std::max(max_l1, fwd_len[r]);
+        max_l2 = std::max(max_l2, rev_len[r]);
+    }
+    if (max_l1 > 4096) return fail(MOIRA_ERR_BAD_ARG, "forward reads longer than 4096 bases are not supported");
+    if (max_l1 == 0) max_l1 = 1;
+    if (max_l2 == 0) max_l2 = 1;
+    if (max_l2 > 1024) max_l2 = 1024;   // longer reverse reads get MOIRA_PAIR_TOO_LONG
+    if (out_stride < (uint64_t)max_l1 + max_l2 || (out_stride & 15u))
+        return fail(MOIRA_ERR_BAD_ARG, "out_stride must be a multiple of 16 and at least max(fwd_len) + max(rev_len) = %u", max_l1 + max_l2);
+    if (cp->consensus == MOIRA_CONSENSUS_POSTERIOR && (rc = ensure_post_tables(c))) return rc;
+    const size_t warps = (size_t)c->sm_count * CONTIG_WARPS_PER_CTA;
+    const size_t tw = contig_trace_words_per_warp(max_l1, max_l2);
+    if ((rc = ensure(c->trace, warps * tw * sizeof(uint32_t)))) return rc;
+    if (fp && (rc = ensure(c->pair_counters, MOIRA_N_COUNTERS * 8))) return rc;
+    uint64_t *d_cnt = (uint64_t *)c->pair_counters.p;
+    if (fp) CU(cudaMemsetAsync(d_cnt, 0, MOIRA_N_COUNTERS * 8, c->streams[0]));
+    if (fp) { CU(cudaEventRecord(c->meta_ready, c->streams[0])); CU(cudaStreamWaitEvent(c->streams[1], c->meta_ready, 0)); }
+
+    // Chunks of pairs alternate between the two streams: the copies of one chunk overlap the kernels of the other.
+    constexpr uint64_t PAIR_CHUNK = 1u << 17;
+    int ci = 0;
+    for (uint64_t start = 0; start < n; start += PAIR_CHUNK, ci++) {
+        const uint64_t cn = std::min<uint64_t>(PAIR_CHUNK, n - start);
+        PairBufs &b = c->pb[ci & 1];
+        cudaStream_t s = c->streams[ci & 1];
+        if (ci >= 2) CU(cudaStreamSynchronize(s));   // the host arrays of chunk ci - 2 are complete; its buffers are free
+        // byte ranges of this chunk in the four host arrays; bases and qualities that live in ONE buffer (the
+        // FASTQ text) travel once
+        uint64_t f0 = ~0ull, f1 = 0, r0 = ~0ull, r1 = 0, fq0 = ~0ull, fq1 = 0, rq0 = ~0ull, rq1 = 0;
+        for (uint64_t r = start; r < start + cn; r++) {
+            f0 = std::min(f0, fwd_off[r]); f1 = std::max(f1, fwd_off[r] + fwd_len[r]);
+            r0 = std::min(r0, rev_off[r]); r1 = std::max(r1, rev_off[r] + rev_len[r]);
+            fq0 = std::min(fq0, fwd_qoff[r]); fq1 = std::max(fq1, fwd_qoff[r] + fwd_len[r]);
+            rq0 = std::min(rq0, rev_qoff[r]); rq1 = std::max(rq1, rev_qoff[r] + rev_len[r]);
+        }
+        const bool f_shared = (const void *)fwd_seq == (const void *)fwd_qual, r_shared = (const void *)rev_seq == (const void *)rev_qual;
+        if (f_shared) { f0 = fq0 = std::min(f0, fq0); f1 = fq1 = std::max(f1, fq1); }
+        if (r_shared) { r0 = rq0 = std::min(r0, rq0); r1 = rq1 = std::max(r1, rq1); }
+        if ((rc = ensure(b.fseq, f1 - f0 + 16)) || (!f_shared && (rc = ensure(b.fqual, fq1 - fq0 + 16))) ||
+            (rc = ensure(b.rseq, r1 - r0 + 16)) || (!r_shared && (rc = ensure(b.rqual, rq1 - rq0 + 16))) ||
+            (rc = ensure(b.foff, cn * 16)) || (rc = ensure(b.roff, cn * 16)) ||
+            (rc = ensure(b.flen, cn * 4)) || (rc = ensure(b.rlen, cn * 4)) || (rc = ensure(b.cseq, cn * out_stride)) ||
+            (rc = ensure(b.cqual, cn * out_stride)) || (rc = ensure(b.slab, cn * out_stride + 256)) || (rc = ensure(b.clen, cn * 4)) ||
+            (rc = ensure(b.overlap, cn * 4)) || (rc = ensure(b.gaps, cn * 4)) || (rc = ensure(b.mism, cn * 4)) ||
+            (rc = ensure(b.status, cn)) || (rc = ensure(b.ee, cn * 8)) || (rc = ensure(b.ns, cn * 4)) || (rc = ensure(b.flags, cn)))
+            return rc;
+        CU(cudaMemcpyAsync(b.fseq.p, fwd_seq + f0, f1 - f0, cudaMemcpyHostToDevice, s));
+        if (!f_shared) CU(cudaMemcpyAsync(b.fqual.p, fwd_qual + fq0, fq1 - fq0, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b.rseq.p, rev_seq + r0, r1 - r0, cudaMemcpyHostToDevice, s));
+        if (!r_shared) CU(cudaMemcpyAsync(b.rqual.p, rev_qual + rq0, rq1 - rq0, cudaMemcpyHostToDevice, s));
+        uint64_t *d_foff = (uint64_t *)b.foff.p, *d_roff = (uint64_t *)b.roff.p;   // [0, cn): bases, [cn, 2 cn): qualities
+        CU(cudaMemcpyAsync(d_foff, fwd_off + start, cn * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d_foff + cn, fwd_qoff + start, cn * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d_roff, rev_off + start, cn * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d_roff + cn, rev_qoff + start, cn * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b.flen.p, fwd_len + start, cn * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b.rlen.p, rev_len + start, cn * 4, cudaMemcpyHostToDevice, s));
+        ContigArgs a;
+        fill_contig_args(a, c, cp, lower_n);
+        // offsets stay absolute: the device pointers are shifted by the chunk's first byte
+        a.fseq = (const char *)b.fseq.p - f0;
+        a.fqual = f_shared ? (const uint8_t *)b.fseq.p - f0 : (const uint8_t *)b.fqual.p - fq0;
+        a.rseq = (const char *)b.rseq.p - r0;
+        a.rqual = r_shared ? (const uint8_t *)b.rseq.p - r0 : (const uint8_t *)b.rqual.p - rq0;
+        a.foff = d_foff; a.fqoff = d_foff + cn; a.flen = (const uint32_t *)b.flen.p;
+        a.roff = d_roff; a.rqoff = d_roff + cn; a.rlen = (const uint32_t *)b.rlen.p;
+        a.qual_base = qual_base;
+        a.n_pairs = cn;
+        // every chunk uses the whole trace scratch: chunks on the two streams must not run their contig kernels at once
+        if (ci >= 1) { CU(cudaEventRecord(c->tickets[0].done[(ci - 1) & 1], c->streams[(ci - 1) & 1])); CU(cudaStreamWaitEvent(s, c->tickets[0].done[(ci - 1) & 1], 0)); }
+        a.trace = (uint32_t *)c->trace.p; a.trace_words_per_warp = tw;
+        a.out_stride = out_stride;
+        a.cseq = (char *)b.cseq.p; a.cqual = (uint8_t *)b.cqual.p; a.slab = fp ? (uint8_t *)b.slab.p : nullptr;
+        a.clen = (uint32_t *)b.clen.p; a.overlap = (int32_t *)b.overlap.p; a.gaps = (int32_t *)b.gaps.p; a.mism = (int32_t *)b.mism.p;
+        a.status = (uint8_t *)b.status.p;
+        a.max_l1 = max_l1; a.max_l2 = max_l2;
+        LaunchCfg cfg{c->sm_count, s};
+        const int lr = launch_contigs(a, false, cfg);
+        if (lr) return fail(lr == -2 ? MOIRA_ERR_BAD_ARG : MOIRA_ERR_CUDA, "contig kernel launch failed: %s", lr == -2 ? "reads too long" : cudaGetErrorString(cudaGetLastError()));
+        c->launches++;
+        if (fp) {
+            const uint32_t cap = (uint32_t)std::min<uint64_t>(out_stride, 0xFFFFFFF0u);
+            rc = run_filter_full(c, c->ws[ci & 1], (const uint8_t *)b.slab.p, nullptr, (const uint32_t *)b.clen.p, out_stride, 0, cn, fp,
+                                 cap, 0, (double *)b.ee.p, (int32_t *)b.ns.p, (uint8_t *)b.flags.p, d_cnt, s);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(ee_out + start, b.ee.p, cn * 8, cudaMemcpyDeviceToHost, s));
+            if (ns_out) CU(cudaMemcpyAsync(ns_out + start, b.ns.p, cn * 4, cudaMemcpyDeviceToHost, s));
+            if (flags_out) CU(cudaMemcpyAsync(flags_out + start, b.flags.p, cn, cudaMemcpyDeviceToHost, s));
+        }
+        CU(cudaMemcpyAsync(contig_seq + start * out_stride, b.cseq.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(contig_qual + start * out_stride, b.cqual.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(contig_len + start, b.clen.p, cn * 4, cudaMemcpyDeviceToHost, s));
+        if (overlap) CU(cudaMemcpyAsync(overlap + start, b.overlap.p, cn * 4, cudaMemcpyDeviceToHost, s));
+        if (gaps) CU(cudaMemcpyAsync(gaps + start, b.gaps.p, cn * 4, cudaMemcpyDeviceToHost, s));
+        if (mismatches) CU(cudaMemcpyAsync(mismatches + start, b.mism.p, cn * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(status + start, b.status.p, cn, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(c->streams[1]));
+    CU(cudaStreamSynchronize(c->streams[0]));
+    if (fp && counters_out) CU(cudaMemcpy(counters_out, d_cnt, MOIRA_N_COUNTERS * 8, cudaMemcpyDeviceToHost));
+    CU(cudaGetLastError());
+    return MOIRA_OK;
+}
+
+// One pair through the contig kernel (the single-call entry points): inputs, the two output rows and the
+// scalar results live in one device allocation.
+struct SingleOut {
+    std::vector<uint8_t> row_a, row_b;   // contig bases / qualities, or the two aligned strings
+    uint32_t clen = 0;
+    int32_t overlap = 0, gaps = 0, mism = 0, alen = 0;
+    long long score = 0;
+    uint8_t status = 0;
+};
+
+static int single_pair(moira_ctx *c, ContigArgs &a, const std::string &f, const std::vector<uint8_t> &fq, const std::string &r,
+                       const std::vector<uint8_t> &rq, bool alignment_only, SingleOut &out)
+{
+    const size_t L1 = f.size(), L2 = r.size();
+    const size_t cap = (L1 + L2 + 16) & ~(size_t)15;
+    const size_t in_bytes = (2 * (L1 + L2) + 15) & ~(size_t)15;
+    const size_t meta = 32, tail_bytes = 48;
+    int rc;
+    if ((rc = ensure(c->pb[0].fseq, in_bytes + meta + 2 * cap + tail_bytes))) return rc;
+    uint8_t *d = (uint8_t *)c->pb[0].fseq.p;
+    std::vector<uint8_t> h(in_bytes + meta, 0);
+    memcpy(h.data(), f.data(), L1);
+    memcpy(h.data() + L1, fq.data(), L1);
+    memcpy(h.data() + 2 * L1, r.data(), L2);
+    memcpy(h.data() + 2 * L1 + L2, rq.data(), L2);
+    const uint32_t l1 = (uint32_t)L1, l2 = (uint32_t)L2;
+    memcpy(h.data() + in_bytes + 8, &l1, 4);     // [in_bytes, +8): offset 0 of both reads
+    memcpy(h.data() + in_bytes + 12, &l2, 4);
+    cudaStream_t s = c->streams[0];
+    CU(cudaMemcpyAsync(d, h.data(), h.size(), cudaMemcpyHostToDevice, s));
+    a.fseq = (const char *)d; a.fqual = d + L1; a.rseq = (const char *)d + 2 * L1; a.rqual = d + 2 * L1 + L2;
+    a.foff = a.roff = (const uint64_t *)(d + in_bytes);
+    a.flen = (const uint32_t *)(d + in_bytes + 8); a.rlen = (const uint32_t *)(d + in_bytes + 12);
+    a.n_pairs = 1;
+    a.rev_direct = 1;
+    a.max_l1 = std::max<uint32_t>(1, l1); a.max_l2 = std::max<uint32_t>(1, l2);
+    if (!contig_columns_per_lane(a.max_l2) || a.max_l1 > 4096) return fail(MOIRA_ERR_BAD_ARG, "sequences longer than 4096 x 1024 bases are not supported");
+    const size_t tw = contig_trace_words_per_warp(a.max_l1, a.max_l2);
+    if ((rc = ensure(c->trace, (size_t)c->sm_count * CONTIG_WARPS_PER_CTA * tw * sizeof(uint32_t)))) return rc;
+    a.trace = (uint32_t *)c->trace.p; a.trace_words_per_warp = tw;
+    if (alignment_only) {
+        if ((rc = ensure(c->hbuf, contig_hbuf_words(a.max_l1, a.max_l2) * sizeof(int32_t)))) return rc;
+        a.hbuf = (int32_t *)c->hbuf.p;
+    }
+    uint8_t *o = d + in_bytes + meta;            // row A | row B | scalars
+    uint8_t *tail = o + 2 * cap;
+    a.out_stride = cap;
+    a.cseq = (char *)o; a.cqual = o + cap; a.slab = nullptr;
+    if (alignment_only) { a.al1 = (char *)o; a.al2 = (char *)o + cap; }
+    a.clen = (uint32_t *)tail; a.overlap = (int32_t *)(tail + 4); a.gaps = (int32_t *)(tail + 8); a.mism = (int32_t *)(tail + 12);
+    a.alen = (int32_t *)(tail + 16); a.score = (long long *)(tail + 24); a.status = tail + 32;
+    LaunchCfg cfg{c->sm_count, s};
+    const int lr = launch_contigs(a, alignment_only, cfg);
+    if (lr) return fail(lr == -2 ? MOIRA_ERR_BAD_ARG : MOIRA_ERR_CUDA, "contig kernel launch failed");
+    c->launches++;
+    std::vector<uint8_t> back(2 * cap + tail_bytes);
+    CU(cudaMemcpyAsync(back.data(), o, back.size(), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    out.row_a.assign(back.begin(), back.begin() + cap);
+    out.row_b.assign(back.begin() + cap, back.begin() + 2 * cap);
+    const uint8_t *t = back.data() + 2 * cap;
+    memcpy(&out.clen, t, 4); memcpy(&out.overlap, t + 4, 4); memcpy(&out.gaps, t + 8, 4); memcpy(&out.mism, t + 12, 4);
+    memcpy(&out.alen, t + 16, 4); memcpy(&out.score, t + 24, 8);
+    out.status = t[32];
+    return MOIRA_OK;
+}
+
+int moira_nw_align(moira_ctx *c, const char *seq_1, const char *seq_2, int match, int mismatch, int gap, char *aligned_1,
+                   char *aligned_2, uint64_t *aligned_len, int64_t *score)
+{
+    if (!c || !seq_1 || !seq_2 || !aligned_1 || !aligned_2 || !aligned_len) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const std::string f(seq_1), r(seq_2);
+    aligned_1[0] = aligned_2[0] = 0;
+    *aligned_len = 0;
+    if (score) *score = 0;
+    if (f.empty() || r.empty()) {   // a matrix of one row / column: the other sequence against gaps, all cells 0
+        const size_t n = f.size() + r.size();
+        for (size_t k = 0; k < n; k++) { aligned_1[k] = f.empty() ? '-' : f[k]; aligned_2[k] = r.empty() ? '-' : r[k]; }
+        aligned_1[n] = aligned_2[n] = 0;
+        *aligned_len = n;
+        return MOIRA_OK;
+    }
+    moira_contig_params p;
+    moira_contig_params_default(&p);
+    p.match = match; p.mismatch = mismatch; p.gap = gap;
+    ContigArgs a;
+    fill_contig_args(a, c, &p, 0);
+    const std::vector<uint8_t> q1(f.size(), 0), q2(r.size(), 0);
+    SingleOut out;
+    const int rc = single_pair(c, a, f, q1, r, q2, true, out);
+    if (rc) return rc;
+    memcpy(aligned_1, out.row_a.data(), out.alen);
+    memcpy(aligned_2, out.row_b.data(), out.alen);
+    aligned_1[out.alen] = aligned_2[out.alen] = 0;
+    *aligned_len = (uint64_t)out.alen;
+    if (score) *score = out.score;
+    return MOIRA_OK;
+}
+
+int moira_make_contig(moira_ctx *c, const char *fwd_aligned, const int32_t *fwd_quals, uint64_t n_fq, const char *rev_aligned,
+                      const int32_t *rev_quals, uint64_t n_rq, const moira_contig_params *p, char *contig, int32_t *contig_quals,
+                      uint64_t *contig_len, int32_t *overlap, int32_t *gaps, int32_t *mismatches)
+{
+    if (!c || !fwd_aligned || !rev_aligned || (!fwd_quals && n_fq) || (!rev_quals && n_rq) || !contig || !contig_quals || !contig_len)
+        return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    int rc = check_contig_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    const std::string a1(fwd_aligned), a2(rev_aligned);
+    if (a1.size() != a2.size()) return fail(MOIRA_ERR_LENGTH_MISMATCH, "aligned sequences differ in length");
+    std::string f, r;
+    for (char ch : a1) if (ch != '-') f.push_back(ch);
+    for (char ch : a2) if (ch != '-') r.push_back(ch);
+    if (f.size() != n_fq || r.size() != n_rq) return fail(MOIRA_ERR_LENGTH_MISMATCH, "LengthMismatchError");   // moira.py:1407-1410
+    std::vector<uint8_t> q1(n_fq), q2(n_rq);
+    for (uint64_t k = 0; k < n_fq; k++) {
+        if (fwd_quals[k] < 0 || fwd_quals[k] > 0xFC) return fail(MOIRA_ERR_BAD_QUALITY, "quality %d is outside 0..252", fwd_quals[k]);
+        q1[k] = (uint8_t)fwd_quals[k];
+    }
+    for (uint64_t k = 0; k < n_rq; k++) {
+        if (rev_quals[k] < 0 || rev_quals[k] > 0xFC) return fail(MOIRA_ERR_BAD_QUALITY, "quality %d is outside 0..252", rev_quals[k]);
+        q2[k] = (uint8_t)rev_quals[k];
+    }
+    *contig_len = 0;
+    contig[0] = 0;
+    if (overlap) *overlap = 0;
+    if (gaps) *gaps = 0;
+    if (mismatches) *mismatches = 0;
+    if (a1.empty()) return MOIRA_OK;
+    if (f.empty() || r.empty()) return fail(MOIRA_ERR_BAD_ARG, "an aligned sequence holds gaps only");
+    if (a1.size() > f.size() + r.size()) return fail(MOIRA_ERR_BAD_ARG, "alignment has columns that are gaps in both sequences");
+    if (p->consensus == MOIRA_CONSENSUS_POSTERIOR && (rc = ensure_post_tables(c))) return rc;
+    ContigArgs a;
+    fill_contig_args(a, c, p, 0);
+    if ((rc = ensure(c->pb[0].rseq, 2 * a1.size() + 64))) return rc;       // the aligned strings
+    CU(cudaMemcpy(c->pb[0].rseq.p, a1.data(), a1.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy((char *)c->pb[0].rseq.p + a1.size(), a2.data(), a2.size(), cudaMemcpyHostToDevice));
+    a.pre_a1 = (const char *)c->pb[0].rseq.p;
+    a.pre_a2 = a.pre_a1 + a1.size();
+    a.pre_len = (int32_t)a1.size();
+    SingleOut out;
+    rc = single_pair(c, a, f, q1, r, q2, false, out);
+    if (rc) return rc;
+    if (out.status == MOIRA_PAIR_BAD_QUALITY) return fail(MOIRA_ERR_BAD_QUALITY, "a consensus quality is outside 0..252");
+    if (out.status != MOIRA_PAIR_OK) return fail(MOIRA_ERR_BAD_ARG, "contig construction failed (pair status %d)", out.status);
+    memcpy(contig, out.row_a.data(), out.clen);
+    contig[out.clen] = 0;
+    for (uint32_t k = 0; k < out.clen; k++) contig_quals[k] = out.row_b[k] > 0xFC ? (int32_t)out.row_b[k] - 256 : out.row_b[k];
+    *contig_len = out.clen;
+    if (overlap) *overlap = out.overlap;
+    if (gaps) *gaps = out.gaps;
+    if (mismatches) *mismatches = out.mism;
     return MOIRA_OK;
 }
 

@@ -562,7 +562,7 @@ extern "C" int moira_parse_fasta_qual(const char *fasta, uint64_t fasta_bytes, c
                     if (nq < slen) {
                         const char ch = fasta[sb + nq];
                         const uint8_t qv = v <= 0 ? 0 : (v > 0xFC ? 0xFC : (uint8_t)v);
-                        if (qrow) qrow[nq] = v <= 0 ? 1 : (v > 255 ? 255 : (uint8_t)v);   // what process_data writes back (moira.py:814)
+                        if (qrow) qrow[nq] = v <= 0 ? 0 : (v > 255 ? 255 : (uint8_t)v);
                         if (ch == 'N') row[nq] = 0xFF;
                         else if (ch == 'n' && lower_n_ambiguous) row[nq] = 0xFE;
                         else { row[nq] = qv; bad_q |= v > 0xFC; }

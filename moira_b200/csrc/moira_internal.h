@@ -109,6 +109,37 @@ int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, do
 int kernels_init(int sm_count);  // sets function attributes (dynamic smem opt-in)
 int max_first_pass_k();
 
+// ---- paired-end contig construction (moira_contig.cu) ------------------------------------------------
+struct ContigArgs {
+    const char *fseq; const uint8_t *fqual; const uint64_t *foff, *fqoff; const uint32_t *flen;   // forward reads
+    const char *rseq; const uint8_t *rqual; const uint64_t *roff, *rqoff; const uint32_t *rlen;   // reverse reads
+    int32_t qual_base;               // quality = byte - qual_base
+    uint64_t n_pairs;
+    int32_t match, mismatch, gap, insert, deltaq, consensus, qscore_cap, trim_overlap, lower_n;
+    int32_t rev_direct;              // 1: the reverse read is already reverse-complemented (single-pair entry points)
+    const int16_t *post_match;       // [256 * 256] posterior consensus quality of two agreeing bases (host glibc)
+    const int16_t *post_mis;         // [256 * 256] ... of the better of two disagreeing bases, index [hi * 256 + lo]
+    uint32_t *trace;                 // per-warp traceback pointer buffers
+    uint64_t trace_words_per_warp;
+    int32_t *hbuf;                   // score matrix (only for the nw_align entry point)
+    const char *pre_a1, *pre_a2;     // make_contig entry point: the alignment is given
+    int32_t pre_len;
+    char *al1, *al2;                 // nw_align entry point: aligned strings, length, path score
+    int32_t *alen;
+    long long *score;
+    uint64_t out_stride;
+    char *cseq; uint8_t *cqual; uint8_t *slab;
+    uint32_t *clen; int32_t *overlap, *gaps, *mism; uint8_t *status;
+    uint32_t max_l1, max_l2;         // longest forward / reverse read of the batch
+    uint32_t smem_s1, smem_per_warp; // filled by launch_contigs
+};
+int contig_columns_per_lane(uint32_t max_l2);                         // 0: reverse reads too long
+size_t contig_trace_words_per_warp(uint32_t max_l1, uint32_t max_l2);
+size_t contig_hbuf_words(uint32_t max_l1, uint32_t max_l2);
+int contig_grid(int sm_count, uint64_t n_pairs, int warps);
+constexpr int CONTIG_WARPS_PER_CTA = 16;
+int launch_contigs(ContigArgs a, bool want_score, const LaunchCfg &cfg);   // 0 ok, -1 CUDA error, -2 unsupported size
+
 // moira_parse_fastq with the number of text bytes consumed (moira_host.cpp)
 int parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous, uint8_t *slab,
                       uint64_t slab_capacity, uint64_t *out_offsets, uint32_t *lengths, uint64_t *hdr_off,

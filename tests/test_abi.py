@@ -252,7 +252,7 @@ def test_parse_fasta_qual_matches_oracle_parser(forward_records):
     for i in (0, 3, 500, 999):
         assert fa[int(hoff[i]):int(hoff[i]) + int(hlen[i])].decode().replace(":", "_") == recs[i][0]
         assert fa[int(soff[i]):int(soff[i]) + int(ln[i])].decode() == recs[i][1]
-        assert list(qslab[int(off[i]):int(off[i]) + int(ln[i])]) == [v if v > 0 else 1 for v in recs[i][2]]
+        assert list(qslab[int(off[i]):int(off[i]) + int(ln[i])]) == [max(v, 0) for v in recs[i][2]]
 
 
 def test_parse_fasta_qual_errors_and_threads():
@@ -267,7 +267,7 @@ def test_parse_fasta_qual_errors_and_threads():
         P(b">a\nAC\n", b">a\n7 300\n")
     assert ei.value.code == L.ERR_BAD_QUALITY
     slab, qslab, off, ln, *_ = P(b">r1 d\n ANnT \n>r2\nC", b">r1\n 40\t0  -3 12\n>r2\n9\n\n")
-    assert list(ln) == [4, 1] and list(slab[:4]) == [40, 0xFF, 0xFE, 12] and slab[16] == 9 and list(qslab[:4]) == [40, 1, 1, 12]
+    assert list(ln) == [4, 1] and list(slab[:4]) == [40, 0xFF, 0xFE, 12] and slab[16] == 9 and list(qslab[:4]) == [40, 0, 0, 12]
     assert list(P(b">r\nAn\n", b">r\n5 6\n", False)[0][:2]) == [5, 6]
     # parallel path (>= 1 MB): identical rows for any thread count, and the first bad record is the one reported
     rng = np.random.default_rng(5)
@@ -286,7 +286,7 @@ def test_parse_fasta_qual_errors_and_threads():
         assert all(np.array_equal(x, y) for x, y in zip(outs[0][3:], other[3:]))
         assert all(np.array_equal(x, y) for x, y in zip(rows(outs[0], 0), rows(other, 0)))
         assert all(np.array_equal(x, y) for x, y in zip(rows(outs[0], 1), rows(other, 1)))
-    assert [list(r) for r in rows(outs[2], 1)[:50]] == [[max(v, 1) for v in q] for _, _, q in recs[:50]]
+    assert [list(r) for r in rows(outs[2], 1)[:50]] == [[max(v, 0) for v in q] for _, _, q in recs[:50]]
     bad = list(recs)
     bad[3210] = ("r3210", "ACGT", [1, 2, 3])
     fa, qu = _fasta_qual_text(bad)

@@ -40,7 +40,15 @@ def test_argument_surface_matches_reference_defaults():
     buf = io.StringIO()
     assert cli.check_arguments(cli.parse_arguments(["-ffq", "x", "-a", "1.5"]), buf) is False
     assert "alpha parameter must be between 0" in buf.getvalue()
-    assert cli.check_arguments(cli.parse_arguments(["-ffq", "x", "--paired"]), io.StringIO()) is False
+    buf = io.StringIO()
+    assert cli.check_arguments(cli.parse_arguments(["-ffq", "x", "--paired"]), buf) is False        # moira.py:701-705
+    assert "You must provide one reverse fastq file" in buf.getvalue()
+    a = cli.parse_arguments(["-ffq", "x", "-rfq", "y", "--only_contig"])
+    assert cli.check_arguments(a, io.StringIO()) is True and a.paired is True                        # moira.py:695-696
+    assert (a.match, a.mismatch, a.gap, a.insert, a.deltaq, a.consensus_qscore, a.qscore_cap, a.trim_overlap) == \
+        (1, -1, -2, 20, 6, "best", 40, False)                                                        # moira.py:629-646
+    for bad in (["-m", "-1"], ["-x", "1"], ["-g", "1"], ["-i", "0"], ["-d", "0"], ["-mo", "0"]):
+        assert cli.check_arguments(cli.parse_arguments(["-ffq", "x", "-rfq", "y", "--paired"] + bad), io.StringIO()) is False
     assert cli.check_arguments(cli.parse_arguments([]), io.StringIO()) is False
 
 
@@ -132,3 +140,68 @@ def test_fasta_qual_input_reclassifies_golden_contigs(tmp_path, contigs):
         bad_q = tmp_path / "bad.qual"
         bad_q.write_text(open(qu).read().replace(contigs[3]["header"], "someone_else", 1))
         cli.run(["-ff", str(fa), "-fq", str(bad_q), "-op", prefix, "--silent"])
+
+
+@pytest.mark.gpu
+def test_paired_dataset_outputs_match_goldens(tmp_path, contigs, paired_names):
+    """test_moira.py:88-101 (testProcessPairedDataset) and :102-113 (testCompression: gz forward + bz2 reverse input):
+    read pairs -> contigs on the device -> filter -> collapse -> the golden paired.qc.* records and names."""
+    prefix = str(tmp_path / "paired")
+    assert cli.run(["-ffq", os.path.join(GOLDEN, "test1.fastq.gz"), "-rfq", os.path.join(GOLDEN, "test2.fastq.bz2"), "--paired",
+                    "-op", prefix, "--silent"]) == 0
+    want = {"good": {}, "bad": {}}
+    for c in contigs:
+        line = ">%s%s" % (c["header"], "\t" + c["reason"] if c["reason"] else "")
+        want[c["label"]][line] = (c["seq"], " ".join(map(str, c["quals"])))
+    for lab in ("good", "bad"):
+        fa = _records("%s.qc.%s.fasta" % (prefix, lab))
+        qu = _records("%s.qc.%s.qual" % (prefix, lab))
+        assert set(fa) == set(want[lab]) == set(qu)
+        for hdr, (seq, qual) in want[lab].items():
+            assert fa[hdr] == seq and qu[hdr] == qual
+        assert _names("%s.qc.%s.names" % (prefix, lab)) == paired_names[lab]
+    report = open(prefix + ".contigs.report").read().splitlines()
+    assert report[0] == "header\tn_seqs\toverlap_length\tgaps\tmismatches" and len(report) == 401
+    assert sum(int(line.split("\t")[1]) for line in report[1:]) == 1000
+
+
+@pytest.mark.gpu
+def test_paired_options_only_contig_min_overlap_and_fasta_qual_input(tmp_path, oracle_contigs, forward_records, reverse_records):
+    f1, f2 = os.path.join(GOLDEN, "test1.fastq.gz"), os.path.join(GOLDEN, "test2.fastq.bz2")
+    by_header = {h: (c, q, ov) for h, c, q, ov, _, _ in oracle_contigs}
+    # --only_contig, no collapse: every contig is written to the good files, unfiltered (moira.py:900-908)
+    pre = str(tmp_path / "oc")
+    assert cli.run(["-ffq", f1, "-rfq", f2, "--only_contig", "-c", "False", "-op", pre, "--silent"]) == 0
+    fa, qu = _records(pre + ".qc.good.fasta"), _records(pre + ".qc.good.qual")
+    assert len(fa) == 1000 and not open(pre + ".qc.bad.fasta").read()
+    for h, (c, q, _) in by_header.items():
+        assert fa[">" + h] == c and qu[">" + h] == " ".join(str(max(v, 1)) for v in q)
+    # --min_overlap: contigs whose reads overlap by less are rejected with the reference's note (moira.py:886-897)
+    cut = sorted(ov for _, _, ov in by_header.values())[100]
+    pre = str(tmp_path / "mo")
+    assert cli.run(["-ffq", f1, "-rfq", f2, "--paired", "-c", "False", "-mo", str(cut), "-op", pre, "--silent"]) == 0
+    bad = _records(pre + ".qc.bad.fasta")
+    short = {h for h, (_, _, ov) in by_header.items() if ov < cut}
+    assert {k[1:].split("\t")[0] for k in bad if "overlap length below %d" % cut in k} == short and len(short) >= 50
+    # the same pairs as fasta + qual files give the same contigs
+    names = {}
+    for tag, recs in (("f", forward_records), ("r", reverse_records)):
+        names[tag] = (str(tmp_path / (tag + ".fasta")), str(tmp_path / (tag + ".qual")))
+        with open(names[tag][0], "w") as fa_fh, open(names[tag][1], "w") as qu_fh:
+            for h, s_, q in recs[:200]:
+                fa_fh.write(">%s\n%s\n" % (h, s_))
+                qu_fh.write(">%s\n%s\n" % (h, " ".join(map(str, q))))
+    pre = str(tmp_path / "fq")
+    assert cli.run(["-ff", names["f"][0], "-fq", names["f"][1], "-rf", names["r"][0], "-rq", names["r"][1], "--only_contig",
+                    "-c", "False", "-op", pre, "--silent"]) == 0
+    fa = _records(pre + ".qc.good.fasta")
+    assert len(fa) == 200
+    for h, _, _ in forward_records[:200]:
+        assert fa[">" + h] == by_header[h][0]
+    # mismatching headers between the two files
+    swapped = tmp_path / "swapped.fastq"
+    raw = bz2.open(f2, "rb").read().split(b"\n")
+    raw[4], raw[0] = raw[0], raw[4]
+    swapped.write_bytes(b"\n".join(raw))
+    with pytest.raises(cli.NameMismatchError):
+        cli.run(["-ffq", f1, "-rfq", str(swapped), "--paired", "-op", str(tmp_path / "x"), "--silent"])
