@@ -182,7 +182,7 @@ def test_paired_options_only_contig_min_overlap_and_fasta_qual_input(tmp_path, o
     assert cli.run(["-ffq", f1, "-rfq", f2, "--paired", "-c", "False", "-mo", str(cut), "-op", pre, "--silent"]) == 0
     bad = _records(pre + ".qc.bad.fasta")
     short = {h for h, (_, _, ov) in by_header.items() if ov < cut}
-    assert {k[1:].split("\t")[0] for k in bad if "overlap length below %d" % cut in k} == short and len(short) >= 50
+    assert {k[1:].split("\t")[0] for k in bad if "overlap length below %d" % cut in k} == short and len(short) >= 20
     # the same pairs as fasta + qual files give the same contigs
     names = {}
     for tag, recs in (("f", forward_records), ("r", reverse_records)):
