@@ -329,6 +329,8 @@ MOIRA_API int moira_ctx_launch_count(const moira_ctx *ctx, uint64_t *out);
  * measured with CUDA events on the stream the kernel was launched on. */
 MOIRA_API int moira_ctx_set_timing(moira_ctx *ctx, int enabled);
 MOIRA_API int moira_ctx_last_kernel_ms(moira_ctx *ctx, float *ms_out, const char **name_out);
+/* The same for the contig kernel launches of moira_filter_pairs since moira_ctx_set_timing(ctx, 1). */
+MOIRA_API int moira_ctx_last_contig_ms(moira_ctx *ctx, float *ms_out, int *launches_out);
 
 #ifdef __cplusplus
 }

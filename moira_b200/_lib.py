@@ -36,7 +36,7 @@ EXPORTS = [
     "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_filter_batch",
     "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads", "moira_pack_q6",
     "moira_parse_fastq", "moira_parse_fasta_qual", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
-    "moira_ctx_last_kernel_ms", "moira_contig_params_default", "moira_filter_pairs", "moira_nw_align", "moira_make_contig",
+    "moira_ctx_last_kernel_ms", "moira_ctx_last_contig_ms", "moira_contig_params_default", "moira_filter_pairs", "moira_nw_align", "moira_make_contig",
 ]
 
 
@@ -104,6 +104,7 @@ lib.moira_set_host_threads.argtypes = [_i]
 lib.moira_fp64_peak.argtypes = [_vp, _i, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
 lib.moira_ctx_launch_count.argtypes = [_vp, ctypes.POINTER(_u64)]
 lib.moira_ctx_set_timing.argtypes = [_vp, _i]
+lib.moira_ctx_last_contig_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i)]
 lib.moira_ctx_last_kernel_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p)]
 _cpp = ctypes.POINTER(ContigParams)
 lib.moira_contig_params_default.restype = None

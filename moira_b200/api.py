@@ -97,6 +97,25 @@ class PairResult:
     mismatches: np.ndarray
     status: np.ndarray         # uint8[n], L.PAIR_*
     filter: "FilterResult | None" = None
+    _pinned: object = None
+
+    @staticmethod
+    def allocate(n: int, stride: int, with_filter: bool, pinned: bool = False) -> "PairResult":
+        """Output arrays for n pairs; pinned=True puts the two big contig arrays in page-locked memory (faster D2H,
+        worth it when the result object is reused across calls)."""
+        if pinned:
+            keep = [PinnedBuffer(max(1, n * stride)), PinnedBuffer(max(1, n * stride))]
+            seq, qual = keep[0].u8[:n * stride].reshape(n, stride), keep[1].u8[:n * stride].reshape(n, stride)
+        else:
+            keep = None
+            seq, qual = np.zeros((n, stride), np.uint8), np.zeros((n, stride), np.uint8)
+        res = PairResult(seq, qual, np.zeros(n, np.uint32), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32),
+                         np.zeros(n, np.uint8))
+        res._pinned = keep
+        if with_filter:
+            res.filter = FilterResult(np.zeros(n, np.float64), np.zeros(n, np.int32), np.zeros(n, np.uint8),
+                                      np.zeros(L.N_COUNTERS, np.uint64))
+        return res
 
     def contig(self, r: int):
         n = int(self.contig_len[r])
@@ -221,6 +240,12 @@ class Context:
         L.check(lib.moira_ctx_last_kernel_ms(self._h, ctypes.byref(ms), ctypes.byref(name)))
         return ms.value, (name.value or b"").decode()
 
+    def last_contig_ms(self):
+        ms = ctypes.c_float()
+        n = ctypes.c_int()
+        L.check(lib.moira_ctx_last_contig_ms(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
     def fp64_peak(self, iters: int = 20000):
         ops = ctypes.c_double()
         ms = ctypes.c_double()
@@ -281,7 +306,8 @@ class Context:
 
     def filter_pairs(self, fwd_seq, fwd_qual, fwd_off, fwd_len, rev_seq, rev_qual, rev_off, rev_len,
                      contig_params: ContigParams, filter_params: FilterParams | None = None,
-                     lower_n_ambiguous: bool = True, fwd_qual_off=None, rev_qual_off=None, qual_base: int = 0) -> PairResult:
+                     lower_n_ambiguous: bool = True, fwd_qual_off=None, rev_qual_off=None, qual_base: int = 0,
+                     out: "PairResult | None" = None) -> PairResult:
         """Read pairs -> contigs (and, with filter_params, the filter on them) in one C call (moira_filter_pairs).
         *_seq: uint8 ASCII bases at [off[r], off[r] + len[r]); *_qual: uint8 qualities (+ qual_base) at
         [qual_off[r], ...) (qual_off None: same offsets).  Passing the FASTQ text as both arrays with the parser's
@@ -297,16 +323,15 @@ class Context:
             raise ValueError("offset / length arrays of the two files differ in size")
         mx = (int(fwd_len.max()) if n else 0) + (min(int(rev_len.max()), 1024) if n else 0)
         stride = max(16, (mx + 15) // 16 * 16)
-        res = PairResult(np.zeros((n, stride), np.uint8), np.zeros((n, stride), np.uint8), np.zeros(n, np.uint32),
-                         np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8))
+        if out is not None:
+            if out.contig_seq.shape != (n, stride) or (filter_params is not None) != (out.filter is not None):
+                raise ValueError("`out` was allocated for another batch shape")
+            res = out
+        else:
+            res = PairResult.allocate(n, stride, filter_params is not None)
         cp = contig_params.to_c()
-        fr = None
-        fp = None
-        if filter_params is not None:
-            fp = filter_params.to_c()
-            fr = FilterResult(np.zeros(n, np.float64), np.zeros(n, np.int32), np.zeros(n, np.uint8),
-                              np.zeros(L.N_COUNTERS, np.uint64))
-            res.filter = fr
+        fp = filter_params.to_c() if filter_params is not None else None
+        fr = res.filter
         L.check(lib.moira_filter_pairs(
             self._h, _ptr(fwd_seq), fwd_seq.nbytes, _ptr(fwd_qual), fwd_qual.nbytes, _ptr(fwd_off), _ptr(fwd_qual_off),
             _ptr(fwd_len), _ptr(rev_seq), rev_seq.nbytes, _ptr(rev_qual), rev_qual.nbytes, _ptr(rev_off), _ptr(rev_qual_off),

@@ -133,6 +133,8 @@ struct moira_ctx {
     PairBufs pb[2];
     DevBuf trace, hbuf, post, pair_counters;
     bool post_ready = false;
+    cudaEvent_t ct0[MAX_TIMED] = {}, ct1[MAX_TIMED] = {};   // around the contig kernel launches when timing is on
+    int n_ctimed = 0;
     // single-read scratch (pinned)
     uint8_t *one_slab = nullptr;
     size_t one_cap = 0;
@@ -464,6 +466,7 @@ static int ctx_init(moira_ctx *c, int device, int sm_count)
     for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->meta_ready, cudaEventDisableTiming));
     for (int i = 0; i < MAX_TIMED; i++) { CU(cudaEventCreate(&c->t0[i])); CU(cudaEventCreate(&c->t1[i])); }
+    for (int i = 0; i < MAX_TIMED; i++) { CU(cudaEventCreate(&c->ct0[i])); CU(cudaEventCreate(&c->ct1[i])); }
     for (auto &t : c->tickets)
         for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&t.done[i], cudaEventDisableTiming));
     return MOIRA_OK;
@@ -493,6 +496,8 @@ int moira_ctx_destroy(moira_ctx *c)
     for (int i = 0; i < MAX_TIMED; i++) {
         if (c->t0[i]) cudaEventDestroy(c->t0[i]);
         if (c->t1[i]) cudaEventDestroy(c->t1[i]);
+        if (c->ct0[i]) cudaEventDestroy(c->ct0[i]);
+        if (c->ct1[i]) cudaEventDestroy(c->ct1[i]);
     }
     if (c->meta_ready) cudaEventDestroy(c->meta_ready);
     for (int i = 0; i < 2; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -996,8 +1001,11 @@ int moira_filter_pairs(moira_ctx *c, const char *fwd_seq, uint64_t fwd_bytes, co
         a.status = (uint8_t *)b.status.p;
         a.max_l1 = max_l1; a.max_l2 = max_l2;
         LaunchCfg cfg{c->sm_count, s};
+        const bool ctimed = c->timing && c->n_ctimed < MAX_TIMED;
+        if (ctimed) CU(cudaEventRecord(c->ct0[c->n_ctimed], s));
         const int lr = launch_contigs(a, false, cfg);
         if (lr) return fail(lr == -2 ? MOIRA_ERR_BAD_ARG : MOIRA_ERR_CUDA, "contig kernel launch failed: %s", lr == -2 ? "reads too long" : cudaGetErrorString(cudaGetLastError()));
+        if (ctimed) { CU(cudaEventRecord(c->ct1[c->n_ctimed], s)); c->n_ctimed++; }
         c->launches++;
         if (fp) {
             const uint32_t cap = (uint32_t)std::min<uint64_t>(out_stride, 0xFFFFFFF0u);
@@ -1212,6 +1220,22 @@ int moira_ctx_set_timing(moira_ctx *c, int enabled)
     if (!c) return fail(MOIRA_ERR_BAD_ARG, "ctx is NULL");
     c->timing = enabled ? 1 : 0;
     c->n_timed = 0;
+    c->n_ctimed = 0;
+    return MOIRA_OK;
+}
+
+int moira_ctx_last_contig_ms(moira_ctx *c, float *ms_out, int *launches_out)
+{
+    if (!c || !ms_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    float total = 0;
+    for (int i = 0; i < c->n_ctimed; i++) {
+        CU(cudaEventSynchronize(c->ct1[i]));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ct0[i], c->ct1[i]));
+        total += ms;
+    }
+    *ms_out = total;
+    if (launches_out) *launches_out = c->n_ctimed;
     return MOIRA_OK;
 }
 

@@ -11,7 +11,7 @@
 // its columns.  Lane l of the warp owns the C columns [l C + 1, l C + C] and walks down the rows one step
 // behind lane l - 1 (a skewed wavefront): at step t it fills row t - l + 1 of its strip from registers
 // (the strip's previous row) plus one boundary value handed over by a shuffle.  Per step the warp stores
-// ONE coalesced 128-byte line of 2-bit traceback pointers (word [t][lane]) to a per-warp trace buffer in
+// ONE coalesced 128-byte line of traceback bits (word [t][lane]: a 'diagonal' and an 'up' bit per cell) to a per-warp trace buffer in
 // global memory (L2-resident: it is rewritten for every pair).  The traceback then walks the path with the
 // trace staged through a 32-row window in shared memory, and the consensus runs over the aligned positions
 // 32 at a time with ballot-compacted output.  Integer work only, except the posterior quality tables, which
@@ -110,6 +110,7 @@ __device__ int pair_to_contig(const ContigArgs &a, uint64_t pair, const PairView
         int bc = 0, bci = 0;                             // best of the last column so far; row 0 holds 0
         int br = lane == 0 ? 0 : INT_MIN, bri = lane == 0 ? 0 : -1;   // best of the last row; column 0 holds 0
         const int steps = L1 + nl - 1;
+        const int sub_eq = a.match, sub_ne = a.mismatch, gap = a.gap;
         for (int t = 0; t < steps; t++) {
             const int i = t - lane + 1;
             const int lb_in = __shfl_up_sync(FULL, hlast, 1);
@@ -117,32 +118,38 @@ __device__ int pair_to_contig(const ContigArgs &a, uint64_t pair, const PairView
             if (i >= 1 && i <= L1 && lane < nl) {
                 const int ch = (uint8_t)s1[i - 1];
                 int left = lb, diagp = lb_prev;
-                uint64_t ptr = 0;
+                // One bit per cell and mask instead of a 2-bit code: D = the diagonal wins (it wins every tie,
+                // nw_align.pyx:96-97), U = up beats left (ties to up, :107).  h = max(d, max(up, left) + gap).
+                uint32_t mask_d = 0, mask_u = 0;
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    const int d = diagp + (ch == s2c[c] ? a.match : a.mismatch);   // nw_align.pyx:88-91
-                    const int u = hprev[c] + a.gap;
-                    const int l = left + a.gap;
-                    int h, code;                                                    // nw_align.pyx:96-116
-                    if (d >= u) {
-                        if (d >= l) { h = d; code = 0; } else { h = l; code = 2; }
-                    } else {
-                        if (u >= l) { h = u; code = 1; } else { h = l; code = 2; }
-                    }
-                    diagp = hprev[c];
+                    const int d = diagp + (ch == s2c[c] ? sub_eq : sub_ne);          // nw_align.pyx:88-91
+                    const int up = hprev[c];
+                    const int h = __viaddmax_s32(max(up, left), gap, d);
+                    if (h == d) mask_d |= 1u << c;
+                    if (up >= left) mask_u |= 1u << c;
+                    diagp = up;
                     hprev[c] = h;
                     left = h;
-                    ptr |= (uint64_t)code << (2 * c);
                     if (SCORE) hbuf[((size_t)t * 32 + lane) * C + c] = h;
-                    if (lane == lc && c == c_last && h >= bc) { bc = h; bci = i; }   // nw_align.pyx:169-173
-                    if (i == L1 && lane * C + c + 1 <= L2 && h >= br) { br = h; bri = lane * C + c + 1; }   // :177-181
                 }
                 hlast = left;
                 lb_prev = lb;
-                if (C <= 16) trace[(size_t)t * 32 + lane] = (uint32_t)ptr;
+                if (C <= 16) trace[(size_t)t * 32 + lane] = mask_d | (mask_u << 16);
                 else {
-                    trace[((size_t)t * 2) * 32 + lane] = (uint32_t)ptr;
-                    trace[((size_t)t * 2 + 1) * 32 + lane] = (uint32_t)(ptr >> 32);
+                    trace[((size_t)t * 2) * 32 + lane] = mask_d;
+                    trace[((size_t)t * 2 + 1) * 32 + lane] = mask_u;
+                }
+                if (lane == lc) {                        // last column: ">=" keeps the last of equal scores (nw_align.pyx:169-173)
+                    int h = hprev[0];
+#pragma unroll
+                    for (int c = 1; c < C; c++) if (c == c_last) h = hprev[c];
+                    if (h >= bc) { bc = h; bci = i; }
+                }
+                if (i == L1) {                           // last row, once per lane (nw_align.pyx:177-181)
+#pragma unroll
+                    for (int c = 0; c < C; c++)
+                        if (lane * C + c + 1 <= L2 && hprev[c] >= br) { br = hprev[c]; bri = lane * C + c + 1; }
                 }
             }
         }
@@ -178,8 +185,14 @@ __device__ int pair_to_contig(const ContigArgs &a, uint64_t pair, const PairView
                     }
                     __syncwarp();
                 }
-                const uint32_t word = W == 1 ? win[(t - wlo) * 32 + l] : win[((t - wlo) * 2 + (c >= 16)) * 32 + l];
-                code = (word >> (2 * (c & 15))) & 3;
+                uint32_t dbit, ubit;
+                if (W == 1) {
+                    const uint32_t word = win[(t - wlo) * 32 + l];
+                    dbit = (word >> c) & 1u; ubit = (word >> (16 + c)) & 1u;
+                } else {
+                    dbit = (win[((t - wlo) * 2) * 32 + l] >> c) & 1u; ubit = (win[((t - wlo) * 2 + 1) * 32 + l] >> c) & 1u;
+                }
+                code = dbit ? 0 : (ubit ? 1 : 2);
             }
             if (SCORE && i > 0 && j > 0) score += hbuf[((size_t)(i - 1 + (j - 1) / C) * 32 + (j - 1) / C) * C + (j - 1) % C];
             if (lane == 0) {
