@@ -381,6 +381,39 @@ def run_ours(args):
                      "api": "moira_filter_fastq: FASTQ text in host memory -> parse ranges on all host threads -> pinned slabs -> async submits"}
         del text
 
+    # ---- the step before the filter when reads come in pairs: contig construction, N = 1 only ----
+    contigs = None
+    if world == 1 and not args.no_e2e:
+        from tools.bench_contigs import make_pairs
+        from moira_b200 import ContigParams, PairResult, PinnedBuffer
+        np_pairs, rl = 1 << 18, 251
+        pf, pr_ = make_pairs(np_pairs, rl)
+        keep = []
+
+        def _pin(arr):
+            pb = PinnedBuffer(arr.nbytes)
+            keep.append(pb)
+            v = pb.view(arr.dtype, arr.size)
+            v[:] = arr
+            return v
+
+        pf = (_pin(pf[0]), _pin(pf[1]), pf[2], pf[3])
+        pr_ = (_pin(pr_[0]), _pin(pr_[1]), pr_[2], pr_[3])
+        pout = PairResult.allocate(np_pairs, (2 * rl + 15) // 16 * 16, True, pinned=True)
+        ctx.filter_pairs(*pf, *pr_, ContigParams(), p_dec, out=pout)
+        ctx.set_timing(True)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.filter_pairs(*pf, *pr_, ContigParams(), p_dec, out=pout)
+        dtp = (time.perf_counter() - t0) / 3
+        cms, claunches = ctx.last_contig_ms()
+        ctx.set_timing(False)
+        contigs = {"kernel": {"value": np_pairs / (cms / 3 * 1e-3), "unit": "pairs/s", "cells_per_s": np_pairs * rl * rl / (cms / 3 * 1e-3)},
+                   "e2e": {"value": np_pairs / dtp, "unit": "pairs/s"},
+                   "workload": "%d synthetic 2 x %d bp MiSeq V4 pairs -> contigs -> filter (moira_filter_pairs); details: tools/bench_contigs.py, profiles/r01_contigs.json" % (np_pairs, rl),
+                   "contig_kernel_launches_per_step": claunches / 3, "bad_pairs": int(np.count_nonzero(pout.status))}
+        del pf, pr_, pout, keep
+
     # ---- CPU baseline: the reference's own C core on this box's host cores (rank 0, N = 1) ------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -436,7 +469,7 @@ def run_ours(args):
                        "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU, NCCL all-reduce of 80 counters per step",
                        "rank_cpu_affinity": numa_cpus},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "parity": parity, "modes": modes, "e2e_parse": e2e_parse,
+            "clocks": sampler.summary(), "parity": parity, "modes": modes, "e2e_parse": e2e_parse, "contigs": contigs,
             "exact_ee": {"value": value_exact, "unit": "reads/s", "note": "exact statistic for every read (escalation ladder), device-resident"},
         }
         print(json.dumps(line))
