@@ -111,6 +111,7 @@ __device__ int pair_to_contig(const ContigArgs &a, uint64_t pair, const PairView
         int br = lane == 0 ? 0 : INT_MIN, bri = lane == 0 ? 0 : -1;   // best of the last row; column 0 holds 0
         const int steps = L1 + nl - 1;
         const int sub_eq = a.match, sub_ne = a.mismatch, gap = a.gap;
+#pragma unroll 2
         for (int t = 0; t < steps; t++) {
             const int i = t - lane + 1;
             const int lb_in = __shfl_up_sync(FULL, hlast, 1);
@@ -166,43 +167,59 @@ __device__ int pair_to_contig(const ContigArgs &a, uint64_t pair, const PairView
 
         // ---- traceback (nw_align.pyx:122-143); every lane walks the same path ----
         int i = L1, j = L2, wlo = INT_MAX;
+        int l = (L2 - 1) / C, c = (L2 - 1) % C;          // owner lane and strip column of column j, kept incrementally
         long long score = 0;
-        while (i > 0 || j > 0) {
-            int code;
-            if (j == 0) code = 1;                        // first column points up (nw_align.pyx:75-76)
-            else if (i == 0) code = 2;                   // first row points left (:82-83)
-            else if (mode == 1 && j == L2 && i > bci) code = 1;   // :191-194
-            else if (mode == 2 && i == L1 && j > bri) code = 2;   // :196-199
-            else {
-                const int l = (j - 1) / C, c = (j - 1) % C;
-                const int t = i - 1 + l;
-                if (t < wlo || t > wlo + 31) {           // t never increases along the path
-                    __syncwarp();
-                    wlo = t >= 31 ? t - 31 : 0;
-                    for (int r = 0; r < 32 * W; r++) {
-                        const size_t row = (size_t)wlo * W + r;
-                        win[r * 32 + lane] = row < (size_t)steps * W ? __ldcg(trace + row * 32 + lane) : 0u;
-                    }
-                    __syncwarp();
-                }
-                uint32_t dbit, ubit;
-                if (W == 1) {
-                    const uint32_t word = win[(t - wlo) * 32 + l];
-                    dbit = (word >> c) & 1u; ubit = (word >> (16 + c)) & 1u;
-                } else {
-                    dbit = (win[((t - wlo) * 2) * 32 + l] >> c) & 1u; ubit = (win[((t - wlo) * 2 + 1) * 32 + l] >> c) & 1u;
-                }
-                code = dbit ? 0 : (ubit ? 1 : 2);
+        auto cell_score = [&](int ii, int jj, int ll, int cc) -> long long {
+            return (ii > 0 && jj > 0) ? (long long)hbuf[((size_t)(ii - 1 + ll) * 32 + ll) * C + cc] : 0ll;
+        };
+        // nw_overlap's rewritten cells come first on the path and only there: the last column above the best row
+        // (mode 1, nw_align.pyx:191-194) or the last row right of the best column (mode 2, :196-199)
+        if (mode == 1) {
+            while (i > bci) {
+                if (SCORE) score += cell_score(i, j, l, c);
+                if (lane == 0) { A1[n] = (uint16_t)i; A2[n] = 0; }
+                n++; i--;
             }
-            if (SCORE && i > 0 && j > 0) score += hbuf[((size_t)(i - 1 + (j - 1) / C) * 32 + (j - 1) / C) * C + (j - 1) % C];
+        } else if (mode == 2) {
+            while (j > bri) {
+                if (SCORE) score += cell_score(i, j, l, c);
+                if (lane == 0) { A1[n] = 0; A2[n] = (uint16_t)j; }
+                n++; j--;
+                if (--c < 0) { c = C - 1; l--; }
+            }
+        }
+        while (i > 0 && j > 0) {
+            const int t = i - 1 + l;
+            if (t < wlo) {                               // t never increases along the path
+                __syncwarp();
+                wlo = t >= 31 ? t - 31 : 0;
+                for (int r = 0; r < 32 * W; r++) {
+                    const size_t row = (size_t)wlo * W + r;
+                    win[r * 32 + lane] = row < (size_t)steps * W ? __ldcg(trace + row * 32 + lane) : 0u;
+                }
+                __syncwarp();
+            }
+            bool dbit, ubit;
+            if (W == 1) {
+                const uint32_t word = win[(t - wlo) * 32 + l] >> c;
+                dbit = word & 1u; ubit = word & 0x10000u;
+            } else {
+                dbit = (win[((t - wlo) * 2) * 32 + l] >> c) & 1u; ubit = (win[((t - wlo) * 2 + 1) * 32 + l] >> c) & 1u;
+            }
+            const bool mv_i = dbit || ubit, mv_j = dbit || !ubit;    // diagonal: both; up: i only; left: j only
+            if (SCORE) score += cell_score(i, j, l, c);
             if (lane == 0) {
-                A1[n] = code != 2 ? (uint16_t)i : 0;
-                A2[n] = code != 1 ? (uint16_t)j : 0;
+                A1[n] = mv_i ? (uint16_t)i : 0;
+                A2[n] = mv_j ? (uint16_t)j : 0;
             }
             n++;
-            i -= code != 2;
-            j -= code != 1;
+            if (mv_i) i--;
+            if (mv_j) { j--; if (--c < 0) { c = C - 1; l--; } }
         }
+        // what is left runs along the first column (points up, nw_align.pyx:75-76) or the first row (left, :82-83)
+        for (int k = lane; k < i; k += 32) { A1[n + k] = (uint16_t)(i - k); A2[n + k] = 0; }
+        for (int k = lane; k < j; k += 32) { A1[n + k] = 0; A2[n + k] = (uint16_t)(j - k); }
+        n += i + j;
         __syncwarp();
         if (a.al1) {   // nw_align entry point: hand the aligned strings and the path score back
             for (int p = lane; p < n; p += 32) {
