@@ -26,7 +26,8 @@ namespace moira {
 namespace {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
-constexpr int CONTIG_WARPS = CONTIG_WARPS_PER_CTA;
+// warps per CTA: 28 while the strip is narrow enough for 72 registers per thread, else 16
+__host__ __device__ constexpr int contig_warps(int c) { return c <= 8 ? CONTIG_WARPS_PER_CTA : 16; }
 
 // moira.py:1210-1213; 0 = not an IUPAC code (the reference raises ValueError, moira.py:1228-1229)
 __device__ __forceinline__ int complement_of(int b)
@@ -309,7 +310,7 @@ __device__ int pair_to_contig(const ContigArgs &a, uint64_t pair, const PairView
 }
 
 template <int C, bool SCORE>
-__global__ void __launch_bounds__(CONTIG_WARPS * 32, 1) contig_kernel(const ContigArgs a)
+__global__ void __launch_bounds__(contig_warps(C) * 32, 1) contig_kernel(const ContigArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -387,7 +388,7 @@ int launch_contigs(ContigArgs a, bool want_score, const LaunchCfg &cfg)
     if (!c) return -2;
     a.smem_s1 = (a.max_l1 + 15u) & ~15u;
     a.smem_per_warp = (a.smem_s1 + 4096u * (c <= 16 ? 1 : 2) + 4u * (a.max_l1 + a.max_l2) + 15u) & ~15u;
-    int warps = CONTIG_WARPS;
+    int warps = contig_warps(c);
     while (warps > 1 && (size_t)a.smem_per_warp * warps > 227 * 1024) warps--;
     const size_t smem = (size_t)a.smem_per_warp * warps;
     if (smem > 227 * 1024) return -2;

@@ -137,7 +137,7 @@ int contig_columns_per_lane(uint32_t max_l2);                         // 0: reve
 size_t contig_trace_words_per_warp(uint32_t max_l1, uint32_t max_l2);
 size_t contig_hbuf_words(uint32_t max_l1, uint32_t max_l2);
 int contig_grid(int sm_count, uint64_t n_pairs, int warps);
-constexpr int CONTIG_WARPS_PER_CTA = 16;
+constexpr int CONTIG_WARPS_PER_CTA = 28;   // the most any instantiation runs (sizes the per-warp scratch)
 int launch_contigs(ContigArgs a, bool want_score, const LaunchCfg &cfg);   // 0 ok, -1 CUDA error, -2 unsupported size
 
 // moira_parse_fastq with the number of text bytes consumed (moira_host.cpp)
