@@ -87,7 +87,14 @@ struct PairBufs {
     DevBuf cseq, cqual, slab, clen, overlap, gaps, mism, status, ee, ns, flags;
     DevBuf *all[19] = {&fseq, &fqual, &foff, &flen, &rseq, &rqual, &roff, &rlen, &cseq, &cqual, &slab, &clen,
                        &overlap, &gaps, &mism, &status, &ee, &ns, &flags};
+    // Pinned staging of the small per-pair results: a D2H copy into pageable user memory would block the host
+    // until the chunk's kernels are done and serialise the two streams.  Flushed to the caller's arrays when the
+    // stream is next synchronised.
+    uint8_t *stage = nullptr;
+    size_t stage_cap = 0;
+    uint64_t pend_start = 0, pend_n = 0;   // chunk whose results sit in `stage`
 };
+constexpr size_t PAIR_STAGE_BYTES = 8 + 4 * 5 + 2;   // ee | ns, clen, overlap, gaps, mism | flags, status
 
 struct Ticket {
     bool busy = false;
@@ -484,8 +491,10 @@ int moira_ctx_destroy(moira_ctx *c)
         if (t.counters_pinned) cudaFreeHost(t.counters_pinned);
     }
     for (auto &b : c->fq) b.release();
-    for (auto &pb : c->pb)
+    for (auto &pb : c->pb) {
         for (DevBuf *b : pb.all) if (b->p) cudaFree(b->p);
+        if (pb.stage) cudaFreeHost(pb.stage);
+    }
     for (DevBuf *b : {&c->trace, &c->hbuf, &c->post, &c->pair_counters}) if (b->p) cudaFree(b->p);
     for (auto &w : c->ws) {
         if (w.queues) cudaFree(w.queues);
@@ -897,7 +906,7 @@ static void fill_contig_args(ContigArgs &a, const moira_ctx *c, const moira_cont
     a.post_mis = a.post_match ? a.post_match + 65536 : nullptr;
 }
 
-int moira_filter_pairs(moira_ctx *c, const char *fwd_seq, uint64_t fwd_bytes, const uint8_t *fwd_qual, uint64_t fwd_qbytes,
+static int filter_pairs_impl(moira_ctx *c, const char *fwd_seq, uint64_t fwd_bytes, const uint8_t *fwd_qual, uint64_t fwd_qbytes,
                        const uint64_t *fwd_off, const uint64_t *fwd_qoff, const uint32_t *fwd_len, const char *rev_seq,
                        uint64_t rev_bytes, const uint8_t *rev_qual, uint64_t rev_qbytes, const uint64_t *rev_off,
                        const uint64_t *rev_qoff, const uint32_t *rev_len,
@@ -943,13 +952,39 @@ int moira_filter_pairs(moira_ctx *c, const char *fwd_seq, uint64_t fwd_bytes, co
     if (fp) { CU(cudaEventRecord(c->meta_ready, c->streams[0])); CU(cudaStreamWaitEvent(c->streams[1], c->meta_ready, 0)); }
 
     // Chunks of pairs alternate between the two streams: the copies of one chunk overlap the kernels of the other.
-    constexpr uint64_t PAIR_CHUNK = 1u << 17;
+    constexpr uint64_t PAIR_CHUNK = 1u << 16;
+    auto flush = [&](PairBufs &b) {
+        const uint64_t st0 = b.pend_start, m = b.pend_n;
+        if (!m) return;
+        const uint8_t *st = b.stage;
+        if (fp) {
+            memcpy(ee_out + st0, st, m * 8);
+            if (ns_out) memcpy(ns_out + st0, st + m * 8, m * 4);
+            if (flags_out) memcpy(flags_out + st0, st + m * 28, m);
+        }
+        memcpy(contig_len + st0, st + m * 12, m * 4);
+        if (overlap) memcpy(overlap + st0, st + m * 16, m * 4);
+        if (gaps) memcpy(gaps + st0, st + m * 20, m * 4);
+        if (mismatches) memcpy(mismatches + st0, st + m * 24, m * 4);
+        memcpy(status + st0, st + m * 29, m);
+        b.pend_n = 0;
+    };
+    c->pb[0].pend_n = c->pb[1].pend_n = 0;
     int ci = 0;
     for (uint64_t start = 0; start < n; start += PAIR_CHUNK, ci++) {
         const uint64_t cn = std::min<uint64_t>(PAIR_CHUNK, n - start);
         PairBufs &b = c->pb[ci & 1];
         cudaStream_t s = c->streams[ci & 1];
-        if (ci >= 2) CU(cudaStreamSynchronize(s));   // the host arrays of chunk ci - 2 are complete; its buffers are free
+        if (ci >= 2) { CU(cudaStreamSynchronize(s)); flush(b); }   // chunk ci - 2 is complete: hand its results over, reuse its buffers
+        if (cn * PAIR_STAGE_BYTES > b.stage_cap) {
+            if (b.stage) cudaFreeHost(b.stage);
+            b.stage = nullptr; b.stage_cap = 0;
+            if (cudaHostAlloc((void **)&b.stage, PAIR_CHUNK * PAIR_STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(MOIRA_ERR_NOMEM, "cudaHostAlloc of the result staging buffer failed");
+            }
+            b.stage_cap = PAIR_CHUNK * PAIR_STAGE_BYTES;
+        }
         // byte ranges of this chunk in the four host arrays; bases and qualities that live in ONE buffer (the
         // FASTQ text) travel once
         uint64_t f0 = ~0ull, f1 = 0, r0 = ~0ull, r1 = 0, fq0 = ~0ull, fq1 = 0, rq0 = ~0ull, rq1 = 0;
@@ -993,7 +1028,7 @@ int moira_filter_pairs(moira_ctx *c, const char *fwd_seq, uint64_t fwd_bytes, co
         a.qual_base = qual_base;
         a.n_pairs = cn;
         // every chunk uses the whole trace scratch: chunks on the two streams must not run their contig kernels at once
-        if (ci >= 1) { CU(cudaEventRecord(c->tickets[0].done[(ci - 1) & 1], c->streams[(ci - 1) & 1])); CU(cudaStreamWaitEvent(s, c->tickets[0].done[(ci - 1) & 1], 0)); }
+        if (ci >= 1) CU(cudaStreamWaitEvent(s, c->tickets[0].done[(ci - 1) & 1], 0));   // recorded behind that chunk's kernels
         a.trace = (uint32_t *)c->trace.p; a.trace_words_per_warp = tw;
         a.out_stride = out_stride;
         a.cseq = (char *)b.cseq.p; a.cqual = (uint8_t *)b.cqual.p; a.slab = fp ? (uint8_t *)b.slab.p : nullptr;
@@ -1012,23 +1047,52 @@ int moira_filter_pairs(moira_ctx *c, const char *fwd_seq, uint64_t fwd_bytes, co
             rc = run_filter_full(c, c->ws[ci & 1], (const uint8_t *)b.slab.p, nullptr, (const uint32_t *)b.clen.p, out_stride, 0, cn, fp,
                                  cap, 0, (double *)b.ee.p, (int32_t *)b.ns.p, (uint8_t *)b.flags.p, d_cnt, s);
             if (rc) return rc;
-            CU(cudaMemcpyAsync(ee_out + start, b.ee.p, cn * 8, cudaMemcpyDeviceToHost, s));
-            if (ns_out) CU(cudaMemcpyAsync(ns_out + start, b.ns.p, cn * 4, cudaMemcpyDeviceToHost, s));
-            if (flags_out) CU(cudaMemcpyAsync(flags_out + start, b.flags.p, cn, cudaMemcpyDeviceToHost, s));
         }
+        // The next chunk's contig kernel starts behind this chunk's kernels (a persistent contig grid in between would
+        // hold the filter back and with it the copies); only the D2H copies below overlap it.
+        CU(cudaEventRecord(c->tickets[0].done[ci & 1], s));
+        // small results -> pinned staging (sections of cn entries each), big rows straight to the caller
+        uint8_t *st = b.stage;
+        if (fp) {
+            CU(cudaMemcpyAsync(st, b.ee.p, cn * 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(st + cn * 8, b.ns.p, cn * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(st + cn * 28, b.flags.p, cn, cudaMemcpyDeviceToHost, s));
+        }
+        CU(cudaMemcpyAsync(st + cn * 12, b.clen.p, cn * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(st + cn * 16, b.overlap.p, cn * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(st + cn * 20, b.gaps.p, cn * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(st + cn * 24, b.mism.p, cn * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(st + cn * 29, b.status.p, cn, cudaMemcpyDeviceToHost, s));
+        b.pend_start = start; b.pend_n = cn;
         CU(cudaMemcpyAsync(contig_seq + start * out_stride, b.cseq.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(contig_qual + start * out_stride, b.cqual.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(contig_len + start, b.clen.p, cn * 4, cudaMemcpyDeviceToHost, s));
-        if (overlap) CU(cudaMemcpyAsync(overlap + start, b.overlap.p, cn * 4, cudaMemcpyDeviceToHost, s));
-        if (gaps) CU(cudaMemcpyAsync(gaps + start, b.gaps.p, cn * 4, cudaMemcpyDeviceToHost, s));
-        if (mismatches) CU(cudaMemcpyAsync(mismatches + start, b.mism.p, cn * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(status + start, b.status.p, cn, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(c->streams[1]));
     CU(cudaStreamSynchronize(c->streams[0]));
+    flush(c->pb[0]);
+    flush(c->pb[1]);
     if (fp && counters_out) CU(cudaMemcpy(counters_out, d_cnt, MOIRA_N_COUNTERS * 8, cudaMemcpyDeviceToHost));
     CU(cudaGetLastError());
     return MOIRA_OK;
+}
+
+int moira_filter_pairs(moira_ctx *c, const char *fwd_seq, uint64_t fwd_bytes, const uint8_t *fwd_qual, uint64_t fwd_qbytes,
+                       const uint64_t *fwd_off, const uint64_t *fwd_qoff, const uint32_t *fwd_len, const char *rev_seq,
+                       uint64_t rev_bytes, const uint8_t *rev_qual, uint64_t rev_qbytes, const uint64_t *rev_off,
+                       const uint64_t *rev_qoff, const uint32_t *rev_len,
+                       int qual_base, uint64_t n, const moira_contig_params *cp, int lower_n,
+                       const moira_params *fp, uint64_t out_stride, char *contig_seq, uint8_t *contig_qual, uint32_t *contig_len,
+                       int32_t *overlap, int32_t *gaps, int32_t *mismatches, uint8_t *status, double *ee_out, int32_t *ns_out,
+                       uint8_t *flags_out, uint64_t *counters_out)
+{
+    const int rc = filter_pairs_impl(c, fwd_seq, fwd_bytes, fwd_qual, fwd_qbytes, fwd_off, fwd_qoff, fwd_len, rev_seq, rev_bytes, rev_qual,
+                                     rev_qbytes, rev_off, rev_qoff, rev_len, qual_base, n, cp, lower_n, fp, out_stride, contig_seq,
+                                     contig_qual, contig_len, overlap, gaps, mismatches, status, ee_out, ns_out, flags_out, counters_out);
+    if (rc && c) {   // nothing may still be writing into the caller's arrays when the error is returned
+        for (cudaStream_t s : c->streams) if (s) cudaStreamSynchronize(s);
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 // One pair through the contig kernel (the single-call entry points): inputs, the two output rows and the
