@@ -111,3 +111,58 @@ json.dump({"pb_tpr<K=4>": {"dram_bytes_per_read": traffic / reads, "source": "pr
           open(os.path.join(out, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out, "%s_pb_tpr4_ncu.md" % tag)).read())
 print(open(os.path.join(out, "%s_launches_summary.md" % tag)).read())
+
+# ---- contig kernel (gpurun_out/<tag>_contig.ncu-rep, tools/bench_contigs.py --no-cpu --pairs 131072 --steps 1) ----
+rep = os.path.join(ROOT, "gpurun_out", "%s_contig.ncu-rep" % tag)
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    g = lambda k: float(vals[hdr.index(k)].replace(",", ""))
+    want = ["gpu__time_duration.sum", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+            "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_elapsed.avg.per_second",
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+    pairs, cells = 131072, 251 * 251
+    name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "contig_kernel"
+    md = ["# %s: `ncu --set full --clock-control none` of the contig kernel `%s`" % (tag, name), "",
+          "Workload: %d synthetic MiSeq V4 pairs, 2 x 251 bp (`tools/bench_contigs.py --no-cpu --pairs %d --steps 1`), one launch." % (pairs, pairs),
+          "Raw report kept in gpurun_out/ (scratch).", "", "| metric | value | unit |", "|---|---|---|"]
+    for w in want:
+        if w in hdr:
+            md.append("| %s | %s | %s |" % (w, vals[hdr.index(w)], units[hdr.index(w)]))
+
+    def in_bytes(k):
+        u = units[hdr.index(k)]
+        return g(k) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+
+    dram = in_bytes("dram__bytes_read.sum") + in_bytes("dram__bytes_write.sum")
+    alu = g("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active")
+    t_ms = g("gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}[units[hdr.index("gpu__time_duration.sum")]]
+    inst = g("smsp__inst_executed.sum")
+    md += ["", "Binding resource: the integer ALU pipe (16 lanes per SM sub-partition: one warp instruction every 2 cycles) -- "
+           "`sm__pipe_alu_cycles_active` = %.1f %% of peak, i.e. roofline fraction %.2f against the ALU issue peak.  DRAM traffic "
+           "(%.1f KB per pair, almost all of it the traceback-bit lines being written back from L2) runs at ~%.0f GB/s, far from the "
+           "HBM bound." % (alu, alu / 100, dram / pairs / 1e3, dram / (t_ms * 1e-3) / 1e9),
+           "", "Executed warp instructions per pair: %.0f for %d matrix cells, i.e. %.2f warp instructions per cell with everything "
+           "included -- wavefront fill and drain, traceback, consensus.  The recurrence itself is ~9.7 instructions per cell: ISETP + SEL + "
+           "IADD for the diagonal, VIMNMX + VIADDMNMX for max(up, left) + gap against it, two ISETP + two SEL/IADD3 for the traceback bits."
+           % (inst / pairs, cells, inst / pairs / cells)]
+    cj = os.path.join(out, "%s_contigs.json" % tag)
+    if os.path.exists(cj):
+        d = json.load(open(cj))
+        md += ["", "Bench of the same build (profiles/%s_contigs.json): kernel %.3g pairs/s (%.0f G cells/s), end to end %.3g pairs/s; unmodified "
+               "reference aligner %.0f pairs/s on one core, C restatement of the whole pair -> contig step %.3g pairs/s on %d cores." % (
+                   tag, d["kernel"]["value"], d["kernel"]["cells_per_s"] / 1e9, d["e2e"]["value"],
+                   d["cpu_baseline"]["reference_nw_align_1core"]["value"], d["cpu_baseline"]["oracle_pair_to_contig_allcores"]["value"],
+                   d["cpu_baseline"]["oracle_pair_to_contig_allcores"]["cores"])]
+    open(os.path.join(out, "%s_contig_ncu.md" % tag), "w").write("\n".join(md) + "\n")
+    print("wrote profiles/%s_contig_ncu.md" % tag)
