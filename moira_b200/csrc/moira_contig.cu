@@ -348,11 +348,8 @@ __global__ void __launch_bounds__(contig_warps(C) * 32, 1) contig_kernel(const C
 template <int C, bool SCORE>
 int launch_c(const ContigArgs &a, int grid, int warps, size_t smem, cudaStream_t s)
 {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(contig_kernel<C, SCORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-        configured = true;
-    }
+    // per device and cheap: set on every launch rather than remembered (one process may hold contexts on several GPUs)
+    if (cudaFuncSetAttribute(contig_kernel<C, SCORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
     contig_kernel<C, SCORE><<<grid, warps * 32, smem, s>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -68,3 +68,17 @@ def test_two_rank_gloo_counter_reduce(tmp_path):
     whole = _counters(slab, off, ln)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / ("rank%d.npy" % r)), whole)
+
+
+def test_read_pairs_shard_like_reads(oracle_contigs, forward_records, reverse_records):
+    """Pairs are as independent as reads: rank r of N builds the contigs of its contiguous range of pairs and the
+    concatenation over ranks is the single-rank result (what `moira_filter_pairs` per rank + one counter reduce gives)."""
+    n = 120
+    whole = [c[1:] for c in oracle_contigs[:n]]
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            b, e = shard.shard_range(n, r, world)
+            parts += [po.pair_to_contig(forward_records[i][1], forward_records[i][2], reverse_records[i][1], reverse_records[i][2])
+                      for i in range(b, e)]
+        assert parts == whole
