@@ -288,21 +288,25 @@ class Context:
         L.check(lib.moira_filter_device(self._h, d_slab, d_offsets, d_lengths, int(stride), int(fixed_length),
                                         int(n_reads), ctypes.byref(cp), d_ee, d_ns, d_flags, d_counters, stream))
 
-    def filter_fastq(self, text: bytes, params: FilterParams, fastq_offset: int = 33, out: FilterResult | None = None):
-        """FASTQ text -> FilterResult in one streaming C call (moira_filter_fastq); also returns lengths."""
-        buf = np.frombuffer(text, dtype=np.uint8)
+    def filter_fastq(self, text, params: FilterParams, fastq_offset: int = 33, out: FilterResult | None = None):
+        """FASTQ text (bytes, or a uint8 array -- e.g. a view of pinned memory) -> FilterResult in one streaming C call
+        (moira_filter_fastq); also returns the read lengths.  With `out` given, its size is the read capacity and the
+        counting pass over the text is skipped."""
+        buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
         n = ctypes.c_uint64()
-        L.check(lib.moira_fastq_count_reads(_ptr(buf), buf.nbytes, ctypes.byref(n)))
-        nr = n.value
         if out is None:
+            L.check(lib.moira_fastq_count_reads(_ptr(buf), buf.nbytes, ctypes.byref(n)))
+            nr = n.value
             out = FilterResult(np.empty(nr, np.float64), np.empty(nr, np.int32), np.empty(nr, np.uint8),
                                np.zeros(L.N_COUNTERS, np.uint64))
+        else:
+            nr = int(out.ee.shape[0])
         lengths = np.empty(nr, np.uint32)
         cp = params.to_c()
         L.check(lib.moira_filter_fastq(self._h, _ptr(buf), buf.nbytes, int(fastq_offset), int(params.lower_n_ambiguous),
                                        ctypes.byref(cp), nr, _ptr(out.ee), _ptr(out.ns), _ptr(out.flags), _ptr(lengths),
                                        _ptr(out.counters), ctypes.byref(n)))
-        return out, lengths
+        return out, lengths[:n.value]
 
     def filter_pairs(self, fwd_seq, fwd_qual, fwd_off, fwd_len, rev_seq, rev_qual, rev_off, rev_len,
                      contig_params: ContigParams, filter_params: FilterParams | None = None,

@@ -7,9 +7,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -96,6 +101,22 @@ struct PairBufs {
 };
 constexpr size_t PAIR_STAGE_BYTES = 8 + 4 * 5 + 2;   // ee | ns, clen, overlap, gaps, mism | flags, status
 
+// one chunk of FASTQ text being parsed and filtered on the device
+struct FqSlot {
+    DevBuf text, bcnt, bstart, nl, soff, qoff, len, slab, ee, ns, flags, meta;
+    uint8_t *h_text = nullptr;     // pinned staging of the chunk's text (pageable callers)
+    size_t h_text_cap = 0;
+    uint8_t *h_res = nullptr;      // pinned staging of the results: ee | ns | len | flags
+    size_t h_res_cap = 0;
+    uint32_t *h_meta = nullptr;    // pinned: max length, min length, first bad record
+    uint64_t pos = 0, bytes = 0, n_rec = 0, first_read = 0;
+    uint64_t skip = 0;             // the device buffer starts `skip` bytes before the chunk (page-aligned source of the copy)
+    cudaEvent_t ev = nullptr;      // behind the chunk's latest D2H: what the host waits for, not the whole stream
+    int state = 0;                 // 0 free, 1 indexed (meta on its way), 2 filtering (results on their way)
+    int stream = 0;
+    DevBuf *all[12] = {&text, &bcnt, &bstart, &nl, &soff, &qoff, &len, &slab, &ee, &ns, &flags, &meta};
+};
+
 struct Ticket {
     bool busy = false;
     DevBuf slab, slab6, offsets, lengths, ee, ns, flags, counters;
@@ -136,6 +157,12 @@ struct moira_ctx {
     int n_timed = 0;
     cudaEvent_t t0[MAX_TIMED] = {}, t1[MAX_TIMED] = {};
     const char *timed_name = "";
+    // FASTQ parsing on the device (moira_filter_fastq): three chunks in flight
+    FqSlot fqd[3];
+    uint8_t *fq_ring[6] = {};        // pinned staging of the text of pageable callers, filled by the planner thread
+    size_t fq_ring_cap[6] = {};
+    DevBuf fq_counters;
+    int device_parse = 1;
     // paired-end contig construction: per-stream device buffers, traceback scratch, posterior tables
     PairBufs pb[2];
     DevBuf trace, hbuf, post, pair_counters;
@@ -461,6 +488,7 @@ static int ctx_init(moira_ctx *c, int device, int sm_count)
     c->sm_count = sm_count;
     build_tables(c->h_p, c->h_q, c->h_e, &c->e_equals_p);
     if (const char *e = getenv("MOIRA_B200_NO_LENSORT")) c->length_sort = (e[0] == '1') ? 0 : 1;   // diagnostics
+    if (const char *e = getenv("MOIRA_B200_HOST_PARSE")) c->device_parse = (e[0] == '1') ? 0 : 1;   // moira_filter_fastq: parse on the host cores instead
     if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
     if (kernels_init(c->sm_count)) return fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaMalloc(&c->d_p, 256 * sizeof(double)));
@@ -491,6 +519,15 @@ int moira_ctx_destroy(moira_ctx *c)
         if (t.counters_pinned) cudaFreeHost(t.counters_pinned);
     }
     for (auto &b : c->fq) b.release();
+    for (auto &q : c->fqd) {
+        for (DevBuf *b : q.all) if (b->p) cudaFree(b->p);
+        if (q.h_text) cudaFreeHost(q.h_text);
+        if (q.h_res) cudaFreeHost(q.h_res);
+        if (q.h_meta) cudaFreeHost(q.h_meta);
+        if (q.ev) cudaEventDestroy(q.ev);
+    }
+    for (uint8_t *r : c->fq_ring) if (r) cudaFreeHost(r);
+    if (c->fq_counters.p) cudaFree(c->fq_counters.p);
     for (auto &pb : c->pb) {
         for (DevBuf *b : pb.all) if (b->p) cudaFree(b->p);
         if (pb.stage) cudaFreeHost(pb.stage);
@@ -734,6 +771,235 @@ int moira_filter_batch(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, c
     return moira_wait(c, ticket);
 }
 
+namespace {
+
+int ensure_pinned(uint8_t **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return MOIRA_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    if (cudaHostAlloc((void **)p, want, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MOIRA_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", want);
+    }
+    *cap = want;
+    return MOIRA_OK;
+}
+
+// FASTQ text -> decisions with the parsing on the device.  Per chunk of ~64 MB of text (cut behind a complete
+// record by fastq_plan_chunk): H2D of the text, newline index, record table (lengths, validation), then -- once the
+// host has read back the chunk's max / min length -- slab conversion, the filter, and D2H of the results.  Three
+// chunks are in flight: while chunk k is being indexed, chunk k-1 is filtered and chunk k-2 is handed to the caller.
+int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int fastq_offset, int lower_n, const moira_params *params,
+                        uint64_t max_reads, double *ee_out, int32_t *ns_out, uint8_t *flags_out, uint32_t *lengths_out,
+                        uint64_t *counters_out, uint64_t *n_reads_out)
+{
+    constexpr uint64_t RANGE = 64ull << 20;
+    int rc;
+    if ((rc = ensure(c->fq_counters, MOIRA_N_COUNTERS * 8))) return rc;
+    uint64_t *d_cnt = (uint64_t *)c->fq_counters.p;
+    CU(cudaMemsetAsync(d_cnt, 0, MOIRA_N_COUNTERS * 8, c->streams[0]));
+    CU(cudaEventRecord(c->meta_ready, c->streams[0]));
+    CU(cudaStreamWaitEvent(c->streams[1], c->meta_ready, 0));
+    cudaPointerAttributes attr;
+    const bool pinned_src = text_bytes && cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    for (auto &q : c->fqd) q.state = 0;
+
+    // stage 2 of a chunk: its index is done -> convert, filter, results on their way
+    auto filter_chunk = [&](FqSlot &q) -> int {
+        cudaStream_t s = c->streams[q.stream];
+        CU(cudaEventSynchronize(q.ev));
+        const uint32_t maxlen = q.h_meta[0], minlen = q.h_meta[1], bad = q.h_meta[2];
+        if (bad != 0xFFFFFFFFu) {
+            // let the host parser raise the reference's error for this range (same message as the host path)
+            std::vector<uint8_t> slab(16);
+            uint64_t n = 0, cap = 0;
+            int r = parse_fastq_range(text + q.pos, q.bytes, fastq_offset, lower_n, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                      nullptr, 0, &n, &cap, nullptr, 1);
+            if (!r) {
+                slab.resize(cap + 16);
+                std::vector<uint64_t> off(n + 1);
+                std::vector<uint32_t> len(n + 1);
+                r = parse_fastq_range(text + q.pos, q.bytes, fastq_offset, lower_n, slab.data(), slab.size(), off.data(), len.data(), nullptr,
+                                      nullptr, nullptr, nullptr, n, &n, &cap, nullptr, 1);
+            }
+            return r ? r : fail(MOIRA_ERR_PARSE, "record %u of the range at byte %llu is malformed", bad, (unsigned long long)q.pos);
+        }
+        const uint32_t stride = std::max<uint32_t>(16, (maxlen + 15u) & ~15u);
+        int r;
+        if ((r = ensure(q.slab, (size_t)q.n_rec * stride + 256))) return r;
+        if (launch_fq_convert((const uint8_t *)q.text.p, (const uint32_t *)q.soff.p, (const uint32_t *)q.qoff.p, (const uint32_t *)q.len.p,
+                              (uint32_t)q.n_rec, stride, lower_n, fastq_offset, (uint8_t *)q.slab.p, (uint32_t *)q.meta.p, c->sm_count, s))
+            return fail(MOIRA_ERR_CUDA, "fastq convert launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        c->launches++;
+        const bool same = minlen == maxlen;
+        r = run_filter_full(c, c->ws[q.stream], (const uint8_t *)q.slab.p, nullptr, same ? nullptr : (const uint32_t *)q.len.p, stride,
+                            same ? maxlen : 0, q.n_rec, params, maxlen, minlen, (double *)q.ee.p, (int32_t *)q.ns.p, (uint8_t *)q.flags.p,
+                            d_cnt, s);
+        if (r) return r;
+        const uint64_t m = q.n_rec;
+        CU(cudaMemcpyAsync(q.h_res, q.ee.p, m * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(q.h_res + m * 8, q.ns.p, m * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(q.h_res + m * 12, q.len.p, m * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(q.h_res + m * 16, q.flags.p, m, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(q.h_meta, q.meta.p, 12, cudaMemcpyDeviceToHost, s));     // a quality above 252 shows up here
+        CU(cudaEventRecord(q.ev, s));
+        q.state = 2;
+        return MOIRA_OK;
+    };
+    // stage 3: results -> the caller's arrays
+    auto retire_chunk = [&](FqSlot &q) -> int {
+        CU(cudaEventSynchronize(q.ev));
+        if (q.h_meta[2] != 0xFFFFFFFFu)
+            return fail(MOIRA_ERR_BAD_QUALITY, "a quality of record %u of the range at byte %llu is outside 0..252", q.h_meta[2],
+                        (unsigned long long)q.pos);
+        const uint64_t m = q.n_rec, at = q.first_read;
+        memcpy(ee_out + at, q.h_res, m * 8);
+        if (ns_out) memcpy(ns_out + at, q.h_res + m * 8, m * 4);
+        if (lengths_out) memcpy(lengths_out + at, q.h_res + m * 12, m * 4);
+        if (flags_out) memcpy(flags_out + at, q.h_res + m * 16, m);
+        q.state = 0;
+        return MOIRA_OK;
+    };
+
+    // The chunk plans (where each chunk ends, how many records and newlines it holds) come from a planner thread that
+    // runs ahead of the copies: counting the newlines of a chunk on the host takes about as long as its H2D copy.
+    // For a pageable source the same pass also copies the chunk into a ring of pinned buffers (one read of the text
+    // for both); ring entry i % RING is free again once the H2D copy of chunk i - RING has completed (h2d_done).
+    constexpr int RING = 6;
+    if (!pinned_src)
+        for (int r = 0; r < RING; r++)
+            if ((rc = ensure_pinned(&c->fq_ring[r], &c->fq_ring_cap[r], std::min<uint64_t>(RANGE, text_bytes) + 64))) return rc;
+    struct Plan { uint64_t pos, bytes, n_rec, n_nl; const uint8_t *staged; int rc; bool last; };
+    std::deque<Plan> plans;
+    std::mutex pm;
+    std::condition_variable pcv;
+    bool stop = false;
+    uint64_t h2d_done = 0;
+    std::thread planner([&]() {
+        uint64_t p = 0;
+        for (uint64_t i = 0;; i++) {
+            Plan pl{p, 0, 0, 0, nullptr, MOIRA_OK, false};
+            uint8_t *ring = pinned_src ? nullptr : c->fq_ring[i % RING];
+            if (ring) {
+                std::unique_lock<std::mutex> lk(pm);
+                pcv.wait(lk, [&] { return stop || i < h2d_done + RING - 1; });
+                if (stop) return;
+            }
+            if (p >= text_bytes) pl.last = true;
+            else pl.rc = fastq_plan_chunk(text, text_bytes, p, RANGE, ring, &pl.bytes, &pl.n_rec, &pl.n_nl);
+            pl.staged = ring;
+            if (pl.rc || pl.n_rec == 0) pl.last = true;
+            {
+                std::unique_lock<std::mutex> lk(pm);
+                pcv.wait(lk, [&] { return stop || plans.size() < 4; });
+                if (stop) return;
+                plans.push_back(pl);
+            }
+            pcv.notify_all();
+            if (pl.last) return;
+            p += pl.bytes;
+        }
+    });
+    auto next_plan = [&]() {
+        std::unique_lock<std::mutex> lk(pm);
+        pcv.wait(lk, [&] { return !plans.empty(); });
+        Plan pl = plans.front();
+        plans.pop_front();
+        lk.unlock();
+        pcv.notify_all();
+        return pl;
+    };
+    struct PlannerJoin {   // whatever path leaves this function: stop and join the planner
+        std::thread &t; std::mutex &m; std::condition_variable &cv; bool &stop;
+        ~PlannerJoin() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); if (t.joinable()) t.join(); }
+    } planner_join{planner, pm, pcv, stop};
+
+    uint64_t pos = 0, n_done = 0;
+    int k = 0;
+    rc = MOIRA_OK;
+    const bool dbg = getenv("MOIRA_B200_FQ_DEBUG") != nullptr;
+    double t_plan = 0, t_issue = 0, t_filter = 0, t_retire = 0;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    while (!rc) {
+        FqSlot &q = c->fqd[k % 3];
+        double t0 = now();
+        if (q.state == 2 && (rc = retire_chunk(q))) break;          // chunk k - 3
+        t_retire += now() - t0; t0 = now();
+        // stage 1: plan, stage, copy, index
+        const Plan pl = next_plan();
+        if ((rc = pl.rc)) break;
+        pos = pl.pos;
+        const uint64_t bytes = pl.bytes, n_rec = pl.n_rec, n_nl = pl.n_nl;
+        if (n_rec == 0) {
+            if (pos >= text_bytes || pos + std::min<uint64_t>(RANGE, text_bytes - pos) >= text_bytes) break;   // a trailing partial record is ignored, as the reference does
+            rc = fail(MOIRA_ERR_PARSE, "a FASTQ record is longer than the %llu-byte streaming range", (unsigned long long)RANGE);
+            break;
+        }
+        t_plan += now() - t0; t0 = now();
+        if (n_done + n_rec > max_reads) { rc = fail(MOIRA_ERR_BAD_ARG, "more than max_reads = %llu records", (unsigned long long)max_reads); break; }
+        q.pos = pos; q.bytes = bytes; q.n_rec = n_rec; q.first_read = n_done; q.stream = k & 1;
+        // a pinned source is copied from its page boundary (unaligned DMA is several times slower); staging is aligned anyway
+        q.skip = pinned_src ? (uint64_t)((uintptr_t)(text + pos) & 4095u) : 0;
+        if (q.skip > pos) q.skip = 0;   // never read before the caller's buffer
+        const uint64_t span = q.skip + bytes;
+        cudaStream_t s = c->streams[q.stream];
+        const uint32_t nb = fq_blocks(span);
+        if (!q.ev) CU(cudaEventCreateWithFlags(&q.ev, cudaEventDisableTiming));
+        if ((rc = ensure(q.text, span + 64)) || (rc = ensure(q.bcnt, (size_t)nb * 4 + 16)) || (rc = ensure(q.bstart, (size_t)nb * 4 + 16)) ||
+            (rc = ensure(q.nl, (size_t)n_nl * 4 + 64)) || (rc = ensure(q.soff, n_rec * 4)) || (rc = ensure(q.qoff, n_rec * 4)) ||
+            (rc = ensure(q.len, n_rec * 4)) || (rc = ensure(q.ee, n_rec * 8)) || (rc = ensure(q.ns, n_rec * 4)) ||
+            (rc = ensure(q.flags, n_rec)) || (rc = ensure(q.meta, 16)) || (rc = ensure_pinned(&q.h_res, &q.h_res_cap, n_rec * 17 + 64)))
+            break;
+        if (!q.h_meta && cudaHostAlloc((void **)&q.h_meta, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); rc = fail(MOIRA_ERR_NOMEM, "cudaHostAlloc failed"); break; }
+        q.h_meta[0] = 0; q.h_meta[1] = 0xFFFFFFFFu; q.h_meta[2] = 0xFFFFFFFFu;
+        CU(cudaMemcpyAsync(q.meta.p, q.h_meta, 12, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(q.text.p, pinned_src ? (const void *)(text + pos - q.skip) : (const void *)pl.staged, span, cudaMemcpyHostToDevice, s));
+        if (launch_fq_index((const uint8_t *)q.text.p, q.skip, span, (uint32_t *)q.bcnt.p, (uint32_t *)q.bstart.p, (uint32_t *)q.nl.p, s) ||
+            launch_fq_records((const uint8_t *)q.text.p, q.skip, span, (const uint32_t *)q.nl.p, (const uint32_t *)q.bstart.p + nb, (uint32_t)n_rec,
+                              (uint32_t *)q.soff.p, (uint32_t *)q.qoff.p, (uint32_t *)q.len.p, (uint32_t *)q.meta.p, s)) {
+            rc = fail(MOIRA_ERR_CUDA, "fastq index launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        c->launches += 4;
+        CU(cudaMemcpyAsync(q.h_meta, q.meta.p, 12, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(q.ev, s));
+        q.state = 1;
+        n_done += n_rec;
+        t_issue += now() - t0; t0 = now();
+        // chunk k - 1 has had a whole iteration for its copy and index: filter it now
+        if (k >= 1) {
+            FqSlot &p1 = c->fqd[(k - 1) % 3];
+            if (p1.state == 1 && (rc = filter_chunk(p1))) break;
+            { std::lock_guard<std::mutex> lk(pm); h2d_done = (uint64_t)k; }   // the copy of chunk k - 1 is complete
+            pcv.notify_all();
+        }
+        t_filter += now() - t0;
+        k++;
+    }
+    if (dbg) fprintf(stderr, "[fq] chunks %d pinned %d plan %.2f issue %.2f filter %.2f retire %.2f ms\n", k, (int)pinned_src, t_plan, t_issue, t_filter, t_retire);
+    for (int j = 0; j < 3 && !rc; j++) {                            // drain, oldest first
+        FqSlot &q = c->fqd[(k + j) % 3];
+        if (q.state == 1) rc = filter_chunk(q);
+        if (!rc && q.state == 2) rc = retire_chunk(q);
+    }
+    if (rc) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    if (counters_out) CU(cudaMemcpy(counters_out, d_cnt, MOIRA_N_COUNTERS * 8, cudaMemcpyDeviceToHost));
+    *n_reads_out = n_done;
+    return MOIRA_OK;
+}
+
+}  // namespace
+
 // FASTQ text -> decisions, streaming: ranges of ~64 MB of text are parsed (all host threads) into
 // pinned slabs and submitted asynchronously, so parsing range k+1 overlaps the H2D copy, the kernels
 // and the D2H copy of range k.
@@ -745,6 +1011,10 @@ int moira_filter_fastq(moira_ctx *c, const char *text, uint64_t text_bytes, int 
     int rc = check_params(params);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
+    if (params->slab_format != MOIRA_SLAB_Q8) return fail(MOIRA_ERR_BAD_ARG, "slab_format does not apply to FASTQ text");
+    if (c->device_parse)
+        return filter_fastq_device(c, text, text_bytes, fastq_offset, lower_n_ambiguous, params, max_reads, ee_out, ns_out, flags_out,
+                                   lengths_out, counters_out, n_reads_out);
     constexpr int SLOTS = 3;
     const uint64_t RANGE = 64ull << 20;
     struct Slot { int ticket = -1; uint64_t counters[MOIRA_N_COUNTERS]; };

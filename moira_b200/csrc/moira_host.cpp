@@ -422,6 +422,67 @@ int moira::parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_of
     return MOIRA_OK;
 }
 
+void moira::parallel_memcpy(void *dst, const void *src, uint64_t bytes)
+{
+    int T = g_host_threads > 0 ? g_host_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 64) T = 64;
+    if (bytes < (1u << 20)) T = 1;
+    moira::parallel_run(T, T, [&](int t) {
+        const uint64_t b = bytes * (uint64_t)t / T, e = bytes * (uint64_t)(t + 1) / T;
+        memcpy((char *)dst + b, (const char *)src + b, e - b);
+    });
+}
+
+// Plan one chunk of a FASTQ text for the device parser: count the newlines of text[pos, pos + target) on all host
+// threads (copying the bytes into `copy_to`, pinned staging, on the way when the caller's text is pageable) and cut
+// the chunk behind its last complete 4-line record.  Outputs: bytes of the chunk, its records, its newlines.
+int moira::fastq_plan_chunk(const char *text, uint64_t text_bytes, uint64_t pos, uint64_t target_bytes, uint8_t *copy_to,
+                            uint64_t *chunk_bytes_out, uint64_t *n_rec_out, uint64_t *n_newlines_out)
+{
+    const uint64_t len = std::min<uint64_t>(target_bytes, text_bytes - pos);
+    const bool final_range = pos + len >= text_bytes;
+    int T = g_host_threads > 0 ? g_host_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 64) T = 64;
+    if (len < (1u << 20)) T = 1;
+    std::vector<uint64_t> cnt(T, 0);
+    const char *base = text + pos;
+    moira::parallel_run(T, T, [&](int t) {
+        const uint64_t b = len * (uint64_t)t / T, e = len * (uint64_t)(t + 1) / T;
+        uint64_t c = 0;
+        const char *p = base + b, *end = base + e;
+        while (p < end) {
+            const char *nl = (const char *)memchr(p, '\n', end - p);
+            if (!nl) break;
+            c++;
+            p = nl + 1;
+        }
+        cnt[t] = c;
+        if (copy_to) memcpy(copy_to + b, base + b, e - b);
+    });
+    uint64_t total_nl = 0;
+    for (int t = 0; t < T; t++) total_nl += cnt[t];
+    const uint64_t lines = total_nl + ((final_range && len && base[len - 1] != '\n') ? 1 : 0);
+    const uint64_t n_rec = lines / 4;
+    *n_rec_out = n_rec;
+    if (n_rec == 0) { *chunk_bytes_out = final_range ? len : 0; *n_newlines_out = 0; return MOIRA_OK; }
+    const uint64_t keep = 4 * n_rec;
+    uint64_t end = len;
+    if (keep <= total_nl) {
+        // the chunk ends just behind its keep-th newline: walk back over the newlines that follow it
+        uint64_t p = len;
+        for (uint64_t k = 0; k <= total_nl - keep; k++) {
+            const char *nl = (const char *)memrchr(base, '\n', p);
+            p = (uint64_t)(nl - base);
+        }
+        end = p + 1;
+    }
+    *chunk_bytes_out = end;
+    *n_newlines_out = keep <= total_nl ? keep : total_nl;
+    return MOIRA_OK;
+}
+
 // ---- FASTA + QUAL ------------------------------------------------------------------------------------
 // Record semantics of parse_fasta_and_qual (moira/moira.py:1093-1149, single-end): both files hold one
 // header line and one data line per record ("Expects sequences and qualities to be stored in a single

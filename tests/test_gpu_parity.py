@@ -384,3 +384,56 @@ def test_submit_failing_midway_leaves_the_context_usable(ctx):
     for _ in range(L.MAX_INFLIGHT + 1):                         # no ticket leaked by the failed submission
         again = ctx.filter_batch(slab, off, ln, p)
         assert np.array_equal(again.flags, good.flags) and np.array_equal(again.counters, good.counters)
+
+
+@pytest.mark.gpu
+def test_device_fastq_parser_agrees_with_host_parser(ctx, monkeypatch):
+    """moira_filter_fastq parses on the device by default.  Ragged reads, N / n, '@' and '+' as quality
+    characters, CRLF and padded lines, an unterminated last record and a trailing partial record must give what
+    the host parser (pinned on the reference's records in test_abi.py) plus filter_batch give; errors are the
+    host parser's."""
+    rng = np.random.default_rng(21)
+    recs = []
+    for i in range(40000):
+        n = int(rng.integers(1, 400)) if i % 4 else 253
+        seq = "".join(rng.choice(list("ACGTNn"), size=n, p=[.24, .24, .24, .24, .03, .01]))
+        q = rng.integers(33, 74, size=n).astype(np.uint8)
+        if i % 3 == 0:
+            q[0] = ord("@")
+        if i % 5 == 0:
+            q[-1] = ord("+")
+        eol = "\r\n" if i % 7 == 0 else "\n"
+        pad = "  " if i % 11 == 0 else ""
+        recs.append("@r%d some text%s%s%s%s%s+%s%s%s%s" % (i, eol, pad, seq, pad, eol, eol, q.tobytes().decode(), "\t" if i % 13 == 0 else "", eol))
+    body = "".join(recs).encode()
+    p = FilterParams(exact_ee=True, ee_output="final")
+    for tail in (b"", b"@last\nACGTN\n+\nIIII#", b"@partial\nACGT\n+\n"):
+        text = body + tail
+        slab, off, ln, *_ = moira_b200.parse_fastq(text, 33, True)
+        ref = ctx.filter_batch(slab, off, ln, p)
+        res, lengths = ctx.filter_fastq(text, p)
+        assert len(lengths) == len(ln) == 40000 + (1 if tail.startswith(b"@last") else 0)
+        assert np.array_equal(lengths, ln) and np.array_equal(res.ee, ref.ee) and np.array_equal(res.ns, ref.ns)
+        assert np.array_equal(res.flags, ref.flags) and np.array_equal(res.counters, ref.counters)
+    # the host-parse variant of the same entry point (a context created with MOIRA_B200_HOST_PARSE=1)
+    monkeypatch.setenv("MOIRA_B200_HOST_PARSE", "1")
+    c2 = moira_b200.Context(0)
+    try:
+        res_h, lengths_h = c2.filter_fastq(text, p)
+        assert np.array_equal(lengths_h, ln) and np.array_equal(res_h.ee, ref.ee) and np.array_equal(res_h.flags, ref.flags)
+    finally:
+        c2.close()
+        monkeypatch.delenv("MOIRA_B200_HOST_PARSE")
+    # errors: detected on the device, raised with the host parser's message
+    good = "".join(recs[:3000]).encode()
+    for bad, word in ((b"@bad\nACGT\n+\nIII\n", "LengthMismatchError"), (b"@bad\n\n+\nIII\n", "EmptySeqError"),
+                      (b"@bad\nACG\n+\n\n", "EmptyQualError")):
+        with pytest.raises(moira_b200.MoiraError) as ei:
+            ctx.filter_fastq(good + bad + good, p)
+        assert ei.value.code == L.ERR_PARSE and word in ei.value.message and "3000" in ei.value.message
+    with pytest.raises(moira_b200.MoiraError) as ei:
+        ctx.filter_fastq(good, p, fastq_offset=-190)
+    assert ei.value.code == L.ERR_BAD_QUALITY
+    # the context is fine afterwards
+    res3, _ = ctx.filter_fastq(text, p)
+    assert np.array_equal(res3.ee, ref.ee)
