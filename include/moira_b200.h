@@ -113,7 +113,8 @@ typedef struct moira_params {
     int32_t  ee_output;   /* MOIRA_EE_* */
     int32_t  length_sort; /* ragged batches: 0 = bucket reads by length on the device when it pays (default), 2 = never */
     int32_t  slab_format; /* MOIRA_SLAB_*: format of the HOST slab given to moira_filter_batch / moira_submit */
-    int32_t  reserved;
+    int32_t  cascade;     /* first pass of a decision that needs 3..8 PMF entries: 0 = two-entry sweep first when a pilot launch
+                             says it pays (default), 1 = always, 2 = never (one sweep with all the entries) */
     double   alpha;       /* --alpha */
     double   thr;         /* --uncert or --maxerrors value */
 } moira_params;

@@ -46,7 +46,7 @@ class Params(ctypes.Structure):
         ("mode", ctypes.c_int32), ("thr_kind", ctypes.c_int32), ("ambigs", ctypes.c_int32),
         ("round_flag", ctypes.c_int32), ("truncate", ctypes.c_uint32), ("exact_ee", ctypes.c_int32),
         ("ee_output", ctypes.c_int32), ("length_sort", ctypes.c_int32),
-        ("slab_format", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("slab_format", ctypes.c_int32), ("cascade", ctypes.c_int32),
         ("alpha", ctypes.c_double), ("thr", ctypes.c_double),
     ]
 

@@ -30,6 +30,7 @@ class FilterParams:
     ee_output: str = "raw"                 # 'raw' = calculate_errors_* value, 'final' = process_data value
     slab_format: str = "q8"                # host slab format: 'q8' (one byte per base) or 'q6' (pack_q6 transport image)
     length_sort: int = 0                   # ragged batches: 0 = bucket by length on the device when it pays, 2 = never
+    cascade: int = 0                       # decisions needing 3..8 PMF entries: 0 = two-entry sweep first when the pilot says it pays, 1 = always, 2 = never
 
     def to_c(self) -> L.Params:
         if self.error_calc not in _MODES:
@@ -48,6 +49,7 @@ class FilterParams:
         p.exact_ee = 1 if self.exact_ee else 0
         p.ee_output = L.EE_FINAL if self.ee_output == "final" else L.EE_RAW
         p.length_sort = int(self.length_sort)
+        p.cascade = int(self.cascade)
         p.slab_format = L.SLAB_Q6 if self.slab_format == "q6" else L.SLAB_Q8
         p.alpha = float(self.alpha)
         return p

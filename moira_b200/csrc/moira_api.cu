@@ -39,7 +39,8 @@ constexpr int MAX_TIMED = 256;
 struct Workspace {
     uint32_t *queues = nullptr;
     uint32_t *counts = nullptr;
-    uint32_t cap = 0;
+    uint32_t cap = 0;      // reads per queue in the current layout
+    size_t words = 0;      // allocated
     // length bucketing of ragged batches
     uint32_t *lqueue = nullptr;
     uint32_t *ltables = nullptr;   // hist | bucket_start | cursor | group_start | group_count
@@ -153,6 +154,7 @@ struct moira_ctx {
     uint64_t launches = 0;
     int use_tma = 1;
     int length_sort = 1;
+    int cascade = 1;
     int timing = 0;
     int n_timed = 0;
     cudaEvent_t t0[MAX_TIMED] = {}, t1[MAX_TIMED] = {};
@@ -217,17 +219,20 @@ int ensure(DevBuf &b, size_t bytes)
     return MOIRA_OK;
 }
 
-int ensure_ws(Workspace &w, uint32_t cap)
+// queue memory for `nq` queues of `cap` reads each (the ladder uses NB queues, the decision cascade only queue 0)
+int ensure_ws(Workspace &w, uint32_t cap, int nq = NB)
 {
-    if (cap <= w.cap && w.queues) return MOIRA_OK;
+    if (!w.counts) CU(cudaMalloc(&w.counts, (NB + 4) * sizeof(uint32_t)));   // queue counts | first-pass policy word
+    const size_t words = (size_t)nq * cap;
+    if (words <= w.words && w.queues) { w.cap = cap; return MOIRA_OK; }
     if (w.queues) cudaFree(w.queues);
-    if (!w.counts) CU(cudaMalloc(&w.counts, NB * sizeof(uint32_t)));
-    w.queues = nullptr; w.cap = 0;
-    if (cudaMalloc(&w.queues, (size_t)NB * cap * sizeof(uint32_t)) != cudaSuccess) {
+    w.queues = nullptr; w.cap = 0; w.words = 0;
+    if (cudaMalloc(&w.queues, words * sizeof(uint32_t)) != cudaSuccess) {
         cudaGetLastError();
-        return fail(MOIRA_ERR_NOMEM, "cudaMalloc of escalation queues (%u reads) failed", cap);
+        return fail(MOIRA_ERR_NOMEM, "cudaMalloc of escalation queues (%d x %u reads) failed", nq, cap);
     }
     w.cap = cap;
+    w.words = words;
     return MOIRA_OK;
 }
 
@@ -365,16 +370,24 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
     }
     const bool ladder = p->mode == MOIRA_MODE_PB && (p->exact_ee || !k_decides_all);
     a.allow_push = ladder ? 1 : 0;
+    // Cascaded first pass: when the decision needs only a few entries (k_first = 3..8), most reads of a typical run are
+    // either clean (j* <= 1: two entries settle them exactly) or hopeless (the Newton bound on acc[k_first - 1] from
+    // those two entries already rejects them).  Sweeping two entries costs 4-5 FP64 operations per base instead of
+    // 3 k_first - 2; only the reads in between are swept again with k_first entries (decision mode) or walk the ladder
+    // (exact mode).  Whether that pays depends on the data: a pilot launch over the first tiles measures the escalated
+    // fraction on the device, and the two candidate launches for the rest read that verdict (no host synchronisation).
+    const bool cascade_ok = p->mode == MOIRA_MODE_PB && k_decides_all && k_first >= 3 && k_first <= 8 && p->cascade != 2 && c->cascade;
+    const bool queues_needed = ladder || cascade_ok;
 
-    const uint64_t sub = ladder ? SUB_BATCH : (1ull << 31);
+    const uint64_t sub = ladder ? SUB_BATCH : cascade_ok ? (1ull << 26) : (1ull << 31);
     for (uint64_t start = 0; start < n_reads; start += sub) {
         const uint32_t n = (uint32_t)std::min<uint64_t>(sub, n_reads - start);
         a.base = start; a.n = n; a.queue = nullptr; a.queue_count = nullptr; a.rung = -1;
-        if (ladder) {
-            int rc = ensure_ws(ws, (uint32_t)std::min<uint64_t>(n_reads, SUB_BATCH));
+        if (queues_needed) {
+            int rc = ensure_ws(ws, (uint32_t)std::min<uint64_t>(n_reads, sub), ladder ? NB : 1);
             if (rc) return rc;
             a.queues = ws.queues; a.queue_counts = ws.counts; a.queue_cap = ws.cap;
-            CU(cudaMemsetAsync(ws.counts, 0, NB * sizeof(uint32_t), stream));
+            CU(cudaMemsetAsync(ws.counts, 0, (NB + 4) * sizeof(uint32_t), stream));
         }
         // uniform-stride slab: feed the first pass with TMA tensor tiles of this sub-batch's rows
         CUtensorMap tmap;
@@ -413,6 +426,46 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             c->launches++;
             a.queue = nullptr; a.queue_count = nullptr; a.seg_start = nullptr; a.seg_count = nullptr;
+        } else if (cascade_ok) {
+            // two-entry launches: escalate to queue 0; in decision mode certain rejects are settled by the bound
+            FilterArgs a2 = a;
+            a2.allow_push = 1;
+            a2.k_dec = p->exact_ee ? 0 : k_first;
+            const uint32_t warps = (uint32_t)c->sm_count * 16u;            // tpr_warps(2) per CTA
+            const uint32_t pilot_n = 2u * warps * 32u;                     // two tiles per warp
+            const bool pilot = p->cascade != 1 && n >= 8u * pilot_n;
+            const bool blind = p->cascade == 1 || k_first <= 4;            // without a pilot: only where k_first is small
+            uint32_t *policy = ws.counts + NB;
+            static const char *cname[] = {"", "", "", "pb_cascade<2,3>", "pb_cascade<2,4>", "pb_cascade<2,5>", "pb_cascade<2,6>",
+                                          "pb_cascade<2,7>", "pb_cascade<2,8>"};
+            if (pilot) {
+                a2.n = pilot_n;
+                rc = launch_pb_first(a2, 2, cfg, nullptr);
+                if (rc >= 0 && launch_policy(ws.counts, (uint32_t)(pilot_n * 0.35), policy, stream)) rc = -1;
+                a2.n = n; a2.tile0 = pilot_n / 32u; a2.policy = policy; a2.policy_want = 0;
+                if (rc >= 0) rc = launch_pb_first(a2, 2, cfg, nullptr);
+                FilterArgs a1 = a;                                         // the other candidate: k_first entries at once
+                a1.tile0 = pilot_n / 32u; a1.policy = policy; a1.policy_want = 1;
+                if (rc >= 0) rc = launch_pb_first(a1, k_first, cfg, nullptr);
+                c->launches += 4;
+            } else if (blind) {
+                rc = launch_pb_first(a2, 2, cfg, nullptr);
+                c->launches++;
+            } else {
+                rc = launch_pb_first(a, k_first, cfg, &name);
+                c->launches++;
+            }
+            if (rc >= 0 && !p->exact_ee && (pilot || blind)) {
+                // second sweep, k_first entries, over the escalated reads only: settles every one of them
+                FilterArgs a3 = a;
+                a3.queue = ws.queues; a3.queue_count = ws.counts; a3.allow_push = 0;
+                LaunchCfg cfg3 = cfg;
+                cfg3.tmap = nullptr;
+                rc = launch_pb_first(a3, k_first, cfg3, nullptr);
+                c->launches++;
+            }
+            if (pilot || blind) name = cname[k_first];
+            if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else {
             rc = p->mode == MOIRA_MODE_PB ? launch_pb_first(a, k_first, cfg, &name) : launch_lambda(a, cfg, &name);
             if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -489,6 +542,7 @@ static int ctx_init(moira_ctx *c, int device, int sm_count)
     build_tables(c->h_p, c->h_q, c->h_e, &c->e_equals_p);
     if (const char *e = getenv("MOIRA_B200_NO_LENSORT")) c->length_sort = (e[0] == '1') ? 0 : 1;   // diagnostics
     if (const char *e = getenv("MOIRA_B200_HOST_PARSE")) c->device_parse = (e[0] == '1') ? 0 : 1;   // moira_filter_fastq: parse on the host cores instead
+    if (const char *e = getenv("MOIRA_B200_NO_CASCADE")) c->cascade = (e[0] == '1') ? 0 : 1;   // diagnostics: full-K first pass always
     if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
     if (kernels_init(c->sm_count)) return fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaMalloc(&c->d_p, 256 * sizeof(double)));

@@ -61,6 +61,13 @@ struct FilterArgs {
     int32_t rung;                // -1 on the first pass, else this kernel's rung
     int32_t min_rung;            // lowest rung the classifier may forward to (its cap exceeds the first-pass K)
     int32_t allow_push;          // 0: no ladder follows (first-pass K provably decides everything)
+    // cascaded first pass (decision mode): this launch tracks fewer entries than the k_dec = floor(cutoff) + 2 the
+    // decision needs; reads it cannot settle exactly are rejected when the Newton bound on acc[k_dec - 1] allows it
+    // and pushed to queue 0 otherwise.  0: off.
+    int32_t k_dec;
+    uint32_t tile0;              // first pass: the launch starts at this warp tile (the tiles before belong to the pilot launch)
+    const uint32_t *policy;      // not null: the launch runs only if *policy == policy_want (set on the device by the pilot)
+    uint32_t policy_want;
     // tables (device, 256 doubles each)
     const double *lut_p;
     const double *lut_q;
@@ -105,6 +112,9 @@ int launch_sorted_first(const FilterArgs &a, const uint32_t *seg_start, const ui
 int launch_pb_first_k(const FilterArgs &a, int k_index, const LaunchCfg &cfg, const char **name);
 // expand a 6-bit transport image into slab bytes [0, slab_bytes) (both device pointers, 16-byte aligned)
 int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_bytes, const LaunchCfg &cfg);
+// after the pilot launch: *policy = 1 (go on with the full-K first pass) if more than `max_pushed` of the pilot's reads were
+// escalated, else 0 (go on with the cascade)
+int launch_policy(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s);
 int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, double *ops_out);
 int kernels_init(int sm_count);  // sets function attributes (dynamic smem opt-in)
 int max_first_pass_k();

@@ -51,6 +51,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef MOIRA_PAIR_LUT
 #define MOIRA_PAIR_LUT 1   // 1: first-pass kernels look up (q, e) pairs (no DSUB, LDS.128); 0: p only (LDS.64 + DSUB)
 #endif
+#ifndef MOIRA_PL_MAXK
+#define MOIRA_PL_MAXK 2    // ... but K <= this looks up p only: with so little arithmetic per base the 16-byte lookups bind
+#endif
 constexpr int CHUNK = MOIRA_CHUNK;               // bytes of one row staged per pipeline stage (64 or 128)
 // row stride = CHUNK + 16 B (144 B = 36 words / 80 B = 20 words): the 8 lanes of an LDS.128 phase
 // start at word offsets lane*36 (or lane*20) mod 32 = distinct multiples of 4 -> conflict-free
@@ -186,6 +189,8 @@ struct ReadResult {
     bool has_n;
     bool resolved;
     bool numeric;
+    bool escalate;     // cascade: not settled by this launch's entries and not a certain reject either -> next sweep, whatever
+                       // the other rules say (so that the cascade writes exactly what the single sweep writes)
 };
 
 __device__ __forceinline__ int pick_rung(const FilterArgs &a, int kneed)
@@ -229,7 +234,7 @@ __device__ __forceinline__ void finish_read(const FilterArgs &a, bool valid, uin
     if (!res.resolved && !res.numeric) {
         // ee_raw is a lower bound.  The read is settled only if a decision is all that is asked
         // for and the bound already exceeds the cutoff (or another rule rejects it anyway).
-        undecided = a.exact || (reason == MOIRA_REASON_NONE && ok);
+        undecided = a.exact || res.escalate || (reason == MOIRA_REASON_NONE && ok);
         ok = false;
     }
     if (reason != MOIRA_REASON_NONE) ok = false;
@@ -270,6 +275,24 @@ __device__ __forceinline__ void flush_counters(const FilterArgs &a, const uint32
         uint32_t v = i < 16 ? s_cnt[i] : s_hist[i - 16];
         if (v) atomicAdd(&a.counters[i], (unsigned long long)v);
     }
+}
+
+// Upper bound of acc[kd - 1] = P(X <= kd - 1) from P(X = 0) and P(X = 1) alone.  The PMF of a Poisson-binomial count
+// is e_j(w) * prod(1 - p_i) with w_i = p_i / (1 - p_i), and Newton's inequalities for the elementary symmetric
+// polynomials give P[j+1] / P[j] <= (j / (j + 1)) * P[j] / P[j-1], hence P[j] <= P[0] * r^j / j! with r = P[1] / P[0].
+// The prefix version holds too (acc[kd - 1] never increases as bases are added), so the bound may be taken after any
+// number of bases.  Returns 1 when P[0] is too small for the quotient to be trusted.
+__device__ __forceinline__ double newton_bound(double p0, double p1, int kd)
+{
+    if (!(p0 > 1e-280)) return 1.0;
+    const double r = p1 / p0;
+    double term = p0, sum = p0;
+#pragma unroll 1
+    for (int j = 1; j < kd; j++) {
+        term = term * r / (double)j;
+        sum += term;
+    }
+    return sum == sum ? sum : 1.0;
 }
 
 // bernoullimodule.c:233-254: cumulative sum in index order, strict '>' against 1-alpha, then
@@ -580,8 +603,11 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
                 // remaining chunks are still staged and scanned for N/n (Ns stays exact) but the
                 // FP64 sweep -- the binding resource -- is skipped.
                 double tracked = P[0];
+                if (K >= 2 && a.k_dec > K) tracked = newton_bound(P[0], P[K >= 2 ? 1 : 0], a.k_dec);   // certain at the decision's K
+                else {
 #pragma unroll
-                for (int j = 1; j < K; j++) tracked += P[j];
+                    for (int j = 1; j < K; j++) tracked += P[j];
+                }
                 const bool certain = valid && tracked < a.oma - 1e-9;
                 const bool finished = !valid || processed >= g.eff;
                 if (__all_sync(FULL, certain || finished) && __any_sync(FULL, certain)) skip_math = true;
@@ -593,6 +619,7 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         res.ns = (int)ns;
         res.has_n = has_n != 0u;
         res.numeric = false;
+        res.escalate = false;
         res.processed = processed < g.eff ? processed : g.eff;
         if (MODE == 2) {
             // Upper quantile of the error count by Cornish-Fisher with the Poisson skew bound:
@@ -613,7 +640,12 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         }
         if (MODE == 0) {
             res.resolved = cdf_quantile<K>(P, a.oma, res.ee_raw);
-            if (res.processed < g.eff) { res.resolved = false; res.ee_raw = (double)(K - 1); }
+            const int kd = (K >= 2 && a.k_dec > K) ? a.k_dec : K;
+            if (res.processed < g.eff) { res.resolved = false; res.ee_raw = (double)(kd - 1); }
+            else if (kd > K && !res.resolved) {
+                if (newton_bound(P[0], P[K >= 2 ? 1 : 0], kd) < a.oma - 1e-9) res.ee_raw = (double)(kd - 1);   // j* >= kd: a certain reject, without the kd-entry sweep
+                else res.escalate = true;
+            }
         } else {
             const double lam = P[0];
             if (a.mode == MOIRA_MODE_EXPECTED_ERROR) {
@@ -663,15 +695,21 @@ template <int K, int MODE, bool EQP, bool TMA>
 __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int TPR_WARPS = tpr_warps(K);
-    constexpr bool PL = (EQP && MODE == 0 && !(MOIRA_PAIR_LUT && K <= 8)) || MODE == 1;
+    constexpr bool PL = (EQP && MODE == 0 && !(MOIRA_PAIR_LUT && K <= 8 && K > MOIRA_PL_MAXK)) || MODE == 1;
     extern __shared__ __align__(128) uint8_t smem[];
     if (a.queue && (a.seg_count ? *a.seg_count : *a.queue_count) == 0) return;   // empty rung / segment: nothing to set up
+    if (a.policy && *a.policy != a.policy_want) return;                          // the pilot chose the other first pass
     const TprCtx ctx = tpr_setup<TPR_WARPS, MODE, PL, TMA>(a, smem);
     const uint32_t *queue = a.queue && a.seg_start ? a.queue + *a.seg_start : a.queue;
     const uint32_t count = a.queue ? (a.seg_count ? *a.seg_count : *a.queue_count) : a.n;
-    tpr_tiles<K, MODE, PL, TMA>(a, &tmap, ctx, queue, count, blockIdx.x * TPR_WARPS + ctx.warp, gridDim.x * TPR_WARPS);
+    tpr_tiles<K, MODE, PL, TMA>(a, &tmap, ctx, queue, count, a.tile0 + blockIdx.x * TPR_WARPS + ctx.warp, gridDim.x * TPR_WARPS);
     __syncthreads();
     flush_counters(a, ctx.s_cnt, ctx.s_hist);
+}
+
+__global__ void policy_kernel(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy)
+{
+    *policy = *queue_count > max_pushed ? 1u : 0u;
 }
 
 // All thread-per-read rungs of the escalation ladder in ONE launch: the CTA sets its table up once and
@@ -841,6 +879,7 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
         res.has_n = has_n != 0u;
         res.resolved = found;
         res.numeric = false;
+        res.escalate = false;
         finish_read(a, lane == 0, r_local, g, res, s_cnt, s_hist, lane);
     }
     __syncthreads();
@@ -914,6 +953,7 @@ __global__ void __launch_bounds__(BLK_THREADS) blk_kernel(const FilterArgs a)
         res.ee_raw = js < 0 ? (double)(K - 1)
                    : js == 0 ? 0.0
                              : __dadd_rn((double)(js - 1), __ddiv_rn(__dsub_rn(a.oma, s_res[0]), __dsub_rn(s_res[1], s_res[0])));
+        res.escalate = false;
         res.processed = g.eff;
         res.ns = ns;
         res.has_n = has_n;
@@ -1236,6 +1276,12 @@ int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg0)
     case NB - 1: blk_kernel<<<cfg.sm_count, BLK_THREADS, BLK_SMEM, cfg.stream>>>(a); break;
     default: return -1;   // rungs 1..N_TPR_RUNGS run fused, see launch_ladder_tpr
     }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_policy(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s)
+{
+    policy_kernel<<<1, 1, 0, s>>>(queue_count, max_pushed, policy);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

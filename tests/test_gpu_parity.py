@@ -437,3 +437,66 @@ def test_device_fastq_parser_agrees_with_host_parser(ctx, monkeypatch):
     # the context is fine afterwards
     res3, _ = ctx.filter_fastq(text, p)
     assert np.array_equal(res3.ee, ref.ee)
+
+
+@pytest.mark.parametrize("profile,n,kw", [
+    ("v4", 40000, dict()), ("v4", 40000, dict(maxerrors=1.5)), ("v4", 40000, dict(uncert=0.02, ambigs="ignore")),
+    ("v3v4", 20000, dict()), ("v3v4", 20000, dict(maxerrors=6.0, round=True)), ("mixed", 20000, dict(maxerrors=4.2, length_sort=2)),
+    ("mixed", 20000, dict(truncate=250, ambigs="disallow", length_sort=2)), ("v4", 40000, dict(alpha=0.2)),
+    ("v4", 40000, dict(alpha=1e-6, maxerrors=2.0)),
+])
+def test_cascaded_first_pass_gives_identical_results(ctx, profile, n, kw):
+    """Decisions that need 3..8 PMF entries: the two-entry sweep + Newton-bound rejects + second sweep (cascade = 1)
+    must write what the single full-K sweep (cascade = 2) writes -- ee, Ns, flags, counters, bit for bit -- in both
+    modes, and both must agree with the oracle."""
+    slab, off, ln = synth.generate(profile, n, 31)
+    for exact in (False, True):
+        one = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact, cascade=2, **kw))
+        two = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact, cascade=1, **kw))
+        auto = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact, **kw))
+        for r in (two, auto):
+            assert np.array_equal(r.ee, one.ee) and np.array_equal(r.ns, one.ns) and np.array_equal(r.flags, one.flags)
+            assert np.array_equal(r.counters, one.counters)
+        p = FilterParams(exact_ee=exact, **{k: v for k, v in kw.items() if k != "length_sort"})
+        eff = np.minimum(ln, p.truncate) if p.truncate else ln
+        ee_o, ns_o = po.pb_batch(slab, off, eff.astype(np.uint32), p.alpha)
+        _check_decisions(two, ee_o, ns_o, ln, _has_n(slab, off, eff), p)
+        lb = two.lower_bound
+        assert np.array_equal(two.ee[~lb], ee_o[~lb]) and np.all(two.ee[lb] <= ee_o[lb]) and not (exact and lb.any())
+
+
+def test_cascade_pilot_chooses_per_batch(ctx):
+    """Batches large enough for the pilot launch (>= 8 x 2 tiles per warp): on clean-or-hopeless reads the pilot keeps
+    the cascade, on reads that mostly need 3-4 entries it switches the rest of the batch to the full-K sweep; either
+    way the results equal the single-sweep ones."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n = 1_400_000
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    borderline = torch.randint(20, 25, (n, synth.V4_STRIDE), dtype=torch.uint8, device=dev, generator=g)   # mean error count ~1.6
+    borderline[:, synth.V4_LEN:] = 0xFD
+    slabs = {"v4": synth.generate_v4_device(n, 77, dev), "borderline": borderline}
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, slab in slabs.items():
+        outs = []
+        for exact, cascade in ((False, 2), (False, 0), (True, 2), (True, 0)):
+            ee = torch.empty(n, dtype=torch.float64, device=dev)
+            ns = torch.empty(n, dtype=torch.int32, device=dev)
+            fl = torch.empty(n, dtype=torch.uint8, device=dev)
+            cnt = torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev)
+            before = ctx.launch_count
+            ctx.filter_device(slab.data_ptr(), None, None, synth.V4_STRIDE, synth.V4_LEN, n,
+                              FilterParams(exact_ee=exact, cascade=cascade), ee.data_ptr(), ns.data_ptr(), fl.data_ptr(),
+                              cnt.data_ptr(), stream)
+            torch.cuda.synchronize()
+            outs.append((ee.cpu().numpy(), ns.cpu().numpy(), fl.cpu().numpy(), cnt.cpu().numpy(), ctx.launch_count - before))
+        for a, b in ((0, 1), (2, 3)):
+            for k in range(4):
+                assert np.array_equal(outs[a][k], outs[b][k]), (name, a, k)
+        assert outs[0][4] == 1 and outs[1][4] == 5      # one sweep | pilot, verdict, two candidates, second sweep
+        idx = np.random.default_rng(3).choice(n, 2000, replace=False)
+        rows = slab[torch.as_tensor(idx, device=dev)].cpu().numpy()
+        off = np.arange(len(idx), dtype=np.uint64) * synth.V4_STRIDE
+        ee_o, ns_o = po.pb_batch(rows.reshape(-1), off, np.full(len(idx), synth.V4_LEN, np.uint32), 0.005)
+        assert np.array_equal(outs[3][0][idx], ee_o) and np.array_equal(outs[3][1][idx], ns_o)

@@ -1,0 +1,20 @@
+"""Two decision-mode steps over config C2 (for ncu captures): python tools/one_step.py [n_reads]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import moira_b200
+from moira_b200 import FilterParams, synth
+from moira_b200 import _lib as L
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+dev = torch.device("cuda", 0)
+ctx = moira_b200.Context(0)
+slab = synth.generate_v4_device(n, 20160106, dev)
+ee = torch.empty(n, dtype=torch.float64, device=dev); ns = torch.empty(n, dtype=torch.int32, device=dev)
+fl = torch.empty(n, dtype=torch.uint8, device=dev); cnt = torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev)
+for _ in range(2):
+    ctx.filter_device(slab.data_ptr(), None, None, synth.V4_STRIDE, synth.V4_LEN, n, FilterParams(exact_ee=False), ee.data_ptr(),
+                      ns.data_ptr(), fl.data_ptr(), cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+print(cnt.cpu().numpy()[:8])
+ctx.close()
