@@ -96,6 +96,8 @@ extern "C" {
 #define MOIRA_CNT_NEAR_CUTOFF  5
 #define MOIRA_CNT_LOWER_BOUND  6
 #define MOIRA_CNT_NUMERIC      7
+#define MOIRA_CNT_ESCALATED    8   /* reads a first pass could not settle (swept again with more entries); diagnostic: depends on
+                                      the cascade setting and the mode, unlike every other counter */
 #define MOIRA_CNT_HIST         16  /* 64 bins of floor(final ee); last bin = >= 63 */
 #define MOIRA_N_HIST           64
 #define MOIRA_N_COUNTERS       80

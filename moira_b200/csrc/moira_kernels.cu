@@ -246,6 +246,10 @@ __device__ __forceinline__ void finish_read(const FilterArgs &a, bool valid, uin
     if (numeric) { ok = false; if (reason == MOIRA_REASON_NONE) reason = MOIRA_REASON_ERRORS; }
 
     // ---- escalate: first pass -> classifier (rung 0); a rung -> the next one -------------------
+    if (a.rung < 0) {   // first pass: how many reads it hands on (diagnostic counter)
+        const unsigned pm = __ballot_sync(FULL, push);
+        if (pm && lane == 0) atomicAdd(&s_cnt[MOIRA_CNT_ESCALATED], (uint32_t)__popc(pm));
+    }
     push_read(a, push, a.rung + 1, r_local, lane);
     if (!valid || push) return;
 
@@ -286,11 +290,15 @@ __device__ __forceinline__ double newton_bound(double p0, double p1, int kd)
 {
     if (!(p0 > 1e-280)) return 1.0;
     const double r = p1 / p0;
-    double term = p0, sum = p0;
-#pragma unroll 1
-    for (int j = 1; j < kd; j++) {
-        term = term * r / (double)j;
-        sum += term;
+    // 1/j rounded up (the 1e-9 margin of the callers covers every rounding here many times over)
+    const double inv[8] = {1.0, 1.0, 0.5, 0.33333333333333337, 0.25, 0.2, 0.16666666666666669, 0.14285714285714288};
+    double term = p1, sum = p0 + p1;
+#pragma unroll
+    for (int j = 2; j < 8; j++) {
+        if (j < kd) {
+            term = term * r * inv[j];
+            sum += term;
+        }
     }
     return sum == sum ? sum : 1.0;
 }
@@ -603,14 +611,18 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
                 // remaining chunks are still staged and scanned for N/n (Ns stays exact) but the
                 // FP64 sweep -- the binding resource -- is skipped.
                 double tracked = P[0];
-                if (K >= 2 && a.k_dec > K) tracked = newton_bound(P[0], P[K >= 2 ? 1 : 0], a.k_dec);   // certain at the decision's K
-                else {
 #pragma unroll
-                    for (int j = 1; j < K; j++) tracked += P[j];
-                }
-                const bool certain = valid && tracked < a.oma - 1e-9;
+                for (int j = 1; j < K; j++) tracked += P[j];
+                bool certain = valid && tracked < a.oma - 1e-9;
                 const bool finished = !valid || processed >= g.eff;
-                if (__all_sync(FULL, certain || finished) && __any_sync(FULL, certain)) skip_math = true;
+                bool all_certain = __all_sync(FULL, certain || finished) && __any_sync(FULL, certain);
+                if (K >= 2 && a.k_dec > K && all_certain) {
+                    // a cascade launch stops only where the reject is certain at the decision's k_dec (the bound is at
+                    // least the tracked mass, so the test above is a cheap necessary condition)
+                    certain = valid && newton_bound(P[0], P[K >= 2 ? 1 : 0], a.k_dec) < a.oma - 1e-9;
+                    all_certain = __all_sync(FULL, certain || finished) && __any_sync(FULL, certain);
+                }
+                if (all_certain) skip_math = true;
             }
         }
 

@@ -456,7 +456,8 @@ def test_cascaded_first_pass_gives_identical_results(ctx, profile, n, kw):
         auto = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact, **kw))
         for r in (two, auto):
             assert np.array_equal(r.ee, one.ee) and np.array_equal(r.ns, one.ns) and np.array_equal(r.flags, one.flags)
-            assert np.array_equal(r.counters, one.counters)
+            same = np.arange(L.N_COUNTERS) != L.CNT_ESCALATED     # the one counter that describes the route, not the result
+            assert np.array_equal(r.counters[same], one.counters[same])
         p = FilterParams(exact_ee=exact, **{k: v for k, v in kw.items() if k != "length_sort"})
         eff = np.minimum(ln, p.truncate) if p.truncate else ln
         ee_o, ns_o = po.pb_batch(slab, off, eff.astype(np.uint32), p.alpha)
@@ -491,9 +492,13 @@ def test_cascade_pilot_chooses_per_batch(ctx):
                               cnt.data_ptr(), stream)
             torch.cuda.synchronize()
             outs.append((ee.cpu().numpy(), ns.cpu().numpy(), fl.cpu().numpy(), cnt.cpu().numpy(), ctx.launch_count - before))
+        same = np.arange(L.N_COUNTERS) != L.CNT_ESCALATED
         for a, b in ((0, 1), (2, 3)):
-            for k in range(4):
+            for k in range(3):
                 assert np.array_equal(outs[a][k], outs[b][k]), (name, a, k)
+            assert np.array_equal(outs[a][3][same], outs[b][3][same]), (name, a)
+        esc = outs[1][3][L.CNT_ESCALATED] / n
+        assert (esc < 0.3) if name == "v4" else (esc < 0.12)   # borderline batch: only the pilot's reads took the two-entry sweep
         assert outs[0][4] == 1 and outs[1][4] == 5      # one sweep | pilot, verdict, two candidates, second sweep
         idx = np.random.default_rng(3).choice(n, 2000, replace=False)
         rows = slab[torch.as_tensor(idx, device=dev)].cpu().numpy()

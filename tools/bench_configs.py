@@ -10,7 +10,7 @@ import moira_b200
 from moira_b200 import FilterParams, synth
 from moira_b200 import _lib as L
 
-def run(ctx, name, profile, n, seed, uncert=0.01, maxerrors=None, reps=5, length_sort=0):
+def run(ctx, name, profile, n, seed, uncert=0.01, maxerrors=None, reps=5, length_sort=0, cascade=0):
     t0 = time.time()
     slab, off, ln = synth.generate(profile, n, seed)
     gen_s = time.time() - t0
@@ -27,8 +27,8 @@ def run(ctx, name, profile, n, seed, uncert=0.01, maxerrors=None, reps=5, length
     cnt = torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     rows = []
-    for label, p in (("pb decision", FilterParams(uncert=uncert, maxerrors=maxerrors, exact_ee=False, length_sort=length_sort)),
-                     ("pb exact-ee", FilterParams(uncert=uncert, maxerrors=maxerrors, exact_ee=True, length_sort=length_sort)),
+    for label, p in (("pb decision", FilterParams(uncert=uncert, maxerrors=maxerrors, exact_ee=False, length_sort=length_sort, cascade=cascade)),
+                     ("pb exact-ee", FilterParams(uncert=uncert, maxerrors=maxerrors, exact_ee=True, length_sort=length_sort, cascade=cascade)),
                      ("poisson", FilterParams(error_calc="poisson", uncert=uncert, maxerrors=maxerrors, exact_ee=False, length_sort=length_sort)),
                      ("expected_error", FilterParams(error_calc="expected_error", uncert=uncert, maxerrors=maxerrors, exact_ee=False, length_sort=length_sort))):
         def step():
@@ -47,18 +47,21 @@ def run(ctx, name, profile, n, seed, uncert=0.01, maxerrors=None, reps=5, length
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         c = cnt.cpu().numpy()
-        rows.append((label, n / ms * 1e3, ms, c[L.CNT_ACCEPTED] / n))
+        rows.append((label, n / ms * 1e3, ms, c[L.CNT_ACCEPTED] / n, c[L.CNT_ESCALATED] / n))
     mean_len = float(ln.mean())
-    for label, rps, ms, acc in rows:
-        print("| %s | %s | %d | %.0f | %.3g | %.3f | %.3f |" % (name, label, n, mean_len, rps, ms, acc))
+    for label, rps, ms, acc, esc in rows:
+        print("| %s | %s | %d | %.0f | %.3g | %.3f | %.3f | %.3f |" % (name, label, n, mean_len, rps, ms, acc, esc))
     sys.stdout.flush()
 
 if __name__ == "__main__":
     ctx = moira_b200.Context(0)
-    print("| config | mode | reads | mean length | reads/s | ms/pass | accepted |\n|---|---|---|---|---|---|---|")
+    print("| config | mode | reads | mean length | reads/s | ms/pass | accepted | escalated by the first pass |\n|---|---|---|---|---|---|---|---|")
     if "--quick" not in sys.argv:
         run(ctx, "C2 v4 253 bp", "v4", 2_000_000, 20160106)
-        run(ctx, "C3 v3v4 ~450 bp", "v3v4", 1_000_000, 20160107)
+        run(ctx, "C2 v4 253 bp, cascade=2 (single sweep)", "v4", 2_000_000, 20160106, cascade=2)
+        run(ctx, "C3 v3v4 ~450 bp", "v3v4", 2_000_000, 20160107)
+        run(ctx, "C3 v3v4 ~450 bp, cascade=1 (forced)", "v3v4", 2_000_000, 20160107, cascade=1)
+        run(ctx, "C3 v3v4 ~450 bp, cascade=2 (single sweep)", "v3v4", 2_000_000, 20160107, cascade=2)
         run(ctx, "C4 ccs 1500 bp", "ccs", 200_000, 20160108)
     run(ctx, "C5 mixed 100-600 bp", "mixed", 1_000_000, 20160109)
     run(ctx, "C5 mixed, length_sort=1", "mixed", 1_000_000, 20160109, length_sort=1)
