@@ -6,7 +6,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-template <int VARIANT, int CHAINS>
+template <int VARIANT, int CHAINS, int K = 4>
 __global__ void probe(int iters, double *sink, const uint32_t *words)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -21,11 +21,11 @@ __global__ void probe(int iters, double *sink, const uint32_t *words)
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lut_lane = lut + ((VARIANT == 3) ? lane * 8 : (lane & 15) * 16);
-    double P[CHAINS][4];
+    double P[CHAINS][K];
 #pragma unroll
     for (int c = 0; c < CHAINS; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) P[c][j] = 1.0 / (1.0 + threadIdx.x + c + j);
+        for (int j = 0; j < K; j++) P[c][j] = 1.0 / (1.0 + threadIdx.x + c + j);
     uint32_t w = words[threadIdx.x & 255];
     double q = 0.9999, e = 1e-4;
     for (int it = 0; it < iters; it++) {
@@ -45,7 +45,7 @@ __global__ void probe(int iters, double *sink, const uint32_t *words)
                     q = __dsub_rn(1.0, e);
                 }
 #pragma unroll
-                for (int j = 3; j >= 1; j--) P[c][j] = __dadd_rn(__dmul_rn(q, P[c][j]), __dmul_rn(e, P[c][j - 1]));
+                for (int j = K - 1; j >= 1; j--) P[c][j] = __dadd_rn(__dmul_rn(q, P[c][j]), __dmul_rn(e, P[c][j - 1]));
                 P[c][0] = __dmul_rn(q, P[c][0]);
             }
         }
@@ -56,29 +56,29 @@ __global__ void probe(int iters, double *sink, const uint32_t *words)
 #pragma unroll
     for (int c = 0; c < CHAINS; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) s += P[c][j];
+        for (int j = 0; j < K; j++) s += P[c][j];
     if (s == 123.456) sink[0] = s;
 }
 
-template <int VARIANT, int CHAINS>
+template <int VARIANT, int CHAINS, int K = 4>
 void run(const char *name, int threads, int blocks_per_sm, int sms, double *sink, uint32_t *words)
 {
     const int iters = 20000 / CHAINS;
     const int smem = 2 * 65536 + 1024;
-    cudaFuncSetAttribute(probe<VARIANT, CHAINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(probe<VARIANT, CHAINS, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    probe<VARIANT, CHAINS><<<sms * blocks_per_sm, threads, smem>>>(iters / 10, sink, words);
+    probe<VARIANT, CHAINS, K><<<sms * blocks_per_sm, threads, smem>>>(iters / 10, sink, words);
     cudaEventRecord(a);
-    probe<VARIANT, CHAINS><<<sms * blocks_per_sm, threads, smem>>>(iters, sink, words);
+    probe<VARIANT, CHAINS, K><<<sms * blocks_per_sm, threads, smem>>>(iters, sink, words);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms;
     cudaEventElapsedTime(&ms, a, b);
     cudaError_t err = cudaGetLastError();
-    double fp64 = (double)sms * blocks_per_sm * threads * (double)iters * CHAINS * 4 * (VARIANT == 3 ? 11 : 10);
+    double fp64 = (double)sms * blocks_per_sm * threads * (double)iters * CHAINS * 4 * (3 * K - 2 + (VARIANT == 3 ? 1 : 0));
     double bases = (double)sms * blocks_per_sm * threads * (double)iters * CHAINS * 4;
-    printf("%-28s warps/SM %2d chains %d : %7.3f ms  %6.2f TFP64op/s  %6.2f Gbase/s  (%s)\n", name,
+    printf("K=%d %-28s warps/SM %2d chains %d : %7.3f ms  %6.2f TFP64op/s  %6.2f Gbase/s  (%s)\n", K, name,
            threads / 32 * blocks_per_sm, CHAINS, ms, fp64 / ms / 1e9, bases / ms / 1e6, cudaGetErrorString(err));
 }
 
@@ -104,5 +104,15 @@ int main()
     run<2, 2>("fp64 + PRMT + LDS.128", 512, 1, sms, sink, words);
     run<3, 2>("fp64 + PRMT + LDS.64 + DSUB", 512, 1, sms, sink, words);
     run<2, 2>("fp64 + PRMT + LDS.128", 256, 1, sms, sink, words);
+    // the two-entry sweep of the cascade (K = 2)
+    for (int threads : {512, 768, 1024}) {
+        run<0, 1, 2>("fp64 only", threads, 1, sms, sink, words);
+        run<3, 1, 2>("fp64 + PRMT + LDS.64 + DSUB", threads, 1, sms, sink, words);
+        run<2, 1, 2>("fp64 + PRMT + LDS.128", threads, 1, sms, sink, words);
+    }
+    run<0, 2, 2>("fp64 only", 512, 1, sms, sink, words);
+    run<3, 2, 2>("fp64 + PRMT + LDS.64 + DSUB", 512, 1, sms, sink, words);
+    run<3, 4, 2>("fp64 + PRMT + LDS.64 + DSUB", 512, 1, sms, sink, words);
+    run<2, 2, 2>("fp64 + PRMT + LDS.128", 512, 1, sms, sink, words);
     return 0;
 }
