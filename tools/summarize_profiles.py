@@ -47,8 +47,11 @@ with open(os.path.join(out, "%s_launches_summary.md" % tag), "w") as fh:
     fh.write("| kernel | launches | total ms | share of our kernels | mean us |\n|---|---|---|---|---|\n")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         fh.write("| `%s` | %d | %.3f | %.1f %% | %.1f |\n" % (k.replace("moira::<unnamed>::", ""), a[0], a[1] / 1e6, 100 * a[1] / tot, a[1] / a[0] / 1e3))
-    fh.write("\nThe decision-mode step is one `tpr_kernel<4,0,1>` launch (pb_tpr<K=4>); exact-ee steps add the classifier\n"
-             "(`tpr_kernel<2,2,1>`) and the ladder rungs. `fp64_peak_kernel` is the roofline probe, outside the timed region.\n")
+    fh.write("\nA decision-mode step is the `pb_cascade<2,4>` group: `tpr_kernel<2,0,1,1>` twice (pilot over the first 151 552 reads, then\n"
+             "the rest), `policy_kernel`, `tpr_kernel<4,0,1,1>` (the candidate not chosen: returns at once) and `tpr_kernel<4,0,1,0>` over the\n"
+             "escalated reads (empty on this workload); the `cascade = 2` steps of the bench (roofline.single_sweep) are one full\n"
+             "`tpr_kernel<4,0,1,1>` launch each. Exact-ee steps add the classifier (`tpr_kernel<2,2,1,0>`) and the ladder rungs; `tpr_kernel<1,1,1,1>`\n"
+             "is the Poisson / expected-error sweep (modes section). `fp64_peak_kernel` is the roofline probe, outside the timed region.\n")
 
 # ---- full capture of the dominant kernel ---------------------------------------------------------------
 rep = os.path.join(ROOT, "gpurun_out", "%s_pb_tpr4.ncu-rep" % tag)
@@ -107,8 +110,10 @@ with open(os.path.join(out, "%s_pb_tpr4_ncu.md" % tag), "w") as fh:
     fh.write("\nDFMA: %.4f per base (%.1f per read and thread) -- all of it the IEEE division of the interpolation step\n"
              "(`__ddiv_rn`, once per read, bernoullimodule.c:172); the PMF recurrence itself is DMUL/DADD only.\n"
              % (cnt.get("DFMA", 0) / base_warps, cnt.get("DFMA", 0) / base_warps * 253))
-json.dump({"pb_tpr<K=4>": {"dram_bytes_per_read": traffic / reads, "source": "profiles/%s_pb_tpr4_ncu.md" % tag}},
-          open(os.path.join(out, "traffic.json"), "w"), indent=1)
+tj_path = os.path.join(out, "traffic.json")
+tj = json.load(open(tj_path)) if os.path.exists(tj_path) else {}
+tj["pb_tpr<K=4>"] = {"dram_bytes_per_read": traffic / reads, "source": "profiles/%s_pb_tpr4_ncu.md" % tag}
+json.dump(tj, open(tj_path, "w"), indent=1)
 print(open(os.path.join(out, "%s_pb_tpr4_ncu.md" % tag)).read())
 print(open(os.path.join(out, "%s_launches_summary.md" % tag)).read())
 
