@@ -62,6 +62,7 @@ def _pool_chunk(chunk):
 
 
 _POOL = None   # forked in main() before CUDA is initialised (the workers only ever run _pool_chunk)
+_OUT = sys.stdout   # main() points this at the real stdout and file descriptor 1 at stderr
 
 
 def run_reference(args):
@@ -90,7 +91,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 class ClockSampler(threading.Thread):
@@ -497,6 +498,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "reads_per_gpu": n, "read_len": READ_LEN, "row_stride": STRIDE,
                        "error_calc": "poisson_binomial", "mode": "decision (exact ee for accepted reads, lower bound for certain rejects)",
+                       "first_pass": "cascade = 0 (library default): pilot launch decides per batch between the two-entry sweep with Newton-bound rejects and the single K=4 sweep",
                        "l2": "inputs (2.56 GB/GPU) larger than L2; no flush", "accepted_fraction": accepted_frac,
                        "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU, NCCL all-reduce of 80 counters per step",
                        "rank_cpu_affinity": numa_cpus},
@@ -504,7 +506,7 @@ def run_ours(args):
             "clocks": sampler.summary(), "parity": parity, "modes": modes, "e2e_parse": e2e_parse, "contigs": contigs,
             "exact_ee": {"value": value_exact, "unit": "reads/s", "note": "exact statistic for every read (escalation ladder), device-resident"},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -520,7 +522,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    global _POOL
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    # NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the run and the line goes to the real one.
+    global _POOL, _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl != "reference" and int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu:
         try:
             import multiprocessing as mp
