@@ -32,6 +32,11 @@ def test_header_constants_match_binding():
         if hasattr(L, k):
             assert getattr(L, k) == int(v, 0), k
     assert ctypes.sizeof(L.Params) == 56
+    # the ctypes mirror of moira_params has the header's fields, in the header's order
+    body = re.search(r"typedef struct moira_params \{(.*?)\} moira_params;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:int32_t|uint32_t|double)\s+(\w+)\s*;", body)
+    assert fields == [f[0] for f in L.Params._fields_] and "cascade" in fields
 
 
 def test_lut_matches_oracle_tables():
