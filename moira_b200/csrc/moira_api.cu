@@ -111,6 +111,8 @@ struct FqSlot {
     size_t h_res_cap = 0;
     uint32_t *h_meta = nullptr;    // pinned: max length, min length, first bad record
     uint64_t pos = 0, bytes = 0, n_rec = 0, first_read = 0;
+    bool counted = true;           // n_rec was counted by the host planner (else it is the device's, read back with the meta words)
+    bool final = false;            // the chunk reaches the end of the text
     uint64_t skip = 0;             // the device buffer starts `skip` bytes before the chunk (page-aligned source of the copy)
     cudaEvent_t ev = nullptr;      // behind the chunk's latest D2H: what the host waits for, not the whole stream
     int state = 0;                 // 0 free, 1 indexed (meta on its way), 2 filtering (results on their way)
@@ -165,6 +167,7 @@ struct moira_ctx {
     size_t fq_ring_cap[6] = {};
     DevBuf fq_counters;
     int device_parse = 1;
+    int fq_guess_cuts = 1;
     // paired-end contig construction: per-stream device buffers, traceback scratch, posterior tables
     PairBufs pb[2];
     DevBuf trace, hbuf, post, pair_counters;
@@ -541,6 +544,7 @@ static int ctx_init(moira_ctx *c, int device, int sm_count)
     c->sm_count = sm_count;
     build_tables(c->h_p, c->h_q, c->h_e, &c->e_equals_p);
     if (const char *e = getenv("MOIRA_B200_NO_LENSORT")) c->length_sort = (e[0] == '1') ? 0 : 1;   // diagnostics
+    if (const char *e = getenv("MOIRA_B200_FQ_COUNT")) c->fq_guess_cuts = (e[0] == '1') ? 0 : 1;   // diagnostics: always count the chunk cuts on the host
     if (const char *e = getenv("MOIRA_B200_HOST_PARSE")) c->device_parse = (e[0] == '1') ? 0 : 1;   // moira_filter_fastq: parse on the host cores instead
     if (const char *e = getenv("MOIRA_B200_NO_CASCADE")) c->cascade = (e[0] == '1') ? 0 : 1;   // diagnostics: full-K first pass always
     if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
@@ -845,9 +849,11 @@ int ensure_pinned(uint8_t **p, size_t *cap, size_t bytes)
 // record by fastq_plan_chunk): H2D of the text, newline index, record table (lengths, validation), then -- once the
 // host has read back the chunk's max / min length -- slab conversion, the filter, and D2H of the results.  Three
 // chunks are in flight: while chunk k is being indexed, chunk k-1 is filtered and chunk k-2 is handed to the caller.
+constexpr int FQ_RETRY_COUNTED = 0x7fff0001;   // internal: a guessed chunk cut failed the device's check -> run again, counting on the host
+
 int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int fastq_offset, int lower_n, const moira_params *params,
                         uint64_t max_reads, double *ee_out, int32_t *ns_out, uint8_t *flags_out, uint32_t *lengths_out,
-                        uint64_t *counters_out, uint64_t *n_reads_out)
+                        uint64_t *counters_out, uint64_t *n_reads_out, bool guess_cuts)
 {
     constexpr uint64_t RANGE = 64ull << 20;
     int rc;
@@ -860,11 +866,28 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
     const bool pinned_src = text_bytes && cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     for (auto &q : c->fqd) q.state = 0;
+    uint64_t n_assigned = 0;   // records of the chunks filtered so far (chunk order): where a chunk's results go
 
     // stage 2 of a chunk: its index is done -> convert, filter, results on their way
     auto filter_chunk = [&](FqSlot &q) -> int {
         cudaStream_t s = c->streams[q.stream];
         CU(cudaEventSynchronize(q.ev));
+        if (!q.counted) {
+            // the device's own count: a chunk cut at a guessed record start must hold whole records (the last one may
+            // end with a partial record, ignored as the reference ignores it)
+            if (q.h_meta[5] || (q.h_meta[4] && !q.final)) return FQ_RETRY_COUNTED;
+            q.n_rec = q.h_meta[3];
+        }
+        q.first_read = n_assigned;
+        if (n_assigned + q.n_rec > max_reads) return fail(MOIRA_ERR_BAD_ARG, "more than max_reads = %llu records", (unsigned long long)max_reads);
+        n_assigned += q.n_rec;
+        if (q.n_rec == 0) { q.state = 0; return MOIRA_OK; }
+        {
+            int r0;
+            if ((r0 = ensure(q.ee, q.n_rec * 8)) || (r0 = ensure(q.ns, q.n_rec * 4)) || (r0 = ensure(q.flags, q.n_rec)) ||
+                (r0 = ensure_pinned(&q.h_res, &q.h_res_cap, q.n_rec * 17 + 64)))
+                return r0;
+        }
         const uint32_t maxlen = q.h_meta[0], minlen = q.h_meta[1], bad = q.h_meta[2];
         if (bad != 0xFFFFFFFFu) {
             // let the host parser raise the reference's error for this range (same message as the host path)
@@ -898,7 +921,7 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         CU(cudaMemcpyAsync(q.h_res + m * 8, q.ns.p, m * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(q.h_res + m * 12, q.len.p, m * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(q.h_res + m * 16, q.flags.p, m, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(q.h_meta, q.meta.p, 12, cudaMemcpyDeviceToHost, s));     // a quality above 252 shows up here
+        CU(cudaMemcpyAsync(q.h_meta, q.meta.p, 12, cudaMemcpyDeviceToHost, s));     // a quality above 252 shows up here (words 0..2 only)
         CU(cudaEventRecord(q.ev, s));
         q.state = 2;
         return MOIRA_OK;
@@ -926,7 +949,7 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
     if (!pinned_src)
         for (int r = 0; r < RING; r++)
             if ((rc = ensure_pinned(&c->fq_ring[r], &c->fq_ring_cap[r], std::min<uint64_t>(RANGE, text_bytes) + 64))) return rc;
-    struct Plan { uint64_t pos, bytes, n_rec, n_nl; const uint8_t *staged; int rc; bool last; };
+    struct Plan { uint64_t pos, bytes, n_rec, n_nl; const uint8_t *staged; int rc; bool last; bool counted; };
     std::deque<Plan> plans;
     std::mutex pm;
     std::condition_variable pcv;
@@ -935,7 +958,7 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
     std::thread planner([&]() {
         uint64_t p = 0;
         for (uint64_t i = 0;; i++) {
-            Plan pl{p, 0, 0, 0, nullptr, MOIRA_OK, false};
+            Plan pl{p, 0, 0, 0, nullptr, MOIRA_OK, false, true};
             uint8_t *ring = pinned_src ? nullptr : c->fq_ring[i % RING];
             if (ring) {
                 std::unique_lock<std::mutex> lk(pm);
@@ -943,9 +966,14 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
                 if (stop) return;
             }
             if (p >= text_bytes) pl.last = true;
-            else pl.rc = fastq_plan_chunk(text, text_bytes, p, RANGE, ring, &pl.bytes, &pl.n_rec, &pl.n_nl);
+            else {
+                int ok = 0;
+                if (guess_cuts) pl.rc = fastq_plan_chunk_fast(text, text_bytes, p, RANGE, ring, &pl.bytes, &ok);
+                if (ok && !pl.rc) { pl.counted = false; pl.n_rec = 0xFFFFFFFFull; }
+                else pl.rc = fastq_plan_chunk(text, text_bytes, p, RANGE, ring, &pl.bytes, &pl.n_rec, &pl.n_nl);
+            }
             pl.staged = ring;
-            if (pl.rc || pl.n_rec == 0) pl.last = true;
+            if (pl.rc || pl.n_rec == 0 || (!pl.counted && pl.bytes == 0)) pl.last = true;
             {
                 std::unique_lock<std::mutex> lk(pm);
                 pcv.wait(lk, [&] { return stop || plans.size() < 4; });
@@ -971,7 +999,7 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         ~PlannerJoin() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); if (t.joinable()) t.join(); }
     } planner_join{planner, pm, pcv, stop};
 
-    uint64_t pos = 0, n_done = 0;
+    uint64_t pos = 0;
     int k = 0;
     rc = MOIRA_OK;
     const bool dbg = getenv("MOIRA_B200_FQ_DEBUG") != nullptr;
@@ -993,35 +1021,41 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
             break;
         }
         t_plan += now() - t0; t0 = now();
-        if (n_done + n_rec > max_reads) { rc = fail(MOIRA_ERR_BAD_ARG, "more than max_reads = %llu records", (unsigned long long)max_reads); break; }
-        q.pos = pos; q.bytes = bytes; q.n_rec = n_rec; q.first_read = n_done; q.stream = k & 1;
+        q.pos = pos; q.bytes = bytes; q.n_rec = n_rec; q.stream = k & 1;
+        q.counted = pl.counted; q.final = pos + bytes >= text_bytes;
         // a pinned source is copied from its page boundary (unaligned DMA is several times slower); staging is aligned anyway
         q.skip = pinned_src ? (uint64_t)((uintptr_t)(text + pos) & 4095u) : 0;
         if (q.skip > pos) q.skip = 0;   // never read before the caller's buffer
         const uint64_t span = q.skip + bytes;
         cudaStream_t s = c->streams[q.stream];
         const uint32_t nb = fq_blocks(span);
+        // sizes of the newline index and the record table: counted by the planner, or (guessed cut) an estimate the
+        // kernels respect -- 8 bytes per line; a text with shorter lines fails the device's check and is counted
+        const uint64_t nl_cap = pl.counted ? n_nl + 16 : span / 8 + 64;
+        const uint64_t rec_cap = pl.counted ? n_rec : nl_cap / 4 + 1;
+        const uint32_t extra_line = (q.final && bytes && text[pos + bytes - 1] != '\n') ? 1u : 0u;
         if (!q.ev) CU(cudaEventCreateWithFlags(&q.ev, cudaEventDisableTiming));
         if ((rc = ensure(q.text, span + 64)) || (rc = ensure(q.bcnt, (size_t)nb * 4 + 16)) || (rc = ensure(q.bstart, (size_t)nb * 4 + 16)) ||
-            (rc = ensure(q.nl, (size_t)n_nl * 4 + 64)) || (rc = ensure(q.soff, n_rec * 4)) || (rc = ensure(q.qoff, n_rec * 4)) ||
-            (rc = ensure(q.len, n_rec * 4)) || (rc = ensure(q.ee, n_rec * 8)) || (rc = ensure(q.ns, n_rec * 4)) ||
-            (rc = ensure(q.flags, n_rec)) || (rc = ensure(q.meta, 16)) || (rc = ensure_pinned(&q.h_res, &q.h_res_cap, n_rec * 17 + 64)))
+            (rc = ensure(q.nl, (size_t)nl_cap * 4 + 64)) || (rc = ensure(q.soff, rec_cap * 4)) || (rc = ensure(q.qoff, rec_cap * 4)) ||
+            (rc = ensure(q.len, rec_cap * 4)) || (rc = ensure(q.meta, 64)))
             break;
         if (!q.h_meta && cudaHostAlloc((void **)&q.h_meta, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); rc = fail(MOIRA_ERR_NOMEM, "cudaHostAlloc failed"); break; }
         q.h_meta[0] = 0; q.h_meta[1] = 0xFFFFFFFFu; q.h_meta[2] = 0xFFFFFFFFu;
-        CU(cudaMemcpyAsync(q.meta.p, q.h_meta, 12, cudaMemcpyHostToDevice, s));
+        q.h_meta[3] = q.h_meta[4] = q.h_meta[5] = q.h_meta[6] = q.h_meta[7] = 0;
+        CU(cudaMemcpyAsync(q.meta.p, q.h_meta, 32, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(q.text.p, pinned_src ? (const void *)(text + pos - q.skip) : (const void *)pl.staged, span, cudaMemcpyHostToDevice, s));
-        if (launch_fq_index((const uint8_t *)q.text.p, q.skip, span, (uint32_t *)q.bcnt.p, (uint32_t *)q.bstart.p, (uint32_t *)q.nl.p, s) ||
+        if (launch_fq_index((const uint8_t *)q.text.p, q.skip, span, (uint32_t *)q.bcnt.p, (uint32_t *)q.bstart.p, (uint32_t *)q.nl.p,
+                            (uint32_t)std::min<uint64_t>(nl_cap, 0xFFFFFFFFull), s) ||
             launch_fq_records((const uint8_t *)q.text.p, q.skip, span, (const uint32_t *)q.nl.p, (const uint32_t *)q.bstart.p + nb, (uint32_t)n_rec,
-                              (uint32_t *)q.soff.p, (uint32_t *)q.qoff.p, (uint32_t *)q.len.p, (uint32_t *)q.meta.p, s)) {
+                              extra_line, (uint32_t)std::min<uint64_t>(nl_cap, 0xFFFFFFFFull), (uint32_t)rec_cap, (uint32_t *)q.soff.p,
+                              (uint32_t *)q.qoff.p, (uint32_t *)q.len.p, (uint32_t *)q.meta.p, s)) {
             rc = fail(MOIRA_ERR_CUDA, "fastq index launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
         c->launches += 4;
-        CU(cudaMemcpyAsync(q.h_meta, q.meta.p, 12, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(q.h_meta, q.meta.p, 32, cudaMemcpyDeviceToHost, s));
         CU(cudaEventRecord(q.ev, s));
         q.state = 1;
-        n_done += n_rec;
         t_issue += now() - t0; t0 = now();
         // chunk k - 1 has had a whole iteration for its copy and index: filter it now
         if (k >= 1) {
@@ -1048,7 +1082,7 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         return rc;
     }
     if (counters_out) CU(cudaMemcpy(counters_out, d_cnt, MOIRA_N_COUNTERS * 8, cudaMemcpyDeviceToHost));
-    *n_reads_out = n_done;
+    *n_reads_out = n_assigned;
     return MOIRA_OK;
 }
 
@@ -1066,9 +1100,16 @@ int moira_filter_fastq(moira_ctx *c, const char *text, uint64_t text_bytes, int 
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     if (params->slab_format != MOIRA_SLAB_Q8) return fail(MOIRA_ERR_BAD_ARG, "slab_format does not apply to FASTQ text");
-    if (c->device_parse)
-        return filter_fastq_device(c, text, text_bytes, fastq_offset, lower_n_ambiguous, params, max_reads, ee_out, ns_out, flags_out,
-                                   lengths_out, counters_out, n_reads_out);
+    if (c->device_parse) {
+        // first with chunk cuts guessed from the text's local structure (no host pass over the text); if the device
+        // finds a chunk that does not hold whole records, once more with the cuts counted on the host
+        rc = filter_fastq_device(c, text, text_bytes, fastq_offset, lower_n_ambiguous, params, max_reads, ee_out, ns_out, flags_out,
+                                 lengths_out, counters_out, n_reads_out, c->fq_guess_cuts != 0);
+        if (rc == FQ_RETRY_COUNTED)
+            rc = filter_fastq_device(c, text, text_bytes, fastq_offset, lower_n_ambiguous, params, max_reads, ee_out, ns_out, flags_out,
+                                     lengths_out, counters_out, n_reads_out, false);
+        return rc;
+    }
     constexpr int SLOTS = 3;
     const uint64_t RANGE = 64ull << 20;
     struct Slot { int ticket = -1; uint64_t counters[MOIRA_N_COUNTERS]; };

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(1024) fq_scan_blocks(const uint32_t *block_cnt
     if (threadIdx.x == 0) block_start[nb] = carry;
 }
 
-__global__ void __launch_bounds__(NL_THREADS) fq_write_nl(const uint4 *text16, uint64_t lo, uint64_t n, const uint32_t *block_start, uint32_t *nl_pos)
+__global__ void __launch_bounds__(NL_THREADS) fq_write_nl(const uint4 *text16, uint64_t lo, uint64_t n, const uint32_t *block_start, uint32_t *nl_pos,
+                                                          uint32_t cap)
 {
     uint32_t m[4];
     const uint64_t tid = (uint64_t)blockIdx.x * NL_THREADS + threadIdx.x;
@@ -132,20 +133,31 @@ __global__ void __launch_bounds__(NL_THREADS) fq_write_nl(const uint4 *text16, u
         while (b) {
             const int bit = __ffs(b) - 1;       // 7, 15, 23 or 31
             b &= b - 1;
-            nl_pos[out++] = (uint32_t)(tid * 16 + 4 * k + (bit >> 3));
+            if (out < cap) nl_pos[out] = (uint32_t)(tid * 16 + 4 * k + (bit >> 3));   // cap: the index was sized by an estimate
+            out++;
         }
     }
 }
 
 __device__ __forceinline__ bool is_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }   // str.strip()'s set
 
-// meta: [0] max length, [1] min length, [2] smallest bad record index (0xFFFFFFFF: none)
+// meta: [0] max length, [1] min length, [2] smallest bad record index (0xFFFFFFFF: none), and for chunks whose record
+// count the host did not establish (n_rec == 0xFFFFFFFF: it is lines / 4 of the device's own newline count):
+// [3] records, [4] lines % 4, [5] 1 if the newline index or the record table would overflow (nothing is parsed then)
 __global__ void __launch_bounds__(256) fq_records(const uint8_t *text, uint64_t lo, uint64_t n, const uint32_t *nl_pos, const uint32_t *n_nl,
-                                                  uint32_t n_rec, uint32_t *seq_off, uint32_t *qual_off, uint32_t *len, uint32_t *meta)
+                                                  uint32_t n_rec, uint32_t extra_line, uint32_t nl_cap, uint32_t rec_cap, uint32_t *seq_off,
+                                                  uint32_t *qual_off, uint32_t *len, uint32_t *meta)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t l = 0, lmin = 0xFFFFFFFFu;
     bool bad = false;
+    if (n_rec == 0xFFFFFFFFu) {
+        const uint32_t lines = *n_nl + extra_line;
+        n_rec = lines / 4;
+        const bool over = *n_nl > nl_cap || n_rec > rec_cap;
+        if (r == 0) { meta[3] = n_rec; meta[4] = lines & 3u; meta[5] = over ? 1u : 0u; }
+        if (over) n_rec = 0;
+    }
     if (r < n_rec) {
         const uint32_t total = *n_nl;
         auto line = [&](uint32_t k, uint32_t &b, uint32_t &e) {
@@ -207,21 +219,25 @@ uint32_t fq_blocks(uint64_t n) { return (uint32_t)((n + NL_THREADS * 16 - 1) / (
 
 // the chunk is bytes [lo, n) of the device buffer d_text (16-byte aligned)
 int launch_fq_index(const uint8_t *d_text, uint64_t lo, uint64_t n, uint32_t *d_block_cnt, uint32_t *d_block_start, uint32_t *d_nl_pos,
-                    cudaStream_t s)
+                    uint32_t nl_cap, cudaStream_t s)
 {
     const uint32_t nb = fq_blocks(n);
     if (nb == 0) return 0;
     fq_count_nl<<<nb, NL_THREADS, 0, s>>>(reinterpret_cast<const uint4 *>(d_text), lo, n, d_block_cnt);
     fq_scan_blocks<<<1, 1024, 0, s>>>(d_block_cnt, nb, d_block_start);
-    fq_write_nl<<<nb, NL_THREADS, 0, s>>>(reinterpret_cast<const uint4 *>(d_text), lo, n, d_block_start, d_nl_pos);
+    fq_write_nl<<<nb, NL_THREADS, 0, s>>>(reinterpret_cast<const uint4 *>(d_text), lo, n, d_block_start, d_nl_pos, nl_cap);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// n_rec == 0xFFFFFFFF: the record count is the device's (see fq_records); the grid then covers rec_cap records
 int launch_fq_records(const uint8_t *d_text, uint64_t lo, uint64_t n, const uint32_t *d_nl_pos, const uint32_t *d_n_nl, uint32_t n_rec,
-                      uint32_t *d_seq_off, uint32_t *d_qual_off, uint32_t *d_len, uint32_t *d_meta, cudaStream_t s)
+                      uint32_t extra_line, uint32_t nl_cap, uint32_t rec_cap, uint32_t *d_seq_off, uint32_t *d_qual_off, uint32_t *d_len,
+                      uint32_t *d_meta, cudaStream_t s)
 {
     if (n_rec == 0) return 0;
-    fq_records<<<(n_rec + 255) / 256, 256, 0, s>>>(d_text, lo, n, d_nl_pos, d_n_nl, n_rec, d_seq_off, d_qual_off, d_len, d_meta);
+    const uint32_t cover = n_rec == 0xFFFFFFFFu ? rec_cap : n_rec;
+    fq_records<<<(cover + 255) / 256, 256, 0, s>>>(d_text, lo, n, d_nl_pos, d_n_nl, n_rec, extra_line, nl_cap, rec_cap, d_seq_off, d_qual_off,
+                                                 d_len, d_meta);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

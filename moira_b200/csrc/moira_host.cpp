@@ -483,6 +483,39 @@ int moira::fastq_plan_chunk(const char *text, uint64_t text_bytes, uint64_t pos,
     return MOIRA_OK;
 }
 
+// Plan a chunk WITHOUT reading it: cut text[pos, pos + target) at the last line start that looks like the start of a
+// record -- a line beginning with '@' whose second successor begins with '+'.  A quality line may begin with '@' too,
+// but then the line two further down is a sequence line, and those never begin with '+'.  The device verifies the guess
+// (a chunk cut this way must hold a multiple of four lines); the caller falls back to fastq_plan_chunk when it fails.
+int moira::fastq_plan_chunk_fast(const char *text, uint64_t text_bytes, uint64_t pos, uint64_t target_bytes, uint8_t *copy_to,
+                                 uint64_t *chunk_bytes_out, int *ok)
+{
+    const uint64_t len = std::min<uint64_t>(target_bytes, text_bytes - pos);
+    const char *base = text + pos, *text_end = text + text_bytes;
+    uint64_t end = len;
+    *ok = 1;
+    if (pos + len < text_bytes) {
+        *ok = 0;
+        uint64_t p = len;
+        for (int tries = 0; tries < 64 && p > 0; tries++) {
+            const char *nl = (const char *)memrchr(base, '\n', p);
+            if (!nl) break;
+            const uint64_t s = (uint64_t)(nl - base) + 1;
+            p = (uint64_t)(nl - base);
+            if (s >= len || base[s] != '@') continue;
+            const char *l1 = (const char *)memchr(base + s, '\n', (size_t)(text_end - (base + s)));
+            if (!l1 || l1 + 1 >= text_end) continue;
+            const char *l2 = (const char *)memchr(l1 + 1, '\n', (size_t)(text_end - (l1 + 1)));
+            if (!l2 || l2 + 1 >= text_end) continue;
+            if (l2[1] == '+') { end = s; *ok = 1; break; }
+        }
+        if (!*ok || end == 0) { *ok = 0; return MOIRA_OK; }
+    }
+    if (copy_to && end) parallel_memcpy(copy_to, base, end);
+    *chunk_bytes_out = end;
+    return MOIRA_OK;
+}
+
 // ---- FASTA + QUAL ------------------------------------------------------------------------------------
 // Record semantics of parse_fasta_and_qual (moira/moira.py:1093-1149, single-end): both files hold one
 // header line and one data line per record ("Expects sequences and qualities to be stored in a single

@@ -153,15 +153,19 @@ int launch_contigs(ContigArgs a, bool want_score, const LaunchCfg &cfg);   // 0 
 // ---- FASTQ parsing on the device (moira_fastq.cu) ---------------------------------------------------------
 uint32_t fq_blocks(uint64_t n);   // 4 KB text blocks of a chunk
 int launch_fq_index(const uint8_t *d_text, uint64_t lo, uint64_t n, uint32_t *d_block_cnt, uint32_t *d_block_start, uint32_t *d_nl_pos,
-                    cudaStream_t s);
+                    uint32_t nl_cap, cudaStream_t s);
 int launch_fq_records(const uint8_t *d_text, uint64_t lo, uint64_t n, const uint32_t *d_nl_pos, const uint32_t *d_n_nl, uint32_t n_rec,
-                      uint32_t *d_seq_off, uint32_t *d_qual_off, uint32_t *d_len, uint32_t *d_meta, cudaStream_t s);
+                      uint32_t extra_line, uint32_t nl_cap, uint32_t rec_cap, uint32_t *d_seq_off, uint32_t *d_qual_off, uint32_t *d_len,
+                      uint32_t *d_meta, cudaStream_t s);
 int launch_fq_convert(const uint8_t *d_text, const uint32_t *d_seq_off, const uint32_t *d_qual_off, const uint32_t *d_len,
                       uint32_t n_rec, uint32_t stride, int lower_n, int qbase, uint8_t *d_slab, uint32_t *d_meta, int sm_count,
                       cudaStream_t s);
 void parallel_memcpy(void *dst, const void *src, uint64_t bytes);   // all host threads
 int fastq_plan_chunk(const char *text, uint64_t text_bytes, uint64_t pos, uint64_t target_bytes, uint8_t *copy_to,
                      uint64_t *chunk_bytes_out, uint64_t *n_rec_out, uint64_t *n_newlines_out);
+// the same without reading the chunk: the cut is the last line start that looks like a record start (ok = 0: none found)
+int fastq_plan_chunk_fast(const char *text, uint64_t text_bytes, uint64_t pos, uint64_t target_bytes, uint8_t *copy_to,
+                          uint64_t *chunk_bytes_out, int *ok);
 
 // moira_parse_fastq with the number of text bytes consumed (moira_host.cpp)
 int parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous, uint8_t *slab,

@@ -424,6 +424,28 @@ def test_device_fastq_parser_agrees_with_host_parser(ctx, monkeypatch):
     finally:
         c2.close()
         monkeypatch.delenv("MOIRA_B200_HOST_PARSE")
+    # several 64 MB chunks: the cuts are guessed from the text's local structure and verified by the device's line count
+    big = body * 5 + b"@last\nACGTN\n+\nIIII#"
+    slab, off, ln, *_ = moira_b200.parse_fastq(big, 33, True)
+    ref_big = ctx.filter_batch(slab, off, ln, p)
+    assert len(big) > 70 * 2**20 and len(ln) == 200001
+    res_big, lengths_big = ctx.filter_fastq(big, p)
+    assert np.array_equal(lengths_big, ln) and np.array_equal(res_big.ee, ref_big.ee) and np.array_equal(res_big.flags, ref_big.flags)
+    assert np.array_equal(res_big.counters, ref_big.counters)
+    monkeypatch.setenv("MOIRA_B200_FQ_COUNT", "1")            # the same with every cut counted on the host
+    c3 = moira_b200.Context(0)
+    try:
+        res_c, lengths_c = c3.filter_fastq(big, p)
+        assert np.array_equal(lengths_c, ln) and np.array_equal(res_c.ee, ref_big.ee) and np.array_equal(res_c.flags, ref_big.flags)
+    finally:
+        c3.close()
+        monkeypatch.delenv("MOIRA_B200_FQ_COUNT")
+    # lines shorter than the index estimate (8 bytes): the device reports the overflow, the call counts and runs again
+    tiny = b"".join(b"@%d\n%s\n+\n%s\n" % (i, b"ACGTN"[i % 5:i % 5 + 1], b"I5#"[i % 3:i % 3 + 1]) for i in range(50000))
+    slab, off, ln, *_ = moira_b200.parse_fastq(tiny, 33, True)
+    ref_t = ctx.filter_batch(slab, off, ln, p)
+    res_t, lengths_t = ctx.filter_fastq(tiny, p)
+    assert np.array_equal(lengths_t, ln) and np.array_equal(res_t.ee, ref_t.ee) and np.array_equal(res_t.flags, ref_t.flags)
     # errors: detected on the device, raised with the host parser's message
     good = "".join(recs[:3000]).encode()
     for bad, word in ((b"@bad\nACGT\n+\nIII\n", "LengthMismatchError"), (b"@bad\n\n+\nIII\n", "EmptySeqError"),
