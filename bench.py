@@ -409,8 +409,9 @@ def run_ours(args):
                      "accepted": int(r0.counters[L.CNT_ACCEPTED]),
                      "pageable_text": {"value": world * m / dt_pageable, "unit": "reads/s",
                                        "note": "the same with the text in ordinary (pageable) host memory: staged through pinned buffers by the host threads"},
-                     "api": "moira_filter_fastq: FASTQ text in pinned host memory -> H2D as it is -> newline index, record table, slab conversion and "
-                            "the filter on the device -> D2H of ee / Ns / flags / lengths; three 64 MB chunks in flight"}
+                     "api": "moira_filter_fastq: FASTQ text in pinned host memory -> H2D as it is (chunk cuts guessed from the local structure of the text, "
+                            "verified by the device's line count) -> newline index, record table, slab conversion and the filter on the device -> "
+                            "D2H of ee / Ns / flags / lengths; three 64 MB chunks in flight"}
         del text
         h_text.free()
 
