@@ -126,6 +126,7 @@ struct Ticket {
     cudaEvent_t done[2] = {nullptr, nullptr};
     uint64_t *counters_out = nullptr;
     uint64_t *counters_pinned = nullptr;
+    moira_params params;   // of the submission (feedback for the pilot-less cascade at moira_wait)
 };
 
 }  // namespace
@@ -168,6 +169,9 @@ struct moira_ctx {
     DevBuf fq_counters;
     int device_parse = 1;
     int fq_guess_cuts = 1;
+    // batches too small for a pilot launch take the cascade blindly (k_first <= 4); the escalated fraction the host
+    // sees in a finished batch's counters switches that off for the next 32 batches when it was above the pilot's limit
+    int blind_off_left = 0;
     // paired-end contig construction: per-stream device buffers, traceback scratch, posterior tables
     PairBufs pb[2];
     DevBuf trace, hbuf, post, pair_counters;
@@ -259,6 +263,15 @@ int ensure_lsort(Workspace &w, uint32_t cap, LenSortBufs &b)
     b.group_start = w.ltables + 3 * LEN_BUCKETS;
     b.group_count = b.group_start + 32;
     return MOIRA_OK;
+}
+
+// feedback for the pilot-less cascade from the counters of a finished Poisson-binomial batch (see moira_ctx::blind_off_left)
+void note_escalations(moira_ctx *c, const moira_params *p, const uint64_t *counters)
+{
+    if (!p || p->mode != MOIRA_MODE_PB || p->exact_ee || !counters) return;
+    if (c->blind_off_left > 0) { c->blind_off_left--; return; }
+    const uint64_t reads = counters[MOIRA_CNT_READS], esc = counters[MOIRA_CNT_ESCALATED];
+    if (reads >= 4096 && esc * 100 > reads * 35) c->blind_off_left = 32;
 }
 
 int check_params(const moira_params *p)
@@ -437,7 +450,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             const uint32_t warps = (uint32_t)c->sm_count * 16u;            // tpr_warps(2) per CTA
             const uint32_t pilot_n = 2u * warps * 32u;                     // two tiles per warp
             const bool pilot = p->cascade != 1 && n >= 8u * pilot_n;
-            const bool blind = p->cascade == 1 || k_first <= 4;            // without a pilot: only where k_first is small
+            const bool blind = p->cascade == 1 || (k_first <= 4 && c->blind_off_left == 0);   // without a pilot: only where k_first is small
             uint32_t *policy = ws.counts + NB;
             static const char *cname[] = {"", "", "", "pb_cascade<2,3>", "pb_cascade<2,4>", "pb_cascade<2,5>", "pb_cascade<2,6>",
                                           "pb_cascade<2,7>", "pb_cascade<2,8>"};
@@ -705,6 +718,7 @@ static int submit_impl(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, c
     t.counters_out = counters_out;
     if (!t.counters_pinned) CU(cudaHostAlloc((void **)&t.counters_pinned, MOIRA_N_COUNTERS * sizeof(uint64_t), cudaHostAllocDefault));
     memset(t.counters_pinned, 0, MOIRA_N_COUNTERS * sizeof(uint64_t));
+    t.params = *params;
     if (n == 0) {
         t.busy = true;
         for (int i = 0; i < 2; i++) CU(cudaEventRecord(t.done[i], c->streams[i]));
@@ -812,6 +826,7 @@ int moira_wait(moira_ctx *c, int ticket)
     CU(cudaEventSynchronize(t.done[1]));
     CU(cudaEventSynchronize(t.done[0]));
     if (t.counters_out) memcpy(t.counters_out, t.counters_pinned, MOIRA_N_COUNTERS * sizeof(uint64_t));
+    note_escalations(c, &t.params, t.counters_pinned);
     CU(cudaGetLastError());
     return MOIRA_OK;
 }
@@ -1081,7 +1096,10 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         memcpy(g_err, keep, sizeof(keep));
         return rc;
     }
-    if (counters_out) CU(cudaMemcpy(counters_out, d_cnt, MOIRA_N_COUNTERS * 8, cudaMemcpyDeviceToHost));
+    if (counters_out) {
+        CU(cudaMemcpy(counters_out, d_cnt, MOIRA_N_COUNTERS * 8, cudaMemcpyDeviceToHost));
+        note_escalations(c, params, counters_out);
+    }
     *n_reads_out = n_assigned;
     return MOIRA_OK;
 }

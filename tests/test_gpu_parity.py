@@ -20,6 +20,13 @@ def _q1(kat):
     return [ord(c) - kat["fastq_offset"] for c in kat["testQual1_ascii"]]
 
 
+def _same_counters(a, b):
+    """Every counter but MOIRA_CNT_ESCALATED, which describes the route a batch took (cascade or single sweep; the
+    library adapts that to the data it has seen), not its result."""
+    keep = np.arange(L.N_COUNTERS) != L.CNT_ESCALATED
+    return np.array_equal(np.asarray(a)[keep], np.asarray(b)[keep])
+
+
 def _has_n(slab, off, ln):
     return np.array([(slab[int(o):int(o) + int(l)] == 0xFF).any() for o, l in zip(off, ln)], dtype=bool)
 
@@ -285,7 +292,7 @@ def test_async_submit_wait_pinned(ctx):
     ref = ctx.filter_batch(slab, off, ln, p)
     for out in outs:
         assert np.array_equal(out.ee, ref.ee) and np.array_equal(out.flags, ref.flags)
-        assert np.array_equal(out.counters, ref.counters)
+        assert _same_counters(out.counters, ref.counters)
     for pb in bufs:
         pb.free()
 
@@ -299,14 +306,14 @@ def test_streaming_fastq_entry_point(ctx):
     ref = ctx.filter_batch(slab, off, ln, p)
     res, lengths = ctx.filter_fastq(text, p)
     assert np.array_equal(lengths, ln) and np.array_equal(res.ee, ref.ee) and np.array_equal(res.flags, ref.flags)
-    assert np.array_equal(res.counters, ref.counters)
+    assert _same_counters(res.counters, ref.counters)
     big = text * 130 + b"@partial\nACGT\n"                      # ~74 MB: two streaming ranges
     assert len(big) > (64 << 20)
     res2, lengths2 = ctx.filter_fastq(big, p)
     assert len(lengths2) == 130 * len(ln)
     assert np.array_equal(lengths2, np.tile(ln, 130)) and np.array_equal(res2.ee, np.tile(ref.ee, 130))
     assert np.array_equal(res2.flags, np.tile(ref.flags, 130))
-    assert np.array_equal(res2.counters, ref.counters * np.uint64(130))
+    assert _same_counters(res2.counters, ref.counters * np.uint64(130))
     with pytest.raises(moira_b200.MoiraError) as ei:
         ctx.filter_fastq(text[:5000] + b"@bad\nACGT\n+\nIII\n" + text[5000:], p)
     assert ei.value.code == L.ERR_PARSE
@@ -364,7 +371,7 @@ def test_q6_transport_format_gives_identical_results(ctx):
             r8 = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact))
             r6 = ctx.filter_batch(img, off, ln, FilterParams(exact_ee=exact, slab_format="q6"))
             assert np.array_equal(r8.ee, r6.ee) and np.array_equal(r8.ns, r6.ns) and np.array_equal(r8.flags, r6.flags)
-            assert np.array_equal(r8.counters, r6.counters)
+            assert _same_counters(r8.counters, r6.counters)
 
 
 @pytest.mark.gpu
@@ -383,7 +390,7 @@ def test_submit_failing_midway_leaves_the_context_usable(ctx):
     assert ei.value.code == L.ERR_BAD_ARG and "multiple of 16" in ei.value.message
     for _ in range(L.MAX_INFLIGHT + 1):                         # no ticket leaked by the failed submission
         again = ctx.filter_batch(slab, off, ln, p)
-        assert np.array_equal(again.flags, good.flags) and np.array_equal(again.counters, good.counters)
+        assert np.array_equal(again.flags, good.flags) and _same_counters(again.counters, good.counters)
 
 
 @pytest.mark.gpu
@@ -414,7 +421,7 @@ def test_device_fastq_parser_agrees_with_host_parser(ctx, monkeypatch):
         res, lengths = ctx.filter_fastq(text, p)
         assert len(lengths) == len(ln) == 40000 + (1 if tail.startswith(b"@last") else 0)
         assert np.array_equal(lengths, ln) and np.array_equal(res.ee, ref.ee) and np.array_equal(res.ns, ref.ns)
-        assert np.array_equal(res.flags, ref.flags) and np.array_equal(res.counters, ref.counters)
+        assert np.array_equal(res.flags, ref.flags) and _same_counters(res.counters, ref.counters)
     # the host-parse variant of the same entry point (a context created with MOIRA_B200_HOST_PARSE=1)
     monkeypatch.setenv("MOIRA_B200_HOST_PARSE", "1")
     c2 = moira_b200.Context(0)
@@ -431,7 +438,7 @@ def test_device_fastq_parser_agrees_with_host_parser(ctx, monkeypatch):
     assert len(big) > 70 * 2**20 and len(ln) == 200001
     res_big, lengths_big = ctx.filter_fastq(big, p)
     assert np.array_equal(lengths_big, ln) and np.array_equal(res_big.ee, ref_big.ee) and np.array_equal(res_big.flags, ref_big.flags)
-    assert np.array_equal(res_big.counters, ref_big.counters)
+    assert _same_counters(res_big.counters, ref_big.counters)
     monkeypatch.setenv("MOIRA_B200_FQ_COUNT", "1")            # the same with every cut counted on the host
     c3 = moira_b200.Context(0)
     try:
@@ -497,7 +504,7 @@ def test_cascade_pilot_chooses_per_batch(ctx):
     n = 1_400_000
     g = torch.Generator(device=dev)
     g.manual_seed(5)
-    borderline = torch.randint(20, 25, (n, synth.V4_STRIDE), dtype=torch.uint8, device=dev, generator=g)   # mean error count ~1.6
+    borderline = torch.randint(26, 29, (n, synth.V4_STRIDE), dtype=torch.uint8, device=dev, generator=g)   # mean error count ~0.5: j* is 2 or 3
     borderline[:, synth.V4_LEN:] = 0xFD
     slabs = {"v4": synth.generate_v4_device(n, 77, dev), "borderline": borderline}
     stream = torch.cuda.current_stream().cuda_stream
@@ -520,10 +527,33 @@ def test_cascade_pilot_chooses_per_batch(ctx):
                 assert np.array_equal(outs[a][k], outs[b][k]), (name, a, k)
             assert np.array_equal(outs[a][3][same], outs[b][3][same]), (name, a)
         esc = outs[1][3][L.CNT_ESCALATED] / n
-        assert (esc < 0.3) if name == "v4" else (esc < 0.12)   # borderline batch: only the pilot's reads took the two-entry sweep
+        assert (esc < 0.3) if name == "v4" else (0.05 < esc < 0.12)   # borderline batch: only the pilot's reads took the two-entry sweep
         assert outs[0][4] == 1 and outs[1][4] == 5      # one sweep | pilot, verdict, two candidates, second sweep
         idx = np.random.default_rng(3).choice(n, 2000, replace=False)
         rows = slab[torch.as_tensor(idx, device=dev)].cpu().numpy()
         off = np.arange(len(idx), dtype=np.uint64) * synth.V4_STRIDE
         ee_o, ns_o = po.pb_batch(rows.reshape(-1), off, np.full(len(idx), synth.V4_LEN, np.uint32), 0.005)
         assert np.array_equal(outs[3][0][idx], ee_o) and np.array_equal(outs[3][1][idx], ns_o)
+
+
+def test_pilotless_cascade_learns_from_finished_batches():
+    """Batches too small for the pilot take the cascade blindly; when a finished batch's counters show that most reads
+    were escalated, the following batches sweep once with all entries -- same results either way."""
+    rng = np.random.default_rng(8)
+    n = 60000
+    slab = np.full((n, 256), 0xFD, np.uint8)
+    slab[:, :253] = rng.integers(26, 29, (n, 253), dtype=np.uint8)          # mean error count ~0.5: j* is 2 or 3 for most reads
+    off = np.arange(n, dtype=np.uint64) * 256
+    ln = np.full(n, 253, np.uint32)
+    c = moira_b200.Context(0)
+    try:
+        p = FilterParams(exact_ee=False)
+        first = c.filter_batch(slab.reshape(-1), off, ln, p)
+        again = c.filter_batch(slab.reshape(-1), off, ln, p)
+        assert int(first.counters[L.CNT_ESCALATED]) > 0.35 * n and int(again.counters[L.CNT_ESCALATED]) == 0
+        assert np.array_equal(first.ee, again.ee) and np.array_equal(first.flags, again.flags) and _same_counters(first.counters, again.counters)
+        ee_o, ns_o = po.pb_batch(slab.reshape(-1), off, ln, 0.005)
+        lb = again.lower_bound
+        assert np.array_equal(again.ee[~lb], ee_o[~lb]) and np.array_equal(again.accept, (ee_o + ns_o) <= 253 * 0.01)
+    finally:
+        c.close()
