@@ -154,6 +154,9 @@ __device__ __forceinline__ uint32_t mark_bits(uint32_t w)
 // count runs only for the others.  ns128 accumulates 128 per marker byte.
 __device__ __forceinline__ void count_marks4(const uint32_t (&w)[4], uint32_t &ns, uint32_t &upper_n)
 {
+#ifdef MOIRA_EXPERIMENT_NO_MARKS   // tuning experiments only: what the N/n accounting costs (results are wrong for reads with N)
+    return;
+#endif
     if ((w[0] | w[1] | w[2] | w[3]) & 0x80808080u) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
