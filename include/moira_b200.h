@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MOIRA_ABI_VERSION 3
+#define MOIRA_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MOIRA_API __attribute__((visibility("default")))
@@ -55,6 +55,7 @@ extern "C" {
 #define MOIRA_ERR_NOMEM          -6
 #define MOIRA_ERR_UNRESOLVED     -7  /* cumulative probability never exceeded 1-alpha (reference would run off its arrays) */
 #define MOIRA_ERR_PARSE          -8  /* malformed FASTQ / FASTA+QUAL input (host parsers) */
+#define MOIRA_ERR_NCCL           -9  /* NCCL not loadable, or a collective failed (moira_comm_*, moira_reduce_counters*) */
 
 /* ---- enums ---------------------------------------------------------------------------------- */
 #define MOIRA_MODE_PB             0  /* --error_calc poisson_binomial   (bernoullimodule.c) */
@@ -98,6 +99,8 @@ extern "C" {
 #define MOIRA_CNT_NUMERIC      7
 #define MOIRA_CNT_ESCALATED    8   /* reads a first pass could not settle (swept again with more entries); diagnostic: depends on
                                       the cascade setting and the mode, unlike every other counter */
+#define MOIRA_CNT_FP64_OPS     9   /* FP64 operations (thread level) executed by the PMF / Lambda sweeps: the numerator of the executed-flop
+                                      roofline; diagnostic like MOIRA_CNT_ESCALATED (depends on cascade / ladder choices) */
 #define MOIRA_CNT_HIST         16  /* 64 bins of floor(final ee); last bin = >= 63 */
 #define MOIRA_N_HIST           64
 #define MOIRA_N_COUNTERS       80
@@ -148,11 +151,21 @@ MOIRA_API int moira_host_free(void *ptr);
  * (a cudaStream_t; NULL = default stream) and the call returns without synchronising.
  * offsets may be NULL (row r starts at r * stride); lengths may be NULL (every read has
  * fixed_length bases).  d_counters (uint64[MOIRA_N_COUNTERS]) is ACCUMULATED into; may be NULL.
- * d_ns / d_flags may be NULL. */
+ * d_ns / d_flags may be NULL.  d_row_marks may be NULL (see moira_count_marks_device). */
 MOIRA_API int moira_filter_device(moira_ctx *ctx, const uint8_t *d_slab, const uint64_t *d_offsets,
                         const uint32_t *d_lengths, uint64_t stride, uint32_t fixed_length,
-                        uint64_t n_reads, const moira_params *params, double *d_ee, int32_t *d_ns,
-                        uint8_t *d_flags, uint64_t *d_counters, void *stream);
+                        uint64_t n_reads, const moira_params *params, const uint32_t *d_row_marks,
+                        double *d_ee, int32_t *d_ns, uint8_t *d_flags, uint64_t *d_counters, void *stream);
+
+/* Row marks: one uint32 per row, Ns (number of 0xFE / 0xFF bytes among the first min(length, truncate) bases) in bits
+ * 0..30 and "contains 'N'" (a 0xFF byte) in bit 31.  Whoever writes a slab sees every byte anyway -- the library's own
+ * producers (6-bit expansion, FASTQ conversion on the device) emit the marks as they go -- and a filter call that is
+ * given them (d_row_marks, indexed like d_ee; NULL = count in the sweep) spends no issue slots on N/n accounting
+ * (bernoullimodule.c:196-199 is the per-base test it replaces).  This entry point is the stand-alone producer for
+ * slabs that came from elsewhere: one memory-bound pass, enqueued on `stream`. */
+MOIRA_API int moira_count_marks_device(moira_ctx *ctx, const uint8_t *d_slab, const uint64_t *d_offsets,
+                        const uint32_t *d_lengths, uint64_t stride, uint32_t fixed_length, uint64_t n_reads,
+                        uint32_t truncate, uint32_t *d_row_marks, void *stream);
 
 /* Host-buffer variant (the call a host program makes): copies the slab in chunks host->device,
  * runs the filter and copies ee / Ns / flags back, overlapping copies of one chunk with the
@@ -315,6 +328,29 @@ MOIRA_API int moira_make_contig(moira_ctx *ctx, const char *fwd_aligned, const i
                                 const moira_contig_params *params, char *contig, int32_t *contig_quals,
                                 uint64_t *contig_len, int32_t *overlap, int32_t *gaps, int32_t *mismatches);
 
+/* ---- multi-GPU: the path's only collective ------------------------------------------------------------
+ * Reads shard by contiguous chunk, one context per GPU; nothing but the MOIRA_N_COUNTERS counters (good / bad counts,
+ * floor(ee) histogram: the device-side counterpart of moira.py:406-408, 483-485, 509-519) is ever exchanged.  Their
+ * sum over GPUs is one NCCL all-reduce (ncclUint64, ncclSum) over NVLink / NVSwitch.  NCCL (libnccl.so.2) is bound at
+ * run time by the first of these calls; without it they fail with MOIRA_ERR_NCCL.
+ *
+ * One process per GPU: rank 0 calls moira_comm_unique_id and hands the 128 bytes to the other ranks by any means
+ * (file, socket, MPI, torch.distributed); every rank then calls moira_comm_init (collective).
+ * One process, several GPUs (the CLI's --devices): moira_comm_init_all over contexts on distinct devices. */
+#define MOIRA_COMM_ID_BYTES 128
+MOIRA_API int moira_comm_unique_id(uint8_t id[MOIRA_COMM_ID_BYTES]);
+MOIRA_API int moira_comm_init(moira_ctx *ctx, const uint8_t id[MOIRA_COMM_ID_BYTES], int rank, int n_ranks);
+MOIRA_API int moira_comm_init_all(moira_ctx *const *ctxs, int n_ctx);
+MOIRA_API int moira_comm_info(const moira_ctx *ctx, int *rank_out, int *n_ranks_out);   /* 0 of 1 without a communicator */
+/* Sum of the counters over all ranks, in place (collective: every rank calls it).
+ *   _device: d_counters is this rank's device array; the all-reduce is enqueued on `stream` behind the filter calls
+ *            that accumulate into it, no host synchronisation;
+ *   host:    counters is this rank's host array; blocks until the sums are in it;
+ *   _all:    one process, n contexts: counters[i] is context i's host array; one NCCL group call. */
+MOIRA_API int moira_reduce_counters_device(moira_ctx *ctx, uint64_t *d_counters, void *stream);
+MOIRA_API int moira_reduce_counters(moira_ctx *ctx, uint64_t counters[MOIRA_N_COUNTERS]);
+MOIRA_API int moira_reduce_counters_all(moira_ctx *const *ctxs, int n_ctx, uint64_t *const *counters);
+
 /* Host threads used by moira_parse_fastq (0 = one per hardware thread, at most 64). */
 MOIRA_API int moira_set_host_threads(int n);
 
@@ -323,6 +359,11 @@ MOIRA_API int moira_set_host_threads(int n);
 /* Register-resident FP64 issue-rate micro-benchmark (non-fused DMUL/DADD in the kernel's own
  * 7:4 ratio), the denominator of the FP64 roofline.  Returns operations per second. */
 MOIRA_API int moira_fp64_peak(moira_ctx *ctx, int iters, double *ops_per_s_out, double *ms_out);
+
+/* Host <-> device copy rate of this context's GPU right now: `bytes` from / to pinned host memory, best of `reps`,
+ * CUDA events on the context's stream -- the denominator of an end-to-end number (frac_of_link).  Ranks that call it at
+ * the same time measure the rate they get while sharing the host's memory system and PCIe root complexes. */
+MOIRA_API int moira_link_probe(moira_ctx *ctx, uint64_t bytes, int reps, double *h2d_gb_per_s_out, double *d2h_gb_per_s_out);
 
 /* Number of kernel launches this context has issued so far (for bench.py's gpu_launches). */
 MOIRA_API int moira_ctx_launch_count(const moira_ctx *ctx, uint64_t *out);

@@ -12,10 +12,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOIRA_B200_LIB") or os.path.join(_HERE, "libmoira_b200.so")   # env override: tuning experiments only
 
 # ---- constants mirrored from include/moira_b200.h -------------------------------------------
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK = 0
 ERR_BAD_ALPHA, ERR_LENGTH_MISMATCH, ERR_BAD_QUALITY, ERR_CUDA = -1, -2, -3, -4
-ERR_BAD_ARG, ERR_NOMEM, ERR_UNRESOLVED, ERR_PARSE = -5, -6, -7, -8
+ERR_BAD_ARG, ERR_NOMEM, ERR_UNRESOLVED, ERR_PARSE, ERR_NCCL = -5, -6, -7, -8, -9
+COMM_ID_BYTES = 128
 MODE_PB, MODE_POISSON, MODE_EXPECTED_ERROR = 0, 1, 2
 THR_UNCERT, THR_MAXERRORS = 0, 1
 AMBIGS_TREAT_AS_ERRORS, AMBIGS_IGNORE, AMBIGS_DISALLOW = 0, 1, 2
@@ -27,6 +28,7 @@ REASON_NONE, REASON_ERRORS, REASON_LENGTH, REASON_AMBIGS = 0, 1, 2, 3
 CNT_READS, CNT_ACCEPTED, CNT_BAD_ERRORS, CNT_BAD_LENGTH, CNT_BAD_AMBIGS = 0, 1, 2, 3, 4
 CNT_NEAR_CUTOFF, CNT_LOWER_BOUND, CNT_NUMERIC, CNT_HIST, N_HIST, N_COUNTERS = 5, 6, 7, 16, 64, 80
 CNT_ESCALATED = 8
+CNT_FP64_OPS = 9
 MAX_INFLIGHT = 4
 CONSENSUS_BEST, CONSENSUS_SUM, CONSENSUS_POSTERIOR = 0, 1, 2
 PAIR_OK, PAIR_EMPTY, PAIR_BAD_BASE, PAIR_BAD_QUALITY, PAIR_TOO_LONG = 0, 1, 2, 3, 4
@@ -34,9 +36,11 @@ PAIR_OK, PAIR_EMPTY, PAIR_BAD_BASE, PAIR_BAD_QUALITY, PAIR_TOO_LONG = 0, 1, 2, 3
 EXPORTS = [
     "moira_abi_version", "moira_last_error", "moira_params_default", "moira_ctx_create",
     "moira_ctx_destroy", "moira_ctx_sm_count", "moira_build_lut", "moira_ctx_get_lut",
-    "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_filter_batch",
+    "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_count_marks_device", "moira_filter_batch",
     "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads", "moira_pack_q6",
     "moira_parse_fastq", "moira_parse_fasta_qual", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
+    "moira_comm_unique_id", "moira_comm_init", "moira_comm_init_all", "moira_comm_info", "moira_reduce_counters_device",
+    "moira_reduce_counters", "moira_reduce_counters_all", "moira_link_probe",
     "moira_ctx_last_kernel_ms", "moira_ctx_last_contig_ms", "moira_contig_params_default", "moira_filter_pairs", "moira_nw_align", "moira_make_contig",
 ]
 
@@ -86,7 +90,8 @@ lib.moira_build_lut.argtypes = [_vp, _vp, _vp, ctypes.POINTER(_i)]
 lib.moira_ctx_get_lut.argtypes = [_vp, _vp, _vp, _vp]
 lib.moira_host_alloc.argtypes = [ctypes.POINTER(_vp), ctypes.c_size_t]
 lib.moira_host_free.argtypes = [_vp]
-lib.moira_filter_device.argtypes = [_vp, _vp, _vp, _vp, _u64, _u32, _u64, _pp, _vp, _vp, _vp, _vp, _vp]
+lib.moira_filter_device.argtypes = [_vp, _vp, _vp, _vp, _u64, _u32, _u64, _pp, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.moira_count_marks_device.argtypes = [_vp, _vp, _vp, _vp, _u64, _u32, _u64, _u32, _vp, _vp]
 lib.moira_filter_batch.argtypes = [_vp, _vp, _u64, _vp, _vp, _u64, _pp, _vp, _vp, _vp, _vp]
 lib.moira_submit.argtypes = [_vp, _vp, _u64, _vp, _vp, _u64, _pp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i)]
 lib.moira_wait.argtypes = [_vp, _i]
@@ -104,6 +109,14 @@ lib.moira_collapse.argtypes = [_vp, _vp, _vp, _vp, _u64, _i, _vp, ctypes.POINTER
 lib.moira_set_host_threads.argtypes = [_i]
 lib.moira_fp64_peak.argtypes = [_vp, _i, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
 lib.moira_ctx_launch_count.argtypes = [_vp, ctypes.POINTER(_u64)]
+lib.moira_comm_unique_id.argtypes = [_vp]
+lib.moira_comm_init.argtypes = [_vp, _vp, _i, _i]
+lib.moira_comm_init_all.argtypes = [ctypes.POINTER(_vp), _i]
+lib.moira_comm_info.argtypes = [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]
+lib.moira_reduce_counters_device.argtypes = [_vp, _vp, _vp]
+lib.moira_reduce_counters.argtypes = [_vp, _vp]
+lib.moira_reduce_counters_all.argtypes = [ctypes.POINTER(_vp), _i, ctypes.POINTER(_vp)]
+lib.moira_link_probe.argtypes = [_vp, _u64, _i, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
 lib.moira_ctx_set_timing.argtypes = [_vp, _i]
 lib.moira_ctx_last_contig_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i)]
 lib.moira_ctx_last_kernel_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p)]

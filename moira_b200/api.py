@@ -254,6 +254,36 @@ class Context:
         L.check(lib.moira_fp64_peak(self._h, int(iters), ctypes.byref(ops), ctypes.byref(ms)))
         return ops.value, ms.value
 
+    def link_probe(self, nbytes: int = 1 << 30, reps: int = 3):
+        """(H2D GB/s, D2H GB/s) from / to pinned host memory right now (moira_link_probe)."""
+        h2d, d2h = ctypes.c_double(), ctypes.c_double()
+        L.check(lib.moira_link_probe(self._h, int(nbytes), int(reps), ctypes.byref(h2d), ctypes.byref(d2h)))
+        return h2d.value, d2h.value
+
+    # ---- multi-GPU: the counters' all-reduce (NCCL inside the library) -----------------------------
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        """Join the communicator `unique_id` (comm_unique_id() of rank 0) as `rank` of `n_ranks`: collective."""
+        if len(unique_id) != L.COMM_ID_BYTES:
+            raise ValueError("unique_id must be %d bytes" % L.COMM_ID_BYTES)
+        buf = (ctypes.c_uint8 * L.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        L.check(lib.moira_comm_init(self._h, buf, int(rank), int(n_ranks)))
+
+    def comm_info(self):
+        r, n = ctypes.c_int(), ctypes.c_int()
+        L.check(lib.moira_comm_info(self._h, ctypes.byref(r), ctypes.byref(n)))
+        return r.value, n.value
+
+    def reduce_counters(self, counters: np.ndarray) -> np.ndarray:
+        """Sum of the host counters over all ranks, in place (moira_reduce_counters): collective, blocking."""
+        if counters.dtype != np.uint64 or counters.shape != (L.N_COUNTERS,) or not counters.flags.c_contiguous:
+            raise ValueError("counters must be a contiguous uint64[%d] array" % L.N_COUNTERS)
+        L.check(lib.moira_reduce_counters(self._h, _ptr(counters)))
+        return counters
+
+    def reduce_counters_device(self, d_counters: int, stream: int | None = None):
+        """In-place all-reduce of a device counters array, enqueued on `stream` (moira_reduce_counters_device)."""
+        L.check(lib.moira_reduce_counters_device(self._h, d_counters, stream))
+
     # ---- hot path -------------------------------------------------------------------------------
     def filter_batch(self, slab, offsets, lengths, params: FilterParams, out: FilterResult | None = None) -> FilterResult:
         """Host buffers in, host buffers out (moira_filter_batch)."""
@@ -284,11 +314,18 @@ class Context:
 
     def filter_device(self, d_slab: int, d_offsets: int | None, d_lengths: int | None, stride: int,
                       fixed_length: int, n_reads: int, params: FilterParams, d_ee: int, d_ns: int | None,
-                      d_flags: int | None, d_counters: int | None, stream: int | None = None):
-        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); enqueues on `stream`, no sync."""
+                      d_flags: int | None, d_counters: int | None, stream: int | None = None, d_row_marks: int | None = None):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); enqueues on `stream`, no sync.  d_row_marks: the slab's
+        row marks (count_marks_device, or the slab's producer) -- the sweeps then count no N/n."""
         cp = params.to_c()
         L.check(lib.moira_filter_device(self._h, d_slab, d_offsets, d_lengths, int(stride), int(fixed_length),
-                                        int(n_reads), ctypes.byref(cp), d_ee, d_ns, d_flags, d_counters, stream))
+                                        int(n_reads), ctypes.byref(cp), d_row_marks, d_ee, d_ns, d_flags, d_counters, stream))
+
+    def count_marks_device(self, d_slab: int, d_offsets: int | None, d_lengths: int | None, stride: int, fixed_length: int,
+                           n_reads: int, d_row_marks: int, truncate: int = 0, stream: int | None = None):
+        """Row marks (Ns | has-N << 31 per row) of a device-resident slab (moira_count_marks_device); enqueues on `stream`."""
+        L.check(lib.moira_count_marks_device(self._h, d_slab, d_offsets, d_lengths, int(stride), int(fixed_length), int(n_reads),
+                                             int(truncate), d_row_marks, stream))
 
     def filter_fastq(self, text, params: FilterParams, fastq_offset: int = 33, out: FilterResult | None = None):
         """FASTQ text (bytes, or a uint8 array -- e.g. a view of pinned memory) -> FilterResult in one streaming C call
@@ -382,6 +419,28 @@ class Context:
                                            int(q.shape[0]), float(alpha), ctypes.byref(ee), ctypes.byref(ns))
         L.check(rc)
         return ee.value, ns.value
+
+
+def comm_unique_id() -> bytes:
+    """A fresh communicator id (moira_comm_unique_id): rank 0 makes it, every rank passes it to Context.comm_init."""
+    buf = (ctypes.c_uint8 * L.COMM_ID_BYTES)()
+    L.check(lib.moira_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init_all(contexts):
+    """One process, several GPUs: a communicator over `contexts` (distinct devices), rank i = contexts[i]."""
+    arr = (ctypes.c_void_p * len(contexts))(*[c._h for c in contexts])
+    L.check(lib.moira_comm_init_all(arr, len(contexts)))
+
+
+def reduce_counters_all(contexts, counters):
+    """One process, several GPUs: every counters[i] (uint64[N_COUNTERS], context i) becomes the sum over all contexts
+    (one NCCL group call, moira_reduce_counters_all)."""
+    arr = (ctypes.c_void_p * len(contexts))(*[c._h for c in contexts])
+    ptrs = (ctypes.c_void_p * len(contexts))(*[c_.ctypes.data for c_ in counters])
+    L.check(lib.moira_reduce_counters_all(arr, len(contexts), ptrs))
+    return counters
 
 
 def pack_sequences(seqs, quals_list):
@@ -543,4 +602,5 @@ def collapse(text, seq_off, seq_len, ee, n_threads: int = 0) -> CollapseResult:
 
 
 __all__ = ["collapse", "CollapseResult","Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",
-           "pack_arrays", "pack_q6", "parse_fastq", "parse_fasta_qual", "build_lut", "ContigParams", "PairResult", "pack_sequences"]
+           "pack_arrays", "pack_q6", "parse_fastq", "parse_fasta_qual", "build_lut", "ContigParams", "PairResult", "pack_sequences",
+           "comm_unique_id", "comm_init_all", "reduce_counters_all"]

@@ -33,7 +33,7 @@ thread_local char g_err[512] = "";
             return fail(MOIRA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr uint32_t SUB_BATCH = 1u << 23;   // reads per first-pass launch when a ladder follows (bounds the queue memory)
+constexpr uint32_t SUB_BATCH = 1u << 25;   // reads per first-pass launch when a ladder follows (bounds the queue memory)
 constexpr int MAX_TIMED = 256;
 
 struct Workspace {
@@ -104,7 +104,7 @@ constexpr size_t PAIR_STAGE_BYTES = 8 + 4 * 5 + 2;   // ee | ns, clen, overlap, 
 
 // one chunk of FASTQ text being parsed and filtered on the device
 struct FqSlot {
-    DevBuf text, bcnt, bstart, nl, soff, qoff, len, slab, ee, ns, flags, meta;
+    DevBuf text, bcnt, bstart, nl, soff, qoff, len, slab, ee, ns, flags, meta, marks;
     uint8_t *h_text = nullptr;     // pinned staging of the chunk's text (pageable callers)
     size_t h_text_cap = 0;
     uint8_t *h_res = nullptr;      // pinned staging of the results: ee | ns | len | flags
@@ -117,12 +117,12 @@ struct FqSlot {
     cudaEvent_t ev = nullptr;      // behind the chunk's latest D2H: what the host waits for, not the whole stream
     int state = 0;                 // 0 free, 1 indexed (meta on its way), 2 filtering (results on their way)
     int stream = 0;
-    DevBuf *all[12] = {&text, &bcnt, &bstart, &nl, &soff, &qoff, &len, &slab, &ee, &ns, &flags, &meta};
+    DevBuf *all[13] = {&text, &bcnt, &bstart, &nl, &soff, &qoff, &len, &slab, &ee, &ns, &flags, &meta, &marks};
 };
 
 struct Ticket {
     bool busy = false;
-    DevBuf slab, slab6, offsets, lengths, ee, ns, flags, counters;
+    DevBuf slab, slab6, offsets, lengths, ee, ns, flags, counters, marks;
     cudaEvent_t done[2] = {nullptr, nullptr};
     uint64_t *counters_out = nullptr;
     uint64_t *counters_pinned = nullptr;
@@ -178,6 +178,7 @@ struct moira_ctx {
     bool post_ready = false;
     cudaEvent_t ct0[MAX_TIMED] = {}, ct1[MAX_TIMED] = {};   // around the contig kernel launches when timing is on
     int n_ctimed = 0;
+    CommState *comm = nullptr;   // communicator rank for the counters' all-reduce (moira_comm.cpp), created on demand
     // single-read scratch (pinned)
     uint8_t *one_slab = nullptr;
     size_t one_cap = 0;
@@ -343,7 +344,7 @@ int first_pass_k_template(int k_wanted)
 int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const uint64_t *d_offsets,
                     const uint32_t *d_lengths, uint64_t stride, uint32_t fixed_length, uint64_t n_reads,
                     const moira_params *p, uint32_t max_len, uint32_t min_len, double *d_ee, int32_t *d_ns, uint8_t *d_flags,
-                    uint64_t *d_counters, cudaStream_t stream)
+                    uint64_t *d_counters, cudaStream_t stream, const uint32_t *d_row_marks = nullptr)
 {
     if (n_reads == 0) return MOIRA_OK;
     if (!d_slab || !d_ee) return fail(MOIRA_ERR_BAD_ARG, "slab / ee pointer is NULL");
@@ -362,6 +363,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
     a.mode = p->mode; a.thr_kind = p->thr_kind; a.ambigs = p->ambigs; a.round_flag = p->round_flag;
     a.truncate = p->truncate; a.exact = p->exact_ee; a.ee_output = p->ee_output;
     a.lut_p = c->d_p; a.lut_q = c->d_q; a.lut_e = c->d_e; a.e_equals_p = c->e_equals_p;
+    a.row_marks = d_row_marks;   // Ns / has-N per row from the slab's producer (over the first eff bases): the sweeps count nothing
     a.rung = -1;
     LaunchCfg cfg{c->sm_count, stream};
 
@@ -584,7 +586,7 @@ int moira_ctx_destroy(moira_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &t : c->tickets) {
-        for (DevBuf *b : {&t.slab, &t.slab6, &t.offsets, &t.lengths, &t.ee, &t.ns, &t.flags, &t.counters})
+        for (DevBuf *b : {&t.slab, &t.slab6, &t.offsets, &t.lengths, &t.ee, &t.ns, &t.flags, &t.counters, &t.marks})
             if (b->p) cudaFree(b->p);
         for (int i = 0; i < 2; i++) if (t.done[i]) cudaEventDestroy(t.done[i]);
         if (t.counters_pinned) cudaFreeHost(t.counters_pinned);
@@ -620,6 +622,8 @@ int moira_ctx_destroy(moira_ctx *c)
     for (int i = 0; i < 2; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->one_slab) cudaFreeHost(c->one_slab);
     if (c->one_out) cudaFreeHost(c->one_out);
+    comm_state_free(c->comm);
+    cudaSetDevice(c->device);
     cudaFree(c->d_p); cudaFree(c->d_q); cudaFree(c->d_e); cudaFree(c->d_sink);
     cudaGetLastError();
     delete c;
@@ -673,14 +677,38 @@ int moira_host_free(void *ptr)
 
 int moira_filter_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_offsets, const uint32_t *d_lengths,
                         uint64_t stride, uint32_t fixed_length, uint64_t n_reads, const moira_params *params,
-                        double *d_ee, int32_t *d_ns, uint8_t *d_flags, uint64_t *d_counters, void *stream)
+                        const uint32_t *d_row_marks, double *d_ee, int32_t *d_ns, uint8_t *d_flags, uint64_t *d_counters,
+                        void *stream)
 {
     if (!c) return fail(MOIRA_ERR_BAD_ARG, "ctx is NULL");
     int rc = check_params(params);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     return run_filter_full(c, c->ws[2], d_slab, d_offsets, d_lengths, stride, fixed_length, n_reads, params, 0, 0, d_ee,
-                           d_ns, d_flags, d_counters, (cudaStream_t)stream);
+                           d_ns, d_flags, d_counters, (cudaStream_t)stream, d_row_marks);
+}
+
+int moira_count_marks_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_offsets, const uint32_t *d_lengths,
+                             uint64_t stride, uint32_t fixed_length, uint64_t n_reads, uint32_t truncate, uint32_t *d_row_marks,
+                             void *stream)
+{
+    if (!c || !d_slab || !d_row_marks) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    if (((uintptr_t)d_slab & 15u) != 0) return fail(MOIRA_ERR_BAD_ARG, "slab must be 16-byte aligned");
+    if (!d_offsets && (stride & 15u)) return fail(MOIRA_ERR_BAD_ARG, "stride must be a multiple of 16");
+    CU(cudaSetDevice(c->device));
+    FilterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.slab = d_slab; a.offsets = d_offsets; a.lengths = d_lengths; a.stride = stride; a.fixed_length = fixed_length;
+    a.truncate = truncate;
+    LaunchCfg cfg{c->sm_count, (cudaStream_t)stream};
+    for (uint64_t start = 0; start < n_reads; start += 1ull << 30) {
+        a.base = start;
+        a.n = (uint32_t)std::min<uint64_t>(1ull << 30, n_reads - start);
+        if (launch_count_marks(a, d_row_marks, d_lengths ? 0 : fixed_length, cfg))
+            return fail(MOIRA_ERR_CUDA, "count-marks launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        c->launches++;
+    }
+    return MOIRA_OK;
 }
 
 static int submit_impl(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, const uint64_t *offsets,
@@ -727,7 +755,7 @@ static int submit_impl(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, c
     }
     const bool q6 = params->slab_format == MOIRA_SLAB_Q6;   // `slab` is the 3/4-size transport image; offsets/lengths are in slab units
     const uint64_t slab8_bytes = q6 ? slab_bytes / 12 * 16 : slab_bytes;
-    if (q6 && (rc = ensure(t.slab6, slab_bytes + 256))) return rc;
+    if (q6 && ((rc = ensure(t.slab6, slab_bytes + 256)) || (rc = ensure(t.marks, n * 4)))) return rc;
     if ((rc = ensure(t.slab, slab8_bytes + 256)) || (rc = ensure(t.offsets, n * 8)) || (rc = ensure(t.lengths, n * 4)) ||
         (rc = ensure(t.ee, n * 8)) || (rc = ensure(t.ns, n * 4)) || (rc = ensure(t.flags, n)) ||
         (rc = ensure(t.counters, MOIRA_N_COUNTERS * 8)))
@@ -774,23 +802,33 @@ static int submit_impl(moira_ctx *c, const uint8_t *slab, uint64_t slab_bytes, c
             end++;
         }
         cudaStream_t s = c->streams[ci & 1];
+        const uint64_t cn = end - start;
+        uniform = uniform && stride0 >= 16 && (stride0 & 15u) == 0 && stride0 >= max_len;
+        const uint32_t *d_marks = nullptr;
         if (q6) {
             // image bytes [b0*3/4, b1*3/4) travel (b0, b1 are multiples of 16), then expand on the device
             const uint64_t i0 = b0 / 16 * 12, i1 = std::min<uint64_t>((b1 + 15) / 16 * 12, slab_bytes);
             uint8_t *d_img = (uint8_t *)t.slab6.p;
             if (i1 > i0) CU(cudaMemcpyAsync(d_img + i0, slab + i0, i1 - i0, cudaMemcpyHostToDevice, s));
             LaunchCfg ucfg{c->sm_count, s};
-            if (launch_unpack_q6(d_img + i0, d_slab + b0, b1 - b0, ucfg)) return fail(MOIRA_ERR_CUDA, "unpack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            // uniform rows: the expanding kernel sees every byte anyway and leaves Ns / has-N per row for the filter
+            uint32_t *marks = nullptr;
+            uint32_t eff = lengths[start];
+            if (params->truncate && eff > params->truncate) eff = params->truncate;
+            if (uniform && same_len) {
+                marks = (uint32_t *)t.marks.p + start;
+                CU(cudaMemsetAsync(marks, 0, cn * 4, s));
+                d_marks = marks;
+            }
+            if (launch_unpack_q6(d_img + i0, d_slab + b0, b1 - b0, marks, stride0, eff, ucfg)) return fail(MOIRA_ERR_CUDA, "unpack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             c->launches++;
         } else {
             const uint64_t copy_end = std::min<uint64_t>(b1, slab_bytes);
             if (copy_end > b0) CU(cudaMemcpyAsync(d_slab + b0, slab + b0, copy_end - b0, cudaMemcpyHostToDevice, s));
         }
-        const uint64_t cn = end - start;
-        uniform = uniform && stride0 >= 16 && (stride0 & 15u) == 0 && stride0 >= max_len;
         if (uniform && same_len) {
             rc = run_filter_full(c, c->ws[ci & 1], d_slab + b0, nullptr, nullptr, stride0, lengths[start], cn, params, max_len, max_len,
-                                 d_ee + start, d_ns + start, d_fl + start, d_cnt, s);
+                                 d_ee + start, d_ns + start, d_fl + start, d_cnt, s, d_marks);
         } else if (uniform) {   // rows at a fixed pitch, lengths vary: only the lengths travel; TMA tiles still apply
             CU(cudaMemcpyAsync(d_len + start, lengths + start, cn * 4, cudaMemcpyHostToDevice, s));
             rc = run_filter_full(c, c->ws[ci & 1], d_slab + b0, nullptr, d_len + start, stride0, 0, cn, params, max_len, min_len,
@@ -921,15 +959,16 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         }
         const uint32_t stride = std::max<uint32_t>(16, (maxlen + 15u) & ~15u);
         int r;
-        if ((r = ensure(q.slab, (size_t)q.n_rec * stride + 256))) return r;
+        if ((r = ensure(q.slab, (size_t)q.n_rec * stride + 256)) || (r = ensure(q.marks, q.n_rec * 4))) return r;
         if (launch_fq_convert((const uint8_t *)q.text.p, (const uint32_t *)q.soff.p, (const uint32_t *)q.qoff.p, (const uint32_t *)q.len.p,
-                              (uint32_t)q.n_rec, stride, lower_n, fastq_offset, (uint8_t *)q.slab.p, (uint32_t *)q.meta.p, c->sm_count, s))
+                              (uint32_t)q.n_rec, stride, lower_n, fastq_offset, (uint8_t *)q.slab.p, (uint32_t *)q.meta.p,
+                              (uint32_t *)q.marks.p, params->truncate, c->sm_count, s))
             return fail(MOIRA_ERR_CUDA, "fastq convert launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         c->launches++;
         const bool same = minlen == maxlen;
         r = run_filter_full(c, c->ws[q.stream], (const uint8_t *)q.slab.p, nullptr, same ? nullptr : (const uint32_t *)q.len.p, stride,
                             same ? maxlen : 0, q.n_rec, params, maxlen, minlen, (double *)q.ee.p, (int32_t *)q.ns.p, (uint8_t *)q.flags.p,
-                            d_cnt, s);
+                            d_cnt, s, (const uint32_t *)q.marks.p);
         if (r) return r;
         const uint64_t m = q.n_rec;
         CU(cudaMemcpyAsync(q.h_res, q.ee.p, m * 8, cudaMemcpyDeviceToHost, s));
@@ -1652,6 +1691,107 @@ int moira_fp64_peak(moira_ctx *c, int iters, double *ops_per_s_out, double *ms_o
     c->launches += 2;
     *ops_per_s_out = ops / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
+    return MOIRA_OK;
+}
+
+// ---- multi-GPU: all-reduce of the counters (moira_comm.cpp) -----------------------------------------
+static int ctx_comm(moira_ctx *c)
+{
+    if (!c->comm && !(c->comm = comm_state_new())) return fail(MOIRA_ERR_NOMEM, "out of host memory");
+    return MOIRA_OK;
+}
+
+int moira_comm_unique_id(uint8_t id[MOIRA_COMM_ID_BYTES])
+{
+    if (!id) return fail(MOIRA_ERR_BAD_ARG, "id is NULL");
+    return comm_unique_id(id);
+}
+
+int moira_comm_init(moira_ctx *c, const uint8_t id[MOIRA_COMM_ID_BYTES], int rank, int n_ranks)
+{
+    if (!c || !id) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    int rc = ctx_comm(c);
+    if (rc) return rc;
+    return comm_init_rank(c->comm, c->device, id, rank, n_ranks);
+}
+
+int moira_comm_init_all(moira_ctx *const *ctxs, int n)
+{
+    if (!ctxs || n < 1) return fail(MOIRA_ERR_BAD_ARG, "no contexts");
+    std::vector<CommState *> st(n);
+    std::vector<int> dev(n);
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i]) return fail(MOIRA_ERR_BAD_ARG, "context %d is NULL", i);
+        int rc = ctx_comm(ctxs[i]);
+        if (rc) return rc;
+        st[i] = ctxs[i]->comm;
+        dev[i] = ctxs[i]->device;
+    }
+    return comm_init_all(st.data(), dev.data(), n);
+}
+
+int moira_comm_info(const moira_ctx *c, int *rank_out, int *n_ranks_out)
+{
+    if (!c) return fail(MOIRA_ERR_BAD_ARG, "ctx is NULL");
+    if (!c->comm) { if (rank_out) *rank_out = 0; if (n_ranks_out) *n_ranks_out = 1; return MOIRA_OK; }
+    return comm_info(c->comm, rank_out, n_ranks_out);
+}
+
+int moira_reduce_counters_device(moira_ctx *c, uint64_t *d_counters, void *stream)
+{
+    if (!c || !d_counters) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    if (!c->comm) return fail(MOIRA_ERR_BAD_ARG, "context has no communicator (moira_comm_init / moira_comm_init_all)");
+    c->launches++;   // the NCCL all-reduce kernel
+    return comm_reduce_device(c->comm, d_counters, (cudaStream_t)stream);
+}
+
+int moira_reduce_counters(moira_ctx *c, uint64_t counters[MOIRA_N_COUNTERS])
+{
+    if (!c || !counters) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    if (!c->comm) return fail(MOIRA_ERR_BAD_ARG, "context has no communicator (moira_comm_init / moira_comm_init_all)");
+    c->launches++;
+    return comm_reduce_host(c->comm, counters);
+}
+
+int moira_reduce_counters_all(moira_ctx *const *ctxs, int n, uint64_t *const *counters)
+{
+    if (!ctxs || !counters || n < 1) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    std::vector<CommState *> st(n);
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i] || !counters[i]) return fail(MOIRA_ERR_BAD_ARG, "context / counters %d is NULL", i);
+        if (!ctxs[i]->comm) return fail(MOIRA_ERR_BAD_ARG, "context %d has no communicator (moira_comm_init_all)", i);
+        st[i] = ctxs[i]->comm;
+        ctxs[i]->launches++;
+    }
+    return comm_reduce_all(st.data(), n, counters);
+}
+
+int moira_link_probe(moira_ctx *c, uint64_t bytes, int reps, double *h2d_out, double *d2h_out)
+{
+    if (!c || !bytes) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    void *h = nullptr, *d = nullptr;
+    if (cudaHostAlloc(&h, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(MOIRA_ERR_NOMEM, "cudaHostAlloc of %llu bytes failed", (unsigned long long)bytes); }
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return fail(MOIRA_ERR_NOMEM, "cudaMalloc of %llu bytes failed", (unsigned long long)bytes); }
+    memset(h, 1, bytes);
+    cudaStream_t s = c->streams[0];
+    double best[2] = {0, 0};
+    cudaError_t e = cudaSuccess;
+    for (int dir = 0; dir < 2 && e == cudaSuccess; dir++)
+        for (int r = 0; r < (reps < 1 ? 1 : reps) + 1 && e == cudaSuccess; r++) {   // the first repetition warms up
+            cudaEventRecord(c->t0[0], s);
+            e = dir == 0 ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s) : cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s);
+            cudaEventRecord(c->t1[0], s);
+            if (e == cudaSuccess) e = cudaEventSynchronize(c->t1[0]);
+            float ms = 0;
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, c->t0[0], c->t1[0]);
+            if (r > 0 && ms > 0) best[dir] = std::max(best[dir], (double)bytes / (ms * 1e-3) / 1e9);
+        }
+    cudaFree(d);
+    cudaFreeHost(h);
+    if (e != cudaSuccess) return fail(MOIRA_ERR_CUDA, "link probe failed: %s", cudaGetErrorString(e));
+    if (h2d_out) *h2d_out = best[0];
+    if (d2h_out) *d2h_out = best[1];
     return MOIRA_OK;
 }
 

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) fq_records(const uint8_t *text, uint64_t 
 
 __global__ void __launch_bounds__(256) fq_convert(const uint8_t *text, const uint32_t *seq_off, const uint32_t *qual_off,
                                                   const uint32_t *len, uint32_t n_rec, uint32_t stride, int lower_n, int qbase,
-                                                  uint8_t *slab, uint32_t *meta)
+                                                  uint8_t *slab, uint32_t *meta, uint32_t *marks, uint32_t truncate)
 {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -195,7 +195,11 @@ __global__ void __launch_bounds__(256) fq_convert(const uint8_t *text, const uin
         const uint8_t *s = text + seq_off[r], *q = text + qual_off[r];
         uint8_t *row = slab + (uint64_t)r * stride;
         bool bad = false;
-        for (uint32_t i = lane; i < stride; i += 32) {
+        // row marks for the filter (Ns | has-'N' << 31 over the bases that survive --truncate): the sweep then counts nothing
+        const uint32_t eff = (truncate && l > truncate) ? truncate : l;
+        uint32_t ns = 0, up = 0;
+        for (uint32_t i0 = 0; i0 < stride; i0 += 32) {   // every lane runs every step (the ballots below)
+            const uint32_t i = i0 + lane;
             uint8_t out = 0xFD;
             if (i < l) {
                 const uint8_t b = s[i];
@@ -207,8 +211,11 @@ __global__ void __launch_bounds__(256) fq_convert(const uint8_t *text, const uin
                     out = (uint8_t)(v < 0 ? 0 : v);               // <= 0 is read as 1 by the table (moira.py:814)
                 }
             }
-            row[i] = out;
+            if (i < stride) row[i] = out;
+            ns += __popc(__ballot_sync(FULL, out >= 0xFE && i < eff));
+            up |= __ballot_sync(FULL, out == 0xFF && i < eff);
         }
+        if (marks && lane == 0) marks[r] = ns | (up ? 0x80000000u : 0u);
         if (__any_sync(FULL, bad) && lane == 0) atomicMin(&meta[2], r);
     }
 }
@@ -242,13 +249,13 @@ int launch_fq_records(const uint8_t *d_text, uint64_t lo, uint64_t n, const uint
 }
 
 int launch_fq_convert(const uint8_t *d_text, const uint32_t *d_seq_off, const uint32_t *d_qual_off, const uint32_t *d_len,
-                      uint32_t n_rec, uint32_t stride, int lower_n, int qbase, uint8_t *d_slab, uint32_t *d_meta, int sm_count,
-                      cudaStream_t s)
+                      uint32_t n_rec, uint32_t stride, int lower_n, int qbase, uint8_t *d_slab, uint32_t *d_meta, uint32_t *d_marks,
+                      uint32_t truncate, int sm_count, cudaStream_t s)
 {
     if (n_rec == 0) return 0;
     const uint32_t want = (n_rec + 7) / 8;
     const uint32_t grid = want < (uint32_t)sm_count * 8 ? want : (uint32_t)sm_count * 8;
-    fq_convert<<<grid, 256, 0, s>>>(d_text, d_seq_off, d_qual_off, d_len, n_rec, stride, lower_n, qbase, d_slab, d_meta);
+    fq_convert<<<grid, 256, 0, s>>>(d_text, d_seq_off, d_qual_off, d_len, n_rec, stride, lower_n, qbase, d_slab, d_meta, d_marks, truncate);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

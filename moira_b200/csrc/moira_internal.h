@@ -32,6 +32,7 @@ struct FilterArgs {
     uint32_t fixed_length;
     uint64_t base;               // first read of this sub-batch
     uint32_t n;                  // reads in this sub-batch (first pass)
+    const uint32_t *row_marks;   // may be null: per row, Ns (bits 0..30) | has-'N' (bit 31) over the first eff bases, indexed like ee[]
     const uint32_t *queue;       // ladder passes: indices relative to base; null on the first pass
     const uint32_t *queue_count; // ladder passes: device count
     // output
@@ -111,7 +112,12 @@ int launch_length_sort(const FilterArgs &a, const LenSortBufs &b, int single_gro
 int launch_sorted_first(const FilterArgs &a, const uint32_t *seg_start, const uint32_t *seg_count, const LaunchCfg &cfg);
 int launch_pb_first_k(const FilterArgs &a, int k_index, const LaunchCfg &cfg, const char **name);
 // expand a 6-bit transport image into slab bytes [0, slab_bytes) (both device pointers, 16-byte aligned)
-int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_bytes, const LaunchCfg &cfg);
+// d_marks != nullptr: rows lie at a uniform pitch of `stride` bytes and are `len` bases long; their marks words (zeroed by the
+// caller, indexed from the first row of the range) receive Ns / has-N
+int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_bytes, uint32_t *d_marks, uint64_t stride, uint32_t len,
+                     const LaunchCfg &cfg);
+// row marks of reads [a.base, a.base + a.n) -> d_marks[a.base + r] (max_len: longest read if known, else 0)
+int launch_count_marks(const FilterArgs &a, uint32_t *d_marks, uint32_t max_len, const LaunchCfg &cfg);
 // after the pilot launch: *policy = 1 (go on with the full-K first pass) if more than `max_pushed` of the pilot's reads were
 // escalated, else 0 (go on with the cascade)
 int launch_policy(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s);
@@ -158,8 +164,8 @@ int launch_fq_records(const uint8_t *d_text, uint64_t lo, uint64_t n, const uint
                       uint32_t extra_line, uint32_t nl_cap, uint32_t rec_cap, uint32_t *d_seq_off, uint32_t *d_qual_off, uint32_t *d_len,
                       uint32_t *d_meta, cudaStream_t s);
 int launch_fq_convert(const uint8_t *d_text, const uint32_t *d_seq_off, const uint32_t *d_qual_off, const uint32_t *d_len,
-                      uint32_t n_rec, uint32_t stride, int lower_n, int qbase, uint8_t *d_slab, uint32_t *d_meta, int sm_count,
-                      cudaStream_t s);
+                      uint32_t n_rec, uint32_t stride, int lower_n, int qbase, uint8_t *d_slab, uint32_t *d_meta, uint32_t *d_marks,
+                      uint32_t truncate, int sm_count, cudaStream_t s);
 void parallel_memcpy(void *dst, const void *src, uint64_t bytes);   // all host threads
 int fastq_plan_chunk(const char *text, uint64_t text_bytes, uint64_t pos, uint64_t target_bytes, uint8_t *copy_to,
                      uint64_t *chunk_bytes_out, uint64_t *n_rec_out, uint64_t *n_newlines_out);
@@ -175,6 +181,18 @@ int parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_offset, i
 
 // run fn(0..n_tasks-1) on up to n_threads threads of a persistent host worker pool (moira_host.cpp)
 void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn);
+
+// ---- the counters' all-reduce over GPUs (moira_comm.cpp; NCCL bound at run time) ---------------------------------
+struct CommState;                       // one communicator rank; owned by a moira_ctx
+CommState *comm_state_new();
+void comm_state_free(CommState *s);
+int comm_unique_id(uint8_t id[MOIRA_COMM_ID_BYTES]);
+int comm_init_rank(CommState *s, int device, const uint8_t id[MOIRA_COMM_ID_BYTES], int rank, int n_ranks);
+int comm_init_all(CommState **states, const int *devices, int n);
+int comm_reduce_device(CommState *s, uint64_t *d_counters, cudaStream_t stream);
+int comm_reduce_host(CommState *s, uint64_t *counters);
+int comm_reduce_all(CommState **states, int n, uint64_t *const *counters);
+int comm_info(const CommState *s, int *rank, int *n_ranks);
 
 // sets the thread-local message returned by moira_last_error() and returns `code`
 int fail(int code, const char *fmt, ...);

@@ -73,6 +73,7 @@ constexpr int BLK_CAP = 24576;                   // PMF entries held in shared m
 constexpr int BLK_SMEM = BLK_CAP * 8 + 256 * 16;
 
 __constant__ double c_fact[MOIRA_FACT_N] = MOIRA_FACT_TABLE;
+__constant__ double c_inv[8] = {1.0, 1.0, 0.5, 0.33333333333333337, 0.25, 0.2, 0.16666666666666669, 0.14285714285714288};
 
 // ---- PTX helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -293,15 +294,12 @@ __device__ __forceinline__ double newton_bound(double p0, double p1, int kd)
 {
     if (!(p0 > 1e-280)) return 1.0;
     const double r = p1 / p0;
-    // 1/j rounded up (the 1e-9 margin of the callers covers every rounding here many times over)
-    const double inv[8] = {1.0, 1.0, 0.5, 0.33333333333333337, 0.25, 0.2, 0.16666666666666669, 0.14285714285714288};
+    // 1/j rounded up (the 1e-9 margin of the callers covers every rounding here many times over); kd <= 8
     double term = p1, sum = p0 + p1;
-#pragma unroll
-    for (int j = 2; j < 8; j++) {
-        if (j < kd) {
-            term = term * r * inv[j];
-            sum += term;
-        }
+#pragma unroll 1
+    for (int j = 2; j < kd; j++) {   // kd is launch-uniform: a real loop, not eight predicated copies
+        term = term * r * c_inv[j];
+        sum += term;
     }
     return sum == sum ? sum : 1.0;
 }
@@ -327,6 +325,7 @@ __device__ __forceinline__ bool cdf_quantile(const double (&P)[K], double oma, d
 }
 
 // Load one 16-byte vector of a staged row, mask what lies beyond the read to padding, account N/n.
+template <bool MARKS>
 __device__ __forceinline__ void load_vec(uint32_t addr, int rem, uint32_t (&w)[4], uint32_t &ns, uint32_t &has_n)
 {
     const uint4 q4 = lds128(addr);
@@ -335,7 +334,7 @@ __device__ __forceinline__ void load_vec(uint32_t addr, int rem, uint32_t (&w)[4
 #pragma unroll
         for (int i = 0; i < 4; i++) w[i] = mask_word(w[i], rem - 4 * i);
     }
-    count_marks4(w, ns, has_n);
+    if (MARKS) count_marks4(w, ns, has_n);
 }
 
 // Lookup address of byte b of w: table base (64 KB aligned) | Q << 8 | lane replica offset, in one PRMT.
@@ -382,20 +381,22 @@ __device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_l
 // `cfull` bytes (warp-uniform, multiple of 16) are inside the read for EVERY lane: no masking there.
 // MATH = false keeps only the N/n accounting (after a warp-wide early exit).
 // `swz` is the lane's XOR term of the TMA 128-byte swizzle ((lane & 7) << 4), 0 for the padded layout.
-template <int K, int MODE, bool PL, bool MATH>
+// MARKS = false: Ns / has-N of every row came with the slab (FilterArgs::row_marks), nothing is counted here.
+template <int K, int MODE, bool PL, bool MATH, bool MARKS>
 __device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t swz, uint32_t cfull, uint32_t cend, int rem0,
                                             uint32_t lut_lane, double (&P)[K], uint32_t &ns, uint32_t &has_n)
 {
+    if (!MATH && !MARKS) return;
     uint32_t v = 0;
     for (; v < cfull; v += 16) {
         const uint4 q4 = lds128(row + (v ^ swz));
         const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
-        count_marks4(w, ns, has_n);
+        if (MARKS) count_marks4(w, ns, has_n);
         if (MATH) sweep_vec<K, MODE, PL>(w, lut_lane, P);
     }
     for (; v < cend; v += 16) {
         uint32_t w[4];
-        load_vec(row + (v ^ swz), rem0 - (int)v, w, ns, has_n);
+        load_vec<MARKS>(row + (v ^ swz), rem0 - (int)v, w, ns, has_n);
         if (MATH) sweep_vec<K, MODE, PL>(w, lut_lane, P);
     }
 }
@@ -494,14 +495,19 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
     // LDGSTS instead of 32 when every lane fetches from its own row -- also for scattered ladder rows.
     const bool coop = true;
 
-    auto tile_read = [&](uint32_t t, bool &valid, uint32_t &r_local, ReadGeom &g) {
+    // Ns / has-N of every row given with the slab (produced by whoever wrote it): the sweep counts nothing
+    const bool marks_given = a.row_marks != nullptr;
+    uint32_t vec_steps = 0;   // 16-base vector steps this warp swept with the FP64 recurrence (warp-uniform)
+    auto tile_read = [&](uint32_t t, bool &valid, uint32_t &r_local, ReadGeom &g, uint32_t &marks) {
         uint32_t i = t * 32 + lane;
         valid = t < n_tiles && i < count;
         r_local = 0;
+        marks = 0;
         g.off = 0; g.len = 0; g.eff = 0;
         if (valid) {
             r_local = queue ? queue[i] : i;
             g = read_geom(a, r_local);
+            if (marks_given) marks = a.row_marks[a.base + r_local];
         }
     };
     // Stage chunk c of the tile's 32 rows into stage `s` with LDGSTS (cp.async), 16 bytes per lane
@@ -566,23 +572,23 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
     };
 
     bool valid, nvalid;
-    uint32_t r_local, nr_local;
+    uint32_t r_local, nr_local, marks, nmarks;
     ReadGeom g, ng;
-    tile_read(tile, valid, r_local, g);
+    tile_read(tile, valid, r_local, g, marks);
     if (tile < n_tiles) issue(g, tile, 0, it);
 
     while (tile < n_tiles) {
         const uint32_t next_tile = tile + total_warps;
-        tile_read(next_tile, nvalid, nr_local, ng);
+        tile_read(next_tile, nvalid, nr_local, ng, nmarks);
         const uint32_t maxeff = __reduce_max_sync(FULL, g.eff);
         const uint32_t mineff = __reduce_min_sync(FULL, g.eff);
-        const uint32_t nch = (maxeff + CHUNK - 1) / CHUNK;
+        uint32_t nch = (maxeff + CHUNK - 1) / CHUNK;
 
         double P[K];
 #pragma unroll
         for (int j = 0; j < K; j++) P[j] = 0.0;
         if (MODE == 0) P[0] = 1.0;
-        uint32_t ns = 0, has_n = 0;
+        uint32_t ns = marks & 0x7FFFFFFFu, has_n = marks >> 31;
         uint32_t processed = 0;
         bool skip_math = false;   // warp-uniform
 
@@ -605,9 +611,14 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
             const uint32_t cbeg = c * CHUNK;
             const uint32_t cend = maxeff - cbeg < CHUNK ? maxeff - cbeg : CHUNK;   // warp-uniform
             const uint32_t cfull = mineff > cbeg ? min((mineff - cbeg) & ~15u, cend) : 0u;   // warp-uniform
-            if (!skip_math) sweep_chunk<K, MODE, PL, true>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
-            else sweep_chunk<K, MODE, PL, false>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
-            if (!skip_math) processed = cbeg + cend;
+            if (!skip_math) {
+                if (marks_given) sweep_chunk<K, MODE, PL, true, false>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+                else sweep_chunk<K, MODE, PL, true, true>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+                processed = cbeg + cend;
+                vec_steps += (cend + 15u) >> 4;
+            } else if (!marks_given) {
+                sweep_chunk<K, MODE, PL, false, true>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+            }
             if (MODE == 0 && c + 1 < nch && !skip_math) {
                 // Early exit: sum_{j<K} P_k[j] never increases with k, so once it is safely below
                 // 1-alpha these K entries cannot reach the quantile.  Taken warp-wide only: the
@@ -625,7 +636,11 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
                     certain = valid && newton_bound(P[0], P[K >= 2 ? 1 : 0], a.k_dec) < a.oma - 1e-9;
                     all_certain = __all_sync(FULL, certain || finished) && __any_sync(FULL, certain);
                 }
-                if (all_certain) skip_math = true;
+                if (all_certain) {
+                    skip_math = true;
+                    // nothing left to count either: the chunk already in flight is consumed and the tile ends there
+                    if (marks_given) nch = c + 2;
+                }
             }
         }
 
@@ -650,7 +665,7 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
             const int kneed = kn > 1.0e6 ? 1000000 : (kn < 2.0 ? 2 : (int)kn);
             push_read(a, valid, pick_rung(a, kneed), r_local, lane);
             tile = next_tile;
-            valid = nvalid; r_local = nr_local; g = ng;
+            valid = nvalid; r_local = nr_local; g = ng; marks = nmarks;
             continue;
         }
         if (MODE == 0) {
@@ -698,8 +713,11 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         finish_read(a, valid, r_local, g, res, s_cnt, s_hist, lane);
 
         tile = next_tile;
-        valid = nvalid; r_local = nr_local; g = ng;
+        valid = nvalid; r_local = nr_local; g = ng; marks = nmarks;
     }
+    // FP64 operations the sweeps of this warp executed (thread level: 32 lanes x 16 positions per vector step)
+    constexpr uint32_t OPB = MODE == 0 ? (uint32_t)(3 * K - 2) + (PL ? 1u : 0u) : (MODE == 1 ? 1u : 2u);
+    if (lane == 0 && vec_steps && a.counters) atomicAdd(&a.counters[MOIRA_CNT_FP64_OPS], (unsigned long long)vec_steps * (512ull * OPB));
 }
 
 // MODE 0: Poisson-binomial with K entries.  MODE 1: Lambda accumulation (K == 1).
@@ -821,6 +839,7 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
         uint4 cur = make_uint4(0xFDFDFDFDu, 0xFDFDFDFDu, 0xFDFDFDFDu, 0xFDFDFDFDu);
         if (g.eff) cur = __ldg(reinterpret_cast<const uint4 *>(row));
         uint32_t swept = 0;   // bases covered by the FP64 sweep
+        uint32_t n_swept = 0; // called bases swept (warp-uniform)
         for (; pos < g.eff; pos += 16) {
             uint4 nxt = cur;
             if (pos + 16 < g.eff) nxt = __ldg(reinterpret_cast<const uint4 *>(row + pos + 16));
@@ -839,6 +858,7 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
                     const uint32_t q8 = (w[k] >> (8 * b)) & 0xFFu;
                     if (q8 >= 0xFDu) continue;               // warp-uniform: padding / N / n leave P untouched
                     const double2 qe = s_lut[q8];
+                    n_swept++;
                     double up = __shfl_up_sync(FULL, P[M - 1], 1);
                     if (lane == 0) up = 0.0;
 #pragma unroll
@@ -896,6 +916,7 @@ __global__ void __launch_bounds__(WPR_THREADS) wpr_kernel(const FilterArgs a)
         res.numeric = false;
         res.escalate = false;
         finish_read(a, lane == 0, r_local, g, res, s_cnt, s_hist, lane);
+        if (lane == 0 && a.counters) atomicAdd(&a.counters[MOIRA_CNT_FP64_OPS], (unsigned long long)n_swept * (96ull * M));
     }
     __syncthreads();
     flush_counters(a, s_cnt, s_hist);
@@ -1105,6 +1126,42 @@ __global__ void __launch_bounds__(256) len_scatter_kernel(const FilterArgs a, co
 }
 
 // ==================================================================================================
+// Row marks: Ns (bits 0..30) and has-'N' (bit 31) of every row, for slabs whose producer did not write them.
+// G lanes per row (16 bytes each per step); memory-bound.
+// ==================================================================================================
+template <int G>
+__global__ void __launch_bounds__(256) count_marks_kernel(const FilterArgs a, uint32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31, sub = lane & (G - 1);
+    const uint64_t groups = (uint64_t)gridDim.x * (256 / G);
+    const uint64_t n_round = ((uint64_t)a.n + (32 / G) - 1) / (32 / G) * (32 / G);   // whole warps stay convergent
+    for (uint64_t r = (uint64_t)blockIdx.x * (256 / G) + threadIdx.x / G; r < n_round; r += groups) {
+        uint32_t ns = 0, up = 0;
+        if (r < a.n) {
+            const ReadGeom g = read_geom(a, (uint32_t)r);
+            const uint8_t *row = a.slab + g.off;
+            for (uint32_t pos = sub * 16; pos < g.eff; pos += G * 16) {
+                const uint4 q4 = __ldg(reinterpret_cast<const uint4 *>(row + pos));
+                uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+                const int rem = (int)g.eff - (int)pos;
+                if (rem < 16) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) w[k] = mask_word(w[k], rem - 4 * k);
+                }
+                count_marks4(w, ns, up);
+            }
+        }
+        up = up ? 1u : 0u;
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) {
+            ns += __shfl_xor_sync(FULL, ns, o);
+            up |= __shfl_xor_sync(FULL, up, o);
+        }
+        if (sub == 0 && r < a.n) out[a.base + r] = ns | (up << 31);
+    }
+}
+
+// ==================================================================================================
 // 6-bit transport image -> slab: 12 image bytes (16 codes) -> 16 slab bytes per thread; flat over the
 // whole chunk (rows keep their positions: image offset = slab offset * 3/4).  Memory-bound.
 // ==================================================================================================
@@ -1117,7 +1174,10 @@ __device__ __forceinline__ uint32_t q6_expand4(uint32_t v24)
 }
 
 // one thread per 16 slab bytes (= 12 image bytes = 3 words): exact, never writes past the range
-__global__ void __launch_bounds__(256) unpack_q6_kernel(const uint32_t *__restrict__ in, uint4 *__restrict__ out, uint64_t n16)
+// marks != nullptr (rows at a uniform pitch of stride16 units, all `len` bases long): the thread that expands a unit with
+// 'N' / 'n' codes inside the read adds them to its row's marks word (zeroed by the caller) -- the filter then counts nothing.
+__global__ void __launch_bounds__(256) unpack_q6_kernel(const uint32_t *__restrict__ in, uint4 *__restrict__ out, uint64_t n16,
+                                                        uint32_t *__restrict__ marks, uint32_t stride16, uint32_t len)
 {
     for (uint64_t u = blockIdx.x * 256ull + threadIdx.x; u < n16; u += gridDim.x * 256ull) {
         const uint32_t w0 = __ldg(in + 3 * u), w1 = __ldg(in + 3 * u + 1), w2 = __ldg(in + 3 * u + 2);
@@ -1127,6 +1187,21 @@ __global__ void __launch_bounds__(256) unpack_q6_kernel(const uint32_t *__restri
         o.z = q6_expand4((w1 >> 16) | ((w2 & 0xFFu) << 16));
         o.w = q6_expand4(w2 >> 8);
         out[u] = o;
+        if (marks && ((o.x | o.y | o.z | o.w) & 0x80808080u)) {
+            const uint64_t row = u / stride16;
+            const int rem = (int)len - (int)((u - row * stride16) * 16);
+            uint32_t w[4] = {o.x, o.y, o.z, o.w};
+            if (rem < 16) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] = mask_word(w[k], rem - 4 * k);
+            }
+            uint32_t ns = 0, up = 0;
+            count_marks4(w, ns, up);
+            if (ns) {
+                atomicAdd(&marks[row], ns);
+                if (up) atomicOr(&marks[row], 0x80000000u);
+            }
+        }
     }
 }
 
@@ -1243,13 +1318,25 @@ int launch_length_sort(const FilterArgs &a, const LenSortBufs &b, int single_gro
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_bytes, const LaunchCfg &cfg)
+int launch_unpack_q6(const uint8_t *d_image, uint8_t *d_slab, uint64_t slab_bytes, uint32_t *d_marks, uint64_t stride, uint32_t len,
+                     const LaunchCfg &cfg)
 {
     const uint64_t n48 = slab_bytes / 16;           // units of 16 slab bytes <- 12 image bytes
     if (!n48) return 0;
     const uint64_t want = (n48 + 255) / 256;
     const int grid = (int)std::min<uint64_t>(want, (uint64_t)cfg.sm_count * 16);
-    unpack_q6_kernel<<<grid, 256, 0, cfg.stream>>>(reinterpret_cast<const uint32_t *>(d_image), reinterpret_cast<uint4 *>(d_slab), n48);
+    unpack_q6_kernel<<<grid, 256, 0, cfg.stream>>>(reinterpret_cast<const uint32_t *>(d_image), reinterpret_cast<uint4 *>(d_slab), n48,
+                                                   d_marks, (uint32_t)(stride / 16), len);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_count_marks(const FilterArgs &a, uint32_t *d_marks, uint32_t max_len, const LaunchCfg &cfg)
+{
+    if (!a.n) return 0;
+    const int grid = cfg.sm_count * 8;
+    if (max_len && max_len <= 128) count_marks_kernel<8><<<grid, 256, 0, cfg.stream>>>(a, d_marks);
+    else if (max_len && max_len <= 256) count_marks_kernel<16><<<grid, 256, 0, cfg.stream>>>(a, d_marks);
+    else count_marks_kernel<32><<<grid, 256, 0, cfg.stream>>>(a, d_marks);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
