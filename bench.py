@@ -2,18 +2,24 @@
 """bench.py -- reads/s through the Poisson-binomial filter (BASELINE.json metric).
 
 Own arm:  python bench.py [--gpus N] [--steps K] [--warmup W]
-  One rank per GPU (torchrun for N > 1).  Workload = BASELINE config C2: 10 M synthetic 253-bp V4
-  contigs per GPU (MiSeq profile, weak scaling), --error_calc poisson_binomial, alpha 0.005,
-  uncert 0.01, treat_as_errors.  A step = one pass of the filter over the GPU's 10 M reads.
-    value   reads/s, whole job, inputs resident in HBM (moira_filter_device, decision mode)
-    e2e     the same through moira_filter_batch with pinned HOST buffers: H2D of the slab, kernels,
-            D2H of ee/Ns/flags/counters inside the timed region
-    roofline       dominant kernel pb_tpr<K=4> against the FP64 (non-fused DMUL/DADD) issue peak
-                   measured live with moira_fp64_peak, plus the HBM view
+  One rank per GPU (torchrun for N > 1).  Headline workload = BASELINE config C2: 10 M synthetic 253-bp V4 contigs per
+  GPU (MiSeq profile, weak scaling), --error_calc poisson_binomial, alpha 0.005, uncert 0.01, treat_as_errors.
+  A step = one pass of the filter over the GPU's reads; the counters accumulate over the steps and are summed over the
+  GPUs by ONE all-reduce (the library's own NCCL call) behind the last step, inside the timed region.
+    value          reads/s, whole job, inputs resident in HBM (moira_filter_device, decision mode)
+    roofline       the step's first-pass launches against the FP64 (non-fused DMUL/DADD) issue peak measured live with
+                   moira_fp64_peak; frac = FP64 operations EXECUTED (device counter) / time / peak, never above 1
+    roofline_exact the same for exact-ee mode (what --collapse needs), with the algorithmic flop of SURVEY 8d beside it
+    e2e            the same metric through moira_filter_batch with pinned HOST byte slabs: H2D, kernels, D2H inside the
+                   timed region; frac_of_link against a copy probe run at the same N
+    configs        the other BASELINE.json configs (C3 ragged ~450 bp, C4 1500 bp exact + collapse, C5 mixed lengths in
+                   three modes) and a real-profile workload bootstrapped from the reference's own contig fixture, each with
+                   reads/s, executed-flop roofline fraction and a bit-exact parity sample against oracle/
     cpu_baseline   the unmodified reference C core (oracle/_ref) on this box's host cores, N = 1 only
-Reference arm:  python bench.py --impl reference ...   times oracle/_ref on the host cores.
+Reference arm:  python bench.py --impl reference ...   times oracle/_ref on the host cores (no CUDA library is loaded).
 """
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -32,11 +38,22 @@ UNCERT = 0.01
 METRIC = "reads/s Poisson-binomial filter (253-bp)"
 WORKLOAD = "C2: 10M synthetic 253-bp V4 contigs per GPU, MiSeq profile, poisson_binomial, alpha 0.005, uncert 0.01"
 FALLBACK_HBM_GBS = 6650.0
+SEED = 20160105
 
 
-def _cpu_sample(n_reads, seed):
-    from moira_b200 import synth
-    return synth.generate("v4", n_reads, seed)
+def shared_config(reads_per_gpu):
+    """The `config` object of BOTH arms (the driver compares them key by key)."""
+    return {"workload": WORKLOAD, "reads_per_gpu": reads_per_gpu, "read_len": READ_LEN, "row_stride": STRIDE,
+            "error_calc": "poisson_binomial", "alpha": ALPHA, "uncert": UNCERT, "ambigs": "treat_as_errors"}
+
+
+def _load_synth_standalone():
+    """moira_b200/synth.py without importing the package (whose __init__ loads the CUDA library): the reference arm
+    must not map the product's .so."""
+    spec = importlib.util.spec_from_file_location("moira_synth_standalone", os.path.join(ROOT, "moira_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _time_reference(slab, off, ln, threads):
@@ -69,11 +86,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    synth = _load_synth_standalone()
     cores = os.cpu_count() or 1
-    probe = _cpu_sample(20000, 20160105 + 1)
+    probe = synth.generate("v4", 20000, SEED + 1)
     rate, _, kind, threads = _time_reference(*probe, threads=cores)
     per_step = int(min(2_000_000, max(20000, rate * 4.0)))          # ~4 s of CPU work per step
-    slab, off, ln = _cpu_sample(per_step, 20160105 + 1)
+    slab, off, ln = synth.generate("v4", per_step, SEED + 1)
     for _ in range(args.warmup):
         _time_reference(slab[: 20000 * STRIDE], off[:20000], ln[:20000], threads)
     t0 = time.perf_counter()
@@ -81,17 +99,27 @@ def run_reference(args):
         _time_reference(slab, off, ln, threads)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = "%d reads per step x %d steps of the C2 workload (same generator, seed 20160106)" % (per_step, args.steps)
+    sample = "%d reads per step x %d steps of the C2 workload (same generator, seed %d)" % (per_step, args.steps, SEED + 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_step": per_step, "read_len": READ_LEN, "error_calc": "poisson_binomial"},
+        "config": shared_config(args.reads),
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=_OUT, flush=True)
+
+
+def collapse_bench(ctx, w, px, world, barrier, max_over_ranks):
+    """C4's second half (filled in with the device-side dereplication): None until then."""
+    return None
+
+
+def cli_bench(text, world, rank, args):
+    """The CLI a user runs, wall clock (filled in with the multi-device CLI): None until then."""
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -166,6 +194,7 @@ def run_ours(args):
     import moira_b200
     from moira_b200 import FilterParams, synth
     from moira_b200 import _lib as L
+    from oracle import py_oracle as po     # the CHECKER of the parity samples (and the cpu_baseline leg), never the product
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,148 +202,251 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
+    ctx = moira_b200.Context(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = args.reads
-    ctx = moira_b200.Context(local_rank)
-
-    # ---- synthetic input, resident in HBM (2.56 GB per GPU >> 126 MB L2: no flush needed) ----
-    slab = synth.generate_v4_device(n, 20160105 + 1 + 1000 * rank, dev)
-    ee = torch.empty(n, dtype=torch.float64, device=dev)
-    ns = torch.empty(n, dtype=torch.int32, device=dev)
-    fl = torch.empty(n, dtype=torch.uint8, device=dev)
-    cnt = torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev)
+        # the path's only collective lives in the library: rank 0's communicator id travels over torch.distributed (plumbing)
+        box = [moira_b200.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
     stream = torch.cuda.current_stream().cuda_stream
-    p_dec = FilterParams(alpha=ALPHA, uncert=UNCERT, exact_ee=False)
-    p_exact = FilterParams(alpha=ALPHA, uncert=UNCERT, exact_ee=True)
-
-    def step(params):
-        cnt.zero_()
-        ctx.filter_device(slab.data_ptr(), None, None, STRIDE, READ_LEN, n, params, ee.data_ptr(), ns.data_ptr(),
-                          fl.data_ptr(), cnt.data_ptr(), stream)
-        if world > 1:   # the path's only collective: good/bad counts + error histogram
-            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = FALLBACK_HBM_GBS, "fallback 6650 GB/s"
+    if os.path.exists(peaks_path):
+        try:
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(params, steps, timing=False):
-        barrier()
-        if timing:
-            ctx.set_timing(True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ctx.launch_count
-        e0.record()
-        for _ in range(steps):
-            step(params)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = ctx.launch_count - l0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        kms, kname = (ctx.last_kernel_ms() if timing else (0.0, ""))
-        if timing:
-            ctx.set_timing(False)
-        return ms, launches, kms, kname
+    t_start = time.time()
 
-    for _ in range(max(3, args.warmup)):
-        step(p_dec)
+    def log(tag, obj):
+        if rank == 0:
+            print("[bench %6.1fs] %s: %s" % (time.time() - t_start, tag, json.dumps(obj)), file=sys.stderr, flush=True)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    class Work:
+        """One device-resident workload: slab (+ lengths, + row marks) and its output arrays."""
+
+        def __init__(self, profile, n, seed, with_sequences=False):
+            self.profile, self.n = profile, n
+            self.stride, self.fixed = synth.DEVICE_LAYOUT[profile]
+            self.slab, self.lengths, self.seqs = synth.generate_device(profile, n, seed, dev, with_sequences=with_sequences)
+            self.max_len = self.fixed or int(self.lengths.max().item())
+            self.min_len = self.fixed or int(self.lengths.min().item())
+            self.ee = torch.empty(n, dtype=torch.float64, device=dev)
+            self.ns = torch.empty(n, dtype=torch.int32, device=dev)
+            self.fl = torch.empty(n, dtype=torch.uint8, device=dev)
+            self.cnt = torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev)
+            # row marks (Ns | has-N per row): what every producer of a slab inside the library leaves next to it (6-bit
+            # expansion, FASTQ conversion); here the stand-alone producer, once, like the generator itself
+            self.marks = torch.zeros(n, dtype=torch.int32, device=dev)
+            ctx.count_marks_device(self.slab.data_ptr(), None, None if self.lengths is None else self.lengths.data_ptr(),
+                                   self.stride, self.fixed or 0, n, self.marks.data_ptr(), 0, stream)
+            torch.cuda.synchronize()
+
+        def params(self, **kw):
+            return FilterParams(alpha=ALPHA, uncert=UNCERT, max_length=self.max_len, min_length=self.min_len, **kw)
+
+        def run(self, params, marks=True):
+            ctx.filter_device(self.slab.data_ptr(), None, None if self.lengths is None else self.lengths.data_ptr(), self.stride,
+                              self.fixed or 0, self.n, params, self.ee.data_ptr(), self.ns.data_ptr(), self.fl.data_ptr(),
+                              self.cnt.data_ptr(), stream, self.marks.data_ptr() if marks else None)
+
+        def timed(self, params, steps, warm=3, marks=True, kernel_timing=False):
+            """(ms total, launches, first-pass kernel ms total, kernel name, counters summed over ranks and steps)."""
+            for _ in range(warm):
+                self.run(params, marks)
+            barrier()
+            if kernel_timing:
+                ctx.set_timing(True)
+            self.cnt.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ctx.launch_count
+            e0.record()
+            for _ in range(steps):
+                self.run(params, marks)
+            if world > 1:   # the path's only collective: good / bad counts + error histogram (SURVEY.md 8e), once per job
+                ctx.reduce_counters_device(self.cnt.data_ptr(), stream)
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            launches = ctx.launch_count - l0
+            kms, kname = (ctx.last_kernel_ms() if kernel_timing else (0.0, ""))
+            if kernel_timing:
+                ctx.set_timing(False)
+            return ms, launches, kms, kname, self.cnt.cpu().numpy().astype(np.int64)
+
+        def lens_host(self, sel):
+            return np.full(len(sel), self.fixed, np.uint32) if self.lengths is None else self.lengths[sel].cpu().numpy().astype(np.uint32)
+
+        def parity(self, k, exact_params, decision_params, calc="poisson_binomial"):
+            """GPU vs oracle/ on the first and the last k/2 reads of THIS rank's workload: ee / Ns bit-exact in exact mode,
+            decisions (and ee of the reads that are not flagged lower-bound) in decision mode."""
+            k = min(k, self.n)
+            sel = torch.cat([torch.arange(0, k // 2, device=dev), torch.arange(self.n - (k - k // 2), self.n, device=dev)])
+            rows = self.slab[sel].cpu().numpy().reshape(-1)
+            lens = self.lens_host(sel)
+            offs = np.arange(k, dtype=np.uint64) * np.uint64(self.stride)
+            if calc == "poisson_binomial":
+                ee_o, ns_o = po.pb_batch(rows, offs, lens, ALPHA)
+            else:
+                ee_o, ns_o, _ = po.poisson_batch(rows, offs, lens, ALPHA)
+            ok_o = (ee_o + ns_o) <= lens.astype(np.float64) * UNCERT
+            out = {"sample_reads_per_rank": int(k), "checker": "oracle/pb_oracle.c" if calc == "poisson_binomial" else "oracle/py_oracle.py"}
+            self.run(exact_params)
+            torch.cuda.synchronize()
+            ee_g, ns_g, fl_g = self.ee[sel].cpu().numpy(), self.ns[sel].cpu().numpy(), self.fl[sel].cpu().numpy()
+            near = (fl_g & L.FLAG_NEAR_CUTOFF) != 0
+            if calc == "poisson_binomial":
+                out["ee_bit_mismatches"] = int((ee_g != ee_o).sum())
+            else:   # device exp / pow against glibc: the tolerance north_star states
+                out["ee_rel_err_max"] = float(np.max(np.abs(ee_g - ee_o) / np.maximum(np.abs(ee_o), 1e-300)))
+                out["ee_outside_1e-12"] = int((np.abs(ee_g - ee_o) > 1e-12 * np.maximum(np.abs(ee_o), 1e-300)).sum())
+            out["ns_mismatches"] = int((ns_g != ns_o).sum())
+            out["decision_mismatches_outside_band"] = int((((fl_g & 1) != 0) != ok_o)[~near].sum())
+            if decision_params is not None:
+                self.run(decision_params)
+                torch.cuda.synchronize()
+                ee_d, fl_d = self.ee[sel].cpu().numpy(), self.fl[sel].cpu().numpy()
+                lb = (fl_d & L.FLAG_LOWER_BOUND) != 0
+                near_d = (fl_d & L.FLAG_NEAR_CUTOFF) != 0
+                out["decision_mode_decision_mismatches"] = int((((fl_d & 1) != 0) != ok_o)[~near_d].sum())
+                if calc == "poisson_binomial":
+                    out["decision_mode_ee_bit_mismatches"] = int((ee_d[~lb] != ee_o[~lb]).sum())
+                out["decision_mode_lower_bound_violations"] = int((ee_d[lb] > ee_o[lb]).sum())
+            for key in list(out):
+                if key.endswith("mismatches") or key.endswith("violations") or key.endswith("band") or key.endswith("1e-12"):
+                    out[key] = int(sum_over_ranks(out[key]))
+            return out
+
+        def algorithmic_flop_exact(self):
+            """SURVEY 8d for exact-ee mode: sum_r (L'-1)(3 K_r - 2) + (K_r - 1) + 6 with K_r = j*_r + 1, from the ee the
+            last exact pass left on the device (j* = ceil(ee), 1 where ee == 0)."""
+            lens = torch.full((self.n,), float(self.fixed), device=dev, dtype=torch.float64) if self.lengths is None else self.lengths.double()
+            lp = (lens - self.ns.double()).clamp_(min=1)
+            k = torch.ceil(self.ee).clamp_(min=1) + 1
+            return float(((lp - 1) * (3 * k - 2) + (k - 1) + 6).sum().item())
+
+        def algorithmic_flop_decision(self):
+            """SURVEY 8d for decision mode: K_r = floor(cutoff_r) + 2, cutoff_r = L * uncert - Ns."""
+            lens = torch.full((self.n,), float(self.fixed), device=dev, dtype=torch.float64) if self.lengths is None else self.lengths.double()
+            nsd = self.ns.double()
+            lp = (lens - nsd).clamp_(min=1)
+            k = torch.floor((lens * UNCERT - nsd).clamp_(min=0)) + 2
+            return float(((lp - 1) * (3 * k - 2) + (k - 1) + 6).sum().item())
+
+    peak_ops, _ = ctx.fp64_peak(40000)
+    peak_ops, _ = ctx.fp64_peak(40000)
+
+    def fp64_view(counters, steps, ms_total, n_reads):
+        """executed-FP64 roofline of `steps` passes: device counter / time / live peak."""
+        ops = float(counters[L.CNT_FP64_OPS]) / world / steps                 # per GPU and step
+        sec = ms_total * 1e-3 / steps
+        return {"executed_flop_per_read": ops / n_reads, "achieved": ops / sec / 1e12, "peak": peak_ops / 1e12, "unit": "TFLOP/s",
+                "frac": ops / sec / peak_ops}
+
+    # ==== C2, the headline ===================================================================================
+    n = args.reads
+    c2 = Work("v4", n, SEED + 1 + 1000 * rank)
+    p_dec, p_exact = c2.params(exact_ee=False), c2.params(exact_ee=True)
+    c2.timed(p_dec, max(3, args.warmup), warm=0)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    ms, launches, kms, kname = timed(p_dec, args.steps, timing=True)
+    ms, launches, kms, kname, counters = c2.timed(p_dec, args.steps, warm=0, kernel_timing=True)
     sampler.stop_flag = True
     sampler.join()
     value = world * n * args.steps / (ms * 1e-3)
-    counters = cnt.cpu().numpy().astype(np.int64)
-    accepted_frac = float(counters[L.CNT_ACCEPTED]) / max(1, int(counters[L.CNT_READS]))
-
-    # exact-ee mode (what --collapse needs), same inputs
-    for _ in range(2):
-        step(p_exact)
-    ms_x, _, _, _ = timed(p_exact, max(3, args.steps // 4))
-    value_exact = world * n * max(3, args.steps // 4) / (ms_x * 1e-3)
-
-    # ---- parity on a bounded sample of THIS run's reads: GPU (exact mode, last step) vs the oracle ----
-    parity = None
-    if rank == 0:
-        from oracle import py_oracle as po
-        k = 20000   # the first and the last 10 000 reads (the last ones sit in the second ladder sub-batch)
-        sel = torch.cat([torch.arange(0, k // 2, device=dev), torch.arange(n - k // 2, n, device=dev)])
-        rows_s = slab[sel].cpu().numpy().reshape(-1)
-        ee_o, ns_o = po.pb_batch(rows_s, np.arange(k, dtype=np.uint64) * STRIDE, np.full(k, READ_LEN, np.uint32), ALPHA)
-        ee_g, ns_g, fl_g = ee[sel].cpu().numpy(), ns[sel].cpu().numpy(), fl[sel].cpu().numpy()
-        ok_o = (ee_o + ns_o) <= READ_LEN * UNCERT
-        near = (fl_g & L.FLAG_NEAR_CUTOFF) != 0
-        parity = {"sample_reads": k, "ee_bit_mismatches": int((ee_g != ee_o).sum()), "ns_mismatches": int((ns_g != ns_o).sum()),
-                  "decision_mismatches_outside_band": int((((fl_g & 1) != 0) != ok_o)[~near].sum()),
-                  "near_cutoff_reads_whole_run": int(counters[L.CNT_NEAR_CUTOFF]), "checker": "oracle/pb_oracle.c"}
-
-    # ---- roofline of the dominant kernel --------------------------------------------------------
-    # The step's launches are one group, "pb_cascade<2,4>": pilot + verdict + two-entry sweep (+ the skipped full sweep)
-    # + four-entry sweep over the escalated reads.  `achieved` follows SURVEY.md 8d: ALGORITHMIC flop per read (K = 4
-    # entries for every base of every read, no credit for work avoided) x reads / measured time of the group.  The
-    # cascade executes fewer FP64 operations than that, so this figure can exceed the pipe's peak; `executed` is the
-    # operation count it really issues, and `single_sweep` is the K = 4 kernel on its own (cascade = 2), where
-    # executed == algorithmic.
+    reads_total = max(1, int(counters[L.CNT_READS]))
+    accepted_frac = float(counters[L.CNT_ACCEPTED]) / reads_total
+    escalated_frac = float(counters[L.CNT_ESCALATED]) / reads_total
+    # all-reduced counters against the sum of every rank's own flags (N-rank GPU parity of the collective)
+    local_acc = float((c2.fl & 1).sum().item()) * args.steps
+    counters_check = {"accepted_allreduced": int(counters[L.CNT_ACCEPTED]), "accepted_sum_of_rank_flags": int(sum_over_ranks(local_acc)),
+                      "reads_allreduced": int(counters[L.CNT_READS]), "reads_expected": world * n * args.steps}
+    counters_check["ok"] = (counters_check["accepted_allreduced"] == counters_check["accepted_sum_of_rank_flags"]
+                            and counters_check["reads_allreduced"] == counters_check["reads_expected"])
+    kernel_ms = kms / max(1, min(args.steps, 256))            # the library keeps the first 256 timed launch groups
     k_dec = synth.decision_k(READ_LEN, UNCERT)
-    kernel_ms = kms / max(1, min(args.steps, 256))   # the library keeps the first 256 timed launches
     w_fp64, w_hbm = synth.w_fp64(READ_LEN, k_dec), synth.w_hbm(READ_LEN)
-    peak_ops, _ = ctx.fp64_peak(40000)
-    achieved = n * w_fp64 / (kernel_ms * 1e-3)
-    escalated_frac = float(counters[L.CNT_ESCALATED]) / max(1, int(counters[L.CNT_READS]))
-    padded = (READ_LEN + 15) // 16 * 16
-    # two-entry sweep: DSUB + 3 DMUL + DADD per swept position; escalated reads: 7 DMUL + 3 DADD per position again
-    executed_per_read = 5 * padded + escalated_frac * 10 * padded if "cascade" in kname else 10 * padded
-    p_single = FilterParams(alpha=ALPHA, uncert=UNCERT, exact_ee=False, cascade=2)
-    for _ in range(3):
-        step(p_single)
-    ms_s, _, kms_s, kname_s = timed(p_single, args.steps, timing=True)
-    kernel_ms_s = kms_s / max(1, min(args.steps, 256))
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    hbm_peak, hbm_src = FALLBACK_HBM_GBS, "fallback"
-    if os.path.exists(peaks_path):
-        try:
-            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
-        except Exception:
-            pass
-    hbm_achieved = n * w_hbm / (kernel_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of the group's dominant kernel from the committed ncu --set full capture
+    exec_ops = float(counters[L.CNT_FP64_OPS]) / world / args.steps
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tj[kname if kname in tj else "pb_tpr<K=4>"]["dram_bytes_per_read"] * n
     except Exception:
         pass
+    # the same pass without the row marks (the sweep counts N/n itself), and the single K=4 sweep (cascade = 2)
+    ms_sc, _, kms_sc, _, cnt_sc = c2.timed(p_dec, args.steps, marks=False, kernel_timing=True)
+    p_single = c2.params(exact_ee=False, cascade=2)
+    ms_s, _, kms_s, kname_s, cnt_s = c2.timed(p_single, args.steps, kernel_timing=True)
+    kernel_ms_s = kms_s / max(1, min(args.steps, 256))
+    exec_ops_s = float(cnt_s[L.CNT_FP64_OPS]) / world / args.steps
+    hbm_achieved = n * w_hbm / (kernel_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "fp64", "kernel": kname, "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "TFLOP/s",
-        "frac": achieved / peak_ops, "traffic": traffic,
+        "bound": "fp64", "kernel": kname, "achieved": exec_ops / (kernel_ms * 1e-3) / 1e12, "peak": peak_ops / 1e12, "unit": "TFLOP/s",
+        "frac": exec_ops / (kernel_ms * 1e-3) / peak_ops, "traffic": traffic,
         "peak_source": "moira_fp64_peak: register-resident non-fused DMUL/DADD probe, measured live in this run",
-        "flop_per_read": w_fp64, "kernel_ms": kernel_ms,
-        "note": "achieved = algorithmic flop (SURVEY 8d: K=4 entries, every base, no credit for avoided work) / time of the step's "
-                "launches; the cascade executes fewer operations (see executed), so frac may exceed 1",
-        "executed": {"flop_per_read": executed_per_read, "escalated_fraction": escalated_frac,
-                     "achieved": n * executed_per_read / (kernel_ms * 1e-3) / 1e12,
-                     "frac": n * executed_per_read / (kernel_ms * 1e-3) / peak_ops},
-        "single_sweep": {"kernel": kname_s, "value": world * n * args.steps / (ms_s * 1e-3), "kernel_ms": kernel_ms_s,
-                         "achieved": n * w_fp64 / (kernel_ms_s * 1e-3) / 1e12, "frac": n * w_fp64 / (kernel_ms_s * 1e-3) / peak_ops,
-                         "note": "cascade = 2: one K=4 sweep over every read; executed == algorithmic flop"},
-        "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                "bytes_per_read": w_hbm, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)" if hbm_src == "measured" else "fallback 6650 GB/s"},
+        "kernel_ms": kernel_ms, "executed_flop_per_read": exec_ops / n, "escalated_fraction": escalated_frac,
+        "note": "achieved = FP64 operations the launches EXECUTED (device counter MOIRA_CNT_FP64_OPS: swept positions x operations "
+                "per position) / CUDA-event time of the step's first-pass launches",
+        "algorithmic_flop_per_read": w_fp64, "algorithmic_tflops": n * w_fp64 / (kernel_ms * 1e-3) / 1e12,
+        "algorithmic_note": "SURVEY 8d credit (K=4 entries for every base, no credit for work avoided): may exceed the peak, not a hardware fraction",
+        "single_sweep_kernel": kname_s, "single_sweep_value": world * n * args.steps / (ms_s * 1e-3),
+        "single_sweep_frac": exec_ops_s / (kernel_ms_s * 1e-3) / peak_ops, "single_sweep_kernel_ms": kernel_ms_s,
+        "slab_only_value": world * n * args.steps / (ms_sc * 1e-3),
+        "slab_only_frac": float(cnt_sc[L.CNT_FP64_OPS]) / world / args.steps / (kms_sc / max(1, min(args.steps, 256)) * 1e-3) / peak_ops,
+        "hbm_frac": hbm_achieved / hbm_peak, "hbm_achieved_gbs": hbm_achieved, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+        "hbm_bytes_per_read": w_hbm,
     }
 
-    # ---- end to end through the host-buffer C-ABI call ------------------------------------------------
+    # ---- exact-ee mode (what --collapse needs), same inputs ----
+    x_steps = max(3, args.steps // 4)
+    ms_x, _, _, _, cnt_x = c2.timed(p_exact, x_steps, warm=2)
+    value_exact = world * n * x_steps / (ms_x * 1e-3)
+    alg_x = c2.algorithmic_flop_exact()
+    roofline_exact = dict(fp64_view(cnt_x, x_steps, ms_x, n), bound="fp64", kernel="pb_cascade<2,4> + escalation ladder (whole step)",
+                          value=value_exact, ms_per_step=ms_x / x_steps,
+                          algorithmic_flop_per_read=alg_x / n, algorithmic_frac=alg_x / (ms_x * 1e-3 / x_steps) / peak_ops,
+                          note="frac = executed FP64 operations / whole-step time / peak; algorithmic = sum_r (L'-1)(3K_r-2)+(K_r-1)+6 with "
+                               "K_r = j*_r + 1 (SURVEY 8d, exact mode) from the device's own ee")
+    parity = c2.parity(20000, p_exact, p_dec)
+    parity["near_cutoff_reads_whole_run"] = int(counters[L.CNT_NEAR_CUTOFF])
+    parity["counters_vs_rank_flags"] = counters_check
+
+    # ==== host link probe (every rank at once: the rate a rank gets while all of them stream) ===============
+    link = None
+    if not args.no_e2e:
+        barrier()
+        h2d_gbs, d2h_gbs = ctx.link_probe(1 << 30, 3)
+        link = {"h2d_gb_per_s_per_gpu": h2d_gbs, "d2h_gb_per_s_per_gpu": d2h_gbs, "h2d_gb_per_s_all_gpus": sum_over_ranks(h2d_gbs),
+                "note": "1 GiB cudaMemcpyAsync from / to pinned host memory, best of 3, every rank at the same time"}
+
+    # ==== end to end through the host-buffer C-ABI call ======================================================
     e2e = None
     if not args.no_e2e:
         h_slab = moira_b200.PinnedBuffer(n * STRIDE)
         torch.cuda.synchronize()
-        h_t = torch.from_numpy(h_slab.u8)
-        h_t.copy_(slab.view(-1))
+        torch.from_numpy(h_slab.u8).copy_(c2.slab.view(-1))
         h_out = moira_b200.PinnedBuffer(n * 13 + 4096)
         out = moira_b200.FilterResult(h_out.view(np.float64, n), h_out.view(np.int32, n, n * 8),
                                       h_out.view(np.uint8, n, n * 12), np.zeros(L.N_COUNTERS, np.uint64))
@@ -324,55 +456,59 @@ def run_ours(args):
         lens = h_meta.view(np.uint32, n, n * 8)
         lens[:] = READ_LEN
         e_steps = max(2, min(5, args.steps))
+        p_e2e = FilterParams(alpha=ALPHA, uncert=UNCERT, exact_ee=False)
 
-        def time_e2e(host_slab, params):
-            ctx.filter_batch(host_slab, off, lens, params, out)         # warm-up (allocates device buffers)
-            ctx.filter_batch(host_slab, off, lens, params, out)
+        def time_e2e(host_slab, params, before=None):
+            for _ in range(2):                                     # warm-up (allocates device buffers)
+                ctx.filter_batch(host_slab, off, lens, params, out)
             barrier()
             t0 = time.perf_counter()
             for _ in range(e_steps):
+                if before is not None:
+                    before()
                 ctx.filter_batch(host_slab, off, lens, params, out)
             barrier()
-            dt = time.perf_counter() - t0
-            if world > 1:
-                t = torch.tensor([dt], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
+            dt = max_over_ranks(time.perf_counter() - t0)
             assert int(out.counters[L.CNT_READS]) == n, "e2e pass did not process every read"
             return dt
 
-        dt8 = time_e2e(h_slab.u8, p_dec)
+        d2h = n * 13 + L.N_COUNTERS * 8
+        dt8 = time_e2e(h_slab.u8, p_e2e)
         acc8 = int(out.counters[L.CNT_ACCEPTED])
-        e2e_q8 = {"value": world * n * e_steps / dt8, "unit": "reads/s", "h2d_bytes_per_step": n * STRIDE,
-                  "d2h_bytes_per_step": n * 13 + L.N_COUNTERS * 8, "steps": e_steps, "ms_per_step": dt8 / e_steps * 1e3,
-                  "api": "moira_filter_batch, one byte per base"}
-        # the library's 6-bit transport image of the same slab (moira_pack_q6, packed once by the host packer
-        # like the slab itself): 3/4 of the bytes cross PCIe, the device expands them before filtering
+        # the library's 6-bit transport image of the same slab: 3/4 of the bytes cross PCIe, the device expands them (and leaves
+        # the row marks) before filtering.  q6_prepacked: the host packer wrote the image once (like the slab itself);
+        # q6_pack_in_loop: moira_pack_q6 of the whole slab inside every timed step.
         h_img = moira_b200.PinnedBuffer(n * STRIDE // 16 * 12)
         moira_b200.pack_q6(h_slab.u8, out=h_img.u8)
         p_q6 = FilterParams(alpha=ALPHA, uncert=UNCERT, exact_ee=False, slab_format="q6")
         dt6 = time_e2e(h_img.u8, p_q6)
         assert int(out.counters[L.CNT_ACCEPTED]) == acc8, "6-bit transport changed the result"
-        e2e = {"value": world * n * e_steps / dt6, "unit": "reads/s", "h2d_bytes_per_step": h_img.nbytes,
-               "d2h_bytes_per_step": n * 13 + L.N_COUNTERS * 8, "steps": e_steps, "ms_per_step": dt6 / e_steps * 1e3,
-               "api": "moira_filter_batch (pinned host slab in the 6-bit transport format -> chunked H2D / device expand / "
-                      "kernels / D2H on two streams; uniform rows: offsets/lengths stay on the host)",
-               "q8": e2e_q8}
+        dt6p = time_e2e(h_img.u8, p_q6, before=lambda: moira_b200.pack_q6(h_slab.u8, out=h_img.u8))
+        e2e = {"value": world * n * e_steps / dt8, "unit": "reads/s", "h2d_bytes_per_step": n * STRIDE, "d2h_bytes_per_step": d2h,
+               "steps": e_steps, "ms_per_step": dt8 / e_steps * 1e3,
+               "api": "moira_filter_batch: pinned host slab, one byte per base -> chunked H2D / kernels / D2H on two streams",
+               "h2d_gb_per_s_per_gpu": n * STRIDE * e_steps / dt8 / 1e9,
+               "frac_of_link": (n * STRIDE * e_steps / dt8 / 1e9) / link["h2d_gb_per_s_per_gpu"],
+               "link_probe": link,
+               "q6_prepacked": {"value": world * n * e_steps / dt6, "unit": "reads/s", "h2d_bytes_per_step": h_img.nbytes,
+                                "ms_per_step": dt6 / e_steps * 1e3, "frac_of_link": (h_img.nbytes * e_steps / dt6 / 1e9) / link["h2d_gb_per_s_per_gpu"]},
+               "q6_pack_in_loop": {"value": world * n * e_steps / dt6p, "unit": "reads/s", "ms_per_step": dt6p / e_steps * 1e3,
+                                   "note": "moira_pack_q6 of the 2.56 GB slab (all host threads of the rank) inside every timed step"}}
+        h_img.free()
 
-    # ---- other --error_calc modes on the same resident slab (kernel-only, decision mode) --------------
+    # ==== other --error_calc modes on the same resident slab (kernel-only, decision mode) =====================
     modes = {}
     for calc in ("poisson", "expected_error"):
-        pm = FilterParams(error_calc=calc, alpha=ALPHA, uncert=UNCERT, exact_ee=False)
-        for _ in range(2):
-            step(pm)
-        ms_m, _, _, _ = timed(pm, 5)
+        pm = c2.params(error_calc=calc, exact_ee=False)
+        ms_m, _, _, _, _ = c2.timed(pm, 5, warm=2)
         modes[calc] = {"value": world * n * 5 / (ms_m * 1e-3), "unit": "reads/s"}
 
-    # ---- end to end INCLUDING host parsing: FASTQ text -> C parser (all host threads) -> filter ------
+    # ==== end to end INCLUDING parsing: FASTQ text -> device parser -> filter =================================
     e2e_parse = None
+    text_for_cli = None
     if not args.no_e2e:
         m = min(n, 2_000_000)
-        rows = slab[:m].cpu().numpy()
+        rows = c2.slab[:m].cpu().numpy()
         rec = np.empty((m, 10 + 1 + READ_LEN + 3 + READ_LEN + 1), dtype=np.uint8)
         ids = np.char.zfill(np.arange(m).astype("U8"), 8)
         rec[:, 0] = ord("@"); rec[:, 1] = ord("r")
@@ -389,33 +525,101 @@ def run_ours(args):
         h_out2 = moira_b200.PinnedBuffer(m * 13 + 4096)
         out2 = moira_b200.FilterResult(h_out2.view(np.float64, m), h_out2.view(np.int32, m, m * 8),
                                        h_out2.view(np.uint8, m, m * 12), np.zeros(L.N_COUNTERS, np.uint64))
-
         h_text = moira_b200.PinnedBuffer(len(text))
         h_text.u8[:] = np.frombuffer(text, dtype=np.uint8)
 
         def parse_rate(src):
-            r0 = ctx.filter_fastq(src, p_dec, 33, out2)[0]
+            r0 = ctx.filter_fastq(src, p_e2e, 33, out2)[0]
             barrier()
             t0 = time.perf_counter()
             for _ in range(3):
-                r0 = ctx.filter_fastq(src, p_dec, 33, out2)[0]
+                r0 = ctx.filter_fastq(src, p_e2e, 33, out2)[0]
             barrier()
-            return (time.perf_counter() - t0) / 3, r0
+            return max_over_ranks(time.perf_counter() - t0) / 3, r0
 
         dt, r0 = parse_rate(h_text.u8)
         dt_pageable, _ = parse_rate(text)
         e2e_parse = {"value": world * m / dt, "unit": "reads/s", "reads": m, "fastq_bytes": len(text),
-                     "text_gb_per_s": len(text) / dt / 1e9, "host_threads": os.cpu_count(),
+                     "text_gb_per_s_per_gpu": len(text) / dt / 1e9, "frac_of_link": (len(text) / dt / 1e9) / link["h2d_gb_per_s_per_gpu"],
                      "accepted": int(r0.counters[L.CNT_ACCEPTED]),
-                     "pageable_text": {"value": world * m / dt_pageable, "unit": "reads/s",
-                                       "note": "the same with the text in ordinary (pageable) host memory: staged through pinned buffers by the host threads"},
-                     "api": "moira_filter_fastq: FASTQ text in pinned host memory -> H2D as it is (chunk cuts guessed from the local structure of the text, "
-                            "verified by the device's line count) -> newline index, record table, slab conversion and the filter on the device -> "
-                            "D2H of ee / Ns / flags / lengths; three 64 MB chunks in flight"}
-        del text
+                     "pageable_text": {"value": world * m / dt_pageable, "unit": "reads/s"},
+                     "api": "moira_filter_fastq: FASTQ text in pinned host memory -> H2D as it is -> newline index, record table, slab "
+                            "conversion (+ row marks) and the filter on the device -> D2H of ee / Ns / flags / lengths; three 64 MB chunks in flight"}
+        text_for_cli = text
         h_text.free()
 
-    # ---- the step before the filter when reads come in pairs: contig construction, N = 1 only ----
+    # ==== the other BASELINE.json configs + the real-profile workload, device-resident =========================
+    configs = {}
+    c2_cfg = {"workload": WORKLOAD, "reads_per_gpu": n, "decision": {"value": value, "unit": "reads/s", "frac": roofline["frac"]},
+              "exact_ee": {"value": value_exact, "unit": "reads/s", "frac": roofline_exact["frac"]},
+              "accepted_fraction": accepted_frac, "escalated_fraction": escalated_frac, "parity": parity}
+    configs["C2"] = c2_cfg
+    log("C2", {"value": value, "roofline": roofline, "roofline_exact": roofline_exact, "parity": parity, "e2e": e2e, "modes": modes,
+               "e2e_parse": e2e_parse})
+    del c2
+    torch.cuda.empty_cache()
+
+    def run_config(name, profile, n_c, seed, what, steps=3, parity_k=4000, collapse=False, modes_c=()):
+        w = Work(profile, n_c, seed, with_sequences=collapse)
+        pd, px = w.params(exact_ee=False), w.params(exact_ee=True)
+        res = {"workload": what, "reads_per_gpu": n_c, "mean_length": float(w.fixed or w.lengths.double().mean().item()),
+               "row_stride": w.stride, "first_pass_K": synth.decision_k(w.max_len, UNCERT)}
+        ms_d, _, _, _, cd = w.timed(pd, steps, warm=2)
+        alg_d = w.algorithmic_flop_decision()
+        res["decision"] = dict(fp64_view(cd, steps, ms_d, n_c), value=world * n_c * steps / (ms_d * 1e-3), ms_per_step=ms_d / steps,
+                               algorithmic_flop_per_read=alg_d / n_c)
+        res["accepted_fraction"] = float(cd[L.CNT_ACCEPTED]) / max(1, int(cd[L.CNT_READS]))
+        res["escalated_fraction"] = float(cd[L.CNT_ESCALATED]) / max(1, int(cd[L.CNT_READS]))
+        ms_x2, _, _, _, cx = w.timed(px, steps, warm=1)
+        alg_x2 = w.algorithmic_flop_exact()
+        res["exact_ee"] = dict(fp64_view(cx, steps, ms_x2, n_c), value=world * n_c * steps / (ms_x2 * 1e-3), ms_per_step=ms_x2 / steps,
+                               algorithmic_flop_per_read=alg_x2 / n_c, algorithmic_frac=alg_x2 / (ms_x2 * 1e-3 / steps) / peak_ops)
+        for calc in modes_c:
+            pm = w.params(error_calc=calc, exact_ee=False)
+            ms_m2, _, _, _, cm = w.timed(pm, steps, warm=1)
+            res[calc] = {"value": world * n_c * steps / (ms_m2 * 1e-3), "unit": "reads/s", "ms_per_step": ms_m2 / steps,
+                         "accepted_fraction": float(cm[L.CNT_ACCEPTED]) / max(1, int(cm[L.CNT_READS])),
+                         "hbm_frac": (n_c * (w.stride + 16) / (ms_m2 * 1e-3 / steps) / 1e9) / hbm_peak}
+            if calc == "poisson":
+                res[calc]["parity"] = w.parity(min(parity_k, 1000), w.params(error_calc="poisson", exact_ee=True), None, calc="poisson")
+        res["parity"] = w.parity(parity_k, px, pd)
+        if collapse:
+            res["collapse"] = run_collapse(w, px)
+        configs[name] = res
+        log(name, res)
+        del w
+        torch.cuda.empty_cache()
+
+    def run_collapse(w, px):
+        """C4: exact ee for every read + dereplication (moira.py:459-475, 491-504)."""
+        return collapse_bench(ctx, w, px, world, barrier, max_over_ranks)
+
+    if not args.no_configs:
+        big = not args.small_configs
+        run_config("real_profile", "real", n, SEED + 7 + 1000 * rank,
+                   "253-bp rows bootstrapped from the reference's real contig fixture (test_results/paired.qc.*, +-1 jitter): SURVEY 8d's preferred generator",
+                   steps=max(3, args.steps // 4), parity_k=20000)
+        run_config("C3", "v3v4", 25_000_000 if big else 2_000_000, SEED + 2 + 1000 * rank,
+                   "C3: synthetic ~450-bp V3-V4 contigs (ragged 420..480 bp, lengths known to the host), %s reads per GPU" % ("25M" if big else "2M"),
+                   steps=3, parity_k=4000)
+        run_config("C4", "ccs", (5_000_000 if big else 500_000) // world, SEED + 3 + 1000 * rank,
+                   "C4: 5M synthetic 1500-bp CCS-like reads in total (sharded over the GPUs), exact ee for every read + collapse",
+                   steps=2, parity_k=20000 if big else 2000, collapse=True)
+        run_config("C5", "mixed", 10_000_000 if big else 1_000_000, SEED + 4 + 1000 * rank,
+                   "C5: mixed lengths 100..600 bp, V3-V4 shape; poisson_binomial vs poisson vs expected_error",
+                   steps=3, parity_k=4000, modes_c=("poisson", "expected_error"))
+        pb_acc, po_acc, ee_acc = (configs["C5"]["accepted_fraction"], configs["C5"]["poisson"]["accepted_fraction"],
+                                  configs["C5"]["expected_error"]["accepted_fraction"])
+        configs["C5"]["cross_mode_accept_delta"] = {"poisson_minus_pb": po_acc - pb_acc, "expected_error_minus_pb": ee_acc - pb_acc}
+
+    # ==== the CLI a user runs: FASTQ file -> output files, wall clock (N GPUs in ONE process, rank 0 drives) ======
+    e2e_cli = None
+    if not args.no_e2e and not args.no_cli and text_for_cli is not None:
+        e2e_cli = cli_bench(text_for_cli, world, rank, args)
+    text_for_cli = None
+    barrier()
+
+    # ==== the step before the filter when reads come in pairs: contig construction (SURVEY 8f #4), N = 1 only ====
     contigs = None
     if world == 1 and not args.no_e2e:
         from tools.bench_contigs import make_pairs
@@ -434,36 +638,34 @@ def run_ours(args):
         pf = (_pin(pf[0]), _pin(pf[1]), pf[2], pf[3])
         pr_ = (_pin(pr_[0]), _pin(pr_[1]), pr_[2], pr_[3])
         pout = PairResult.allocate(np_pairs, (2 * rl + 15) // 16 * 16, True, pinned=True)
-        ctx.filter_pairs(*pf, *pr_, ContigParams(), p_dec, out=pout)
+        p_pairs = FilterParams(alpha=ALPHA, uncert=UNCERT, exact_ee=False)
+        ctx.filter_pairs(*pf, *pr_, ContigParams(), p_pairs, out=pout)
         ctx.set_timing(True)
         t0 = time.perf_counter()
         for _ in range(3):
-            ctx.filter_pairs(*pf, *pr_, ContigParams(), p_dec, out=pout)
+            ctx.filter_pairs(*pf, *pr_, ContigParams(), p_pairs, out=pout)
         dtp = (time.perf_counter() - t0) / 3
         cms, claunches = ctx.last_contig_ms()
         ctx.set_timing(False)
         contigs = {"kernel": {"value": np_pairs / (cms / 3 * 1e-3), "unit": "pairs/s", "cells_per_s": np_pairs * rl * rl / (cms / 3 * 1e-3)},
                    "e2e": {"value": np_pairs / dtp, "unit": "pairs/s"},
-                   "workload": "%d synthetic 2 x %d bp MiSeq V4 pairs -> contigs -> filter (moira_filter_pairs); details: tools/bench_contigs.py, profiles/r01_contigs.json" % (np_pairs, rl),
+                   "workload": "%d synthetic 2 x %d bp MiSeq V4 pairs -> contigs -> filter (moira_filter_pairs); details: tools/bench_contigs.py" % (np_pairs, rl),
                    "contig_kernel_launches_per_step": claunches / 3, "bad_pairs": int(np.count_nonzero(pout.status))}
         del pf, pr_, pout, keep
 
-    # ---- CPU baseline: the reference's own C core on this box's host cores (rank 0, N = 1) ------------
+    # ==== CPU baseline: the reference's own C core on this box's host cores (rank 0, N = 1) ======================
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         probe_n = 20000
-        rows = slab[:2_000_000].cpu().numpy().reshape(-1)
-        offs = np.arange(2_000_000, dtype=np.uint64) * STRIDE
-        lns = np.full(2_000_000, READ_LEN, dtype=np.uint32)
+        rows, offs, lns = synth.generate("v4", 2_000_000, SEED + 1)
         rate, _, kind, threads = _time_reference(rows, offs[:probe_n], lns[:probe_n], cores)
         s_n = int(min(2_000_000, max(probe_n, rate * 12.0)))      # ~12 s of CPU work
         rate, dt, kind, threads = _time_reference(rows, offs[:s_n], lns[:s_n], cores)
         cpu = {"value": rate, "unit": "reads/s", "cores": threads, "kind": kind,
-               "sample": "first %d reads of this run's GPU workload, %.1f s, all host threads, C loop over the reference test()" % (s_n, dt)}
+               "sample": "%d reads of the C2 workload (host generator, seed %d), %.1f s, all host threads, C loop over the reference test()" % (s_n, SEED + 1, dt)}
         # the same core as moira itself calls it (moira.py:817): one Python call per read, list of ints, 1 core
         try:
-            from oracle import py_oracle as po
             if po.have_ref():
                 ref = po.ref_module()
                 k = 20000
@@ -497,15 +699,16 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reads_per_gpu": n, "read_len": READ_LEN, "row_stride": STRIDE,
-                       "error_calc": "poisson_binomial", "mode": "decision (exact ee for accepted reads, lower bound for certain rejects)",
-                       "first_pass": "cascade = 0 (library default): pilot launch decides per batch between the two-entry sweep with Newton-bound rejects and the single K=4 sweep",
-                       "l2": "inputs (2.56 GB/GPU) larger than L2; no flush", "accepted_fraction": accepted_frac,
-                       "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU, NCCL all-reduce of 80 counters per step",
-                       "rank_cpu_affinity": numa_cpus},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "parity": parity, "modes": modes, "e2e_parse": e2e_parse, "contigs": contigs,
-            "exact_ee": {"value": value_exact, "unit": "reads/s", "note": "exact statistic for every read (escalation ladder), device-resident"},
+            "config": shared_config(n),
+            "run": {"mode": "decision (exact ee for accepted reads, lower bound for certain rejects)",
+                    "first_pass": "cascade = 0 (library default): a pilot launch decides per batch between the two-entry sweep with Newton-bound rejects and the single K=4 sweep",
+                    "row_marks": "given: Ns / has-N per row as the library's slab producers leave them (moira_count_marks_device here); roofline.slab_only_value is the pass that counts N/n in the sweep",
+                    "l2": "inputs (2.56 GB/GPU) larger than L2; no flush", "accepted_fraction": accepted_frac,
+                    "parallelism": "reads sharded by contiguous chunk, 1 rank per GPU; one all-reduce of 80 counters (moira_reduce_counters_device, NCCL) behind the last step",
+                    "rank_cpu_affinity": numa_cpus},
+            "roofline": roofline, "roofline_exact": roofline_exact, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(), "parity": parity, "configs": configs, "modes": modes, "e2e_parse": e2e_parse, "e2e_cli": e2e_cli,
+            "contigs": contigs, "exact_ee": {"value": value_exact, "unit": "reads/s"},
         }
         print(json.dumps(line), file=_OUT, flush=True)
     ctx.close()
@@ -519,9 +722,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (C2)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip C3 / C4 / C5 / real_profile")
+    ap.add_argument("--small-configs", action="store_true", help="C3 / C4 / C5 at a tenth of their size (development)")
+    ap.add_argument("--no-cli", action="store_true")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
     # NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the run and the line goes to the real one.

@@ -120,6 +120,10 @@ typedef struct moira_params {
     int32_t  slab_format; /* MOIRA_SLAB_*: format of the HOST slab given to moira_filter_batch / moira_submit */
     int32_t  cascade;     /* first pass of a decision that needs 3..8 PMF entries: 0 = two-entry sweep first when a pilot launch
                              says it pays (default), 1 = always, 2 = never (one sweep with all the entries) */
+    uint32_t max_length;  /* moira_filter_device with d_lengths only (host entry points look at the lengths themselves): longest and */
+    uint32_t min_length;  /* shortest read of the batch when the caller knows them, 0 = unknown.  max_length sizes the first
+                             pass (a decision needs floor(max_length * uncert) + 2 PMF entries); without it the pass starts at
+                             4 entries and the escalation ladder settles the rest */
     double   alpha;       /* --alpha */
     double   thr;         /* --uncert or --maxerrors value */
 } moira_params;

@@ -2,6 +2,7 @@
 hot path, behind the reference's own interfaces.  See DESIGN.md and include/moira_b200.h."""
 from .api import (CollapseResult, collapse, ContigParams, Context, FilterParams, FilterResult, MoiraError, PairResult,  # noqa: F401
                   PinnedBuffer, build_lut,
-                  pack_arrays, pack_q6, pack_reads, pack_sequences, parse_fasta_qual, parse_fastq)
+                  comm_init_all, comm_unique_id, pack_arrays, pack_q6, pack_reads, pack_sequences, parse_fasta_qual, parse_fastq,
+                  reduce_counters_all)
 
 __version__ = "0.1.0"

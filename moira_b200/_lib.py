@@ -52,6 +52,7 @@ class Params(ctypes.Structure):
         ("round_flag", ctypes.c_int32), ("truncate", ctypes.c_uint32), ("exact_ee", ctypes.c_int32),
         ("ee_output", ctypes.c_int32), ("length_sort", ctypes.c_int32),
         ("slab_format", ctypes.c_int32), ("cascade", ctypes.c_int32),
+        ("max_length", ctypes.c_uint32), ("min_length", ctypes.c_uint32),
         ("alpha", ctypes.c_double), ("thr", ctypes.c_double),
     ]
 

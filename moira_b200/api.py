@@ -31,6 +31,8 @@ class FilterParams:
     slab_format: str = "q8"                # host slab format: 'q8' (one byte per base) or 'q6' (pack_q6 transport image)
     length_sort: int = 0                   # ragged batches: 0 = bucket by length on the device when it pays, 2 = never
     cascade: int = 0                       # decisions needing 3..8 PMF entries: 0 = two-entry sweep first when the pilot says it pays, 1 = always, 2 = never
+    max_length: int = 0                    # filter_device with device lengths: longest / shortest read if known (sizes the first pass)
+    min_length: int = 0
 
     def to_c(self) -> L.Params:
         if self.error_calc not in _MODES:
@@ -50,6 +52,7 @@ class FilterParams:
         p.ee_output = L.EE_FINAL if self.ee_output == "final" else L.EE_RAW
         p.length_sort = int(self.length_sort)
         p.cascade = int(self.cascade)
+        p.max_length, p.min_length = int(self.max_length), int(self.min_length)
         p.slab_format = L.SLAB_Q6 if self.slab_format == "q6" else L.SLAB_Q8
         p.alpha = float(self.alpha)
         return p

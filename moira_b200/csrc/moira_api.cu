@@ -420,7 +420,8 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
         // (almost) one length and every tile runs with the K its own cutoff needs.
         // auto: only when the caller's lengths are known to spread by more than a quarter (host path); the
         // device-pointer API sorts only on request (length_sort = 1)
-        const bool lsort = d_lengths && c->length_sort && n >= 32768 && p->length_sort != 2 &&
+        // (reads beyond the last length bucket would share its first-pass K: such batches are not sorted)
+        const bool lsort = d_lengths && c->length_sort && n >= 32768 && p->length_sort != 2 && max_len <= 16u * (LEN_BUCKETS - 1) &&
                            (p->length_sort == 1 || (max_len && min_len * 4 < max_len * 3));
         if (lsort) {
             cfg.tmap = nullptr;   // tiles follow the sorted permutation, not the slab order
@@ -684,8 +685,8 @@ int moira_filter_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_o
     int rc = check_params(params);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    return run_filter_full(c, c->ws[2], d_slab, d_offsets, d_lengths, stride, fixed_length, n_reads, params, 0, 0, d_ee,
-                           d_ns, d_flags, d_counters, (cudaStream_t)stream, d_row_marks);
+    return run_filter_full(c, c->ws[2], d_slab, d_offsets, d_lengths, stride, fixed_length, n_reads, params, params->max_length,
+                           params->min_length, d_ee, d_ns, d_flags, d_counters, (cudaStream_t)stream, d_row_marks);
 }
 
 int moira_count_marks_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_offsets, const uint32_t *d_lengths,

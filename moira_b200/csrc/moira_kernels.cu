@@ -1081,6 +1081,7 @@ __global__ void __launch_bounds__(1024) len_scan_kernel(const FilterArgs a, cons
                 const double cutoff = a.thr_kind == MOIRA_THR_MAXERRORS ? a.thr : __dmul_rn((double)(b * 16), a.thr);
                 const double kd = cutoff < 0.0 ? 2.0 : floor(cutoff) + 2.0;
                 while (g < N_FIRST_K - 1 && (double)first_pass_k(g) < kd) g++;
+                if (b == LEN_BUCKETS - 1) g = N_FIRST_K - 1;   // the catch-all bucket (lengths unknown to the host): the largest K
             }
             atomicMin(&s_gs[g], run);
             atomicAdd(&s_gc[g], v[i]);

@@ -6,6 +6,7 @@ Profiles (calibrated in SURVEY.md 8d against the reference's fixtures under moir
   v3v4    ~450-bp (420..480) contigs, quality dips in the middle of the contig
   ccs     1500-bp CCS-like full-length 16S, uint8-safe Q <= 93
   mixed   lengths uniform in 100..600 with the v3v4 shape
+  real    253-bp rows bootstrapped from the reference's real contig fixture with +-1 jitter (8d's preferred generator)
 
 `generate(profile, n, seed)` is the numpy (host) generator used where the CPU oracle has to see the
 same bytes; `generate_v4_device` builds the same distribution with torch on the GPU (different
@@ -93,6 +94,118 @@ def generate(profile: str, n: int, seed: int):
         q = np.clip(q - shift * (rng.random((n, L)) < 0.5), 2, 93)
         q = _apply_n(rng, q)
         return _rows_to_slab(q, np.full(n, L, dtype=np.uint32))
+    if profile == "real":
+        # SURVEY.md 8d's preferred generator: bootstrap whole quality rows of the reference's real 253-bp contig
+        # fixture (test_results/paired.qc.*, staged in tests/golden/contigs.json.gz) with +-1 jitter
+        rows_q, rows_n = real_rows()
+        idx = rng.integers(0, rows_q.shape[0], n)
+        q = np.clip(rows_q[idx].astype(np.int64) + rng.integers(-1, 2, (n, rows_q.shape[1])), 1, 41)
+        q = np.where(rows_n[idx], N_MARK, q)
+        return _rows_to_slab(q, np.full(n, rows_q.shape[1], dtype=np.uint32))
+    raise ValueError("unknown profile %r" % profile)
+
+
+_REAL = None
+
+
+def real_rows():
+    """(qualities uint8 [328, 253], is-N bool [328, 253]) of the length-253 contigs of the reference's paired fixture."""
+    global _REAL
+    if _REAL is None:
+        import gzip
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "contigs.json.gz")
+        with gzip.open(path) as fh:
+            recs = [c for c in json.load(fh) if len(c["seq"]) == V4_LEN]
+        q = np.array([c["quals"] for c in recs], dtype=np.uint8)
+        isn = np.array([[ch in "Nn" for ch in c["seq"]] for c in recs], dtype=bool)
+        _REAL = (q, isn)
+    return _REAL
+
+
+# (stride, fixed length or None) of the device generators' slabs
+DEVICE_LAYOUT = {"v4": (256, 253), "real": (256, 253), "v3v4": (480, None), "mixed": (608, None), "ccs": (1504, 1500)}
+
+
+def generate_device(profile: str, n: int, seed: int, device, chunk: int = 1 << 19, with_sequences: bool = False):
+    """torch (device-side) generators of the profiles above (same distributions, different random stream).
+    Returns (slab uint8 [n, stride], lengths int32 [n] or None when every read has DEVICE_LAYOUT[profile][1] bases,
+    sequences uint8 [n, stride] or None).  Sequences (ccs, for --collapse): a pool of 250 000 distinct strings with
+    Zipf(1.2) abundance, 'N' where the slab has the marker."""
+    import torch
+
+    stride, fixed = DEVICE_LAYOUT[profile]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    if profile == "v4":
+        return generate_v4_device(n, seed, device), None, None
+    out = torch.full((n, stride), PAD, dtype=torch.uint8, device=device)
+    lengths = None
+    seqs = None
+    if profile == "real":
+        rq, rn = real_rows()
+        rq_t = torch.tensor(rq, device=device, dtype=torch.int16)
+        rn_t = torch.tensor(rn, device=device)
+        for s0 in range(0, n, chunk):
+            m = min(chunk, n - s0)
+            idx = torch.randint(0, rq.shape[0], (m,), generator=g, device=device)
+            jit = torch.randint(-1, 2, (m, V4_LEN), generator=g, device=device, dtype=torch.int16)
+            q = (rq_t[idx] + jit).clamp_(1, 41).to(torch.uint8)
+            q = torch.where(rn_t[idx], torch.full_like(q, N_MARK), q)
+            out[s0:s0 + m, :V4_LEN] = q
+        return out, None, None
+    if profile in ("v3v4", "mixed"):
+        lengths = torch.empty(n, dtype=torch.int32, device=device)
+        lmax = 480 if profile == "v3v4" else 600
+        pos = torch.arange(lmax, device=device, dtype=torch.float32)[None, :]
+        for s0 in range(0, n, chunk):
+            m = min(chunk, n - s0)
+            if profile == "v3v4":
+                ln = torch.randn(m, generator=g, device=device).mul_(8).add_(450).round_().clamp_(420, 480)
+            else:
+                ln = torch.randint(100, 601, (m,), generator=g, device=device).to(torch.float32)
+            lengths[s0:s0 + m] = ln.to(torch.int32)
+            L = ln[:, None]
+            mu = 38 - 12 * (1 - (2 * pos / L - 1).abs()) ** 2
+            d = -(torch.rand((m, 1), generator=g, device=device).clamp_(min=1e-12).log()
+                  + torch.rand((m, 1), generator=g, device=device).clamp_(min=1e-12).log())            # Gamma(2, 1)
+            e = -torch.rand((m, lmax), generator=g, device=device).clamp_(min=1e-12).log()          # Exp(1)
+            q = (mu - e * d).round_().clamp_(2, 40).to(torch.uint8)
+            isn = (q == 2) & (torch.rand((m, lmax), generator=g, device=device) < 0.5)
+            q = torch.where(isn, torch.full_like(q, N_MARK), q)
+            q = torch.where(pos < L, q, torch.full_like(q, PAD))
+            out[s0:s0 + m, :lmax] = q
+            del mu, e, q, isn
+        return out, lengths, None
+    if profile == "ccs":
+        L = 1500
+        cdf = torch.tensor(np.cumsum(_norm(_CCS_P)), device=device, dtype=torch.float32)
+        qv = torch.tensor(_CCS_Q, device=device, dtype=torch.int16)
+        shifts = torch.tensor([0, 0, 0, 10, 25], device=device, dtype=torch.int16)
+        pool = pool_cdf = None
+        if with_sequences:
+            n_pool = 250_000
+            pool = torch.tensor([65, 67, 71, 84], device=device, dtype=torch.uint8)[
+                torch.randint(0, 4, (n_pool, L), generator=g, device=device)]
+            w = torch.arange(1, n_pool + 1, device=device, dtype=torch.float64).pow_(-1.2)
+            pool_cdf = (w.cumsum(0) / w.sum()).to(torch.float32)
+            seqs = torch.zeros((n, stride), dtype=torch.uint8, device=device)
+        sub = max(1, chunk // 4)
+        for s0 in range(0, n, sub):
+            m = min(sub, n - s0)
+            q = qv[torch.searchsorted(cdf, torch.rand((m, L), generator=g, device=device)).clamp_(max=len(_CCS_Q) - 1)]
+            sh = shifts[torch.randint(0, 5, (m, 1), generator=g, device=device)]
+            q = (q - sh * (torch.rand((m, L), generator=g, device=device) < 0.5)).clamp_(2, 93).to(torch.uint8)
+            isn = (q == 2) & (torch.rand((m, L), generator=g, device=device) < 0.5)
+            q = torch.where(isn, torch.full_like(q, N_MARK), q)
+            out[s0:s0 + m, :L] = q
+            if with_sequences:
+                pid = torch.searchsorted(pool_cdf, torch.rand(m, generator=g, device=device)).clamp_(max=pool.shape[0] - 1)
+                sq = pool[pid]
+                seqs[s0:s0 + m, :L] = torch.where(isn, torch.full_like(sq, 78), sq)
+            del q, isn
+        return out, None, seqs
     raise ValueError("unknown profile %r" % profile)
 
 

@@ -31,7 +31,7 @@ def test_header_constants_match_binding():
     for k, v in consts.items():
         if hasattr(L, k):
             assert getattr(L, k) == int(v, 0), k
-    assert ctypes.sizeof(L.Params) == 56
+    assert ctypes.sizeof(L.Params) == 64
     # the ctypes mirror of moira_params has the header's fields, in the header's order
     body = re.search(r"typedef struct moira_params \{(.*?)\} moira_params;", hdr, re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)

@@ -1,0 +1,219 @@
+"""GPU (-m gpu), round 2: row marks from the slab's producers, the N-context path (shards of one slab on several
+contexts == one context), the counters' all-reduce inside the library, the executed-FP64 counter, device-resident
+ragged batches with host-known lengths, and a 20 000-read CCS (1 500 bp) parity sample."""
+import numpy as np
+import pytest
+
+import moira_b200
+from moira_b200 import FilterParams, synth
+from moira_b200 import _lib as L
+from oracle import py_oracle as po
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _dev_arrays(n):
+    dev = torch.device("cuda", 0)
+    return (torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
+            torch.empty(n, dtype=torch.uint8, device=dev), torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev))
+
+
+def _marks_numpy(slab, off, ln, truncate=0):
+    out = np.zeros(len(ln), np.uint32)
+    for r, (o, l) in enumerate(zip(off, ln)):
+        eff = min(int(l), truncate) if truncate else int(l)
+        row = slab[int(o):int(o) + eff]
+        out[r] = int((row >= 0xFE).sum()) | ((1 << 31) if (row == 0xFF).any() else 0)
+    return out
+
+
+def _same_but_diagnostics(a, b):
+    keep = np.ones(L.N_COUNTERS, bool)
+    keep[[L.CNT_ESCALATED, L.CNT_FP64_OPS]] = False
+    return np.array_equal(np.asarray(a)[keep], np.asarray(b)[keep])
+
+
+@pytest.mark.parametrize("profile,n,seed,truncate", [("v4", 40000, 11, 0), ("v4", 40000, 12, 200), ("mixed", 40000, 13, 0),
+                                                      ("mixed", 40000, 14, 250), ("v3v4", 40000, 15, 0)])
+def test_row_marks_producer_and_filter(ctx, profile, n, seed, truncate):
+    """moira_count_marks_device == a numpy count; a filter call that is GIVEN the marks writes exactly what the
+    self-counting call writes (every array, every counter) in decision and exact mode."""
+    slab, off, ln = synth.generate(profile, n, seed)
+    slab = slab.copy()
+    rng = np.random.default_rng(seed)
+    pos = rng.integers(0, len(slab), 2000)
+    slab[pos] = np.where(slab[pos] == 0xFD, 0xFD, 0xFE)          # some lower-case n as well
+    stride = int(off[1] - off[0])
+    dev = torch.device("cuda", 0)
+    d_slab = torch.from_numpy(slab).to(dev)
+    uniform = bool((ln == ln[0]).all())
+    d_len = None if uniform else torch.from_numpy(ln.astype(np.int32)).to(dev)
+    marks = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.count_marks_device(d_slab.data_ptr(), None, None if uniform else d_len.data_ptr(), stride, int(ln[0]) if uniform else 0, n,
+                           marks.data_ptr(), truncate, stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(marks.cpu().numpy().view(np.uint32), _marks_numpy(slab, off, ln, truncate))
+    for exact in (False, True):
+        got = []
+        for use in (False, True):
+            ee, ns, fl, cnt = _dev_arrays(n)
+            p = FilterParams(exact_ee=exact, truncate=truncate or None, max_length=int(ln.max()), min_length=int(ln.min()))
+            ctx.filter_device(d_slab.data_ptr(), None, None if uniform else d_len.data_ptr(), stride, int(ln[0]) if uniform else 0, n, p,
+                              ee.data_ptr(), ns.data_ptr(), fl.data_ptr(), cnt.data_ptr(), stream, marks.data_ptr() if use else None)
+            torch.cuda.synchronize()
+            got.append((ee.cpu().numpy(), ns.cpu().numpy(), fl.cpu().numpy(), cnt.cpu().numpy()))
+        assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1]) and np.array_equal(got[0][2], got[1][2])
+        assert _same_but_diagnostics(got[0][3], got[1][3])
+        assert got[1][3][L.CNT_FP64_OPS] > 0
+    # ... and the exact results are the oracle's
+    eff = np.minimum(ln, truncate) if truncate else ln
+    ee_o, ns_o = po.pb_batch(slab, off, eff.astype(np.uint32), 0.005)
+    assert np.array_equal(got[1][0], ee_o) and np.array_equal(got[1][1], ns_o)
+
+
+def test_q6_transport_leaves_row_marks(ctx):
+    """The 6-bit expansion kernel produces the row marks of uniform rows; results equal the byte-slab path's."""
+    slab, off, ln = synth.generate("v4", 60000, 21)
+    img = moira_b200.pack_q6(slab)
+    for exact in (False, True):
+        for trunc in (None, 100):
+            a = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact, truncate=trunc))
+            b = ctx.filter_batch(img, off, ln, FilterParams(exact_ee=exact, truncate=trunc, slab_format="q6"))
+            assert np.array_equal(a.ee, b.ee) and np.array_equal(a.ns, b.ns) and np.array_equal(a.flags, b.flags)
+            assert _same_but_diagnostics(a.counters, b.counters)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    b = ctx.filter_batch(img, off, ln, FilterParams(exact_ee=True, slab_format="q6"))
+    assert np.array_equal(b.ee, ee_o) and np.array_equal(b.ns, ns_o)
+
+
+def test_shards_on_several_contexts_equal_one_context(ctx):
+    """The N-rank path on the GPU: contiguous shards of one slab on separate contexts (own streams, workspaces, queues),
+    concatenated in rank order, are the single-context result; the shard counters add up to its counters."""
+    from moira_b200.shard import shard_slab
+    slab, off, ln = synth.generate("mixed", 90000, 31)
+    for exact in (False, True):
+        p = FilterParams(exact_ee=exact)
+        whole = ctx.filter_batch(slab, off, ln, p)
+        for world in (2, 3):
+            ctxs = [moira_b200.Context(0) for _ in range(world)]
+            try:
+                parts, tickets = [], []
+                for r, c in enumerate(ctxs):
+                    b, e, byte_b, byte_e = shard_slab(off, ln, r, world)
+                    sub_off = (off[b:e] - np.uint64(byte_b)).astype(np.uint64)
+                    out = moira_b200.FilterResult(np.empty(e - b), np.empty(e - b, np.int32), np.empty(e - b, np.uint8),
+                                                  np.zeros(L.N_COUNTERS, np.uint64))
+                    sub_slab = np.ascontiguousarray(slab[byte_b:byte_e])
+                    sub_len = np.ascontiguousarray(ln[b:e])
+                    tickets.append((c, c.submit(sub_slab, sub_off, sub_len, p, out), (sub_slab, sub_off, sub_len)))   # all in flight at once
+                    parts.append(out)
+                for c, t, _keep in tickets:
+                    c.wait(t)
+                ee, fl = np.concatenate([q.ee for q in parts]), np.concatenate([q.flags for q in parts])
+                total = np.sum([q.counters for q in parts], axis=0)
+                assert np.array_equal(np.concatenate([q.ns for q in parts]), whole.ns)
+                if exact:
+                    assert np.array_equal(ee, whole.ee) and np.array_equal(fl, whole.flags)
+                    assert _same_but_diagnostics(total, whole.counters)
+                else:
+                    # decision mode: WHICH certain rejects carry a lower bound instead of the exact statistic depends on the
+                    # first-pass K of the batch a read travels in; decisions, reasons and every exact value are the same
+                    canon = L.FLAG_ACCEPT | L.FLAG_REASON_MASK | L.FLAG_HAS_N
+                    assert np.array_equal(fl & canon, whole.flags & canon)
+                    both = ((fl | whole.flags) & L.FLAG_LOWER_BOUND) == 0
+                    assert np.array_equal(ee[both], whole.ee[both]) and both.mean() > 0.5
+                    assert np.array_equal(total[:L.CNT_NEAR_CUTOFF], whole.counters[:L.CNT_NEAR_CUTOFF])
+                assert int(total[L.CNT_ACCEPTED]) == int(sum((q.flags & 1).sum() for q in parts))
+            finally:
+                for c in ctxs:
+                    c.close()
+
+
+def test_counters_allreduce_inside_the_library(ctx):
+    """moira_comm_* + moira_reduce_counters*: a communicator of one rank on this box's GPU 0 (sum == identity), host and
+    device variants; with two GPUs, two contexts in one process (moira_comm_init_all / moira_reduce_counters_all)."""
+    c = moira_b200.Context(0)
+    try:
+        assert c.comm_info() == (0, 1)
+        with pytest.raises(moira_b200.MoiraError):
+            c.reduce_counters(np.zeros(L.N_COUNTERS, np.uint64))               # no communicator yet
+        c.comm_init(moira_b200.comm_unique_id(), 0, 1)
+        assert c.comm_info() == (0, 1)
+        v = np.arange(L.N_COUNTERS, dtype=np.uint64) * np.uint64(3) + np.uint64(1 << 40)
+        assert np.array_equal(c.reduce_counters(v.copy()), v)
+        d = torch.from_numpy(v.astype(np.int64)).to("cuda:0")
+        c.reduce_counters_device(d.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy().astype(np.uint64), v)
+    finally:
+        c.close()
+    if torch.cuda.device_count() >= 2:
+        ctxs = [moira_b200.Context(0), moira_b200.Context(1)]
+        try:
+            moira_b200.comm_init_all(ctxs)
+            assert [x.comm_info() for x in ctxs] == [(0, 2), (1, 2)]
+            slab, off, ln = synth.generate("v4", 50000, 41)
+            half = 25000
+            outs = [ctxs[0].filter_batch(slab[:half * 256], off[:half], ln[:half], FilterParams(exact_ee=False)),
+                    ctxs[1].filter_batch(slab[half * 256:], off[half:] - off[half], ln[half:], FilterParams(exact_ee=False))]
+            want = outs[0].counters + outs[1].counters
+            red = moira_b200.reduce_counters_all(ctxs, [o.counters.copy() for o in outs])
+            assert np.array_equal(red[0], want) and np.array_equal(red[1], want)
+            assert int(want[L.CNT_ACCEPTED]) == int((outs[0].flags & 1).sum() + (outs[1].flags & 1).sum())
+        finally:
+            for x in ctxs:
+                x.close()
+
+
+def test_device_ragged_batch_with_known_lengths(ctx):
+    """moira_filter_device on a fixed-pitch ragged slab (C3's layout): with max_length / min_length the first pass is sized
+    for the decision (no ladder in decision mode); results are the oracle's either way."""
+    slab, off, ln = synth.generate("v3v4", 50000, 51)
+    stride = int(off[1] - off[0])
+    dev = torch.device("cuda", 0)
+    d_slab, d_len = torch.from_numpy(slab).to(dev), torch.from_numpy(ln.astype(np.int32)).to(dev)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    ok_o = (ee_o + ns_o) <= ln * 0.01
+    stream = torch.cuda.current_stream().cuda_stream
+    for known in (True, False):
+        for exact in (False, True):
+            ee, ns, fl, cnt = _dev_arrays(len(ln))
+            p = FilterParams(exact_ee=exact, max_length=int(ln.max()) if known else 0, min_length=int(ln.min()) if known else 0)
+            ctx.filter_device(d_slab.data_ptr(), None, d_len.data_ptr(), stride, 0, len(ln), p, ee.data_ptr(), ns.data_ptr(),
+                              fl.data_ptr(), cnt.data_ptr(), stream)
+            torch.cuda.synchronize()
+            f = fl.cpu().numpy()
+            lb = (f & L.FLAG_LOWER_BOUND) != 0
+            assert np.array_equal((f & 1) != 0, ok_o) and np.array_equal(ns.cpu().numpy(), ns_o)
+            assert np.array_equal(ee.cpu().numpy()[~lb], ee_o[~lb]) and not (exact and lb.any())
+            assert not (f & L.FLAG_NUMERIC).any()
+
+
+def test_ccs_20k_reads(ctx):
+    """C4-shaped reads (1 500 bp, Q up to 93, j* up to several hundred): 20 000 reads, ee / Ns bit-exact, decisions identical."""
+    slab, off, ln = synth.generate("ccs", 20000, 61)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    ok_o = (ee_o + ns_o) <= ln * 0.01
+    res = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=True))
+    assert np.array_equal(res.ee, ee_o) and np.array_equal(res.ns, ns_o) and np.array_equal(res.accept, ok_o)
+    dec = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=False))
+    lb = dec.lower_bound
+    assert np.array_equal(dec.accept, ok_o) and np.array_equal(dec.ee[~lb], ee_o[~lb]) and (dec.ee[lb] <= ee_o[lb]).all()
+
+
+def test_real_profile_generator_host_and_device(ctx):
+    """The bootstrapped real-fixture workload: device generator -> filter == oracle on the same bytes."""
+    dev = torch.device("cuda", 0)
+    slab_t, lens, _ = synth.generate_device("real", 30000, 71, dev)
+    assert lens is None
+    slab = slab_t.cpu().numpy().reshape(-1)
+    off = np.arange(30000, dtype=np.uint64) * np.uint64(256)
+    ln = np.full(30000, 253, np.uint32)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    res = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=True))
+    assert np.array_equal(res.ee, ee_o) and np.array_equal(res.ns, ns_o)
+    dec = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=False))
+    assert np.array_equal(dec.accept, (ee_o + ns_o) <= 2.5300000000000002)
+    assert 0.7 < dec.accept.mean() < 0.95
