@@ -113,13 +113,136 @@ def run_reference(args):
 
 
 def collapse_bench(ctx, w, px, world, barrier, max_over_ranks):
-    """C4's second half (filled in with the device-side dereplication): None until then."""
-    return None
+    """C4's second half: --collapse (moira.py:459-475, 491-504) next to the exact-ee filter.  The sequences are resident in
+    HBM like the slab; moira_collapse_device labels them exactly (hash + byte compare), the host turns labels + ee into
+    the reference's groups (moira_collapse_labels).  Parity: the unmodified-semantics host collapse (moira_collapse: hash +
+    memcmp over the strings) on a bounded sample of THIS rank's reads."""
+    import torch
+    import moira_b200
+    n, stride, L_ = w.n, w.stride, w.fixed
+    dev = w.slab.device
+    stream = torch.cuda.current_stream().cuda_stream
+    labels = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def dedup():
+        ctx.collapse_device(w.seqs.data_ptr(), None, None, stride, L_, n, labels.data_ptr(), 0, stream)
+
+    dedup()
+    barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    reps = 2
+    e0.record()
+    for _ in range(reps):
+        w.run(px)
+    e1.record()
+    for _ in range(reps):
+        dedup()
+    e2.record()
+    barrier()
+    ms_filter, ms_dedup = max_over_ranks(e0.elapsed_time(e1)) / reps, max_over_ranks(e1.elapsed_time(e2)) / reps
+    # host half: D2H of labels + ee, groups / representatives / names order / abundance order
+    t0 = time.perf_counter()
+    lab_h = labels.cpu().numpy().view(np.uint32)
+    ee_h = w.ee.cpu().numpy() + w.ns.cpu().numpy()                    # the value process_data returns (treat_as_errors)
+    col = moira_b200.collapse_labels(lab_h, ee_h)
+    t_host = max_over_ranks(time.perf_counter() - t0)
+    # parity on a bounded sample: device labels of the sample alone -> groups == host hash + memcmp collapse
+    k = min(n, 200_000)
+    sub = w.seqs[:k].contiguous()
+    sub_lab = torch.zeros(k, dtype=torch.int32, device=dev)
+    ctx.collapse_device(sub.data_ptr(), None, None, stride, L_, k, sub_lab.data_ptr(), 0, stream)
+    torch.cuda.synchronize()
+    seq_h = sub.cpu().numpy().reshape(-1)
+    off = np.arange(k, dtype=np.uint64) * np.uint64(stride)
+    t0 = time.perf_counter()
+    want = moira_b200.collapse(seq_h, off, np.full(k, L_, np.uint32), ee_h[:k])
+    t_hostcollapse = time.perf_counter() - t0
+    got = moira_b200.collapse_labels(sub_lab.cpu().numpy().view(np.uint32), ee_h[:k])
+    mism = sum(int(not np.array_equal(getattr(got, f), getattr(want, f))) for f in ("group_of_read", "rep", "size", "member_start", "members", "order"))
+    total_ms = ms_filter + ms_dedup + t_host * 1e3
+    return {"reads_per_gpu": n, "groups": int(col.rep.shape[0]), "largest_group": int(col.size.max()) if n else 0,
+            "filter_exact_ms": ms_filter, "dedup_kernels_ms": ms_dedup, "host_groups_ms": t_host * 1e3,
+            "dedup_kernels_value": world * n / (ms_dedup * 1e-3), "dedup_seq_gb_per_s": n * L_ * 2 / (ms_dedup * 1e-3) / 1e9,
+            "exact_plus_collapse_value": world * n / (total_ms * 1e-3), "filter_only_value": world * n / (ms_filter * 1e-3),
+            "slowdown_vs_filter_only": total_ms / ms_filter, "unit": "reads/s",
+            "host_collapse_sample": {"reads": k, "value": k / t_hostcollapse, "unit": "reads/s",
+                                    "note": "moira_collapse (hash + memcmp on all host threads) over the sample's strings"},
+            "parity": {"sample_reads_per_rank": k, "arrays_differing_from_host_collapse": mism},
+            "note": "device: 128-bit hash + exact byte compare of the HBM-resident sequences -> labels; host: D2H of labels and ee, "
+                    "groups / representatives / names order / abundance order from the labels (no base is read on the host)"}
 
 
-def cli_bench(text, world, rank, args):
-    """The CLI a user runs, wall clock (filled in with the multi-device CLI): None until then."""
-    return None
+def make_cli_fastq(slab_rows, seed):
+    """FASTQ text for the CLI run: the qualities of `slab_rows` (uint8 [m, 256], C2 workload), sequences drawn from 100 000
+    distinct random strings with Zipf(1.2) abundance ('N' where the slab has the marker), so that --collapse has the work
+    it has on an amplicon run."""
+    m = slab_rows.shape[0]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pool = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (100_000, READ_LEN))]
+    wts = np.arange(1, 100_001, dtype=np.float64) ** -1.2
+    cdf = np.cumsum(wts / wts.sum())
+    pid = np.minimum(np.searchsorted(cdf, rng.random(m)), 99_999)
+    rec = np.empty((m, 10 + 1 + READ_LEN + 3 + READ_LEN + 1), dtype=np.uint8)
+    ids = np.char.zfill(np.arange(m).astype("U8"), 8)
+    rec[:, 0] = ord("@"); rec[:, 1] = ord("r")
+    rec[:, 2:10] = np.frombuffer("".join(ids.tolist()).encode(), dtype=np.uint8).reshape(m, 8)
+    q = slab_rows[:, :READ_LEN]
+    isn = q == 0xFF
+    rec[:, 10] = 10
+    rec[:, 11:11 + READ_LEN] = np.where(isn, ord("N"), pool[pid])
+    rec[:, 11 + READ_LEN:14 + READ_LEN] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    rec[:, 14 + READ_LEN:14 + 2 * READ_LEN] = np.where(isn, 2, q) + 33
+    rec[:, -1] = 10
+    return rec
+
+
+def cli_bench(rec, accepted_per_read, world, rank, args):
+    """The program a user runs (python -m moira_b200.cli, in-process), wall clock from the FASTQ FILE to the output FILES,
+    on all N GPUs from one process (--devices): default flags (exact ee, --collapse, fasta + qual + names) and the
+    streaming case (-c False -o fastq).  Rank 0 drives; the other ranks wait."""
+    if rank != 0:
+        return None
+    import io as _io
+    import shutil
+    import tempfile
+    from moira_b200 import cli
+    m = rec.shape[0]
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 6 * rec.nbytes else None
+    tmp = tempfile.mkdtemp(prefix="moira_cli_", dir=base)
+    out = {"reads": m, "fastq_bytes": int(rec.nbytes), "devices": world, "tmpdir": "tmpfs" if base else "disk", "unit": "reads/s"}
+    try:
+        path = os.path.join(tmp, "in.fastq")
+        with open(path, "wb") as fh:
+            fh.write(rec)
+        devs = ",".join(str(i) for i in range(world))
+        for tag, extra in (("collapse_default", []), ("no_collapse_fastq", ["-c", "False", "-o", "fastq"])):
+            log = _io.StringIO()
+            t0 = time.perf_counter()
+            rc = cli.main(cli.parse_arguments(["-ffq", path, "-op", os.path.join(tmp, tag), "--devices", devs] + extra), log)
+            dt = time.perf_counter() - t0
+            files = {f: os.path.getsize(os.path.join(tmp, f)) for f in sorted(os.listdir(tmp)) if f.startswith(tag + ".")}
+            res = {"value": m / dt, "seconds": dt, "rc": rc, "output_bytes": int(sum(files.values())),
+                   "decisions_seconds": float(log.getvalue().split(" s to the decisions")[0].rsplit("(", 1)[1]) if " s to the decisions" in log.getvalue() else None}
+            if tag == "no_collapse_fastq":
+                with open(os.path.join(tmp, tag + ".qc.good.fastq"), "rb") as fh:
+                    good = fh.read().count(b"\n") // 4
+                res["good_records"] = good
+                res["matches_device_decisions"] = bool(good == accepted_per_read)
+            else:
+                with open(os.path.join(tmp, tag + ".qc.good.names"), "rb") as fh:
+                    gn = fh.read()
+                with open(os.path.join(tmp, tag + ".qc.bad.names"), "rb") as fh:
+                    bn = fh.read()
+                res["groups"] = gn.count(b"\n") + bn.count(b"\n")
+                res["names_cover_every_read"] = bool(gn.count(b"r") + bn.count(b"r") - res["groups"] == m)
+            out[tag] = res
+            for f in files:
+                os.remove(os.path.join(tmp, f))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    out["value"] = out["collapse_default"]["value"]
+    out["api"] = "python -m moira_b200.cli -ffq FILE --devices 0..N-1: mmap -> record-aligned shards -> moira_filter_fastq_ex per GPU and host thread -> (device labels -> groups) -> moira_format_records -> files"
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -505,7 +628,7 @@ def run_ours(args):
 
     # ==== end to end INCLUDING parsing: FASTQ text -> device parser -> filter =================================
     e2e_parse = None
-    text_for_cli = None
+    text_for_cli, cli_accepted = None, 0
     if not args.no_e2e:
         m = min(n, 2_000_000)
         rows = c2.slab[:m].cpu().numpy()
@@ -545,8 +668,14 @@ def run_ours(args):
                      "pageable_text": {"value": world * m / dt_pageable, "unit": "reads/s"},
                      "api": "moira_filter_fastq: FASTQ text in pinned host memory -> H2D as it is -> newline index, record table, slab "
                             "conversion (+ row marks) and the filter on the device -> D2H of ee / Ns / flags / lengths; three 64 MB chunks in flight"}
-        text_for_cli = text
         h_text.free()
+        del text
+        if rank == 0 and not args.no_cli:
+            m_cli = min(n, args.cli_reads)
+            c2.run(p_e2e)
+            torch.cuda.synchronize()
+            cli_accepted = int((c2.fl[:m_cli] & 1).sum().item())
+            text_for_cli = make_cli_fastq(c2.slab[:m_cli].cpu().numpy(), SEED + 9)
 
     # ==== the other BASELINE.json configs + the real-profile workload, device-resident =========================
     configs = {}
@@ -614,8 +743,12 @@ def run_ours(args):
 
     # ==== the CLI a user runs: FASTQ file -> output files, wall clock (N GPUs in ONE process, rank 0 drives) ======
     e2e_cli = None
-    if not args.no_e2e and not args.no_cli and text_for_cli is not None:
-        e2e_cli = cli_bench(text_for_cli, world, rank, args)
+    if not args.no_e2e and not args.no_cli:
+        torch.cuda.empty_cache()
+        barrier()
+        if text_for_cli is not None:
+            e2e_cli = cli_bench(text_for_cli, cli_accepted, world, rank, args)
+            log("e2e_cli", e2e_cli)
     text_for_cli = None
     barrier()
 
@@ -728,6 +861,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip C3 / C4 / C5 / real_profile")
     ap.add_argument("--small-configs", action="store_true", help="C3 / C4 / C5 at a tenth of their size (development)")
     ap.add_argument("--no-cli", action="store_true")
+    ap.add_argument("--cli-reads", type=int, default=10_000_000, help="reads of the FASTQ file the CLI run filters")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
     # NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the run and the line goes to the real one.

@@ -133,6 +133,7 @@ MOIRA_API int moira_abi_version(void);
 MOIRA_API const char *moira_last_error(void);
 MOIRA_API void moira_params_default(moira_params *p);  /* reference defaults: PB, alpha .005, uncert .01, treat_as_errors */
 
+MOIRA_API int moira_device_count(int *n_out);           /* usable CUDA devices (0 without a driver / GPU) */
 MOIRA_API int moira_ctx_create(int device, moira_ctx **out);
 MOIRA_API int moira_ctx_destroy(moira_ctx *ctx);
 MOIRA_API int moira_ctx_sm_count(const moira_ctx *ctx, int *out);
@@ -252,8 +253,36 @@ MOIRA_API int moira_filter_fastq(moira_ctx *ctx, const char *text, uint64_t text
                                  double *ee_out, int32_t *ns_out, uint8_t *flags_out, uint32_t *lengths_out,
                                  uint64_t *counters_out, uint64_t *n_reads_out);
 
+/* moira_filter_fastq with what a host needs to go on from the decisions to the output files, without parsing the text
+ * again: seq_off_out / qual_off_out (may be NULL) receive, per read, the position of its sequence and quality line in
+ * `text` (both lengths_out[r] bytes long; moira_fastq_headers finds the header tokens from seq_off_out); labels_out (may
+ * be NULL) receives the device-side dereplication of the (truncated) sequences: labels_out[r] is the index of one read
+ * with exactly read r's sequence, the same index for all of them (moira_collapse_labels turns labels + ee into the
+ * reference's groups).  Labels keep every sequence on the device until the last chunk (text_bytes of HBM). */
+MOIRA_API int moira_filter_fastq_ex(moira_ctx *ctx, const char *text, uint64_t text_bytes, int fastq_offset,
+                                    int lower_n_ambiguous, const moira_params *params, uint64_t max_reads,
+                                    double *ee_out, int32_t *ns_out, uint8_t *flags_out, uint32_t *lengths_out,
+                                    uint64_t *seq_off_out, uint64_t *qual_off_out, uint32_t *labels_out,
+                                    uint64_t *counters_out, uint64_t *n_reads_out);
+
+/* Dereplication on the device for sequences that already live there (device pointers; enqueued on `stream`): read r is
+ * d_seq + (d_offsets ? d_offsets[r] : r * stride), d_lengths[r] (or fixed_length) bytes, cut at `truncate` when that is
+ * not 0; any alignment, 8 readable bytes behind the last sequence.  d_labels[r] = index of one read with exactly the
+ * same bytes (128-bit hashes select candidates, the bytes decide).  Replaces the hashing and comparing of the reference's
+ * `uniques` dictionary (moira.py:409-411, 459-465). */
+MOIRA_API int moira_collapse_device(moira_ctx *ctx, const uint8_t *d_seq, const uint64_t *d_offsets, const uint32_t *d_lengths,
+                                    uint64_t stride, uint32_t fixed_length, uint64_t n_reads, uint32_t truncate,
+                                    uint32_t *d_labels, void *stream);
+
+/* The rest of --collapse from labels (equal label <=> equal sequence; any labelling with that property, label < n):
+ * same outputs as moira_collapse, computed without looking at a single base. */
+MOIRA_API int moira_collapse_labels(const uint32_t *labels, const double *ee, uint64_t n, uint64_t *group_of_read,
+                                    uint64_t *n_groups_out, uint64_t *group_rep, uint64_t *group_size,
+                                    uint64_t *member_start, uint64_t *members, uint64_t *abundance_order);
+
 /* Dereplication of identical sequences, the reference's --collapse (moira.py:459-475, 491-504), on
- * all host threads.  Read r's (already truncated) sequence is text[seq_off[r] .. + seq_len[r]); ee[r]
+ * all host threads.  Read r's (already truncated) sequence is text[seq_off[r] .. + seq_len[r]) (text == NULL: seq_off
+ * holds absolute addresses); ee[r]
  * is its final expected-error value.  Outputs (all caller-allocated, capacity n, member_start n+1):
  *   group_of_read[r]            group of read r; groups are numbered by first appearance
  *   group_rep[g]                representative read: first read with the strictly smallest ee (moira.py:466)
@@ -266,6 +295,64 @@ MOIRA_API int moira_collapse(const char *text, const uint64_t *seq_off, const ui
                              uint64_t n, int n_threads, uint64_t *group_of_read, uint64_t *n_groups_out,
                              uint64_t *group_rep, uint64_t *group_size, uint64_t *member_start, uint64_t *members,
                              uint64_t *abundance_order);
+
+/* ---- output records: what write_results prints (moira.py:842-970), formatted natively -----------------
+ * The reads' text stays where the parsers / the contig kernel left it; the host passes byte ranges.  A NULL base pointer
+ * makes the matching offsets absolute addresses (records spread over several buffers). */
+typedef struct moira_records {
+    const char *hdr_base;      /* header token of read r (no leading '>' / '@'): hdr_base + hdr_off[r], hdr_len[r] bytes; ':' is */
+    const uint64_t *hdr_off;   /* written as '_' (moira.py:1121, 1175) */
+    const uint32_t *hdr_len;
+    const char *seq_base;      /* bases: seq_base + seq_off[r] */
+    const uint64_t *seq_off;
+    const uint8_t *qual_base;  /* one byte per base: qual_base + qual_off[r]; quality = byte - qual_sub, read as 1 when <= 0 */
+    const uint64_t *qual_off;  /* (moira.py:814); with qual_sub == 0 bytes 253..255 stand for -3..-1 (contig rows) */
+    const uint32_t *len;       /* bases to write, i.e. after --truncate */
+    int32_t qual_sub;
+} moira_records;
+
+typedef struct moira_write_opts {
+    int32_t fastq;             /* 1: fastq records, 0: fasta + qual records          (--output_format) */
+    int32_t fastq_offset;      /* chr(q + offset) of fastq output                    (--fastq_offset) */
+    int32_t usearch;           /* header += ";ee=%.2f;size=%d;"                      (--pipeline USEARCH, moira.py:858-863) */
+    int32_t names;             /* mothur names lines for the selected groups         (--collapse with --pipeline mothur) */
+    const char *relabel;       /* NULL, or header = relabel + index                  (--relabel, moira.py:853-854) */
+    uint64_t first_index;      /* index of the first selected record */
+    const char *notes[8];      /* by reason code: what follows the header of a rejected record, e.g. "\tuncert > 0.010" */
+} moira_write_opts;
+
+#define MOIRA_BLOCK_GOOD        0   /* <prefix>.qc.good.fasta / .fastq */
+#define MOIRA_BLOCK_GOOD_QUAL   1   /* <prefix>.qc.good.qual */
+#define MOIRA_BLOCK_GOOD_NAMES  2   /* <prefix>.qc.good.names */
+#define MOIRA_BLOCK_BAD         3
+#define MOIRA_BLOCK_BAD_QUAL    4
+#define MOIRA_BLOCK_BAD_NAMES   5
+#define MOIRA_BLOCK_REPORT      6   /* <prefix>.contigs.report lines (when the contig statistics are given) */
+#define MOIRA_BLOCK_N           7
+typedef struct moira_blocks moira_blocks;
+
+/* Format n_sel records in the order sel[0..n_sel) (read indices; NULL = 0, 1, 2, ...) on all host threads.  ee, accept,
+ * reason are indexed by read.  With groups (sel_group[k] = group of sel[k], member_start / members as moira_collapse
+ * returns them) the USEARCH size and the names lines list the group's members.  overlap / gaps / mismatches (may be
+ * NULL, indexed by read) add the contigs report.  The result is a set of memory blocks: parts 0 .. n_parts-1 in
+ * output order, each with MOIRA_BLOCK_N byte strings owned by the library until moira_blocks_free. */
+MOIRA_API int moira_format_records(const moira_records *records, const moira_write_opts *opts, const uint64_t *sel, uint64_t n_sel,
+                                   const double *ee, const uint8_t *accept, const uint8_t *reason, const uint64_t *sel_group,
+                                   const uint64_t *member_start, const uint64_t *members, const int32_t *overlap,
+                                   const int32_t *gaps, const int32_t *mismatches, int n_threads, moira_blocks **out);
+MOIRA_API int moira_blocks_parts(const moira_blocks *blocks, int *n_parts_out);
+MOIRA_API int moira_blocks_get(const moira_blocks *blocks, int part, int which, const char **ptr_out, uint64_t *len_out);
+MOIRA_API int moira_blocks_free(moira_blocks *blocks);
+
+/* Header token (offset, length) of every FASTQ record from the position of its sequence line, as moira_filter_fastq_ex
+ * returns it: the line before, stripped, cut at the first blank, leading '@' dropped (moira.py:1172-1175). */
+MOIRA_API int moira_fastq_headers(const char *text, uint64_t text_bytes, const uint64_t *seq_off, uint64_t n_reads, int n_threads,
+                                  uint64_t *hdr_off_out, uint32_t *hdr_len_out);
+
+/* Record-aligned cut points of a FASTQ text for n_parts shards (one per GPU): cuts_out[0] = 0 <= ... <= cuts_out[n_parts] =
+ * text_bytes; every inner cut is the start of a line that begins with '@' and whose second successor begins with '+' --
+ * in a 4-line FASTQ only header lines do (a quality line may begin with '@', but two lines further down is a sequence). */
+MOIRA_API int moira_fastq_split(const char *text, uint64_t text_bytes, int n_parts, uint64_t *cuts_out);
 
 /* ---- paired-end contig construction ------------------------------------------
  * The producer of the contigs the filter runs on when --paired is given (process_data, moira.py:791-803):

@@ -34,11 +34,13 @@ CONSENSUS_BEST, CONSENSUS_SUM, CONSENSUS_POSTERIOR = 0, 1, 2
 PAIR_OK, PAIR_EMPTY, PAIR_BAD_BASE, PAIR_BAD_QUALITY, PAIR_TOO_LONG = 0, 1, 2, 3, 4
 
 EXPORTS = [
-    "moira_abi_version", "moira_last_error", "moira_params_default", "moira_ctx_create",
+    "moira_abi_version", "moira_last_error", "moira_params_default", "moira_device_count", "moira_ctx_create",
     "moira_ctx_destroy", "moira_ctx_sm_count", "moira_build_lut", "moira_ctx_get_lut",
     "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_count_marks_device", "moira_filter_batch",
     "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads", "moira_pack_q6",
     "moira_parse_fastq", "moira_parse_fasta_qual", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
+    "moira_filter_fastq_ex", "moira_collapse_device", "moira_collapse_labels", "moira_format_records", "moira_blocks_parts",
+    "moira_blocks_get", "moira_blocks_free", "moira_fastq_headers", "moira_fastq_split",
     "moira_comm_unique_id", "moira_comm_init", "moira_comm_init_all", "moira_comm_info", "moira_reduce_counters_device",
     "moira_reduce_counters", "moira_reduce_counters_all", "moira_link_probe",
     "moira_ctx_last_kernel_ms", "moira_ctx_last_contig_ms", "moira_contig_params_default", "moira_filter_pairs", "moira_nw_align", "moira_make_contig",
@@ -63,6 +65,22 @@ class ContigParams(ctypes.Structure):
                                               "trim_overlap")]
 
 
+class Records(ctypes.Structure):
+    """struct moira_records."""
+    _fields_ = [("hdr_base", ctypes.c_void_p), ("hdr_off", ctypes.c_void_p), ("hdr_len", ctypes.c_void_p),
+                ("seq_base", ctypes.c_void_p), ("seq_off", ctypes.c_void_p), ("qual_base", ctypes.c_void_p),
+                ("qual_off", ctypes.c_void_p), ("len", ctypes.c_void_p), ("qual_sub", ctypes.c_int32)]
+
+
+class WriteOpts(ctypes.Structure):
+    """struct moira_write_opts."""
+    _fields_ = [("fastq", ctypes.c_int32), ("fastq_offset", ctypes.c_int32), ("usearch", ctypes.c_int32), ("names", ctypes.c_int32),
+                ("relabel", ctypes.c_char_p), ("first_index", ctypes.c_uint64), ("notes", ctypes.c_char_p * 8)]
+
+
+BLOCK_GOOD, BLOCK_GOOD_QUAL, BLOCK_GOOD_NAMES, BLOCK_BAD, BLOCK_BAD_QUAL, BLOCK_BAD_NAMES, BLOCK_REPORT, BLOCK_N = range(8)
+
+
 class MoiraError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("moira_b200 error %d: %s" % (code, message))
@@ -84,6 +102,7 @@ lib.moira_abi_version.restype = _i
 lib.moira_last_error.restype = ctypes.c_char_p
 lib.moira_params_default.restype = None
 lib.moira_params_default.argtypes = [_pp]
+lib.moira_device_count.argtypes = [ctypes.POINTER(_i)]
 lib.moira_ctx_create.argtypes = [_i, ctypes.POINTER(_vp)]
 lib.moira_ctx_destroy.argtypes = [_vp]
 lib.moira_ctx_sm_count.argtypes = [_vp, ctypes.POINTER(_i)]
@@ -106,6 +125,16 @@ lib.moira_parse_fasta_qual.argtypes = [_vp, _u64, _vp, _u64, _i, _vp, _u64, _vp,
                                        ctypes.POINTER(_u64), ctypes.POINTER(_u64)]
 lib.moira_fastq_count_reads.argtypes = [_vp, _u64, ctypes.POINTER(_u64)]
 lib.moira_filter_fastq.argtypes = [_vp, _vp, _u64, _i, _i, _pp, _u64, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_u64)]
+lib.moira_filter_fastq_ex.argtypes = [_vp, _vp, _u64, _i, _i, _pp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_u64)]
+lib.moira_collapse_device.argtypes = [_vp, _vp, _vp, _vp, _u64, _u32, _u64, _u32, _vp, _vp]
+lib.moira_collapse_labels.argtypes = [_vp, _vp, _u64, _vp, ctypes.POINTER(_u64), _vp, _vp, _vp, _vp, _vp]
+lib.moira_format_records.argtypes = [ctypes.POINTER(Records), ctypes.POINTER(WriteOpts), _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _i, ctypes.POINTER(_vp)]
+lib.moira_blocks_parts.argtypes = [_vp, ctypes.POINTER(_i)]
+lib.moira_blocks_get.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]
+lib.moira_blocks_free.argtypes = [_vp]
+lib.moira_fastq_headers.argtypes = [_vp, _u64, _vp, _u64, _i, _vp, _vp]
+lib.moira_fastq_split.argtypes = [_vp, _u64, _i, _vp]
 lib.moira_collapse.argtypes = [_vp, _vp, _vp, _vp, _u64, _i, _vp, ctypes.POINTER(_u64), _vp, _vp, _vp, _vp, _vp]
 lib.moira_set_host_threads.argtypes = [_i]
 lib.moira_fp64_peak.argtypes = [_vp, _i, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]

@@ -350,6 +350,38 @@ class Context:
                                        _ptr(out.counters), ctypes.byref(n)))
         return out, lengths[:n.value]
 
+    def filter_fastq_ex(self, text, params: FilterParams, fastq_offset: int = 33, max_reads: int | None = None,
+                        offsets: bool = True, labels: bool = False) -> "FastqResult":
+        """moira_filter_fastq_ex: decisions plus what the host needs to go on to the output files without parsing again
+        -- per read the position of its sequence and quality line in `text`, and (labels=True) the device-side
+        dereplication of the (truncated) sequences."""
+        buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+        if max_reads is None:
+            n = ctypes.c_uint64()
+            L.check(lib.moira_fastq_count_reads(_ptr(buf), buf.nbytes, ctypes.byref(n)))
+            max_reads = n.value
+        nr = int(max_reads)
+        res = FilterResult(np.empty(nr, np.float64), np.empty(nr, np.int32), np.empty(nr, np.uint8), np.zeros(L.N_COUNTERS, np.uint64))
+        lengths = np.empty(nr, np.uint32)
+        soff = np.empty(nr, np.uint64) if offsets else None
+        qoff = np.empty(nr, np.uint64) if offsets else None
+        lab = np.empty(nr, np.uint32) if labels else None
+        got = ctypes.c_uint64()
+        cp = params.to_c()
+        L.check(lib.moira_filter_fastq_ex(self._h, _ptr(buf), buf.nbytes, int(fastq_offset), int(params.lower_n_ambiguous),
+                                          ctypes.byref(cp), nr, _ptr(res.ee), _ptr(res.ns), _ptr(res.flags), _ptr(lengths),
+                                          _ptr(soff), _ptr(qoff), _ptr(lab), _ptr(res.counters), ctypes.byref(got)))
+        m = got.value
+        res = FilterResult(res.ee[:m], res.ns[:m], res.flags[:m], res.counters)
+        return FastqResult(res, lengths[:m], None if soff is None else soff[:m], None if qoff is None else qoff[:m],
+                           None if lab is None else lab[:m])
+
+    def collapse_device(self, d_seq: int, d_offsets: int | None, d_lengths: int | None, stride: int, fixed_length: int,
+                        n_reads: int, d_labels: int, truncate: int = 0, stream: int | None = None):
+        """Device-resident sequences -> labels (moira_collapse_device); enqueues on `stream`."""
+        L.check(lib.moira_collapse_device(self._h, d_seq, d_offsets, d_lengths, int(stride), int(fixed_length), int(n_reads),
+                                          int(truncate), d_labels, stream))
+
     def filter_pairs(self, fwd_seq, fwd_qual, fwd_off, fwd_len, rev_seq, rev_qual, rev_off, rev_len,
                      contig_params: ContigParams, filter_params: FilterParams | None = None,
                      lower_n_ambiguous: bool = True, fwd_qual_off=None, rev_qual_off=None, qual_base: int = 0,
@@ -586,7 +618,7 @@ class CollapseResult:
 def collapse(text, seq_off, seq_len, ee, n_threads: int = 0) -> CollapseResult:
     """moira_collapse: dereplicate identical sequences with the reference's --collapse semantics
     (moira.py:459-475, 491-504).  `text` is a bytes-like buffer holding the sequences."""
-    buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+    buf = None if text is None else (np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text)   # None: absolute addresses
     seq_off = _as(seq_off, np.uint64)
     seq_len = _as(seq_len, np.uint32)
     ee = _as(ee, np.float64)
@@ -604,6 +636,136 @@ def collapse(text, seq_off, seq_len, ee, n_threads: int = 0) -> CollapseResult:
     return CollapseResult(g_of, rep[:G], size[:G], mstart[:G + 1], members, order[:G])
 
 
-__all__ = ["collapse", "CollapseResult","Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",
+def collapse_labels(labels, ee) -> CollapseResult:
+    """moira_collapse_labels: the reference's groups, representatives, names order and abundance order from labels
+    (equal label <=> equal sequence) and ee."""
+    labels = _as(labels, np.uint32)
+    ee = _as(ee, np.float64)
+    n = int(labels.shape[0])
+    g_of, rep, size = np.empty(n, np.uint64), np.empty(n, np.uint64), np.empty(n, np.uint64)
+    mstart, members, order = np.empty(n + 1, np.uint64), np.empty(n, np.uint64), np.empty(n, np.uint64)
+    ng = ctypes.c_uint64()
+    L.check(lib.moira_collapse_labels(_ptr(labels), _ptr(ee), n, _ptr(g_of), ctypes.byref(ng), _ptr(rep), _ptr(size), _ptr(mstart),
+                                      _ptr(members), _ptr(order)))
+    G = ng.value
+    return CollapseResult(g_of, rep[:G], size[:G], mstart[:G + 1], members, order[:G])
+
+
+def fastq_headers(text, seq_off, n_threads: int = 0):
+    """(hdr_off uint64[n], hdr_len uint32[n]): header tokens of FASTQ records from their sequence-line positions."""
+    buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+    seq_off = _as(seq_off, np.uint64)
+    n = int(seq_off.shape[0])
+    ho, hl = np.empty(n, np.uint64), np.empty(n, np.uint32)
+    L.check(lib.moira_fastq_headers(_ptr(buf), buf.nbytes, _ptr(seq_off), n, int(n_threads), _ptr(ho), _ptr(hl)))
+    return ho, hl
+
+
+def fastq_split(text, n_parts: int):
+    """Record-aligned cut points (uint64[n_parts + 1]) of a FASTQ text, one shard per GPU (moira_fastq_split)."""
+    buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+    cuts = np.zeros(n_parts + 1, np.uint64)
+    L.check(lib.moira_fastq_split(_ptr(buf), buf.nbytes, int(n_parts), _ptr(cuts)))
+    return cuts
+
+
+@dataclass
+class FastqResult:
+    filter: FilterResult
+    lengths: np.ndarray            # uint32[n]
+    seq_off: np.ndarray | None     # uint64[n] position of the sequence line in the text
+    qual_off: np.ndarray | None
+    labels: np.ndarray | None      # uint32[n] read index of one read with the same (truncated) sequence
+
+
+@dataclass
+class RecordView:
+    """Where the reads' text lives (struct moira_records): base buffers (uint8 arrays) + per-read byte ranges."""
+    hdr_base: np.ndarray
+    hdr_off: np.ndarray
+    hdr_len: np.ndarray
+    seq_base: np.ndarray
+    seq_off: np.ndarray
+    qual_base: np.ndarray
+    qual_off: np.ndarray
+    length: np.ndarray             # bases to write (after --truncate)
+    qual_sub: int = 0
+
+
+class Blocks:
+    """Formatted output (moira_format_records): memory blocks owned by the library until close()."""
+
+    def __init__(self, handle):
+        self._h = handle
+        n = ctypes.c_int()
+        L.check(lib.moira_blocks_parts(self._h, ctypes.byref(n)))
+        self.n_parts = n.value
+
+    def block(self, part: int, which: int):
+        ptr, ln = ctypes.c_void_p(), ctypes.c_uint64()
+        L.check(lib.moira_blocks_get(self._h, part, which, ctypes.byref(ptr), ctypes.byref(ln)))
+        if not ln.value:
+            return b""
+        return (ctypes.c_char * ln.value).from_address(ptr.value)
+
+    def write(self, which: int, fh):
+        """All parts of one block kind, in order, to a binary file object."""
+        for p in range(self.n_parts):
+            b = self.block(p, which)
+            if len(b):
+                fh.write(b)
+
+    def close(self):
+        if self._h:
+            lib.moira_blocks_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def format_records(rec: RecordView, sel, ee, accept, reason, *, fastq: bool, fastq_offset: int = 33, usearch: bool = False,
+                   names: bool = False, relabel: str | None = None, first_index: int = 0, notes=None, sel_group=None,
+                   member_start=None, members=None, stats=None, n_threads: int = 0) -> Blocks:
+    """moira_format_records: the records `sel` (read indices in output order, None = all) as write_results prints them
+    (moira.py:842-970).  notes: {reason code: bytes appended to a rejected record's header}.  stats: (overlap, gaps,
+    mismatches) int32 arrays for the contigs report."""
+    keep = []
+
+    def arr(a, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a
+
+    r = L.Records()
+    bases = [arr(rec.hdr_base, np.uint8), arr(rec.seq_base, np.uint8), arr(rec.qual_base, np.uint8)]
+    r.hdr_base, r.seq_base, r.qual_base = [_ptr(b) for b in bases]      # None: the offsets are absolute addresses
+    r.hdr_off, r.hdr_len = _ptr(arr(rec.hdr_off, np.uint64)), _ptr(arr(rec.hdr_len, np.uint32))
+    r.seq_off, r.qual_off = _ptr(arr(rec.seq_off, np.uint64)), _ptr(arr(rec.qual_off, np.uint64))
+    r.len = _ptr(arr(rec.length, np.uint32))
+    r.qual_sub = int(rec.qual_sub)
+    o = L.WriteOpts()
+    o.fastq, o.fastq_offset, o.usearch, o.names = int(bool(fastq)), int(fastq_offset), int(bool(usearch)), int(bool(names))
+    o.relabel = relabel.encode("latin-1") if relabel else None
+    o.first_index = int(first_index)
+    for code, text in (notes or {}).items():
+        o.notes[int(code)] = text if isinstance(text, bytes) else text.encode("latin-1")
+    sel = arr(sel, np.uint64)
+    n_sel = int(sel.shape[0]) if sel is not None else int(np.asarray(rec.length).shape[0])
+    ov, gp, mm = (None, None, None) if stats is None else [arr(x, np.int32) for x in stats]
+    out = ctypes.c_void_p()
+    L.check(lib.moira_format_records(ctypes.byref(r), ctypes.byref(o), _ptr(sel), n_sel, _ptr(arr(ee, np.float64)),
+                                     _ptr(arr(accept, np.uint8)), _ptr(arr(reason, np.uint8)), _ptr(arr(sel_group, np.uint64)),
+                                     _ptr(arr(member_start, np.uint64)), _ptr(arr(members, np.uint64)), _ptr(ov), _ptr(gp), _ptr(mm),
+                                     int(n_threads), ctypes.byref(out)))
+    return Blocks(out)
+
+
+__all__ = ["collapse_labels", "fastq_headers", "fastq_split", "FastqResult", "RecordView", "Blocks", "format_records", "collapse", "CollapseResult","Context", "FilterParams", "FilterResult", "PinnedBuffer", "MoiraError", "pack_reads",
            "pack_arrays", "pack_q6", "parse_fastq", "parse_fasta_qual", "build_lut", "ContigParams", "PairResult", "pack_sequences",
            "comm_unique_id", "comm_init_all", "reduce_counters_all"]

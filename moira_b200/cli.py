@@ -6,9 +6,10 @@ main :264-578, write_results :842-970, parsers :1058-1204), but instead of calli
 `bernoulli.calculate_errors_PB` once per read (moira.py:817) it parses reads in batches straight into
 quality slabs and runs them through libmoira_b200.so (one moira_filter_batch per batch).
 
-Scope: single-end filtering (`--forward_fastq` or `--forward_fasta` + `--forward_qual`).  Paired-end
-contig construction (`--paired`, `--only_contig`) is upstream of the hot path and not part of this
-build; those flags are accepted and rejected with a message.
+Flows: single-end FASTQ (text -> device parser -> filter -> device dereplication, sharded over --devices), single-end
+FASTA + QUAL (native host parser), and --paired / --only_contig (contigs built on the device).  Records
+are never turned into Python objects: the parsers leave byte ranges, the device leaves decisions, the native writer
+(moira_format_records) turns both into the output files.
 `--error_calc` adds `expected_error` (north_star) and drops `bootstrap` (deprecated, moira.py:772-776);
 `poisson_binomial_py` is an alias of `poisson_binomial` with the Python twin's 'N'-only rule.
 """
@@ -18,13 +19,16 @@ import argparse
 import bz2
 import gzip
 import io
+import mmap
+import os
 import sys
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
 from . import _lib as L
-from .api import ContigParams, Context, FilterParams, MoiraError, collapse, pack_reads, parse_fasta_qual, parse_fastq
+from .api import ContigParams, Context, FilterParams, MoiraError, collapse, parse_fasta_qual, parse_fastq
 
 __version__ = "0.1.0 (moira 1.3.2 compatible)"
 
@@ -79,7 +83,7 @@ def parse_arguments(argv=None):
     general.add_argument("-op", "--output_prefix", type=str)
     general.add_argument("-oc", "--output_compression", type=str, default="none", choices=("none", "gz", "bz2"))
     general.add_argument("-p", "--processors", type=int, default=1,
-                         help="Accepted for compatibility; the GPU path does not use worker processes.")
+                         help="Accepted for compatibility; the GPU path does not use worker processes (see --devices).")
     general.add_argument("--paired", action="store_true")
     general.add_argument("-fo", "--fastq_offset", type=int, default=33)
     general.add_argument("--only_contig", action="store_true")
@@ -87,6 +91,9 @@ def parse_arguments(argv=None):
     general.add_argument("--nowarnings", action="store_true")
     general.add_argument("--doc", action="store_true")
     general.add_argument("--device", type=int, default=0, help="CUDA device index (B200 path only).")
+    general.add_argument("--devices", type=str, default=None,
+                         help="'all' or a comma-separated list of CUDA devices: reads are sharded by contiguous chunk, one context "
+                              "and one host thread per GPU (the B200 counterpart of --processors); overrides --device.")
     constructor = parser.add_argument_group("Contig construction options")     # moira.py:629-646
     constructor.add_argument("-m", "--match", type=int, default=1)
     constructor.add_argument("-x", "--mismatch", type=int, default=-1)
@@ -195,50 +202,47 @@ def _norm_header(raw: str, lead: str) -> str:
     return raw.strip().replace("\t", " ").split(" ")[0].lstrip(lead).replace(":", "_")
 
 
-def read_fastq_batches(fh, fastq_offset, lower_n_ambiguous, fname):
-    """Yield (headers, seqs, quals_arrays, slab, offsets, lengths) per batch of whole 4-line records."""
-    carry = b""
-    while True:
-        block = fh.read(BATCH_BYTES)
-        data = carry + block
-        if not data:
-            break
-        if block:
-            # keep whole records: cut at the last newline that ends a multiple of 4 lines
-            n_lines = data.count(b"\n")
-            keep_lines = n_lines - (n_lines % 4)
-            if keep_lines == 0:
-                carry = data
-                continue
-            pos = -1
-            # find position after keep_lines-th newline
-            idx = np.flatnonzero(np.frombuffer(data, dtype=np.uint8) == 10)
-            pos = int(idx[keep_lines - 1]) + 1
-            text, carry = data[:pos], data[pos:]
+def load_text(filename):
+    """Whole input file as a uint8 array: plain files are memory-mapped (no copy; the library stages pageable text through
+    its own pinned ring), gzip / bzip2 files (sniffed by magic bytes, moira.py:1065-1068) are inflated into memory."""
+    with io.open(filename, mode="rb") as fh:
+        start = fh.read(3)
+        if start.startswith(b"\x1f\x8b\x08"):
+            data = gzip.GzipFile(filename=filename).read()
+        elif start.startswith(b"\x42\x5a\x68"):
+            data = bz2.BZ2File(filename).read()
         else:
-            text, carry = data, b""
-        try:
-            slab, offsets, lengths, hoff, hlen, soff, qoff = parse_fastq(text, fastq_offset, lower_n_ambiguous)
-        except MoiraError as exc:
-            if exc.code == L.ERR_PARSE:
-                name = exc.message.split(":")[0]
-                cls = {"EmptySeqError": EmptySeqError, "EmptyQualError": EmptyQualError}.get(name)
-                if cls:
-                    raise cls(exc.message, fname) from None
-                raise LengthMismatchError(exc.message, fname) from None
-            raise
-        n = len(lengths)
-        headers = [text[int(hoff[i]):int(hoff[i]) + int(hlen[i])].decode("latin-1").replace(":", "_") for i in range(n)]
-        seqs = [text[int(soff[i]):int(soff[i]) + int(lengths[i])].decode("latin-1") for i in range(n)]
-        # qualities for the writers, as process_data returns them (Q <= 0 -> 1, moira.py:814)
-        buf = np.frombuffer(text, dtype=np.uint8)
-        quals = []
-        for i in range(n):
-            q = buf[int(qoff[i]):int(qoff[i]) + int(lengths[i])].astype(np.int32) - fastq_offset
-            quals.append(np.where(q > 0, q, 1))
-        yield headers, seqs, quals, slab, offsets, lengths
-        if not block:
-            break
+            size = os.fstat(fh.fileno()).st_size
+            if size == 0:
+                return np.zeros(0, np.uint8), None
+            mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            return np.frombuffer(mm, dtype=np.uint8), mm
+    return np.frombuffer(data, dtype=np.uint8), data
+
+
+def _raise_parse_error(exc, *fnames):
+    """MOIRA_ERR_PARSE -> the reference's exception classes (moira.py:994-1055)."""
+    if exc.code != L.ERR_PARSE:
+        raise exc
+    name = exc.message.split(":")[0]
+    if name == "NameMismatchError":
+        raise NameMismatchError(exc.message, "") from None
+    if name == "EmptySeqError":
+        raise EmptySeqError(exc.message, fnames[0]) from None
+    if name == "EmptyQualError":
+        raise EmptyQualError(exc.message, fnames[-1]) from None
+    raise LengthMismatchError(exc.message, *fnames) from None
+
+
+def _gather(buf, off, ln):
+    """Concatenation of buf[off[i] : off[i] + ln[i]] over i (vectorised)."""
+    ln = ln.astype(np.int64)
+    total = int(ln.sum())
+    if total == 0:
+        return np.zeros(0, np.uint8)
+    starts = np.cumsum(ln) - ln
+    idx = np.repeat(off.astype(np.int64) - starts, ln) + np.arange(total, dtype=np.int64)
+    return buf[idx]
 
 
 def _cut_lines(data: bytes, n_lines: int) -> int:
@@ -296,11 +300,8 @@ def read_fasta_qual_batches(ffh, qfh, lower_n_ambiguous, fasta_name, qual_name):
                     raise LengthMismatchError(exc.message, fasta_name, qual_name) from None
                 raise ValueError(exc.message) from None
             raise
-        n = len(lengths)
-        headers = [ftext[int(hoff[i]):int(hoff[i]) + int(hlen[i])].decode("latin-1").replace(":", "_") for i in range(n)]
-        seqs = [ftext[int(soff[i]):int(soff[i]) + int(lengths[i])].decode("latin-1") for i in range(n)]
-        quals = [np.maximum(qslab[int(offsets[i]):int(offsets[i]) + int(lengths[i])].astype(np.int32), 1) for i in range(n)]   # moira.py:814
-        yield headers, seqs, quals, slab, offsets, lengths
+        # arrays only: (fasta text, header offsets / lengths, sequence offsets, plain qualities at the slab's offsets, slab, ...)
+        yield ftext, hoff, hlen, soff, qslab, slab, offsets, lengths
         if not block:
             break
 
@@ -337,7 +338,8 @@ def _whole_records(fh, carry, lines_per_record, want_lines=None):
 def read_pair_batches(args, lower_n_ambiguous):
     """Paired input (moira.py:1093-1204 with both files): blocks of whole records of the forward file and the same
     number of records of the reverse file, parsed natively, headers compared (NameMismatchError).
-    Yields (headers, fwd, rev) with fwd / rev = (bases u8, quals u8, seq_off, qual_off, lengths, qual_base)."""
+    Yields (forward text, header offsets, header lengths, fwd, rev) with fwd / rev = (bases u8, quals u8, seq_off, qual_off,
+    lengths, qual_base)."""
     fastq = bool(args.forward_fastq)
     if fastq:
         files = [(open_input(args.forward_fastq), args.forward_fastq), (open_input(args.reverse_fastq), args.reverse_fastq)]
@@ -383,100 +385,358 @@ def read_pair_batches(args, lower_n_ambiguous):
         n = len(fwd[4])
         if len(rev[4]) != n:
             raise NameMismatchError("(%d forward records)" % n, "(%d reverse records)" % len(rev[4]))
-        headers = [ftext[int(fh_off[i]):int(fh_off[i]) + int(fh_len[i])].decode("latin-1").replace(":", "_") for i in range(n)]
-        for i in range(n):                                                   # moira.py:1141-1142, 1199-1200
-            rh = rtext[int(rh_off[i]):int(rh_off[i]) + int(rh_len[i])].decode("latin-1").replace(":", "_")
-            if rh != headers[i]:
-                raise NameMismatchError(headers[i], None, rh, None)
-        yield headers, fwd, rev
+        fb, rb = np.frombuffer(ftext, dtype=np.uint8), np.frombuffer(rtext, dtype=np.uint8)
+        same = np.array_equal(fh_len, rh_len) and np.array_equal(_gather(fb, fh_off, fh_len), _gather(rb, rh_off, rh_len))
+        if not same:                                                         # moira.py:1141-1142, 1199-1200
+            for i in range(n):
+                fh_ = ftext[int(fh_off[i]):int(fh_off[i]) + int(fh_len[i])].decode("latin-1").replace(":", "_")
+                rh_ = rtext[int(rh_off[i]):int(rh_off[i]) + int(rh_len[i])].decode("latin-1").replace(":", "_")
+                if fh_ != rh_:
+                    raise NameMismatchError(fh_, None, rh_, None)
+        yield ftext, fh_off, fh_len, fwd, rev
         if eof:
             break
 
 
-# ---- output (moira.py:842-970) ----------------------------------------------------------------------
+
+
+# ---- the reads of a run, as arrays ------------------------------------------------------------------------
+REASON_OVERLAP = 4   # host-side: "overlap length below" (moira.py:886-897); the device knows reasons 0..3
+
+
+class ReadSet:
+    """Every read of the run: where its header / bases / qualities lie (absolute addresses into buffers kept alive in
+    `keep`), and what the device said about it.  Filled batch by batch (or shard by shard), concatenated once."""
+
+    def __init__(self, qual_sub):
+        self.qual_sub = qual_sub
+        self.keep = []
+        self.parts = []          # dicts of arrays
+        self.counters = np.zeros(L.N_COUNTERS, np.uint64)
+
+    def add(self, **arrays):
+        self.parts.append(arrays)
+
+    def finish(self):
+        keys = self.parts[0].keys() if self.parts else ()
+        for k in keys:
+            vals = [p[k] for p in self.parts]
+            setattr(self, k, None if vals[0] is None else (vals[0] if len(vals) == 1 else np.concatenate(vals)))
+        if not self.parts:
+            for k, dt in (("hdr_addr", np.uint64), ("hdr_len", np.uint32), ("seq_addr", np.uint64), ("qual_addr", np.uint64),
+                          ("length", np.uint32), ("ee", np.float64), ("flags", np.uint8)):
+                setattr(self, k, np.zeros(0, dt))
+            self.stats = self.labels = None
+        self.parts = []
+        self.n = int(self.length.shape[0])
+        return self
+
+
+def _addr(buf) -> int:
+    return int(buf.ctypes.data) if isinstance(buf, np.ndarray) else int(np.frombuffer(buf, dtype=np.uint8).ctypes.data)
+
+
 class Writers:
+    """The output files of write_results (moira.py:323-370), opened in binary mode: the native writer hands over bytes."""
+
     def __init__(self, args, output_name):
         opener, suffix = {"none": (open, ""), "gz": (gzip.open, ".gz"), "bz2": (bz2.open, ".bz2")}[args.output_compression]
-        self.files = []
+        self.files, self.names, self.by_block = [], [], {}
 
-        def op(name):
-            fh = opener(name + suffix, "wt")
+        def op(name, block):
+            fh = opener(name + suffix, "wb")
             self.files.append(fh)
             self.names.append(name + suffix)
-            return fh
+            self.by_block[block] = fh
 
-        self.names = []
-        if args.output_format == "fastq":
-            self.good = op("%s.qc.good.fastq" % output_name)
-            self.good_qual = None
-            self.bad = op("%s.qc.bad.fastq" % output_name)
-            self.bad_qual = None
-        else:
-            self.good = op("%s.qc.good.fasta" % output_name)
-            self.good_qual = op("%s.qc.good.qual" % output_name)
-            self.bad = op("%s.qc.bad.fasta" % output_name)
-            self.bad_qual = op("%s.qc.bad.qual" % output_name)
+        ext = "fastq" if args.output_format == "fastq" else "fasta"
+        op("%s.qc.good.%s" % (output_name, ext), L.BLOCK_GOOD)
+        if ext == "fasta":
+            op("%s.qc.good.qual" % output_name, L.BLOCK_GOOD_QUAL)
+        op("%s.qc.bad.%s" % (output_name, ext), L.BLOCK_BAD)
+        if ext == "fasta":
+            op("%s.qc.bad.qual" % output_name, L.BLOCK_BAD_QUAL)
         if args.collapse and args.pipeline == "mothur":
-            self.good_names = op("%s.qc.good.names" % output_name)
-            self.bad_names = op("%s.qc.bad.names" % output_name)
-        else:
-            self.good_names = self.bad_names = None
+            op("%s.qc.good.names" % output_name, L.BLOCK_GOOD_NAMES)
+            op("%s.qc.bad.names" % output_name, L.BLOCK_BAD_NAMES)
         if args.paired:                                                           # moira.py:366-368
-            self.report = op("%s.contigs.report" % output_name)
-            self.report.write("header\tn_seqs\toverlap_length\tgaps\tmismatches\n")
-        else:
-            self.report = None
+            op("%s.contigs.report" % output_name, L.BLOCK_REPORT)
+            self.by_block[L.BLOCK_REPORT].write(b"header\tn_seqs\toverlap_length\tgaps\tmismatches\n")
+
+    def write(self, blocks):
+        for which, fh in self.by_block.items():
+            blocks.write(which, fh)
 
     def close(self):
         for fh in self.files:
             fh.close()
 
 
-REASON_OVERLAP = 100   # host-side: "overlap length below" (moira.py:886-897); the device knows reasons 0..3
+def resolve_devices(args):
+    """--devices all | i,j,...  (one context and one host thread per GPU); --device i is the single-GPU spelling."""
+    spec = getattr(args, "devices", None)
+    if not spec:
+        return [args.device]
+    if spec == "all":
+        import ctypes
+        n = ctypes.c_int()
+        L.check(L.lib.moira_device_count(ctypes.byref(n)))
+        return list(range(max(1, n.value)))
+    return [int(x) for x in spec.split(",") if x != ""]
 
 
-def write_result(index, header, sequence, quals, expected_errors, names_info, accept, reason, args, w: Writers, contig_stats=None):
-    """One record, formatted as write_results does (moira.py:842-970); the accept/reason pair comes
-    from the device.  Returns (discarded_errors, discarded_minlength, discarded_minoverlap)."""
-    if args.relabel:
-        header = "%s%d" % (args.relabel, index)
-    if args.pipeline == "USEARCH":
-        header = header + ";ee=%.2f;size=%d;" % (expected_errors, len(names_info) if names_info else 1)
-    n_members = len(names_info) if names_info else 1
-    if w.report is not None and contig_stats is not None:                        # moira.py:866-870
-        w.report.write("%s\t%s\t%s\t%s\t%s\n" % ((header, n_members) + tuple(contig_stats)))
-        # the rules that sit between the length check and the error filter when contigs were built (moira.py:886-908)
-        if reason != L.REASON_LENGTH:
-            if args.min_overlap and contig_stats[0] < args.min_overlap:
-                accept, reason = False, REASON_OVERLAP
-            elif args.only_contig:
-                accept, reason = True, L.REASON_NONE
-    if accept:
-        out, out_q, out_n, note = w.good, w.good_qual, w.good_names, ""
+def reduce_run_counters(ctxs, per_ctx, out):
+    """The path's only collective: per-GPU counters -> their sum, by NCCL inside the library
+    (moira_reduce_counters_all) when the run used more than one GPU."""
+    if len(ctxs) == 1:
+        return per_ctx[0]
+    if len({c.device for c in ctxs}) < len(ctxs):       # several contexts on one GPU (tests): NCCL has one rank per GPU
+        return np.sum(per_ctx, axis=0).astype(np.uint64)
+    from .api import comm_init_all, reduce_counters_all
+    try:
+        comm_init_all(ctxs)
+        return reduce_counters_all(ctxs, [c.copy() for c in per_ctx])[0]
+    except MoiraError as exc:
+        if exc.code != L.ERR_NCCL:
+            raise
+        print("warning: NCCL is not available (%s); the %d counters were added on the host" % (exc.message, L.N_COUNTERS), file=out)
+        return np.sum(per_ctx, axis=0).astype(np.uint64)
+
+
+# ---- the three input flows --------------------------------------------------------------------------------------
+def run_fastq(args, ctxs, params, lower_n, out):
+    """Single-end FASTQ: the text is cut at record starts into one shard per GPU (contiguous chunks: concatenating the
+    shard outputs restores input order, moira.py:455-487); every shard goes through moira_filter_fastq_ex on its own
+    context and host thread -- text -> H2D -> parser, slab conversion, filter (and, with --collapse, the exact
+    dereplication) on the device, three chunks in flight per GPU."""
+    from .api import fastq_headers, fastq_split
+    text, keep = load_text(args.forward_fastq)
+    rs = ReadSet(args.fastq_offset)
+    rs.keep.append((text, keep))
+    D = len(ctxs)
+    cuts = fastq_split(text, D) if D > 1 and text.size else np.array([0, text.size], np.uint64)
+    want_labels = bool(args.collapse)
+    head = text[:1 << 20]
+    lines = int(np.count_nonzero(head == 10))
+    per_byte = (lines / 4.0) / max(1, head.size)
+
+    def work(i):
+        c0, c1 = int(cuts[i]), int(cuts[i + 1])
+        sub = text[c0:c1]
+        if sub.size == 0:
+            return None
+        est = int(per_byte * sub.size * 1.08) + 4096
+        labels = want_labels
+        for _attempt in range(3):
+            try:
+                return ctxs[i].filter_fastq_ex(sub, params, args.fastq_offset, max_reads=est, offsets=True, labels=labels)
+            except MoiraError as exc:
+                if "more than max_reads" in exc.message:
+                    est = None                                     # count the records, then once more
+                elif exc.code == L.ERR_NOMEM and labels:
+                    labels = False                                 # sequences do not fit on the device: dereplicate on the host
+                else:
+                    _raise_parse_error(exc, args.forward_fastq)
+        raise RuntimeError("could not size the outputs of shard %d" % i)
+
+    if D > 1:
+        with ThreadPoolExecutor(D) as pool:
+            results = list(pool.map(work, range(D)))
     else:
-        out, out_q, out_n = w.bad, w.bad_qual, w.bad_names
-        if reason == L.REASON_LENGTH:
-            note = "\tlength below %s" % args.truncate
-        elif reason == REASON_OVERLAP:                                            # the fastq branch prints --truncate (moira.py:888)
-            note = "\toverlap length below %s" % (args.truncate if args.output_format == "fastq" else args.min_overlap)
-        elif reason == L.REASON_AMBIGS:
-            note = "\tcontains ambiguities"
-        elif args.maxerrors:
-            note = "\terrors > %.2f" % args.maxerrors
+        results = [work(0)]
+    base_addr = _addr(text) if text.size else 0
+    read_base = 0
+    per_ctx = []
+    all_labelled = want_labels
+    for i, r in enumerate(results):
+        if r is None:
+            per_ctx.append(np.zeros(L.N_COUNTERS, np.uint64))
+            continue
+        c0 = np.uint64(int(cuts[i]))
+        n = int(r.lengths.shape[0])
+        seq_off, qual_off = r.seq_off + c0, r.qual_off + c0
+        hoff, hlen = fastq_headers(text, seq_off)
+        if r.labels is None:
+            all_labelled = False
+        rs.add(hdr_addr=hoff + np.uint64(base_addr), hdr_len=hlen, seq_addr=seq_off + np.uint64(base_addr),
+               qual_addr=qual_off + np.uint64(base_addr), length=r.lengths, ee=r.filter.ee, flags=r.filter.flags, stats=None,
+               labels=None if r.labels is None else r.labels + np.uint32(read_base))
+        per_ctx.append(r.filter.counters)
+        read_base += n
+    rs.finish()
+    if want_labels and not all_labelled:
+        rs.labels = None
+    rs.label_shards = D if (rs.labels is not None and D > 1) else 1
+    rs.counters = reduce_run_counters(ctxs, per_ctx, out)
+    return rs
+
+
+def _device_round_robin(ctxs, jobs, max_in_flight=2):
+    """Run job(ctx) for every job, job k on context k mod D (one host thread per GPU, at most max_in_flight jobs queued
+    per GPU), yielding the results in job order: the parser of the next batches overlaps the GPUs' work."""
+    D = len(ctxs)
+    pools = [ThreadPoolExecutor(1) for _ in range(D)]
+    pending = []
+    try:
+        for k, job in enumerate(jobs):
+            pending.append(pools[k % D].submit(job, ctxs[k % D]))
+            while len(pending) > max_in_flight * D:
+                yield pending.pop(0).result()
+        while pending:
+            yield pending.pop(0).result()
+    finally:
+        for p in pools:
+            p.shutdown(wait=True)
+
+
+def run_fasta_qual(args, ctxs, params, lower_n, out):
+    """Single-end FASTA + QUAL: whole-record blocks of both files -> native parser (all host threads) -> slab -> one
+    moira_filter_batch per block, blocks dealt round-robin to the GPUs."""
+    rs = ReadSet(0)
+    per_ctx = [np.zeros(L.N_COUNTERS, np.uint64) for _ in ctxs]
+
+    def jobs():
+        for k, (ftext, hoff, hlen, soff, qslab, slab, offsets, lengths) in enumerate(
+                read_fasta_qual_batches(open_input(args.forward_fasta), open_input(args.forward_qual), lower_n, args.forward_fasta,
+                                        args.forward_qual)):
+            def job(ctx, k=k, ftext=ftext, hoff=hoff, hlen=hlen, soff=soff, qslab=qslab, slab=slab, offsets=offsets, lengths=lengths):
+                res = ctx.filter_batch(slab, offsets, lengths, params)
+                return k, ftext, hoff, hlen, soff, qslab, offsets, lengths, res
+            yield job
+
+    for k, ftext, hoff, hlen, soff, qslab, offsets, lengths, res in _device_round_robin(ctxs, jobs()):
+        fa = _addr(ftext)
+        rs.keep.append((ftext, qslab))
+        rs.add(hdr_addr=hoff + np.uint64(fa), hdr_len=hlen, seq_addr=soff + np.uint64(fa), qual_addr=offsets + np.uint64(_addr(qslab)),
+               length=lengths, ee=res.ee, flags=res.flags, stats=None, labels=None)
+        per_ctx[k % len(ctxs)] += res.counters
+    rs.finish()
+    rs.label_shards = 1
+    rs.counters = reduce_run_counters(ctxs, per_ctx, out)
+    return rs
+
+
+def run_pairs(args, ctxs, params, lower_n, contig_params, out):
+    """Paired input: contigs and the filter on them in one call per block (process_data, moira.py:791-833), blocks dealt
+    round-robin to the GPUs; --only_contig skips the filter."""
+    from .api import FilterResult
+    rs = ReadSet(0)
+    per_ctx = [np.zeros(L.N_COUNTERS, np.uint64) for _ in ctxs]
+
+    def jobs():
+        for k, (ftext, hoff, hlen, fwd, rev) in enumerate(read_pair_batches(args, lower_n)):
+            def job(ctx, k=k, ftext=ftext, hoff=hoff, hlen=hlen, fwd=fwd, rev=rev):
+                pr = ctx.filter_pairs(fwd[0], fwd[1], fwd[2], fwd[4], rev[0], rev[1], rev[2], rev[4], contig_params,
+                                      None if args.only_contig else params, lower_n, fwd[3], rev[3], fwd[5])
+                return k, ftext, hoff, hlen, rev, pr
+            yield job
+
+    for k, ftext, hoff, hlen, rev, pr in _device_round_robin(ctxs, jobs()):
+        bad = np.flatnonzero(pr.status)
+        if bad.size:
+            r = int(bad[0])
+            st = int(pr.status[r])
+            header = ftext[int(hoff[r]):int(hoff[r]) + int(hlen[r])].decode("latin-1").replace(":", "_")
+            if st == L.PAIR_BAD_BASE:                                          # moira.py:1228-1229
+                seq = rev[0][int(rev[2][r]):int(rev[2][r]) + int(rev[4][r])].tobytes().decode("latin-1")
+                wrong = [c for c in seq if c not in "ACTGNWSRYMKBVDH-."]
+                raise ValueError('"%s" is not a recognizable IUPAC-coded base.' % (wrong[0] if wrong else "?"))
+            raise ValueError("Contig construction failed for %s (%s)" % (header, {
+                L.PAIR_EMPTY: "empty read", L.PAIR_BAD_QUALITY: "a quality score outside 0..252",
+                L.PAIR_TOO_LONG: "reverse read longer than 1024 bases"}.get(st, "status %d" % st)))
+        n = int(pr.contig_len.shape[0])
+        stride = int(pr.contig_seq.shape[1]) if n else 16
+        if pr.filter is None:                                                  # expected_errors = 0 (moira.py:809-810)
+            res = FilterResult(np.zeros(n), np.zeros(n, np.int32), np.full(n, L.FLAG_ACCEPT, np.uint8), np.zeros(L.N_COUNTERS, np.uint64))
+            if args.truncate:
+                res.flags[pr.contig_len < args.truncate] = L.REASON_LENGTH << 1
         else:
-            note = "\tuncert > %.3f" % args.uncert
-    if args.output_format == "fastq":
-        out.write("@%s%s\n%s\n+\n%s\n" % (header, note, sequence, "".join(chr(int(q) + args.fastq_offset) for q in quals)))
+            res = pr.filter
+        fa = _addr(ftext)
+        rows = np.arange(n, dtype=np.uint64) * np.uint64(stride)
+        rs.keep.append((ftext, pr))
+        rs.add(hdr_addr=hoff + np.uint64(fa), hdr_len=hlen, seq_addr=rows + np.uint64(_addr(pr.contig_seq)),
+               qual_addr=rows + np.uint64(_addr(pr.contig_qual)), length=pr.contig_len, ee=res.ee, flags=res.flags,
+               stats=np.stack([pr.overlap, pr.gaps, pr.mismatches], axis=1), labels=None)
+        per_ctx[k % len(ctxs)] += res.counters
+    rs.finish()
+    rs.label_shards = 1
+    rs.counters = reduce_run_counters(ctxs, per_ctx, out)
+    return rs
+
+
+# ---- decisions -> groups -> files (moira.py:455-519, 842-970) ----------------------------------------------------
+def _string_at(addr, n):
+    import ctypes
+    return ctypes.string_at(int(addr), int(n)).decode("latin-1")
+
+
+def finish_run(args, rs, writers, out):
+    """The collapse dictionary, the abundance sort, write_results' precedence of rules and the final counts -- on arrays;
+    formatting is moira_format_records (native, all host threads).  Returns (processed, errors, minlength, minoverlap)."""
+    from .api import RecordView, collapse_labels, format_records
+    n = rs.n
+    if n == 0:
+        return 0, 0, 0, 0
+    numeric = (rs.flags & L.FLAG_NUMERIC) != 0
+    if numeric.any() or np.isnan(rs.ee).any():                                   # moira.py:456-457
+        bad = int(np.flatnonzero(numeric | np.isnan(rs.ee))[0])
+        raise ReturnedNaNError("Error calculation failed for sequence %s" % _string_at(rs.hdr_addr[bad], rs.hdr_len[bad]).replace(":", "_"))
+    accept = (rs.flags & L.FLAG_ACCEPT).astype(np.uint8)
+    reason = ((rs.flags & L.FLAG_REASON_MASK) >> 1).astype(np.uint8)
+    out_len = np.minimum(rs.length, np.uint32(args.truncate)) if args.truncate else rs.length           # moira.py:806-807
+    # the rules between the length check and the error filter (moira.py:886-908): min_overlap (overlap_length is 0 for
+    # reads that were not assembled, as in the reference), then only_contig
+    not_short = reason != L.REASON_LENGTH
+    if args.min_overlap:
+        ov = rs.stats[:, 0] if rs.stats is not None else np.zeros(n, np.int32)
+        low = not_short & (ov < args.min_overlap)
+        accept[low], reason[low] = 0, REASON_OVERLAP
+        not_short &= ~low
+    if args.only_contig:
+        accept[not_short], reason[not_short] = 1, L.REASON_NONE
+    notes = {L.REASON_ERRORS: ("\terrors > %.2f" % args.maxerrors) if args.maxerrors else ("\tuncert > %.3f" % args.uncert),
+             L.REASON_LENGTH: "\tlength below %s" % args.truncate, L.REASON_AMBIGS: "\tcontains ambiguities",
+             REASON_OVERLAP: "\toverlap length below %s" % (args.truncate if args.output_format == "fastq" else args.min_overlap)}
+    rec = RecordView(None, rs.hdr_addr, rs.hdr_len, None, rs.seq_addr, None, rs.qual_addr, out_len, rs.qual_sub)
+    stats = None if rs.stats is None else (rs.stats[:, 0], rs.stats[:, 1], rs.stats[:, 2])
+    common = dict(fastq=args.output_format == "fastq", fastq_offset=args.fastq_offset, usearch=args.pipeline == "USEARCH",
+                  relabel=args.relabel, notes=notes, stats=stats)
+    CHUNK = 1 << 20
+    if args.collapse:
+        # moira.py:459-475 + 491-504: groups by first appearance, representative = first read with the strictly smallest
+        # ee, names in the reference's order, output by abundance
+        labels = rs.labels
+        if labels is not None and rs.label_shards > 1:
+            # every GPU dereplicated its own shard exactly; sequences that span shards meet here: only the shards' owner
+            # reads (one per distinct sequence and shard) are compared on the host
+            owners = np.flatnonzero(labels == np.arange(n, dtype=np.uint32))
+            oc = collapse(None, rs.seq_addr[owners], out_len[owners], np.zeros(owners.size))
+            lut = np.arange(n, dtype=np.uint32)
+            lut[owners] = owners[oc.rep[oc.group_of_read]].astype(np.uint32)
+            labels = lut[labels]
+        col = collapse_labels(labels, rs.ee) if labels is not None else collapse(None, rs.seq_addr, out_len, rs.ee)
+        sel, sel_group = col.rep[col.order], col.order
+        sizes = col.size[col.order].astype(np.int64)
+        for k0 in range(0, sel.size, CHUNK):
+            k1 = min(sel.size, k0 + CHUNK)
+            blocks = format_records(rec, sel[k0:k1], rs.ee, accept, reason, names=args.pipeline == "mothur", first_index=1 + k0,
+                                    sel_group=sel_group[k0:k1], member_start=col.member_start, members=col.members, **common)
+            writers.write(blocks)
+            blocks.close()
+        acc_s, rsn_s = accept[sel], reason[sel]
     else:
-        out.write(">%s%s\n%s\n" % (header, note, sequence))
-        out_q.write(">%s%s\n%s\n" % (header, note, " ".join(str(int(q)) for q in quals)))
-    if args.collapse and args.pipeline == "mothur" and out_n is not None:
-        out_n.write("%s\t%s\n" % (header, ",".join(names_info)))
-    if accept:
-        return 0, 0, 0
-    if reason == L.REASON_LENGTH:
-        return 0, n_members, 0
-    return (0, 0, n_members) if reason == REASON_OVERLAP else (n_members, 0, 0)
+        for k0 in range(0, n, CHUNK):
+            k1 = min(n, k0 + CHUNK)
+            blocks = format_records(rec, np.arange(k0, k1, dtype=np.uint64), rs.ee, accept, reason, first_index=k0, **common)
+            writers.write(blocks)
+            blocks.close()
+        acc_s, rsn_s, sizes = accept, reason, np.ones(n, np.int64)
+    rej = acc_s == 0
+    minlength = int(sizes[rej & (rsn_s == L.REASON_LENGTH)].sum())
+    minoverlap = int(sizes[rej & (rsn_s == REASON_OVERLAP)].sum())
+    errors = int(sizes[rej].sum()) - minlength - minoverlap
+    return n, errors, minlength, minoverlap
 
 
 # ---- main (moira.py:264-578) ---------------------------------------------------------------------------
@@ -497,121 +757,39 @@ def main(args, out=sys.stdout) -> int:
                           ambigs=args.ambigs, round=args.round, truncate=args.truncate,
                           exact_ee=bool(args.collapse) or args.pipeline == "USEARCH", ee_output="final")
     lower_n = args.error_calc == "poisson_binomial"      # bernoullimodule.c:196 vs moira.py:1605/1660
-
     contig_params = ContigParams(match=args.match, mismatch=args.mismatch, gap=args.gap, insert=args.insert, deltaq=args.deltaq,
                                  consensus_qscore=args.consensus_qscore, qscore_cap=args.qscore_cap, trim_overlap=args.trim_overlap)
     try:
+        inputs = [args.forward_fastq] if args.forward_fastq else [args.forward_fasta, args.forward_qual]
         if args.paired:
-            batches = read_pair_batches(args, lower_n)
-        elif args.forward_fastq:
-            batches = read_fastq_batches(open_input(args.forward_fastq), args.fastq_offset, lower_n, args.forward_fastq)
-        else:
-            batches = read_fasta_qual_batches(open_input(args.forward_fasta), open_input(args.forward_qual), lower_n,
-                                              args.forward_fasta, args.forward_qual)
+            inputs += [args.reverse_fastq] if args.forward_fastq else [args.reverse_fasta, args.reverse_qual]
+        for name in inputs:
+            io.open(name, "rb").close()
         writers = Writers(args, output_name)
     except IOError as exc:
         print(exc, file=out)
         return 1
 
-    ctx = Context(args.device)
-
-    def results():
-        """(headers, sequences, qualities, ee, accept, reason, contig statistics or None) per batch."""
-        if not args.paired:
-            for headers, seqs, quals, slab, offsets, lengths in batches:
-                res = ctx.filter_batch(slab, offsets, lengths, params)
-                yield headers, seqs, quals, res, None
-            return
-        for headers, fwd, rev in batches:
-            # contigs and the filter on them in one call (process_data, moira.py:791-833); --only_contig skips the filter
-            pr = ctx.filter_pairs(fwd[0], fwd[1], fwd[2], fwd[4], rev[0], rev[1], rev[2], rev[4], contig_params,
-                                  None if args.only_contig else params, lower_n, fwd[3], rev[3], fwd[5])
-            bad = np.flatnonzero(pr.status)
-            if bad.size:
-                r = int(bad[0])
-                st = int(pr.status[r])
-                if st == L.PAIR_BAD_BASE:                                          # moira.py:1228-1229
-                    seq = rev[0][int(rev[2][r]):int(rev[2][r]) + int(rev[4][r])].tobytes().decode("latin-1")
-                    wrong = [c for c in seq if c not in "ACTGNWSRYMKBVDH-."]
-                    raise ValueError('"%s" is not a recognizable IUPAC-coded base.' % (wrong[0] if wrong else "?"))
-                raise ValueError("Contig construction failed for %s (%s)" % (headers[r], {
-                    L.PAIR_EMPTY: "empty read", L.PAIR_BAD_QUALITY: "a quality score outside 0..252",
-                    L.PAIR_TOO_LONG: "reverse read longer than 1024 bases"}.get(st, "status %d" % st)))
-            seqs, quals = [], []
-            for r in range(len(headers)):
-                c, q = pr.contig(r)
-                seqs.append(c)
-                quals.append(np.maximum(np.asarray(q, dtype=np.int32), 1))         # moira.py:814
-            if pr.filter is None:                                                  # expected_errors = 0 (moira.py:809-810)
-                n = len(headers)
-                from .api import FilterResult
-                res = FilterResult(np.zeros(n), np.zeros(n, np.int32), np.full(n, L.FLAG_ACCEPT, np.uint8), np.zeros(L.N_COUNTERS, np.uint64))
-                if args.truncate:
-                    short = pr.contig_len < args.truncate
-                    res.flags[short] = L.REASON_LENGTH << 1
-            else:
-                res = pr.filter
-            yield headers, seqs, quals, res, np.stack([pr.overlap, pr.gaps, pr.mismatches], axis=1)
-
-    processed = 0
-    discarded_errors = discarded_minlength = discarded_minoverlap = 0
-    all_headers, all_seqs, all_quals, all_ee, all_acc, all_rsn, all_stats = [], [], [], [], [], [], []   # --collapse: kept for the epilogue
     t0 = time.time()
+    ctxs = []
     try:
-        for headers, seqs, quals, res, stats in results():
-            if np.isnan(res.ee).any() or res.numeric.any():
-                bad = int(np.flatnonzero(np.isnan(res.ee) | res.numeric)[0])
-                raise ReturnedNaNError("Error calculation failed for sequence %s" % headers[bad])
-            accept = res.accept
-            reason = res.reason
-            if args.truncate:                                                      # moira.py:806-807
-                seqs = [s_[:args.truncate] for s_ in seqs]
-                quals = [q_[:args.truncate] for q_ in quals]
-            if args.collapse:
-                all_headers += headers
-                all_seqs += seqs
-                all_quals += quals
-                all_ee.append(res.ee.copy())
-                all_acc.append(accept.copy())
-                all_rsn.append(reason.copy())
-                if stats is not None:
-                    all_stats.append(stats)
-                processed += len(headers)
-            else:
-                for i, header in enumerate(headers):
-                    de, dl, do = write_result(processed, header, seqs[i], quals[i], float(res.ee[i]), None, bool(accept[i]),
-                                              int(reason[i]), args, writers, None if stats is None else stats[i].tolist())
-                    discarded_errors += de
-                    discarded_minlength += dl
-                    discarded_minoverlap += do
-                    processed += 1
-            if not args.silent:
-                print("%d sequences processed in %.1f seconds.\r" % (processed, time.time() - t0), end="", file=out)
-        if args.collapse and processed:
-            # moira.py:459-475 + 491-504, natively: groups by first appearance, representative = first read
-            # with the strictly smallest ee, names in the reference's order, output by abundance
-            ee_all = np.concatenate(all_ee)
-            acc_all = np.concatenate(all_acc)
-            rsn_all = np.concatenate(all_rsn)
-            stats_all = np.concatenate(all_stats) if all_stats else None
-            seq_len = np.fromiter((len(s_) for s_ in all_seqs), dtype=np.uint32, count=processed)
-            seq_off = np.zeros(processed, dtype=np.uint64)
-            seq_off[1:] = np.cumsum(seq_len[:-1], dtype=np.uint64)
-            col = collapse("".join(all_seqs).encode("latin-1"), seq_off, seq_len, ee_all)
-            for index, g in enumerate(col.order.tolist(), start=1):
-                rep = int(col.rep[g])
-                names = [all_headers[r] for r in col.members[int(col.member_start[g]):int(col.member_start[g + 1])].tolist()]
-                de, dl, do = write_result(index, all_headers[rep], all_seqs[rep], all_quals[rep], float(ee_all[rep]), names,
-                                          bool(acc_all[rep]), int(rsn_all[rep]), args, writers,
-                                          None if stats_all is None else stats_all[rep].tolist())
-                discarded_errors += de
-                discarded_minlength += dl
-                discarded_minoverlap += do
+        ctxs = [Context(d) for d in resolve_devices(args)]
+        if args.paired:
+            rs = run_pairs(args, ctxs, params, lower_n, contig_params, out)
+        elif args.forward_fastq:
+            rs = run_fastq(args, ctxs, params, lower_n, out)
+        else:
+            rs = run_fasta_qual(args, ctxs, params, lower_n, out)
+        t_filter = time.time() - t0
+        processed, discarded_errors, discarded_minlength, discarded_minoverlap = finish_run(args, rs, writers, out)
     finally:
         writers.close()
-        ctx.close()
+        for c in ctxs:
+            c.close()
 
     if not args.silent and processed:
+        print("%d sequences processed in %.1f seconds (%.1f s to the decisions, %d GPU%s)." %
+              (processed, time.time() - t0, t_filter, len(ctxs), "" if len(ctxs) == 1 else "s"), file=out)
         remaining = processed - discarded_errors - discarded_minlength - discarded_minoverlap
         print("\n- Kept %d (%.2f%%) of the original sequences." % (remaining, remaining / processed * 100), file=out)
         if args.truncate:
@@ -622,6 +800,12 @@ def main(args, out=sys.stdout) -> int:
                   (discarded_minoverlap, discarded_minoverlap / processed * 100, args.min_overlap), file=out)
         print("- %d (%.2f%%) of the original sequences were discarded due to low quality.\n" %
               (discarded_errors, discarded_errors / processed * 100), file=out)
+        if not args.collapse:
+            c = rs.counters
+            print("- device counters, summed over %d GPU%s: %d reads, %d accepted, %d rejected for errors, %d for length, %d for "
+                  "ambiguities, %d within 1e-12 of the cutoff." % (len(ctxs), "" if len(ctxs) == 1 else "s", int(c[L.CNT_READS]),
+                  int(c[L.CNT_ACCEPTED]), int(c[L.CNT_BAD_ERRORS]), int(c[L.CNT_BAD_LENGTH]), int(c[L.CNT_BAD_AMBIGS]),
+                  int(c[L.CNT_NEAR_CUTOFF])), file=out)
         print("The following output files were generated:", file=out)
         for name in writers.names:
             print(name, file=out)

@@ -179,6 +179,8 @@ struct moira_ctx {
     cudaEvent_t ct0[MAX_TIMED] = {}, ct1[MAX_TIMED] = {};   // around the contig kernel launches when timing is on
     int n_ctimed = 0;
     CommState *comm = nullptr;   // communicator rank for the counters' all-reduce (moira_comm.cpp), created on demand
+    // dereplication on the device (moira_dedup.cu): hashes, table, labels; the FASTQ path's sequence store and its index
+    DevBuf dd_hash, dd_table, dd_labels, dd_store, dd_seq_abs, dd_seq_eff;
     // single-read scratch (pinned)
     uint8_t *one_slab = nullptr;
     size_t one_cap = 0;
@@ -334,6 +336,27 @@ bool make_slab_tmap(CUtensorMap *tm, const uint8_t *d_rows, uint64_t stride, uin
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// labels of reads [0, n) (see moira_dedup.cu) into d_labels, enqueued on `stream`
+int run_dedup(moira_ctx *c, const uint8_t *d_seq, const uint64_t *d_off, const uint32_t *d_len, uint64_t stride, uint32_t fixed_len,
+              uint64_t n, uint32_t truncate, uint32_t *d_labels, cudaStream_t stream)
+{
+    if (n == 0) return MOIRA_OK;
+    if (n >= 0xFFFFFFF0ull) return fail(MOIRA_ERR_BAD_ARG, "more than 2^32 reads in one dereplication");
+    uint64_t slots = 1024;
+    while (slots < 2 * n) slots <<= 1;
+    int rc;
+    if ((rc = ensure(c->dd_hash, n * 16)) || (rc = ensure(c->dd_table, slots * 4))) return rc;
+    CU(cudaMemsetAsync(c->dd_table.p, 0xFF, slots * 4, stream));
+    DedupArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seq = d_seq; a.off = d_off; a.len = d_len; a.stride = stride; a.fixed_len = fixed_len; a.truncate = truncate; a.base = 0; a.n = n;
+    LaunchCfg cfg{c->sm_count, stream};
+    if (launch_dedup(a, (uint64_t *)c->dd_hash.p, (uint32_t *)c->dd_table.p, (uint32_t)(slots - 1), d_labels, cfg))
+        return fail(MOIRA_ERR_CUDA, "dereplication launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    c->launches += 2;
+    return MOIRA_OK;
+}
+
 int first_pass_k_template(int k_wanted)
 {
     for (int i = 0; i < N_FIRST_K; i++) if (k_wanted <= first_pass_k(i)) return first_pass_k(i);
@@ -396,6 +419,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
     // fraction on the device, and the two candidate launches for the rest read that verdict (no host synchronisation).
     const bool cascade_ok = p->mode == MOIRA_MODE_PB && k_decides_all && k_first >= 3 && k_first <= 8 && p->cascade != 2 && c->cascade;
     const bool queues_needed = ladder || cascade_ok;
+    if (cascade_ok) a.min_rung = 1;   // what a two-entry sweep hands on may need as few as three entries
 
     const uint64_t sub = ladder ? SUB_BATCH : cascade_ok ? (1ull << 26) : (1ull << 31);
     for (uint64_t start = 0; start < n_reads; start += sub) {
@@ -606,7 +630,9 @@ int moira_ctx_destroy(moira_ctx *c)
         for (DevBuf *b : pb.all) if (b->p) cudaFree(b->p);
         if (pb.stage) cudaFreeHost(pb.stage);
     }
-    for (DevBuf *b : {&c->trace, &c->hbuf, &c->post, &c->pair_counters}) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : {&c->trace, &c->hbuf, &c->post, &c->pair_counters, &c->dd_hash, &c->dd_table, &c->dd_labels, &c->dd_store,
+                      &c->dd_seq_abs, &c->dd_seq_eff})
+        if (b->p) cudaFree(b->p);
     for (auto &w : c->ws) {
         if (w.queues) cudaFree(w.queues);
         if (w.counts) cudaFree(w.counts);
@@ -628,6 +654,15 @@ int moira_ctx_destroy(moira_ctx *c)
     cudaFree(c->d_p); cudaFree(c->d_q); cudaFree(c->d_e); cudaFree(c->d_sink);
     cudaGetLastError();
     delete c;
+    return MOIRA_OK;
+}
+
+int moira_device_count(int *out)
+{
+    if (!out) return fail(MOIRA_ERR_BAD_ARG, "out is NULL");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *out = n;
     return MOIRA_OK;
 }
 
@@ -687,6 +722,14 @@ int moira_filter_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_o
     CU(cudaSetDevice(c->device));
     return run_filter_full(c, c->ws[2], d_slab, d_offsets, d_lengths, stride, fixed_length, n_reads, params, params->max_length,
                            params->min_length, d_ee, d_ns, d_flags, d_counters, (cudaStream_t)stream, d_row_marks);
+}
+
+int moira_collapse_device(moira_ctx *c, const uint8_t *d_seq, const uint64_t *d_offsets, const uint32_t *d_lengths, uint64_t stride,
+                          uint32_t fixed_length, uint64_t n_reads, uint32_t truncate, uint32_t *d_labels, void *stream)
+{
+    if (!c || !d_seq || !d_labels) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    return run_dedup(c, d_seq, d_offsets, d_lengths, stride, fixed_length, n_reads, truncate, d_labels, (cudaStream_t)stream);
 }
 
 int moira_count_marks_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_offsets, const uint32_t *d_lengths,
@@ -907,11 +950,20 @@ constexpr int FQ_RETRY_COUNTED = 0x7fff0001;   // internal: a guessed chunk cut 
 
 int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int fastq_offset, int lower_n, const moira_params *params,
                         uint64_t max_reads, double *ee_out, int32_t *ns_out, uint8_t *flags_out, uint32_t *lengths_out,
+                        uint64_t *seq_off_out, uint64_t *qual_off_out, uint32_t *labels_out,
                         uint64_t *counters_out, uint64_t *n_reads_out, bool guess_cuts)
 {
     constexpr uint64_t RANGE = 64ull << 20;
     int rc;
     if ((rc = ensure(c->fq_counters, MOIRA_N_COUNTERS * 8))) return rc;
+    const bool want_off = seq_off_out || qual_off_out;
+    if (labels_out) {
+        // --collapse on the device: the (truncated) sequences stay in HBM at their own text offsets until the last chunk is in
+        if (text_bytes > (96ull << 30)) return fail(MOIRA_ERR_NOMEM, "text too large to keep its sequences on the device (%llu bytes)", (unsigned long long)text_bytes);
+        if ((rc = ensure(c->dd_store, text_bytes + 64)) || (rc = ensure(c->dd_seq_abs, max_reads * 8 + 8)) ||
+            (rc = ensure(c->dd_seq_eff, max_reads * 4 + 4)) || (rc = ensure(c->dd_labels, max_reads * 4 + 4)))
+            return rc;
+    }
     uint64_t *d_cnt = (uint64_t *)c->fq_counters.p;
     CU(cudaMemsetAsync(d_cnt, 0, MOIRA_N_COUNTERS * 8, c->streams[0]));
     CU(cudaEventRecord(c->meta_ready, c->streams[0]));
@@ -939,7 +991,7 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         {
             int r0;
             if ((r0 = ensure(q.ee, q.n_rec * 8)) || (r0 = ensure(q.ns, q.n_rec * 4)) || (r0 = ensure(q.flags, q.n_rec)) ||
-                (r0 = ensure_pinned(&q.h_res, &q.h_res_cap, q.n_rec * 17 + 64)))
+                (r0 = ensure_pinned(&q.h_res, &q.h_res_cap, q.n_rec * 25 + 64)))
                 return r0;
         }
         const uint32_t maxlen = q.h_meta[0], minlen = q.h_meta[1], bad = q.h_meta[2];
@@ -963,7 +1015,9 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         if ((r = ensure(q.slab, (size_t)q.n_rec * stride + 256)) || (r = ensure(q.marks, q.n_rec * 4))) return r;
         if (launch_fq_convert((const uint8_t *)q.text.p, (const uint32_t *)q.soff.p, (const uint32_t *)q.qoff.p, (const uint32_t *)q.len.p,
                               (uint32_t)q.n_rec, stride, lower_n, fastq_offset, (uint8_t *)q.slab.p, (uint32_t *)q.meta.p,
-                              (uint32_t *)q.marks.p, params->truncate, c->sm_count, s))
+                              (uint32_t *)q.marks.p, params->truncate, c->sm_count, s, labels_out ? (uint8_t *)c->dd_store.p : nullptr,
+                              q.pos - q.skip, labels_out ? (uint64_t *)c->dd_seq_abs.p + q.first_read : nullptr,
+                              labels_out ? (uint32_t *)c->dd_seq_eff.p + q.first_read : nullptr))
             return fail(MOIRA_ERR_CUDA, "fastq convert launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         c->launches++;
         const bool same = minlen == maxlen;
@@ -976,6 +1030,10 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         CU(cudaMemcpyAsync(q.h_res + m * 8, q.ns.p, m * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(q.h_res + m * 12, q.len.p, m * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(q.h_res + m * 16, q.flags.p, m, cudaMemcpyDeviceToHost, s));
+        if (want_off) {
+            CU(cudaMemcpyAsync(q.h_res + m * 17, q.soff.p, m * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(q.h_res + m * 21, q.qoff.p, m * 4, cudaMemcpyDeviceToHost, s));
+        }
         CU(cudaMemcpyAsync(q.h_meta, q.meta.p, 12, cudaMemcpyDeviceToHost, s));     // a quality above 252 shows up here (words 0..2 only)
         CU(cudaEventRecord(q.ev, s));
         q.state = 2;
@@ -992,6 +1050,17 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         if (ns_out) memcpy(ns_out + at, q.h_res + m * 8, m * 4);
         if (lengths_out) memcpy(lengths_out + at, q.h_res + m * 12, m * 4);
         if (flags_out) memcpy(flags_out + at, q.h_res + m * 16, m);
+        if (want_off) {   // chunk-relative 32-bit offsets -> positions in the caller's text
+            const uint64_t base = q.pos - q.skip;
+            const uint8_t *so = q.h_res + m * 17, *qo = q.h_res + m * 21;
+            for (uint64_t i = 0; i < m; i++) {
+                uint32_t a32, b32;
+                memcpy(&a32, so + 4 * i, 4);
+                memcpy(&b32, qo + 4 * i, 4);
+                if (seq_off_out) seq_off_out[at + i] = base + a32;
+                if (qual_off_out) qual_off_out[at + i] = base + b32;
+            }
+        }
         q.state = 0;
         return MOIRA_OK;
     };
@@ -1140,6 +1209,15 @@ int filter_fastq_device(moira_ctx *c, const char *text, uint64_t text_bytes, int
         CU(cudaMemcpy(counters_out, d_cnt, MOIRA_N_COUNTERS * 8, cudaMemcpyDeviceToHost));
         note_escalations(c, params, counters_out);
     }
+    if (labels_out && n_assigned) {
+        // every chunk has left its sequences in the store: one exact dereplication over all of them
+        CU(cudaStreamSynchronize(c->streams[1]));
+        if ((rc = run_dedup(c, (const uint8_t *)c->dd_store.p, (const uint64_t *)c->dd_seq_abs.p, (const uint32_t *)c->dd_seq_eff.p, 0, 0,
+                            n_assigned, 0, (uint32_t *)c->dd_labels.p, c->streams[0])))
+            return rc;
+        CU(cudaMemcpyAsync(labels_out, c->dd_labels.p, n_assigned * 4, cudaMemcpyDeviceToHost, c->streams[0]));
+        CU(cudaStreamSynchronize(c->streams[0]));
+    }
     *n_reads_out = n_assigned;
     return MOIRA_OK;
 }
@@ -1153,7 +1231,18 @@ int moira_filter_fastq(moira_ctx *c, const char *text, uint64_t text_bytes, int 
                        const moira_params *params, uint64_t max_reads, double *ee_out, int32_t *ns_out,
                        uint8_t *flags_out, uint32_t *lengths_out, uint64_t *counters_out, uint64_t *n_reads_out)
 {
+    return moira_filter_fastq_ex(c, text, text_bytes, fastq_offset, lower_n_ambiguous, params, max_reads, ee_out, ns_out, flags_out,
+                                 lengths_out, nullptr, nullptr, nullptr, counters_out, n_reads_out);
+}
+
+int moira_filter_fastq_ex(moira_ctx *c, const char *text, uint64_t text_bytes, int fastq_offset, int lower_n_ambiguous,
+                          const moira_params *params, uint64_t max_reads, double *ee_out, int32_t *ns_out,
+                          uint8_t *flags_out, uint32_t *lengths_out, uint64_t *seq_off_out, uint64_t *qual_off_out,
+                          uint32_t *labels_out, uint64_t *counters_out, uint64_t *n_reads_out)
+{
     if (!c || (!text && text_bytes) || !ee_out || !n_reads_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    if ((seq_off_out || qual_off_out || labels_out) && !c->device_parse)
+        return fail(MOIRA_ERR_BAD_ARG, "record offsets / labels need the device parser (MOIRA_B200_HOST_PARSE is set)");
     int rc = check_params(params);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
@@ -1162,10 +1251,10 @@ int moira_filter_fastq(moira_ctx *c, const char *text, uint64_t text_bytes, int 
         // first with chunk cuts guessed from the text's local structure (no host pass over the text); if the device
         // finds a chunk that does not hold whole records, once more with the cuts counted on the host
         rc = filter_fastq_device(c, text, text_bytes, fastq_offset, lower_n_ambiguous, params, max_reads, ee_out, ns_out, flags_out,
-                                 lengths_out, counters_out, n_reads_out, c->fq_guess_cuts != 0);
+                                 lengths_out, seq_off_out, qual_off_out, labels_out, counters_out, n_reads_out, c->fq_guess_cuts != 0);
         if (rc == FQ_RETRY_COUNTED)
             rc = filter_fastq_device(c, text, text_bytes, fastq_offset, lower_n_ambiguous, params, max_reads, ee_out, ns_out, flags_out,
-                                     lengths_out, counters_out, n_reads_out, false);
+                                     lengths_out, seq_off_out, qual_off_out, labels_out, counters_out, n_reads_out, false);
         return rc;
     }
     constexpr int SLOTS = 3;

@@ -65,9 +65,10 @@ extern "C" int moira_collapse(const char *text, const uint64_t *seq_off, const u
                               uint64_t *group_rep, uint64_t *group_size, uint64_t *member_start, uint64_t *members,
                               uint64_t *abundance_order)
 {
-    if ((n && (!text || !seq_off || !seq_len || !ee || !group_of_read || !group_rep || !group_size || !member_start || !members ||
+    if ((n && (!seq_off || !seq_len || !ee || !group_of_read || !group_rep || !group_size || !member_start || !members ||
                !abundance_order)) || !n_groups_out)
         return moira::fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    // text == NULL: seq_off holds absolute addresses (sequences spread over several buffers)
     int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     if (T < 1) T = 1;
     if (T > 64) T = 64;
@@ -77,7 +78,7 @@ extern "C" int moira_collapse(const char *text, const uint64_t *seq_off, const u
         const int parts = T * 4;
         parallel_for(parts, T, [&](int p) {
             for (uint64_t r = n * (uint64_t)p / parts, e = n * (uint64_t)(p + 1) / parts; r < e; r++)
-                hash[r] = hash_bytes(text + seq_off[r], seq_len[r]);
+                hash[r] = hash_bytes((const char *)((uintptr_t)text + seq_off[r]), seq_len[r]);
         });
     }
     // stable counting sort of read indices by the top 8 hash bits
@@ -109,7 +110,7 @@ extern "C" int moira_collapse(const char *text, const uint64_t *seq_off, const u
                     break;
                 }
                 const uint64_t f = groups[gi].first;
-                if (hash[f] == h && seq_len[f] == seq_len[r] && memcmp(text + seq_off[f], text + seq_off[r], seq_len[r]) == 0) {
+                if (hash[f] == h && seq_len[f] == seq_len[r] && memcmp((const char *)((uintptr_t)text + seq_off[f]), (const char *)((uintptr_t)text + seq_off[r]), seq_len[r]) == 0) {
                     groups[gi].members.push_back(r);
                     break;
                 }
@@ -154,6 +155,56 @@ extern "C" int moira_collapse(const char *text, const uint64_t *seq_off, const u
                 for (uint64_t r : m) group_of_read[r] = g;
             }
         });
+    }
+    for (uint64_t g = 0; g < G; g++) abundance_order[g] = g;
+    std::stable_sort(abundance_order, abundance_order + G, [&](uint64_t x, uint64_t y) { return group_size[x] > group_size[y]; });
+    return MOIRA_OK;
+}
+
+// The same outputs from labels (equal label <=> equal sequence, label < n) -- the labels come from the device-side
+// dereplication (moira_dedup.cu), so no base is looked at here: three linear passes over the reads in input order,
+// which is exactly the order the reference's dictionary sees them in (moira.py:455-475).
+extern "C" int moira_collapse_labels(const uint32_t *labels, const double *ee, uint64_t n, uint64_t *group_of_read, uint64_t *n_groups_out,
+                                     uint64_t *group_rep, uint64_t *group_size, uint64_t *member_start, uint64_t *members,
+                                     uint64_t *abundance_order)
+{
+    if ((n && (!labels || !ee || !group_of_read || !group_rep || !group_size || !member_start || !members || !abundance_order)) ||
+        !n_groups_out)
+        return moira::fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    constexpr uint64_t NONE = ~0ull;
+    std::vector<uint64_t> gid(n, NONE);       // by label
+    uint64_t G = 0;
+    for (uint64_t r = 0; r < n; r++) {        // groups in order of first appearance
+        const uint32_t l = labels[r];
+        if (l >= n) return moira::fail(MOIRA_ERR_BAD_ARG, "label %u of read %llu is not a read index", l, (unsigned long long)r);
+        uint64_t g = gid[l];
+        if (g == NONE) { g = G++; gid[l] = g; group_size[g] = 0; group_rep[g] = r; }
+        group_of_read[r] = g;
+        group_size[g]++;
+    }
+    *n_groups_out = G;
+    // representative = first read with the strictly smallest ee (:466); count the record breakers on the way
+    std::vector<uint32_t> breakers(G, 0);
+    {
+        std::vector<uint8_t> seen(G, 0);
+        for (uint64_t r = 0; r < n; r++) {
+            const uint64_t g = group_of_read[r];
+            if (!seen[g]) { seen[g] = 1; group_rep[g] = r; breakers[g] = 1; }
+            else if (ee[r] < ee[group_rep[g]]) { group_rep[g] = r; breakers[g]++; }
+        }
+    }
+    uint64_t pos = 0;
+    for (uint64_t g = 0; g < G; g++) { member_start[g] = pos; pos += group_size[g]; }
+    if (n) member_start[G] = pos;
+    // names order (:470-475): every new representative goes to the FRONT, every other read to the back
+    {
+        std::vector<uint64_t> front(G), back(G), cur(G, NONE);
+        for (uint64_t g = 0; g < G; g++) { front[g] = member_start[g] + breakers[g]; back[g] = front[g]; }
+        for (uint64_t r = 0; r < n; r++) {
+            const uint64_t g = group_of_read[r];
+            if (cur[g] == NONE || ee[r] < ee[cur[g]]) { cur[g] = r; members[--front[g]] = r; }
+            else members[back[g]++] = r;
+        }
     }
     for (uint64_t g = 0; g < G; g++) abundance_order[g] = g;
     std::stable_sort(abundance_order, abundance_order + G, [&](uint64_t x, uint64_t y) { return group_size[x] > group_size[y]; });

@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256) fq_records(const uint8_t *text, uint64_t 
 
 __global__ void __launch_bounds__(256) fq_convert(const uint8_t *text, const uint32_t *seq_off, const uint32_t *qual_off,
                                                   const uint32_t *len, uint32_t n_rec, uint32_t stride, int lower_n, int qbase,
-                                                  uint8_t *slab, uint32_t *meta, uint32_t *marks, uint32_t truncate)
+                                                  uint8_t *slab, uint32_t *meta, uint32_t *marks, uint32_t truncate,
+                                                  uint8_t *seq_store, uint64_t chunk_text_base, uint64_t *seq_abs, uint32_t *seq_eff)
 {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -203,6 +204,8 @@ __global__ void __launch_bounds__(256) fq_convert(const uint8_t *text, const uin
             uint8_t out = 0xFD;
             if (i < l) {
                 const uint8_t b = s[i];
+                // --collapse: the (truncated) sequence stays on the device, at its own place in the text, for moira_dedup.cu
+                if (seq_store && i < eff) seq_store[chunk_text_base + seq_off[r] + i] = b;
                 int v = (int)q[i] - qbase;                        // ord(x) - fastq_offset, moira.py:1177
                 if (b == 'N') out = 0xFF;
                 else if (b == 'n' && lower_n) out = 0xFE;
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(256) fq_convert(const uint8_t *text, const uin
             up |= __ballot_sync(FULL, out == 0xFF && i < eff);
         }
         if (marks && lane == 0) marks[r] = ns | (up ? 0x80000000u : 0u);
+        if (seq_store && lane == 0) { seq_abs[r] = chunk_text_base + seq_off[r]; seq_eff[r] = eff; }
         if (__any_sync(FULL, bad) && lane == 0) atomicMin(&meta[2], r);
     }
 }
@@ -250,12 +254,14 @@ int launch_fq_records(const uint8_t *d_text, uint64_t lo, uint64_t n, const uint
 
 int launch_fq_convert(const uint8_t *d_text, const uint32_t *d_seq_off, const uint32_t *d_qual_off, const uint32_t *d_len,
                       uint32_t n_rec, uint32_t stride, int lower_n, int qbase, uint8_t *d_slab, uint32_t *d_meta, uint32_t *d_marks,
-                      uint32_t truncate, int sm_count, cudaStream_t s)
+                      uint32_t truncate, int sm_count, cudaStream_t s, uint8_t *d_seq_store, uint64_t chunk_text_base, uint64_t *d_seq_abs,
+                      uint32_t *d_seq_eff)
 {
     if (n_rec == 0) return 0;
     const uint32_t want = (n_rec + 7) / 8;
     const uint32_t grid = want < (uint32_t)sm_count * 8 ? want : (uint32_t)sm_count * 8;
-    fq_convert<<<grid, 256, 0, s>>>(d_text, d_seq_off, d_qual_off, d_len, n_rec, stride, lower_n, qbase, d_slab, d_meta, d_marks, truncate);
+    fq_convert<<<grid, 256, 0, s>>>(d_text, d_seq_off, d_qual_off, d_len, n_rec, stride, lower_n, qbase, d_slab, d_meta, d_marks, truncate,
+                                    d_seq_store, chunk_text_base, d_seq_abs, d_seq_eff);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

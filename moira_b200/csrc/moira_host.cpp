@@ -516,6 +516,36 @@ int moira::fastq_plan_chunk_fast(const char *text, uint64_t text_bytes, uint64_t
     return MOIRA_OK;
 }
 
+// Record-aligned shard boundaries of a FASTQ text (one shard per GPU): the same local test as above, forwards from the
+// even split points.
+extern "C" int moira_fastq_split(const char *text, uint64_t text_bytes, int n_parts, uint64_t *cuts_out)
+{
+    if (!cuts_out || n_parts < 1 || (!text && text_bytes)) return moira::fail(MOIRA_ERR_BAD_ARG, "bad argument");
+    cuts_out[0] = 0;
+    cuts_out[n_parts] = text_bytes;
+    const char *end = text + text_bytes;
+    for (int p = 1; p < n_parts; p++) {
+        uint64_t at = text_bytes * (uint64_t)p / (uint64_t)n_parts;
+        if (at < cuts_out[p - 1]) at = cuts_out[p - 1];
+        uint64_t cut = text_bytes;
+        const char *cur = text + at;
+        while (cur < end) {
+            const char *nl = (const char *)memchr(cur, '\n', (size_t)(end - cur));
+            if (!nl || nl + 1 >= end) break;
+            const char *s = nl + 1;                                  // a line start
+            cur = s;
+            if (*s != '@') continue;
+            const char *l1 = (const char *)memchr(s, '\n', (size_t)(end - s));
+            if (!l1 || l1 + 1 >= end) break;
+            const char *l2 = (const char *)memchr(l1 + 1, '\n', (size_t)(end - (l1 + 1)));
+            if (!l2 || l2 + 1 >= end) break;
+            if (l2[1] == '+') { cut = (uint64_t)(s - text); break; }
+        }
+        cuts_out[p] = cut;
+    }
+    return MOIRA_OK;
+}
+
 // ---- FASTA + QUAL ------------------------------------------------------------------------------------
 // Record semantics of parse_fasta_and_qual (moira/moira.py:1093-1149, single-end): both files hold one
 // header line and one data line per record ("Expects sequences and qualities to be stored in a single

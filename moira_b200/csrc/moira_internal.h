@@ -14,12 +14,13 @@ namespace moira {
 // classifier that estimates how many PMF entries K each of them needs (mean + upper quantile of
 // the error count, fp32) and forwards it to the cheapest rung that holds that many.  A rung that
 // still cannot settle a read hands it to the next one; the last rung (block-per-read) takes any K.
-constexpr int NB = 20;
-constexpr int N_TPR_RUNGS = 14;   // rungs 1..14 (one fused launch, ladder_tpr_kernel)
-// rungs 1..14 thread-per-read, 15..18 warp-per-read, 19 block-per-read
+constexpr int NB = 25;
+constexpr int N_TPR_RUNGS = 19;   // rungs 1..19 (one fused launch, ladder_tpr_kernel)
+// rungs 1..19 thread-per-read (K = 3..64: the small ones take the reads a two-entry first pass hands on with j* = 2..6,
+// at 7..19 operations per base instead of the 22 of K = 8), 20..23 warp-per-read, 24 block-per-read
 __host__ __device__ constexpr int rung_cap(int b)
 {
-    constexpr int caps[NB] = {0, 8, 10, 12, 14, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 0x7fffffff};
+    constexpr int caps[NB] = {0, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 0x7fffffff};
     return caps[b];
 }
 
@@ -165,7 +166,8 @@ int launch_fq_records(const uint8_t *d_text, uint64_t lo, uint64_t n, const uint
                       uint32_t *d_meta, cudaStream_t s);
 int launch_fq_convert(const uint8_t *d_text, const uint32_t *d_seq_off, const uint32_t *d_qual_off, const uint32_t *d_len,
                       uint32_t n_rec, uint32_t stride, int lower_n, int qbase, uint8_t *d_slab, uint32_t *d_meta, uint32_t *d_marks,
-                      uint32_t truncate, int sm_count, cudaStream_t s);
+                      uint32_t truncate, int sm_count, cudaStream_t s, uint8_t *d_seq_store = nullptr, uint64_t chunk_text_base = 0,
+                      uint64_t *d_seq_abs = nullptr, uint32_t *d_seq_eff = nullptr);
 void parallel_memcpy(void *dst, const void *src, uint64_t bytes);   // all host threads
 int fastq_plan_chunk(const char *text, uint64_t text_bytes, uint64_t pos, uint64_t target_bytes, uint8_t *copy_to,
                      uint64_t *chunk_bytes_out, uint64_t *n_rec_out, uint64_t *n_newlines_out);
@@ -181,6 +183,21 @@ int parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_offset, i
 
 // run fn(0..n_tasks-1) on up to n_threads threads of a persistent host worker pool (moira_host.cpp)
 void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn);
+
+// ---- dereplication on the device (moira_dedup.cu) ------------------------------------------------------------
+struct DedupArgs {
+    const uint8_t *seq;          // sequence bytes; read r at seq + (off ? off[r] : r * stride), any alignment, 8 bytes of slack behind
+    const uint64_t *off;
+    const uint32_t *len;         // may be null: fixed_len
+    uint64_t stride;
+    uint32_t fixed_len;
+    uint32_t truncate;           // compare contig[:truncate] (moira.py:806-807); 0 = off
+    uint64_t base;               // this launch covers reads [base, base + n)
+    uint64_t n;
+};
+// labels[r] = index of one read with exactly r's sequence (the same one for all of them); d_hash: 2 x uint64 per read,
+// d_table: table_mask + 1 slots preset to 0xFFFFFFFF (kept between launches that add reads to the same set)
+int launch_dedup(const DedupArgs &a, uint64_t *d_hash, uint32_t *d_table, uint32_t table_mask, uint32_t *d_labels, const LaunchCfg &cfg);
 
 // ---- the counters' all-reduce over GPUs (moira_comm.cpp; NCCL bound at run time) ---------------------------------
 struct CommState;                       // one communicator rank; owned by a moira_ctx

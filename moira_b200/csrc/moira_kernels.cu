@@ -773,9 +773,11 @@ __global__ void __launch_bounds__(256, 1) ladder_tpr_kernel(const FilterArgs a0)
         tpr_tiles<k, 0, EQP, false>(a, nullptr, ctx, a0.queues + (size_t)(r) * a0.queue_cap, counts[r], first, W); \
         before += (counts[r] + 31) >> 5;                                                                      \
     }
-    MOIRA_RUNG(1, 8) MOIRA_RUNG(2, 10) MOIRA_RUNG(3, 12) MOIRA_RUNG(4, 14) MOIRA_RUNG(5, 16) MOIRA_RUNG(6, 18)
-    MOIRA_RUNG(7, 20) MOIRA_RUNG(8, 22) MOIRA_RUNG(9, 24) MOIRA_RUNG(10, 28) MOIRA_RUNG(11, 32) MOIRA_RUNG(12, 40)
-    MOIRA_RUNG(13, 48) MOIRA_RUNG(14, 64)
+    MOIRA_RUNG(1, 3) MOIRA_RUNG(2, 4) MOIRA_RUNG(3, 5) MOIRA_RUNG(4, 6) MOIRA_RUNG(5, 7)
+    MOIRA_RUNG(6, 8) MOIRA_RUNG(7, 10) MOIRA_RUNG(8, 12) MOIRA_RUNG(9, 14) MOIRA_RUNG(10, 16) MOIRA_RUNG(11, 18)
+    MOIRA_RUNG(12, 20) MOIRA_RUNG(13, 22) MOIRA_RUNG(14, 24) MOIRA_RUNG(15, 28) MOIRA_RUNG(16, 32) MOIRA_RUNG(17, 40)
+    MOIRA_RUNG(18, 48) MOIRA_RUNG(19, 64)
+    static_assert(N_TPR_RUNGS == 19 && rung_cap(19) == 64 && rung_cap(6) == 8, "rung table and ladder kernel out of step");
 #undef MOIRA_RUNG
     __syncthreads();
     flush_counters(a, ctx.s_cnt, ctx.s_hist);
@@ -1372,10 +1374,10 @@ int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg0)
     const int wpr_grid = cfg.sm_count * 4;
     switch (b) {
     case 0: return launch_tpr<2, 2>(a, cfg);     // classifier
-    case 15: wpr_kernel<4><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 16: wpr_kernel<8><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 17: wpr_kernel<16><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
-    case 18: wpr_kernel<32><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case N_TPR_RUNGS + 1: wpr_kernel<4><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case N_TPR_RUNGS + 2: wpr_kernel<8><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case N_TPR_RUNGS + 3: wpr_kernel<16><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
+    case N_TPR_RUNGS + 4: wpr_kernel<32><<<wpr_grid, WPR_THREADS, 0, cfg.stream>>>(a); break;
     case NB - 1: blk_kernel<<<cfg.sm_count, BLK_THREADS, BLK_SMEM, cfg.stream>>>(a); break;
     default: return -1;   // rungs 1..N_TPR_RUNGS run fused, see launch_ladder_tpr
     }

@@ -62,16 +62,31 @@ def test_open_input_sniffs_compression(tmp_path):
         assert cli.open_input(str(p)).read() == raw                                   # moira.py:1058-1090
 
 
-def test_fastq_batches_cut_on_record_boundaries(tmp_path, forward_records, monkeypatch):
+def test_fastq_text_loading_and_record_aligned_shards(tmp_path, forward_records):
+    """The FASTQ flow's host side: load_text (plain = memory-mapped, gz / bz2 inflated) gives the same bytes; the shard
+    cuts (one shard per GPU) fall on record starts, so parsing the shards one by one gives the reference's records."""
+    import numpy as np
+    import moira_b200
     raw = gzip.open(os.path.join(GOLDEN, "test1.fastq.gz"), "rb").read()
-    monkeypatch.setattr(cli, "BATCH_BYTES", 50000)
-    headers, seqs, quals = [], [], []
-    for h, s, q, slab, off, ln in cli.read_fastq_batches(io.BytesIO(raw), 33, True, "mem"):
-        headers += h
-        seqs += s
-        quals += [list(map(int, x)) for x in q]
-    assert headers == [r[0] for r in forward_records] and seqs == [r[1] for r in forward_records]
-    assert quals == [[v if v > 0 else 1 for v in r[2]] for r in forward_records]
+    plain, gz = tmp_path / "a.fastq", tmp_path / "b.fastq.gz"
+    plain.write_bytes(raw)
+    gz.write_bytes(gzip.compress(raw))
+    for path in (plain, gz):
+        text, _keep = cli.load_text(str(path))
+        assert text.tobytes() == raw
+    for parts in (1, 2, 3, 7, 8):
+        cuts = moira_b200.fastq_split(raw, parts)
+        assert cuts[0] == 0 and cuts[-1] == len(raw) and (np.diff(cuts.astype(np.int64)) >= 0).all()
+        got = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            piece = raw[int(a):int(b)]
+            assert piece[:1] in (b"@", b"")
+            slab, off, ln, hoff, hlen, soff, qoff = moira_b200.parse_fastq(piece, 33, True)
+            ho2, hl2 = moira_b200.fastq_headers(piece, soff)
+            assert np.array_equal(ho2, hoff) and np.array_equal(hl2, hlen)
+            got += [(piece[int(h):int(h) + int(l)].decode().replace(":", "_"), piece[int(s_):int(s_) + int(n)].decode())
+                    for h, l, s_, n in zip(hoff, hlen, soff, ln)]
+        assert got == [(r[0], r[1]) for r in forward_records]
 
 
 @pytest.mark.gpu

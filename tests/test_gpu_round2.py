@@ -217,3 +217,86 @@ def test_real_profile_generator_host_and_device(ctx):
     dec = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=False))
     assert np.array_equal(dec.accept, (ee_o + ns_o) <= 2.5300000000000002)
     assert 0.7 < dec.accept.mean() < 0.95
+
+
+def _random_sequences(rng, n, pool, lo, hi):
+    """n sequences drawn (with repeats) from `pool` distinct random strings of lo..hi bases, some differing only in the
+    last base or in length."""
+    base = []
+    for _ in range(pool):
+        L_ = int(rng.integers(lo, hi + 1))
+        base.append(bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), L_)))
+    base += [b[:-1] + b"T" for b in base[:pool // 4]] + [b[:-1] for b in base[:pool // 4] if len(b) > 1]
+    return [base[int(i)] for i in rng.integers(0, len(base), n)]
+
+
+@pytest.mark.parametrize("lo,hi,truncate", [(1, 40, 0), (200, 260, 0), (1400, 1600, 0), (100, 300, 150)])
+def test_device_dereplication_equals_host_collapse(ctx, lo, hi, truncate):
+    """moira_collapse_device + moira_collapse_labels == moira_collapse (hash + memcmp on the host): groups, representatives,
+    names order, abundance order -- on unaligned back-to-back sequences and on 16-byte rows."""
+    rng = np.random.default_rng(lo + hi)
+    n = 30000
+    seqs = _random_sequences(rng, n, 3000, lo, hi)
+    ee = rng.integers(0, 4, n).astype(np.float64) + rng.integers(0, 2, n) * 0.25
+    ln = np.array([len(s_) for s_ in seqs], np.uint32)
+    off = np.zeros(n, np.uint64)
+    off[1:] = np.cumsum(ln[:-1], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(seqs) + b"\0" * 16, dtype=np.uint8)
+    eff = np.minimum(ln, truncate) if truncate else ln
+    want = moira_b200.collapse(blob, off, eff, ee)
+    dev = torch.device("cuda", 0)
+    d_blob, d_off, d_len = torch.from_numpy(blob.copy()).to(dev), torch.from_numpy(off.astype(np.int64)).to(dev), torch.from_numpy(ln.astype(np.int32)).to(dev)
+    d_lab = torch.zeros(n, dtype=torch.int32, device=dev)
+    ctx.collapse_device(d_blob.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), 0, 0, n, d_lab.data_ptr(), truncate,
+                        torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    labels = d_lab.cpu().numpy().view(np.uint32)
+    got = moira_b200.collapse_labels(labels, ee)
+    for f in ("group_of_read", "rep", "size", "member_start", "members", "order"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    # equal label <=> equal (truncated) sequence
+    key = {}
+    for r, s_ in enumerate(seqs):
+        s_ = s_[:truncate] if truncate else s_
+        assert key.setdefault(s_, int(labels[r])) == int(labels[r])
+    assert len(set(key.values())) == len(key)
+
+
+def test_fastq_ex_offsets_and_device_labels(ctx):
+    """moira_filter_fastq_ex: record offsets == the host parser's, labels + ee -> the groups of the host collapse, with and
+    without --truncate, on a text of several chunks."""
+    import gzip, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = gzip.open(os.path.join(root, "tests", "golden", "test1.fastq.gz"), "rb").read() * 150      # ~ 90 MB: two chunks
+    slab, off, ln, hoff, hlen, soff, qoff = moira_b200.parse_fastq(text, 33, True)
+    for trunc in (None, 180):
+        p = FilterParams(exact_ee=True, ee_output="final", truncate=trunc)
+        r = ctx.filter_fastq_ex(text, p, 33, offsets=True, labels=True)
+        assert np.array_equal(r.lengths, ln) and np.array_equal(r.seq_off, soff) and np.array_equal(r.qual_off, qoff)
+        ref = ctx.filter_batch(slab, off, ln, p)
+        assert np.array_equal(r.filter.ee, ref.ee) and np.array_equal(r.filter.flags, ref.flags)
+        eff = np.minimum(ln, trunc) if trunc else ln
+        want = moira_b200.collapse(text, soff, eff, ref.ee)
+        got = moira_b200.collapse_labels(r.labels, r.filter.ee)
+        for f in ("group_of_read", "rep", "size", "member_start", "members", "order"):
+            assert np.array_equal(getattr(got, f), getattr(want, f)), f
+        ho, hl = moira_b200.fastq_headers(text, r.seq_off)
+        assert np.array_equal(ho, hoff) and np.array_equal(hl, hlen)
+
+
+@pytest.mark.parametrize("extra", [[], ["-c", "False", "-o", "fastq", "-pi", "USEARCH", "-t", "200"], ["-l", "seq", "-me", "3"]])
+def test_cli_shards_over_several_contexts_give_the_same_files(tmp_path, extra):
+    """--devices: the reads of one FASTQ sharded over three contexts (own streams, parsers, dereplication tables) -- the
+    shard labels are merged on the host -- write byte-identical files to the single-context run."""
+    import gzip, os
+    from moira_b200 import cli
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fq = tmp_path / "in.fastq"
+    fq.write_bytes(gzip.open(os.path.join(root, "tests", "golden", "test1.fastq.gz"), "rb").read() * 3)
+    one, three = str(tmp_path / "one"), str(tmp_path / "three")
+    assert cli.run(["-ffq", str(fq), "-op", one, "--silent", "--device", "0"] + extra) == 0
+    assert cli.run(["-ffq", str(fq), "-op", three, "--silent", "--devices", "0,0,0"] + extra) == 0
+    names = sorted(f[len("one"):] for f in os.listdir(tmp_path) if f.startswith("one."))
+    assert len(names) >= 2
+    for suffix in names:
+        assert open(one + suffix, "rb").read() == open(three + suffix, "rb").read(), suffix
