@@ -498,16 +498,14 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
     // Ns / has-N of every row given with the slab (produced by whoever wrote it): the sweep counts nothing
     const bool marks_given = a.row_marks != nullptr;
     uint32_t vec_steps = 0;   // 16-base vector steps this warp swept with the FP64 recurrence (warp-uniform)
-    auto tile_read = [&](uint32_t t, bool &valid, uint32_t &r_local, ReadGeom &g, uint32_t &marks) {
+    auto tile_read = [&](uint32_t t, bool &valid, uint32_t &r_local, ReadGeom &g) {
         uint32_t i = t * 32 + lane;
         valid = t < n_tiles && i < count;
         r_local = 0;
-        marks = 0;
         g.off = 0; g.len = 0; g.eff = 0;
         if (valid) {
             r_local = queue ? queue[i] : i;
             g = read_geom(a, r_local);
-            if (marks_given) marks = a.row_marks[a.base + r_local];
         }
     };
     // Stage chunk c of the tile's 32 rows into stage `s` with LDGSTS (cp.async), 16 bytes per lane
@@ -572,23 +570,28 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
     };
 
     bool valid, nvalid;
-    uint32_t r_local, nr_local, marks, nmarks;
+    uint32_t r_local, nr_local;
     ReadGeom g, ng;
-    tile_read(tile, valid, r_local, g, marks);
+    tile_read(tile, valid, r_local, g);
     if (tile < n_tiles) issue(g, tile, 0, it);
+    // longest / shortest read of the tile: reduced where the tile's geometry is complete anyway (before the loop, and at the
+    // end of the previous tile), so that the loop head does not wait on loads
+    uint32_t maxeff = __reduce_max_sync(FULL, g.eff);
+    uint32_t mineff = __reduce_min_sync(FULL, g.eff);
 
     while (tile < n_tiles) {
         const uint32_t next_tile = tile + total_warps;
-        tile_read(next_tile, nvalid, nr_local, ng, nmarks);
-        const uint32_t maxeff = __reduce_max_sync(FULL, g.eff);
-        const uint32_t mineff = __reduce_min_sync(FULL, g.eff);
+        tile_read(next_tile, nvalid, nr_local, ng);
+        // this tile's marks: requested here, first needed by the epilogue -- the sweep in between hides the latency (a load
+        // carried from the previous iteration made the loop head wait for the loads just issued for the next tile)
+        const uint32_t marks = (marks_given && valid) ? __ldg(a.row_marks + a.base + r_local) : 0u;
         uint32_t nch = (maxeff + CHUNK - 1) / CHUNK;
 
         double P[K];
 #pragma unroll
         for (int j = 0; j < K; j++) P[j] = 0.0;
         if (MODE == 0) P[0] = 1.0;
-        uint32_t ns = marks & 0x7FFFFFFFu, has_n = marks >> 31;
+        uint32_t ns = 0, has_n = 0;
         uint32_t processed = 0;
         bool skip_math = false;   // warp-uniform
 
@@ -645,6 +648,7 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         }
 
         // ---- per-read epilogue ----
+        if (marks_given) { ns = marks & 0x7FFFFFFFu; has_n = marks >> 31; }
         ReadResult res;
         res.ns = (int)ns;
         res.has_n = has_n != 0u;
@@ -665,7 +669,9 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
             const int kneed = kn > 1.0e6 ? 1000000 : (kn < 2.0 ? 2 : (int)kn);
             push_read(a, valid, pick_rung(a, kneed), r_local, lane);
             tile = next_tile;
-            valid = nvalid; r_local = nr_local; g = ng; marks = nmarks;
+            valid = nvalid; r_local = nr_local; g = ng;
+            maxeff = __reduce_max_sync(FULL, g.eff);
+            mineff = __reduce_min_sync(FULL, g.eff);
             continue;
         }
         if (MODE == 0) {
@@ -713,7 +719,9 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         finish_read(a, valid, r_local, g, res, s_cnt, s_hist, lane);
 
         tile = next_tile;
-        valid = nvalid; r_local = nr_local; g = ng; marks = nmarks;
+        valid = nvalid; r_local = nr_local; g = ng;
+        maxeff = __reduce_max_sync(FULL, g.eff);
+        mineff = __reduce_min_sync(FULL, g.eff);
     }
     // FP64 operations the sweeps of this warp executed (thread level: 32 lanes x 16 positions per vector step)
     constexpr uint32_t OPB = MODE == 0 ? (uint32_t)(3 * K - 2) + (PL ? 1u : 0u) : (MODE == 1 ? 1u : 2u);
