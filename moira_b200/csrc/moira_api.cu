@@ -158,6 +158,9 @@ struct moira_ctx {
     int use_tma = 1;
     int length_sort = 1;
     int cascade = 1;
+    int cascade_multi = 1; // decisions needing 5..8 entries: first stage picked among 2..5 entries (0: two entries or none)
+    double direct_gap = 0.5;
+    int direct_rung = 1;   // the first pass picks the ladder rung of the reads it hands on (0: every one goes through the classifier)
     int timing = 0;
     int n_timed = 0;
     cudaEvent_t t0[MAX_TIMED] = {}, t1[MAX_TIMED] = {};
@@ -232,7 +235,7 @@ int ensure(DevBuf &b, size_t bytes)
 // queue memory for `nq` queues of `cap` reads each (the ladder uses NB queues, the decision cascade only queue 0)
 int ensure_ws(Workspace &w, uint32_t cap, int nq = NB)
 {
-    if (!w.counts) CU(cudaMalloc(&w.counts, (NB + 4) * sizeof(uint32_t)));   // queue counts | first-pass policy word
+    if (!w.counts) CU(cudaMalloc(&w.counts, (NB + 4 + 16) * sizeof(uint32_t)));   // queue counts | first-pass policy word | pilot histogram
     const size_t words = (size_t)nq * cap;
     if (words <= w.words && w.queues) { w.cap = cap; return MOIRA_OK; }
     if (w.queues) cudaFree(w.queues);
@@ -411,6 +414,8 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
     }
     const bool ladder = p->mode == MOIRA_MODE_PB && (p->exact_ee || !k_decides_all);
     a.allow_push = ladder ? 1 : 0;
+    a.direct_rung = (ladder && c->direct_rung) ? 1 : 0;
+    a.direct_gap = c->direct_gap;
     // Cascaded first pass: when the decision needs only a few entries (k_first = 3..8), most reads of a typical run are
     // either clean (j* <= 1: two entries settle them exactly) or hopeless (the Newton bound on acc[k_first - 1] from
     // those two entries already rejects them).  Sweeping two entries costs 4-5 FP64 operations per base instead of
@@ -429,7 +434,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             int rc = ensure_ws(ws, (uint32_t)std::min<uint64_t>(n_reads, sub), ladder ? NB : 1);
             if (rc) return rc;
             a.queues = ws.queues; a.queue_counts = ws.counts; a.queue_cap = ws.cap;
-            CU(cudaMemsetAsync(ws.counts, 0, (NB + 4) * sizeof(uint32_t), stream));
+            CU(cudaMemsetAsync(ws.counts, 0, (NB + 4 + 16) * sizeof(uint32_t), stream));
         }
         // uniform-stride slab: feed the first pass with TMA tensor tiles of this sub-batch's rows
         CUtensorMap tmap;
@@ -481,7 +486,35 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             uint32_t *policy = ws.counts + NB;
             static const char *cname[] = {"", "", "", "pb_cascade<2,3>", "pb_cascade<2,4>", "pb_cascade<2,5>", "pb_cascade<2,6>",
                                           "pb_cascade<2,7>", "pb_cascade<2,8>"};
-            if (pilot) {
+            static const char *mname[] = {"", "", "", "", "", "pb_cascade<2..4,5>", "pb_cascade<2..5,6>", "pb_cascade<2..5,7>",
+                                          "pb_cascade<2..5,8>"};
+            // decisions that need 5 .. 8 entries: the first stage is chosen among 2 .. 5 entries (two pilots, see policy_*_kernel)
+            const bool multi = pilot && !p->exact_ee && k_first >= 5 && n >= 16u * pilot_n && c->cascade_multi;
+            if (multi) {
+                uint32_t *jhist = ws.counts + NB + 4;
+                a2.n = pilot_n;
+                rc = launch_pb_first(a2, 2, cfg, nullptr);                 // pilot A: two entries, escalations counted
+                if (rc >= 0 && launch_policy_first(ws.counts, (uint32_t)(pilot_n * 0.35), policy, stream)) rc = -1;
+                FilterArgs b = a;                                          // pilot B (only if A was escalated too often):
+                b.n = 2u * pilot_n; b.tile0 = pilot_n / 32u;               // k_first entries at once over the next reads,
+                b.policy = policy; b.policy_want = MOIRA_POLICY_UNDECIDED; // histogram of floor(ee) for the verdict
+                b.jhist = jhist;
+                if (rc >= 0) rc = launch_pb_first(b, k_first, cfg, nullptr);
+                if (rc >= 0 && launch_policy_second(jhist, k_first, policy, stream)) rc = -1;
+                a2.n = n; a2.tile0 = pilot_n / 32u; a2.policy = policy; a2.policy_want = 2;
+                if (rc >= 0) rc = launch_pb_first(a2, 2, cfg, nullptr);
+                c->launches += 5;
+                for (int k1 = 3; k1 <= 5 && k1 < k_first && rc >= 0; k1++) {
+                    FilterArgs ak = a2;
+                    ak.tile0 = 2u * pilot_n / 32u; ak.policy_want = (uint32_t)k1;
+                    rc = launch_pb_first(ak, k1, cfg, nullptr);
+                    c->launches++;
+                }
+                FilterArgs a1 = a;                                         // the last candidate: k_first entries at once
+                a1.tile0 = 2u * pilot_n / 32u; a1.policy = policy; a1.policy_want = 0;
+                if (rc >= 0) rc = launch_pb_first(a1, k_first, cfg, nullptr);
+                c->launches++;
+            } else if (pilot) {
                 a2.n = pilot_n;
                 rc = launch_pb_first(a2, 2, cfg, nullptr);
                 if (rc >= 0 && launch_policy(ws.counts, (uint32_t)(pilot_n * 0.35), policy, stream)) rc = -1;
@@ -507,7 +540,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
                 rc = launch_pb_first(a3, k_first, cfg3, nullptr);
                 c->launches++;
             }
-            if (pilot || blind) name = cname[k_first];
+            if (pilot || blind) name = multi ? mname[k_first] : cname[k_first];
             if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else {
             rc = p->mode == MOIRA_MODE_PB ? launch_pb_first(a, k_first, cfg, &name) : launch_lambda(a, cfg, &name);
@@ -587,6 +620,9 @@ static int ctx_init(moira_ctx *c, int device, int sm_count)
     if (const char *e = getenv("MOIRA_B200_FQ_COUNT")) c->fq_guess_cuts = (e[0] == '1') ? 0 : 1;   // diagnostics: always count the chunk cuts on the host
     if (const char *e = getenv("MOIRA_B200_HOST_PARSE")) c->device_parse = (e[0] == '1') ? 0 : 1;   // moira_filter_fastq: parse on the host cores instead
     if (const char *e = getenv("MOIRA_B200_NO_CASCADE")) c->cascade = (e[0] == '1') ? 0 : 1;   // diagnostics: full-K first pass always
+    if (const char *e = getenv("MOIRA_B200_NO_CASCADE_MULTI")) c->cascade_multi = (e[0] == '1') ? 0 : 1;   // diagnostics
+    if (const char *e = getenv("MOIRA_B200_DIRECT_GAP")) c->direct_gap = atof(e);   // tuning
+    if (const char *e = getenv("MOIRA_B200_NO_DIRECT_RUNG")) c->direct_rung = (e[0] == '1') ? 0 : 1;   // diagnostics: classifier pass for all
     if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
     if (kernels_init(c->sm_count)) return fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaMalloc(&c->d_p, 256 * sizeof(double)));

@@ -63,11 +63,15 @@ struct FilterArgs {
     int32_t rung;                // -1 on the first pass, else this kernel's rung
     int32_t min_rung;            // lowest rung the classifier may forward to (its cap exceeds the first-pass K)
     int32_t allow_push;          // 0: no ladder follows (first-pass K provably decides everything)
+    double direct_gap;           // ... as long as sum g - sum f of its bases is at most this (else: the classifier)
+    int32_t direct_rung;         // first pass with a ladder behind it: a read swept completely but not settled goes straight to
+                                 // the rung its two lowest entries call for (rung_from_two_entries), not through the classifier
     // cascaded first pass (decision mode): this launch tracks fewer entries than the k_dec = floor(cutoff) + 2 the
     // decision needs; reads it cannot settle exactly are rejected when the Newton bound on acc[k_dec - 1] allows it
     // and pushed to queue 0 otherwise.  0: off.
     int32_t k_dec;
     uint32_t tile0;              // first pass: the launch starts at this warp tile (the tiles before belong to the pilot launch)
+    uint32_t *jhist;             // not null (second pilot launch of the cascade): 16 bins of floor(ee) of this launch's reads
     const uint32_t *policy;      // not null: the launch runs only if *policy == policy_want (set on the device by the pilot)
     uint32_t policy_want;
     // tables (device, 256 doubles each)
@@ -122,6 +126,10 @@ int launch_count_marks(const FilterArgs &a, uint32_t *d_marks, uint32_t max_len,
 // after the pilot launch: *policy = 1 (go on with the full-K first pass) if more than `max_pushed` of the pilot's reads were
 // escalated, else 0 (go on with the cascade)
 int launch_policy(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s);
+// cascade with a first stage of 2 .. 5 entries: verdict of the two-entry pilot (2 or undecided), then of the k_first-entry pilot
+constexpr uint32_t MOIRA_POLICY_UNDECIDED = 0xFFu;
+int launch_policy_first(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s);
+int launch_policy_second(const uint32_t *jhist, int k_first, uint32_t *policy, cudaStream_t s);
 int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, double *ops_out);
 int kernels_init(int sm_count);  // sets function attributes (dynamic smem opt-in)
 int max_first_pass_k();

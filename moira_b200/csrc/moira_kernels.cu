@@ -29,6 +29,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "fact_table.h"
 #include "moira_internal.h"
@@ -73,7 +74,7 @@ constexpr int BLK_CAP = 24576;                   // PMF entries held in shared m
 constexpr int BLK_SMEM = BLK_CAP * 8 + 256 * 16;
 
 __constant__ double c_fact[MOIRA_FACT_N] = MOIRA_FACT_TABLE;
-__constant__ double c_inv[8] = {1.0, 1.0, 0.5, 0.33333333333333337, 0.25, 0.2, 0.16666666666666669, 0.14285714285714288};
+__constant__ double c_ratio[9] = {1.0, 1.0, 0.5, 0.66666666666666674, 0.75, 0.80000000000000004, 0.83333333333333337, 0.85714285714285721, 0.875};   // (j - 1) / j, rounded up
 
 // ---- PTX helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,6 +137,13 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
     return v;
 }
 
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
 // ---- byte handling -------------------------------------------------------------------------------
 // Replace bytes at positions >= nvalid (0..4) of a little-endian word by the padding code 0xFD.
 __device__ __forceinline__ uint32_t mask_word(uint32_t w, int nvalid)
@@ -195,6 +203,7 @@ struct ReadResult {
     bool numeric;
     bool escalate;     // cascade: not settled by this launch's entries and not a certain reject either -> next sweep, whatever
                        // the other rules say (so that the cascade writes exactly what the single sweep writes)
+    int next_rung;     // where an unsettled read goes: the next rung, or the one the first pass picked itself (direct_rung)
 };
 
 __device__ __forceinline__ int pick_rung(const FilterArgs &a, int kneed)
@@ -202,6 +211,35 @@ __device__ __forceinline__ int pick_rung(const FilterArgs &a, int kneed)
     int b = a.min_rung > 1 ? a.min_rung : 1;
     while (b < NB - 1 && rung_cap(b) < kneed) b++;
     return b;
+}
+
+// The rung of a read the first pass swept completely without settling it, from the two entries every sweep tracks
+// (no classifier pass over the row): with f_i = -ln(1 - p_i) and g_i = p_i / (1 - p_i),
+//     A = -ln P[0] = sum f_i        B = P[1] / P[0] = sum g_i        (P[1] = prod(1 - p_i) * sum g_i)
+// and  1.34 f - 0.34 g >= p  for every p <= 10^-0.1 (Q >= 1; equality to second order at p -> 0, +0.012 at Q = 1), so
+//     mu_hat = 1.34 A - 0.34 B >= mu = sum p_i >= sigma^2 ,
+// which goes into the classifier's own quantile estimate (Cornish-Fisher with the Poisson skew bound).  An over-estimate
+// costs entries (about one on MiSeq-like noisy reads), an under-estimate one more rung; results never depend on it.
+// P[0] too small for the quotient: rung 0, the classifier.
+__device__ __forceinline__ int rung_from_two_entries(const FilterArgs &a, double p0, double p1, uint32_t eff, uint32_t ns, int k_tried)
+{
+    if (!(p0 > 1e-280)) return 0;
+    const double A = -log(p0), B = p1 / p0;
+    // B - A = sum(p^2 / 2 + 2 p^3 / 3 + ...) measures how loose the estimate is (sigma^2 = mu - sum p^2 is taken as mu): reads
+    // with many low-quality bases are worth the classifier's pass over the row
+    if (!(B - A <= a.direct_gap)) return 0;
+    double mu = 1.34 * A - 0.34 * B;
+    if (!(mu > 0.0)) mu = 0.0;
+    double kn = mu + a.z * sqrt(mu) + a.zc;
+    if (!a.exact) {   // a decision needs at most floor(cutoff on the raw statistic) + 2 entries
+        double c = (a.thr_kind == MOIRA_THR_MAXERRORS) ? a.thr : __dmul_rn((double)eff, a.thr);
+        if (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) c -= (double)ns;
+        const double kd = floor(c) + 2.0;
+        if (kd < kn) kn = kd;
+    }
+    int kneed = kn > 1.0e6 ? 1000000 : (kn < 2.0 ? 2 : (int)kn);
+    if (kneed <= k_tried) kneed = k_tried + 1;   // k_tried entries did not settle it
+    return pick_rung(a, kneed);
 }
 
 // Append read r_local to the queue of `rung` (warp-aggregated).  Called convergently; lanes with
@@ -254,7 +292,7 @@ __device__ __forceinline__ void finish_read(const FilterArgs &a, bool valid, uin
         const unsigned pm = __ballot_sync(FULL, push);
         if (pm && lane == 0) atomicAdd(&s_cnt[MOIRA_CNT_ESCALATED], (uint32_t)__popc(pm));
     }
-    push_read(a, push, a.rung + 1, r_local, lane);
+    push_read(a, push, res.next_rung, r_local, lane);
     if (!valid || push) return;
 
     // ---- write + count ----------------------------------------------------------------------
@@ -283,25 +321,42 @@ __device__ __forceinline__ void flush_counters(const FilterArgs &a, const uint32
         uint32_t v = i < 16 ? s_cnt[i] : s_hist[i - 16];
         if (v) atomicAdd(&a.counters[i], (unsigned long long)v);
     }
+    // pilot launch of the cascade: its own histogram of floor(ee) (bins >= 15 together) for the policy kernel
+    if (a.jhist)
+        for (int i = threadIdx.x; i < MOIRA_N_HIST; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&a.jhist[i < 15 ? i : 15], s_hist[i]);
 }
 
-// Upper bound of acc[kd - 1] = P(X <= kd - 1) from P(X = 0) and P(X = 1) alone.  The PMF of a Poisson-binomial count
+// Upper bound of acc[kd - 1] = P(X <= kd - 1) from the K < kd entries a sweep tracks.  The PMF of a Poisson-binomial count
 // is e_j(w) * prod(1 - p_i) with w_i = p_i / (1 - p_i), and Newton's inequalities for the elementary symmetric
-// polynomials give P[j+1] / P[j] <= (j / (j + 1)) * P[j] / P[j-1], hence P[j] <= P[0] * r^j / j! with r = P[1] / P[0].
-// The prefix version holds too (acc[kd - 1] never increases as bases are added), so the bound may be taken after any
-// number of bases.  Returns 1 when P[0] is too small for the quotient to be trusted.
-__device__ __forceinline__ double newton_bound(double p0, double p1, int kd)
+// polynomials give rho_{j+1} <= (j / (j + 1)) * rho_j for the ratios rho_j = P[j] / P[j-1].  So beyond the tracked entries
+//     P[K] <= P[K-1] * rho_{K-1} * (K-1)/K ,   P[K+1] <= P[K] * rho_{K-1} * (K-1)/(K+1) , ...
+// (K = 2: P[j] <= P[0] * r^j / j! with r = P[1] / P[0]).  The prefix version holds too (acc[kd - 1] never increases as bases
+// are added), so the bound may be taken after any number of bases.  Returns 1 when the last-but-one entry is too small for
+// the quotient to be trusted.
+template <int K>
+__device__ __forceinline__ double newton_bound(const double (&P)[K], int kd)
 {
-    if (!(p0 > 1e-280)) return 1.0;
-    const double r = p1 / p0;
-    // 1/j rounded up (the 1e-9 margin of the callers covers every rounding here many times over); kd <= 8
-    double term = p1, sum = p0 + p1;
+    static_assert(K >= 2, "needs two tracked entries");
+    if (!(P[K - 2] > 1e-280)) return 1.0;
+    double rho = P[K - 1] / P[K - 2];
+    double term = P[K - 1], sum = P[0];
+#pragma unroll
+    for (int j = 1; j < K; j++) sum += P[j];
 #pragma unroll 1
-    for (int j = 2; j < kd; j++) {   // kd is launch-uniform: a real loop, not eight predicated copies
-        term = term * r * c_inv[j];
+    for (int j = K; j < kd; j++) {   // kd is launch-uniform: a real loop, not eight predicated copies
+        rho = rho * c_ratio[j];      // (j - 1) / j rounded up; the 1e-9 margin of the callers covers every rounding here many times over
+        term = term * rho;
         sum += term;
     }
     return sum == sum ? sum : 1.0;
+}
+
+template <int K>
+__device__ __forceinline__ double cascade_bound(const double (&P)[K], int kd)
+{
+    if constexpr (K >= 2) return newton_bound<K>(P, kd);
+    else return 1.0;
 }
 
 // bernoullimodule.c:233-254: cumulative sum in index order, strict '>' against 1-alpha, then
@@ -344,8 +399,8 @@ __device__ __forceinline__ uint32_t lut_addr_of(uint32_t w, uint32_t lut_lane)
     return __byte_perm(w, lut_lane, 0x7604u | (B << 4));
 }
 // The per-base work on one 16-byte vector already in registers.
-template <int K, int MODE, bool PL>
-__device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_lane, double (&P)[K])
+template <int K, int MODE, bool PL, typename T>
+__device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_lane, T (&P)[K])
 {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -368,7 +423,7 @@ __device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_l
             } else if (MODE == 1) {
                 P[0] = __dadd_rn(P[0], lds_f64(addr));     // moira.py:1663, in index order
             } else {
-                const double2 t = lds_f64x2(addr);         // classifier: mean and variance of the error count
+                const float2 t = lds_f32x2(addr);          // classifier: mean and variance of the error count (fp32: an estimate)
                 P[0] += t.x;
                 P[1] += t.y;
             }
@@ -382,9 +437,9 @@ __device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_l
 // MATH = false keeps only the N/n accounting (after a warp-wide early exit).
 // `swz` is the lane's XOR term of the TMA 128-byte swizzle ((lane & 7) << 4), 0 for the padded layout.
 // MARKS = false: Ns / has-N of every row came with the slab (FilterArgs::row_marks), nothing is counted here.
-template <int K, int MODE, bool PL, bool MATH, bool MARKS>
+template <int K, int MODE, bool PL, bool MATH, bool MARKS, typename T>
 __device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t swz, uint32_t cfull, uint32_t cend, int rem0,
-                                            uint32_t lut_lane, double (&P)[K], uint32_t &ns, uint32_t &has_n)
+                                            uint32_t lut_lane, T (&P)[K], uint32_t &ns, uint32_t &has_n)
 {
     if (!MATH && !MARKS) return;
     uint32_t v = 0;
@@ -392,12 +447,12 @@ __device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t swz, uint32_t
         const uint4 q4 = lds128(row + (v ^ swz));
         const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
         if (MARKS) count_marks4(w, ns, has_n);
-        if (MATH) sweep_vec<K, MODE, PL>(w, lut_lane, P);
+        if (MATH) sweep_vec<K, MODE, PL, T>(w, lut_lane, P);
     }
     for (; v < cend; v += 16) {
         uint32_t w[4];
         load_vec<MARKS>(row + (v ^ swz), rem0 - (int)v, w, ns, has_n);
-        if (MATH) sweep_vec<K, MODE, PL>(w, lut_lane, P);
+        if (MATH) sweep_vec<K, MODE, PL, T>(w, lut_lane, P);
     }
 }
 
@@ -445,11 +500,11 @@ __device__ __forceinline__ TprCtx tpr_setup(const FilterArgs &a, uint8_t *smem)
     } else if (MODE == 0) {
         double2 *t = reinterpret_cast<double2 *>(lut_ptr);
         for (int i = threadIdx.x; i < 256 * 16; i += TPR_THREADS) t[i] = make_double2(a.lut_q[i >> 4], a.lut_e[i >> 4]);
-    } else {
-        double2 *t = reinterpret_cast<double2 *>(lut_ptr);
-        for (int i = threadIdx.x; i < 256 * 16; i += TPR_THREADS) {
-            const double pv = a.lut_p[i >> 4];
-            t[i] = make_double2(pv, pv * (1.0 - pv));
+    } else {   // classifier: (p, p (1 - p)) in fp32, 32 replicas of 8 bytes like the p-only table
+        float2 *t = reinterpret_cast<float2 *>(lut_ptr);
+        for (int i = threadIdx.x; i < 256 * 32; i += TPR_THREADS) {
+            const double pv = a.lut_p[i >> 5];
+            t[i] = make_float2((float)pv, (float)(pv * (1.0 - pv)));
         }
     }
     for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += TPR_THREADS) s_cnt[i] = 0;
@@ -465,7 +520,7 @@ __device__ __forceinline__ TprCtx tpr_setup(const FilterArgs &a, uint8_t *smem)
     __syncthreads();
 
     TprCtx c;
-    c.lut_lane = lut + (PL ? lane * 8 : (lane & 15) * 16);
+    c.lut_lane = lut + ((PL || MODE == 2) ? lane * 8 : (lane & 15) * 16);
     c.stage_warp = (uint32_t)warp < n_below ? below0 + warp * 2 * STG : above + (warp - n_below) * 2 * STG;
     c.bar0 = bar0;
     c.s_cnt = s_cnt;
@@ -587,10 +642,11 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         const uint32_t marks = (marks_given && valid) ? __ldg(a.row_marks + a.base + r_local) : 0u;
         uint32_t nch = (maxeff + CHUNK - 1) / CHUNK;
 
-        double P[K];
+        using acc_t = typename std::conditional<MODE == 2, float, double>::type;
+        acc_t P[K];
 #pragma unroll
-        for (int j = 0; j < K; j++) P[j] = 0.0;
-        if (MODE == 0) P[0] = 1.0;
+        for (int j = 0; j < K; j++) P[j] = 0;
+        if (MODE == 0) P[0] = 1;
         uint32_t ns = 0, has_n = 0;
         uint32_t processed = 0;
         bool skip_math = false;   // warp-uniform
@@ -615,14 +671,14 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
             const uint32_t cend = maxeff - cbeg < CHUNK ? maxeff - cbeg : CHUNK;   // warp-uniform
             const uint32_t cfull = mineff > cbeg ? min((mineff - cbeg) & ~15u, cend) : 0u;   // warp-uniform
             if (!skip_math) {
-                if (marks_given) sweep_chunk<K, MODE, PL, true, false>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
-                else sweep_chunk<K, MODE, PL, true, true>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+                if (marks_given) sweep_chunk<K, MODE, PL, true, false, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+                else sweep_chunk<K, MODE, PL, true, true, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
                 processed = cbeg + cend;
                 vec_steps += (cend + 15u) >> 4;
             } else if (!marks_given) {
-                sweep_chunk<K, MODE, PL, false, true>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+                sweep_chunk<K, MODE, PL, false, true, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
             }
-            if (MODE == 0 && c + 1 < nch && !skip_math) {
+            if constexpr (MODE == 0) if (c + 1 < nch && !skip_math) {
                 // Early exit: sum_{j<K} P_k[j] never increases with k, so once it is safely below
                 // 1-alpha these K entries cannot reach the quantile.  Taken warp-wide only: the
                 // remaining chunks are still staged and scanned for N/n (Ns stays exact) but the
@@ -636,7 +692,7 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
                 if (K >= 2 && a.k_dec > K && all_certain) {
                     // a cascade launch stops only where the reject is certain at the decision's k_dec (the bound is at
                     // least the tracked mass, so the test above is a cheap necessary condition)
-                    certain = valid && newton_bound(P[0], P[K >= 2 ? 1 : 0], a.k_dec) < a.oma - 1e-9;
+                    certain = valid && cascade_bound<K>(P, a.k_dec) < a.oma - 1e-9;
                     all_certain = __all_sync(FULL, certain || finished) && __any_sync(FULL, certain);
                 }
                 if (all_certain) {
@@ -654,12 +710,13 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         res.has_n = has_n != 0u;
         res.numeric = false;
         res.escalate = false;
+        res.next_rung = a.rung + 1;
         res.processed = processed < g.eff ? processed : g.eff;
-        if (MODE == 2) {
+        if constexpr (MODE == 2) {
             // Upper quantile of the error count by Cornish-Fisher with the Poisson skew bound:
             // j* <~ mu + z*sigma + (z^2-1)/6; K = j* + 1 plus margin (zc holds the constants).
             // An under-estimate only costs one more rung; the result is never affected.
-            double kn = P[0] + a.z * sqrt(P[1]) + a.zc;
+            double kn = (double)P[0] + a.z * sqrt((double)P[1]) + a.zc + 1e-4 * (double)P[0];   // fp32 sums: relative error << 1e-4
             if (!a.exact) {   // a decision needs at most floor(cutoff on the raw statistic) + 2 entries
                 double c = (a.thr_kind == MOIRA_THR_MAXERRORS) ? a.thr : __dmul_rn((double)g.eff, a.thr);
                 if (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) c -= (double)ns;
@@ -673,16 +730,18 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
             maxeff = __reduce_max_sync(FULL, g.eff);
             mineff = __reduce_min_sync(FULL, g.eff);
             continue;
-        }
-        if (MODE == 0) {
+        } else {
+        if constexpr (MODE == 0) {
             res.resolved = cdf_quantile<K>(P, a.oma, res.ee_raw);
             const int kd = (K >= 2 && a.k_dec > K) ? a.k_dec : K;
+            if (K >= 2 && a.direct_rung && a.rung < 0 && !res.resolved && res.processed >= g.eff)   // first pass only: the rungs have their queues read already
+                res.next_rung = rung_from_two_entries(a, P[0], P[K >= 2 ? 1 : 0], g.eff, ns, K);
             if (res.processed < g.eff) { res.resolved = false; res.ee_raw = (double)(kd - 1); }
             else if (kd > K && !res.resolved) {
-                if (newton_bound(P[0], P[K >= 2 ? 1 : 0], kd) < a.oma - 1e-9) res.ee_raw = (double)(kd - 1);   // j* >= kd: a certain reject, without the kd-entry sweep
+                if (cascade_bound<K>(P, kd) < a.oma - 1e-9) res.ee_raw = (double)(kd - 1);   // j* >= kd: a certain reject, without the kd-entry sweep
                 else res.escalate = true;
             }
-        } else {
+        } else if constexpr (MODE == 1) {
             const double lam = P[0];
             if (a.mode == MOIRA_MODE_EXPECTED_ERROR) {
                 res.ee_raw = lam;
@@ -717,6 +776,7 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
             }
         }
         finish_read(a, valid, r_local, g, res, s_cnt, s_hist, lane);
+        }
 
         tile = next_tile;
         valid = nvalid; r_local = nr_local; g = ng;
@@ -724,7 +784,7 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         mineff = __reduce_min_sync(FULL, g.eff);
     }
     // FP64 operations the sweeps of this warp executed (thread level: 32 lanes x 16 positions per vector step)
-    constexpr uint32_t OPB = MODE == 0 ? (uint32_t)(3 * K - 2) + (PL ? 1u : 0u) : (MODE == 1 ? 1u : 2u);
+    constexpr uint32_t OPB = MODE == 0 ? (uint32_t)(3 * K - 2) + (PL ? 1u : 0u) : (MODE == 1 ? 1u : 0u);   // the classifier sums in fp32
     if (lane == 0 && vec_steps && a.counters) atomicAdd(&a.counters[MOIRA_CNT_FP64_OPS], (unsigned long long)vec_steps * (512ull * OPB));
 }
 
@@ -751,6 +811,35 @@ __global__ void __launch_bounds__(tpr_warps(K) * 32, 1) tpr_kernel(const FilterA
 __global__ void policy_kernel(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy)
 {
     *policy = *queue_count > max_pushed ? 1u : 0u;
+}
+
+// Cascade with a first stage of K1 = 2 .. 5 entries (decisions that need k_first = 5 .. 8).  Verdict of the first pilot
+// (two-entry sweep over n_pilot reads, escalations counted in queue 0): at most `max_pushed` handed on -> *policy = 2.
+// Otherwise MOIRA_POLICY_UNDECIDED: the second pilot (k_first-entry sweep, with a histogram of floor(ee)) runs.
+__global__ void policy_first_kernel(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy)
+{
+    *policy = *queue_count > max_pushed ? MOIRA_POLICY_UNDECIDED : 2u;
+}
+// Verdict of the second pilot: the cheapest first stage in issue cycles per base, 2 F + O with F = 3 K - 2 FP64 operations
+// and O = 4.3 others (profiles/r02_k2_regions_before_fix.md), counting every read with j* >= K1 as swept again with k_first
+// entries through the queue (x 1.1: gathered rows, no TMA) -- the Newton bound settles some of them, so the estimate is on
+// the safe side.  floor(ee) >= K1 - 1  <=>  j* >= K1 (up to reads with N, which need fewer entries).  0: single sweep.
+__global__ void policy_second_kernel(const uint32_t *jhist, int k_first, uint32_t *policy)
+{
+    if (*policy != MOIRA_POLICY_UNDECIDED) return;
+    double total = 0.0, tail[17];
+    for (int i = 0; i < 16; i++) total += (double)jhist[i];
+    tail[16] = 0.0;
+    for (int i = 15; i >= 0; i--) tail[i] = tail[i + 1] + (double)jhist[i];
+    const double full = 2.0 * (3 * k_first - 2) + 4.3;
+    double best = full;
+    uint32_t choice = 0;
+    for (int k1 = 3; k1 <= 5 && k1 < k_first; k1++) {
+        const double esc = total > 0.0 ? tail[k1 - 1] / total : 1.0;
+        const double cost = 2.0 * (3 * k1 - 2) + 4.3 + esc * full * 1.1;
+        if (cost < best * 0.97) { best = cost; choice = (uint32_t)k1; }
+    }
+    *policy = choice;
 }
 
 // All thread-per-read rungs of the escalation ladder in ONE launch: the CTA sets its table up once and
@@ -1395,6 +1484,16 @@ int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg0)
 int launch_policy(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s)
 {
     policy_kernel<<<1, 1, 0, s>>>(queue_count, max_pushed, policy);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+int launch_policy_first(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s)
+{
+    policy_first_kernel<<<1, 1, 0, s>>>(queue_count, max_pushed, policy);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+int launch_policy_second(const uint32_t *jhist, int k_first, uint32_t *policy, cudaStream_t s)
+{
+    policy_second_kernel<<<1, 1, 0, s>>>(jhist, k_first, policy);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
