@@ -342,6 +342,13 @@ MOIRA_API int moira_format_records(const moira_records *records, const moira_wri
                                    const int32_t *gaps, const int32_t *mismatches, int n_threads, moira_blocks **out);
 MOIRA_API int moira_blocks_parts(const moira_blocks *blocks, int *n_parts_out);
 MOIRA_API int moira_blocks_get(const moira_blocks *blocks, int part, int which, const char **ptr_out, uint64_t *len_out);
+/* All parts of block kind `which`, in order, to the open file descriptor `fd` at byte `file_offset` (parallel pwrite; the
+ * descriptor's own position is not used or moved).  *written_out = the bytes written. */
+MOIRA_API int moira_blocks_write(const moira_blocks *blocks, int which, int fd, uint64_t file_offset, int n_threads,
+                                 uint64_t *written_out);
+/* Hands a batch back: the next moira_format_records reuses its memory (steady streams of batches).  moira_blocks_free
+ * releases a batch (may be NULL) and everything that was recycled. */
+MOIRA_API int moira_blocks_recycle(moira_blocks *blocks);
 MOIRA_API int moira_blocks_free(moira_blocks *blocks);
 
 /* Header token (offset, length) of every FASTQ record from the position of its sequence line, as moira_filter_fastq_ex

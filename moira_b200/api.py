@@ -715,6 +715,18 @@ class Blocks:
             if len(b):
                 fh.write(b)
 
+    def pwrite(self, which: int, fd: int, offset: int, n_threads: int = 0) -> int:
+        """All parts of one block kind to file descriptor fd at byte `offset` (native, parallel); returns the bytes written."""
+        n = ctypes.c_uint64()
+        L.check(lib.moira_blocks_write(self._h, int(which), int(fd), int(offset), int(n_threads), ctypes.byref(n)))
+        return n.value
+
+    def recycle(self):
+        """Hand the memory back to the library for the next format_records call (steady streams of batches)."""
+        if self._h:
+            lib.moira_blocks_recycle(self._h)
+            self._h = None
+
     def close(self):
         if self._h:
             lib.moira_blocks_free(self._h)

@@ -437,17 +437,22 @@ def _addr(buf) -> int:
 
 
 class Writers:
-    """The output files of write_results (moira.py:323-370), opened in binary mode: the native writer hands over bytes."""
+    """The output files of write_results (moira.py:323-370), opened in binary mode: the native writer hands over bytes.
+    Uncompressed files are written by moira_blocks_write (parallel pwrite at offsets kept here) on a writer thread, one
+    batch of blocks behind the formatter; gz / bz2 files go through Python's compressors."""
 
     def __init__(self, args, output_name):
+        self.native = args.output_compression == "none"
         opener, suffix = {"none": (open, ""), "gz": (gzip.open, ".gz"), "bz2": (bz2.open, ".bz2")}[args.output_compression]
-        self.files, self.names, self.by_block = [], [], {}
+        self.files, self.names, self.by_block, self.pos = [], [], {}, {}
+        self.seconds = 0.0
 
         def op(name, block):
             fh = opener(name + suffix, "wb")
             self.files.append(fh)
             self.names.append(name + suffix)
             self.by_block[block] = fh
+            self.pos[block] = 0
 
         ext = "fastq" if args.output_format == "fastq" else "fasta"
         op("%s.qc.good.%s" % (output_name, ext), L.BLOCK_GOOD)
@@ -461,15 +466,45 @@ class Writers:
             op("%s.qc.bad.names" % output_name, L.BLOCK_BAD_NAMES)
         if args.paired:                                                           # moira.py:366-368
             op("%s.contigs.report" % output_name, L.BLOCK_REPORT)
-            self.by_block[L.BLOCK_REPORT].write(b"header\tn_seqs\toverlap_length\tgaps\tmismatches\n")
+            head = b"header\tn_seqs\toverlap_length\tgaps\tmismatches\n"
+            fh = self.by_block[L.BLOCK_REPORT]
+            fh.write(head)
+            if self.native:
+                fh.flush()
+                self.pos[L.BLOCK_REPORT] = len(head)
+        self._pool = ThreadPoolExecutor(1)
+        self._pending = None
+
+    def _write_now(self, blocks):
+        t0 = time.time()
+        try:
+            for which, fh in self.by_block.items():
+                if self.native:
+                    self.pos[which] += blocks.pwrite(which, fh.fileno(), self.pos[which])
+                else:
+                    blocks.write(which, fh)
+        finally:
+            blocks.recycle()
+            self.seconds += time.time() - t0
 
     def write(self, blocks):
-        for which, fh in self.by_block.items():
-            blocks.write(which, fh)
+        """Queue one batch of formatted blocks (closed when written); returns once the batch before it is on file."""
+        self.drain()
+        self._pending = self._pool.submit(self._write_now, blocks)
+
+    def drain(self):
+        if self._pending is not None:
+            pending, self._pending = self._pending, None
+            pending.result()
 
     def close(self):
-        for fh in self.files:
-            fh.close()
+        try:
+            self.drain()
+        finally:
+            self._pool.shutdown(wait=True)
+            L.lib.moira_blocks_free(None)       # the recycled batches
+            for fh in self.files:
+                fh.close()
 
 
 def resolve_devices(args):
@@ -510,7 +545,9 @@ def run_fastq(args, ctxs, params, lower_n, out):
     context and host thread -- text -> H2D -> parser, slab conversion, filter (and, with --collapse, the exact
     dereplication) on the device, three chunks in flight per GPU."""
     from .api import fastq_headers, fastq_split
+    tp = time.time()
     text, keep = load_text(args.forward_fastq)
+    tp = _phase("load_text", tp)
     rs = ReadSet(args.fastq_offset)
     rs.keep.append((text, keep))
     D = len(ctxs)
@@ -544,6 +581,7 @@ def run_fastq(args, ctxs, params, lower_n, out):
             results = list(pool.map(work, range(D)))
     else:
         results = [work(0)]
+    tp = _phase("moira_filter_fastq_ex (all GPUs)", tp)
     base_addr = _addr(text) if text.size else 0
     read_base = 0
     per_ctx = []
@@ -567,7 +605,9 @@ def run_fastq(args, ctxs, params, lower_n, out):
     if want_labels and not all_labelled:
         rs.labels = None
     rs.label_shards = D if (rs.labels is not None and D > 1) else 1
+    tp = _phase("headers + read set", tp)
     rs.counters = reduce_run_counters(ctxs, per_ctx, out)
+    tp = _phase("counters all-reduce", tp)
     return rs
 
 
@@ -671,6 +711,15 @@ def _string_at(addr, n):
     return ctypes.string_at(int(addr), int(n)).decode("latin-1")
 
 
+_T_PHASES = []
+
+
+def _phase(name, t0):
+    """MOIRA_B200_CLI_TIMING=1: wall-clock seconds of the host phases, printed with the summary."""
+    _T_PHASES.append((name, time.time() - t0))
+    return time.time()
+
+
 def finish_run(args, rs, writers, out):
     """The collapse dictionary, the abundance sort, write_results' precedence of rules and the final counts -- on arrays;
     formatting is moira_format_records (native, all host threads).  Returns (processed, errors, minlength, minoverlap)."""
@@ -678,6 +727,7 @@ def finish_run(args, rs, writers, out):
     n = rs.n
     if n == 0:
         return 0, 0, 0, 0
+    tp = time.time()
     numeric = (rs.flags & L.FLAG_NUMERIC) != 0
     if numeric.any() or np.isnan(rs.ee).any():                                   # moira.py:456-457
         bad = int(np.flatnonzero(numeric | np.isnan(rs.ee))[0])
@@ -702,7 +752,7 @@ def finish_run(args, rs, writers, out):
     stats = None if rs.stats is None else (rs.stats[:, 0], rs.stats[:, 1], rs.stats[:, 2])
     common = dict(fastq=args.output_format == "fastq", fastq_offset=args.fastq_offset, usearch=args.pipeline == "USEARCH",
                   relabel=args.relabel, notes=notes, stats=stats)
-    CHUNK = 1 << 20
+    CHUNK = 1 << 18
     if args.collapse:
         # moira.py:459-475 + 491-504: groups by first appearance, representative = first read with the strictly smallest
         # ee, names in the reference's order, output by abundance
@@ -715,23 +765,26 @@ def finish_run(args, rs, writers, out):
             lut = np.arange(n, dtype=np.uint32)
             lut[owners] = owners[oc.rep[oc.group_of_read]].astype(np.uint32)
             labels = lut[labels]
+        tp = _phase("decision arrays", tp)
         col = collapse_labels(labels, rs.ee) if labels is not None else collapse(None, rs.seq_addr, out_len, rs.ee)
         sel, sel_group = col.rep[col.order], col.order
         sizes = col.size[col.order].astype(np.int64)
+        tp = _phase("groups", tp)
         for k0 in range(0, sel.size, CHUNK):
             k1 = min(sel.size, k0 + CHUNK)
             blocks = format_records(rec, sel[k0:k1], rs.ee, accept, reason, names=args.pipeline == "mothur", first_index=1 + k0,
                                     sel_group=sel_group[k0:k1], member_start=col.member_start, members=col.members, **common)
             writers.write(blocks)
-            blocks.close()
         acc_s, rsn_s = accept[sel], reason[sel]
     else:
+        tp = _phase("decision arrays", tp)
         for k0 in range(0, n, CHUNK):
             k1 = min(n, k0 + CHUNK)
             blocks = format_records(rec, np.arange(k0, k1, dtype=np.uint64), rs.ee, accept, reason, first_index=k0, **common)
             writers.write(blocks)
-            blocks.close()
         acc_s, rsn_s, sizes = accept, reason, np.ones(n, np.int64)
+    writers.drain()
+    tp = _phase("format + write (writer thread busy %.2f s)" % writers.seconds, tp)
     rej = acc_s == 0
     minlength = int(sizes[rej & (rsn_s == L.REASON_LENGTH)].sum())
     minoverlap = int(sizes[rej & (rsn_s == REASON_OVERLAP)].sum())
@@ -771,9 +824,11 @@ def main(args, out=sys.stdout) -> int:
         return 1
 
     t0 = time.time()
+    del _T_PHASES[:]
     ctxs = []
     try:
         ctxs = [Context(d) for d in resolve_devices(args)]
+        _phase("contexts", t0)
         if args.paired:
             rs = run_pairs(args, ctxs, params, lower_n, contig_params, out)
         elif args.forward_fastq:
@@ -787,6 +842,9 @@ def main(args, out=sys.stdout) -> int:
         for c in ctxs:
             c.close()
 
+    if os.environ.get("MOIRA_B200_CLI_TIMING") == "1":
+        for name, sec in _T_PHASES:
+            print("  [timing] %-60s %.3f s" % (name, sec), file=out)
     if not args.silent and processed:
         print("%d sequences processed in %.1f seconds (%.1f s to the decisions, %d GPU%s)." %
               (processed, time.time() - t0, t_filter, len(ctxs), "" if len(ctxs) == 1 else "s"), file=out)

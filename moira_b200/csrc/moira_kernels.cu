@@ -398,36 +398,63 @@ __device__ __forceinline__ uint32_t lut_addr_of(uint32_t w, uint32_t lut_lane)
 {
     return __byte_perm(w, lut_lane, 0x7604u | (B << 4));
 }
-// The per-base work on one 16-byte vector already in registers.
+// The per-base work on the four bases of one quality word.
 template <int K, int MODE, bool PL, typename T>
-__device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_lane, T (&P)[K])
+__device__ __forceinline__ void sweep_word(uint32_t wi, uint32_t lut_lane, T (&P)[K])
 {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const uint32_t addr = __byte_perm(w[i], lut_lane, 0x7604u | (b << 4));   // table | Q << 8 | replica
-            if (MODE == 0) {
-                double q, e;
-                if (PL) {
-                    e = lds_f64(addr);
-                    q = __dsub_rn(1.0, e);                 // (1 - p), bernoullimodule.c:140
-                } else {
-                    const double2 qe = lds_f64x2(addr);
-                    q = qe.x; e = qe.y;
-                }
-#pragma unroll
-                for (int j = K - 1; j >= 1; j--)
-                    P[j] = __dadd_rn(__dmul_rn(q, P[j]), __dmul_rn(e, P[j - 1]));
-                P[0] = __dmul_rn(q, P[0]);
-            } else if (MODE == 1) {
-                P[0] = __dadd_rn(P[0], lds_f64(addr));     // moira.py:1663, in index order
+    for (int b = 0; b < 4; b++) {
+        const uint32_t addr = __byte_perm(wi, lut_lane, 0x7604u | (b << 4));   // table | Q << 8 | replica
+        if (MODE == 0) {
+            double q, e;
+            if (PL) {
+                e = lds_f64(addr);
+                q = __dsub_rn(1.0, e);                 // (1 - p), bernoullimodule.c:140
             } else {
-                const float2 t = lds_f32x2(addr);          // classifier: mean and variance of the error count (fp32: an estimate)
-                P[0] += t.x;
-                P[1] += t.y;
+                const double2 qe = lds_f64x2(addr);
+                q = qe.x; e = qe.y;
             }
+#pragma unroll
+            for (int j = K - 1; j >= 1; j--)
+                P[j] = __dadd_rn(__dmul_rn(q, P[j]), __dmul_rn(e, P[j - 1]));
+            P[0] = __dmul_rn(q, P[0]);
+        } else if (MODE == 1) {
+            P[0] = __dadd_rn(P[0], lds_f64(addr));     // moira.py:1663, in index order
+        } else {
+            const float2 t = lds_f32x2(addr);          // classifier: mean and variance of the error count (fp32: an estimate)
+            P[0] += t.x;
+            P[1] += t.y;
         }
+    }
+}
+// The per-base work on one 16-byte vector already in registers.  ROLL = 1 / 2 keeps the loop over the four words rolled
+// (one / two words per iteration): the ladder kernel -- every K in one kernel, 14 .. 50 KB of unrolled 16-base body per K --
+// streamed its code through the instruction caches (ncu: 9 % of its warp states were no_instruction).  The single-K first
+// pass kernels keep the unrolled body (rolled: -4 % on the K = 18 sweep of 1 500-bp reads).
+#ifndef MOIRA_LADDER_ROLL
+#define MOIRA_LADDER_ROLL 1
+#endif
+#ifndef MOIRA_ROLL_MINK
+#define MOIRA_ROLL_MINK 12
+#endif
+template <int K, int MODE, bool PL, int ROLL, typename T>
+__device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_lane, T (&P)[K])
+{
+    if constexpr (MODE == 0 && ROLL == 1 && K >= MOIRA_ROLL_MINK) {
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+            const uint32_t wi = i == 0 ? w[0] : (i == 1 ? w[1] : (i == 2 ? w[2] : w[3]));
+            sweep_word<K, MODE, PL, T>(wi, lut_lane, P);
+        }
+    } else if constexpr (MODE == 0 && ROLL == 2 && K >= MOIRA_ROLL_MINK) {
+#pragma unroll 1
+        for (int i = 0; i < 2; i++) {
+            sweep_word<K, MODE, PL, T>(i == 0 ? w[0] : w[2], lut_lane, P);
+            sweep_word<K, MODE, PL, T>(i == 0 ? w[1] : w[3], lut_lane, P);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) sweep_word<K, MODE, PL, T>(w[i], lut_lane, P);
     }
 }
 
@@ -437,7 +464,7 @@ __device__ __forceinline__ void sweep_vec(const uint32_t (&w)[4], uint32_t lut_l
 // MATH = false keeps only the N/n accounting (after a warp-wide early exit).
 // `swz` is the lane's XOR term of the TMA 128-byte swizzle ((lane & 7) << 4), 0 for the padded layout.
 // MARKS = false: Ns / has-N of every row came with the slab (FilterArgs::row_marks), nothing is counted here.
-template <int K, int MODE, bool PL, bool MATH, bool MARKS, typename T>
+template <int K, int MODE, bool PL, bool MATH, bool MARKS, int ROLL, typename T>
 __device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t swz, uint32_t cfull, uint32_t cend, int rem0,
                                             uint32_t lut_lane, T (&P)[K], uint32_t &ns, uint32_t &has_n)
 {
@@ -447,12 +474,12 @@ __device__ __forceinline__ void sweep_chunk(uint32_t row, uint32_t swz, uint32_t
         const uint4 q4 = lds128(row + (v ^ swz));
         const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
         if (MARKS) count_marks4(w, ns, has_n);
-        if (MATH) sweep_vec<K, MODE, PL, T>(w, lut_lane, P);
+        if (MATH) sweep_vec<K, MODE, PL, ROLL, T>(w, lut_lane, P);
     }
     for (; v < cend; v += 16) {
         uint32_t w[4];
         load_vec<MARKS>(row + (v ^ swz), rem0 - (int)v, w, ns, has_n);
-        if (MATH) sweep_vec<K, MODE, PL, T>(w, lut_lane, P);
+        if (MATH) sweep_vec<K, MODE, PL, ROLL, T>(w, lut_lane, P);
     }
 }
 
@@ -533,7 +560,7 @@ __device__ __forceinline__ TprCtx tpr_setup(const FilterArgs &a, uint8_t *smem)
 // The persistent tile loop of one warp: tiles first_tile, first_tile + tile_step, ... of `count` reads
 // (taken through `queue` when it is not null), K PMF entries per read.  All staging state is local, so
 // a CTA may call this several times with different K (ladder kernel).
-template <int K, int MODE, bool PL, bool TMA>
+template <int K, int MODE, bool PL, bool TMA, int ROLL = 0>
 __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap *tmap_ptr, const TprCtx &ctx,
                                           const uint32_t *queue, uint32_t count, uint32_t first_tile, uint32_t total_warps)
 {
@@ -671,12 +698,12 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
             const uint32_t cend = maxeff - cbeg < CHUNK ? maxeff - cbeg : CHUNK;   // warp-uniform
             const uint32_t cfull = mineff > cbeg ? min((mineff - cbeg) & ~15u, cend) : 0u;   // warp-uniform
             if (!skip_math) {
-                if (marks_given) sweep_chunk<K, MODE, PL, true, false, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
-                else sweep_chunk<K, MODE, PL, true, true, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+                if (marks_given) sweep_chunk<K, MODE, PL, true, false, ROLL, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+                else sweep_chunk<K, MODE, PL, true, true, ROLL, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
                 processed = cbeg + cend;
                 vec_steps += (cend + 15u) >> 4;
             } else if (!marks_given) {
-                sweep_chunk<K, MODE, PL, false, true, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
+                sweep_chunk<K, MODE, PL, false, true, ROLL, acc_t>(row, swz, cfull, cend, (int)g.eff - (int)cbeg, lut_lane, P, ns, has_n);
             }
             if constexpr (MODE == 0) if (c + 1 < nch && !skip_math) {
                 // Early exit: sum_{j<K} P_k[j] never increases with k, so once it is safely below
@@ -867,7 +894,7 @@ __global__ void __launch_bounds__(256, 1) ladder_tpr_kernel(const FilterArgs a0)
 #define MOIRA_RUNG(r, k)                                                                                      \
     if (counts[r]) {                                                                                          \
         const uint32_t first = (gw + W - before % W) % W;                                                     \
-        tpr_tiles<k, 0, EQP, false>(a, nullptr, ctx, a0.queues + (size_t)(r) * a0.queue_cap, counts[r], first, W); \
+        tpr_tiles<k, 0, EQP, false, MOIRA_LADDER_ROLL>(a, nullptr, ctx, a0.queues + (size_t)(r) * a0.queue_cap, counts[r], first, W); \
         before += (counts[r] + 31) >> 5;                                                                      \
     }
     MOIRA_RUNG(1, 3) MOIRA_RUNG(2, 4) MOIRA_RUNG(3, 5) MOIRA_RUNG(4, 6) MOIRA_RUNG(5, 7)

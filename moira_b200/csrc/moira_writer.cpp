@@ -3,9 +3,12 @@
 // ";ee=%.2f;size=%d;" header, --relabel, the rejection reason behind the header, the contigs report -- produced from the
 // byte ranges the parsers (host or device) and the contig kernel left behind, on all host threads, into memory
 // blocks the host program only has to write to its files.  The accept / reject decision itself is the device's.
+#include <errno.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -19,6 +22,12 @@ struct moira_blocks {
 };
 
 namespace {
+
+// formatted batches follow each other at a steady size: a finished batch handed back with moira_blocks_recycle keeps its
+// strings' capacity for the next moira_format_records (fresh gigabytes of heap per batch cost more page faults than formatting)
+std::mutex g_pool_mu;
+std::vector<moira_blocks *> g_pool;
+constexpr size_t POOL_MAX = 3;
 
 inline void put_uint(std::string &o, uint64_t v)
 {
@@ -66,10 +75,16 @@ int moira_format_records(const moira_records *rec, const moira_write_opts *opt, 
     if (T < 1) T = 1;
     if (T > 64) T = 64;
     const int parts = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)T * 4, n_sel / 2048 + 1));
-    moira_blocks *b = new (std::nothrow) moira_blocks();
+    moira_blocks *b = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool.empty()) { b = g_pool.back(); g_pool.pop_back(); }
+    }
+    if (!b) b = new (std::nothrow) moira_blocks();
     if (!b) return fail(MOIRA_ERR_NOMEM, "out of host memory");
     b->n_parts = parts;
-    b->buf.resize((size_t)parts * MOIRA_BLOCK_N);
+    if (b->buf.size() < (size_t)parts * MOIRA_BLOCK_N) b->buf.resize((size_t)parts * MOIRA_BLOCK_N);
+    for (auto &str : b->buf) str.clear();   // keeps the capacity of a recycled batch
     const bool has_stats = overlap && gaps && mismatches;
     const size_t relabel_len = opt->relabel ? strlen(opt->relabel) : 0;
     bool failed = false;
@@ -79,6 +94,34 @@ int moira_format_records(const moira_records *rec, const moira_write_opts *opt, 
             std::string hdr;
             char tmp[64];
             const uint64_t k0 = n_sel * (uint64_t)p / parts, k1 = n_sel * (uint64_t)(p + 1) / parts;
+            {   // size the blocks once (growing them by doubling copies every byte again and faults fresh pages each time)
+                uint64_t good_b = 0, bad_b = 0, good_n = 0, bad_n = 0, good_m = 0, bad_m = 0;
+                for (uint64_t k = k0; k < k1; k++) {
+                    const uint64_t r = sel ? sel[k] : k;
+                    const uint64_t hl = (relabel_len ? relabel_len + 20 : rec->hdr_len[r]) + (opt->usearch ? 48 : 0) + 40;
+                    uint64_t mem = 0;
+                    if (opt->names) {
+                        const uint64_t m0 = member_start[sel_group[k]], m1 = member_start[sel_group[k] + 1];
+                        mem = hl + 2 + (m1 - m0) * (uint64_t)(rec->hdr_len[r] + 12);   // members' headers: about the representative's length
+                    }
+                    if (accept[r]) { good_b += rec->len[r]; good_n += hl; good_m += mem; }
+                    else { bad_b += rec->len[r]; bad_n += hl; bad_m += mem; }
+                }
+                const uint64_t recs = k1 - k0;
+                if (opt->fastq) {
+                    o[MOIRA_BLOCK_GOOD].reserve(2 * good_b + good_n + 8 * recs);
+                    o[MOIRA_BLOCK_BAD].reserve(2 * bad_b + bad_n + 8 * recs);
+                } else {
+                    o[MOIRA_BLOCK_GOOD].reserve(good_b + good_n + 4 * recs);
+                    o[MOIRA_BLOCK_BAD].reserve(bad_b + bad_n + 4 * recs);
+                    o[MOIRA_BLOCK_GOOD_QUAL].reserve(3 * good_b + good_b / 8 + good_n + 4 * recs);
+                    o[MOIRA_BLOCK_BAD_QUAL].reserve(3 * bad_b + bad_b / 8 + bad_n + 4 * recs);
+                }
+                if (opt->names) {
+                    o[MOIRA_BLOCK_GOOD_NAMES].reserve(good_m);
+                    o[MOIRA_BLOCK_BAD_NAMES].reserve(bad_m);
+                }
+            }
             for (uint64_t k = k0; k < k1; k++) {
                 const uint64_t r = sel ? sel[k] : k;
                 const uint32_t L = rec->len[r];
@@ -117,14 +160,20 @@ int moira_format_records(const moira_records *rec, const moira_write_opts *opt, 
                     main.append(s, L);
                     main.push_back('\n');
                     ql.push_back('>'); ql += hdr; ql += note; ql.push_back('\n');
-                    for (uint32_t i = 0; i < L; i++) {
-                        if (i) ql.push_back(' ');
-                        const int v = qual_value(q[i], rec->qual_sub);
-                        if (v >= 100) ql.push_back((char)('0' + v / 100));
-                        if (v >= 10) ql.push_back((char)('0' + (v / 10) % 10));
-                        ql.push_back((char)('0' + v % 10));
+                    {   // "%d %d ... %d\n": at most four bytes per value
+                        const size_t at = ql.size();
+                        ql.resize(at + 4 * (size_t)L + 1);
+                        char *w = &ql[at];
+                        for (uint32_t i = 0; i < L; i++) {
+                            if (i) *w++ = ' ';
+                            const int v = qual_value(q[i], rec->qual_sub);
+                            if (v >= 100) *w++ = (char)('0' + v / 100);
+                            if (v >= 10) *w++ = (char)('0' + (v / 10) % 10);
+                            *w++ = (char)('0' + v % 10);
+                        }
+                        *w++ = '\n';
+                        ql.resize((size_t)(w - ql.data()));
                     }
-                    ql.push_back('\n');
                 }
                 if (opt->names) {   // "%s\t%s\n" % (header, ','.join(names_info)): the members' own headers, names order
                     std::string &nm = o[good ? MOIRA_BLOCK_GOOD_NAMES : MOIRA_BLOCK_BAD_NAMES];
@@ -162,8 +211,56 @@ int moira_blocks_get(const moira_blocks *b, int part, int which, const char **pt
     return MOIRA_OK;
 }
 
+// All parts of one block kind, in order, to file descriptor `fd` at `file_offset` (pwrite, the parts side by side on the
+// host threads: page-cache copies scale with the writers).  The caller keeps the file position: *written_out is what to add.
+int moira_blocks_write(const moira_blocks *b, int which, int fd, uint64_t file_offset, int n_threads, uint64_t *written_out)
+{
+    if (!b || !written_out || which < 0 || which >= MOIRA_BLOCK_N || fd < 0) return moira::fail(MOIRA_ERR_BAD_ARG, "bad argument");
+    std::vector<uint64_t> at((size_t)b->n_parts + 1, file_offset);
+    for (int p = 0; p < b->n_parts; p++) at[(size_t)p + 1] = at[p] + b->buf[(size_t)p * MOIRA_BLOCK_N + which].size();
+    *written_out = at[b->n_parts] - file_offset;
+    if (*written_out == 0) return MOIRA_OK;
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 16) T = 16;
+    int err = 0;
+    moira::parallel_run(b->n_parts, T, [&](int p) {
+        const std::string &s = b->buf[(size_t)p * MOIRA_BLOCK_N + which];
+        size_t done = 0;
+        while (done < s.size()) {
+            const ssize_t w = pwrite(fd, s.data() + done, s.size() - done, (off_t)(at[p] + done));
+            if (w < 0) {
+                if (errno == EINTR) continue;
+                err = errno;
+                return;
+            }
+            done += (size_t)w;
+        }
+    });
+    if (err) return moira::fail(MOIRA_ERR_BAD_ARG, "pwrite failed: %s", strerror(err));
+    return MOIRA_OK;
+}
+
+// Hand a batch back for reuse by the next moira_format_records (at most a few are kept; the rest are freed).
+int moira_blocks_recycle(moira_blocks *b)
+{
+    if (!b) return MOIRA_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < POOL_MAX) { g_pool.push_back(b); return MOIRA_OK; }
+    }
+    delete b;
+    return MOIRA_OK;
+}
+
+// Frees the batch and every recycled one.
 int moira_blocks_free(moira_blocks *b)
 {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (moira_blocks *x : g_pool) delete x;
+        g_pool.clear();
+    }
     delete b;
     return MOIRA_OK;
 }
