@@ -140,12 +140,23 @@ def collapse_bench(ctx, w, px, world, barrier, max_over_ranks):
     e2.record()
     barrier()
     ms_filter, ms_dedup = max_over_ranks(e0.elapsed_time(e1)) / reps, max_over_ranks(e1.elapsed_time(e2)) / reps
-    # host half: D2H of labels + ee, groups / representatives / names order / abundance order
+    # groups / representatives / names order / abundance order from labels + ee
+    ee_fin = (w.ee + w.ns.to(torch.float64)).contiguous()             # the value process_data returns (treat_as_errors)
+    torch.cuda.synchronize()
+    col = ctx.collapse_groups(labels.data_ptr(), ee_fin.data_ptr(), n)     # (the first call allocates the scratch)
+    barrier()
+    t0 = time.perf_counter()
+    col = ctx.collapse_groups(labels.data_ptr(), ee_fin.data_ptr(), n)     # device passes + D2H of the six uint32 arrays (pinned)
+    t_host = max_over_ranks(time.perf_counter() - t0)
+    n_groups, largest = int(col.rep.shape[0]), int(col.size.max()) if n else 0
+    dev_arrays = {f: np.array(getattr(col, f), dtype=np.uint64) for f in ("group_of_read", "rep", "size", "member_start", "members", "order")}
     t0 = time.perf_counter()
     lab_h = labels.cpu().numpy().view(np.uint32)
-    ee_h = w.ee.cpu().numpy() + w.ns.cpu().numpy()                    # the value process_data returns (treat_as_errors)
-    col = moira_b200.collapse_labels(lab_h, ee_h)
-    t_host = max_over_ranks(time.perf_counter() - t0)
+    ee_h = ee_fin.cpu().numpy()
+    col_host = moira_b200.collapse_labels(lab_h, ee_h)                # the host version, D2H of labels + ee included
+    t_hostgroups = max_over_ranks(time.perf_counter() - t0)
+    groups_differ = sum(int(not np.array_equal(dev_arrays[f], getattr(col_host, f))) for f in dev_arrays)
+    del dev_arrays
     # parity on a bounded sample: device labels of the sample alone -> groups == host hash + memcmp collapse
     k = min(n, 200_000)
     sub = w.seqs[:k].contiguous()
@@ -160,16 +171,20 @@ def collapse_bench(ctx, w, px, world, barrier, max_over_ranks):
     got = moira_b200.collapse_labels(sub_lab.cpu().numpy().view(np.uint32), ee_h[:k])
     mism = sum(int(not np.array_equal(getattr(got, f), getattr(want, f))) for f in ("group_of_read", "rep", "size", "member_start", "members", "order"))
     total_ms = ms_filter + ms_dedup + t_host * 1e3
-    return {"reads_per_gpu": n, "groups": int(col.rep.shape[0]), "largest_group": int(col.size.max()) if n else 0,
-            "filter_exact_ms": ms_filter, "dedup_kernels_ms": ms_dedup, "host_groups_ms": t_host * 1e3,
+    return {"reads_per_gpu": n, "groups": n_groups, "largest_group": largest,
+            "filter_exact_ms": ms_filter, "dedup_kernels_ms": ms_dedup, "groups_device_ms": t_host * 1e3,
+            "groups_host_ms": t_hostgroups * 1e3, "device_groups_arrays_differing_from_host_groups": groups_differ,
             "dedup_kernels_value": world * n / (ms_dedup * 1e-3), "dedup_seq_gb_per_s": n * L_ * 2 / (ms_dedup * 1e-3) / 1e9,
             "exact_plus_collapse_value": world * n / (total_ms * 1e-3), "filter_only_value": world * n / (ms_filter * 1e-3),
             "slowdown_vs_filter_only": total_ms / ms_filter, "unit": "reads/s",
             "host_collapse_sample": {"reads": k, "value": k / t_hostcollapse, "unit": "reads/s",
                                     "note": "moira_collapse (hash + memcmp on all host threads) over the sample's strings"},
             "parity": {"sample_reads_per_rank": k, "arrays_differing_from_host_collapse": mism},
-            "note": "device: 128-bit hash + exact byte compare of the HBM-resident sequences -> labels; host: D2H of labels and ee, "
-                    "groups / representatives / names order / abundance order from the labels (no base is read on the host)"}
+            "note": "device: 128-bit hash + exact byte compare of the HBM-resident sequences -> labels (moira_collapse_device); "
+                    "groups / representatives / names order / abundance order from labels + ee on the device too "
+                    "(moira_collapse_groups on the device-resident labels and ee: device passes + D2H of the six uint32 result arrays into "
+                    "pinned host memory inside groups_device_ms; groups_host_ms is the host version, moira_collapse_labels, with its "
+                    "D2H of labels + ee, for comparison)"}
 
 
 def make_cli_fastq(slab_rows, seed):

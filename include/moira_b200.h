@@ -279,6 +279,20 @@ MOIRA_API int moira_collapse_device(moira_ctx *ctx, const uint8_t *d_seq, const 
 MOIRA_API int moira_collapse_labels(const uint32_t *labels, const double *ee, uint64_t n, uint64_t *group_of_read,
                                     uint64_t *n_groups_out, uint64_t *group_rep, uint64_t *group_size,
                                     uint64_t *member_start, uint64_t *members, uint64_t *abundance_order);
+/* The same outputs computed on the device (csrc/moira_groups.cu: first-appearance numbering by atomicMin + scan, stable
+ * radix sort by group, running minimum of ee by key, stable sort by size): labels / ee and all outputs are HOST arrays
+ * (uint32 on the device and over PCIe).  n < 2^31.  Results are identical to moira_collapse_labels'. */
+/* The device version without the widening copy: labels / ee are host arrays, or -- on_device != 0 -- device arrays (the
+ * outputs of moira_collapse_device and of the filter); the six result arrays are uint32 views of pinned host memory owned
+ * by the context, valid until its next moira_collapse_groups / moira_collapse_labels_device call. */
+MOIRA_API int moira_collapse_groups(moira_ctx *ctx, const uint32_t *labels, const double *ee, int on_device, uint64_t n,
+                                    uint64_t *n_groups_out, const uint32_t **group_of_read, const uint32_t **group_rep,
+                                    const uint32_t **group_size, const uint32_t **member_start, const uint32_t **members,
+                                    const uint32_t **abundance_order);
+MOIRA_API int moira_collapse_labels_device(moira_ctx *ctx, const uint32_t *labels, const double *ee, uint64_t n,
+                                           uint64_t *group_of_read, uint64_t *n_groups_out, uint64_t *group_rep,
+                                           uint64_t *group_size, uint64_t *member_start, uint64_t *members,
+                                           uint64_t *abundance_order);
 
 /* Dereplication of identical sequences, the reference's --collapse (moira.py:459-475, 491-504), on
  * all host threads.  Read r's (already truncated) sequence is text[seq_off[r] .. + seq_len[r]) (text == NULL: seq_off

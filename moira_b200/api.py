@@ -382,6 +382,42 @@ class Context:
         L.check(lib.moira_collapse_device(self._h, d_seq, d_offsets, d_lengths, int(stride), int(fixed_length), int(n_reads),
                                           int(truncate), d_labels, stream))
 
+    def collapse_labels(self, labels, ee) -> "CollapseResult":
+        """moira_collapse_labels_device: groups, representatives, names order and abundance order from labels and ee, computed
+        on this context's GPU (host arrays in and out); identical to the module-level collapse_labels (host)."""
+        labels = _as(labels, np.uint32)
+        ee = _as(ee, np.float64)
+        n = int(labels.shape[0])
+        g_of, rep, size = np.empty(n, np.uint64), np.empty(n, np.uint64), np.empty(n, np.uint64)
+        mstart, members, order = np.empty(n + 1, np.uint64), np.empty(n, np.uint64), np.empty(n, np.uint64)
+        ng = ctypes.c_uint64()
+        L.check(lib.moira_collapse_labels_device(self._h, _ptr(labels), _ptr(ee), n, _ptr(g_of), ctypes.byref(ng), _ptr(rep),
+                                                 _ptr(size), _ptr(mstart), _ptr(members), _ptr(order)))
+        G = ng.value
+        return CollapseResult(g_of, rep[:G], size[:G], mstart[:G + 1], members, order[:G])
+
+    def collapse_groups(self, labels, ee, n: int | None = None) -> "CollapseResult":
+        """moira_collapse_groups: as collapse_labels, without the widening copy -- the result arrays are uint32 views of the
+        context's pinned memory (valid until the next collapse call on this context).  labels / ee: numpy arrays, or device
+        pointers (ints) together with n."""
+        on_device = isinstance(labels, int)
+        if on_device:
+            lp, ep, n = ctypes.c_void_p(labels), ctypes.c_void_p(ee), int(n)
+        else:
+            labels, ee = _as(labels, np.uint32), _as(ee, np.float64)
+            lp, ep, n = _ptr(labels), _ptr(ee), int(labels.shape[0])
+        ng = ctypes.c_uint64()
+        ptrs = [ctypes.c_void_p() for _ in range(6)]
+        L.check(lib.moira_collapse_groups(self._h, lp, ep, 1 if on_device else 0, n, ctypes.byref(ng), *[ctypes.byref(p) for p in ptrs]))
+        G = ng.value
+        counts = [n, G, G, G + 1, n, G]
+
+        def view(p, c):
+            if not c or not p.value:
+                return np.empty(0, np.uint32)
+            return np.ctypeslib.as_array((ctypes.c_uint32 * c).from_address(p.value))
+        return CollapseResult(*[view(p, c) for p, c in zip(ptrs, counts)])
+
     def filter_pairs(self, fwd_seq, fwd_qual, fwd_off, fwd_len, rev_seq, rev_qual, rev_off, rev_len,
                      contig_params: ContigParams, filter_params: FilterParams | None = None,
                      lower_n_ambiguous: bool = True, fwd_qual_off=None, rev_qual_off=None, qual_base: int = 0,

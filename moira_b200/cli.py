@@ -521,11 +521,14 @@ def resolve_devices(args):
 
 
 def reduce_run_counters(ctxs, per_ctx, out):
-    """The path's only collective: per-GPU counters -> their sum, by NCCL inside the library
-    (moira_reduce_counters_all) when the run used more than one GPU."""
+    """The path's only exchange: per-GPU counters -> their sum.  All contexts of a CLI run live in this one
+    process, so the sum is taken on the host: an NCCL communicator for 640 bytes costs seconds to build and to tear down
+    (measured: 3.3 s + 3 s on two B200s against 2.5 s for the whole 10 M-read run).  Hosts with one process per GPU use
+    moira_comm_init + moira_reduce_counters (NCCL over NVLink, inside the library) as bench.py does; MOIRA_B200_CLI_NCCL=1
+    makes the CLI take that route too (moira_comm_init_all / moira_reduce_counters_all)."""
     if len(ctxs) == 1:
         return per_ctx[0]
-    if len({c.device for c in ctxs}) < len(ctxs):       # several contexts on one GPU (tests): NCCL has one rank per GPU
+    if os.environ.get("MOIRA_B200_CLI_NCCL") != "1" or len({c.device for c in ctxs}) < len(ctxs):
         return np.sum(per_ctx, axis=0).astype(np.uint64)
     from .api import comm_init_all, reduce_counters_all
     try:
@@ -720,7 +723,7 @@ def _phase(name, t0):
     return time.time()
 
 
-def finish_run(args, rs, writers, out):
+def finish_run(args, rs, writers, out, ctx=None):
     """The collapse dictionary, the abundance sort, write_results' precedence of rules and the final counts -- on arrays;
     formatting is moira_format_records (native, all host threads).  Returns (processed, errors, minlength, minoverlap)."""
     from .api import RecordView, collapse_labels, format_records
@@ -766,7 +769,21 @@ def finish_run(args, rs, writers, out):
             lut[owners] = owners[oc.rep[oc.group_of_read]].astype(np.uint32)
             labels = lut[labels]
         tp = _phase("decision arrays", tp)
-        col = collapse_labels(labels, rs.ee) if labels is not None else collapse(None, rs.seq_addr, out_len, rs.ee)
+        if labels is None:
+            col = collapse(None, rs.seq_addr, out_len, rs.ee)
+        else:
+            col = None
+            if ctx is not None and n < (1 << 31):
+                try:
+                    v = ctx.collapse_groups(labels, rs.ee)         # groups / representatives / orders on the GPU (uint32 views)
+                    from .api import CollapseResult
+                    col = CollapseResult(*[np.asarray(getattr(v, f), dtype=np.uint64) for f in
+                                           ("group_of_read", "rep", "size", "member_start", "members", "order")])
+                except MoiraError as exc:
+                    if exc.code != L.ERR_NOMEM:
+                        raise
+            if col is None:
+                col = collapse_labels(labels, rs.ee)
         sel, sel_group = col.rep[col.order], col.order
         sizes = col.size[col.order].astype(np.int64)
         tp = _phase("groups", tp)
@@ -836,7 +853,7 @@ def main(args, out=sys.stdout) -> int:
         else:
             rs = run_fasta_qual(args, ctxs, params, lower_n, out)
         t_filter = time.time() - t0
-        processed, discarded_errors, discarded_minlength, discarded_minoverlap = finish_run(args, rs, writers, out)
+        processed, discarded_errors, discarded_minlength, discarded_minoverlap = finish_run(args, rs, writers, out, ctxs[0] if ctxs else None)
     finally:
         writers.close()
         for c in ctxs:

@@ -184,6 +184,10 @@ struct moira_ctx {
     CommState *comm = nullptr;   // communicator rank for the counters' all-reduce (moira_comm.cpp), created on demand
     // dereplication on the device (moira_dedup.cu): hashes, table, labels; the FASTQ path's sequence store and its index
     DevBuf dd_hash, dd_table, dd_labels, dd_store, dd_seq_abs, dd_seq_eff;
+    // groups from labels on the device (moira_groups.cu): device scratch and the pinned landing zone of its results
+    DevBuf grp_dev;
+    uint8_t *grp_host = nullptr;
+    size_t grp_host_cap = 0;
     // single-read scratch (pinned)
     uint8_t *one_slab = nullptr;
     size_t one_cap = 0;
@@ -216,6 +220,21 @@ void build_tables(double *h_p, double *h_q, double *h_e, int *eqp)
         volatile double omp = 1.0 - h_p[b];
         if (h_e[b] != h_p[b] || h_q[b] != omp) *eqp = 0;
     }
+}
+
+// pinned host memory that only grows
+int ensure_host(uint8_t **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return MOIRA_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    if (cudaHostAlloc((void **)p, want, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MOIRA_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", want);
+    }
+    *cap = want;
+    return MOIRA_OK;
 }
 
 int ensure(DevBuf &b, size_t bytes)
@@ -667,8 +686,9 @@ int moira_ctx_destroy(moira_ctx *c)
         if (pb.stage) cudaFreeHost(pb.stage);
     }
     for (DevBuf *b : {&c->trace, &c->hbuf, &c->post, &c->pair_counters, &c->dd_hash, &c->dd_table, &c->dd_labels, &c->dd_store,
-                      &c->dd_seq_abs, &c->dd_seq_eff})
+                      &c->dd_seq_abs, &c->dd_seq_eff, &c->grp_dev})
         if (b->p) cudaFree(b->p);
+    if (c->grp_host) cudaFreeHost(c->grp_host);
     for (auto &w : c->ws) {
         if (w.queues) cudaFree(w.queues);
         if (w.counts) cudaFree(w.counts);
@@ -766,6 +786,57 @@ int moira_collapse_device(moira_ctx *c, const uint8_t *d_seq, const uint64_t *d_
     if (!c || !d_seq || !d_labels) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
     return run_dedup(c, d_seq, d_offsets, d_lengths, stride, fixed_length, n_reads, truncate, d_labels, (cudaStream_t)stream);
+}
+
+int moira_collapse_groups(moira_ctx *c, const uint32_t *labels, const double *ee, int on_device, uint64_t n, uint64_t *n_groups_out,
+                          const uint32_t **group_of_read, const uint32_t **group_rep, const uint32_t **group_size,
+                          const uint32_t **member_start, const uint32_t **members, const uint32_t **abundance_order)
+{
+    if (!c || !n_groups_out || !group_of_read || !group_rep || !group_size || !member_start || !members || !abundance_order)
+        return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    *n_groups_out = 0;
+    *group_of_read = *group_rep = *group_size = *member_start = *members = *abundance_order = nullptr;
+    if (n == 0) return MOIRA_OK;
+    if (!labels || !ee) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c->grp_dev, groups_device_bytes(n)))) return rc;
+    if ((rc = ensure_host(&c->grp_host, &c->grp_host_cap, groups_host_bytes(n)))) return rc;
+    size_t off[6];
+    uint64_t G = 0;
+    if ((rc = groups_from_labels_device(c->sm_count, c->streams[0], (uint8_t *)c->grp_dev.p, c->grp_host, labels, ee, on_device, n, &G, off)))
+        return rc;
+    c->launches += 8;
+    *n_groups_out = G;
+    const uint32_t **dst[6] = {group_of_read, group_rep, group_size, member_start, members, abundance_order};
+    for (int i = 0; i < 6; i++) *dst[i] = reinterpret_cast<const uint32_t *>(c->grp_host + off[i]);
+    return MOIRA_OK;
+}
+
+int moira_collapse_labels_device(moira_ctx *c, const uint32_t *labels, const double *ee, uint64_t n, uint64_t *group_of_read,
+                                 uint64_t *n_groups_out, uint64_t *group_rep, uint64_t *group_size, uint64_t *member_start,
+                                 uint64_t *members, uint64_t *abundance_order)
+{
+    if (!n_groups_out) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    *n_groups_out = 0;
+    if (n == 0) return MOIRA_OK;
+    if (!group_of_read || !group_rep || !group_size || !member_start || !members || !abundance_order)
+        return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    const uint32_t *h[6];
+    uint64_t G = 0;
+    const int rc = moira_collapse_groups(c, labels, ee, 0, n, &G, &h[0], &h[1], &h[2], &h[3], &h[4], &h[5]);
+    if (rc) return rc;
+    *n_groups_out = G;
+    // uint32 on the device and over PCIe, uint64 in the caller's arrays
+    uint64_t *dst[6] = {group_of_read, group_rep, group_size, member_start, members, abundance_order};
+    const uint64_t cnt[6] = {n, G, G, G + 1, n, G};
+    const int parts = 64;
+    parallel_run(parts * 6, (int)std::max(1u, std::thread::hardware_concurrency()), [&](int t) {
+        const int a = t / parts, p = t % parts;
+        const uint64_t lo = cnt[a] * (uint64_t)p / parts, hi = cnt[a] * (uint64_t)(p + 1) / parts;
+        for (uint64_t i = lo; i < hi; i++) dst[a][i] = h[a][i];
+    });
+    return MOIRA_OK;
 }
 
 int moira_count_marks_device(moira_ctx *c, const uint8_t *d_slab, const uint64_t *d_offsets, const uint32_t *d_lengths,

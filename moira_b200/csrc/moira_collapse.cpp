@@ -60,6 +60,25 @@ void parallel_for(int n_items, int threads, F &&fn)
 
 }  // namespace
 
+// abundance_order = the groups by size, largest first, equal sizes in order of first appearance (sorted(..., reverse=True)
+// on the sizes is stable, moira.py:492): a counting sort -- sizes are small integers, a comparison sort of millions of
+// groups cost more than everything else in the collapse.
+static void sort_by_abundance(const uint64_t *group_size, uint64_t G, uint64_t *abundance_order)
+{
+    uint64_t max_size = 0;
+    for (uint64_t g = 0; g < G; g++) max_size = std::max(max_size, group_size[g]);
+    if (max_size > (1ull << 26)) {   // absurdly large groups: fall back to the comparison sort
+        for (uint64_t g = 0; g < G; g++) abundance_order[g] = g;
+        std::stable_sort(abundance_order, abundance_order + G, [&](uint64_t x, uint64_t y) { return group_size[x] > group_size[y]; });
+        return;
+    }
+    std::vector<uint64_t> start(max_size + 2, 0);
+    for (uint64_t g = 0; g < G; g++) start[group_size[g]]++;
+    uint64_t pos = 0;
+    for (uint64_t sz = max_size + 1; sz-- > 0;) { const uint64_t c = start[sz]; start[sz] = pos; pos += c; }
+    for (uint64_t g = 0; g < G; g++) abundance_order[start[group_size[g]]++] = g;
+}
+
 extern "C" int moira_collapse(const char *text, const uint64_t *seq_off, const uint32_t *seq_len, const double *ee,
                               uint64_t n, int n_threads, uint64_t *group_of_read, uint64_t *n_groups_out,
                               uint64_t *group_rep, uint64_t *group_size, uint64_t *member_start, uint64_t *members,
@@ -156,8 +175,7 @@ extern "C" int moira_collapse(const char *text, const uint64_t *seq_off, const u
             }
         });
     }
-    for (uint64_t g = 0; g < G; g++) abundance_order[g] = g;
-    std::stable_sort(abundance_order, abundance_order + G, [&](uint64_t x, uint64_t y) { return group_size[x] > group_size[y]; });
+    sort_by_abundance(group_size, G, abundance_order);
     return MOIRA_OK;
 }
 
@@ -206,7 +224,6 @@ extern "C" int moira_collapse_labels(const uint32_t *labels, const double *ee, u
             else members[back[g]++] = r;
         }
     }
-    for (uint64_t g = 0; g < G; g++) abundance_order[g] = g;
-    std::stable_sort(abundance_order, abundance_order + G, [&](uint64_t x, uint64_t y) { return group_size[x] > group_size[y]; });
+    sort_by_abundance(group_size, G, abundance_order);
     return MOIRA_OK;
 }

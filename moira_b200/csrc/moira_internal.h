@@ -207,6 +207,12 @@ struct DedupArgs {
 // d_table: table_mask + 1 slots preset to 0xFFFFFFFF (kept between launches that add reads to the same set)
 int launch_dedup(const DedupArgs &a, uint64_t *d_hash, uint32_t *d_table, uint32_t table_mask, uint32_t *d_labels, const LaunchCfg &cfg);
 
+// ---- groups, representatives, names order and abundance order from labels, on the device (moira_groups.cu) ----------
+size_t groups_device_bytes(uint64_t n);
+size_t groups_host_bytes(uint64_t n);
+int groups_from_labels_device(int sm_count, cudaStream_t stream, uint8_t *d_buf, uint8_t *h_pinned, const uint32_t *labels, const double *ee,
+                              int on_device, uint64_t n, uint64_t *n_groups_out, size_t out_off[6]);
+
 // ---- the counters' all-reduce over GPUs (moira_comm.cpp; NCCL bound at run time) ---------------------------------
 struct CommState;                       // one communicator rank; owned by a moira_ctx
 CommState *comm_state_new();

@@ -339,3 +339,33 @@ def test_multi_stage_cascade_equals_single_sweep(ctx, profile, n):
     lb = (f & L.FLAG_LOWER_BOUND) != 0
     assert np.array_equal((f & 1) != 0, (ee_o + ns_o) <= ln * uncert)
     assert np.array_equal(outs[0][0][:m][~lb], ee_o[~lb]) and np.array_equal(outs[0][1][:m], ns_o)
+
+
+@pytest.mark.parametrize("n,pool,ties", [(1, 1, False), (50_000, 7, True), (200_000, 60_000, False), (300_000, 300_000, True)])
+def test_groups_on_the_device_equal_groups_on_the_host(ctx, n, pool, ties):
+    """moira_collapse_labels_device == moira_collapse_labels: first-appearance numbering, representatives (first read with the
+    strictly smallest ee), names order (record breakers to the front), abundance order with ties -- on a few huge groups,
+    on mostly singletons, with many equal ee values."""
+    rng = np.random.default_rng(n + pool)
+    key = rng.integers(0, pool, n)
+    _, first_idx, inv = np.unique(key, return_index=True, return_inverse=True)
+    # the label is ANY member of the group (the read that claimed the hash slot), not necessarily the first
+    pick = {}
+    order = rng.permutation(n)
+    for r in order[: min(n, 400_000)]:
+        pick.setdefault(int(inv[r]), int(r))
+    labels = np.array([pick[int(g)] for g in inv], dtype=np.uint32)
+    ee = rng.integers(0, 5, n).astype(np.float64) if ties else rng.random(n) * 30
+    want = moira_b200.collapse_labels(labels, ee)
+    got = ctx.collapse_labels(labels, ee)
+    for f in ("group_of_read", "rep", "size", "member_start", "members", "order"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    # the uint32 views, from host arrays and from device arrays
+    d_lab, d_ee = torch.from_numpy(labels.view(np.int32)).to("cuda:0"), torch.from_numpy(ee).to("cuda:0")
+    for views in (ctx.collapse_groups(labels, ee), ctx.collapse_groups(d_lab.data_ptr(), d_ee.data_ptr(), n)):
+        for f in ("group_of_read", "rep", "size", "member_start", "members", "order"):
+            assert getattr(views, f).dtype == np.uint32 and np.array_equal(getattr(views, f), getattr(want, f)), f
+    with pytest.raises(moira_b200.MoiraError):
+        bad = labels.copy()
+        bad[n // 2] = n + 5
+        ctx.collapse_labels(bad, ee)
