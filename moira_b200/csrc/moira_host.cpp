@@ -53,7 +53,7 @@ Pool &pool()
 }
 }  // namespace
 
-void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn)
+void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn, bool inline_if_busy)
 {
     if (n_tasks <= 0) return;
     if (n_tasks == 1 || n_threads <= 1) {
@@ -61,7 +61,18 @@ void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn
         return;
     }
     Pool &p = pool();
-    std::lock_guard<std::mutex> run_lock(p.run_mutex);
+    // one parallel phase at a time uses the pool.  inline_if_busy: a caller that finds it taken runs its tasks itself instead
+    // of queueing -- for the staging copies of several contexts' planner threads (one process, several GPUs), which then
+    // proceed side by side; every other phase waits its turn (running a big formatting job on one thread would be worse)
+    std::unique_lock<std::mutex> run_lock(p.run_mutex, std::defer_lock);
+    if (inline_if_busy) {
+        if (!run_lock.try_lock()) {
+            for (int t = 0; t < n_tasks; t++) fn(t);
+            return;
+        }
+    } else {
+        run_lock.lock();
+    }
     std::unique_lock<std::mutex> lk(p.m);
     while ((int)p.workers.size() < n_threads - 1) {
         p.workers.emplace_back([&p] { p.worker(); });
@@ -431,7 +442,7 @@ void moira::parallel_memcpy(void *dst, const void *src, uint64_t bytes)
     moira::parallel_run(T, T, [&](int t) {
         const uint64_t b = bytes * (uint64_t)t / T, e = bytes * (uint64_t)(t + 1) / T;
         memcpy((char *)dst + b, (const char *)src + b, e - b);
-    });
+    }, true);
 }
 
 // Plan one chunk of a FASTQ text for the device parser: count the newlines of text[pos, pos + target) on all host

@@ -190,7 +190,7 @@ int parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_offset, i
                       uint64_t *n_reads_out, uint64_t *slab_bytes_out, uint64_t *consumed_out, int final_range);
 
 // run fn(0..n_tasks-1) on up to n_threads threads of a persistent host worker pool (moira_host.cpp)
-void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn);
+void parallel_run(int n_tasks, int n_threads, const std::function<void(int)> &fn, bool inline_if_busy = false);
 
 // ---- dereplication on the device (moira_dedup.cu) ------------------------------------------------------------
 struct DedupArgs {

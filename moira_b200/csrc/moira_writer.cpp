@@ -4,6 +4,7 @@
 // byte ranges the parsers (host or device) and the contig kernel left behind, on all host threads, into memory
 // blocks the host program only has to write to its files.  The accept / reject decision itself is the device's.
 #include <errno.h>
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 #include <unistd.h>
@@ -220,24 +221,34 @@ int moira_blocks_write(const moira_blocks *b, int which, int fd, uint64_t file_o
     for (int p = 0; p < b->n_parts; p++) at[(size_t)p + 1] = at[p] + b->buf[(size_t)p * MOIRA_BLOCK_N + which].size();
     *written_out = at[b->n_parts] - file_offset;
     if (*written_out == 0) return MOIRA_OK;
-    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    // own threads, not the library's pool: the pool belongs to the formatter, which is busy with the next batch meanwhile
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency() / 2;
     if (T < 1) T = 1;
-    if (T > 16) T = 16;
-    int err = 0;
-    moira::parallel_run(b->n_parts, T, [&](int p) {
-        const std::string &s = b->buf[(size_t)p * MOIRA_BLOCK_N + which];
-        size_t done = 0;
-        while (done < s.size()) {
-            const ssize_t w = pwrite(fd, s.data() + done, s.size() - done, (off_t)(at[p] + done));
-            if (w < 0) {
-                if (errno == EINTR) continue;
-                err = errno;
-                return;
+    if (T > 8) T = 8;
+    if (T > b->n_parts) T = b->n_parts;
+    std::atomic<int> next{0}, err{0};
+    auto work = [&]() {
+        for (;;) {
+            const int p = next.fetch_add(1);
+            if (p >= b->n_parts) return;
+            const std::string &s = b->buf[(size_t)p * MOIRA_BLOCK_N + which];
+            size_t done = 0;
+            while (done < s.size()) {
+                const ssize_t w = pwrite(fd, s.data() + done, s.size() - done, (off_t)(at[p] + done));
+                if (w < 0) {
+                    if (errno == EINTR) continue;
+                    err = errno;
+                    return;
+                }
+                done += (size_t)w;
             }
-            done += (size_t)w;
         }
-    });
-    if (err) return moira::fail(MOIRA_ERR_BAD_ARG, "pwrite failed: %s", strerror(err));
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto &x : th) x.join();
+    if (err) return moira::fail(MOIRA_ERR_BAD_ARG, "pwrite failed: %s", strerror(err.load()));
     return MOIRA_OK;
 }
 
