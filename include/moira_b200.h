@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MOIRA_ABI_VERSION 4
+#define MOIRA_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define MOIRA_API __attribute__((visibility("default")))
