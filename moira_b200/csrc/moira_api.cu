@@ -508,7 +508,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             static const char *mname[] = {"", "", "", "", "", "pb_cascade<2..4,5>", "pb_cascade<2..5,6>", "pb_cascade<2..5,7>",
                                           "pb_cascade<2..5,8>"};
             // decisions that need 5 .. 8 entries: the first stage is chosen among 2 .. 5 entries (two pilots, see policy_*_kernel)
-            const bool multi = pilot && !p->exact_ee && k_first >= 5 && n >= 16u * pilot_n && c->cascade_multi;
+            const bool multi = pilot && k_first >= 5 && n >= 16u * pilot_n && c->cascade_multi;
             if (multi) {
                 uint32_t *jhist = ws.counts + NB + 4;
                 a2.n = pilot_n;
@@ -519,7 +519,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
                 b.policy = policy; b.policy_want = MOIRA_POLICY_UNDECIDED; // histogram of floor(ee) for the verdict
                 b.jhist = jhist;
                 if (rc >= 0) rc = launch_pb_first(b, k_first, cfg, nullptr);
-                if (rc >= 0 && launch_policy_second(jhist, k_first, policy, stream)) rc = -1;
+                if (rc >= 0 && launch_policy_second(jhist, k_first, p->exact_ee ? 1 : 0, policy, stream)) rc = -1;
                 a2.n = n; a2.tile0 = pilot_n / 32u; a2.policy = policy; a2.policy_want = 2;
                 if (rc >= 0) rc = launch_pb_first(a2, 2, cfg, nullptr);
                 c->launches += 5;

@@ -129,7 +129,7 @@ int launch_policy(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *po
 // cascade with a first stage of 2 .. 5 entries: verdict of the two-entry pilot (2 or undecided), then of the k_first-entry pilot
 constexpr uint32_t MOIRA_POLICY_UNDECIDED = 0xFFu;
 int launch_policy_first(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s);
-int launch_policy_second(const uint32_t *jhist, int k_first, uint32_t *policy, cudaStream_t s);
+int launch_policy_second(const uint32_t *jhist, int k_first, int exact, uint32_t *policy, cudaStream_t s);
 int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, double *ops_out);
 int kernels_init(int sm_count);  // sets function attributes (dynamic smem opt-in)
 int max_first_pass_k();

@@ -851,28 +851,33 @@ __global__ void policy_first_kernel(const uint32_t *queue_count, uint32_t max_pu
 // and O = 4.3 others (profiles/r02_k2_regions_before_fix.md), counting every read with j* >= K1 as swept again with k_first
 // entries through the queue (x 1.1: gathered rows, no TMA) -- the Newton bound settles some of them, so the estimate is on
 // the safe side.  floor(ee) >= K1 - 1  <=>  j* >= K1 (up to reads with N, which need fewer entries).  0: single sweep.
-__global__ void policy_second_kernel(const uint32_t *jhist, int k_first, uint32_t *policy)
+// Exact mode (every read's statistic is wanted): the same choice with the ladder's cost for the reads K1 entries do not settle.
+__global__ void policy_second_kernel(const uint32_t *jhist, int k_first, int exact, uint32_t *policy)
 {
     if (*policy != MOIRA_POLICY_UNDECIDED) return;
     double total = 0.0, tail[17];
     for (int i = 0; i < 16; i++) total += (double)jhist[i];
     tail[16] = 0.0;
     for (int i = 15; i >= 0; i--) tail[i] = tail[i + 1] + (double)jhist[i];
-    const double full = 2.0 * (3 * k_first - 2) + 4.3;
+    auto cyc = [](int k) { return 2.0 * (3 * k - 2) + 4.3; };
+    const double full = cyc(k_first);
     double best = full;
     uint32_t choice = 0;
     for (int k1 = 3; k1 <= 5 && k1 < k_first; k1++) {
-        const double esc = total > 0.0 ? tail[k1 - 1] / total : 1.0;
-        const double cost = 2.0 * (3 * k1 - 2) + 4.3 + esc * full * 1.1;
+        double cost = cyc(k1);
+        if (!exact) {
+            const double esc = total > 0.0 ? tail[k1 - 1] / total : 1.0;
+            cost += esc * full * 1.1;
+        } else if (total > 0.0) {
+            // exact mode: a read with floor(ee) = j >= k1 - 1 (j* = j + 1 >= k1) goes on to the rung that holds j* + 1 entries
+            // plus about one of estimate; what the pilot's k_first entries did not settle either costs the same whatever k1 is
+            for (int j = k1 - 1; j <= k_first - 2 && j < 16; j++) cost += 1.1 * ((double)jhist[j] / total) * cyc(j + 3);
+        }
         if (cost < best * 0.97) { best = cost; choice = (uint32_t)k1; }
     }
     *policy = choice;
 }
 
-// All thread-per-read rungs of the escalation ladder in ONE launch: the CTA sets its table up once and
-// every warp walks its share of the tiles of rung 1, rung 2, ... with the K of each rung, so no warp
-// waits at a kernel boundary for the last wave of the previous rung.  Reads a rung cannot settle go
-// straight to the first warp-per-read rung.
 template <bool EQP>
 __global__ void __launch_bounds__(256, 1) ladder_tpr_kernel(const FilterArgs a0)
 {
@@ -1518,9 +1523,9 @@ int launch_policy_first(const uint32_t *queue_count, uint32_t max_pushed, uint32
     policy_first_kernel<<<1, 1, 0, s>>>(queue_count, max_pushed, policy);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
-int launch_policy_second(const uint32_t *jhist, int k_first, uint32_t *policy, cudaStream_t s)
+int launch_policy_second(const uint32_t *jhist, int k_first, int exact, uint32_t *policy, cudaStream_t s)
 {
-    policy_second_kernel<<<1, 1, 0, s>>>(jhist, k_first, policy);
+    policy_second_kernel<<<1, 1, 0, s>>>(jhist, k_first, exact, policy);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

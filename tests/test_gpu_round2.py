@@ -317,28 +317,31 @@ def test_multi_stage_cascade_equals_single_sweep(ctx, profile, n):
     ctx.count_marks_device(slab.data_ptr(), None, d_len, stride, fixed or 0, n, marks.data_ptr(), 0, stream)
     # uncert 0.012 on 'real' (253 bp): cutoff 3.036 -> 5 entries, the smallest decision the multi-stage cascade takes
     uncert = 0.012 if profile == "real" else 0.01
-    outs = []
-    for cascade in (0, 2):
-        ee, ns, fl, cnt = _dev_arrays(n)
-        p = FilterParams(exact_ee=False, cascade=cascade, max_length=max_len, min_length=min_len, length_sort=2, uncert=uncert)
-        ctx.filter_device(slab.data_ptr(), None, d_len, stride, fixed or 0, n, p, ee.data_ptr(), ns.data_ptr(), fl.data_ptr(),
-                          cnt.data_ptr(), stream, marks.data_ptr())
-        torch.cuda.synchronize()
-        outs.append((ee.cpu().numpy(), ns.cpu().numpy(), fl.cpu().numpy(), cnt.cpu().numpy()))
-    for k in range(3):
-        assert np.array_equal(outs[0][k], outs[1][k]), k
-    assert _same_but_diagnostics(outs[0][3], outs[1][3])
-    assert outs[0][3][L.CNT_FP64_OPS] < outs[1][3][L.CNT_FP64_OPS]          # the cascade executed less
-    # oracle on a sample
     m = 3000
     h_slab = slab[:m].cpu().numpy().reshape(-1)
     off = np.arange(m, dtype=np.uint64) * np.uint64(stride)
     ln = np.full(m, fixed, np.uint32) if lens is None else lens[:m].cpu().numpy().astype(np.uint32)
     ee_o, ns_o = po.pb_batch(h_slab, off, ln, 0.005)
-    f = outs[0][2][:m]
-    lb = (f & L.FLAG_LOWER_BOUND) != 0
-    assert np.array_equal((f & 1) != 0, (ee_o + ns_o) <= ln * uncert)
-    assert np.array_equal(outs[0][0][:m][~lb], ee_o[~lb]) and np.array_equal(outs[0][1][:m], ns_o)
+    for exact in (False, True):
+        outs = []
+        for cascade in (0, 2):
+            ee, ns, fl, cnt = _dev_arrays(n)
+            p = FilterParams(exact_ee=exact, cascade=cascade, max_length=max_len, min_length=min_len, length_sort=2, uncert=uncert)
+            ctx.filter_device(slab.data_ptr(), None, d_len, stride, fixed or 0, n, p, ee.data_ptr(), ns.data_ptr(), fl.data_ptr(),
+                              cnt.data_ptr(), stream, marks.data_ptr())
+            torch.cuda.synchronize()
+            outs.append((ee.cpu().numpy(), ns.cpu().numpy(), fl.cpu().numpy(), cnt.cpu().numpy()))
+        for k in range(3):
+            assert np.array_equal(outs[0][k], outs[1][k]), (exact, k)
+        assert _same_but_diagnostics(outs[0][3], outs[1][3])
+        if not exact:
+            assert outs[0][3][L.CNT_FP64_OPS] < outs[1][3][L.CNT_FP64_OPS]          # the cascade executed less
+        # oracle on a sample
+        f = outs[0][2][:m]
+        lb = (f & L.FLAG_LOWER_BOUND) != 0
+        assert not (exact and lb.any()) and not (f & L.FLAG_NUMERIC).any()
+        assert np.array_equal((f & 1) != 0, (ee_o + ns_o) <= ln * uncert)
+        assert np.array_equal(outs[0][0][:m][~lb], ee_o[~lb]) and np.array_equal(outs[0][1][:m], ns_o)
 
 
 @pytest.mark.parametrize("n,pool,ties", [(1, 1, False), (50_000, 7, True), (200_000, 60_000, False), (300_000, 300_000, True)])
