@@ -489,6 +489,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             } else {
                 rc = launch_sorted_first(a, lb.group_start, lb.group_count, cfg);
                 name = "pb_tpr<K per length bucket>";
+                c->launches++;   // two launches: K <= 12 on 16 warps, wider on 8
             }
             if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             c->launches++;

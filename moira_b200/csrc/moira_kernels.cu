@@ -914,15 +914,25 @@ __global__ void __launch_bounds__(256, 1) ladder_tpr_kernel(const FilterArgs a0)
 
 // First pass over a length-sorted permutation, every K template in ONE launch: segment g of the queue
 // (seg_start[g], seg_count[g]; written by len_scan_kernel) is swept with first_pass_k(g) entries.
-template <bool EQP>
-__global__ void __launch_bounds__(256, 1) sorted_first_kernel(const FilterArgs a, const uint32_t *seg_start, const uint32_t *seg_count)
+// WIDE = false: the groups with K <= 12 on 16 warps per CTA (<= 128 registers per thread, four warps per scheduler like the
+// single-K kernels); WIDE = true: K = 14 .. 32 on 8 warps.  Two launches; one whose groups are all empty returns before
+// any set-up.
+template <bool EQP, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 256 : 512, 1) sorted_first_kernel(const FilterArgs a, const uint32_t *seg_start, const uint32_t *seg_count)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const TprCtx ctx = tpr_setup<8, 0, EQP, false>(a, smem);
-    const uint32_t W = gridDim.x * 8, gw = blockIdx.x * 8 + ctx.warp;
+    constexpr int WARPS = WIDE ? 8 : 16;
+    constexpr int G0 = WIDE ? 9 : 0, G1 = WIDE ? N_FIRST_K : 9;   // first_pass_k(8) == 12
+    static_assert(first_pass_k(8) == 12 && first_pass_k(9) == 14 && N_FIRST_K == 17, "group table and sorted first pass out of step");
+    uint32_t any = 0;
+#pragma unroll
+    for (int g = G0; g < G1; g++) any |= seg_count[g];
+    if (!any) return;
+    const TprCtx ctx = tpr_setup<WARPS, 0, EQP, false>(a, smem);
+    const uint32_t W = gridDim.x * WARPS, gw = blockIdx.x * WARPS + ctx.warp;
     uint32_t before = 0;
 #define MOIRA_GROUP(g, k)                                                                              \
-    {                                                                                                  \
+    if constexpr ((g) >= G0 && (g) < G1) {                                                             \
         const uint32_t cnt = seg_count[g];                                                             \
         if (cnt) {                                                                                     \
             const uint32_t first = (gw + W - before % W) % W;                                          \
@@ -1409,8 +1419,10 @@ int kernels_init(int)
     MOIRA_FOR_EACH_K(X)
 #undef X
     if (init_tpr<1, 1, false>() || init_tpr<1, 1, true>() || init_tpr<2, 2, false>()) return -1;
-    if (cudaFuncSetAttribute(sorted_first_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(sorted_first_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(sorted_first_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(sorted_first_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(sorted_first_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(sorted_first_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(ladder_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(ladder_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM) != cudaSuccess) return -1;
@@ -1474,8 +1486,13 @@ int launch_count_marks(const FilterArgs &a, uint32_t *d_marks, uint32_t max_len,
 
 int launch_sorted_first(const FilterArgs &a, const uint32_t *seg_start, const uint32_t *seg_count, const LaunchCfg &cfg)
 {
-    if (a.e_equals_p) sorted_first_kernel<true><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a, seg_start, seg_count);
-    else sorted_first_kernel<false><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a, seg_start, seg_count);
+    if (a.e_equals_p) {
+        sorted_first_kernel<true, false><<<cfg.sm_count, 512, TPR_SMEM, cfg.stream>>>(a, seg_start, seg_count);
+        sorted_first_kernel<true, true><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a, seg_start, seg_count);
+    } else {
+        sorted_first_kernel<false, false><<<cfg.sm_count, 512, TPR_SMEM, cfg.stream>>>(a, seg_start, seg_count);
+        sorted_first_kernel<false, true><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a, seg_start, seg_count);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
