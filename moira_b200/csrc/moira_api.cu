@@ -572,7 +572,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             for (int b = 0; b < NB; b++) {
                 if (b == 1) {   // every thread-per-read rung in one launch
                     if (launch_ladder_tpr(a, cfg)) return fail(MOIRA_ERR_CUDA, "ladder launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-                    c->launches++;
+                    c->launches += 2;   // rungs 1..8 on 16 warps, 9..19 on 8
                     b = N_TPR_RUNGS;
                     continue;
                 }

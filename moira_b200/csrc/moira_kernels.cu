@@ -878,35 +878,40 @@ __global__ void policy_second_kernel(const uint32_t *jhist, int k_first, int exa
     *policy = choice;
 }
 
-template <bool EQP>
-__global__ void __launch_bounds__(256, 1) ladder_tpr_kernel(const FilterArgs a0)
+// Two launches like the length-bucketed first pass: rungs 1..8 (K <= 12) on 16 warps per CTA, rungs 9..19 on 8.
+template <bool EQP, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 256 : 512, 1) ladder_tpr_kernel(const FilterArgs a0)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int WARPS = WIDE ? 8 : 16;
+    constexpr int R0 = WIDE ? 9 : 1, R1 = WIDE ? N_TPR_RUNGS : 8;   // rung_cap(8) == 12
     uint32_t counts[N_TPR_RUNGS + 1];
     uint32_t any = 0;
 #pragma unroll
-    for (int r = 1; r <= N_TPR_RUNGS; r++) {
+    for (int r = R0; r <= R1; r++) {
         const uint32_t c = a0.queue_counts[r];
         counts[r] = c < a0.queue_cap ? c : a0.queue_cap;
         any |= counts[r];
     }
     if (!any) return;
-    const TprCtx ctx = tpr_setup<8, 0, EQP, false>(a0, smem);
+    const TprCtx ctx = tpr_setup<WARPS, 0, EQP, false>(a0, smem);
     FilterArgs a = a0;
     a.rung = N_TPR_RUNGS;                      // escalations of this kernel land in rung N_TPR_RUNGS + 1
-    const uint32_t W = gridDim.x * 8, gw = blockIdx.x * 8 + ctx.warp;
+    const uint32_t W = gridDim.x * WARPS, gw = blockIdx.x * WARPS + ctx.warp;
     uint32_t before = 0;                       // tiles of the rungs already walked: keeps the load balanced
 #define MOIRA_RUNG(r, k)                                                                                      \
-    if (counts[r]) {                                                                                          \
-        const uint32_t first = (gw + W - before % W) % W;                                                     \
-        tpr_tiles<k, 0, EQP, false, MOIRA_LADDER_ROLL>(a, nullptr, ctx, a0.queues + (size_t)(r) * a0.queue_cap, counts[r], first, W); \
-        before += (counts[r] + 31) >> 5;                                                                      \
+    if constexpr ((r) >= R0 && (r) <= R1) {                                                                   \
+        if (counts[r]) {                                                                                      \
+            const uint32_t first = (gw + W - before % W) % W;                                                 \
+            tpr_tiles<k, 0, EQP, false, MOIRA_LADDER_ROLL>(a, nullptr, ctx, a0.queues + (size_t)(r) * a0.queue_cap, counts[r], first, W); \
+            before += (counts[r] + 31) >> 5;                                                                  \
+        }                                                                                                     \
     }
     MOIRA_RUNG(1, 3) MOIRA_RUNG(2, 4) MOIRA_RUNG(3, 5) MOIRA_RUNG(4, 6) MOIRA_RUNG(5, 7)
     MOIRA_RUNG(6, 8) MOIRA_RUNG(7, 10) MOIRA_RUNG(8, 12) MOIRA_RUNG(9, 14) MOIRA_RUNG(10, 16) MOIRA_RUNG(11, 18)
     MOIRA_RUNG(12, 20) MOIRA_RUNG(13, 22) MOIRA_RUNG(14, 24) MOIRA_RUNG(15, 28) MOIRA_RUNG(16, 32) MOIRA_RUNG(17, 40)
     MOIRA_RUNG(18, 48) MOIRA_RUNG(19, 64)
-    static_assert(N_TPR_RUNGS == 19 && rung_cap(19) == 64 && rung_cap(6) == 8, "rung table and ladder kernel out of step");
+    static_assert(N_TPR_RUNGS == 19 && rung_cap(19) == 64 && rung_cap(6) == 8 && rung_cap(8) == 12, "rung table and ladder kernel out of step");
 #undef MOIRA_RUNG
     __syncthreads();
     flush_counters(a, ctx.s_cnt, ctx.s_hist);
@@ -1423,8 +1428,10 @@ int kernels_init(int)
     if (cudaFuncSetAttribute(sorted_first_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(sorted_first_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(sorted_first_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(ladder_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(ladder_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ladder_tpr_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ladder_tpr_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ladder_tpr_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ladder_tpr_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM) != cudaSuccess) return -1;
     return 0;
 }
@@ -1498,8 +1505,13 @@ int launch_sorted_first(const FilterArgs &a, const uint32_t *seg_start, const ui
 
 int launch_ladder_tpr(const FilterArgs &a, const LaunchCfg &cfg)
 {
-    if (a.e_equals_p) ladder_tpr_kernel<true><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a);
-    else ladder_tpr_kernel<false><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a);
+    if (a.e_equals_p) {
+        ladder_tpr_kernel<true, false><<<cfg.sm_count, 512, TPR_SMEM, cfg.stream>>>(a);
+        ladder_tpr_kernel<true, true><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a);
+    } else {
+        ladder_tpr_kernel<false, false><<<cfg.sm_count, 512, TPR_SMEM, cfg.stream>>>(a);
+        ladder_tpr_kernel<false, true><<<cfg.sm_count, 256, TPR_SMEM, cfg.stream>>>(a);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
