@@ -240,6 +240,11 @@ MOIRA_API int moira_parse_fasta_qual(const char *fasta, uint64_t fasta_bytes, co
                                      uint64_t *out_offsets, uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len,
                                      uint64_t *seq_off, uint64_t max_reads, uint64_t *n_reads_out, uint64_t *slab_bytes_out);
 
+/* Byte offsets just behind the line_numbers[k]-th newline (ascending line numbers; 0 -> 0, beyond the last newline ->
+ * text_bytes) and the number of newlines of the text: cuts two paired files into blocks holding the same records. */
+MOIRA_API int moira_line_offsets(const char *text, uint64_t text_bytes, const uint64_t *line_numbers, uint64_t n_queries,
+                                 uint64_t *offsets_out, uint64_t *n_lines_out);
+
 /* Number of complete 4-line records in a FASTQ text buffer (to size the output arrays). */
 MOIRA_API int moira_fastq_count_reads(const char *text, uint64_t text_bytes, uint64_t *n_reads_out);
 
@@ -282,6 +287,11 @@ MOIRA_API int moira_collapse_labels(const uint32_t *labels, const double *ee, ui
 /* The same outputs computed on the device (csrc/moira_groups.cu: first-appearance numbering by atomicMin + scan, stable
  * radix sort by group, running minimum of ee by key, stable sort by size): labels / ee and all outputs are HOST arrays
  * (uint32 on the device and over PCIe).  n < 2^31.  Results are identical to moira_collapse_labels'. */
+/* Labels (as moira_collapse_device's) of sequences anywhere in HOST memory: seq_addr[r] = absolute address of read r's
+ * bases, seq_len[r] its length (truncate > 0: only the first `truncate` bases count).  The rows are gathered by all host
+ * threads, shipped in chunks and labelled on the device; labels_out is a host array of n. */
+MOIRA_API int moira_collapse_addr(moira_ctx *ctx, const uint64_t *seq_addr, const uint32_t *seq_len, uint64_t n, uint32_t truncate,
+                                  uint32_t *labels_out);
 /* The device version without the widening copy: labels / ee are host arrays, or -- on_device != 0 -- device arrays (the
  * outputs of moira_collapse_device and of the filter); the six result arrays are uint32 views of pinned host memory owned
  * by the context, valid until its next moira_collapse_groups / moira_collapse_labels_device call. */

@@ -39,8 +39,8 @@ EXPORTS = [
     "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_count_marks_device", "moira_filter_batch",
     "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads", "moira_pack_q6",
     "moira_parse_fastq", "moira_parse_fasta_qual", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
-    "moira_filter_fastq_ex", "moira_collapse_device", "moira_collapse_labels", "moira_collapse_labels_device", "moira_collapse_groups", "moira_format_records", "moira_blocks_parts",
-    "moira_blocks_get", "moira_blocks_write", "moira_blocks_recycle", "moira_blocks_free", "moira_fastq_headers", "moira_fastq_split",
+    "moira_filter_fastq_ex", "moira_collapse_device", "moira_collapse_labels", "moira_collapse_labels_device", "moira_collapse_groups", "moira_collapse_addr", "moira_format_records", "moira_blocks_parts",
+    "moira_blocks_get", "moira_blocks_write", "moira_blocks_recycle", "moira_blocks_free", "moira_fastq_headers", "moira_fastq_split", "moira_line_offsets",
     "moira_comm_unique_id", "moira_comm_init", "moira_comm_init_all", "moira_comm_info", "moira_reduce_counters_device",
     "moira_reduce_counters", "moira_reduce_counters_all", "moira_link_probe",
     "moira_ctx_last_kernel_ms", "moira_ctx_last_contig_ms", "moira_contig_params_default", "moira_filter_pairs", "moira_nw_align", "moira_make_contig",
@@ -128,12 +128,14 @@ lib.moira_filter_fastq.argtypes = [_vp, _vp, _u64, _i, _i, _pp, _u64, _vp, _vp, 
 lib.moira_filter_fastq_ex.argtypes = [_vp, _vp, _u64, _i, _i, _pp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_u64)]
 lib.moira_collapse_device.argtypes = [_vp, _vp, _vp, _vp, _u64, _u32, _u64, _u32, _vp, _vp]
 lib.moira_collapse_labels.argtypes = [_vp, _vp, _u64, _vp, ctypes.POINTER(_u64), _vp, _vp, _vp, _vp, _vp]
+lib.moira_collapse_addr.argtypes = [_vp, _vp, _vp, _u64, _u32, _vp]
 lib.moira_collapse_groups.argtypes = [_vp, _vp, _vp, _i, _u64, ctypes.POINTER(_u64)] + [ctypes.POINTER(_vp)] * 6
 lib.moira_collapse_labels_device.argtypes = [_vp, _vp, _vp, _u64, _vp, ctypes.POINTER(_u64), _vp, _vp, _vp, _vp, _vp]
 lib.moira_format_records.argtypes = [ctypes.POINTER(Records), ctypes.POINTER(WriteOpts), _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _i, ctypes.POINTER(_vp)]
 lib.moira_blocks_parts.argtypes = [_vp, ctypes.POINTER(_i)]
 lib.moira_blocks_get.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]
+lib.moira_line_offsets.argtypes = [_vp, _u64, _vp, _u64, _vp, ctypes.POINTER(_u64)]
 lib.moira_blocks_write.argtypes = [_vp, _i, _i, _u64, _i, ctypes.POINTER(_u64)]
 lib.moira_blocks_recycle.argtypes = [_vp]
 lib.moira_blocks_free.argtypes = [_vp]

@@ -396,6 +396,14 @@ class Context:
         G = ng.value
         return CollapseResult(g_of, rep[:G], size[:G], mstart[:G + 1], members, order[:G])
 
+    def collapse_addr(self, seq_addr, seq_len, truncate: int = 0) -> np.ndarray:
+        """moira_collapse_addr: dereplication labels (uint32[n]) of sequences given by absolute host addresses, made on the GPU."""
+        seq_addr, seq_len = _as(seq_addr, np.uint64), _as(seq_len, np.uint32)
+        n = int(seq_addr.shape[0])
+        labels = np.empty(n, np.uint32)
+        L.check(lib.moira_collapse_addr(self._h, _ptr(seq_addr), _ptr(seq_len), n, int(truncate or 0), _ptr(labels)))
+        return labels
+
     def collapse_groups(self, labels, ee, n: int | None = None) -> "CollapseResult":
         """moira_collapse_groups: as collapse_labels, without the widening copy -- the result arrays are uint32 views of the
         context's pinned memory (valid until the next collapse call on this context).  labels / ee: numpy arrays, or device
@@ -695,6 +703,17 @@ def fastq_headers(text, seq_off, n_threads: int = 0):
     ho, hl = np.empty(n, np.uint64), np.empty(n, np.uint32)
     L.check(lib.moira_fastq_headers(_ptr(buf), buf.nbytes, _ptr(seq_off), n, int(n_threads), _ptr(ho), _ptr(hl)))
     return ho, hl
+
+
+def line_offsets(text, line_numbers):
+    """(offsets uint64[k], n_lines): byte offsets just behind the given (ascending) numbers of newlines of `text`, and its
+    newline count (moira_line_offsets)."""
+    buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+    q = _as(line_numbers, np.uint64)
+    out = np.empty(q.shape[0], np.uint64)
+    n = ctypes.c_uint64()
+    L.check(lib.moira_line_offsets(_ptr(buf), buf.nbytes, _ptr(q), int(q.shape[0]), _ptr(out), ctypes.byref(n)))
+    return out, n.value
 
 
 def fastq_split(text, n_parts: int):

@@ -335,6 +335,77 @@ def _whole_records(fh, carry, lines_per_record, want_lines=None):
     return data[:pos], data[pos:], keep, eof and pos >= len(data)
 
 
+def _parse_error_for(exc, fname):
+    """MoiraError(ERR_PARSE) of a native parser -> the reference's exception class (moira.py:1178-1183, 1141-1142)."""
+    if exc.code != L.ERR_PARSE:
+        return exc
+    name = exc.message.split(":")[0]
+    cls = {"EmptySeqError": EmptySeqError, "EmptyQualError": EmptyQualError}.get(name)
+    if cls:
+        return cls(exc.message, fname)
+    if name == "NameMismatchError":
+        return NameMismatchError(exc.message, "")
+    return LengthMismatchError(exc.message, fname)
+
+
+def _check_pair_headers(ftext, fh_off, fh_len, rtext, rh_off, rh_len):
+    """Both files must name the same record at every position (moira.py:1199-1200)."""
+    fb = ftext if isinstance(ftext, np.ndarray) else np.frombuffer(ftext, dtype=np.uint8)
+    rb = rtext if isinstance(rtext, np.ndarray) else np.frombuffer(rtext, dtype=np.uint8)
+    if np.array_equal(fh_len, rh_len) and np.array_equal(_gather(fb, fh_off, fh_len), _gather(rb, rh_off, rh_len)):
+        return
+    for i in range(len(fh_len)):
+        fh_ = fb[int(fh_off[i]):int(fh_off[i]) + int(fh_len[i])].tobytes().decode("latin-1").replace(":", "_")
+        rh_ = rb[int(rh_off[i]):int(rh_off[i]) + int(rh_len[i])].tobytes().decode("latin-1").replace(":", "_")
+        if fh_ != rh_:
+            raise NameMismatchError(fh_, None, rh_, None)
+
+
+def _read_fastq_pair_batches(args, lower_n_ambiguous):
+    """Two FASTQ files in lock step without touching the text in Python: both files are memory-mapped (gz / bz2: inflated
+    once), moira_line_offsets cuts them at the same record numbers (one parallel newline count per file), and every pair
+    of blocks goes through the native parser as a view."""
+    from .api import line_offsets
+    ftext, fkeep = load_text(args.forward_fastq)
+    rtext, rkeep = load_text(args.reverse_fastq)
+    if ftext.size == 0 or (ftext.size < 4096 and not ftext.tobytes().strip()):
+        if rtext.size and (rtext.size >= 4096 or rtext.tobytes().strip()):
+            raise NameMismatchError("", "(the forward file ended first)")
+        return
+    head = ftext[:1 << 20]
+    rec_bytes = max(16.0, head.size / max(1.0, np.count_nonzero(head == 10) / 4.0))
+    per_block = max(1, int(BATCH_BYTES / rec_bytes))
+    _, nl_f = line_offsets(ftext, np.zeros(0, np.uint64))
+    n_blocks = max(1, -(-((nl_f + 3) // 4) // per_block))
+    marks = (np.arange(1, n_blocks, dtype=np.uint64) * np.uint64(4 * per_block))
+    fcut, _ = line_offsets(ftext, marks)
+    rcut, _ = line_offsets(rtext, marks)
+    fcut = np.concatenate([[0], fcut, [ftext.size]]).astype(np.int64)
+    rcut = np.concatenate([[0], rcut, [rtext.size]]).astype(np.int64)
+    for k in range(n_blocks):
+        fb, rb = ftext[fcut[k]:fcut[k + 1]], rtext[rcut[k]:rcut[k + 1]]
+        if fb.size == 0 and rb.size == 0:
+            continue
+        parsed = []
+        for buf, fname in ((fb, args.forward_fastq), (rb, args.reverse_fastq)):
+            try:
+                _, _, ln, hoff, hlen, soff, qoff = parse_fastq(buf, args.fastq_offset, lower_n_ambiguous)
+            except MoiraError as exc:
+                raise _parse_error_for(exc, fname) from None
+            parsed.append((buf, hoff, hlen, (buf, buf, soff, qoff, ln, args.fastq_offset)))
+        (ft, fh_off, fh_len, fwd), (rt, rh_off, rh_len, rev) = parsed
+        n = len(fwd[4])
+        if len(rev[4]) != n:
+            if n == 0:
+                raise NameMismatchError("", "(the forward file ended first)")
+            raise NameMismatchError("(%d forward records)" % n, "(%d reverse records)" % len(rev[4]))
+        if n == 0:
+            continue
+        _check_pair_headers(ft, fh_off, fh_len, rt, rh_off, rh_len)
+        yield ft, fh_off, fh_len, fwd, rev
+    del fkeep, rkeep
+
+
 def read_pair_batches(args, lower_n_ambiguous):
     """Paired input (moira.py:1093-1204 with both files): blocks of whole records of the forward file and the same
     number of records of the reverse file, parsed natively, headers compared (NameMismatchError).
@@ -342,12 +413,11 @@ def read_pair_batches(args, lower_n_ambiguous):
     lengths, qual_base)."""
     fastq = bool(args.forward_fastq)
     if fastq:
-        files = [(open_input(args.forward_fastq), args.forward_fastq), (open_input(args.reverse_fastq), args.reverse_fastq)]
-        per = 4
-    else:
-        files = [(open_input(args.forward_fasta), args.forward_fasta), (open_input(args.forward_qual), args.forward_qual),
-                 (open_input(args.reverse_fasta), args.reverse_fasta), (open_input(args.reverse_qual), args.reverse_qual)]
-        per = 2
+        yield from _read_fastq_pair_batches(args, lower_n_ambiguous)
+        return
+    files = [(open_input(args.forward_fasta), args.forward_fasta), (open_input(args.forward_qual), args.forward_qual),
+             (open_input(args.reverse_fasta), args.reverse_fasta), (open_input(args.reverse_qual), args.reverse_qual)]
+    per = 2
     carries = [b""] * len(files)
     while True:
         text0, carries[0], n_lines, eof = _whole_records(files[0][0], carries[0], per)
@@ -362,37 +432,17 @@ def read_pair_batches(args, lower_n_ambiguous):
 
         def parse(idx):
             try:
-                if fastq:
-                    _, _, ln, hoff, hlen, soff, qoff = parse_fastq(texts[idx], args.fastq_offset, lower_n_ambiguous)
-                    buf = np.frombuffer(texts[idx], dtype=np.uint8)
-                    return texts[idx], hoff, hlen, (buf, buf, soff, qoff, ln, args.fastq_offset)
                 _, qslab, off, ln, hoff, hlen, soff = parse_fasta_qual(texts[2 * idx], texts[2 * idx + 1], lower_n_ambiguous)
                 return texts[2 * idx], hoff, hlen, (np.frombuffer(texts[2 * idx], dtype=np.uint8), qslab, soff, off, ln, 0)
             except MoiraError as exc:
-                if exc.code == L.ERR_PARSE:
-                    name = exc.message.split(":")[0]
-                    cls = {"EmptySeqError": EmptySeqError, "EmptyQualError": EmptyQualError}.get(name)
-                    fname = files[idx if fastq else 2 * idx][1]
-                    if cls:
-                        raise cls(exc.message, fname) from None
-                    if name == "NameMismatchError":
-                        raise NameMismatchError(exc.message, "") from None
-                    raise LengthMismatchError(exc.message, fname) from None
-                raise
+                raise _parse_error_for(exc, files[2 * idx][1]) from None
 
         ftext, fh_off, fh_len, fwd = parse(0)
         rtext, rh_off, rh_len, rev = parse(1)
         n = len(fwd[4])
         if len(rev[4]) != n:
             raise NameMismatchError("(%d forward records)" % n, "(%d reverse records)" % len(rev[4]))
-        fb, rb = np.frombuffer(ftext, dtype=np.uint8), np.frombuffer(rtext, dtype=np.uint8)
-        same = np.array_equal(fh_len, rh_len) and np.array_equal(_gather(fb, fh_off, fh_len), _gather(rb, rh_off, rh_len))
-        if not same:                                                         # moira.py:1141-1142, 1199-1200
-            for i in range(n):
-                fh_ = ftext[int(fh_off[i]):int(fh_off[i]) + int(fh_len[i])].decode("latin-1").replace(":", "_")
-                rh_ = rtext[int(rh_off[i]):int(rh_off[i]) + int(rh_len[i])].decode("latin-1").replace(":", "_")
-                if fh_ != rh_:
-                    raise NameMismatchError(fh_, None, rh_, None)
+        _check_pair_headers(ftext, fh_off, fh_len, rtext, rh_off, rh_len)                  # moira.py:1141-1142, 1199-1200
         yield ftext, fh_off, fh_len, fwd, rev
         if eof:
             break
@@ -679,7 +729,7 @@ def run_pairs(args, ctxs, params, lower_n, contig_params, out):
         if bad.size:
             r = int(bad[0])
             st = int(pr.status[r])
-            header = ftext[int(hoff[r]):int(hoff[r]) + int(hlen[r])].decode("latin-1").replace(":", "_")
+            header = bytes(ftext[int(hoff[r]):int(hoff[r]) + int(hlen[r])]).decode("latin-1").replace(":", "_")
             if st == L.PAIR_BAD_BASE:                                          # moira.py:1228-1229
                 seq = rev[0][int(rev[2][r]):int(rev[2][r]) + int(rev[4][r])].tobytes().decode("latin-1")
                 wrong = [c for c in seq if c not in "ACTGNWSRYMKBVDH-."]
@@ -769,6 +819,14 @@ def finish_run(args, rs, writers, out, ctx=None):
             lut[owners] = owners[oc.rep[oc.group_of_read]].astype(np.uint32)
             labels = lut[labels]
         tp = _phase("decision arrays", tp)
+        if labels is None and ctx is not None and n < (1 << 31):
+            # no labels from the input flow (pairs, FASTA + QUAL, or a shard that did not fit): make them on the GPU from
+            # wherever the sequences lie in host memory
+            try:
+                labels = ctx.collapse_addr(rs.seq_addr, out_len)
+            except MoiraError as exc:
+                if exc.code != L.ERR_NOMEM:
+                    raise
         if labels is None:
             col = collapse(None, rs.seq_addr, out_len, rs.ee)
         else:
@@ -802,10 +860,12 @@ def finish_run(args, rs, writers, out, ctx=None):
         acc_s, rsn_s, sizes = accept, reason, np.ones(n, np.int64)
     writers.drain()
     tp = _phase("format + write (writer thread busy %.2f s)" % writers.seconds, tp)
+    tp = time.time()
     rej = acc_s == 0
     minlength = int(sizes[rej & (rsn_s == L.REASON_LENGTH)].sum())
     minoverlap = int(sizes[rej & (rsn_s == REASON_OVERLAP)].sum())
     errors = int(sizes[rej].sum()) - minlength - minoverlap
+    _phase("final counts", tp)
     return n, errors, minlength, minoverlap
 
 
@@ -872,9 +932,12 @@ def main(args, out=sys.stdout) -> int:
         t_filter = time.time() - t0
         processed, discarded_errors, discarded_minlength, discarded_minoverlap = finish_run(args, rs, writers, out, ctxs[0] if ctxs else None)
     finally:
+        tc = time.time()
         writers.close()
+        tc = _phase("close writers", tc)
         for c in ctxs:
             c.close()
+        _phase("close contexts", tc)
 
     if os.environ.get("MOIRA_B200_CLI_TIMING") == "1":
         for name, sec in _T_PHASES:

@@ -664,8 +664,12 @@ static int ctx_init(moira_ctx *c, int device, int sm_count)
 int moira_ctx_destroy(moira_ctx *c)
 {
     if (!c) return MOIRA_OK;
+    const bool trace = getenv("MOIRA_B200_TRACE_DESTROY") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+    const double t_begin = now();
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (trace) fprintf(stderr, "[moira_ctx_destroy] device synchronised after %.3f s\n", now() - t_begin);
     for (auto &t : c->tickets) {
         for (DevBuf *b : {&t.slab, &t.slab6, &t.offsets, &t.lengths, &t.ee, &t.ns, &t.flags, &t.counters, &t.marks})
             if (b->p) cudaFree(b->p);
@@ -710,6 +714,7 @@ int moira_ctx_destroy(moira_ctx *c)
     cudaSetDevice(c->device);
     cudaFree(c->d_p); cudaFree(c->d_q); cudaFree(c->d_e); cudaFree(c->d_sink);
     cudaGetLastError();
+    if (trace) fprintf(stderr, "[moira_ctx_destroy] everything freed after %.3f s\n", now() - t_begin);
     delete c;
     return MOIRA_OK;
 }
@@ -787,6 +792,73 @@ int moira_collapse_device(moira_ctx *c, const uint8_t *d_seq, const uint64_t *d_
     if (!c || !d_seq || !d_labels) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
     return run_dedup(c, d_seq, d_offsets, d_lengths, stride, fixed_length, n_reads, truncate, d_labels, (cudaStream_t)stream);
+}
+
+// Labels of sequences that lie anywhere in host memory (contig rows of several batches, sequence lines of a FASTA text):
+// the rows are gathered back to back into pinned staging by all host threads, shipped in chunks (the gather of chunk k + 1
+// runs while chunk k crosses PCIe), labelled on the device exactly like moira_collapse_device's, and the labels come back.
+int moira_collapse_addr(moira_ctx *c, const uint64_t *seq_addr, const uint32_t *seq_len, uint64_t n, uint32_t truncate, uint32_t *labels_out)
+{
+    if (!c || (n && (!seq_addr || !seq_len || !labels_out))) return fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    if (n == 0) return MOIRA_OK;
+    if (n >= 0xFFFFFFF0ull) return fail(MOIRA_ERR_BAD_ARG, "more than 2^32 reads in one dereplication");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t stream = c->streams[0];
+    const int T = (int)std::max(1u, std::thread::hardware_concurrency());
+    // offsets of the packed rows
+    std::vector<uint64_t> off(n + 1);
+    std::vector<uint32_t> eff(n);
+    uint64_t total = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        const uint32_t l = (truncate && seq_len[r] > truncate) ? truncate : seq_len[r];
+        off[r] = total; eff[r] = l; total += l;
+    }
+    off[n] = total;
+    int rc;
+    if ((rc = ensure(c->dd_store, total + 64)) || (rc = ensure(c->dd_seq_abs, n * 8 + 8)) || (rc = ensure(c->dd_seq_eff, n * 4 + 4)) ||
+        (rc = ensure(c->dd_labels, n * 4 + 4)))
+        return rc;
+    constexpr uint64_t CHUNK_BYTES = 128ull << 20;
+    const uint64_t stage_bytes = std::min<uint64_t>(total, CHUNK_BYTES) + (64u << 10);
+    if ((rc = ensure_host(&c->grp_host, &c->grp_host_cap, 2 * stage_bytes))) return rc;
+    cudaEvent_t freed[2];
+    for (auto &e : freed) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    uint64_t r0 = 0;
+    int slot = 0;
+    bool used[2] = {false, false};
+    while (r0 < n) {
+        uint64_t r1 = r0;
+        while (r1 < n && off[r1 + 1] - off[r0] <= stage_bytes) r1++;
+        if (r1 == r0) { rc = fail(MOIRA_ERR_BAD_ARG, "a sequence of %u bytes does not fit the staging buffer", eff[r0]); break; }
+        uint8_t *stage = c->grp_host + (size_t)slot * stage_bytes;
+        if (used[slot]) cudaEventSynchronize(freed[slot]);
+        const int parts = T * 4;
+        parallel_run(parts, T, [&](int p) {
+            for (uint64_t r = r0 + (r1 - r0) * (uint64_t)p / parts, e = r0 + (r1 - r0) * (uint64_t)(p + 1) / parts; r < e; r++)
+                memcpy(stage + (off[r] - off[r0]), reinterpret_cast<const void *>((uintptr_t)seq_addr[r]), eff[r]);
+        });
+        if (cudaMemcpyAsync((uint8_t *)c->dd_store.p + off[r0], stage, off[r1] - off[r0], cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+            rc = fail(MOIRA_ERR_CUDA, "H2D of the sequences failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaEventRecord(freed[slot], stream);
+        used[slot] = true;
+        slot ^= 1;
+        r0 = r1;
+    }
+    if (!rc) {
+        if (cudaMemsetAsync((uint8_t *)c->dd_store.p + total, 0, 64, stream) != cudaSuccess ||
+            cudaMemcpyAsync(c->dd_seq_abs.p, off.data(), n * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+            cudaMemcpyAsync(c->dd_seq_eff.p, eff.data(), n * 4, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+            rc = fail(MOIRA_ERR_CUDA, "H2D of the sequence index failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc) rc = run_dedup(c, (const uint8_t *)c->dd_store.p, (const uint64_t *)c->dd_seq_abs.p, (const uint32_t *)c->dd_seq_eff.p, 0, 0, n, 0,
+                            (uint32_t *)c->dd_labels.p, stream);
+    if (!rc && cudaMemcpyAsync(labels_out, c->dd_labels.p, n * 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+        rc = fail(MOIRA_ERR_CUDA, "D2H of the labels failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (cudaStreamSynchronize(stream) != cudaSuccess && !rc) rc = fail(MOIRA_ERR_CUDA, "dereplication failed: %s", cudaGetErrorString(cudaGetLastError()));
+    for (auto &e : freed) cudaEventDestroy(e);
+    return rc;
 }
 
 int moira_collapse_groups(moira_ctx *c, const uint32_t *labels, const double *ee, int on_device, uint64_t n, uint64_t *n_groups_out,

@@ -557,6 +557,55 @@ extern "C" int moira_fastq_split(const char *text, uint64_t text_bytes, int n_pa
     return MOIRA_OK;
 }
 
+// Byte offsets just behind given numbers of newlines (ascending) of a text, and the text's newline count: one parallel
+// count over 1 MB blocks, then a short scan per query.  This is how blocks of whole records are cut out of two paired
+// files so that they hold the same records (moira.py:1093-1204 reads them in lock step): offsets of lines 4R, 8R, ...
+// in both.  An offset beyond the last newline is text_bytes.
+extern "C" int moira_line_offsets(const char *text, uint64_t text_bytes, const uint64_t *line_numbers, uint64_t n_queries,
+                                  uint64_t *offsets_out, uint64_t *n_lines_out)
+{
+    if ((!text && text_bytes) || (n_queries && (!line_numbers || !offsets_out))) return moira::fail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    constexpr uint64_t BLK = 1u << 20;
+    const uint64_t nb = (text_bytes + BLK - 1) / BLK;
+    std::vector<uint64_t> cnt(nb + 1, 0);
+    int T = g_host_threads > 0 ? g_host_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 64) T = 64;
+    const int parts = (int)std::min<uint64_t>(std::max<uint64_t>(nb, 1), (uint64_t)T * 8);
+    moira::parallel_run(parts, T, [&](int p) {
+        for (uint64_t b = nb * (uint64_t)p / parts, e = nb * (uint64_t)(p + 1) / parts; b < e; b++) {
+            const char *q = text + b * BLK, *end = text + std::min(text_bytes, (b + 1) * BLK);
+            uint64_t c = 0;
+            while (q < end) {
+                const char *nl = (const char *)memchr(q, '\n', (size_t)(end - q));
+                if (!nl) break;
+                c++;
+                q = nl + 1;
+            }
+            cnt[b + 1] = c;
+        }
+    });
+    for (uint64_t b = 0; b < nb; b++) cnt[b + 1] += cnt[b];      // cnt[b] = newlines before block b
+    if (n_lines_out) *n_lines_out = cnt[nb];
+    uint64_t b = 0;
+    for (uint64_t k = 0; k < n_queries; k++) {
+        const uint64_t want = line_numbers[k];
+        if (k && want < line_numbers[k - 1]) return moira::fail(MOIRA_ERR_BAD_ARG, "line numbers must ascend");
+        if (want == 0) { offsets_out[k] = 0; continue; }
+        if (want > cnt[nb]) { offsets_out[k] = text_bytes; continue; }
+        while (b + 1 < nb && cnt[b + 1] < want) b++;             // the want-th newline lies in block b
+        const char *q = text + b * BLK, *end = text + std::min(text_bytes, (b + 1) * BLK);
+        uint64_t left = want - cnt[b];
+        while (left) {
+            const char *nl = (const char *)memchr(q, '\n', (size_t)(end - q));
+            q = nl + 1;
+            left--;
+        }
+        offsets_out[k] = (uint64_t)(q - text);
+    }
+    return MOIRA_OK;
+}
+
 // ---- FASTA + QUAL ------------------------------------------------------------------------------------
 // Record semantics of parse_fasta_and_qual (moira/moira.py:1093-1149, single-end): both files hold one
 // header line and one data line per record ("Expects sequences and qualities to be stored in a single

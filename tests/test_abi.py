@@ -301,3 +301,22 @@ def test_parse_fasta_qual_errors_and_threads():
             P(fa, qu, True)
         assert "record 3210" in ei.value.message and "LengthMismatchError" in ei.value.message
     L.lib.moira_set_host_threads(0)
+
+
+def test_line_offsets_cut_paired_texts_at_the_same_records():
+    """moira_line_offsets: offsets behind the k-th newline, texts with and without a final newline, queries beyond the end."""
+    import moira_b200
+    rng = np.random.default_rng(3)
+    lines = [bytes(rng.integers(65, 91, int(rng.integers(0, 300))).astype(np.uint8)) for _ in range(5000)]
+    for tail in (b"\n", b""):
+        text = b"\n".join(lines) + tail
+        q = np.array([0, 1, 2, 7, 4000, 4999, 5000, 5001, 99999], np.uint64)
+        off, n = moira_b200.line_offsets(text, q)
+        assert n == text.count(b"\n")
+        pos = [0]
+        for i, c in enumerate(text):
+            if c == 10:
+                pos.append(i + 1)
+        want = [pos[int(k)] if int(k) < len(pos) else len(text) for k in q]
+        assert off.tolist() == want
+    assert moira_b200.line_offsets(b"", np.array([0, 3], np.uint64))[0].tolist() == [0, 0]

@@ -372,3 +372,29 @@ def test_groups_on_the_device_equal_groups_on_the_host(ctx, n, pool, ties):
         bad = labels.copy()
         bad[n // 2] = n + 5
         ctx.collapse_labels(bad, ee)
+
+
+@pytest.mark.parametrize("lo,hi,truncate", [(1, 60, 0), (240, 260, 0), (100, 300, 120)])
+def test_labels_of_host_sequences_by_address(ctx, lo, hi, truncate):
+    """moira_collapse_addr: sequences scattered over several host buffers (as the contig rows of several batches are) ->
+    labels on the device -> groups == the host's hash + memcmp collapse of the same strings."""
+    rng = np.random.default_rng(hi * 7 + truncate)
+    n = 40000
+    seqs = _random_sequences(rng, n, 4000, lo, hi)
+    ee = rng.integers(0, 6, n).astype(np.float64) * 0.5
+    ln = np.array([len(s_) for s_ in seqs], np.uint32)
+    # three separate buffers with gaps
+    bufs, addr = [], np.zeros(n, np.uint64)
+    for part in range(3):
+        idx = np.arange(part, n, 3)
+        blob = np.frombuffer(b"".join(seqs[i] + b"##" for i in idx), dtype=np.uint8).copy()
+        bufs.append(blob)
+        pos = np.zeros(len(idx), np.uint64)
+        pos[1:] = np.cumsum(ln[idx][:-1].astype(np.uint64) + np.uint64(2))
+        addr[idx] = pos + np.uint64(blob.ctypes.data)
+    labels = ctx.collapse_addr(addr, ln, truncate)
+    eff = np.minimum(ln, truncate) if truncate else ln
+    want = moira_b200.collapse(None, addr, eff, ee)
+    got = ctx.collapse_groups(labels, ee)
+    for f in ("group_of_read", "rep", "size", "member_start", "members", "order"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k tpr_kernel -s 7 -c 1 -o /tmp/r02_k4q python tools/one_step.py 10000000 decision real > gpurun_out/r02_k4q.log 2>&1
+echo "ncu rc=$?"
+ncu -i /tmp/r02_k4q.ncu-rep --page raw --csv > gpurun_out/r02_k4q_raw.csv 2>/dev/null
+ncu -i /tmp/r02_k4q.ncu-rep --page source --csv > gpurun_out/r02_k4q_source.csv 2>/dev/null
+ls -la gpurun_out/r02_k4q*
