@@ -251,42 +251,33 @@ def _cut_lines(data: bytes, n_lines: int) -> int:
     return int(idx[n_lines - 1]) + 1 if 0 < n_lines <= len(idx) else len(data)
 
 
-def read_fasta_qual_batches(ffh, qfh, lower_n_ambiguous, fasta_name, qual_name):
-    """moira.py:1093-1149, single-end: sequences and qualities on one line each.  Whole-record blocks of
-    both files go through the native parser (moira_parse_fasta_qual)."""
-    fcarry = qcarry = b""
-    while True:
-        block = ffh.read(BATCH_BYTES)
-        fdata = fcarry + block
-        if block:
-            n_lines = fdata.count(b"\n")
-            keep = n_lines - (n_lines % 2)
-            if keep == 0:
-                fcarry = fdata
-                continue
-            pos = _cut_lines(fdata, keep)
-            ftext, fcarry = fdata[:pos], fdata[pos:]
-        else:
-            ftext, fcarry = fdata, b""
-            keep = ftext.count(b"\n") + (1 if ftext and not ftext.endswith(b"\n") else 0)
-            keep -= keep % 2
-        # the same number of lines from the qual file
-        while qcarry.count(b"\n") < keep:
-            qblock = qfh.read(BATCH_BYTES)
-            if not qblock:
-                break
-            qcarry += qblock
-        if block:
-            qpos = _cut_lines(qcarry, keep)
-            qtext, qcarry = qcarry[:qpos], qcarry[qpos:]
-        else:
-            qtext, qcarry = qcarry + qfh.read(), b""
-            if len(qtext.split()) and not ftext.strip():
-                raise NameMismatchError("", _norm_header(qtext.decode("latin-1").splitlines()[0], ">"))
-        if not ftext.strip():
-            break
+def read_fasta_qual_batches(fasta_name, qual_name, lower_n_ambiguous):
+    """moira.py:1093-1149, single-end: sequences and qualities on one line each.  Both files are memory-mapped (gz / bz2:
+    inflated once), cut at the same record numbers by moira_line_offsets, and every pair of blocks goes through the native
+    parser (moira_parse_fasta_qual) as a view -- no text passes through Python."""
+    from .api import line_offsets
+    ftext, fkeep = load_text(fasta_name)
+    qtext, qkeep = load_text(qual_name)
+    f_empty = ftext.size == 0 or (ftext.size < 4096 and not ftext.tobytes().strip())
+    if f_empty:
+        if qtext.size and (qtext.size >= 4096 or qtext.tobytes().strip()):
+            raise NameMismatchError("", _norm_header(qtext[:4096].tobytes().decode("latin-1").splitlines()[0], ">"))
+        return
+    head, qhead = ftext[:1 << 20], qtext[:1 << 20]
+    rec_bytes = max(8.0, head.size / max(1.0, np.count_nonzero(head == 10) / 2.0)) + \
+        max(8.0, qhead.size / max(1.0, np.count_nonzero(qhead == 10) / 2.0))
+    per_block = max(1, int(2 * BATCH_BYTES / rec_bytes))
+    _, nl_f = line_offsets(ftext, np.zeros(0, np.uint64))
+    n_blocks = max(1, -(-((nl_f + 1) // 2) // per_block))
+    marks = np.arange(1, n_blocks, dtype=np.uint64) * np.uint64(2 * per_block)
+    fcut = np.concatenate([[0], line_offsets(ftext, marks)[0], [ftext.size]]).astype(np.int64)
+    qcut = np.concatenate([[0], line_offsets(qtext, marks)[0], [qtext.size]]).astype(np.int64)
+    for k in range(n_blocks):
+        fb, qb = ftext[fcut[k]:fcut[k + 1]], qtext[qcut[k]:qcut[k + 1]]
+        if fb.size == 0 and qb.size == 0:
+            continue
         try:
-            slab, qslab, offsets, lengths, hoff, hlen, soff = parse_fasta_qual(ftext, qtext, lower_n_ambiguous)
+            slab, qslab, offsets, lengths, hoff, hlen, soff = parse_fasta_qual(fb, qb, lower_n_ambiguous)
         except MoiraError as exc:
             if exc.code == L.ERR_PARSE:
                 name = exc.message.split(":")[0]
@@ -300,10 +291,11 @@ def read_fasta_qual_batches(ffh, qfh, lower_n_ambiguous, fasta_name, qual_name):
                     raise LengthMismatchError(exc.message, fasta_name, qual_name) from None
                 raise ValueError(exc.message) from None
             raise
+        if len(lengths) == 0:
+            continue
         # arrays only: (fasta text, header offsets / lengths, sequence offsets, plain qualities at the slab's offsets, slab, ...)
-        yield ftext, hoff, hlen, soff, qslab, slab, offsets, lengths
-        if not block:
-            break
+        yield fb, hoff, hlen, soff, qslab, slab, offsets, lengths
+    del fkeep, qkeep
 
 
 def _whole_records(fh, carry, lines_per_record, want_lines=None):
@@ -690,8 +682,7 @@ def run_fasta_qual(args, ctxs, params, lower_n, out):
 
     def jobs():
         for k, (ftext, hoff, hlen, soff, qslab, slab, offsets, lengths) in enumerate(
-                read_fasta_qual_batches(open_input(args.forward_fasta), open_input(args.forward_qual), lower_n, args.forward_fasta,
-                                        args.forward_qual)):
+                read_fasta_qual_batches(args.forward_fasta, args.forward_qual, lower_n)):
             def job(ctx, k=k, ftext=ftext, hoff=hoff, hlen=hlen, soff=soff, qslab=qslab, slab=slab, offsets=offsets, lengths=lengths):
                 res = ctx.filter_batch(slab, offsets, lengths, params)
                 return k, ftext, hoff, hlen, soff, qslab, offsets, lengths, res
