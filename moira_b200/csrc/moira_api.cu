@@ -99,6 +99,12 @@ struct PairBufs {
     uint8_t *stage = nullptr;
     size_t stage_cap = 0;
     uint64_t pend_start = 0, pend_n = 0;   // chunk whose results sit in `stage`
+    // Pageable callers (numpy arrays, memory-mapped files): the chunk's input bytes are gathered into `in_stage` by all host
+    // threads and cross PCIe from there; the contig rows come back into `out_stage` and are copied to the caller's arrays
+    // at the flush (a cudaMemcpyAsync from / to pageable memory runs at a fraction of the link and blocks the host).
+    uint8_t *in_stage = nullptr, *out_stage = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    bool out_staged = false;
 };
 constexpr size_t PAIR_STAGE_BYTES = 8 + 4 * 5 + 2;   // ee | ns, clen, overlap, gaps, mism | flags, status
 
@@ -689,6 +695,8 @@ int moira_ctx_destroy(moira_ctx *c)
     for (auto &pb : c->pb) {
         for (DevBuf *b : pb.all) if (b->p) cudaFree(b->p);
         if (pb.stage) cudaFreeHost(pb.stage);
+        if (pb.in_stage) cudaFreeHost(pb.in_stage);
+        if (pb.out_stage) cudaFreeHost(pb.out_stage);
     }
     for (DevBuf *b : {&c->trace, &c->hbuf, &c->post, &c->pair_counters, &c->dd_hash, &c->dd_table, &c->dd_labels, &c->dd_store,
                       &c->dd_seq_abs, &c->dd_seq_eff, &c->grp_dev})
@@ -1659,8 +1667,21 @@ static int filter_pairs_impl(moira_ctx *c, const char *fwd_seq, uint64_t fwd_byt
         if (gaps) memcpy(gaps + st0, st + m * 20, m * 4);
         if (mismatches) memcpy(mismatches + st0, st + m * 24, m * 4);
         memcpy(status + st0, st + m * 29, m);
+        if (b.out_staged) {
+            parallel_memcpy(contig_seq + st0 * out_stride, b.out_stage, m * out_stride);
+            parallel_memcpy(contig_qual + st0 * out_stride, b.out_stage + m * out_stride, m * out_stride);
+        }
         b.pend_n = 0;
     };
+    // pageable inputs / outputs are staged through pinned memory (see PairBufs)
+    auto pinned = [](const void *p) {
+        cudaPointerAttributes attr;
+        const bool yes = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return yes;
+    };
+    const bool stage_in = !(pinned(fwd_seq) && pinned(fwd_qual) && pinned(rev_seq) && pinned(rev_qual));
+    const bool stage_out = !(pinned(contig_seq) && pinned(contig_qual));
     c->pb[0].pend_n = c->pb[1].pend_n = 0;
     int ci = 0;
     for (uint64_t start = 0; start < n; start += PAIR_CHUNK, ci++) {
@@ -1697,10 +1718,26 @@ static int filter_pairs_impl(moira_ctx *c, const char *fwd_seq, uint64_t fwd_byt
             (rc = ensure(b.overlap, cn * 4)) || (rc = ensure(b.gaps, cn * 4)) || (rc = ensure(b.mism, cn * 4)) ||
             (rc = ensure(b.status, cn)) || (rc = ensure(b.ee, cn * 8)) || (rc = ensure(b.ns, cn * 4)) || (rc = ensure(b.flags, cn)))
             return rc;
-        CU(cudaMemcpyAsync(b.fseq.p, fwd_seq + f0, f1 - f0, cudaMemcpyHostToDevice, s));
-        if (!f_shared) CU(cudaMemcpyAsync(b.fqual.p, fwd_qual + fq0, fq1 - fq0, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b.rseq.p, rev_seq + r0, r1 - r0, cudaMemcpyHostToDevice, s));
-        if (!r_shared) CU(cudaMemcpyAsync(b.rqual.p, rev_qual + rq0, rq1 - rq0, cudaMemcpyHostToDevice, s));
+        if (stage_in) {
+            const size_t need = (f1 - f0) + (f_shared ? 0 : fq1 - fq0) + (r1 - r0) + (r_shared ? 0 : rq1 - rq0) + 64;
+            if ((rc = ensure_host(&b.in_stage, &b.in_cap, need))) return rc;
+            uint8_t *w = b.in_stage;
+            auto ship = [&](void *dst, const void *src, size_t bytes) {
+                parallel_memcpy(w, src, bytes);
+                const cudaError_t e = cudaMemcpyAsync(dst, w, bytes, cudaMemcpyHostToDevice, s);
+                w += (bytes + 15) & ~(size_t)15;
+                return e;
+            };
+            CU(ship(b.fseq.p, fwd_seq + f0, f1 - f0));
+            if (!f_shared) CU(ship(b.fqual.p, fwd_qual + fq0, fq1 - fq0));
+            CU(ship(b.rseq.p, rev_seq + r0, r1 - r0));
+            if (!r_shared) CU(ship(b.rqual.p, rev_qual + rq0, rq1 - rq0));
+        } else {
+            CU(cudaMemcpyAsync(b.fseq.p, fwd_seq + f0, f1 - f0, cudaMemcpyHostToDevice, s));
+            if (!f_shared) CU(cudaMemcpyAsync(b.fqual.p, fwd_qual + fq0, fq1 - fq0, cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(b.rseq.p, rev_seq + r0, r1 - r0, cudaMemcpyHostToDevice, s));
+            if (!r_shared) CU(cudaMemcpyAsync(b.rqual.p, rev_qual + rq0, rq1 - rq0, cudaMemcpyHostToDevice, s));
+        }
         uint64_t *d_foff = (uint64_t *)b.foff.p, *d_roff = (uint64_t *)b.roff.p;   // [0, cn): bases, [cn, 2 cn): qualities
         CU(cudaMemcpyAsync(d_foff, fwd_off + start, cn * 8, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(d_foff + cn, fwd_qoff + start, cn * 8, cudaMemcpyHostToDevice, s));
@@ -1756,8 +1793,15 @@ static int filter_pairs_impl(moira_ctx *c, const char *fwd_seq, uint64_t fwd_byt
         CU(cudaMemcpyAsync(st + cn * 24, b.mism.p, cn * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(st + cn * 29, b.status.p, cn, cudaMemcpyDeviceToHost, s));
         b.pend_start = start; b.pend_n = cn;
-        CU(cudaMemcpyAsync(contig_seq + start * out_stride, b.cseq.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(contig_qual + start * out_stride, b.cqual.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
+        b.out_staged = stage_out;
+        if (stage_out) {
+            if ((rc = ensure_host(&b.out_stage, &b.out_cap, 2 * cn * out_stride))) return rc;
+            CU(cudaMemcpyAsync(b.out_stage, b.cseq.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(b.out_stage + cn * out_stride, b.cqual.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
+        } else {
+            CU(cudaMemcpyAsync(contig_seq + start * out_stride, b.cseq.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(contig_qual + start * out_stride, b.cqual.p, cn * out_stride, cudaMemcpyDeviceToHost, s));
+        }
     }
     CU(cudaStreamSynchronize(c->streams[1]));
     CU(cudaStreamSynchronize(c->streams[0]));
