@@ -206,11 +206,37 @@ struct ReadResult {
     int next_rung;     // where an unsettled read goes: the next rung, or the one the first pass picked itself (direct_rung)
 };
 
+// Smallest rung whose capacity holds k entries, in closed form: a search through rung_cap()'s table indexes a constexpr array
+// with a run-time value, which the compiler keeps in LOCAL memory -- ncu showed the classifier waiting on those LDL/STL
+// (20 % of its warp-state samples).
+__host__ __device__ constexpr int rung_for(int k)
+{
+    if (k <= 8) return k <= 3 ? 1 : k - 2;
+    if (k <= 24) return 6 + ((k - 8 + 1) >> 1);
+    if (k <= 28) return 15;
+    if (k <= 32) return 16;
+    if (k <= 40) return 17;
+    if (k <= 48) return 18;
+    if (k <= 64) return 19;
+    if (k <= 128) return 20;
+    if (k <= 256) return 21;
+    if (k <= 512) return 22;
+    if (k <= 1024) return 23;
+    return NB - 1;
+}
+constexpr bool rung_for_matches_table()
+{
+    for (int k = 1; k <= 1100; k++) {
+        const int b = rung_for(k);
+        if (b < 1 || b > NB - 1 || rung_cap(b) < k || (b > 1 && rung_cap(b - 1) >= k)) return false;
+    }
+    return true;
+}
+static_assert(rung_for_matches_table(), "rung_for() and rung_cap() out of step");
 __device__ __forceinline__ int pick_rung(const FilterArgs &a, int kneed)
 {
-    int b = a.min_rung > 1 ? a.min_rung : 1;
-    while (b < NB - 1 && rung_cap(b) < kneed) b++;
-    return b;
+    const int lo = a.min_rung > 1 ? a.min_rung : 1, b = rung_for(kneed);
+    return b > lo ? b : lo;
 }
 
 // The rung of a read the first pass swept completely without settling it, from the two entries every sweep tracks
