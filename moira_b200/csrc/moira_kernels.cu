@@ -457,6 +457,9 @@ __device__ __forceinline__ void sweep_word(uint32_t wi, uint32_t lut_lane, T (&P
 // (one / two words per iteration): the ladder kernel -- every K in one kernel, 14 .. 50 KB of unrolled 16-base body per K --
 // streamed its code through the instruction caches (ncu: 9 % of its warp states were no_instruction).  The single-K first
 // pass kernels keep the unrolled body (rolled: -4 % on the K = 18 sweep of 1 500-bp reads).
+#ifndef MOIRA_LADDER_SPLIT
+#define MOIRA_LADDER_SPLIT 8   // last rung of the 16-warp ladder launch
+#endif
 #ifndef MOIRA_LADDER_ROLL
 #define MOIRA_LADDER_ROLL 1
 #endif
@@ -910,7 +913,7 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) ladder_tpr_kernel(const F
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int WARPS = WIDE ? 8 : 16;
-    constexpr int R0 = WIDE ? 9 : 1, R1 = WIDE ? N_TPR_RUNGS : 8;   // rung_cap(8) == 12
+    constexpr int R0 = WIDE ? MOIRA_LADDER_SPLIT + 1 : 1, R1 = WIDE ? N_TPR_RUNGS : MOIRA_LADDER_SPLIT;   // rung_cap(8) == 12, rung_cap(14) == 24
     uint32_t counts[N_TPR_RUNGS + 1];
     uint32_t any = 0;
 #pragma unroll
