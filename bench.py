@@ -751,6 +751,9 @@ def run_ours(args):
                                algorithmic_flop_per_read=alg_d / n_c)
         res["accepted_fraction"] = float(cd[L.CNT_ACCEPTED]) / max(1, int(cd[L.CNT_READS]))
         res["escalated_fraction"] = float(cd[L.CNT_ESCALATED]) / max(1, int(cd[L.CNT_READS]))
+        # classify-first batches (decisions / statistics that need 9 or more entries): the fp32 classifier is the first pass and
+        # the ladder sweeps every read once with its own K
+        res["classified_first_fraction"] = float(cd[L.CNT_CLASSIFIED]) / max(1, int(cd[L.CNT_READS]))
         ms_x2, _, _, _, cx = w.timed(px, steps, warm=1)
         alg_x2 = w.algorithmic_flop_exact()
         res["exact_ee"] = dict(fp64_view(cx, steps, ms_x2, n_c), value=world * n_c * steps / (ms_x2 * 1e-3), ms_per_step=ms_x2 / steps,

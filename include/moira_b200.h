@@ -101,6 +101,8 @@ extern "C" {
                                       the cascade setting and the mode, unlike every other counter */
 #define MOIRA_CNT_FP64_OPS     9   /* FP64 operations (thread level) executed by the PMF / Lambda sweeps: the numerator of the executed-flop
                                       roofline; diagnostic like MOIRA_CNT_ESCALATED (depends on cascade / ladder choices) */
+#define MOIRA_CNT_CLASSIFIED   10  /* reads of classify-first batches (the classifier ran as the first pass and the ladder did every sweep:
+                                      exact mode or decisions that need 9 or more entries); diagnostic like the two above */
 #define MOIRA_CNT_HIST         16  /* 64 bins of floor(final ee); last bin = >= 63 */
 #define MOIRA_N_HIST           64
 #define MOIRA_N_COUNTERS       80

@@ -29,6 +29,7 @@ CNT_READS, CNT_ACCEPTED, CNT_BAD_ERRORS, CNT_BAD_LENGTH, CNT_BAD_AMBIGS = 0, 1, 
 CNT_NEAR_CUTOFF, CNT_LOWER_BOUND, CNT_NUMERIC, CNT_HIST, N_HIST, N_COUNTERS = 5, 6, 7, 16, 64, 80
 CNT_ESCALATED = 8
 CNT_FP64_OPS = 9
+CNT_CLASSIFIED = 10
 MAX_INFLIGHT = 4
 CONSENSUS_BEST, CONSENSUS_SUM, CONSENSUS_POSTERIOR = 0, 1, 2
 PAIR_OK, PAIR_EMPTY, PAIR_BAD_BASE, PAIR_BAD_QUALITY, PAIR_TOO_LONG = 0, 1, 2, 3, 4

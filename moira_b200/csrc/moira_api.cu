@@ -166,6 +166,11 @@ struct moira_ctx {
     int cascade = 1;
     int cascade_multi = 1; // decisions needing 5..8 entries: first stage picked among 2..5 entries (0: two entries or none)
     double direct_gap = 0.5;
+    int classify_first_k = 9;          // exact mode, first-pass K at least this: the classifier runs first and the ladder does all sweeps
+    int classify_first_dec_k = 9;      // the same in decision mode
+    int classify_first_sorted_k = 9;   // the same for length-bucketed (ragged) batches
+    int exact_sorted_k_cap = 4;        // length-bucketed first pass in exact mode: at most this many entries (0: the decision's K);
+                                       // measured on C5 (100..600 bp): 4 -> 4.56 ms, 5 -> 4.68, 6 -> 4.88, none (3..8) -> 5.08, 3 -> 5.24
     int direct_rung = 1;   // the first pass picks the ladder rung of the reads it hands on (0: every one goes through the classifier)
     int timing = 0;
     int n_timed = 0;
@@ -302,6 +307,7 @@ void note_escalations(moira_ctx *c, const moira_params *p, const uint64_t *count
     if (!p || p->mode != MOIRA_MODE_PB || p->exact_ee || !counters) return;
     if (c->blind_off_left > 0) { c->blind_off_left--; return; }
     const uint64_t reads = counters[MOIRA_CNT_READS], esc = counters[MOIRA_CNT_ESCALATED];
+    if (counters[MOIRA_CNT_CLASSIFIED]) return;   // a classify-first batch says nothing about the cascade
     if (reads >= 4096 && esc * 100 > reads * 35) c->blind_off_left = 32;
 }
 
@@ -437,7 +443,14 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
         a.min_rung = 1;
         while (a.min_rung < NB - 1 && rung_cap(a.min_rung) <= k_first) a.min_rung++;
     }
-    const bool ladder = p->mode == MOIRA_MODE_PB && (p->exact_ee || !k_decides_all);
+    // Classify first: where the decision's own K is large (long reads, lax cutoffs) a first pass with that K is paid by every
+    // read although most need far fewer entries -- or, in exact mode, far more, and then the pass was for nothing.  The
+    // classifier (fp32 mean / variance of the error count: a quarter of a two-entry sweep) reads every row once and sends each
+    // read to the rung that holds its own j* + 1 entries (decision mode: at most the decision's K); the ladder does all the
+    // FP64 work.  Length-bucketed (ragged) batches: the classifier walks the sorted permutation.
+    const bool cf_plain = p->mode == MOIRA_MODE_PB && k_first >= (p->exact_ee ? c->classify_first_k : c->classify_first_dec_k);
+    const bool cf_sorted = p->mode == MOIRA_MODE_PB && k_first >= (p->exact_ee ? c->classify_first_sorted_k : c->classify_first_dec_k);
+    const bool ladder = p->mode == MOIRA_MODE_PB && (p->exact_ee || !k_decides_all || cf_plain || cf_sorted);
     a.allow_push = ladder ? 1 : 0;
     a.direct_rung = (ladder && c->direct_rung) ? 1 : 0;
     a.direct_gap = c->direct_gap;
@@ -447,7 +460,7 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
     // 3 k_first - 2; only the reads in between are swept again with k_first entries (decision mode) or walk the ladder
     // (exact mode).  Whether that pays depends on the data: a pilot launch over the first tiles measures the escalated
     // fraction on the device, and the two candidate launches for the rest read that verdict (no host synchronisation).
-    const bool cascade_ok = p->mode == MOIRA_MODE_PB && k_decides_all && k_first >= 3 && k_first <= 8 && p->cascade != 2 && c->cascade;
+    const bool cascade_ok = p->mode == MOIRA_MODE_PB && k_decides_all && k_first >= 3 && k_first <= 8 && p->cascade != 2 && c->cascade && !cf_plain;
     const bool queues_needed = ladder || cascade_ok;
     if (cascade_ok) a.min_rung = 1;   // what a two-entry sweep hands on may need as few as three entries
 
@@ -483,7 +496,8 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             if ((rc = ensure_lsort(ws, (uint32_t)std::min<uint64_t>(n_reads, sub), lb))) return rc;
             CU(cudaMemsetAsync(lb.hist, 0, LEN_BUCKETS * sizeof(uint32_t), stream));
             const int single = p->mode != MOIRA_MODE_PB;
-            if (launch_length_sort(a, lb, single, cfg)) return fail(MOIRA_ERR_CUDA, "length-sort launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            a.first_k_cap = (ladder && p->exact_ee && a.allow_push) ? c->exact_sorted_k_cap : 0;
+            if (launch_length_sort(a, lb, single || cf_sorted, cfg)) return fail(MOIRA_ERR_CUDA, "length-sort launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             c->launches += 3;
             a.queue = lb.queue;
             a.min_rung = 1;
@@ -492,6 +506,14 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
                 a.seg_count = lb.group_count;
                 a.queue_count = lb.group_count;
                 rc = launch_lambda(a, cfg, &name);
+            } else if (cf_sorted) {
+                // the classifier walks the length-sorted permutation, so the rung queues fill in (almost) length order and the
+                // ladder's warp tiles hold reads of (almost) one length
+                a.seg_start = lb.group_start;
+                a.seg_count = lb.group_count;
+                a.queue_count = lb.group_count;
+                rc = launch_classify_first(a, cfg);
+                name = "classifier over the length-sorted reads + ladder";
             } else {
                 rc = launch_sorted_first(a, lb.group_start, lb.group_count, cfg);
                 name = "pb_tpr<K per length bucket>";
@@ -500,6 +522,12 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             if (rc < 0) return fail(MOIRA_ERR_CUDA, "first-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             c->launches++;
             a.queue = nullptr; a.queue_count = nullptr; a.seg_start = nullptr; a.seg_count = nullptr;
+        } else if (cf_plain) {
+            a.min_rung = 1;
+            rc = launch_classify_first(a, cfg);
+            name = "classifier + ladder";
+            if (rc < 0) return fail(MOIRA_ERR_CUDA, "classifier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            c->launches++;
         } else if (cascade_ok) {
             // two-entry launches: escalate to queue 0; in decision mode certain rejects are settled by the bound
             FilterArgs a2 = a;
@@ -649,6 +677,10 @@ static int ctx_init(moira_ctx *c, int device, int sm_count)
     if (const char *e = getenv("MOIRA_B200_NO_CASCADE_MULTI")) c->cascade_multi = (e[0] == '1') ? 0 : 1;   // diagnostics
     if (const char *e = getenv("MOIRA_B200_DIRECT_GAP")) c->direct_gap = atof(e);   // tuning
     if (const char *e = getenv("MOIRA_B200_NO_DIRECT_RUNG")) c->direct_rung = (e[0] == '1') ? 0 : 1;   // diagnostics: classifier pass for all
+    if (const char *e = getenv("MOIRA_B200_CLASSIFY_FIRST_K")) c->classify_first_k = atoi(e);   // tuning (1000: never)
+    if (const char *e = getenv("MOIRA_B200_CLASSIFY_FIRST_DEC_K")) c->classify_first_dec_k = atoi(e);   // tuning
+    if (const char *e = getenv("MOIRA_B200_CLASSIFY_FIRST_SORTED_K")) c->classify_first_sorted_k = atoi(e);   // tuning
+    if (const char *e = getenv("MOIRA_B200_EXACT_SORTED_KCAP")) c->exact_sorted_k_cap = atoi(e);   // tuning
     if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
     if (kernels_init(c->sm_count)) return fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaMalloc(&c->d_p, 256 * sizeof(double)));

@@ -70,6 +70,7 @@ struct FilterArgs {
     // decision needs; reads it cannot settle exactly are rejected when the Newton bound on acc[k_dec - 1] allows it
     // and pushed to queue 0 otherwise.  0: off.
     int32_t k_dec;
+    int32_t first_k_cap;         // length-bucketed first pass, exact mode: no bucket is swept with more entries than this (0: no cap)
     uint32_t tile0;              // first pass: the launch starts at this warp tile (the tiles before belong to the pilot launch)
     uint32_t *jhist;             // not null (second pilot launch of the cascade): 16 bins of floor(ee) of this launch's reads
     const uint32_t *policy;      // not null: the launch runs only if *policy == policy_want (set on the device by the pilot)
@@ -93,6 +94,8 @@ int launch_pb_first(const FilterArgs &a, int k_wanted, const LaunchCfg &cfg, con
 int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name);
 // ladder rung b over queue b (b == 0: classifier; b > N_TPR_RUNGS: warp-/block-per-read rungs)
 int launch_rung(const FilterArgs &a, int b, const LaunchCfg &cfg);
+// the classifier as the first pass: all reads of the sub-batch (or the queue / segment in `a`) -> rung queues
+int launch_classify_first(const FilterArgs &a, const LaunchCfg &cfg);
 // rungs 1..N_TPR_RUNGS in one launch
 int launch_ladder_tpr(const FilterArgs &a, const LaunchCfg &cfg);
 // ---- on-device length bucketing of ragged batches (counting sort by padded length) ----------------

@@ -780,6 +780,10 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
                 if (kd < kn) kn = kd;
             }
             const int kneed = kn > 1.0e6 ? 1000000 : (kn < 2.0 ? 2 : (int)kn);
+            if (a.rung < 0) {   // classifier run as the first pass (classify-first): every read is handed on
+                const unsigned vm = __ballot_sync(FULL, valid);
+                if (vm && lane == 0) atomicAdd(&s_cnt[MOIRA_CNT_CLASSIFIED], (uint32_t)__popc(vm));
+            }
             push_read(a, valid, pick_rung(a, kneed), r_local, lane);
             tile = next_tile;
             valid = nvalid; r_local = nr_local; g = ng;
@@ -1254,9 +1258,11 @@ __global__ void __launch_bounds__(1024) len_scan_kernel(const FilterArgs a, cons
             if (!single_group) {
                 // K a decision needs for the longest read of the bucket: floor(cutoff) + 2
                 const double cutoff = a.thr_kind == MOIRA_THR_MAXERRORS ? a.thr : __dmul_rn((double)(b * 16), a.thr);
-                const double kd = cutoff < 0.0 ? 2.0 : floor(cutoff) + 2.0;
+                double kd = cutoff < 0.0 ? 2.0 : floor(cutoff) + 2.0;
+                if (b == LEN_BUCKETS - 1) kd = 1e9;   // the catch-all bucket (lengths unknown to the host): the largest K
+                // exact mode with a ladder behind the first pass: the pass only has to settle the reads that are cheap to settle
+                if (a.first_k_cap && kd > (double)a.first_k_cap) kd = (double)a.first_k_cap;
                 while (g < N_FIRST_K - 1 && (double)first_pass_k(g) < kd) g++;
-                if (b == LEN_BUCKETS - 1) g = N_FIRST_K - 1;   // the catch-all bucket (lengths unknown to the host): the largest K
             }
             atomicMin(&s_gs[g], run);
             atomicAdd(&s_gc[g], v[i]);
@@ -1452,7 +1458,7 @@ int kernels_init(int)
 #define X(k) if (init_tpr<k, 0, false>() || init_tpr<k, 0, true>()) return -1;
     MOIRA_FOR_EACH_K(X)
 #undef X
-    if (init_tpr<1, 1, false>() || init_tpr<1, 1, true>() || init_tpr<2, 2, false>()) return -1;
+    if (init_tpr<1, 1, false>() || init_tpr<1, 1, true>() || init_tpr<2, 2, false>() || init_tpr<2, 2, true>()) return -1;
     if (cudaFuncSetAttribute(sorted_first_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(sorted_first_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(sorted_first_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPR_SMEM) != cudaSuccess) return -1;
@@ -1548,6 +1554,14 @@ int launch_lambda(const FilterArgs &a, const LaunchCfg &cfg, const char **name)
 {
     if (name) *name = "lambda_tpr";
     return cfg.tmap ? launch_tpr_tma<1, 1>(a, cfg) : launch_tpr<1, 1>(a, cfg);
+}
+
+// The classifier as the first pass (exact mode, reads that need many entries): over all reads of the sub-batch in slab order
+// (TMA tiles when cfg.tmap is set) or over the queue / segment the caller put into `a`; every read goes to the rung its
+// mean / variance estimate calls for.
+int launch_classify_first(const FilterArgs &a, const LaunchCfg &cfg)
+{
+    return cfg.tmap ? launch_tpr_tma<2, 2>(a, cfg) : launch_tpr<2, 2>(a, cfg);
 }
 
 int launch_rung(const FilterArgs &a0, int b, const LaunchCfg &cfg0)

@@ -23,7 +23,7 @@ def _q1(kat):
 def _same_counters(a, b):
     """Every counter but MOIRA_CNT_ESCALATED, which describes the route a batch took (cascade or single sweep; the
     library adapts that to the data it has seen), not its result."""
-    keep = (np.arange(L.N_COUNTERS) != L.CNT_ESCALATED) & (np.arange(L.N_COUNTERS) != L.CNT_FP64_OPS)
+    keep = (np.arange(L.N_COUNTERS) != L.CNT_ESCALATED) & (np.arange(L.N_COUNTERS) != L.CNT_FP64_OPS) & (np.arange(L.N_COUNTERS) != L.CNT_CLASSIFIED)
     return np.array_equal(np.asarray(a)[keep], np.asarray(b)[keep])
 
 
@@ -485,7 +485,7 @@ def test_cascaded_first_pass_gives_identical_results(ctx, profile, n, kw):
         auto = ctx.filter_batch(slab, off, ln, FilterParams(exact_ee=exact, **kw))
         for r in (two, auto):
             assert np.array_equal(r.ee, one.ee) and np.array_equal(r.ns, one.ns) and np.array_equal(r.flags, one.flags)
-            same = (np.arange(L.N_COUNTERS) != L.CNT_ESCALATED) & (np.arange(L.N_COUNTERS) != L.CNT_FP64_OPS)   # the counters that describe the route, not the result
+            same = (np.arange(L.N_COUNTERS) != L.CNT_ESCALATED) & (np.arange(L.N_COUNTERS) != L.CNT_FP64_OPS) & (np.arange(L.N_COUNTERS) != L.CNT_CLASSIFIED)   # the counters that describe the route, not the result
             assert np.array_equal(r.counters[same], one.counters[same])
         p = FilterParams(exact_ee=exact, **{k: v for k, v in kw.items() if k != "length_sort"})
         eff = np.minimum(ln, p.truncate) if p.truncate else ln
@@ -521,7 +521,7 @@ def test_cascade_pilot_chooses_per_batch(ctx):
                               cnt.data_ptr(), stream)
             torch.cuda.synchronize()
             outs.append((ee.cpu().numpy(), ns.cpu().numpy(), fl.cpu().numpy(), cnt.cpu().numpy(), ctx.launch_count - before))
-        same = (np.arange(L.N_COUNTERS) != L.CNT_ESCALATED) & (np.arange(L.N_COUNTERS) != L.CNT_FP64_OPS)
+        same = (np.arange(L.N_COUNTERS) != L.CNT_ESCALATED) & (np.arange(L.N_COUNTERS) != L.CNT_FP64_OPS) & (np.arange(L.N_COUNTERS) != L.CNT_CLASSIFIED)
         for a, b in ((0, 1), (2, 3)):
             for k in range(3):
                 assert np.array_equal(outs[a][k], outs[b][k]), (name, a, k)

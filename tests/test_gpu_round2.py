@@ -30,7 +30,7 @@ def _marks_numpy(slab, off, ln, truncate=0):
 
 def _same_but_diagnostics(a, b):
     keep = np.ones(L.N_COUNTERS, bool)
-    keep[[L.CNT_ESCALATED, L.CNT_FP64_OPS]] = False
+    keep[[L.CNT_ESCALATED, L.CNT_FP64_OPS, L.CNT_CLASSIFIED]] = False
     return np.array_equal(np.asarray(a)[keep], np.asarray(b)[keep])
 
 
@@ -398,3 +398,79 @@ def test_labels_of_host_sequences_by_address(ctx, lo, hi, truncate):
     got = ctx.collapse_groups(labels, ee)
     for f in ("group_of_read", "rep", "size", "member_start", "members", "order"):
         assert np.array_equal(getattr(got, f), getattr(want, f)), f
+
+
+def _fresh_ctx(env):
+    """A context created under environment switches (the library reads them at context creation)."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return moira_b200.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("n,maxerrors,length_sort", [(60000, None, 2), (60000, None, 1), (3000, None, 0), (40000, 24.0, 0)])
+def test_classify_first_equals_first_pass_with_the_decisions_k(n, maxerrors, length_sort):
+    """Long reads (1 500 bp: the decision needs 17 entries): by default the fp32 classifier runs first and the ladder sweeps
+    every read once with its own K.  Against the route with a K = 18 first pass: exact mode writes the same arrays and
+    counters; decision mode the same decisions, the same ee for every accepted read, valid lower bounds for the others;
+    both are the oracle's.  length_sort = 1: the classifier walks the length-sorted permutation."""
+    slab, off, ln = synth.generate("ccs", n, 91)
+    slab = slab.copy()
+    rng = np.random.default_rng(5)
+    slab[off[rng.integers(0, n, 500)] + rng.integers(0, 1500, 500).astype(np.uint64)] = 0xFF      # some N
+    ln = ln.copy()
+    ln[:50] = rng.integers(0, 40, 50)                                                                # and some very short / empty reads
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    cut = np.full(n, maxerrors) if maxerrors else ln * 0.01
+    ok_o = (ee_o + ns_o) <= cut
+    kw = dict(maxerrors=maxerrors, length_sort=length_sort) if maxerrors else dict(length_sort=length_sort)
+    cf = _fresh_ctx({})
+    fp = _fresh_ctx({"MOIRA_B200_CLASSIFY_FIRST_K": "1000", "MOIRA_B200_CLASSIFY_FIRST_DEC_K": "1000"})
+    try:
+        for exact in (True, False):
+            p = FilterParams(exact_ee=exact, **kw)
+            a, b = cf.filter_batch(slab, off, ln, p), fp.filter_batch(slab, off, ln, p)
+            assert int(a.counters[L.CNT_CLASSIFIED]) == n and int(b.counters[L.CNT_CLASSIFIED]) == 0
+            assert np.array_equal(a.accept, ok_o) and np.array_equal(b.accept, ok_o)
+            assert np.array_equal(a.ns, ns_o) and np.array_equal(b.ns, ns_o)
+            assert not (a.flags & L.FLAG_NUMERIC).any()
+            if exact:
+                assert np.array_equal(a.ee, ee_o) and np.array_equal(b.ee, ee_o) and np.array_equal(a.flags, b.flags)
+                assert _same_but_diagnostics(a.counters, b.counters)
+            else:
+                la, lb = a.lower_bound, b.lower_bound
+                assert np.array_equal(a.ee[~la], ee_o[~la]) and (a.ee[la] <= ee_o[la]).all() and not (la & a.accept).any()
+                assert np.array_equal(b.ee[~lb], ee_o[~lb]) and (b.ee[lb] <= ee_o[lb]).all()
+                keep = [L.CNT_READS, L.CNT_ACCEPTED, L.CNT_BAD_ERRORS, L.CNT_BAD_LENGTH, L.CNT_BAD_AMBIGS]
+                assert np.array_equal(np.asarray(a.counters)[keep], np.asarray(b.counters)[keep])
+                # fewer FP64 operations than sweeping 18 entries for every read
+                assert int(a.counters[L.CNT_FP64_OPS]) < int(b.counters[L.CNT_FP64_OPS])
+    finally:
+        cf.close()
+        fp.close()
+
+
+def test_length_bucketed_exact_first_pass_with_capped_k():
+    """Ragged batches in exact mode: the length-bucketed first pass sweeps at most four entries and the ladder does the
+    rest; same arrays and counters as with every bucket's own decision K, and the oracle's."""
+    n = 80000
+    slab, off, ln = synth.generate("mixed", n, 93)
+    ee_o, ns_o = po.pb_batch(slab, off, ln, 0.005)
+    capped = _fresh_ctx({})
+    full = _fresh_ctx({"MOIRA_B200_EXACT_SORTED_KCAP": "0"})
+    try:
+        p = FilterParams(exact_ee=True, length_sort=1)
+        a, b = capped.filter_batch(slab, off, ln, p), full.filter_batch(slab, off, ln, p)
+        assert np.array_equal(a.ee, ee_o) and np.array_equal(a.ns, ns_o) and np.array_equal(b.ee, ee_o)
+        assert np.array_equal(a.flags, b.flags) and _same_but_diagnostics(a.counters, b.counters)
+        assert int(a.counters[L.CNT_ESCALATED]) > int(b.counters[L.CNT_ESCALATED])
+    finally:
+        capped.close()
+        full.close()

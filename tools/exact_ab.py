@@ -37,10 +37,18 @@ for w in work:
             e1.record()
             torch.cuda.synchronize()
             if rep: best = min(best, e0.elapsed_time(e1))
+        ctx.set_timing(True)   # one more call with the library's own events around the first-pass launches
+        ctx.filter_device(slab.data_ptr(), None, d_len, stride, fixed or 0, n, p, ee.data_ptr(), ns.data_ptr(), fl.data_ptr(),
+                          cnt.data_ptr(), stream, marks.data_ptr())
+        torch.cuda.synchronize()
+        first_ms, first_name = ctx.last_kernel_ms()
+        ctx.set_timing(False)
         c = cnt.cpu().numpy()
+        c = c // 2   # two calls added into these counters
         ops = float(c[L.CNT_FP64_OPS])
         out.append("%s %.3f ms %.4g reads/s  exec %.0f flop/read  frac %.3f  esc %.3f" % (
-            "exact" if exact else "decision", best, n / best * 1e3, ops / n, ops / (best * 1e-3) / peak, c[L.CNT_ESCALATED] / n))
+            "exact" if exact else "decision", best, n / best * 1e3, ops / n, ops / (best * 1e-3) / peak, c[L.CNT_ESCALATED] / n)
+            + "  first pass %.3f ms (%s)" % (first_ms, first_name))
     print(" | ".join(out), flush=True)
     del slab, lens, ee, ns, fl, marks
     torch.cuda.empty_cache()
