@@ -258,6 +258,38 @@ def cli_bench(rec, accepted_per_read, world, rank, args):
             for f in files:
                 os.remove(os.path.join(tmp, f))
         if world == 1:
+            # compressed files in and out (moira.py:1065-1068 sniffed gzip input, --output_compression gz): the whole file as
+            # blocked gzip (BGZF, what bgzip / Illumina's writers produce: moira_gz_inflate on all host threads), a 2 M-read
+            # prefix as one plain gzip member (one inflate thread: a deflate stream cannot be split), and gzip outputs
+            from moira_b200 import gz_deflate
+            import zlib
+            gzp = os.path.join(tmp, "in.bgzf.fastq.gz")
+            fd = os.open(gzp, os.O_CREAT | os.O_WRONLY, 0o644)
+            t0 = time.perf_counter()
+            gz_bytes = gz_deflate(rec.reshape(-1), fd, 0, 6, 0, eof=True)
+            t_def = time.perf_counter() - t0
+            os.close(fd)
+            m_plain = min(m, 2_000_000)
+            plain_p = os.path.join(tmp, "in.plain.fastq.gz")
+            zc = zlib.compressobj(1, zlib.DEFLATED, 31)
+            with open(plain_p, "wb") as fh:
+                fh.write(zc.compress(rec[:m_plain].tobytes()))
+                fh.write(zc.flush())
+            comp = {"bgzf_input_bytes": int(gz_bytes), "bgzf_written_in_seconds": t_def,
+                    "bgzf_deflate_gb_per_s": rec.nbytes / t_def / 1e9}
+            for tag, pth, mm_, extra in (("bgzf_in", gzp, m, []), ("plain_gzip_in", plain_p, m_plain, []),
+                                         ("bgzf_in_gz_out", gzp, m, ["-oc", "gz"])):
+                t0 = time.perf_counter()
+                rc = cli.main(cli.parse_arguments(["-ffq", pth, "-op", os.path.join(tmp, "z_" + tag), "--devices", devs] + extra), _io.StringIO())
+                dt = time.perf_counter() - t0
+                files = {f: os.path.getsize(os.path.join(tmp, f)) for f in sorted(os.listdir(tmp)) if f.startswith("z_" + tag + ".")}
+                comp[tag] = {"value": mm_ / dt, "unit": "reads/s", "reads": mm_, "seconds": dt, "rc": rc, "output_bytes": int(sum(files.values()))}
+                for f in files:
+                    os.remove(os.path.join(tmp, f))
+            os.remove(gzp); os.remove(plain_p)
+            comp["note"] = ("default flags (exact ee, collapse, fasta + qual + names); bgzf_in: every 64 KB member inflated on its own thread; "
+                            "plain_gzip_in: one member, one inflate thread (zlib), %d reads; gz_out: outputs as BGZF members compressed on all host threads" % m_plain)
+            out["compressed"] = comp
             # the paired flow (moira's main use): two FASTQ files -> contigs -> filter -> collapse -> files
             from tools.bench_contigs import make_pairs
             n_pairs, rl = 400_000, 251

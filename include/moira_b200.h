@@ -374,6 +374,11 @@ MOIRA_API int moira_blocks_write(const moira_blocks *blocks, int which, int fd, 
                                  uint64_t *written_out);
 /* Hands a batch back: the next moira_format_records reuses its memory (steady streams of batches).  moira_blocks_free
  * releases a batch (may be NULL) and everything that was recycled. */
+/* The same through gzip (--output_compression gz, moira.py:323-370): every part is cut into 65 280-byte pieces, compressed
+ * on n_threads threads (zlib, `level` 1..9) into BGZF members -- gzip members that carry their own size, so that any gunzip
+ * reads the file and moira_gz_inflate / htslib read it in parallel -- and written at `file_offset`. */
+MOIRA_API int moira_blocks_write_gz(const moira_blocks *blocks, int which, int fd, uint64_t file_offset, int level, int n_threads,
+                                    uint64_t *written_out);
 MOIRA_API int moira_blocks_recycle(moira_blocks *blocks);
 MOIRA_API int moira_blocks_free(moira_blocks *blocks);
 
@@ -451,6 +456,25 @@ MOIRA_API int moira_make_contig(moira_ctx *ctx, const char *fwd_aligned, const i
                                 const char *rev_aligned, const int32_t *rev_quals, uint64_t n_rev_quals,
                                 const moira_contig_params *params, char *contig, int32_t *contig_quals,
                                 uint64_t *contig_len, int32_t *overlap, int32_t *gaps, int32_t *mismatches);
+
+/* ---- gzip inputs and outputs on the host threads (moira_gz.cpp) ------------------------------------------------------
+ * Replace gzip.GzipFile(filename).read() behind the reference's magic-byte sniffing (moira.py:1065-1068) and its gzip
+ * output files (moira.py:323-370, --output_compression gz).
+ *
+ * moira_gz_scan: a BGZF file (bgzip / htslib / Illumina FASTQ writers: gzip members of <= 64 KB that carry their own
+ * compressed size) -> the number of members and the exact inflated size; any other file -> 0, 0 (nothing is inflated).
+ * moira_gz_inflate: the whole file -> a buffer owned by the library (*out, *out_bytes; release with moira_gz_free).
+ * BGZF members are inflated in parallel on n_threads threads (<= 0: all), each straight into its place, CRC-32 and size
+ * checked; other gzip files (single member, concatenated plain members, zero padding behind the last) by one thread.
+ * MOIRA_ERR_PARSE: not gzip, truncated, corrupt.
+ * moira_gz_deflate: `bytes` of data -> BGZF members written to fd at file_offset (parallel compression, then pwrite);
+ * moira_gz_eof: the empty member BGZF readers expect at the end of a file (28 bytes). */
+MOIRA_API int moira_gz_scan(const uint8_t *gz, uint64_t gz_bytes, uint64_t *n_members_out, uint64_t *inflated_bytes_out);
+MOIRA_API int moira_gz_inflate(const uint8_t *gz, uint64_t gz_bytes, int n_threads, uint8_t **out, uint64_t *out_bytes);
+MOIRA_API int moira_gz_free(uint8_t *buffer);
+MOIRA_API int moira_gz_deflate(const uint8_t *data, uint64_t bytes, int level, int n_threads, int fd, uint64_t file_offset,
+                               uint64_t *written_out);
+MOIRA_API int moira_gz_eof(int fd, uint64_t file_offset, uint64_t *written_out);
 
 /* ---- multi-GPU: the path's only collective ------------------------------------------------------------
  * Reads shard by contiguous chunk, one context per GPU; nothing but the MOIRA_N_COUNTERS counters (good / bad counts,

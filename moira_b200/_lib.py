@@ -44,6 +44,7 @@ EXPORTS = [
     "moira_blocks_get", "moira_blocks_write", "moira_blocks_recycle", "moira_blocks_free", "moira_fastq_headers", "moira_fastq_split", "moira_line_offsets",
     "moira_comm_unique_id", "moira_comm_init", "moira_comm_init_all", "moira_comm_info", "moira_reduce_counters_device",
     "moira_reduce_counters", "moira_reduce_counters_all", "moira_link_probe",
+    "moira_gz_scan", "moira_gz_inflate", "moira_gz_free", "moira_gz_deflate", "moira_gz_eof", "moira_blocks_write_gz",
     "moira_ctx_last_kernel_ms", "moira_ctx_last_contig_ms", "moira_contig_params_default", "moira_filter_pairs", "moira_nw_align", "moira_make_contig",
 ]
 
@@ -138,6 +139,12 @@ lib.moira_blocks_parts.argtypes = [_vp, ctypes.POINTER(_i)]
 lib.moira_blocks_get.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]
 lib.moira_line_offsets.argtypes = [_vp, _u64, _vp, _u64, _vp, ctypes.POINTER(_u64)]
 lib.moira_blocks_write.argtypes = [_vp, _i, _i, _u64, _i, ctypes.POINTER(_u64)]
+lib.moira_blocks_write_gz.argtypes = [_vp, _i, _i, _u64, _i, _i, ctypes.POINTER(_u64)]
+lib.moira_gz_scan.argtypes = [_vp, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]
+lib.moira_gz_inflate.argtypes = [_vp, _u64, _i, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]
+lib.moira_gz_free.argtypes = [_vp]
+lib.moira_gz_deflate.argtypes = [_vp, _u64, _i, _i, _i, _u64, ctypes.POINTER(_u64)]
+lib.moira_gz_eof.argtypes = [_i, _u64, ctypes.POINTER(_u64)]
 lib.moira_blocks_recycle.argtypes = [_vp]
 lib.moira_blocks_free.argtypes = [_vp]
 lib.moira_fastq_headers.argtypes = [_vp, _u64, _vp, _u64, _i, _vp, _vp]

@@ -5,6 +5,7 @@ the decision).  Everything numeric happens in the CUDA library; this module only
 from __future__ import annotations
 
 import ctypes
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -695,6 +696,47 @@ def collapse_labels(labels, ee) -> CollapseResult:
     return CollapseResult(g_of, rep[:G], size[:G], mstart[:G + 1], members, order[:G])
 
 
+def _gz_owned_array(ptr: int, nbytes: int):
+    """uint8 array over a buffer of moira_gz_inflate; the buffer is released when the last view of it is gone."""
+    if not nbytes:
+        lib.moira_gz_free(ptr)
+        return np.zeros(0, np.uint8)
+    carr = (ctypes.c_uint8 * nbytes).from_address(ptr)
+    weakref.finalize(carr, lib.moira_gz_free, ctypes.c_void_p(ptr))
+    return np.frombuffer(carr, dtype=np.uint8)
+
+
+def gz_scan(gz):
+    """(members, inflated bytes) of a BGZF file -- gzip members that carry their own size: read without inflating --, (0, 0)
+    for any other file."""
+    a = np.frombuffer(gz, dtype=np.uint8) if not isinstance(gz, np.ndarray) else gz
+    n, total = ctypes.c_uint64(), ctypes.c_uint64()
+    L.check(lib.moira_gz_scan(_ptr(a), a.size, ctypes.byref(n), ctypes.byref(total)))
+    return n.value, total.value
+
+
+def gz_inflate(gz, n_threads: int = 0):
+    """gzip.GzipFile(...).read() on the host threads (moira.py:1065-1068): BGZF / blocked gzip members in parallel, any other
+    gzip file on one thread.  Returns a uint8 array over memory the library owns (released with its last view).
+    MoiraError(ERR_PARSE) for files that are not gzip, truncated or corrupt."""
+    a = np.frombuffer(gz, dtype=np.uint8) if not isinstance(gz, np.ndarray) else gz
+    out, nb = ctypes.c_void_p(), ctypes.c_uint64()
+    L.check(lib.moira_gz_inflate(_ptr(a), a.size, int(n_threads), ctypes.byref(out), ctypes.byref(nb)))
+    return _gz_owned_array(out.value, nb.value)
+
+
+def gz_deflate(data, fd: int, offset: int = 0, level: int = 6, n_threads: int = 0, eof: bool = False) -> int:
+    """`data` -> BGZF members at byte `offset` of the open descriptor fd (parallel compression); returns the bytes written."""
+    a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    n = ctypes.c_uint64()
+    L.check(lib.moira_gz_deflate(_ptr(a), a.size, int(level), int(n_threads), int(fd), int(offset), ctypes.byref(n)))
+    total = n.value
+    if eof:
+        L.check(lib.moira_gz_eof(int(fd), int(offset) + total, ctypes.byref(n)))
+        total += n.value
+    return total
+
+
 def fastq_headers(text, seq_off, n_threads: int = 0):
     """(hdr_off uint64[n], hdr_len uint32[n]): header tokens of FASTQ records from their sequence-line positions."""
     buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
@@ -774,6 +816,12 @@ class Blocks:
         """All parts of one block kind to file descriptor fd at byte `offset` (native, parallel); returns the bytes written."""
         n = ctypes.c_uint64()
         L.check(lib.moira_blocks_write(self._h, int(which), int(fd), int(offset), int(n_threads), ctypes.byref(n)))
+        return n.value
+
+    def pwrite_gz(self, which: int, fd: int, offset: int, level: int = 6, n_threads: int = 0) -> int:
+        """The same through gzip: BGZF members compressed on all host threads (moira_blocks_write_gz); returns the bytes written."""
+        n = ctypes.c_uint64()
+        L.check(lib.moira_blocks_write_gz(self._h, int(which), int(fd), int(offset), int(level), int(n_threads), ctypes.byref(n)))
         return n.value
 
     def recycle(self):

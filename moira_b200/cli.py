@@ -208,7 +208,17 @@ def load_text(filename):
     with io.open(filename, mode="rb") as fh:
         start = fh.read(3)
         if start.startswith(b"\x1f\x8b\x08"):
-            data = gzip.GzipFile(filename=filename).read()
+            # moira_gz_inflate: blocked gzip (BGZF: bgzip, Illumina's FASTQ writers) on all host threads, any other gzip
+            # file on one -- straight from the mapped file into memory the library owns
+            from .api import gz_inflate
+            mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            try:
+                text = gz_inflate(np.frombuffer(mm, dtype=np.uint8))
+            except MoiraError as exc:
+                if exc.code != L.ERR_PARSE:
+                    raise
+                raise IOError("%s: %s" % (filename, exc.message)) from None
+            return text, text
         elif start.startswith(b"\x42\x5a\x68"):
             data = bz2.BZ2File(filename).read()
         else:
@@ -481,11 +491,13 @@ def _addr(buf) -> int:
 class Writers:
     """The output files of write_results (moira.py:323-370), opened in binary mode: the native writer hands over bytes.
     Uncompressed files are written by moira_blocks_write (parallel pwrite at offsets kept here) on a writer thread, one
-    batch of blocks behind the formatter; gz / bz2 files go through Python's compressors."""
+    batch of blocks behind the formatter; gz files the same way through moira_blocks_write_gz (BGZF members compressed on
+    all host threads: any gunzip reads them); bz2 files go through Python's compressor."""
 
     def __init__(self, args, output_name):
-        self.native = args.output_compression == "none"
-        opener, suffix = {"none": (open, ""), "gz": (gzip.open, ".gz"), "bz2": (bz2.open, ".bz2")}[args.output_compression]
+        self.native = args.output_compression in ("none", "gz")
+        self.gz = args.output_compression == "gz"       # BGZF members compressed on all host threads (moira_blocks_write_gz)
+        opener, suffix = {"none": (open, ""), "gz": (open, ".gz"), "bz2": (bz2.open, ".bz2")}[args.output_compression]
         self.files, self.names, self.by_block, self.pos = [], [], {}, {}
         self.seconds = 0.0
 
@@ -510,10 +522,14 @@ class Writers:
             op("%s.contigs.report" % output_name, L.BLOCK_REPORT)
             head = b"header\tn_seqs\toverlap_length\tgaps\tmismatches\n"
             fh = self.by_block[L.BLOCK_REPORT]
-            fh.write(head)
-            if self.native:
-                fh.flush()
-                self.pos[L.BLOCK_REPORT] = len(head)
+            if self.gz:
+                from .api import gz_deflate
+                self.pos[L.BLOCK_REPORT] = gz_deflate(head, fh.fileno(), 0)
+            else:
+                fh.write(head)
+                if self.native:
+                    fh.flush()
+                    self.pos[L.BLOCK_REPORT] = len(head)
         self._pool = ThreadPoolExecutor(1)
         self._pending = None
 
@@ -521,7 +537,9 @@ class Writers:
         t0 = time.time()
         try:
             for which, fh in self.by_block.items():
-                if self.native:
+                if self.gz:
+                    self.pos[which] += blocks.pwrite_gz(which, fh.fileno(), self.pos[which])
+                elif self.native:
                     self.pos[which] += blocks.pwrite(which, fh.fileno(), self.pos[which])
                 else:
                     blocks.write(which, fh)
@@ -545,6 +563,11 @@ class Writers:
         finally:
             self._pool.shutdown(wait=True)
             L.lib.moira_blocks_free(None)       # the recycled batches
+            if self.gz:                         # the empty member that ends a BGZF file (an empty output is a valid gzip file too)
+                import ctypes
+                n = ctypes.c_uint64()
+                for which, fh in self.by_block.items():
+                    L.lib.moira_gz_eof(fh.fileno(), self.pos[which], ctypes.byref(n))
             for fh in self.files:
                 fh.close()
 

@@ -228,6 +228,9 @@ int comm_reduce_host(CommState *s, uint64_t *counters);
 int comm_reduce_all(CommState **states, int n, uint64_t *const *counters);
 int comm_info(const CommState *s, int *rank, int *n_ranks);
 
+// BGZF members of `n` bytes written to fd at file_offset (moira_gz.cpp)
+int gz_deflate_to_fd(const uint8_t *in, uint64_t n, int level, int n_threads, int fd, uint64_t file_offset, uint64_t *written_out);
+
 // sets the thread-local message returned by moira_last_error() and returns `code`
 int fail(int code, const char *fmt, ...);
 

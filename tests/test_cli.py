@@ -68,10 +68,14 @@ def test_fastq_text_loading_and_record_aligned_shards(tmp_path, forward_records)
     import numpy as np
     import moira_b200
     raw = gzip.open(os.path.join(GOLDEN, "test1.fastq.gz"), "rb").read()
-    plain, gz = tmp_path / "a.fastq", tmp_path / "b.fastq.gz"
+    plain, gz, bgzf = tmp_path / "a.fastq", tmp_path / "b.fastq.gz", tmp_path / "c.fastq.gz"
     plain.write_bytes(raw)
     gz.write_bytes(gzip.compress(raw))
-    for path in (plain, gz):
+    fd = os.open(str(bgzf), os.O_CREAT | os.O_WRONLY, 0o644)             # blocked gzip (bgzip / Illumina writers): inflated in parallel
+    moira_b200.gz_deflate(raw, fd, eof=True)
+    os.close(fd)
+    assert moira_b200.gz_scan(bgzf.read_bytes())[0] > 1 and gzip.open(str(bgzf), "rb").read() == raw
+    for path in (plain, gz, bgzf):
         text, _keep = cli.load_text(str(path))
         assert text.tobytes() == raw
     for parts in (1, 2, 3, 7, 8):
@@ -118,6 +122,17 @@ def test_compression_and_formats(tmp_path):
         pre = str(tmp_path / comp)
         assert cli.run(["-ffq", src, "-op", pre, "-oc", comp, "--silent"]) == 0
         assert opener("%s.qc.good.fasta.%s" % (pre, comp), "rt").read() == plain
+    # blocked gzip in (inflated on all host threads), and the gz outputs above are blocked gzip themselves: one as the next input
+    import moira_b200
+    bg = str(tmp_path / "in.bgzf.gz")
+    fd = os.open(bg, os.O_CREAT | os.O_WRONLY, 0o644)
+    moira_b200.gz_deflate(gzip.open(src, "rb").read(), fd, eof=True)
+    os.close(fd)
+    pre = str(tmp_path / "frombgzf")
+    assert cli.run(["-ffq", bg, "-op", pre, "--silent"]) == 0
+    assert open(pre + ".qc.good.fasta").read() == plain
+    names_gz = open(str(tmp_path / "gz") + ".qc.good.names.gz", "rb").read()
+    assert moira_b200.gz_scan(names_gz)[0] >= 1 and moira_b200.gz_inflate(names_gz).tobytes() == open(base + ".qc.good.names", "rb").read()
     # no collapse, fastq output, USEARCH headers, maxerrors mode, truncation
     pre = str(tmp_path / "nc")
     assert cli.run(["-ffq", src, "-op", pre, "-c", "False", "-o", "fastq", "-pi", "USEARCH", "-me", "2", "-t", "200",
