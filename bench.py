@@ -266,7 +266,7 @@ def cli_bench(rec, accepted_per_read, world, rank, args):
             gzp = os.path.join(tmp, "in.bgzf.fastq.gz")
             fd = os.open(gzp, os.O_CREAT | os.O_WRONLY, 0o644)
             t0 = time.perf_counter()
-            gz_bytes = gz_deflate(rec.reshape(-1), fd, 0, 6, 0, eof=True)
+            gz_bytes = gz_deflate(rec.reshape(-1), fd, 0, 1, 0, eof=True)     # level 1: this only prepares the input
             t_def = time.perf_counter() - t0
             os.close(fd)
             m_plain = min(m, 2_000_000)
@@ -276,7 +276,7 @@ def cli_bench(rec, accepted_per_read, world, rank, args):
                 fh.write(zc.compress(rec[:m_plain].tobytes()))
                 fh.write(zc.flush())
             comp = {"bgzf_input_bytes": int(gz_bytes), "bgzf_written_in_seconds": t_def,
-                    "bgzf_deflate_gb_per_s": rec.nbytes / t_def / 1e9}
+                    "bgzf_deflate_level1_gb_per_s": rec.nbytes / t_def / 1e9}
             for tag, pth, mm_, extra in (("bgzf_in", gzp, m, []), ("plain_gzip_in", plain_p, m_plain, []),
                                          ("bgzf_in_gz_out", gzp, m, ["-oc", "gz"])):
                 t0 = time.perf_counter()

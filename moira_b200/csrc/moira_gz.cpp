@@ -207,13 +207,19 @@ bool deflate_range(z_stream &zs, z_stream &z0, bool &z0_ready, const uint8_t *in
 
 namespace moira {
 
-int gz_deflate_to_fd(const uint8_t *in, uint64_t n, int level, int n_threads, int fd, uint64_t file_offset, uint64_t *written_out)
+int gz_deflate_segments_to_fd(const std::vector<std::pair<const uint8_t *, uint64_t>> &segs, int level, int n_threads, int fd,
+                              uint64_t file_offset, uint64_t *written_out)
 {
     *written_out = 0;
-    if (!n) return MOIRA_OK;
     if (level < 0 || level > 9) level = 6;
-    constexpr uint64_t RANGE = 64ull * BGZF_PIECE;          // 4 MB of input per task
-    const uint64_t n_ranges = (n + RANGE - 1) / RANGE;
+    // tasks of at most 4 MB of input, never across a segment boundary (a member holds bytes of one segment only); the
+    // threads share the tasks of ALL segments
+    constexpr uint64_t RANGE = 64ull * BGZF_PIECE;
+    std::vector<std::pair<const uint8_t *, uint64_t>> tasks;
+    for (const auto &sg : segs)
+        for (uint64_t a = 0; a < sg.second; a += RANGE) tasks.emplace_back(sg.first + a, std::min<uint64_t>(RANGE, sg.second - a));
+    const uint64_t n_ranges = tasks.size();
+    if (!n_ranges) return MOIRA_OK;
     std::vector<std::string> parts(n_ranges);
     std::atomic<uint64_t> next{0};
     std::atomic<int> bad{0};
@@ -227,9 +233,8 @@ int gz_deflate_to_fd(const uint8_t *in, uint64_t n, int level, int n_threads, in
         for (;;) {
             const uint64_t r = next.fetch_add(1);
             if (r >= n_ranges || bad) break;
-            const uint64_t a = r * RANGE, len = std::min<uint64_t>(RANGE, n - a);
-            parts[r].reserve((size_t)(len / 3));
-            if (!deflate_range(zs, z0, z0_ready, in + a, len, parts[r])) { bad = 1; break; }
+            parts[r].reserve((size_t)(tasks[r].second / 3));
+            if (!deflate_range(zs, z0, z0_ready, tasks[r].first, tasks[r].second, parts[r])) { bad = 1; break; }
         }
         deflateEnd(&zs);
         if (z0_ready) deflateEnd(&z0);
@@ -258,6 +263,13 @@ int gz_deflate_to_fd(const uint8_t *in, uint64_t n, int level, int n_threads, in
     if (err) return fail(MOIRA_ERR_BAD_ARG, "pwrite failed: %s", strerror(err.load()));
     *written_out = at[n_ranges] - file_offset;
     return MOIRA_OK;
+}
+
+int gz_deflate_to_fd(const uint8_t *in, uint64_t n, int level, int n_threads, int fd, uint64_t file_offset, uint64_t *written_out)
+{
+    std::vector<std::pair<const uint8_t *, uint64_t>> segs;
+    if (n) segs.emplace_back(in, n);
+    return gz_deflate_segments_to_fd(segs, level, n_threads, fd, file_offset, written_out);
 }
 
 }  // namespace moira

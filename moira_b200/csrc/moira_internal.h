@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <functional>
+#include <utility>
+#include <vector>
 
 #include "../../include/moira_b200.h"
 
@@ -230,6 +232,9 @@ int comm_info(const CommState *s, int *rank, int *n_ranks);
 
 // BGZF members of `n` bytes written to fd at file_offset (moira_gz.cpp)
 int gz_deflate_to_fd(const uint8_t *in, uint64_t n, int level, int n_threads, int fd, uint64_t file_offset, uint64_t *written_out);
+// the same for several pieces of memory in output order; the threads share the work of all of them
+int gz_deflate_segments_to_fd(const std::vector<std::pair<const uint8_t *, uint64_t>> &segs, int level, int n_threads, int fd,
+                              uint64_t file_offset, uint64_t *written_out);
 
 // sets the thread-local message returned by moira_last_error() and returns `code`
 int fail(int code, const char *fmt, ...);

@@ -137,10 +137,10 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
     return v;
 }
 
-__device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
+__device__ __forceinline__ float lds_f32(uint32_t addr)
 {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
 
@@ -447,9 +447,9 @@ __device__ __forceinline__ void sweep_word(uint32_t wi, uint32_t lut_lane, T (&P
         } else if (MODE == 1) {
             P[0] = __dadd_rn(P[0], lds_f64(addr));     // moira.py:1663, in index order
         } else {
-            const float2 t = lds_f32x2(addr);          // classifier: mean and variance of the error count (fp32: an estimate)
-            P[0] += t.x;
-            P[1] += t.y;
+            const float pv = lds_f32(addr);            // classifier: sum p and sum p^2 (fp32: an estimate) -> mean, variance = sum p - sum p^2
+            P[0] += pv;
+            P[1] = __fmaf_rn(pv, pv, P[1]);
         }
     }
 }
@@ -556,12 +556,10 @@ __device__ __forceinline__ TprCtx tpr_setup(const FilterArgs &a, uint8_t *smem)
     } else if (MODE == 0) {
         double2 *t = reinterpret_cast<double2 *>(lut_ptr);
         for (int i = threadIdx.x; i < 256 * 16; i += TPR_THREADS) t[i] = make_double2(a.lut_q[i >> 4], a.lut_e[i >> 4]);
-    } else {   // classifier: (p, p (1 - p)) in fp32, 32 replicas of 8 bytes like the p-only table
-        float2 *t = reinterpret_cast<float2 *>(lut_ptr);
-        for (int i = threadIdx.x; i < 256 * 32; i += TPR_THREADS) {
-            const double pv = a.lut_p[i >> 5];
-            t[i] = make_float2((float)pv, (float)(pv * (1.0 - pv)));
-        }
+    } else {   // classifier: p in fp32, 64 replicas of 4 bytes per row: lane l reads bank l whatever the quality (LDS.32, one
+               // wavefront per warp lookup -- with (p, p (1 - p)) pairs the pass was bound by the shared-memory pipe)
+        float *t = reinterpret_cast<float *>(lut_ptr);
+        for (int i = threadIdx.x; i < 256 * 64; i += TPR_THREADS) t[i] = (float)a.lut_p[i >> 6];
     }
     for (int i = threadIdx.x; i < 16 + MOIRA_N_HIST; i += TPR_THREADS) s_cnt[i] = 0;
     const uint32_t bar0 = bar_addr + warp * 16;
@@ -576,7 +574,7 @@ __device__ __forceinline__ TprCtx tpr_setup(const FilterArgs &a, uint8_t *smem)
     __syncthreads();
 
     TprCtx c;
-    c.lut_lane = lut + ((PL || MODE == 2) ? lane * 8 : (lane & 15) * 16);
+    c.lut_lane = lut + (MODE == 2 ? lane * 4 : PL ? lane * 8 : (lane & 15) * 16);
     c.stage_warp = (uint32_t)warp < n_below ? below0 + warp * 2 * STG : above + (warp - n_below) * 2 * STG;
     c.bar0 = bar0;
     c.s_cnt = s_cnt;
@@ -772,19 +770,39 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
             // Upper quantile of the error count by Cornish-Fisher with the Poisson skew bound:
             // j* <~ mu + z*sigma + (z^2-1)/6; K = j* + 1 plus margin (zc holds the constants).
             // An under-estimate only costs one more rung; the result is never affected.
-            double kn = (double)P[0] + a.z * sqrt((double)P[1]) + a.zc + 1e-4 * (double)P[0];   // fp32 sums: relative error << 1e-4
+            const double var = (double)P[0] > (double)P[1] ? (double)P[0] - (double)P[1] : 0.0;   // sum p (1 - p)
+            double kn = (double)P[0] + a.z * sqrt(var) + a.zc + 1e-4 * (double)P[0];   // fp32 sums: relative error << 1e-4
+            bool hopeless = false;
             if (!a.exact) {   // a decision needs at most floor(cutoff on the raw statistic) + 2 entries
                 double c = (a.thr_kind == MOIRA_THR_MAXERRORS) ? a.thr : __dmul_rn((double)g.eff, a.thr);
                 if (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) c -= (double)ns;
                 const double kd = floor(c) + 2.0;
                 if (kd < kn) kn = kd;
+                // Certain rejects without any FP64 sweep.  X = number of errors is a sum of independent Bernoulli(p_i) with mean
+                // mu, so for 0 < t < mu the Chernoff bound gives  P(X <= t) <= exp(t - mu + t ln(mu / t))  (t = 0: exp(-mu)).
+                // With t = kd - 1: if that is below 1 - alpha, then acc[kd - 1] <= 1 - alpha, j* >= kd and the statistic is at
+                // least kd - 1 = floor(c) + 1 > c -- the read is rejected whatever its exact value, and it is written here as the
+                // kd-entry sweep would write it (lower bound kd - 1, MOIRA_FLAG_LOWER_BOUND).  mu_lo is a rigorous lower bound of
+                // mu from the fp32 sum: (eff + 2) roundings of at most 2^-24 each, doubled; the 1e-9 margin covers the rounding
+                // of the reference's own double sums (<= L 2^-52 relative) by orders of magnitude.
+                const double t = kd - 1.0;
+                const double mu_lo = (double)P[0] * (1.0 - ((double)g.eff + 2.0) * 1.2e-7);
+                if (kd >= 1.0 && kd <= 1.0e6 && mu_lo > t) {
+                    const double bound = t > 0.0 ? exp(t - mu_lo + t * log(mu_lo / t)) : exp(-mu_lo);
+                    hopeless = bound < a.oma - 1e-9;
+                    res.ee_raw = t;
+                }
             }
             const int kneed = kn > 1.0e6 ? 1000000 : (kn < 2.0 ? 2 : (int)kn);
             if (a.rung < 0) {   // classifier run as the first pass (classify-first): every read is handed on
                 const unsigned vm = __ballot_sync(FULL, valid);
                 if (vm && lane == 0) atomicAdd(&s_cnt[MOIRA_CNT_CLASSIFIED], (uint32_t)__popc(vm));
             }
-            push_read(a, valid, pick_rung(a, kneed), r_local, lane);
+            if (!a.exact && __any_sync(FULL, valid && hopeless)) {
+                res.resolved = false;
+                finish_read(a, valid && hopeless, r_local, g, res, s_cnt, s_hist, lane);
+            }
+            push_read(a, valid && !hopeless, pick_rung(a, kneed), r_local, lane);
             tile = next_tile;
             valid = nvalid; r_local = nr_local; g = ng;
             maxeff = __reduce_max_sync(FULL, g.eff);

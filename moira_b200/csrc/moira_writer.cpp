@@ -255,16 +255,12 @@ int moira_blocks_write(const moira_blocks *b, int which, int fd, uint64_t file_o
 int moira_blocks_write_gz(const moira_blocks *b, int which, int fd, uint64_t file_offset, int level, int n_threads, uint64_t *written_out)
 {
     if (!b || !written_out || which < 0 || which >= MOIRA_BLOCK_N || fd < 0) return moira::fail(MOIRA_ERR_BAD_ARG, "bad argument");
-    uint64_t at = file_offset;
-    for (int p = 0; p < b->n_parts; p++) {   // parts in output order; the threads share every part's pieces
+    std::vector<std::pair<const uint8_t *, uint64_t>> segs;   // parts in output order; the threads share the pieces of all of them
+    for (int p = 0; p < b->n_parts; p++) {
         const std::string &s = b->buf[(size_t)p * MOIRA_BLOCK_N + which];
-        uint64_t w = 0;
-        const int rc = moira::gz_deflate_to_fd(reinterpret_cast<const uint8_t *>(s.data()), s.size(), level, n_threads, fd, at, &w);
-        if (rc) return rc;
-        at += w;
+        if (!s.empty()) segs.emplace_back(reinterpret_cast<const uint8_t *>(s.data()), s.size());
     }
-    *written_out = at - file_offset;
-    return MOIRA_OK;
+    return moira::gz_deflate_segments_to_fd(segs, level, n_threads, fd, file_offset, written_out);
 }
 
 // Hand a batch back for reuse by the next moira_format_records (at most a few are kept; the rest are freed).
