@@ -229,7 +229,10 @@ def cli_bench(rec, accepted_per_read, world, rank, args):
         path = os.path.join(tmp, "in.fastq")
         with open(path, "wb") as fh:
             fh.write(rec)
-        devs = ",".join(str(i) for i in range(world))
+        # the ranks' GPUs by number; when that is every GPU of the box, "all" -- the CLI then takes as many as the input can keep
+        # busy (one per 2 GiB of text: contexts cost more than they save on a file this size)
+        import torch
+        devs = "all" if world > 1 and world == torch.cuda.device_count() else ",".join(str(i) for i in range(world))
         for tag, extra in (("collapse_default", []), ("no_collapse_fastq", ["-c", "False", "-o", "fastq"])):
             dt = None
             for _rep in range(2):      # the faster of two runs: page-cache and driver effects (mmap faults, cudaFree) vary by seconds
@@ -240,7 +243,9 @@ def cli_bench(rec, accepted_per_read, world, rank, args):
                 if dt is None or dt_r < dt:
                     dt, rc, log = dt_r, rc_r, log_r
             files = {f: os.path.getsize(os.path.join(tmp, f)) for f in sorted(os.listdir(tmp)) if f.startswith(tag + ".")}
+            used = log.getvalue().split(" s to the decisions, ")[1].split(" GPU")[0] if " s to the decisions, " in log.getvalue() else None
             res = {"value": m / dt, "seconds": dt, "rc": rc, "runs": 2, "output_bytes": int(sum(files.values())),
+                   "devices_asked": devs, "devices_used": int(used) if used else None,
                    "decisions_seconds": float(log.getvalue().split(" s to the decisions")[0].rsplit("(", 1)[1]) if " s to the decisions" in log.getvalue() else None}
             if tag == "no_collapse_fastq":
                 with open(os.path.join(tmp, tag + ".qc.good.fastq"), "rb") as fh:

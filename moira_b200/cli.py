@@ -93,7 +93,8 @@ def parse_arguments(argv=None):
     general.add_argument("--device", type=int, default=0, help="CUDA device index (B200 path only).")
     general.add_argument("--devices", type=str, default=None,
                          help="'all' or a comma-separated list of CUDA devices: reads are sharded by contiguous chunk, one context "
-                              "and one host thread per GPU (the B200 counterpart of --processors); overrides --device.")
+                              "and one host thread per GPU (the B200 counterpart of --processors); overrides --device.  'all' takes "
+                              "one GPU per 2 GiB of input text, at most every GPU of the box; a list is taken as given.")
     constructor = parser.add_argument_group("Contig construction options")     # moira.py:629-646
     constructor.add_argument("-m", "--match", type=int, default=1)
     constructor.add_argument("-x", "--mismatch", type=int, default=-1)
@@ -582,7 +583,19 @@ def resolve_devices(args):
         import ctypes
         n = ctypes.c_int()
         L.check(L.lib.moira_device_count(ctypes.byref(n)))
-        return list(range(max(1, n.value)))
+        # "all" = as many of the GPUs as the input can keep busy: a context costs 0.3 s to create and tear down and the run
+        # is output-bound beyond a few GB of text per GPU (measured: 10 M reads take 2.6 s on one B200, 5.1 s on eight), so one
+        # GPU per 2 GiB of (inflated) input text; an explicit list is taken as given
+        per_gpu = int(os.environ.get("MOIRA_B200_CLI_BYTES_PER_GPU", str(2 << 30)))
+        total = 0
+        for name in (args.forward_fastq, args.reverse_fastq, args.forward_fasta, args.forward_qual, args.reverse_fasta, args.reverse_qual):
+            if name and os.path.exists(name):
+                size = os.path.getsize(name)
+                with io.open(name, "rb") as fh:
+                    magic = fh.read(3)
+                total += size * (4 if magic.startswith(b"\x1f\x8b\x08") or magic.startswith(b"\x42\x5a\x68") else 1)
+        want = max(1, -(-total // max(1, per_gpu)))
+        return list(range(max(1, min(n.value, want))))
     return [int(x) for x in spec.split(",") if x != ""]
 
 
