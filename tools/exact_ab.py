@@ -26,7 +26,7 @@ for w in work:
     min_len = fixed or int(lens.min().item())
     out = [profile, "n=%d" % n]
     for exact in (False, True):
-        p = FilterParams(exact_ee=exact, max_length=max_len, min_length=min_len)
+        p = FilterParams(exact_ee=exact, max_length=max_len, min_length=min_len, uncert=float(os.environ.get("AB_UNCERT", "0.01")))
         best = 1e9
         for rep in range(4):
             cnt = torch.zeros(L.N_COUNTERS, dtype=torch.int64, device=dev)
