@@ -169,6 +169,8 @@ struct moira_ctx {
     int classify_first_k = 9;          // exact mode, first-pass K at least this: the classifier runs first and the ladder does all sweeps
     int classify_first_dec_k = 9;      // the same in decision mode
     int classify_first_sorted_k = 9;   // the same for length-bucketed (ragged) batches
+    int sorted_cascade = 1;            // length-bucketed first pass in decision mode (K = 5..8): capped buckets + Newton bound + rungs, by pilot
+    int sorted_cascade_cap = 4;
     int exact_sorted_k_cap = 4;        // length-bucketed first pass in exact mode: at most this many entries (0: the decision's K);
                                        // measured on C5 (100..600 bp): 4 -> 4.56 ms, 5 -> 4.68, 6 -> 4.88, none (3..8) -> 5.08, 3 -> 5.24
     int direct_rung = 1;   // the first pass picks the ladder rung of the reads it hands on (0: every one goes through the classifier)
@@ -461,15 +463,20 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
     // (exact mode).  Whether that pays depends on the data: a pilot launch over the first tiles measures the escalated
     // fraction on the device, and the two candidate launches for the rest read that verdict (no host synchronisation).
     const bool cascade_ok = p->mode == MOIRA_MODE_PB && k_decides_all && k_first >= 3 && k_first <= 8 && p->cascade != 2 && c->cascade && !cf_plain;
-    const bool queues_needed = ladder || cascade_ok;
+    // Length-bucketed (ragged) batches whose decisions need 5 .. 8 entries: the same idea per bucket -- at most four entries
+    // first, the Newton bound at every read's own K, the rest to the rung that holds that K -- if a pilot over the first reads
+    // (sorted and swept the same way) hands on few enough.
+    const bool sc_possible = p->mode == MOIRA_MODE_PB && !p->exact_ee && k_decides_all && k_first >= 5 && k_first <= 8 && p->cascade != 2 &&
+                             c->cascade && c->sorted_cascade && d_lengths && c->length_sort && !cf_sorted;
+    const bool queues_needed = ladder || cascade_ok || sc_possible;
     if (cascade_ok) a.min_rung = 1;   // what a two-entry sweep hands on may need as few as three entries
 
-    const uint64_t sub = ladder ? SUB_BATCH : cascade_ok ? (1ull << 26) : (1ull << 31);
+    const uint64_t sub = ladder ? SUB_BATCH : (cascade_ok || sc_possible) ? (1ull << 26) : (1ull << 31);
     for (uint64_t start = 0; start < n_reads; start += sub) {
         const uint32_t n = (uint32_t)std::min<uint64_t>(sub, n_reads - start);
         a.base = start; a.n = n; a.queue = nullptr; a.queue_count = nullptr; a.rung = -1;
         if (queues_needed) {
-            int rc = ensure_ws(ws, (uint32_t)std::min<uint64_t>(n_reads, sub), ladder ? NB : 1);
+            int rc = ensure_ws(ws, (uint32_t)std::min<uint64_t>(n_reads, sub), ladder ? NB : sc_possible ? 9 : 1);   // rung_cap(8) == 12
             if (rc) return rc;
             a.queues = ws.queues; a.queue_counts = ws.counts; a.queue_cap = ws.cap;
             CU(cudaMemsetAsync(ws.counts, 0, (NB + 4 + 16) * sizeof(uint32_t), stream));
@@ -497,8 +504,12 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
             CU(cudaMemsetAsync(lb.hist, 0, LEN_BUCKETS * sizeof(uint32_t), stream));
             const int single = p->mode != MOIRA_MODE_PB;
             a.first_k_cap = (ladder && p->exact_ee && a.allow_push) ? c->exact_sorted_k_cap : 0;
-            if (launch_length_sort(a, lb, single || cf_sorted, cfg)) return fail(MOIRA_ERR_CUDA, "length-sort launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            c->launches += 3;
+            // decisions that need 5 .. 8 entries: capped buckets by pilot (below); sorts its own ranges
+            const bool sc = sc_possible && !single && !cf_sorted && (p->cascade == 1 || n >= 16u * 2u * (uint32_t)c->sm_count * 16u * 32u);
+            if (!sc) {
+                if (launch_length_sort(a, lb, single || cf_sorted, cfg)) return fail(MOIRA_ERR_CUDA, "length-sort launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                c->launches += 3;
+            }
             a.queue = lb.queue;
             a.min_rung = 1;
             if (single) {
@@ -514,6 +525,32 @@ int run_filter_full(moira_ctx *c, Workspace &ws, const uint8_t *d_slab, const ui
                 a.queue_count = lb.group_count;
                 rc = launch_classify_first(a, cfg);
                 name = "classifier over the length-sorted reads + ladder";
+            } else if (sc) {
+                const uint32_t pilot_n = 2u * (uint32_t)c->sm_count * 16u * 32u;
+                uint32_t *policy = ws.counts + NB;
+                FilterArgs as = a;
+                as.allow_push = 1;
+                as.first_k_cap = c->sorted_cascade_cap;
+                if (p->cascade != 1) {
+                    // pilot: the first reads of the sub-batch (slab order: a fair sample of the lengths), bucketed and swept with the cap
+                    as.queue = nullptr; as.n = pilot_n;
+                    if (launch_length_sort(as, lb, 0, cfg)) return fail(MOIRA_ERR_CUDA, "length-sort launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    as.queue = lb.queue;
+                    rc = launch_sorted_first(as, lb.group_start, lb.group_count, cfg);
+                    if (rc >= 0 && launch_policy_sorted(ws.counts, (uint32_t)(pilot_n * 0.20), policy, stream)) rc = -1;
+                    CU(cudaMemsetAsync(lb.hist, 0, LEN_BUCKETS * sizeof(uint32_t), stream));
+                    as.cap_policy = policy; as.first_read = pilot_n;
+                    c->launches += 6;
+                }
+                as.queue = nullptr; as.n = n;
+                if (rc >= 0 && launch_length_sort(as, lb, 0, cfg)) return fail(MOIRA_ERR_CUDA, "length-sort launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                as.queue = lb.queue;
+                if (rc >= 0) rc = launch_sorted_first(as, lb.group_start, lb.group_count, cfg);
+                // what the capped buckets handed on: one more sweep each, with the entries the read's own decision needs
+                as.queue = nullptr; as.first_read = 0; as.cap_policy = nullptr;
+                if (rc >= 0 && launch_ladder_tpr(as, cfg)) rc = -1;
+                name = "pb_tpr<K per length bucket, at most 4 first>";
+                c->launches += 3 + 1 + 2;
             } else {
                 rc = launch_sorted_first(a, lb.group_start, lb.group_count, cfg);
                 name = "pb_tpr<K per length bucket>";
@@ -680,6 +717,8 @@ static int ctx_init(moira_ctx *c, int device, int sm_count)
     if (const char *e = getenv("MOIRA_B200_CLASSIFY_FIRST_K")) c->classify_first_k = atoi(e);   // tuning (1000: never)
     if (const char *e = getenv("MOIRA_B200_CLASSIFY_FIRST_DEC_K")) c->classify_first_dec_k = atoi(e);   // tuning
     if (const char *e = getenv("MOIRA_B200_CLASSIFY_FIRST_SORTED_K")) c->classify_first_sorted_k = atoi(e);   // tuning
+    if (const char *e = getenv("MOIRA_B200_NO_SORTED_CASCADE")) c->sorted_cascade = (e[0] == '1') ? 0 : 1;   // diagnostics
+    if (const char *e = getenv("MOIRA_B200_SORTED_CASCADE_CAP")) c->sorted_cascade_cap = atoi(e);   // tuning
     if (const char *e = getenv("MOIRA_B200_EXACT_SORTED_KCAP")) c->exact_sorted_k_cap = atoi(e);   // tuning
     if (const char *e = getenv("MOIRA_B200_NO_TMA")) c->use_tma = (e[0] == '1') ? 0 : 1;   // diagnostics: force the cp.async staging
     if (kernels_init(c->sm_count)) return fail(MOIRA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -72,7 +72,9 @@ struct FilterArgs {
     // decision needs; reads it cannot settle exactly are rejected when the Newton bound on acc[k_dec - 1] allows it
     // and pushed to queue 0 otherwise.  0: off.
     int32_t k_dec;
-    int32_t first_k_cap;         // length-bucketed first pass, exact mode: no bucket is swept with more entries than this (0: no cap)
+    int32_t first_k_cap;         // length-bucketed first pass: no bucket is swept with more entries than this (0: no cap)
+    const uint32_t *cap_policy;  // not null: the cap applies only if *cap_policy == 1 (verdict of the sorted pilot, decision mode)
+    uint32_t first_read;         // length sort: reads [first_read, n) of the sub-batch (the reads before belong to the pilot)
     uint32_t tile0;              // first pass: the launch starts at this warp tile (the tiles before belong to the pilot launch)
     uint32_t *jhist;             // not null (second pilot launch of the cascade): 16 bins of floor(ee) of this launch's reads
     const uint32_t *policy;      // not null: the launch runs only if *policy == policy_want (set on the device by the pilot)
@@ -135,6 +137,8 @@ int launch_policy(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *po
 constexpr uint32_t MOIRA_POLICY_UNDECIDED = 0xFFu;
 int launch_policy_first(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s);
 int launch_policy_second(const uint32_t *jhist, int k_first, int exact, uint32_t *policy, cudaStream_t s);
+// length-bucketed first pass with capped K (decision mode): 1 = few of the pilot's reads were handed on, keep the cap; 0 = drop it
+int launch_policy_sorted(const uint32_t *queue_counts, uint32_t max_pushed, uint32_t *policy, cudaStream_t s);
 int launch_fp64_peak(int iters, int sm_count, double *d_sink, cudaStream_t s, double *ops_out);
 int kernels_init(int sm_count);  // sets function attributes (dynamic smem opt-in)
 int max_first_pass_k();

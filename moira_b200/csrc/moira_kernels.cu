@@ -587,7 +587,10 @@ __device__ __forceinline__ TprCtx tpr_setup(const FilterArgs &a, uint8_t *smem)
 // The persistent tile loop of one warp: tiles first_tile, first_tile + tile_step, ... of `count` reads
 // (taken through `queue` when it is not null), K PMF entries per read.  All staging state is local, so
 // a CTA may call this several times with different K (ladder kernel).
-template <int K, int MODE, bool PL, bool TMA, int ROLL = 0>
+// PERREAD (length-bucketed first pass): the decision's K is taken per read, floor(cutoff_r) + 2, instead of FilterArgs::k_dec --
+// a bucket may be swept with fewer entries than its reads' decisions need (first_k_cap); what those entries cannot settle
+// is rejected by the Newton bound at the read's own K or pushed to the rung that holds it.
+template <int K, int MODE, bool PL, bool TMA, int ROLL = 0, bool PERREAD = false>
 __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap *tmap_ptr, const TprCtx &ctx,
                                           const uint32_t *queue, uint32_t count, uint32_t first_tile, uint32_t total_warps)
 {
@@ -607,6 +610,13 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
     // Ns / has-N of every row given with the slab (produced by whoever wrote it): the sweep counts nothing
     const bool marks_given = a.row_marks != nullptr;
     uint32_t vec_steps = 0;   // 16-base vector steps this warp swept with the FP64 recurrence (warp-uniform)
+    // entries the decision on one read needs: floor(cutoff on the raw statistic) + 2, at least this sweep's K
+    auto kd_of = [&](uint32_t eff, uint32_t n_marks) -> int {
+        double c = (a.thr_kind == MOIRA_THR_MAXERRORS) ? a.thr : __dmul_rn((double)eff, a.thr);
+        if (a.ambigs == MOIRA_AMBIGS_TREAT_AS_ERRORS) c -= (double)n_marks;
+        const double kd = floor(c) + 2.0;
+        return kd > (double)K ? (kd > 1.0e6 ? 1000000 : (int)kd) : K;
+    };
     auto tile_read = [&](uint32_t t, bool &valid, uint32_t &r_local, ReadGeom &g) {
         uint32_t i = t * 32 + lane;
         valid = t < n_tiles && i < count;
@@ -743,7 +753,14 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
                 bool certain = valid && tracked < a.oma - 1e-9;
                 const bool finished = !valid || processed >= g.eff;
                 bool all_certain = __all_sync(FULL, certain || finished) && __any_sync(FULL, certain);
-                if (K >= 2 && a.k_dec > K && all_certain) {
+                if constexpr (PERREAD) {
+                    if (K >= 2 && all_certain && !a.exact && a.first_k_cap) {
+                        // the read's own K without its N/n (not all counted yet): at least the K of the epilogue, so the test is on the safe side
+                        const int kdl = kd_of(g.eff, 0u);
+                        if (kdl > K) certain = valid && kdl <= 8 && cascade_bound<K>(P, kdl) < a.oma - 1e-9;
+                        all_certain = __all_sync(FULL, certain || finished) && __any_sync(FULL, certain);
+                    }
+                } else if (K >= 2 && a.k_dec > K && all_certain) {
                     // a cascade launch stops only where the reject is certain at the decision's k_dec (the bound is at
                     // least the tracked mass, so the test above is a cheap necessary condition)
                     certain = valid && cascade_bound<K>(P, a.k_dec) < a.oma - 1e-9;
@@ -811,13 +828,18 @@ __device__ __forceinline__ void tpr_tiles(const FilterArgs &a, const CUtensorMap
         } else {
         if constexpr (MODE == 0) {
             res.resolved = cdf_quantile<K>(P, a.oma, res.ee_raw);
-            const int kd = (K >= 2 && a.k_dec > K) ? a.k_dec : K;
+            const int kd = PERREAD ? ((K >= 2 && !a.exact && a.first_k_cap) ? kd_of(g.eff, ns) : K)
+                                   : ((K >= 2 && a.k_dec > K) ? a.k_dec : K);
             if (K >= 2 && a.direct_rung && a.rung < 0 && !res.resolved && res.processed >= g.eff)   // first pass only: the rungs have their queues read already
                 res.next_rung = rung_from_two_entries(a, P[0], P[K >= 2 ? 1 : 0], g.eff, ns, K);
             if (res.processed < g.eff) { res.resolved = false; res.ee_raw = (double)(kd - 1); }
             else if (kd > K && !res.resolved) {
-                if (cascade_bound<K>(P, kd) < a.oma - 1e-9) res.ee_raw = (double)(kd - 1);   // j* >= kd: a certain reject, without the kd-entry sweep
-                else res.escalate = true;
+                // (c_ratio[] of the bound reaches kd = 8; a read that needs more -- longer than the caller said -- goes to its rung)
+                if (kd <= 8 && cascade_bound<K>(P, kd) < a.oma - 1e-9) res.ee_raw = (double)(kd - 1);   // j* >= kd: a certain reject, without the kd-entry sweep
+                else {
+                    res.escalate = true;
+                    if constexpr (PERREAD) res.next_rung = pick_rung(a, kd);   // swept once more, with the entries its own decision needs
+                }
             }
         } else if constexpr (MODE == 1) {
             const double lam = P[0];
@@ -897,6 +919,15 @@ __global__ void policy_kernel(const uint32_t *queue_count, uint32_t max_pushed, 
 __global__ void policy_first_kernel(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy)
 {
     *policy = *queue_count > max_pushed ? MOIRA_POLICY_UNDECIDED : 2u;
+}
+// Length-bucketed first pass, decision mode: verdict of the pilot that swept its reads with at most first_k_cap entries per bucket.
+// What those entries did not settle sits in the rung queues; few enough -> the rest of the batch is swept the same way (1),
+// else every bucket gets the K of its own cutoff (0).
+__global__ void policy_sorted_kernel(const uint32_t *queue_counts, uint32_t max_pushed, uint32_t *policy)
+{
+    uint32_t pushed = 0;
+    for (int r = 0; r <= N_TPR_RUNGS; r++) pushed += queue_counts[r];
+    *policy = pushed > max_pushed ? 0u : 1u;
 }
 // Verdict of the second pilot: the cheapest first stage in issue cycles per base, 2 F + O with F = 3 K - 2 FP64 operations
 // and O = 4.3 others (profiles/r02_k2_regions_before_fix.md), counting every read with j* >= K1 as swept again with k_first
@@ -992,7 +1023,7 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) sorted_first_kernel(const
         const uint32_t cnt = seg_count[g];                                                             \
         if (cnt) {                                                                                     \
             const uint32_t first = (gw + W - before % W) % W;                                          \
-            tpr_tiles<k, 0, EQP, false>(a, nullptr, ctx, a.queue + seg_start[g], cnt, first, W);       \
+            tpr_tiles<k, 0, EQP, false, 0, true>(a, nullptr, ctx, a.queue + seg_start[g], cnt, first, W); \
             before += (cnt + 31) >> 5;                                                                 \
         }                                                                                              \
     }
@@ -1234,10 +1265,10 @@ __global__ void __launch_bounds__(256) len_hist_kernel(const FilterArgs a, uint3
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < LEN_BUCKETS; i += 256) s_h[i] = 0;
     __syncthreads();
-    const uint32_t n_round = (a.n + 255u) & ~255u;
-    for (uint32_t r = blockIdx.x * 256 + threadIdx.x; r < n_round; r += gridDim.x * 256) {
-        const bool ok = r < a.n;
-        warp_agg_inc(s_h, ok ? len_bucket(read_geom(a, r).eff) : 0u, ok, lane);
+    const uint32_t cnt = a.n - a.first_read, n_round = (cnt + 255u) & ~255u;     // reads [first_read, n) of the sub-batch
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n_round; i += gridDim.x * 256) {
+        const bool ok = i < cnt;
+        warp_agg_inc(s_h, ok ? len_bucket(read_geom(a, a.first_read + i).eff) : 0u, ok, lane);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < LEN_BUCKETS; i += 256)
@@ -1253,6 +1284,8 @@ __global__ void __launch_bounds__(1024) len_scan_kernel(const FilterArgs a, cons
     __shared__ uint32_t s_gs[N_FIRST_K], s_gc[N_FIRST_K];
     constexpr int PER = LEN_BUCKETS / 1024;
     const int t = threadIdx.x;
+    // the cap may hang on a verdict left on the device by a pilot (decision mode: capped buckets only pay when few reads escalate)
+    const int cap = (a.first_k_cap && (!a.cap_policy || *a.cap_policy == 1u)) ? a.first_k_cap : 0;
     if (t < N_FIRST_K) { s_gs[t] = 0xFFFFFFFFu; s_gc[t] = 0; }
     uint32_t v[PER], sum = 0;
 #pragma unroll
@@ -1279,7 +1312,7 @@ __global__ void __launch_bounds__(1024) len_scan_kernel(const FilterArgs a, cons
                 double kd = cutoff < 0.0 ? 2.0 : floor(cutoff) + 2.0;
                 if (b == LEN_BUCKETS - 1) kd = 1e9;   // the catch-all bucket (lengths unknown to the host): the largest K
                 // exact mode with a ladder behind the first pass: the pass only has to settle the reads that are cheap to settle
-                if (a.first_k_cap && kd > (double)a.first_k_cap) kd = (double)a.first_k_cap;
+                if (cap && kd > (double)cap) kd = (double)cap;
                 while (g < N_FIRST_K - 1 && (double)first_pass_k(g) < kd) g++;
             }
             atomicMin(&s_gs[g], run);
@@ -1301,7 +1334,7 @@ __global__ void __launch_bounds__(256) len_scatter_kernel(const FilterArgs a, co
     __shared__ uint32_t s_cnt[LEN_BUCKETS];
     __shared__ uint32_t s_base[LEN_BUCKETS];
     const int lane = threadIdx.x & 31;
-    for (uint32_t c0 = blockIdx.x * LS_CHUNK; c0 < a.n; c0 += gridDim.x * LS_CHUNK) {
+    for (uint32_t c0 = a.first_read + blockIdx.x * LS_CHUNK; c0 < a.n; c0 += gridDim.x * LS_CHUNK) {
         for (int i = threadIdx.x; i < LEN_BUCKETS; i += 256) s_cnt[i] = 0;
         __syncthreads();
         uint32_t slot[LS_CHUNK / 256], bkt[LS_CHUNK / 256];
@@ -1611,6 +1644,11 @@ int launch_policy(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *po
 int launch_policy_first(const uint32_t *queue_count, uint32_t max_pushed, uint32_t *policy, cudaStream_t s)
 {
     policy_first_kernel<<<1, 1, 0, s>>>(queue_count, max_pushed, policy);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+int launch_policy_sorted(const uint32_t *queue_counts, uint32_t max_pushed, uint32_t *policy, cudaStream_t s)
+{
+    policy_sorted_kernel<<<1, 1, 0, s>>>(queue_counts, max_pushed, policy);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int launch_policy_second(const uint32_t *jhist, int k_first, int exact, uint32_t *policy, cudaStream_t s)

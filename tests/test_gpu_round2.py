@@ -474,3 +474,49 @@ def test_length_bucketed_exact_first_pass_with_capped_k():
     finally:
         capped.close()
         full.close()
+
+
+def test_length_bucketed_decision_with_capped_buckets(ctx):
+    """Ragged batches whose decisions need 5 .. 8 entries: buckets swept with at most four entries first (Newton bound at every
+    read's own K, the rest to the rung that holds it) -- by pilot (cascade = 0) or forced (1) -- give the decisions, Ns and
+    accepted-read ee of the sweep with every bucket's own K (2); lower bounds are valid; a sample is the oracle's."""
+    n = 3_000_000
+    dev = torch.device("cuda", 0)
+    slab, lens, _ = synth.generate_device("mixed", n, 97, dev)
+    stride, fixed = synth.DEVICE_LAYOUT["mixed"]
+    max_len, min_len = int(lens.max().item()), int(lens.min().item())
+    stream = torch.cuda.current_stream().cuda_stream
+    m = 4000
+    idx = np.sort(np.random.default_rng(9).choice(n, m, replace=False))
+    h_rows = slab[torch.as_tensor(idx, device=dev)].cpu().numpy().reshape(-1)
+    off = np.arange(m, dtype=np.uint64) * np.uint64(stride)
+    ln = lens[torch.as_tensor(idx, device=dev)].cpu().numpy().astype(np.uint32)
+    ee_o, ns_o = po.pb_batch(h_rows, off, ln, 0.005)
+    for ambigs in ("treat_as_errors", "ignore"):
+        outs = []
+        for cascade in (0, 1, 2):
+            ee, ns, fl, cnt = _dev_arrays(n)
+            p = FilterParams(exact_ee=False, cascade=cascade, max_length=max_len, min_length=min_len, length_sort=1, ambigs=ambigs)
+            ctx.filter_device(slab.data_ptr(), None, lens.data_ptr(), stride, 0, n, p, ee.data_ptr(), ns.data_ptr(), fl.data_ptr(),
+                              cnt.data_ptr(), stream)
+            torch.cuda.synchronize()
+            outs.append((ee.cpu().numpy(), ns.cpu().numpy(), fl.cpu().numpy(), cnt.cpu().numpy()))
+        ref = outs[2]
+        lb_ref = (ref[2] & L.FLAG_LOWER_BOUND) != 0
+        for o in outs[:2]:
+            lb = (o[2] & L.FLAG_LOWER_BOUND) != 0
+            assert np.array_equal(o[2] & 0x0F, ref[2] & 0x0F)                    # accept bit and reason
+            assert np.array_equal(o[1], ref[1])
+            assert not ((o[2] & 1) & lb).any() and not (o[2] & L.FLAG_NUMERIC).any()
+            both = ~lb & ~lb_ref
+            assert np.array_equal(o[0][both], ref[0][both])
+            keep = [L.CNT_READS, L.CNT_ACCEPTED, L.CNT_BAD_ERRORS, L.CNT_BAD_LENGTH, L.CNT_BAD_AMBIGS]
+            assert np.array_equal(o[3][keep], ref[3][keep])
+            assert int(o[3][L.CNT_ESCALATED]) > 0 and int(o[3][L.CNT_FP64_OPS]) < int(ref[3][L.CNT_FP64_OPS])
+            # oracle on the sample
+            f, e = o[2][idx], o[0][idx]
+            s_lb = (f & L.FLAG_LOWER_BOUND) != 0
+            cut = ln * 0.01
+            stat = ee_o + (ns_o if ambigs == "treat_as_errors" else 0)
+            assert np.array_equal((f & 1) != 0, stat <= cut)
+            assert np.array_equal(e[~s_lb], ee_o[~s_lb]) and (e[s_lb] <= ee_o[s_lb]).all()       # ee_output = raw: the statistic without Ns
