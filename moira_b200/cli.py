@@ -29,6 +29,7 @@ import numpy as np
 
 from . import _lib as L
 from .api import ContigParams, Context, FilterParams, MoiraError, collapse, parse_fasta_qual, parse_fastq
+from .contig import LengthMismatchError  # noqa: F401  (moira.py:1024-1038; one class for the parsers, the calculators and make_contig)
 
 __version__ = "0.1.0 (moira 1.3.2 compatible)"
 
@@ -47,11 +48,6 @@ class UnpairedFilesError(Exception):
 class NameMismatchError(Exception):
     def __init__(self, *headers):
         super().__init__("Sequence headers do not match: %s" % ", ".join(str(h) for h in headers))
-
-
-class LengthMismatchError(Exception):
-    def __init__(self, header, *files):
-        super().__init__("Sequence and quality lengths differ for %s (%s)" % (header, ", ".join(map(str, files))))
 
 
 class EmptySeqError(Exception):

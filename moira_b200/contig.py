@@ -21,7 +21,14 @@ _ctx = None
 
 
 class LengthMismatchError(Exception):
-    pass
+    """moira.py:1024-1038: raised bare by the calculators and the contig constructor, with a header and file names by the parsers."""
+
+    def __init__(self, header=None, *files):
+        self.header, self.files = header, files
+        if header is None:
+            super().__init__("Sequence and qualities are of different lengths.")
+        else:
+            super().__init__("Sequence and quality lengths differ for %s (%s)" % (header, ", ".join(map(str, files))))
 
 
 def _context() -> Context:
