@@ -520,3 +520,38 @@ def test_length_bucketed_decision_with_capped_buckets(ctx):
             stat = ee_o + (ns_o if ambigs == "treat_as_errors" else 0)
             assert np.array_equal((f & 1) != 0, stat <= cut)
             assert np.array_equal(e[~s_lb], ee_o[~s_lb]) and (e[s_lb] <= ee_o[s_lb]).all()       # ee_output = raw: the statistic without Ns
+
+
+@pytest.mark.parametrize("kw", [dict(alpha=1e-6), dict(alpha=0.2), dict(uncert=0.02), dict(maxerrors=9.5), dict(ambigs="ignore"),
+                                dict(ambigs="disallow"), dict(round=True), dict(truncate=1200), dict(truncate=900, maxerrors=12.0),
+                                dict(uncert=0.05, alpha=0.05)])
+def test_classify_first_decisions_under_every_rule(kw):
+    """Classify-first in decision mode (Chernoff rejects included) under the decision rules of write_results: accept bit and
+    reason equal those of a context that sweeps the decision's K first, accepted reads carry the same ee, lower bounds are
+    below the exact statistic (taken from an exact-mode run of that context)."""
+    n = 40000
+    slab, off, ln = synth.generate("ccs", n, 101)
+    slab = slab.copy()
+    ln = ln.copy()
+    rng = np.random.default_rng(11)
+    slab[off[rng.integers(0, n, 3000)] + rng.integers(0, 1400, 3000).astype(np.uint64)] = 0xFF       # N in one read of eight
+    slab[off[rng.integers(0, n, 300)] + rng.integers(0, 1400, 300).astype(np.uint64)] = 0xFE         # and some n
+    ln[rng.integers(0, n, 2000)] = rng.integers(1, 1500, 2000)                                        # ragged
+    cf = _fresh_ctx({})
+    fp = _fresh_ctx({"MOIRA_B200_CLASSIFY_FIRST_K": "1000", "MOIRA_B200_CLASSIFY_FIRST_DEC_K": "1000"})
+    try:
+        for length_sort in (2, 1):
+            exact = fp.filter_batch(slab, off, ln, FilterParams(exact_ee=True, length_sort=length_sort, **kw))
+            a = cf.filter_batch(slab, off, ln, FilterParams(exact_ee=False, length_sort=length_sort, **kw))
+            b = fp.filter_batch(slab, off, ln, FilterParams(exact_ee=False, length_sort=length_sort, **kw))
+            assert int(a.counters[L.CNT_CLASSIFIED]) > 0 and int(b.counters[L.CNT_CLASSIFIED]) == 0
+            assert np.array_equal(a.flags & 0x0F, b.flags & 0x0F) and np.array_equal(a.flags & 0x0F, exact.flags & 0x0F)
+            assert np.array_equal(a.ns, exact.ns) and not (a.flags & L.FLAG_NUMERIC).any()
+            la = a.lower_bound
+            assert not (la & a.accept).any()
+            assert np.array_equal(a.ee[~la], exact.ee[~la]) and (a.ee[la] <= exact.ee[la]).all()
+            keep = [L.CNT_READS, L.CNT_ACCEPTED, L.CNT_BAD_ERRORS, L.CNT_BAD_LENGTH, L.CNT_BAD_AMBIGS]
+            assert np.array_equal(np.asarray(a.counters)[keep], np.asarray(exact.counters)[keep])
+    finally:
+        cf.close()
+        fp.close()
