@@ -93,3 +93,20 @@ def test_random_batches_and_rules_against_the_oracle(ctx, seed, shape, n):
             assert not (exact and lb.any()) and not (lb & res.accept).any(), tag
             assert np.array_equal(res.ee[~lb], ee_o[~lb]) and (res.ee[lb] <= ee_o[lb]).all(), tag
             assert int(res.counters[L.CNT_READS]) == n and int(res.counters[L.CNT_ACCEPTED]) == int(res.accept.sum()), tag
+
+
+def test_single_read_calls_of_any_length_against_the_oracle():
+    """The drop-in single-read functions (batches of one: every route, classify-first and the wide rungs included) on reads of
+    1 .. 6 000 bases, clean and noisy, against the C restatement."""
+    import bernoulli
+    import moira
+    rng = np.random.default_rng(77)
+    for length in (1, 2, 17, 100, 301, 899, 1500, 3000, 6000):
+        for lo, hi in ((30, 42), (2, 20), (0, 94)):
+            quals = [int(q) for q in rng.integers(lo, hi, length)]
+            seq = "".join(rng.choice(list("ACGTNn"), size=length, p=[.245, .245, .245, .245, .015, .005]))
+            for alpha in (0.005, 0.1):
+                want_c = po.pb_c(seq, [q if q > 0 else 1 for q in quals], alpha)
+                assert bernoulli.calculate_errors_PB(seq, quals, alpha) == want_c, (length, lo, alpha)
+                up = seq.replace("n", "A")                                  # the Python twin counts 'N' only: same answer without 'n'
+                assert moira.calculate_errors_PB(up, quals, alpha) == po.pb_c(up, [q if q > 0 else 1 for q in quals], alpha)
