@@ -249,6 +249,12 @@ MOIRA_API int moira_line_offsets(const char *text, uint64_t text_bytes, const ui
 
 /* Number of complete 4-line records in a FASTQ text buffer (to size the output arrays). */
 MOIRA_API int moira_fastq_count_reads(const char *text, uint64_t text_bytes, uint64_t *n_reads_out);
+/* The record table of a FASTQ text without a slab (parse_fastq's record semantics, moira.py:1152-1204: strip, 4 lines,
+ * header token, Empty / LengthMismatch errors): lengths, header token and sequence / quality line byte ranges.  For
+ * callers that hand the TEXT itself to the device (moira_filter_pairs reads bases and quality characters where they
+ * lie).  lengths == NULL: count only. */
+MOIRA_API int moira_index_fastq(const char *text, uint64_t text_bytes, uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len,
+                                uint64_t *seq_off, uint64_t *qual_off, uint64_t max_reads, uint64_t *n_reads_out);
 
 /* FASTQ text in, decisions out, in one call: the text is cut into ~64 MB ranges that are parsed (all
  * host threads, moira_parse_fastq semantics) into pinned slabs and submitted asynchronously, so the

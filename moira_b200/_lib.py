@@ -39,7 +39,7 @@ EXPORTS = [
     "moira_ctx_destroy", "moira_ctx_sm_count", "moira_build_lut", "moira_ctx_get_lut",
     "moira_host_alloc", "moira_host_free", "moira_filter_device", "moira_count_marks_device", "moira_filter_batch",
     "moira_submit", "moira_wait", "moira_calculate_errors_PB", "moira_pack_reads", "moira_pack_q6",
-    "moira_parse_fastq", "moira_parse_fasta_qual", "moira_fastq_count_reads", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
+    "moira_parse_fastq", "moira_parse_fasta_qual", "moira_fastq_count_reads", "moira_index_fastq", "moira_filter_fastq", "moira_collapse", "moira_set_host_threads", "moira_fp64_peak", "moira_ctx_launch_count", "moira_ctx_set_timing",
     "moira_filter_fastq_ex", "moira_collapse_device", "moira_collapse_labels", "moira_collapse_labels_device", "moira_collapse_groups", "moira_collapse_addr", "moira_format_records", "moira_blocks_parts",
     "moira_blocks_get", "moira_blocks_write", "moira_blocks_recycle", "moira_blocks_free", "moira_fastq_headers", "moira_fastq_split", "moira_line_offsets",
     "moira_comm_unique_id", "moira_comm_init", "moira_comm_init_all", "moira_comm_info", "moira_reduce_counters_device",
@@ -126,6 +126,7 @@ lib.moira_parse_fastq.argtypes = [_vp, _u64, _i, _i, _vp, _u64, _vp, _vp, _vp, _
 lib.moira_parse_fasta_qual.argtypes = [_vp, _u64, _vp, _u64, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                        ctypes.POINTER(_u64), ctypes.POINTER(_u64)]
 lib.moira_fastq_count_reads.argtypes = [_vp, _u64, ctypes.POINTER(_u64)]
+lib.moira_index_fastq.argtypes = [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64)]
 lib.moira_filter_fastq.argtypes = [_vp, _vp, _u64, _i, _i, _pp, _u64, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_u64)]
 lib.moira_filter_fastq_ex.argtypes = [_vp, _vp, _u64, _i, _i, _pp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_u64)]
 lib.moira_collapse_device.argtypes = [_vp, _vp, _vp, _vp, _u64, _u32, _u64, _u32, _vp, _vp]

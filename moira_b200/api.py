@@ -625,6 +625,21 @@ def parse_fastq(text: bytes, fastq_offset: int = 33, lower_n_ambiguous: bool = T
     return slab, offsets, lengths, hdr_off, hdr_len, seq_off, qual_off
 
 
+def index_fastq(text):
+    """FASTQ bytes -> (lengths, hdr_off, hdr_len, seq_off, qual_off) via moira_index_fastq: the record table without a slab,
+    for flows that hand the text itself to the device (read pairs).  Errors as parse_fastq."""
+    buf = np.frombuffer(text, dtype=np.uint8)
+    n = ctypes.c_uint64()
+    L.check(lib.moira_index_fastq(_ptr(buf), buf.nbytes, None, None, None, None, None, 0, ctypes.byref(n)))
+    nr = n.value
+    lengths, hdr_len = np.empty(nr, np.uint32), np.empty(nr, np.uint32)
+    hdr_off, seq_off, qual_off = np.empty(nr, np.uint64), np.empty(nr, np.uint64), np.empty(nr, np.uint64)
+    if nr:
+        L.check(lib.moira_index_fastq(_ptr(buf), buf.nbytes, _ptr(lengths), _ptr(hdr_off), _ptr(hdr_len), _ptr(seq_off), _ptr(qual_off),
+                                      nr, ctypes.byref(n)))
+    return lengths, hdr_off, hdr_len, seq_off, qual_off
+
+
 def parse_fasta_qual(fasta: bytes, qual: bytes, lower_n_ambiguous: bool = True):
     """FASTA + QUAL bytes -> (slab, qual_slab, offsets, lengths, hdr_off, hdr_len, seq_off) via
     moira_parse_fasta_qual.  qual_slab holds the plain qualities (negative values as 0) at the slab's offsets."""

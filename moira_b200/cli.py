@@ -364,7 +364,7 @@ def _read_fastq_pair_batches(args, lower_n_ambiguous):
     """Two FASTQ files in lock step without touching the text in Python: both files are memory-mapped (gz / bz2: inflated
     once), moira_line_offsets cuts them at the same record numbers (one parallel newline count per file), and every pair
     of blocks goes through the native parser as a view."""
-    from .api import line_offsets
+    from .api import index_fastq, line_offsets
     ftext, fkeep = load_text(args.forward_fastq)
     rtext, rkeep = load_text(args.reverse_fastq)
     if ftext.size == 0 or (ftext.size < 4096 and not ftext.tobytes().strip()):
@@ -388,7 +388,7 @@ def _read_fastq_pair_batches(args, lower_n_ambiguous):
         parsed = []
         for buf, fname in ((fb, args.forward_fastq), (rb, args.reverse_fastq)):
             try:
-                _, _, ln, hoff, hlen, soff, qoff = parse_fastq(buf, args.fastq_offset, lower_n_ambiguous)
+                ln, hoff, hlen, soff, qoff = index_fastq(buf)      # the contig kernel reads bases and quality characters from the text itself
             except MoiraError as exc:
                 raise _parse_error_for(exc, fname) from None
             parsed.append((buf, hoff, hlen, (buf, buf, soff, qoff, ln, args.fastq_offset)))

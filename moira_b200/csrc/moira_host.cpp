@@ -273,7 +273,14 @@ void fq_parse_segment(const FqJob &j, FqSeg &g, uint64_t next_begin)
             break;
         }
         const uint64_t padded = (slen + 15u) & ~15ull;
-        {
+        if (!j.slab) {   // index only (moira_index_fastq): where the records are, nothing converted
+            const uint64_t r = g.read_base + n;
+            if (j.lengths) j.lengths[r] = (uint32_t)slen;
+            if (j.hdr_off) j.hdr_off[r] = hb;
+            if (j.hdr_len) j.hdr_len[r] = (uint32_t)(he - hb);
+            if (j.seq_off) j.seq_off[r] = lb[1];
+            if (j.qual_off) j.qual_off[r] = lb[3];
+        } else {
             const uint64_t r = g.read_base + n;
             uint8_t *row = j.slab + g.slab_base + pos;
             const char *s = text + lb[1];
@@ -323,6 +330,16 @@ extern "C" int moira_parse_fastq(const char *text, uint64_t text_bytes, int fast
     return moira::parse_fastq_range(text, text_bytes, fastq_offset, lower_n_ambiguous, slab, slab_capacity, out_offsets,
                                     lengths, hdr_off, hdr_len, seq_off, qual_off, max_reads, n_reads_out, slab_bytes_out,
                                     nullptr, 1);
+}
+
+extern "C" int moira_index_fastq(const char *text, uint64_t text_bytes, uint32_t *lengths, uint64_t *hdr_off, uint32_t *hdr_len, uint64_t *seq_off,
+                      uint64_t *qual_off, uint64_t max_reads, uint64_t *n_reads_out)
+{
+    uint64_t cap = 0;
+    if (!n_reads_out) return hfail(MOIRA_ERR_BAD_ARG, "NULL argument");
+    // lengths == NULL: count only (as moira_parse_fastq with slab == NULL)
+    return moira::parse_fastq_range(text, text_bytes, 33, 1, nullptr, 0, nullptr, lengths, hdr_off, hdr_len, seq_off, qual_off, max_reads,
+                                    n_reads_out, &cap, nullptr, 1);
 }
 
 extern "C" int moira_fastq_count_reads(const char *text, uint64_t text_bytes, uint64_t *n_reads_out)
@@ -415,9 +432,10 @@ int moira::parse_fastq_range(const char *text, uint64_t text_bytes, int fastq_of
     }
     *n_reads_out = n;
     *slab_bytes_out = cap;
-    if (!slab) return MOIRA_OK;
+    const bool index_only = !slab && lengths;     // moira_index_fastq: the record table without a slab
+    if (!slab && !index_only) return MOIRA_OK;
     if (n > max_reads) return hfail(MOIRA_ERR_BAD_ARG, "more than max_reads = %llu records", (unsigned long long)max_reads);
-    if (cap > slab_capacity) return hfail(MOIRA_ERR_BAD_ARG, "slab capacity too small (need %llu)", (unsigned long long)cap);
+    if (!index_only && cap > slab_capacity) return hfail(MOIRA_ERR_BAD_ARG, "slab capacity too small (need %llu)", (unsigned long long)cap);
     FqJob job{text, text_bytes, fastq_offset, lower_n_ambiguous, slab, out_offsets, hdr_off, seq_off, qual_off, lengths, hdr_len};
     auto next_begin = [&](int t) { return t + 1 < T ? segs[t + 1].rec_start : text_bytes; };
     run([&](int t) { if (segs[t].n_reads) fq_parse_segment(job, segs[t], next_begin(t)); });

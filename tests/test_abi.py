@@ -320,3 +320,22 @@ def test_line_offsets_cut_paired_texts_at_the_same_records():
         want = [pos[int(k)] if int(k) < len(pos) else len(text) for k in q]
         assert off.tolist() == want
     assert moira_b200.line_offsets(b"", np.array([0, 3], np.uint64))[0].tolist() == [0, 0]
+
+
+def test_index_fastq_equals_parse_fastq_without_a_slab():
+    """moira_index_fastq (the record table for flows that hand the text itself to the device) == moira_parse_fastq's byte
+    ranges and lengths, with the same errors for malformed records; multi-threaded ranges included."""
+    import gzip
+    from moira_b200.api import index_fastq
+    raw = gzip.open(os.path.join(ROOT, "tests", "golden", "test1.fastq.gz"), "rb").read()
+    for text in (raw, raw * 4, raw[:-1], raw + b"@tail\nAC\n+\n", b"", b"\n\n", b"@a\n  ACGT \n+\n IIII\n"):
+        a = moira_b200.parse_fastq(text, 33, True)
+        b = index_fastq(text)
+        assert np.array_equal(a[2], b[0]) and np.array_equal(a[3], b[1]) and np.array_equal(a[4], b[2])
+        assert np.array_equal(a[5], b[3]) and np.array_equal(a[6], b[4])
+    for bad in (b"@a\nACG\n+\nII\n", b"@a\n\n+\n\n", b"@a\nAC\n+\n\n"):
+        with pytest.raises(moira_b200.MoiraError) as e1:
+            moira_b200.parse_fastq(bad, 33, True)
+        with pytest.raises(moira_b200.MoiraError) as e2:
+            index_fastq(bad)
+        assert e1.value.code == e2.value.code == L.ERR_PARSE and e1.value.message == e2.value.message
