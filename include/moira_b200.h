@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MOIRA_ABI_VERSION 5
+#define MOIRA_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define MOIRA_API __attribute__((visibility("default")))

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOIRA_B200_LIB") or os.path.join(_HERE, "libmoira_b200.so")   # env override: tuning experiments only
 
 # ---- constants mirrored from include/moira_b200.h -------------------------------------------
-ABI_VERSION = 5
+ABI_VERSION = 6
 OK = 0
 ERR_BAD_ALPHA, ERR_LENGTH_MISMATCH, ERR_BAD_QUALITY, ERR_CUDA = -1, -2, -3, -4
 ERR_BAD_ARG, ERR_NOMEM, ERR_UNRESOLVED, ERR_PARSE, ERR_NCCL = -5, -6, -7, -8, -9
