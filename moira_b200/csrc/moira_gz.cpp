@@ -13,6 +13,8 @@
 //             in parallel.
 // zlib does the deflate work (a library call for library work); CRC-32 and ISIZE of every member are checked on input.
 #include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -25,6 +27,7 @@
 #include <thread>
 #include <vector>
 
+#include "moira_inflate.h"
 #include "moira_internal.h"
 
 namespace {
@@ -105,12 +108,106 @@ uint8_t *map_new(size_t bytes)
 {
     if (!bytes) bytes = 1;
     void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-    return p == MAP_FAILED ? nullptr : (uint8_t *)p;
+    if (p == MAP_FAILED) return nullptr;
+#ifdef MADV_HUGEPAGE
+    madvise(p, bytes, MADV_HUGEPAGE);   // gigabytes of first-touch output: 2 MB pages where the kernel grants them (a hint, may fail)
+#endif
+    return (uint8_t *)p;
 }
 uint8_t *map_grow(uint8_t *p, size_t old_bytes, size_t new_bytes)
 {
     void *q = mremap(p, old_bytes, new_bytes, MREMAP_MAYMOVE);
     return q == MAP_FAILED ? nullptr : (uint8_t *)q;
+}
+
+bool use_own_inflate()
+{
+    static const bool yes = [] { const char *e = getenv("MOIRA_B200_ZLIB_INFLATE"); return !(e && e[0] == '1'); }();
+    return yes;
+}
+
+// CRC-32 of a large buffer on several threads (zlib's crc32 per slice, crc32_combine for the result)
+uint32_t crc32_parallel(const uint8_t *p, uint64_t n, int T)
+{
+    if (n < (8u << 20) || T <= 1) {
+        uLong c = crc32(0L, Z_NULL, 0);
+        for (uint64_t at = 0; at < n; at += 1u << 30) c = crc32(c, p + at, (uInt)std::min<uint64_t>(1u << 30, n - at));
+        return (uint32_t)c;
+    }
+    std::vector<uLong> part((size_t)T);
+    std::vector<uint64_t> cut((size_t)T + 1);
+    for (int t = 0; t <= T; t++) cut[t] = n * (uint64_t)t / T;
+    std::atomic<int> next{0};
+    run_threads(T, [&]() {
+        for (;;) {
+            const int t = next.fetch_add(1);
+            if (t >= T) return;
+            uLong c = crc32(0L, Z_NULL, 0);
+            for (uint64_t at = cut[t]; at < cut[t + 1]; at += 1u << 30) c = crc32(c, p + at, (uInt)std::min<uint64_t>(1u << 30, cut[t + 1] - at));
+            part[t] = c;
+        }
+    });
+    uLong c = part[0];
+    for (int t = 1; t < T; t++) c = crc32_combine(c, part[t], (z_off_t)(cut[t + 1] - cut[t]));
+    return (uint32_t)c;
+}
+
+// length of a gzip member header (RFC 1952 2.3), 0 if it is malformed or runs off the buffer
+uint64_t gzip_header_bytes(const uint8_t *p, uint64_t n)
+{
+    if (n < 18 || p[0] != 31 || p[1] != 139 || p[2] != 8 || (p[3] & 0xE0)) return 0;
+    const int flg = p[3];
+    uint64_t at = 10;
+    if (flg & 4) { if (at + 2 > n) return 0; at += 2 + le16(p + at); }
+    if (flg & 8) { while (at < n && p[at]) at++; at++; }
+    if (flg & 16) { while (at < n && p[at]) at++; at++; }
+    if (flg & 2) at += 2;
+    return at + 8 <= n ? at : 0;
+}
+
+// One thread, member after member, with this library's own DEFLATE decoder (moira_inflate.h); every member's CRC-32 and size
+// are checked against its trailer.  Returns 1 when the file was inflated, 0 when anything looked wrong -- the caller then
+// takes the zlib route from the start, which also words the error.
+int inflate_stream_own(const uint8_t *gz, uint64_t n, int n_threads, uint8_t **out, uint64_t *out_bytes)
+{
+    size_t cap = (size_t)(n * 4 + (1u << 20));
+    uint8_t *buf = map_new(cap);
+    if (!buf) return 0;
+    uint64_t in_at = 0, out_at = 0;
+    bool ok = true;
+    static thread_local moira_inflate::State st;
+    for (;;) {
+        while (in_at < n && gz[in_at] == 0) in_at++;           // zero padding between / behind members
+        if (in_at >= n) break;
+        const uint64_t hb = gzip_header_bytes(gz + in_at, n - in_at);
+        if (!hb) { ok = false; break; }
+        moira_inflate::start(st, gz + in_at + hb, gz + n);
+        const uint64_t member_out = out_at;
+        for (;;) {
+            uint8_t *pos = nullptr;
+            // the window of a member is its own output (a member never refers to the one before)
+            const moira_inflate::Result r = moira_inflate::run(st, buf + member_out, buf + out_at, buf + cap, &pos);
+            if (r == moira_inflate::BAD_DATA) { ok = false; break; }
+            out_at = (uint64_t)(pos - buf);
+            if (r == moira_inflate::DONE) break;
+            const size_t ncap = cap + cap / 2 + (64u << 20);
+            uint8_t *nb = map_grow(buf, cap, ncap);
+            if (!nb) { ok = false; break; }
+            buf = nb; cap = ncap;
+        }
+        if (!ok) break;
+        const uint8_t *tail = moira_inflate::input_position(st);
+        if (tail > gz + n || (uint64_t)(gz + n - tail) < 8) { ok = false; break; }
+        const uint64_t mlen = out_at - member_out;
+        if (le32(tail + 4) != (uint32_t)mlen || le32(tail) != crc32_parallel(buf + member_out, mlen, threads_for(n_threads))) { ok = false; break; }
+        in_at = (uint64_t)(tail - gz) + 8;
+    }
+    if (!ok) { munmap(buf, cap); return 0; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_maps[buf] = cap;
+    *out = buf;
+    *out_bytes = out_at;
+    return 1;
 }
 
 // one thread, member after member (what gzip.GzipFile(...).read() does)
@@ -294,7 +391,11 @@ int moira_gz_inflate(const uint8_t *gz, uint64_t gz_bytes, int n_threads, uint8_
     if (gz_bytes < 2 || gz[0] != 31 || gz[1] != 139) return moira::fail(MOIRA_ERR_PARSE, "not a gzip file");
     std::vector<Member> mem;
     uint64_t total = 0;
-    if (!bgzf_members(gz, gz_bytes, mem, &total)) return inflate_stream(gz, gz_bytes, out, out_bytes);
+    if (!bgzf_members(gz, gz_bytes, mem, &total)) {
+        if (use_own_inflate() && inflate_stream_own(gz, gz_bytes, n_threads, out, out_bytes)) return MOIRA_OK;
+        if (getenv("MOIRA_B200_GZ_DEBUG")) fprintf(stderr, "[moira_gz] own decoder declined the stream: zlib\n");
+        return inflate_stream(gz, gz_bytes, out, out_bytes);      // zlib: the reference decoder, and the one that words the errors
+    }
 
     uint8_t *buf = map_new((size_t)total);
     if (!buf) return moira::fail(MOIRA_ERR_NOMEM, "cannot map %llu bytes for the inflated text", (unsigned long long)total);
@@ -304,6 +405,7 @@ int moira_gz_inflate(const uint8_t *gz, uint64_t gz_bytes, int n_threads, uint8_
     std::atomic<long long> bad_at{-1};
     int T = threads_for(n_threads);
     if ((size_t)T > n_tasks) T = (int)std::max<size_t>(1, n_tasks);
+    const bool own = use_own_inflate();
     run_threads(T, [&]() {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
@@ -313,6 +415,15 @@ int moira_gz_inflate(const uint8_t *gz, uint64_t gz_bytes, int n_threads, uint8_
             if (t >= n_tasks || bad_at >= 0) break;
             for (size_t i = t * PER_TASK; i < std::min(mem.size(), (t + 1) * PER_TASK); i++) {
                 const Member &m = mem[i];
+                const uint32_t crc_member = le32(gz + m.at + m.size - 8);
+                if (own) {   // this library's decoder first; zlib below if it disagrees with the member's trailer in any way
+                    static thread_local moira_inflate::State st;
+                    moira_inflate::start(st, gz + m.at + m.head, gz + m.at + m.size - BGZF_TAIL);
+                    uint8_t *pos = nullptr;
+                    if (moira_inflate::run(st, buf + m.out, buf + m.out, buf + m.out + m.isize, &pos) == moira_inflate::DONE &&
+                        pos == buf + m.out + m.isize && (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf + m.out, m.isize) == crc_member)
+                        continue;
+                }
                 inflateReset(&zs);
                 zs.next_in = const_cast<Bytef *>(gz + m.at + m.head); zs.avail_in = m.size - m.head - BGZF_TAIL;
                 zs.next_out = buf + m.out; zs.avail_out = m.isize;

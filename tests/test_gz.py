@@ -108,3 +108,46 @@ def test_large_stream_grows_its_buffer():
     blob = z.compress(data) + z.flush()
     out = gz_inflate(blob)
     assert out.size == len(data) and not out.any()
+
+
+def test_own_decoder_against_zlib_on_many_streams_and_corruptions(tmp_path):
+    """The library's DEFLATE decoder (moira_inflate.h) sits in front of zlib: every kind of block (stored, fixed, dynamic; levels
+    0..9; long matches; empty members), then 300 random truncations / bit flips / garbage runs of plain and blocked gzip files --
+    the result is Python's gzip result, error for error (a decoder that disagrees with a member's CRC-32 hands over to zlib)."""
+    rng = np.random.default_rng(6)
+    fastq = gzip.open(os.path.join(GOLDEN, "test1.fastq.gz"), "rb").read()
+    texts = [b"", b"a", b"ab" * 70000, bytes(100000), fastq, rng.integers(0, 256, 200000, dtype=np.uint8).tobytes(),
+             fastq[:50000] + bytes(rng.integers(0, 4, 300000, dtype=np.uint8) + 65) + fastq[:1000] * 40]
+    for data in texts:
+        for level in (0, 1, 4, 6, 9):
+            z = gzip.compress(data, level)
+            assert gz_inflate(z).tobytes() == data
+            co = zlib.compressobj(level, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)          # fixed Huffman blocks
+            z = co.compress(data) + co.flush()
+            assert gz_inflate(z).tobytes() == data
+            co = zlib.compressobj(level, zlib.DEFLATED, 31)                             # many small blocks: full flushes
+            z = b"".join(co.compress(data[i:i + 7001]) + co.flush(zlib.Z_FULL_FLUSH) for i in range(0, len(data), 7001)) + co.flush()
+            assert gz_inflate(z).tobytes() == data
+    plain, blocked = gzip.compress(fastq, 6), _bgzf(fastq, tmp_path)
+    for trial in range(300):
+        src = bytearray(plain if trial % 2 else blocked)
+        kind = trial % 3
+        if kind == 0:
+            src = src[:int(rng.integers(1, len(src)))]
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                src[int(rng.integers(0, len(src)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            a = int(rng.integers(0, len(src) - 64))
+            src[a:a + 64] = rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
+        src = bytes(src)
+        try:
+            want = gzip.decompress(src)
+        except Exception:
+            want = None
+        try:
+            got = gz_inflate(src).tobytes()
+        except moira_b200.MoiraError as exc:
+            assert exc.code == L.ERR_PARSE
+            got = None
+        assert got == want, (trial, kind)
