@@ -293,7 +293,7 @@ def cli_bench(rec, accepted_per_read, world, rank, args):
                     os.remove(os.path.join(tmp, f))
             os.remove(gzp); os.remove(plain_p)
             comp["note"] = ("default flags (exact ee, collapse, fasta + qual + names); bgzf_in: every 64 KB member inflated on its own thread; "
-                            "plain_gzip_in: one member, one inflate thread (zlib), %d reads; gz_out: outputs as BGZF members compressed on all host threads" % m_plain)
+                            "plain_gzip_in: one member, one inflate thread (the library's own DEFLATE decoder, CRC-checked, zlib behind it), %d reads; gz_out: outputs as BGZF members compressed on all host threads" % m_plain)
             out["compressed"] = comp
             # the paired flow (moira's main use): two FASTQ files -> contigs -> filter -> collapse -> files
             from tools.bench_contigs import make_pairs
