@@ -110,3 +110,29 @@ def test_single_read_calls_of_any_length_against_the_oracle():
                 assert bernoulli.calculate_errors_PB(seq, quals, alpha) == want_c, (length, lo, alpha)
                 up = seq.replace("n", "A")                                  # the Python twin counts 'N' only: same answer without 'n'
                 assert moira.calculate_errors_PB(up, quals, alpha) == po.pb_c(up, [q if q > 0 else 1 for q in quals], alpha)
+
+
+@pytest.mark.parametrize("shape,n", [("long", 4000), ("ragged", 20000), ("wild", 6000)])
+def test_fastq_text_through_the_device_parser_equals_the_slab_path(ctx, shape, n):
+    """moira_filter_fastq (text -> device parser -> whatever route the filter picks: classify-first for the long reads, the
+    bucketed passes for the ragged ones) == moira_filter_batch on the slab the host packer makes of the same reads, both modes."""
+    rng = np.random.default_rng(500 + n)
+    slab, off, ln = _batch(rng, n, shape)
+    ln = np.maximum(ln, 1).astype(np.uint32)                      # FASTQ records cannot be empty (EmptySeqError)
+    recs = []
+    for r in range(n):
+        q = slab[int(off[r]):int(off[r]) + int(ln[r])]
+        seq = np.where(q == 0xFF, ord("N"), np.where(q == 0xFE, ord("n"), ord("A"))).astype(np.uint8).tobytes()
+        qual = (np.where(q >= 0xFD, 2, np.minimum(q, 93)) + 33).astype(np.uint8).tobytes()
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (r, seq, qual))
+    text = b"".join(recs)
+    pslab, poff, pln, *_ = moira_b200.parse_fastq(text, 33, True)
+    for exact in (True, False):
+        p = FilterParams(exact_ee=exact)
+        want = ctx.filter_batch(pslab, poff, pln, p)
+        got, glen = ctx.filter_fastq(text, p)
+        assert np.array_equal(glen, pln)
+        assert np.array_equal(got.ns, want.ns) and np.array_equal(got.flags & 0x0F, want.flags & 0x0F)
+        lb = got.lower_bound | want.lower_bound
+        assert np.array_equal(got.ee[~lb], want.ee[~lb]) and not (exact and lb.any())
+        assert not (got.flags & L.FLAG_NUMERIC).any()
