@@ -283,7 +283,11 @@ def cli_bench(rec, accepted_per_read, world, rank, args):
             comp = {"bgzf_input_bytes": int(gz_bytes), "bgzf_written_in_seconds": t_def,
                     "bgzf_deflate_level1_gb_per_s": rec.nbytes / t_def / 1e9}
             for tag, pth, mm_, extra in (("bgzf_in", gzp, m, []), ("plain_gzip_in", plain_p, m_plain, []),
-                                         ("bgzf_in_gz_out", gzp, m, ["-oc", "gz"])):
+                                         ("bgzf_in_gz_out", gzp, m, ["-oc", "gz"]), ("bgzf_in_gz_out_level1", gzp, m, ["-oc", "gz"])):
+                if tag.endswith("level1"):
+                    os.environ["MOIRA_B200_GZ_LEVEL"] = "1"      # the library's own compressor (verified piece by piece, zlib behind it)
+                else:
+                    os.environ.pop("MOIRA_B200_GZ_LEVEL", None)
                 t0 = time.perf_counter()
                 rc = cli.main(cli.parse_arguments(["-ffq", pth, "-op", os.path.join(tmp, "z_" + tag), "--devices", devs] + extra), _io.StringIO())
                 dt = time.perf_counter() - t0
@@ -291,9 +295,10 @@ def cli_bench(rec, accepted_per_read, world, rank, args):
                 comp[tag] = {"value": mm_ / dt, "unit": "reads/s", "reads": mm_, "seconds": dt, "rc": rc, "output_bytes": int(sum(files.values()))}
                 for f in files:
                     os.remove(os.path.join(tmp, f))
+            os.environ.pop("MOIRA_B200_GZ_LEVEL", None)
             os.remove(gzp); os.remove(plain_p)
             comp["note"] = ("default flags (exact ee, collapse, fasta + qual + names); bgzf_in: every 64 KB member inflated on its own thread; "
-                            "plain_gzip_in: one member, one inflate thread (the library's own DEFLATE decoder, CRC-checked, zlib behind it), %d reads; gz_out: outputs as BGZF members compressed on all host threads" % m_plain)
+                            "plain_gzip_in: one member, one inflate thread (the library's own DEFLATE decoder, CRC-checked, zlib behind it), %d reads; gz_out: outputs as BGZF members compressed on all host threads (zlib level 6, bgzip's default; level1: the library's own compressor, every piece inflated and compared before it is written)" % m_plain)
             out["compressed"] = comp
             # the paired flow (moira's main use): two FASTQ files -> contigs -> filter -> collapse -> files
             from tools.bench_contigs import make_pairs

@@ -27,6 +27,7 @@
 #include <thread>
 #include <vector>
 
+#include "moira_deflate.h"
 #include "moira_inflate.h"
 #include "moira_internal.h"
 
@@ -267,27 +268,53 @@ int inflate_stream(const uint8_t *gz, uint64_t n, uint8_t **out, uint64_t *out_b
 
 // compress `n` bytes into BGZF members appended to `out`; `z0` (level 0, set up on first use) takes the pieces that do not
 // shrink enough to fit a member
-bool deflate_range(z_stream &zs, z_stream &z0, bool &z0_ready, const uint8_t *in, uint64_t n, std::string &out)
+bool use_own_deflate()
+{
+    static const bool yes = [] { const char *e = getenv("MOIRA_B200_ZLIB_DEFLATE"); return !(e && e[0] == '1'); }();
+    return yes;
+}
+
+// `fast`: this library's own compressor (moira_deflate.h) first; every piece it makes is inflated again (moira_inflate.h)
+// and compared with the input before it is accepted -- a compressed output file is not the place for an unverified encoder.
+bool deflate_range(z_stream &zs, z_stream &z0, bool &z0_ready, const uint8_t *in, uint64_t n, std::string &out, bool fast)
 {
     uint8_t block[BGZF_MAX];
     constexpr uint32_t ROOM = BGZF_MAX - BGZF_HEAD - BGZF_TAIL;
+    static thread_local moira_deflate::Workspace ws;
+    static thread_local moira_inflate::State ist;
+    static thread_local uint8_t back[BGZF_MAX];
     for (uint64_t at = 0; at < n; at += BGZF_PIECE) {
         const uint32_t len = (uint32_t)std::min<uint64_t>(BGZF_PIECE, n - at);
-        if (deflateReset(&zs) != Z_OK) return false;
-        zs.next_in = const_cast<Bytef *>(in + at); zs.avail_in = len;
-        zs.next_out = block + BGZF_HEAD; zs.avail_out = ROOM;
-        uint32_t clen;
-        if (deflate(&zs, Z_FINISH) == Z_STREAM_END) clen = ROOM - zs.avail_out;
-        else {   // incompressible: stored
-            if (!z0_ready) {
-                memset(&z0, 0, sizeof(z0));
-                if (deflateInit2(&z0, 0, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
-                z0_ready = true;
-            } else if (deflateReset(&z0) != Z_OK) return false;
-            z0.next_in = const_cast<Bytef *>(in + at); z0.avail_in = len;
-            z0.next_out = block + BGZF_HEAD; z0.avail_out = ROOM;
-            if (deflate(&z0, Z_FINISH) != Z_STREAM_END) return false;
-            clen = ROOM - z0.avail_out;
+        uint32_t clen = 0;
+        bool done = false;
+        if (fast) {
+            const size_t c = moira_deflate::compress_piece(in + at, len, block + BGZF_HEAD, ROOM, ws);
+            if (c && c < (size_t)len + 16) {
+                moira_inflate::start(ist, block + BGZF_HEAD, block + BGZF_HEAD + c);
+                uint8_t *pos = nullptr;
+                if (moira_inflate::run(ist, back, back, back + len, &pos) == moira_inflate::DONE && pos == back + len &&
+                    memcmp(back, in + at, len) == 0 && moira_inflate::input_position(ist) == block + BGZF_HEAD + c) {
+                    clen = (uint32_t)c;
+                    done = true;
+                }
+            }
+        }
+        if (!done) {
+            if (deflateReset(&zs) != Z_OK) return false;
+            zs.next_in = const_cast<Bytef *>(in + at); zs.avail_in = len;
+            zs.next_out = block + BGZF_HEAD; zs.avail_out = ROOM;
+            if (deflate(&zs, Z_FINISH) == Z_STREAM_END) clen = ROOM - zs.avail_out;
+            else {   // incompressible: stored
+                if (!z0_ready) {
+                    memset(&z0, 0, sizeof(z0));
+                    if (deflateInit2(&z0, 0, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+                    z0_ready = true;
+                } else if (deflateReset(&z0) != Z_OK) return false;
+                z0.next_in = const_cast<Bytef *>(in + at); z0.avail_in = len;
+                z0.next_out = block + BGZF_HEAD; z0.avail_out = ROOM;
+                if (deflate(&z0, Z_FINISH) != Z_STREAM_END) return false;
+                clen = ROOM - z0.avail_out;
+            }
         }
         static const uint8_t head[BGZF_HEAD] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, 0, 0};
         memcpy(block, head, BGZF_HEAD);
@@ -309,6 +336,7 @@ int gz_deflate_segments_to_fd(const std::vector<std::pair<const uint8_t *, uint6
 {
     *written_out = 0;
     if (level < 0 || level > 9) level = 6;
+    const bool fast = level == 1 && use_own_deflate();     // level 1: the library's own compressor, zlib (level 1) behind it
     // tasks of at most 4 MB of input, never across a segment boundary (a member holds bytes of one segment only); the
     // threads share the tasks of ALL segments
     constexpr uint64_t RANGE = 64ull * BGZF_PIECE;
@@ -331,7 +359,7 @@ int gz_deflate_segments_to_fd(const std::vector<std::pair<const uint8_t *, uint6
             const uint64_t r = next.fetch_add(1);
             if (r >= n_ranges || bad) break;
             parts[r].reserve((size_t)(tasks[r].second / 3));
-            if (!deflate_range(zs, z0, z0_ready, tasks[r].first, tasks[r].second, parts[r])) { bad = 1; break; }
+            if (!deflate_range(zs, z0, z0_ready, tasks[r].first, tasks[r].second, parts[r], fast)) { bad = 1; break; }
         }
         deflateEnd(&zs);
         if (z0_ready) deflateEnd(&z0);

@@ -151,3 +151,29 @@ def test_own_decoder_against_zlib_on_many_streams_and_corruptions(tmp_path):
             assert exc.code == L.ERR_PARSE
             got = None
         assert got == want, (trial, kind)
+
+
+def test_own_compressor_level_1_is_read_by_every_inflater(tmp_path):
+    """Level 1 = the library's own DEFLATE compressor (moira_deflate.h; each piece inflated and compared before it is written):
+    Python's gzip and zlib, and the library's two readers, all get the input back -- text, runs, noise (stored members), tiny
+    pieces, piece-boundary sizes."""
+    rng = np.random.default_rng(9)
+    fastq = gzip.open(os.path.join(GOLDEN, "test1.fastq.gz"), "rb").read()
+    texts = [b"", b"x", b"abc", b"aaaa" * 5, fastq, fastq[:0xff00], fastq[:0xff00 + 1], bytes(300000), b"ab" * 100001,
+             rng.integers(0, 256, 150000, dtype=np.uint8).tobytes(), bytes(rng.integers(65, 69, 400000, dtype=np.uint8)),
+             fastq[:70000] + rng.integers(0, 256, 70000, dtype=np.uint8).tobytes() + fastq[:70000]]
+    for data in texts:
+        raw = _bgzf(data, tmp_path, level=1, threads=3, eof=True)
+        assert gzip.decompress(raw) == data
+        assert gz_inflate(raw).tobytes() == data and gz_inflate(raw, 1).tobytes() == data
+        # member by member through zlib's raw inflate (what htslib does)
+        at, got = 0, []
+        while at < len(raw):
+            size = int.from_bytes(raw[at + 16:at + 18], "little") + 1
+            got.append(zlib.decompress(raw[at + 18:at + size - 8], -15))
+            assert zlib.crc32(got[-1]) == int.from_bytes(raw[at + size - 8:at + size - 4], "little")
+            at += size
+        assert b"".join(got) == data
+    # it shrinks text at least as well as zlib's level 1
+    z1 = zlib.compressobj(1, zlib.DEFLATED, -15)
+    assert len(_bgzf(fastq, tmp_path, level=1, eof=False)) < 1.05 * len(z1.compress(fastq) + z1.flush())
