@@ -213,9 +213,12 @@ inline const uint8_t *input_position(const State &s) { return s.in - (s.bitcnt >
 inline void copy_match(uint8_t *out, uint32_t dist, uint32_t len, bool room16)
 {
     const uint8_t *src = out - dist;
-    if (room16 && dist >= 8) {
+    if (room16 && dist >= 16) {
         uint8_t *end = out + len;
-        do { memcpy(out, src, 8); out += 8; src += 8; } while (out < end);       // may write up to 7 bytes past the match: room16 guarantees the space
+        do { memcpy(out, src, 16); out += 16; src += 16; } while (out < end);    // may write up to 15 bytes past the match: room16 guarantees the space
+    } else if (room16 && dist >= 8) {
+        uint8_t *end = out + len;
+        do { memcpy(out, src, 8); out += 8; src += 8; } while (out < end);
     } else if (room16 && dist == 1) {
         memset(out, *src, len);
     } else {
